@@ -1,0 +1,135 @@
+"""Pins the CPU oracle against the known answers of SURVEY Appendix B (derived from the reference formulas,
+the reference ships no tests) and against scipy for the third-party mvtnorm::dmvt arithmetic."""
+import math
+
+import numpy as np
+import pytest
+
+from hydrobayes_b200 import _abi as A
+
+
+def test_floor_constant(oracle):
+    # R/internals.R:19,65 : log(.Machine$double.xmin)
+    assert oracle.log_xmin() == pytest.approx(-708.3964185322641, rel=0, abs=1e-12)
+
+
+def test_philox_known_answers(oracle):
+    # Random123 known-answer vectors for philox4x32-10
+    assert oracle.philox([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert oracle.philox([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert oracle.philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_mixture(oracle):
+    # R/test_mixture.R:16
+    exp = {-8: 0.06649038006690544, 0: 8.420452447111373e-16, 10: 0.33245190033452726, 1: 1.0279773571668917e-18}
+    for x, v in exp.items():
+        assert oracle.mixture(x) == pytest.approx(v, rel=1e-13)
+    logs = {-8: -2.7106980024327276, 0: -34.71069792628283, 10: -1.1012600899986273, 1: -41.418938533204674}
+    for x, v in logs.items():
+        ll, fx, rc = oracle.logdensity("mixture", 1, [[x]])
+        assert rc == 0 and ll[0] == pytest.approx(v, rel=1e-13)
+
+
+def test_mixture_floor(oracle):
+    ll, fx, rc = oracle.logdensity("mixture", 1, [[60.0], [-70.0]])
+    assert rc == 0
+    assert np.all(ll == oracle.log_xmin())  # density underflows to 0 -> log = -Inf -> floored
+
+
+def test_t_distribution_known(oracle):
+    # R/test_t_distribution.R:19-46 ; SURVEY Appendix B
+    assert oracle.tdist_logpdf(np.zeros((1, 1)))[0] == pytest.approx(-0.9231050070343514, rel=1e-13)
+    assert oracle.tdist_logpdf(np.zeros((1, 2)))[0] == pytest.approx(-2.040609620463428, rel=1e-13)
+    assert oracle.tdist_logpdf(np.zeros((1, 100)))[0] == pytest.approx(-213.43955272792834, rel=1e-13)
+    assert oracle.tdist_logpdf(np.ones((1, 1)))[0] == pytest.approx(-1.4272487165462735, rel=1e-13)
+    assert oracle.tdist_logpdf(np.ones((1, 2)))[0] == pytest.approx(-2.582068622322943, rel=1e-13)
+    assert oracle.tdist_logpdf(np.ones((1, 100)))[0] == pytest.approx(-218.01512992854524, rel=1e-13)
+    assert oracle.tdist_logpdf((np.arange(1, 3) / 2)[None])[0] == pytest.approx(-2.3125212751191637, rel=1e-13)
+    assert oracle.tdist_logpdf((np.arange(1, 101) / 100)[None])[0] == pytest.approx(-213.5956709533909, rel=1e-13)
+
+
+def test_t_distribution_vs_scipy(oracle):
+    from scipy.stats import multivariate_t
+    rng = np.random.default_rng(7)
+    for d in (1, 3, 10, 100):
+        i = np.arange(1, d + 1)
+        Cm = (0.5 * np.eye(d) + 0.5) * np.sqrt(np.outer(i, i))
+        x = rng.uniform(-5, 15, size=(16, d))
+        ref = multivariate_t(loc=np.zeros(d), shape=Cm, df=60).logpdf(x)
+        got = oracle.tdist_logpdf(x)
+        np.testing.assert_allclose(got, np.atleast_1d(ref), rtol=1e-12)
+
+
+def test_hydromodel(oracle):
+    # R/test_HydroModel.R:17-36
+    y = oracle.hydromodel([0, 1, 2, 0, 5], 0.5)
+    np.testing.assert_allclose(y, [1 / 3, 5 / 9, 1.037037037037037, 0.691358024691358, 2.1275720164609053], rtol=1e-15)
+    with pytest.raises(ValueError):
+        oracle.hydromodel([0, 1], -0.1)
+    with pytest.raises(ValueError):
+        oracle.hydromodel([0, -1], 0.1)
+
+
+def test_rstat_known(oracle):
+    # R/gelman_rubin.R:21-56 ; SURVEY Appendix B deterministic array
+    i = np.arange(1, 101)[:, None, None]
+    k = np.arange(1, 3)[None, :, None]
+    c = np.arange(1, 5)[None, None, :]
+    x = np.sin(0.37 * i * k + 1.3 * c) + 0.1 * c * k
+    r = oracle.rstat(x)
+    np.testing.assert_allclose(r, [1.0113185866169283, 1.0735661244327646], rtol=1e-12)
+
+
+def _rstat_numpy(x):
+    t, d, n = x.shape
+    y = x[math.ceil(t / 2) - 1:, :, :]
+    xm = 2 / (t - 2) * y.sum(axis=0)              # [d, n]
+    W = 2 / (n * (t - 2)) * ((y - xm[None]) ** 2).sum(axis=(0, 2))
+    B = 1 / (2 * (n - 1)) * ((xm - xm.mean(axis=1, keepdims=True)) ** 2).sum(axis=1)
+    sigma = (t - 2) / t * W + 2 * B
+    return np.sqrt((n + 1) / n * sigma / W - (t - 2) / (n * t))
+
+
+@pytest.mark.parametrize("t,d,n", [(51, 1, 3), (100, 2, 4), (201, 5, 16), (64, 100, 8)])
+def test_rstat_vs_numpy(oracle, t, d, n):
+    x = np.random.default_rng(t).normal(size=(t, d, n)).cumsum(axis=0)
+    np.testing.assert_allclose(oracle.rstat(x), _rstat_numpy(x), rtol=1e-11)
+
+
+def test_bound_par(oracle):
+    # R/internals.R:89-113
+    B, R, F = A.HB_BOUND_BOUND, A.HB_BOUND_REFLECT, A.HB_BOUND_FOLD
+    assert oracle.bound_par(0.5, 0, 1, B) == 0.5
+    assert oracle.bound_par(-0.2, 0, 1, B) == 0.0
+    assert oracle.bound_par(1.7, 0, 1, B) == 1.0
+    assert oracle.bound_par(-0.25, 0, 1, R) == 0.25
+    assert oracle.bound_par(1.25, 0, 1, R) == 0.75
+    assert oracle.bound_par(2.25, 0, 1, R) == pytest.approx(0.25)   # reflects twice
+    assert oracle.bound_par(-0.25, 0, 1, F) == 0.75
+    assert oracle.bound_par(1.25, 0, 1, F) == 0.25
+    assert oracle.bound_par(3.25, 0, 1, F) == pytest.approx(0.25)
+    assert oracle.bound_par(5.0, 0, 1, A.HB_BOUND_NONE) == 5.0
+
+
+def test_quantile_type7(oracle):
+    x = np.array([3.0, 1.0, 4.0, 1.5, 9.0, 2.6, 5.0])
+    for p in (0.25, 0.75, 0.5, 0.0, 1.0):
+        assert oracle.quantile7(x, p) == pytest.approx(np.quantile(x, p, method="linear"), rel=1e-15)
+    y = np.random.default_rng(3).normal(size=1024)
+    for p in (0.25, 0.75):
+        assert oracle.quantile7(y, p) == pytest.approx(np.quantile(y, p), rel=1e-14)
+
+
+def test_glue_likelihood(oracle):
+    # R/internals.R:13-14 : glue_shape*log(max(1 - sum((res-obs)^2)/sum((obs-mean(obs))^2), 0))
+    rng = np.random.default_rng(5)
+    P = rng.gamma(0.7, 8, size=200) * (rng.uniform(size=200) < 0.4)
+    obs = oracle.hydromodel(P, 0.4) + rng.normal(0, 0.05, size=200)
+    for K in (0.3, 0.4, 1.5):
+        sim = oracle.hydromodel(P, K)
+        nse = 1 - ((sim - obs) ** 2).sum() / ((obs - obs.mean()) ** 2).sum()
+        exp = max(50 * math.log(max(nse, 0)) if nse > 0 else -math.inf, oracle.log_xmin())
+        ll, fx, rc = oracle.logdensity("HydroModel", 31, [[K]], forcing=P, obs=obs, glue_shape=50.0)
+        assert rc == 0 and ll[0] == pytest.approx(exp, rel=1e-12)
