@@ -1,0 +1,9 @@
+"""hydrobayes_b200 -- B200-native DREAM sampler behind the HydroBayes API (dream / dream_parallel / R_stat).
+
+The package is a thin host layer over the C-ABI library libhydrobayes_b200.so (CUDA, sm_100a).  No CPU fallback.
+"""
+from ._abi import HbConfig, HbError, HbTape, default_config, lib, lib_path  # noqa: F401
+from .sampler import HydroModel, R_stat, Sampler, dream, dream_parallel, log_density, prior_sample  # noqa: F401
+
+__all__ = ["dream", "dream_parallel", "R_stat", "HydroModel", "log_density", "prior_sample", "Sampler", "HbConfig",
+           "HbTape", "HbError", "default_config", "lib", "lib_path"]

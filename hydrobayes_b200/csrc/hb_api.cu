@@ -1,0 +1,784 @@
+// hb_api.cu -- the C ABI (include/hydrobayes_b200.h): handle life cycle, the generation loop of the synchronous
+// sweep (R/dream_parallel.R:257-435 as K1 -> K2 plugin -> K3 -> finalize [-> exchange] [-> outlier check]),
+// result fetch in R's layouts, and the stand-alone entry points.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "hb_internal.h"
+
+int hb_seq_supported(const hb_config* cfg, std::string& why);   // hb_seq.cu
+int hb_seq_run(hb_handle* h, long long n_generations);          // hb_seq.cu
+void hb_seq_destroy(hb_handle* h);
+
+namespace {
+
+std::string g_create_err;
+
+int fail(hb_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  if (h) h->err = buf; else g_create_err = buf;
+  return code;
+}
+
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) return fail(h, HB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+template <typename T>
+cudaError_t dalloc(T** p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  return cudaMalloc((void**)p, n * sizeof(T));
+}
+
+void compute_dims(hb_handle* h) {
+  const hb_config& c = h->cfg;
+  if (c.burnin > 0 || c.thin > 1) h->out_t = (long long)((1 - c.burnin) * (double)c.t / c.thin + 1);   // :195-198
+  else h->out_t = c.t;
+  if (c.sweep == HB_SWEEP_SYNCHRONOUS) {
+    h->ar_rows = c.t / c.update_interval + 1; h->ar_cols = 2;                                         // :205
+    h->cr_rows = h->ar_rows; h->cr_cols = c.nCR + 1;                                                  // :204
+  } else {
+    h->ar_rows = h->out_t; h->ar_cols = c.nCR; h->cr_rows = h->out_t; h->cr_cols = c.nCR;             // R/dream.R:162
+  }
+  h->H = (long long)floor(c.adapt * (double)c.t) + 1;
+  h->rstat_rows = (c.check_convergence && h->out_t > 50) ? h->out_t - 50 : 0;
+}
+
+// host-side Philox for the outlier replacement draws (slot map in hb_common.cuh)
+void sample_replacements(const hb_handle* h, long long gen, const std::vector<long long>& outl,
+                         std::vector<long long>& news) {
+  const long long nc = h->nc;
+  news.resize(outl.size());
+  std::vector<long long> cand; cand.reserve((size_t)nc);
+  size_t o = 0;
+  for (long long j = 0; j < nc; ++j) { if (o < outl.size() && outl[o] == j) { ++o; continue; } cand.push_back(j); }
+  long long n_rem = (long long)cand.size();
+  const hb_phx ph(h->cfg.seed, ((uint64_t)0xFFFFFFFFu << 32) | 0u, (uint32_t)gen);
+  uint4 w = make_uint4(0, 0, 0, 0);
+  for (size_t q = 0; q < outl.size(); ++q) {
+    if ((q & 1) == 0) w = ph.slot((uint32_t)(q >> 1));
+    const unsigned __int128 prod = (unsigned __int128)hb_pair64(w, (int)(q & 1)) * (unsigned __int128)(uint64_t)n_rem;
+    const long long r = (long long)(uint64_t)(prod >> 64);
+    news[q] = cand[(size_t)r];
+    cand[(size_t)r] = cand[(size_t)--n_rem];
+  }
+}
+
+// stats::quantile type 7 on a sorted copy (recollection): (1-h)*x[lo] + h*x[hi]
+double quantile7_sorted(const std::vector<double>& s, double p) {
+  const long long n = (long long)s.size();
+  const double index = 1 + (double)(n > 1 ? n - 1 : 0) * p;
+  const double lo = floor(index), hi = ceil(index);
+  double qs = s[(size_t)lo - 1];
+  const double xh = s[(size_t)hi - 1];
+  if (index > lo && xh != qs) { const double hh = index - lo; qs = (1 - hh) * qs + hh * xh; }
+  return qs;
+}
+
+struct prof_scope {
+  hb_handle* h; const char* name; cudaEvent_t a = nullptr, b = nullptr;
+  prof_scope(hb_handle* h_, const char* n) : h(h_), name(n) {
+    if (h->profile) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, h->stream); }
+  }
+  void done(int launches = 1) {
+    h->launches += launches;
+    if (h->profile) {
+      cudaEventRecord(b, h->stream); cudaEventSynchronize(b);
+      float ms = 0; cudaEventElapsedTime(&ms, a, b);
+      auto& k = h->kstats[name]; k.ms += ms; k.launches += launches;
+      cudaEventDestroy(a); cudaEventDestroy(b);
+    }
+  }
+};
+
+int check_flags(hb_handle* h) {
+  hb_ctrl c;
+  CK(cudaMemcpyAsync(&c, h->ctrl, sizeof c, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  unsigned e = c.err;
+  if (h->target_is_hydro) e |= hb_hydro_poll_err(h->tctx);
+  if (!e) return HB_OK;
+  if (e & HB_FLAG_BAD_TAPE) return fail(h, HB_ERR_INVALID, "invalid tape record (D, partner or id out of range)");
+  if (e & HB_FLAG_PROP_NONFINITE) return fail(h, HB_ERR_NONFINITE, "Calculated proposal is not finite!");
+  if (e & HB_FLAG_LP_NONFINITE) return fail(h, HB_ERR_NONFINITE, "Calculated log-prior is not finite");
+  if (e & HB_FLAG_LL_NONFINITE) return fail(h, HB_ERR_NONFINITE, "Calculated log-likelihood is not finite!");
+  if (e & HB_FLAG_TARGET_DOMAIN) return fail(h, HB_ERR_INVALID, "Argument 'param' has to be >= zero!");
+  if (e & HB_FLAG_J_NAN) return fail(h, HB_ERR_NONFINITE, "missing value where TRUE/FALSE needed (J is NaN: zero std_x)");
+  return fail(h, HB_ERR_INVALID, "device error flags 0x%x", e);
+}
+
+int allocate(hb_handle* h) {
+  const hb_config& c = h->cfg;
+  const long long nl = h->n_local, nc = h->nc;
+  const int d = h->d, ldx = h->ldx;
+  CK(dalloc(&h->X, (size_t)nc * ldx));
+  CK(cudaMemsetAsync(h->X, 0, (size_t)nc * ldx * sizeof(double), h->stream));
+  if (c.past_sample) { CK(dalloc(&h->Z, (size_t)h->m_cap * ldx)); }
+  CK(dalloc(&h->XP, (size_t)nl * ldx));
+  CK(cudaMemsetAsync(h->XP, 0, (size_t)nl * ldx * sizeof(double), h->stream));
+  CK(dalloc(&h->id, (size_t)nl));
+  CK(dalloc(&h->lp_xp, (size_t)nl)); CK(dalloc(&h->ll_raw, (size_t)nl)); CK(dalloc(&h->fx_xp, (size_t)nl));
+  CK(dalloc(&h->lp, (size_t)nl)); CK(dalloc(&h->ll, (size_t)nl)); CK(dalloc(&h->lpost, (size_t)nl));
+  CK(dalloc(&h->fx, (size_t)nl));
+  CK(dalloc(&h->lpost_hist, (size_t)h->H * nl));
+  CK(dalloc(&h->hist_x, (size_t)h->out_t * nl * d));
+  CK(dalloc(&h->hist_l, (size_t)h->out_t * nl * 3));
+  if (c.store_fx) CK(dalloc(&h->hist_fx, (size_t)h->out_t * nl));
+  if (c.record_accept) { CK(dalloc(&h->accept_rec, (size_t)(h->t - 1) * nl)); CK(cudaMemsetAsync(h->accept_rec, 0, (size_t)(h->t - 1) * nl, h->stream)); }
+  CK(dalloc(&h->ctrl, 1));
+  CK(dalloc(&h->shift, (size_t)d)); CK(dalloc(&h->colsum, (size_t)2 * d)); CK(dalloc(&h->qsum, (size_t)c.nCR * d));
+  size_t smem = 0;
+  h->k3_blocks = hb_k3_grid(nl, d, c.nCR, h->sm_count, &smem);
+  if (h->k3_blocks < 1) return fail(h, HB_ERR_UNSUPPORTED, "d = %d with nCR = %d exceeds the shared-memory budget of K3", d, c.nCR);
+  CK(dalloc(&h->partials, (size_t)h->k3_blocks * (c.nCR + 2) * d));
+  CK(dalloc(&h->out_ar, (size_t)h->ar_rows * h->ar_cols)); CK(dalloc(&h->out_cr, (size_t)h->cr_rows * h->cr_cols));
+  CK(hb_launch_fill(h->out_ar, h->ar_rows * h->ar_cols, NAN, h->stream));
+  CK(hb_launch_fill(h->out_cr, h->cr_rows * h->cr_cols, NAN, h->stream));
+  CK(dalloc(&h->proxy, (size_t)nl)); CK(dalloc(&h->proxy_full, (size_t)nc)); CK(dalloc(&h->lpost_full, (size_t)nc));
+  CK(dalloc(&h->outl_dev, (size_t)nc)); CK(dalloc(&h->news_dev, (size_t)nc));
+  if (h->rstat_rows > 0) { CK(dalloc(&h->rstat_dev, (size_t)h->rstat_rows * d)); CK(hb_launch_fill(h->rstat_dev, h->rstat_rows * d, NAN, h->stream)); }
+  CK(dalloc(&h->rstat_xm, (size_t)nl * d)); CK(dalloc(&h->rstat_ss, (size_t)nl * d));
+  // control block: pCR = 1/nCR (R/dream_parallel.R:192), counters zero, i_ar = 1 (:250)
+  hb_ctrl hc; memset(&hc, 0, sizeof hc);
+  for (int q = 0; q < c.nCR; ++q) hc.pCR[q] = 1.0 / c.nCR;
+  hc.i_ar = 1; hc.cum_eval = (double)nc;
+  CK(cudaMemcpyAsync(h->ctrl, &hc, sizeof hc, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return HB_OK;
+}
+
+// initial population: prior, target, lpost[1,], output row 1   (R/dream_parallel.R:211-250)
+int initialise(hb_handle* h) {
+  const hb_config& c = h->cfg;
+  const long long nl = h->n_local;
+  const int d = h->d, ldx = h->ldx;
+  const double* Xl = h->X + h->chain0 * ldx;
+  unsigned* errp = &h->ctrl->err;
+  CK(hb_launch_prior(Xl, ldx, d, nl, c.prior, h->pmin, h->pmax, h->lp_xp, errp, h->stream)); h->launches++;
+  if (int rc = h->vt->launch(h->tctx, Xl, nl, d, ldx, h->ll_raw, h->fx_xp, h->stream)) return fail(h, rc, "target launch failed");
+  h->launches++;
+  CK(hb_launch_init_state(h->lp_xp, h->ll_raw, h->fx_xp, h->lp, h->ll, h->lpost, h->fx, h->lpost_hist, nl, errp, h->stream));
+  CK(hb_launch_store_row(Xl, ldx, d, nl, h->lp, h->ll, h->lpost, h->fx, h->hist_x, h->hist_l, h->hist_fx, h->stream));
+  h->launches += 2;
+  // shift for the one-pass column variance: chain 0 of the run
+  CK(cudaMemcpyAsync(h->shift, h->X, sizeof(double) * d, cudaMemcpyDeviceToDevice, h->stream));
+  // AR/CR row 1: out_AR[1,1] = out_CR[1,1] = nc ; out_AR[1,2] = NA ; out_CR[1,-1] = pCR   (:245-247)
+  std::vector<double> ar((size_t)h->ar_rows * h->ar_cols, NAN), cr((size_t)h->cr_rows * h->cr_cols, NAN);
+  ar[0] = (double)h->nc; cr[0] = (double)h->nc;
+  for (int q = 0; q < c.nCR; ++q) cr[(size_t)h->cr_rows * (q + 1)] = 1.0 / c.nCR;
+  CK(cudaMemcpyAsync(h->out_ar, ar.data(), ar.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->out_cr, cr.data(), cr.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->gen = 1; h->ind_out = 1; h->initialised = true;
+  return check_flags(h);
+}
+
+// check_outlier (R/internals.R:71-87) at generation i: proxies and copies on the device, order statistics and the
+// without-replacement draw on the host (runs at most adapt*t/updateInterval times per run)
+int outlier_check(hb_handle* h, long long i) {
+  const long long nc = h->nc, nl = h->n_local;
+  const long long r0 = (i + 1) / 2;   // ceiling(i/2), 1-based
+  {
+    prof_scope ps(h, "OUTLIER");
+    CK(hb_launch_proxy(h->lpost_hist, nl, r0 - 1, i - 1, nl, h->proxy, h->stream));
+    ps.done();
+  }
+  std::vector<double> proxy((size_t)nc);
+  if (h->world > 1) {
+    if (int rc = hb_nccl_allgather_f64(h->comm, h->proxy, h->proxy_full, (size_t)nl, h->stream, h->err)) return rc;
+    if (int rc = hb_nccl_allgather_f64(h->comm, h->lpost, h->lpost_full, (size_t)nl, h->stream, h->err)) return rc;
+    CK(cudaMemcpyAsync(proxy.data(), h->proxy_full, sizeof(double) * nc, cudaMemcpyDeviceToHost, h->stream));
+  } else {
+    CK(cudaMemcpyAsync(proxy.data(), h->proxy, sizeof(double) * nc, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  std::vector<double> s(proxy);
+  std::sort(s.begin(), s.end());
+  const double q1 = quantile7_sorted(s, 0.25), q3 = quantile7_sorted(s, 0.75);   // :75
+  const double iqr = fabs(q3 - q1);                                               // :76
+  std::vector<long long> outl;
+  for (long long j = 0; j < nc; ++j) if (proxy[(size_t)j] < q1 - 2 * iqr) outl.push_back(j);   // :78
+  if (outl.empty()) return HB_OK;
+  std::vector<long long> news;
+  if (h->cfg.rng_mode == HB_RNG_TAPE) {
+    const long long e = i / h->cfg.update_interval - 1;
+    if (e < 0 || e >= h->tape_events) return fail(h, HB_ERR_INVALID, "tape has no outlier event %lld", e);
+    news.resize(outl.size());
+    for (size_t q = 0; q < outl.size(); ++q) {
+      news[q] = h->tape_outlier_new[(size_t)e * h->nct + q];
+      if (news[q] < 0 || news[q] >= nc) return fail(h, HB_ERR_INVALID, "tape outlier replacement out of range");
+    }
+  } else {
+    sample_replacements(h, i, outl, news);                                        // :81
+  }
+  std::vector<int> o32(outl.begin(), outl.end()), n32(news.begin(), news.end());
+  CK(cudaMemcpyAsync(h->outl_dev, o32.data(), sizeof(int) * o32.size(), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->news_dev, n32.data(), sizeof(int) * n32.size(), cudaMemcpyHostToDevice, h->stream));
+  if (h->world > 1) return fail(h, HB_ERR_UNSUPPORTED, "outlier reset on a sharded population is not wired yet");
+  double* hrow = (i <= h->H) ? h->lpost_hist + (i - 1) * nl : nullptr;
+  {
+    prof_scope ps(h, "OUTLIER");
+    CK(hb_launch_outlier_reset(h->X, h->ldx, h->d, h->lpost, hrow, h->outl_dev, h->news_dev, (int)o32.size(), nullptr, h->stream));
+    ps.done();
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  for (long long j : outl) { h->outlier_gen.push_back(i); h->outlier_chain.push_back(j); }   // outl[[i]]  R/dream_parallel.R:418
+  return HB_OK;
+}
+
+int run_generation(hb_handle* h, long long i) {
+  const hb_config& c = h->cfg;
+  const long long nl = h->n_local;
+  const int d = h->d, ldx = h->ldx;
+  const bool store = ((double)i > c.burnin * (double)h->t) && (i % c.thin == 0);       // :263, :386
+  if (store) {
+    h->ind_out++;
+    if (h->ind_out > h->out_t) return fail(h, HB_ERR_INVALID, "subscript out of bounds (non-integer out_t, R/dream_parallel.R:195)");
+  }
+  const bool in_adapt = ((double)i <= c.adapt * (double)h->t);                         // :403
+  const bool upd = (i % c.update_interval == 0);
+  const bool tape_mode = (c.rng_mode == HB_RNG_TAPE);
+
+  {  // K1
+    hb_k1_params p{};
+    p.X = h->X; p.Z = h->Z; p.m_arch = h->m_arch; p.XP = h->XP; p.id_out = h->id; p.lp_xp = h->lp_xp;
+    p.ctrl = h->ctrl; p.err = &h->ctrl->err; p.nc = h->nc; p.chain0 = h->chain0; p.n_local = nl; p.gchain0 = 0;
+    p.d = d; p.ldx = ldx; p.delta = c.delta; p.nCR = c.nCR; p.c_val = c.c_val; p.c_star = c.c_star; p.p_g = c.p_g;
+    p.beta0 = c.beta0; p.psnooker = c.psnooker; p.past_sample = c.past_sample;
+    p.bound = h->have_min_max ? c.bound : 0; p.prior = c.prior; p.pmin = h->pmin; p.pmax = h->pmax;
+    p.seed = c.seed; p.gen = (uint32_t)i; p.tape = h->tape; p.tape_g = i - 2;
+    prof_scope ps(h, "K1");
+    CK(hb_launch_k1(p, tape_mode, h->sm_count, h->stream));
+    ps.done();
+  }
+  {  // K2: the target plugin
+    prof_scope ps(h, "K2");
+    if (int rc = h->vt->launch(h->tctx, h->XP, nl, d, ldx, h->ll_raw, h->fx_xp, h->stream)) return fail(h, rc, "target launch failed");
+    ps.done();
+  }
+  {  // K3
+    hb_k3_params p{};
+    p.X = h->X; p.XP = h->XP; p.id = h->id; p.lp_xp = h->lp_xp; p.ll_raw = h->ll_raw;
+    p.fx_xp = c.store_fx ? h->fx_xp : nullptr;
+    p.lp = h->lp; p.ll = h->ll; p.lpost = h->lpost; p.fx = c.store_fx ? h->fx : nullptr;
+    p.lpost_hist_row = (i <= h->H) ? h->lpost_hist + (i - 1) * nl : nullptr;
+    if (store) {
+      p.hist_x = h->hist_x + (size_t)(h->ind_out - 1) * nl * d;
+      p.hist_l = h->hist_l + (size_t)(h->ind_out - 1) * nl * 3;
+      p.hist_fx = h->hist_fx ? h->hist_fx + (size_t)(h->ind_out - 1) * nl : nullptr;
+    }
+    p.accept_rec = h->accept_rec ? h->accept_rec + (size_t)(i - 2) * nl : nullptr;
+    p.ctrl = h->ctrl; p.shift = h->shift; p.partials = h->partials;
+    p.chain0 = h->chain0; p.n_local = nl; p.gchain0 = 0; p.d = d; p.ldx = ldx; p.nCR = c.nCR;
+    p.adapt = in_adapt; p.seed = c.seed; p.gen = (uint32_t)i;
+    p.u_accept = tape_mode ? h->tape.u_accept + (size_t)(i - 2) * h->tape.nct : nullptr;
+    prof_scope ps(h, "K3");
+    int nb = 0;
+    CK(hb_launch_k3(p, h->sm_count, &nb, nullptr, h->stream));
+    ps.done();
+  }
+  h->pending_evals += h->nc;
+  if (in_adapt || upd) {  // finalize: J / n_id / n_acc, pCR adaptation, AR/CR rows
+    hb_fin_params f{};
+    f.ctrl = h->ctrl; f.partials = h->partials; f.nblocks = h->k3_blocks; f.shift = h->shift; f.colsum = h->colsum;
+    f.qsum = h->qsum; f.nc = h->nc; f.d = d; f.nCR = c.nCR; f.adapt = in_adapt; f.do_pcr = in_adapt && upd;
+    f.do_arcr = upd; f.out_ar = h->out_ar; f.out_cr = h->out_cr; f.ar_rows = h->ar_rows;
+    f.n_eval_inc = h->pending_evals;
+    prof_scope ps(h, "FIN");
+    if (h->world > 1) {
+      f.phase = 0; CK(hb_launch_finalize(f, h->stream));
+      if (in_adapt) {
+        if (int rc = hb_nccl_allreduce_f64(h->comm, h->colsum, (size_t)2 * d, h->stream, h->err)) return rc;
+        if (int rc = hb_nccl_allreduce_f64(h->comm, h->qsum, (size_t)c.nCR * d, h->stream, h->err)) return rc;
+      }
+      if (int rc = hb_nccl_allreduce_u64(h->comm, h->ctrl->n_id_gen, HB_MAX_NCR + 1, h->stream, h->err)) return rc;
+      f.phase = 1; CK(hb_launch_finalize(f, h->stream));
+      ps.done(2);
+    } else {
+      f.phase = 2; CK(hb_launch_finalize(f, h->stream));
+      ps.done();
+    }
+    h->pending_evals = 0;
+  }
+  if (h->world > 1) {  // chain-state exchange: every rank needs every row for the next generation's partner draws
+    prof_scope ps(h, "XCHG");
+    if (int rc = hb_nccl_allgather_f64(h->comm, h->X + h->chain0 * ldx, h->X, (size_t)nl * ldx, h->stream, h->err)) return rc;
+    ps.done();
+  }
+  if (c.past_sample && h->archive_update > 0 && (i % h->archive_update == 0)) {     // :382-383  z <- rbind(z, xt)
+    if (h->m_arch + h->nc > h->m_cap) return fail(h, HB_ERR_STATE, "archive capacity exceeded");
+    CK(cudaMemcpyAsync(h->Z + (size_t)h->m_arch * ldx, h->X, sizeof(double) * (size_t)h->nc * ldx, cudaMemcpyDeviceToDevice, h->stream));
+    h->m_arch += h->nc;
+  }
+  if (c.check_convergence && store && h->ind_out > 50) {   // R_stat(chain[1:ind_out, 1:d, ]) as R/dream_test.R:344
+    prof_scope ps(h, "K4");
+    CK(hb_launch_rstat(h->hist_x, h->ind_out, nl, 0, nl, d, h->rstat_xm, h->rstat_ss, h->rstat_dev + (size_t)(h->ind_out - 51) * d, h->stream));
+    ps.done(2);
+  }
+  if (in_adapt && upd && !c.past_sample && c.outlier_check) {                        // :414-419
+    if (int rc = outlier_check(h, i)) return rc;
+  }
+  h->gen = i;
+  return HB_OK;
+}
+
+int upload_tape(hb_handle* h, const hb_tape* tp) {
+  const long long n_gen = tp->n_gen, nct = tp->nct;
+  const int d = tp->d, delta = tp->delta;
+  auto up = [&](const void* src, size_t bytes, const void** dst) -> int {
+    *dst = nullptr;
+    if (!src) return HB_OK;
+    void* p = nullptr;
+    CK(cudaMalloc(&p, bytes ? bytes : 1));
+    h->tape_allocs.push_back(p);
+    CK(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice));
+    *dst = p;
+    return HB_OK;
+  };
+  const size_t n = (size_t)n_gen * nct;
+  int rc = HB_OK;
+  if ((rc = up(tp->u_snooker, n * 8, (const void**)&h->tape.u_snooker))) return rc;
+  if ((rc = up(tp->D, n, (const void**)&h->tape.D))) return rc;
+  if ((rc = up(tp->partners, n * 2 * delta * 4, (const void**)&h->tape.partners))) return rc;
+  if ((rc = up(tp->id, n, (const void**)&h->tape.id))) return rc;
+  if ((rc = up(tp->zt, n * d * 8, (const void**)&h->tape.zt))) return rc;
+  if ((rc = up(tp->lambda, n * d * 8, (const void**)&h->tape.lambda))) return rc;
+  if ((rc = up(tp->g_is_one, n, (const void**)&h->tape.g_is_one))) return rc;
+  if ((rc = up(tp->zeta, n * d * 8, (const void**)&h->tape.zeta))) return rc;
+  if ((rc = up(tp->g_snooker, n * 8, (const void**)&h->tape.g_snooker))) return rc;
+  if ((rc = up(tp->u_accept, n * 8, (const void**)&h->tape.u_accept))) return rc;
+  h->tape.nct = nct;
+  h->tape_n_gen = n_gen;
+  h->tape_events = tp->n_events;
+  if (tp->outlier_new && tp->n_events > 0) h->tape_outlier_new.assign(tp->outlier_new, tp->outlier_new + (size_t)tp->n_events * nct);
+  h->have_tape = true;
+  return HB_OK;
+}
+
+}  // namespace
+
+// =========================================== C ABI ========================================================
+extern "C" {
+
+void hb_config_default(hb_config* c) {
+  memset(c, 0, sizeof *c);
+  c->abi_version = HB_ABI_VERSION; c->sweep = HB_SWEEP_SYNCHRONOUS; c->n_runs = 1;
+  c->burnin = 0; c->adapt = 0.1; c->update_interval = 10; c->delta = 3; c->c_val = 0.1; c->c_star = 1e-12; c->nCR = 3;
+  c->thin = 1; c->p_g = 0.2; c->beta0 = 1; c->outlier_check = 1; c->prior = HB_PRIOR_FLAT; c->bound = HB_BOUND_NONE;
+  c->mt = 1; c->rng_mode = HB_RNG_PHILOX; c->seed = 1312;
+}
+
+int hb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char* hb_last_error(const hb_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int hb_create(const hb_config* cfg, int device, hb_handle** out) {
+  hb_handle* h = nullptr;
+  if (!cfg || !out) return fail(h, HB_ERR_INVALID, "hb_create: null argument");
+  *out = nullptr;
+  if (cfg->abi_version != HB_ABI_VERSION) return fail(h, HB_ERR_INVALID, "hb_config.abi_version %d != %d", cfg->abi_version, HB_ABI_VERSION);
+  // argument checks, R/dream.R:136-137 and R/dream_parallel.R:166-175
+  if (cfg->nc < 1 || cfg->t < 2 || cfg->d < 1) return fail(h, HB_ERR_INVALID, "nc, t, d must be positive (t >= 2)");
+  if (!cfg->past_sample && cfg->nc <= 2 * (long long)cfg->delta) return fail(h, HB_ERR_INVALID, "Argument 'nc' must be > 'delta' * 2!");
+  if (cfg->delta < 1 || cfg->delta > HB_MAX_DELTA) return fail(h, HB_ERR_UNSUPPORTED, "delta must be in 1..%d on the device", HB_MAX_DELTA);
+  if (cfg->nCR < 1 || cfg->nCR > HB_MAX_NCR) return fail(h, HB_ERR_UNSUPPORTED, "nCR must be in 1..%d on the device", HB_MAX_NCR);
+  if (cfg->mt > 1) return fail(h, HB_ERR_UNSUPPORTED, "mt > 1 (MT-DREAM) is not on the device path");
+  if ((cfg->mt > 1 || cfg->psnooker > 0) && (cfg->lik == 21 || cfg->lik == 22))
+    return fail(h, HB_ERR_INVALID, "ABC method cannot be combined with MT-DREAM or snooker updating, see Sadegh and Vrugt (2014), WRR!");
+  if (cfg->lik != 1 && cfg->lik != 2 && cfg->lik != 31) {
+    if (cfg->lik == 21 || cfg->lik == 22 || cfg->lik == 99) return fail(h, HB_ERR_UNSUPPORTED, "lik = %d needs an R closure (abc_rho / lik_fun) and stays off the device path", cfg->lik);
+    return fail(h, HB_ERR_INVALID, "Argument 'lik' has to be one of {1,2,21,22}!");
+  }
+  if (cfg->thin < 1 || cfg->update_interval < 1) return fail(h, HB_ERR_INVALID, "thin and updateInterval must be >= 1");
+  if (cfg->psnooker > 0 && !cfg->past_sample) return fail(h, HB_ERR_INVALID, "psnooker > 0 can only be applied if past_sample == TRUE");
+  if (cfg->prior == HB_PRIOR_NORMAL) return fail(h, HB_ERR_UNSUPPORTED, "prior = 'normal' is not on the device path yet");
+  if (cfg->d > 1024) return fail(h, HB_ERR_UNSUPPORTED, "d > 1024 is not supported on the device");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); return fail(h, HB_ERR_NO_DEVICE, "no CUDA device is available and there is no CPU fallback"); }
+  if (device < 0 || device >= ndev) return fail(h, HB_ERR_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+  h = new hb_handle();
+  h->cfg = *cfg;
+  if (h->cfg.n_runs < 1) h->cfg.n_runs = 1;
+  h->device = device;
+  h->nc = cfg->nc; h->t = cfg->t; h->d = cfg->d; h->nct = h->cfg.n_runs * cfg->nc;
+  h->ldx = cfg->d == 1 ? 1 : (cfg->d + 3) & ~3;
+  h->m0 = cfg->m0 > 0 ? cfg->m0 : (cfg->past_sample ? 10LL * cfg->d : cfg->nc);          // :168-171
+  h->archive_update = cfg->archive_update > 0 ? cfg->archive_update : (cfg->past_sample ? 10 : 0);   // :172-173
+  if (h->m0 < h->nc) { std::string e = "m0 must be >= nc"; delete h; g_create_err = e; return HB_ERR_INVALID; }
+  h->m_arch = h->m0;
+  h->m_cap = h->m0 + (h->archive_update ? h->nc * (h->t / h->archive_update + 1) : 0);
+  h->n_local = h->nc; h->chain0 = 0;
+  compute_dims(h);
+  if (cfg->sweep == HB_SWEEP_SEQUENTIAL || h->cfg.n_runs > 1) {
+    std::string why;
+    if (hb_seq_supported(&h->cfg, why) != HB_OK) { g_create_err = why; delete h; return HB_ERR_UNSUPPORTED; }
+  }
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+  if (e != cudaSuccess) { g_create_err = std::string("CUDA initialisation failed: ") + cudaGetErrorString(e); delete h; return HB_ERR_CUDA; }
+  *out = h;
+  return HB_OK;
+}
+
+void hb_destroy(hb_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  hb_seq_destroy(h);
+  if (h->vt && h->tctx) h->vt->destroy(h->tctx);
+  hb_nccl_destroy(h->comm);
+  void* ptrs[] = {h->X, h->Z, h->XP, h->id, h->lp_xp, h->ll_raw, h->fx_xp, h->lp, h->ll, h->lpost, h->fx, h->lpost_hist,
+                  h->hist_x, h->hist_l, h->hist_fx, h->accept_rec, h->ctrl, h->shift, h->colsum, h->qsum, h->partials,
+                  h->out_ar, h->out_cr, h->proxy, h->proxy_full, h->lpost_full, h->outl_dev, h->news_dev, h->rstat_dev,
+                  h->rstat_xm, h->rstat_ss, h->stage, h->pmin, h->pmax};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  for (void* p : h->tape_allocs) cudaFree(p);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int hb_set_bounds(hb_handle* h, const double* par_min, const double* par_max, int n) {
+  if (!h) return HB_ERR_INVALID;
+  if (!par_min || !par_max) return fail(h, HB_ERR_INVALID, "hb_set_bounds: min and max must both be given (R/internals.R:210)");
+  if (n != 1 && n != h->d) return fail(h, HB_ERR_INVALID, "hb_set_bounds: n must be 1 or d");
+  cudaSetDevice(h->device);
+  h->pmin_h.resize((size_t)h->d); h->pmax_h.resize((size_t)h->d);
+  for (int k = 0; k < h->d; ++k) { h->pmin_h[k] = par_min[n > 1 ? k : 0]; h->pmax_h[k] = par_max[n > 1 ? k : 0]; }   // :211-212
+  if (!h->pmin) { CK(dalloc(&h->pmin, (size_t)h->d)); CK(dalloc(&h->pmax, (size_t)h->d)); }
+  CK(cudaMemcpy(h->pmin, h->pmin_h.data(), sizeof(double) * h->d, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->pmax, h->pmax_h.data(), sizeof(double) * h->d, cudaMemcpyHostToDevice));
+  h->have_min_max = true;
+  return HB_OK;
+}
+
+int hb_set_prior_normal(hb_handle* h, const double*, const double*) {
+  return fail(h, HB_ERR_UNSUPPORTED, "prior = 'normal' is not on the device path yet");
+}
+
+int hb_set_obs(hb_handle* h, const double* obs, int64_t n) {
+  if (!h || !obs || n < 1) return fail(h, HB_ERR_INVALID, "hb_set_obs: bad arguments");
+  h->obs_h.assign(obs, obs + n);
+  return HB_OK;
+}
+
+int hb_set_target(hb_handle* h, const char* name, const double* data, const int64_t* dims, int ndims) {
+  if (!h || !name) return HB_ERR_INVALID;
+  cudaSetDevice(h->device);
+  const hb_target_vtable* vt = hb_find_target(name);
+  if (!vt) return fail(h, HB_ERR_UNKNOWN_TARGET, "object '%s' of mode 'function' was not found in the device plugin registry (arbitrary R closures stay off the GPU path)", name);
+  if (h->vt && h->tctx) { h->vt->destroy(h->tctx); h->tctx = nullptr; }
+  char err[256] = {0};
+  void* ctx = nullptr;
+  const int rc = vt->init(&ctx, h->d, h->cfg.lik, data, dims, ndims, h->obs_h.empty() ? nullptr : h->obs_h.data(),
+                          (int64_t)h->obs_h.size(), h->cfg.glue_shape, err, (int)sizeof err);
+  if (rc != HB_OK) return fail(h, rc, "%s", err[0] ? err : "target init failed");
+  h->vt = vt; h->tctx = ctx; h->target_name = name; h->target_is_hydro = (h->target_name == "HydroModel");
+  return HB_OK;
+}
+
+int hb_set_target_batched(hb_handle* h, const char*, const double*, int64_t, const double*, int64_t) {
+  return fail(h, HB_ERR_UNSUPPORTED, "batched independent runs are not wired yet");
+}
+
+int hb_comm_unique_id(void* id128) {
+  std::string err;
+  const int rc = hb_nccl_unique_id(id128, err);
+  if (rc) g_create_err = err;
+  return rc;
+}
+
+int hb_comm_init(hb_handle* h, int rank, int world, const void* id128) {
+  if (!h) return HB_ERR_INVALID;
+  if (h->have_initial) return fail(h, HB_ERR_STATE, "hb_comm_init must precede hb_set_initial");
+  if (world < 1 || rank < 0 || rank >= world) return fail(h, HB_ERR_INVALID, "bad rank/world");
+  if (h->nc % world) return fail(h, HB_ERR_INVALID, "nc must be divisible by the number of GPUs");
+  if (h->cfg.sweep != HB_SWEEP_SYNCHRONOUS || h->cfg.n_runs > 1) return fail(h, HB_ERR_UNSUPPORTED, "only the synchronous single-population sweep shards across GPUs");
+  cudaSetDevice(h->device);
+  if (world > 1) { if (int rc = hb_nccl_init(&h->comm, rank, world, id128, h->err)) return rc; }
+  h->rank = rank; h->world = world;
+  h->n_local = h->nc / world; h->chain0 = rank * h->n_local;
+  return HB_OK;
+}
+
+int hb_set_initial(hb_handle* h, const double* x0) {
+  if (!h || !x0) return HB_ERR_INVALID;
+  if (h->have_initial) return fail(h, HB_ERR_STATE, "hb_set_initial was already called");
+  cudaSetDevice(h->device);
+  if (h->cfg.sweep == HB_SWEEP_SEQUENTIAL || h->cfg.n_runs > 1) return fail(h, HB_ERR_UNSUPPORTED, "sequential sweep / batched runs are not wired yet");
+  if (int rc = allocate(h)) return rc;
+  const long long m0 = h->m0, nc = h->nc;
+  const int d = h->d, ldx = h->ldx;
+  double* tmp = nullptr;
+  CK(dalloc(&tmp, (size_t)m0 * d));
+  CK(cudaMemcpyAsync(tmp, x0, sizeof(double) * (size_t)m0 * d, cudaMemcpyHostToDevice, h->stream));
+  // xt <- z[(m0-nc+1):m0, ]  (R/dream_parallel.R:213)
+  CK(hb_launch_colmajor_to_rows(tmp, m0, m0 - nc, nc, d, ldx, h->X, h->stream));
+  if (h->Z) CK(hb_launch_colmajor_to_rows(tmp, m0, 0, m0, d, ldx, h->Z, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(tmp);
+  h->have_initial = true;
+  return HB_OK;
+}
+
+int hb_set_tape(hb_handle* h, const hb_tape* tape) {
+  if (!h || !tape) return HB_ERR_INVALID;
+  cudaSetDevice(h->device);
+  if (tape->nct != h->nct || tape->d != h->d || tape->delta != h->cfg.delta || tape->n_gen < h->t - 1)
+    return fail(h, HB_ERR_INVALID, "tape geometry does not match the configuration");
+  if (!tape->D || !tape->partners || !tape->id || !tape->zt || !tape->lambda || !tape->g_is_one || !tape->zeta || !tape->u_accept)
+    return fail(h, HB_ERR_INVALID, "tape is missing a required array");
+  return upload_tape(h, tape);
+}
+
+int hb_run(hb_handle* h, int64_t n_generations, int64_t* done_total) {
+  if (!h) return HB_ERR_INVALID;
+  cudaSetDevice(h->device);
+  if (!h->vt) return fail(h, HB_ERR_STATE, "hb_run: no target set");
+  if (!h->have_initial) return fail(h, HB_ERR_STATE, "hb_run: hb_set_initial has not been called");
+  if (h->cfg.rng_mode == HB_RNG_TAPE && !h->have_tape) return fail(h, HB_ERR_STATE, "hb_run: rng_mode is TAPE but no tape was set");
+  if (h->cfg.prior == HB_PRIOR_UNIFORM && !h->have_min_max) return fail(h, HB_ERR_INVALID, "prior = 'uniform' needs min and max");
+  if (!h->initialised) { if (int rc = initialise(h)) return rc; }
+  long long last = h->gen + n_generations;
+  if (last > h->t) last = h->t;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  for (long long i = h->gen + 1; i <= last; ++i) {
+    if (int rc = run_generation(h, i)) return rc;
+  }
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaEventSynchronize(h->ev1));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->loop_ms += ms;
+  if (done_total) *done_total = h->gen;
+  return check_flags(h);
+}
+
+int hb_sync(hb_handle* h) {
+  if (!h) return HB_ERR_INVALID;
+  cudaSetDevice(h->device);
+  CK(cudaStreamSynchronize(h->stream));
+  return HB_OK;
+}
+
+int hb_out_dims(const hb_handle* h, int64_t* out_t, int64_t* ar_rows, int64_t* ar_cols, int64_t* cr_rows, int64_t* cr_cols,
+                int64_t* fx_m, int64_t* rstat_rows) {
+  if (!h) return HB_ERR_INVALID;
+  if (out_t) *out_t = h->out_t;
+  if (ar_rows) *ar_rows = h->ar_rows;
+  if (ar_cols) *ar_cols = h->ar_cols;
+  if (cr_rows) *cr_rows = h->cr_rows;
+  if (cr_cols) *cr_cols = h->cr_cols;
+  if (fx_m) *fx_m = h->cfg.store_fx ? 1 : 0;
+  if (rstat_rows) *rstat_rows = h->rstat_rows;
+  return HB_OK;
+}
+
+int64_t hb_ind_out(const hb_handle* h) { return h ? h->ind_out : 0; }
+
+int hb_fetch_chain_rows(hb_handle* h, int64_t row0, int64_t nrows, double* out) {
+  if (!h || !out) return HB_ERR_INVALID;
+  if (!h->initialised) return fail(h, HB_ERR_STATE, "nothing has been run yet");
+  if (row0 < 0 || nrows < 1 || row0 + nrows > h->out_t) return fail(h, HB_ERR_INVALID, "row range out of bounds");
+  cudaSetDevice(h->device);
+  const long long nl = h->n_local;
+  const int dd = h->d + 3;
+  const size_t per_chain = (size_t)nrows * dd * sizeof(double);
+  size_t want = std::min<size_t>((size_t)256 << 20, per_chain * (size_t)nl);
+  if (want < per_chain) want = per_chain;
+  if (h->stage_bytes < want) { if (h->stage) cudaFree(h->stage); h->stage = nullptr; CK(cudaMalloc((void**)&h->stage, want)); h->stage_bytes = want; }
+  const long long chunk = (long long)(h->stage_bytes / per_chain);
+  for (long long c0 = 0; c0 < nl; c0 += chunk) {
+    const long long ncs = std::min(chunk, nl - c0);
+    CK(hb_launch_chain_transpose(h->hist_x, h->hist_l, h->out_t, row0, nrows, h->ind_out, nl, h->d, c0, ncs, h->stage, h->stream));
+    h->launches++;
+    CK(cudaMemcpyAsync(out + (size_t)c0 * dd * nrows, h->stage, per_chain * (size_t)ncs, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return HB_OK;
+}
+
+int hb_fetch_chain(hb_handle* h, double* chain) { return h ? hb_fetch_chain_rows(h, 0, h->out_t, chain) : HB_ERR_INVALID; }
+
+int hb_fetch_fx(hb_handle* h, double* fx) {
+  if (!h || !fx) return HB_ERR_INVALID;
+  if (!h->cfg.store_fx || !h->hist_fx) return fail(h, HB_ERR_STATE, "store_fx was not enabled");
+  cudaSetDevice(h->device);
+  const long long nl = h->n_local;
+  std::vector<double> tmp((size_t)h->out_t * nl);
+  CK(cudaMemcpy(tmp.data(), h->hist_fx, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  for (long long it = 0; it < h->out_t; ++it)
+    for (long long c = 0; c < nl; ++c) fx[it + h->out_t * c] = it < h->ind_out ? tmp[(size_t)it * nl + c] : NAN;
+  return HB_OK;
+}
+
+int hb_fetch_ar(hb_handle* h, double* ar) {
+  if (!h || !ar) return HB_ERR_INVALID;
+  cudaSetDevice(h->device);
+  CK(cudaMemcpy(ar, h->out_ar, sizeof(double) * (size_t)h->ar_rows * h->ar_cols, cudaMemcpyDeviceToHost));
+  return HB_OK;
+}
+int hb_fetch_cr(hb_handle* h, double* cr) {
+  if (!h || !cr) return HB_ERR_INVALID;
+  cudaSetDevice(h->device);
+  CK(cudaMemcpy(cr, h->out_cr, sizeof(double) * (size_t)h->cr_rows * h->cr_cols, cudaMemcpyDeviceToHost));
+  return HB_OK;
+}
+
+int hb_fetch_rstat(hb_handle* h, double* rstat) {
+  if (!h || !rstat) return HB_ERR_INVALID;
+  if (h->rstat_rows < 1) return fail(h, HB_ERR_STATE, "check_convergence was not enabled (or out_t <= 50)");
+  cudaSetDevice(h->device);
+  std::vector<double> tmp((size_t)h->rstat_rows * h->d);
+  CK(cudaMemcpy(tmp.data(), h->rstat_dev, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  for (long long r = 0; r < h->rstat_rows; ++r)
+    for (int k = 0; k < h->d; ++k) rstat[r + h->rstat_rows * k] = tmp[(size_t)r * h->d + k];
+  return HB_OK;
+}
+
+int hb_fetch_state(hb_handle* h, double* xt, double* lp, double* ll, double* lpost) {
+  if (!h) return HB_ERR_INVALID;
+  if (!h->have_initial) return fail(h, HB_ERR_STATE, "no state yet");
+  cudaSetDevice(h->device);
+  const long long nc = h->nc, nl = h->n_local;
+  if (xt) {
+    double* tmp = nullptr;
+    CK(dalloc(&tmp, (size_t)nc * h->d));
+    CK(hb_launch_rows_to_colmajor(h->X, h->ldx, h->d, nc, tmp, h->stream));
+    CK(cudaMemcpyAsync(xt, tmp, sizeof(double) * (size_t)nc * h->d, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(tmp);
+  }
+  if (lp) CK(cudaMemcpy(lp, h->lp, sizeof(double) * nl, cudaMemcpyDeviceToHost));
+  if (ll) CK(cudaMemcpy(ll, h->ll, sizeof(double) * nl, cudaMemcpyDeviceToHost));
+  if (lpost) CK(cudaMemcpy(lpost, h->lpost, sizeof(double) * nl, cudaMemcpyDeviceToHost));
+  return HB_OK;
+}
+
+int hb_fetch_accept(hb_handle* h, uint8_t* accept) {
+  if (!h || !accept) return HB_ERR_INVALID;
+  if (!h->accept_rec) return fail(h, HB_ERR_STATE, "record_accept was not enabled");
+  cudaSetDevice(h->device);
+  CK(cudaMemcpy(accept, h->accept_rec, (size_t)(h->t - 1) * h->n_local, cudaMemcpyDeviceToHost));
+  return HB_OK;
+}
+
+int hb_fetch_outliers(hb_handle* h, int64_t* n_pairs, int64_t* gen, int64_t* chain, int64_t cap) {
+  if (!h || !n_pairs) return HB_ERR_INVALID;
+  *n_pairs = (int64_t)h->outlier_gen.size();
+  if (gen && chain)
+    for (int64_t q = 0; q < *n_pairs && q < cap; ++q) { gen[q] = h->outlier_gen[(size_t)q]; chain[q] = h->outlier_chain[(size_t)q]; }
+  return HB_OK;
+}
+
+int hb_rstat(hb_handle* h, double* out_d) {
+  if (!h || !out_d) return HB_ERR_INVALID;
+  if (!h->initialised) return fail(h, HB_ERR_STATE, "nothing has been run yet");
+  if (h->ind_out < 3) return fail(h, HB_ERR_INVALID, "R_stat needs at least 3 stored generations");
+  if (h->world > 1) return fail(h, HB_ERR_UNSUPPORTED, "hb_rstat on a sharded population is not wired yet");
+  cudaSetDevice(h->device);
+  double* o = nullptr;
+  CK(dalloc(&o, (size_t)h->d));
+  prof_scope ps(h, "K4");
+  CK(hb_launch_rstat(h->hist_x, h->ind_out, h->n_local, 0, h->n_local, h->d, h->rstat_xm, h->rstat_ss, o, h->stream));
+  ps.done(2);
+  CK(cudaMemcpyAsync(out_d, o, sizeof(double) * h->d, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(o);
+  return HB_OK;
+}
+
+int hb_get_timing(const hb_handle* h, double* loop_ms, int64_t* kernel_launches) {
+  if (!h) return HB_ERR_INVALID;
+  if (loop_ms) *loop_ms = h->loop_ms;
+  if (kernel_launches) *kernel_launches = h->launches;
+  return HB_OK;
+}
+
+int hb_profile(hb_handle* h, int enable) {
+  if (!h) return HB_ERR_INVALID;
+  h->profile = enable != 0;
+  return HB_OK;
+}
+
+int hb_get_kernel_ms(const hb_handle* h, const char* kernel, double* total_ms, int64_t* launches) {
+  if (!h || !kernel) return HB_ERR_INVALID;
+  auto it = h->kstats.find(kernel);
+  if (total_ms) *total_ms = it == h->kstats.end() ? 0.0 : it->second.ms;
+  if (launches) *launches = it == h->kstats.end() ? 0 : it->second.launches;
+  return HB_OK;
+}
+
+// ---- stand-alone entry points ---------------------------------------------------------------------------
+static void set_msg(char* err, int errlen, const char* m) { if (err && errlen > 0) snprintf(err, (size_t)errlen, "%s", m); }
+
+int hb_rstat_array(const double* x, int64_t t, int32_t d, int64_t n, double* out, char* err, int errlen) {
+  if (!x || !out || t < 3 || d < 1 || n < 2) { set_msg(err, errlen, "R_stat: need x[t >= 3, d >= 1, n >= 2]"); return HB_ERR_INVALID; }
+  if (hb_device_count() < 1) { set_msg(err, errlen, "no CUDA device is available and there is no CPU fallback"); return HB_ERR_NO_DEVICE; }
+  double *xd = nullptr, *xm = nullptr, *ss = nullptr, *od = nullptr;
+  const size_t tot = (size_t)t * d * n;
+  bool ok = cudaMalloc((void**)&xd, tot * 8) == cudaSuccess && cudaMalloc((void**)&xm, (size_t)n * d * 8) == cudaSuccess &&
+            cudaMalloc((void**)&ss, (size_t)n * d * 8) == cudaSuccess && cudaMalloc((void**)&od, (size_t)d * 8) == cudaSuccess;
+  ok = ok && cudaMemcpy(xd, x, tot * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+  ok = ok && hb_launch_rstat_colmajor(xd, t, d, n, xm, ss, od, nullptr) == cudaSuccess;
+  ok = ok && cudaMemcpy(out, od, (size_t)d * 8, cudaMemcpyDeviceToHost) == cudaSuccess;
+  cudaFree(xd); cudaFree(xm); cudaFree(ss); cudaFree(od);
+  if (!ok) { set_msg(err, errlen, cudaGetErrorString(cudaGetLastError())); return HB_ERR_CUDA; }
+  return HB_OK;
+}
+
+int hb_logdensity(const char* name, int32_t lik, const double* data, const int64_t* dims, int ndims, const double* obs,
+                  int64_t n_obs, double glue_shape, const double* x, int64_t n, int32_t d, double* ll_out, double* fx_out,
+                  char* err, int errlen) {
+  if (!name || !x || !ll_out || n < 1 || d < 1) { set_msg(err, errlen, "hb_logdensity: bad arguments"); return HB_ERR_INVALID; }
+  if (hb_device_count() < 1) { set_msg(err, errlen, "no CUDA device is available and there is no CPU fallback"); return HB_ERR_NO_DEVICE; }
+  const hb_target_vtable* vt = hb_find_target(name);
+  if (!vt) { set_msg(err, errlen, "unknown target"); return HB_ERR_UNKNOWN_TARGET; }
+  void* ctx = nullptr;
+  int rc = vt->init(&ctx, d, lik, data, dims, ndims, obs, n_obs, glue_shape, err, errlen);
+  if (rc) return rc;
+  const int ldx = d == 1 ? 1 : (d + 3) & ~3;
+  double *xc = nullptr, *xr = nullptr, *ll = nullptr, *fx = nullptr;
+  bool ok = cudaMalloc((void**)&xc, (size_t)n * d * 8) == cudaSuccess && cudaMalloc((void**)&xr, (size_t)n * ldx * 8) == cudaSuccess &&
+            cudaMalloc((void**)&ll, (size_t)n * 8) == cudaSuccess && cudaMalloc((void**)&fx, (size_t)n * 8) == cudaSuccess;
+  ok = ok && cudaMemcpy(xc, x, (size_t)n * d * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+  ok = ok && cudaMemset(fx, 0, (size_t)n * 8) == cudaSuccess;
+  ok = ok && hb_launch_colmajor_to_rows(xc, n, 0, n, d, ldx, xr, nullptr) == cudaSuccess;
+  if (ok) rc = vt->launch(ctx, xr, n, d, ldx, ll, fx, nullptr);
+  ok = ok && rc == HB_OK && cudaDeviceSynchronize() == cudaSuccess;
+  ok = ok && cudaMemcpy(ll_out, ll, (size_t)n * 8, cudaMemcpyDeviceToHost) == cudaSuccess;
+  if (ok && fx_out) ok = cudaMemcpy(fx_out, fx, (size_t)n * 8, cudaMemcpyDeviceToHost) == cudaSuccess;
+  unsigned dom = 0;
+  if (ok && strcmp(name, "HydroModel") == 0) dom = hb_hydro_poll_err(ctx);
+  vt->destroy(ctx);
+  cudaFree(xc); cudaFree(xr); cudaFree(ll); cudaFree(fx);
+  if (!ok) { set_msg(err, errlen, rc ? "target launch failed" : cudaGetErrorString(cudaGetLastError())); return rc ? rc : HB_ERR_CUDA; }
+  if (dom) { set_msg(err, errlen, "Argument 'param' has to be >= zero!"); return HB_ERR_INVALID; }
+  for (int64_t i = 0; i < n; ++i) {                         // calc_ll floor and check, R/internals.R:19-21
+    double v = ll_out[i];
+    if (!(v >= HB_FLOOR)) v = (v != v) ? v : HB_FLOOR;
+    if (!std::isfinite(v)) { set_msg(err, errlen, "Calculated log-likelihood is not finite!"); return HB_ERR_NONFINITE; }
+    ll_out[i] = v;
+  }
+  return HB_OK;
+}
+
+}  // extern "C"

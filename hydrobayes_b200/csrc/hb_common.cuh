@@ -1,0 +1,160 @@
+// hb_common.cuh -- shared device helpers: Philox4x32-10, uniform conversions, group (sub-warp) primitives.
+//
+// Philox slot map (DESIGN.md "Philox slot map"): counter = (chain_lo, chain_hi, generation, slot), key = seed.
+//   slot 0      words 0-1 -> u_snooker (53 bit)        words 2-3 -> D = 1 + mulhi64(r, delta)      R/internals.R:119,123
+//   slot 1..4   two 64-bit draws each -> partial Fisher-Yates partner draws 0..7 (delta <= 4)     R/internals.R:134,142
+//   slot 5      words 0-1 -> u_id (crossover index)     words 2-3 -> u_gamma                        R/internals.R:173,192
+//   slot 6      words 0-1 -> u_accept                   words 2-3 -> g_snooker = 1.2 + u            R/internals.R:241,156
+//   slot 8+k    word 0 -> zt_k, word 1 -> lambda_k, words 2-3 -> zeta_k (Box-Muller, float)         R/internals.R:175,188,194
+//   outlier replacement draws: chain = (0xFFFFFFFF << 32) | run, slot = q >> 1, pair q & 1 (host side) R/internals.R:81
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define HB_FLOOR (-708.3964185322641)  // log(.Machine$double.xmin), R/internals.R:19,65
+
+// error bits raised by kernels into hb_ctrl::err
+enum : unsigned {
+  HB_FLAG_PROP_NONFINITE = 1u,   // R/internals.R:209
+  HB_FLAG_LP_NONFINITE = 2u,     // R/internals.R:67
+  HB_FLAG_LL_NONFINITE = 4u,     // R/internals.R:21
+  HB_FLAG_J_NAN = 8u,            // if(any(J > 0)) on NaN, R/dream_parallel.R:407
+  HB_FLAG_BAD_TAPE = 16u,
+  HB_FLAG_TARGET_DOMAIN = 32u    // HydroModel: param < 0, R/test_HydroModel.R:18
+};
+
+enum { HB_SLOT_HEAD = 0, HB_SLOT_PARTNER0 = 1, HB_SLOT_CHOICE = 5, HB_SLOT_ACCEPT = 6, HB_SLOT_DIM0 = 8 };
+
+#define HB_MAX_NCR 16
+#define HB_MAX_DELTA 4
+
+// Device-resident control block: everything the reference keeps in R scalars/vectors between generations.
+struct hb_ctrl {
+  double pCR[HB_MAX_NCR];        // R/dream_parallel.R:192
+  double J[HB_MAX_NCR];          // :183
+  double n_id[HB_MAX_NCR];       // :183 (doubles holding integers, like R)
+  unsigned long long n_id_gen[HB_MAX_NCR];  // per-generation integer counters (atomics), folded by the finalize kernel
+  unsigned long long n_acc_gen;
+  double n_acc;                  // :184, per AR interval
+  double n_eval;                 // :185
+  double cum_eval;               // out_CR[i_ar-1,1] + n_eval, :430
+  long long i_ar;                // :250
+  unsigned err;                  // HB_FLAG_*
+  unsigned pad;
+};
+
+__host__ __device__ __forceinline__ uint4 hb_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                          uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    const uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+struct hb_phx {
+  uint32_t k0, k1, c0, c1, gen;
+  __host__ __device__ __forceinline__ hb_phx(uint64_t seed, uint64_t gchain, uint32_t generation)
+      : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)), c0((uint32_t)gchain), c1((uint32_t)(gchain >> 32)),
+        gen(generation) {}
+  __host__ __device__ __forceinline__ uint4 slot(uint32_t s) const { return hb_philox4x32_10(c0, c1, gen, s, k0, k1); }
+};
+
+__host__ __device__ __forceinline__ uint64_t hb_pair64(const uint4& w, int which) {
+  return which ? (((uint64_t)w.w << 32) | w.z) : (((uint64_t)w.y << 32) | w.x);
+}
+// open-interval uniforms, identical arithmetic on host and device (exact in binary floating point)
+__host__ __device__ __forceinline__ double hb_u53(uint64_t x) { return (double)(x >> 11) * 0x1.0p-53 + 0x1.0p-54; }
+__host__ __device__ __forceinline__ double hb_u32d(uint32_t x) { return ((double)x + 0.5) * 0x1.0p-32; }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint64_t hb_mulhi64(uint64_t a, uint64_t b) { return __umul64hi(a, b); }
+
+// zeta ~ N(0, c_star^2): Box-Muller in float (zeta is a 1e-12-scale jitter), fast intrinsics
+__device__ __forceinline__ double hb_zeta(uint32_t w2, uint32_t w3, double c_star) {
+  const float u1 = (float)hb_u32d(w2), u2 = (float)hb_u32d(w3);
+  return c_star * (double)(sqrtf(-2.0f * __logf(u1)) * __cosf(6.283185307179586f * u2));
+}
+
+// sparse partial Fisher-Yates over 0..n-1 (R's sample(n, k) without replacement: y = x[r]; x[r] = x[--n])
+struct hb_fy {
+  long long pos[2 * HB_MAX_DELTA];
+  long long val[2 * HB_MAX_DELTA];
+  int cnt;
+  __device__ __forceinline__ hb_fy() : cnt(0) {}
+  __device__ __forceinline__ long long get(long long p) const {
+    long long v = p;
+#pragma unroll
+    for (int i = 0; i < 2 * HB_MAX_DELTA; ++i)
+      if (i < cnt && pos[i] == p) v = val[i];  // later entries override earlier ones
+    return v;
+  }
+  __device__ __forceinline__ long long draw(uint64_t rnd, long long& n_rem) {
+    const long long r = (long long)hb_mulhi64(rnd, (uint64_t)n_rem);
+    const long long y = get(r);
+    const long long last = get(n_rem - 1);
+#pragma unroll
+    for (int i = 0; i < 2 * HB_MAX_DELTA; ++i)
+      if (i == cnt) { pos[i] = r; val[i] = last; }
+    cnt++;
+    n_rem--;
+    return y;
+  }
+};
+
+// bound_par, R/internals.R:89-113
+__device__ __forceinline__ double hb_bound_par(double par, double mn, double mx, int handle) {
+  double o = par;
+  if (par < mn || par > mx) {
+    if (handle == 1) {
+      o = fmax(fmin(par, mx), mn);
+    } else if (handle == 2) {
+      while (o < mn || o > mx) {
+        if (o < mn) o = mn + fabs(mn - o);
+        if (o > mx) o = mx - fabs(mx - o);
+      }
+    } else if (handle == 3) {
+      while (o < mn || o > mx) {
+        if (o < mn) o = mx - fabs(mn - o);
+        if (o > mx) o = mn + fabs(mx - o);
+      }
+    }
+  }
+  return o;
+}
+
+// ---- sub-warp group primitives: G consecutive lanes (G a power of two <= 32) cooperate on one chain -------
+// All take the group's lane mask so that groups of one warp may diverge from one another.
+template <int G>
+__device__ __forceinline__ unsigned hb_group_mask(int lane) {
+  return (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (lane & ~(G - 1)));
+}
+template <int G>
+__device__ __forceinline__ double hb_group_sum(double v, unsigned gmask = 0xffffffffu) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+  return v;
+}
+template <int G>
+__device__ __forceinline__ int hb_group_sum_int(int v, unsigned gmask = 0xffffffffu) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+  return v;
+}
+template <int G>
+__device__ __forceinline__ unsigned hb_group_ballot(bool p, int lane, unsigned gmask = 0xffffffffu) {
+  const unsigned b = __ballot_sync(gmask, p);
+  if (G == 32) return b;
+  return (b >> (lane & ~(G - 1))) & ((1u << (G & 31)) - 1u);
+}
+
+__device__ __forceinline__ double hb_warp_sum(double v) { return hb_group_sum<32>(v); }
+#endif  // __CUDACC__

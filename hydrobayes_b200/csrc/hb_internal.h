@@ -1,0 +1,97 @@
+// hb_internal.h -- the handle behind the C ABI (host side, C++).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/hydrobayes_b200.h"
+#include "hb_kernels.h"
+
+const hb_target_vtable* hb_find_target(const char* name);
+unsigned hb_hydro_poll_err(void* ctx);
+
+struct hb_nccl;  // hb_comm.cu
+
+struct hb_kstat { double ms = 0; long long launches = 0; };
+
+struct hb_handle {
+  hb_config cfg{};
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  std::string err;
+
+  // derived sizes (R/dream_parallel.R:166-205)
+  long long nc = 0, t = 0, nct = 0;
+  int d = 0, ldx = 0;
+  long long m0 = 0, m_arch = 0, m_cap = 0;
+  int archive_update = 0;
+  long long out_t = 0, ar_rows = 0, ar_cols = 0, cr_rows = 0, cr_cols = 0, H = 0;
+  long long rstat_rows = 0;
+
+  // multi-GPU shard of the population
+  int rank = 0, world = 1;
+  long long chain0 = 0, n_local = 0;
+  hb_nccl* comm = nullptr;
+
+  // bounds / prior
+  bool have_min_max = false;
+  std::vector<double> pmin_h, pmax_h;
+  double *pmin = nullptr, *pmax = nullptr;
+  std::vector<double> obs_h;
+
+  // target plugin
+  const hb_target_vtable* vt = nullptr;
+  void* tctx = nullptr;
+  std::string target_name;
+  bool target_is_hydro = false;
+
+  // device state
+  double *X = nullptr, *Z = nullptr, *XP = nullptr;
+  int* id = nullptr;
+  double *lp_xp = nullptr, *ll_raw = nullptr, *fx_xp = nullptr;
+  double *lp = nullptr, *ll = nullptr, *lpost = nullptr, *fx = nullptr;
+  double* lpost_hist = nullptr;           // [H][n_local]
+  double *hist_x = nullptr, *hist_l = nullptr, *hist_fx = nullptr;   // [out_t][n_local][d|3|1]
+  uint8_t* accept_rec = nullptr;          // [t-1][n_local]
+  hb_ctrl* ctrl = nullptr;
+  double *shift = nullptr, *colsum = nullptr, *qsum = nullptr, *partials = nullptr;
+  int k3_blocks = 0;
+  double *out_ar = nullptr, *out_cr = nullptr;
+  double *proxy = nullptr, *proxy_full = nullptr, *lpost_full = nullptr;
+  int *outl_dev = nullptr, *news_dev = nullptr;
+  double *rstat_dev = nullptr, *rstat_xm = nullptr, *rstat_ss = nullptr;
+  double* stage = nullptr; size_t stage_bytes = 0;
+
+  // tape
+  bool have_tape = false;
+  hb_tape_dev tape{};
+  std::vector<void*> tape_allocs;
+  std::vector<int32_t> tape_outlier_new;  // host copy [n_events][nct]
+  long long tape_events = 0, tape_n_gen = 0;
+
+  // progress
+  bool have_initial = false, initialised = false;
+  long long gen = 1;                      // last completed generation (1 = initial state)
+  long long ind_out = 1;
+  long long pending_evals = 0;
+  std::vector<long long> outlier_gen, outlier_chain;
+
+  // timing
+  double loop_ms = 0;
+  long long launches = 0;
+  bool profile = false;
+  std::map<std::string, hb_kstat> kstats;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+// hb_comm.cu: NCCL loaded lazily with dlopen (no link-time dependency; single-GPU use needs no NCCL)
+int hb_nccl_unique_id(void* id128, std::string& err);
+int hb_nccl_init(hb_nccl** out, int rank, int world, const void* id128, std::string& err);
+void hb_nccl_destroy(hb_nccl* c);
+int hb_nccl_allgather_f64(hb_nccl* c, const double* send, double* recv, size_t count, cudaStream_t st, std::string& err);
+int hb_nccl_allreduce_f64(hb_nccl* c, double* buf, size_t count, cudaStream_t st, std::string& err);
+int hb_nccl_allreduce_u64(hb_nccl* c, unsigned long long* buf, size_t count, cudaStream_t st, std::string& err);
+int hb_nccl_allreduce_u32_bor(hb_nccl* c, unsigned* buf, size_t count, cudaStream_t st, std::string& err);

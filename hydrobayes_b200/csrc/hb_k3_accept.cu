@@ -1,0 +1,467 @@
+// hb_k3_accept.cu -- K3: Metropolis accept/reject + state update + history store + adaptation statistics,
+// the finalize step (J, n_id, pCR adaptation, AR/CR rows) and the outlier-reset pieces.
+//
+// Replaces metropolis_acceptance (R/internals.R:221-247), the update block R/dream_parallel.R:348-378, the store
+// block :386-399, the pCR adaptation :403-411, check_outlier's copy (R/internals.R:82-83) and the AR/CR rows :425-433.
+//
+// Statistics: std_x (R/dream_parallel.R:376) is the post-update sample sd over chains.  K3 accumulates, per block and
+// in a fixed order, the shifted column sums  sum(x - c), sum((x - c)^2)  (c = last generation's column mean) and
+// Q[id][k] = sum over accepted chains with crossover index id of dx_k^2; the finalize kernel reduces the block
+// partials in block order (deterministic), forms var_k and J[id] += sum_k Q[id][k] / var_k, which equals
+// sum_j sum_k (dx_jk / std_k)^2 of :377-378.  All of this only runs inside the adaptation period: J and n_id are
+// unobservable afterwards (:403).
+#include "hb_kernels.h"
+
+namespace {
+
+template <int G, int ITER, bool TAPE>
+__global__ void __launch_bounds__(256) hb_k3_kernel(const hb_k3_params p) {
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int CPW = 32 / G;
+  extern __shared__ double smem[];
+  __shared__ unsigned long long s_cnt[HB_MAX_NCR + 1];
+  const int lane = threadIdx.x & 31;
+  const int lg = lane & (G - 1);
+  const int gbase = lane & ~(G - 1);
+  const int warp_in_block = threadIdx.x >> 5;
+  const int slot = warp_in_block * CPW + lane / G;          // accumulator slot of this group
+  const int n_slots = (blockDim.x >> 5) * CPW;
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int d = p.d, ldx = p.ldx, nCR = p.nCR;
+  const bool adapt = p.adapt != 0;
+  const int E = (nCR + 2) * d;                              // accumulator elements per slot
+  unsigned errbits = 0;
+
+  if (threadIdx.x <= nCR) s_cnt[threadIdx.x] = 0ull;
+  if (adapt) {
+    for (int e = threadIdx.x; e < n_slots * E; e += blockDim.x) smem[e] = 0.0;
+  }
+  __syncthreads();
+  double* acc = smem + (size_t)slot * E;                    // [ (nCR+2) ][ d ] : rows 0,1 = s1,s2 ; 2+q = Q[q]
+  double s1[ITER], s2[ITER], sh[ITER];
+#pragma unroll
+  for (int m = 0; m < ITER; ++m) {
+    s1[m] = 0; s2[m] = 0;
+    const int k = m * G + lg;
+    sh[m] = (adapt && k < d) ? p.shift[k] : 0.0;
+  }
+
+  for (long long base = warp_id * CPW; base < p.n_local; base += n_warps * CPW) {
+    const long long jl = base + lane / G;
+    const bool valid = jl < p.n_local;
+    const long long j = p.chain0 + (valid ? jl : 0);
+    const long long gch = p.gchain0 + j;
+    int accf = 0, id = 0;
+    double lpx = 0, lln = 0, lpostx = 0, lpost_old = 0;
+    if (valid && lg == 0) {
+      lpx = p.lp_xp[jl];
+      double llr = p.ll_raw[jl];
+      if (!(llr >= HB_FLOOR)) llr = (llr != llr) ? llr : HB_FLOOR;    // calc_ll floor, R/internals.R:19
+      if (!isfinite(llr)) errbits |= HB_FLAG_LL_NONFINITE;            // :21
+      lln = llr;
+      lpostx = lpx + lln;                                             // R/dream_parallel.R:291
+      lpost_old = p.lpost[jl];
+      double u;
+      if (TAPE) u = p.u_accept[gch];
+      else { const hb_phx ph(p.seed, (uint64_t)gch, p.gen); u = hb_u53(hb_pair64(ph.slot(HB_SLOT_ACCEPT), 0)); }
+      const double p_acc = fmin(fmax(-100.0, lpostx - lpost_old), 0.0); // R/internals.R:239
+      accf = p_acc > log(u);                                          // :241
+      id = p.id[jl];
+    }
+    if (G > 1) { accf = __shfl_sync(FULL, accf, gbase); id = __shfl_sync(FULL, id, gbase); }
+
+    const bool need_x = adapt || p.hist_x != nullptr;
+#pragma unroll
+    for (int m = 0; m < ITER; ++m) {
+      const int k = m * G + lg;
+      if (valid && k < d) {
+        double xn = 0.0;
+        if (accf) {
+          xn = p.XP[jl * (long long)ldx + k];
+          if (adapt) {
+            const double dx = xn - p.X[j * (long long)ldx + k];       // R/dream_parallel.R:357 (after bound handling)
+            acc[(2 + id) * d + k] += dx * dx;
+          }
+          p.X[j * (long long)ldx + k] = xn;                           // :358
+        } else if (need_x) {
+          xn = p.X[j * (long long)ldx + k];
+        }
+        if (adapt) { const double c = xn - sh[m]; s1[m] += c; s2[m] += c * c; }
+        if (p.hist_x) p.hist_x[jl * (long long)d + k] = xn;           // chain[ind_out, 1:d, ] :388
+      }
+    }
+    if (valid && lg == 0) {
+      double lp_c, ll_c, lpost_c;
+      if (accf) {
+        p.lp[jl] = lpx; p.ll[jl] = lln; p.lpost[jl] = lpostx;         // :359-361
+        if (p.fx && p.fx_xp) p.fx[jl] = p.fx_xp[jl];                  // :362
+        lp_c = lpx; ll_c = lln; lpost_c = lpostx;
+      } else {
+        lpost_c = lpost_old;                                          // :365
+        lp_c = 0; ll_c = 0;
+        if (p.hist_l) { lp_c = p.lp[jl]; ll_c = p.ll[jl]; }
+      }
+      if (p.hist_l) {                                                 // :389-391
+        p.hist_l[jl * 3 + 0] = lp_c; p.hist_l[jl * 3 + 1] = ll_c; p.hist_l[jl * 3 + 2] = lpost_c;
+      }
+      if (p.hist_fx && p.fx) p.hist_fx[jl] = p.fx[jl];                // :394
+      if (p.lpost_hist_row) p.lpost_hist_row[jl] = lpost_c;
+      if (p.accept_rec) p.accept_rec[jl] = (uint8_t)accf;
+      atomicAdd(&s_cnt[1 + id], 1ull);                                // n_id  :368-369
+      if (accf) atomicAdd(&s_cnt[0], 1ull);                           // n_acc :374
+    }
+  }
+
+  if (adapt) {
+#pragma unroll
+    for (int m = 0; m < ITER; ++m) {
+      const int k = m * G + lg;
+      if (k < d) { acc[k] = s1[m]; acc[d + k] = s2[m]; }
+    }
+  }
+  __syncthreads();
+  if (adapt) {
+    // fixed-order reduction over the block's slots -> one partial row per block
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+      double s = 0.0;
+      for (int q = 0; q < n_slots; ++q) s += smem[(size_t)q * E + e];
+      p.partials[(size_t)blockIdx.x * E + e] = s;
+    }
+  }
+  if (threadIdx.x <= nCR) {
+    const unsigned long long v = s_cnt[threadIdx.x];
+    if (v) {
+      if (threadIdx.x == 0) atomicAdd(&p.ctrl->n_acc_gen, v);
+      else atomicAdd(&p.ctrl->n_id_gen[threadIdx.x - 1], v);
+    }
+  }
+  if (errbits) atomicOr(&p.ctrl->err, errbits);
+}
+
+template <int G>
+struct k3_geom {
+  static constexpr int CPW = 32 / G;
+};
+
+template <int G, int ITER>
+cudaError_t launch_gi(const hb_k3_params& p, int sm_count, int* nblocks_out, size_t* smem_out, cudaStream_t st) {
+  constexpr int CPW = 32 / G;
+  const size_t per_warp = (size_t)CPW * (p.nCR + 2) * p.d * sizeof(double);
+  int warps = 8;
+  const size_t budget = 160 * 1024;
+  while (warps > 1 && per_warp * warps > budget) warps >>= 1;
+  const size_t smem_adapt = per_warp * warps;
+  if (smem_adapt > 220 * 1024) return cudaErrorInvalidValue;
+  const int threads = warps * 32;
+  const long long warps_needed = (p.n_local + CPW - 1) / CPW;
+  long long blocks = (warps_needed + warps - 1) / warps;
+  const long long cap = (long long)sm_count * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if (nblocks_out) *nblocks_out = (int)blocks;
+  if (smem_out) *smem_out = smem_adapt;
+  if (p.X == nullptr) return cudaSuccess;                   // geometry query only
+  const size_t smem = p.adapt ? smem_adapt : 0;
+  const bool tape = p.u_accept != nullptr;
+  cudaError_t e = cudaSuccess;
+  if (tape) {
+    if (smem > 48 * 1024) e = cudaFuncSetAttribute(hb_k3_kernel<G, ITER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    hb_k3_kernel<G, ITER, true><<<(unsigned)blocks, threads, smem, st>>>(p);
+  } else {
+    if (smem > 48 * 1024) e = cudaFuncSetAttribute(hb_k3_kernel<G, ITER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    hb_k3_kernel<G, ITER, false><<<(unsigned)blocks, threads, smem, st>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t dispatch(const hb_k3_params& p, int sm_count, int* nb, size_t* sm, cudaStream_t st) {
+  const int d = p.d;
+  if (d <= 1) return launch_gi<1, 1>(p, sm_count, nb, sm, st);
+  if (d <= 2) return launch_gi<2, 1>(p, sm_count, nb, sm, st);
+  if (d <= 4) return launch_gi<4, 1>(p, sm_count, nb, sm, st);
+  if (d <= 8) return launch_gi<8, 1>(p, sm_count, nb, sm, st);
+  if (d <= 16) return launch_gi<16, 1>(p, sm_count, nb, sm, st);
+  if (d <= 32) return launch_gi<32, 1>(p, sm_count, nb, sm, st);
+  if (d <= 64) return launch_gi<32, 2>(p, sm_count, nb, sm, st);
+  if (d <= 128) return launch_gi<32, 4>(p, sm_count, nb, sm, st);
+  if (d <= 256) return launch_gi<32, 8>(p, sm_count, nb, sm, st);
+  if (d <= 512) return launch_gi<32, 16>(p, sm_count, nb, sm, st);
+  if (d <= 1024) return launch_gi<32, 32>(p, sm_count, nb, sm, st);
+  return cudaErrorInvalidValue;
+}
+
+// ---- finalize -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hb_finalize_kernel(const hb_fin_params p) {
+  __shared__ double red[256];
+  const int d = p.d, nCR = p.nCR;
+  const int E = (nCR + 2) * d;
+  hb_ctrl* c = p.ctrl;
+  if (p.adapt && (p.phase == 0 || p.phase == 2)) {
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+      double s = 0.0;
+      for (int b = 0; b < p.nblocks; ++b) s += p.partials[(size_t)b * E + e];
+      if (e < 2 * d) p.colsum[e] = s; else p.qsum[e - 2 * d] = s;
+    }
+  }
+  if (p.phase == 0) return;
+  __syncthreads();
+  if (p.adapt) {
+    // var_k of the post-update population (n-1 denominator), R/dream_parallel.R:376
+    const double n = (double)p.nc;
+    for (int q = 0; q < nCR; ++q) {
+      double part = 0.0;
+      for (int k = threadIdx.x; k < d; k += blockDim.x) {
+        const double a = p.colsum[k], b = p.colsum[d + k];
+        const double var = (b - a * a / n) / (n - 1.0);
+        part += p.qsum[q * d + k] / var;                    // sum_j (dx_jk/std_k)^2 over chains with id == q
+      }
+      red[threadIdx.x] = part;
+      __syncthreads();
+      for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) c->J[q] += red[0];              // :377-378
+      __syncthreads();
+    }
+    for (int k = threadIdx.x; k < d; k += blockDim.x) p.shift[k] += p.colsum[k] / n;   // next generation's shift
+  }
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < nCR; ++q) { c->n_id[q] += (double)c->n_id_gen[q]; c->n_id_gen[q] = 0ull; }   // :368-369
+    c->n_acc += (double)c->n_acc_gen; c->n_acc_gen = 0ull;                                          // :374
+    c->n_eval += (double)p.n_eval_inc;                                                              // :375
+    if (p.do_pcr) {                                         // R/dream_parallel.R:407-411
+      bool anypos = false, anynan = false;
+      for (int q = 0; q < nCR; ++q) { if (c->J[q] != c->J[q]) anynan = true; if (c->J[q] > 0) anypos = true; }
+      if (anynan) atomicOr(&c->err, HB_FLAG_J_NAN);
+      else if (anypos) {
+        double s = 0.0;
+        for (int q = 0; q < nCR; ++q) {
+          double v = c->J[q] / c->n_id[q];
+          if (v != v) v = 1.0 / nCR;                        // n_id == 0 -> NaN -> 1/nCR
+          c->pCR[q] = v; s += v;
+        }
+        for (int q = 0; q < nCR; ++q) c->pCR[q] = c->pCR[q] / s;
+      }
+    }
+    if (p.do_arcr) {                                        // :425-433
+      c->i_ar += 1;
+      const long long r = c->i_ar - 1;
+      c->cum_eval += c->n_eval;
+      if (r < p.ar_rows) {
+        p.out_ar[r + p.ar_rows] = c->n_acc / c->n_eval;
+        p.out_ar[r] = c->cum_eval;
+        p.out_cr[r] = c->cum_eval;
+        for (int q = 0; q < nCR; ++q) p.out_cr[r + p.ar_rows * (q + 1)] = c->pCR[q];
+      }
+      c->n_acc = 0; c->n_eval = 0;
+    }
+  }
+}
+
+// ---- outlier pieces -------------------------------------------------------------------------------------
+// proxy <- colMeans(lpost[ceiling(i/2):i, ])  R/internals.R:73 ; Kahan-compensated column sum
+__global__ void hb_proxy_kernel(const double* __restrict__ hist, long long n, long long row0, long long row1,
+                                long long ld, double* __restrict__ proxy) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  double s = 0.0, c = 0.0;
+  for (long long r = row0; r <= row1; ++r) {
+    const double y = hist[r * ld + j] - c;
+    const double t = s + y;
+    c = (t - s) - y;
+    s = t;
+  }
+  proxy[j] = s / (double)(row1 - row0 + 1);
+}
+
+// x[outliers,] <- x[new_states,] ; dens[nrow, outliers] <- dens[nrow, new_states]  (R/internals.R:82-83).
+// new_states never contains an outlier, so sources are not modified by this kernel.
+__global__ void hb_outlier_reset_kernel(double* X, int ldx, int d, double* lpost, double* hist_row, const int* outl,
+                                        const int* news, int n_out) {
+  const int q = blockIdx.x;
+  if (q >= n_out) return;
+  const long long dst = outl[q], srcc = news[q];
+  for (int k = threadIdx.x; k < d; k += blockDim.x) X[dst * ldx + k] = X[srcc * ldx + k];
+  if (threadIdx.x == 0) {
+    const double v = lpost[srcc];
+    lpost[dst] = v;
+    if (hist_row) hist_row[dst] = v;
+  }
+}
+
+// ---- misc ------------------------------------------------------------------------------------------------
+__global__ void hb_init_state_kernel(const double* lp_in, const double* ll_raw, const double* fx_in, double* lp,
+                                     double* ll, double* lpost, double* fx, double* hist_row, long long n,
+                                     unsigned* err) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  double l = ll_raw[j];
+  if (!(l >= HB_FLOOR)) l = (l != l) ? l : HB_FLOOR;
+  if (!isfinite(l)) atomicOr(err, HB_FLAG_LL_NONFINITE);
+  const double a = lp_in[j];
+  lp[j] = a; ll[j] = l; lpost[j] = a + l;                    // R/dream_parallel.R:238
+  if (fx && fx_in) fx[j] = fx_in[j];
+  if (hist_row) hist_row[j] = a + l;
+}
+
+__global__ void hb_prior_kernel(const double* X, int ldx, int d, long long n, int prior, const double* pmin,
+                                const double* pmax, double* lp, unsigned* err) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  double s = 0.0;
+  if (prior == 1)
+    for (int k = 0; k < d; ++k) {
+      const double x = X[j * ldx + k], a = pmin[k], b = pmax[k];
+      s += (a <= x && x <= b) ? -log(b - a) : -INFINITY;
+    }
+  if (!(s >= HB_FLOOR)) s = (s != s) ? s : HB_FLOOR;
+  if (!isfinite(s)) atomicOr(err, HB_FLAG_LP_NONFINITE);
+  lp[j] = s;
+}
+
+__global__ void hb_store_row_kernel(const double* X, int ldx, int d, long long n, const double* lp, const double* ll,
+                                    const double* lpost, const double* fx, double* hist_x, double* hist_l,
+                                    double* hist_fx) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n * d) { const long long j = e / d; const int k = (int)(e % d); hist_x[e] = X[j * ldx + k]; }
+  if (e < n) {
+    hist_l[e * 3 + 0] = lp[e]; hist_l[e * 3 + 1] = ll[e]; hist_l[e * 3 + 2] = lpost[e];
+    if (hist_fx && fx) hist_fx[e] = fx[e];
+  }
+}
+
+__global__ void hb_colmajor_to_rows_kernel(const double* in, long long n_rows_total, long long row0, long long n, int d,
+                                           int ldx, double* out) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * ldx) return;
+  const long long j = e / ldx; const int k = (int)(e % ldx);
+  out[e] = (k < d) ? in[(row0 + j) + n_rows_total * k] : 0.0;
+}
+
+__global__ void hb_rows_to_colmajor_kernel(const double* in, int ldx, int d, long long n, double* out) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * d) return;
+  const long long j = e % n; const int k = (int)(e / n);
+  out[e] = in[j * ldx + k];
+}
+
+__global__ void hb_fill_kernel(double* p, long long n, double v) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) p[e] = v;
+}
+
+// history [rows][nct][d] (+ [rows][nct][3]) -> R's chain[nrows, d+3, ncs] for chains c0..c0+ncs-1 (32x32 smem tiles)
+__global__ void hb_chain_transpose_kernel(const double* __restrict__ hist_x, const double* __restrict__ hist_l,
+                                          long long row0, long long nrows, long long rows_filled, long long nct, int d,
+                                          long long c0, long long ncs, double* __restrict__ out) {
+  __shared__ double tile[32][33];
+  const int dd = d + 3;
+  const long long ncols = ncs * dd;                         // output columns: (c - c0)*(d+3) + k
+  const long long colb = (long long)blockIdx.x * 32, rowb = (long long)blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const long long it = rowb + r, col = colb + threadIdx.x;
+    double v = NAN;                                         // rows not yet written stay NA (R: array(NA, ...))
+    if (it < nrows && col < ncols && row0 + it < rows_filled) {
+      const long long c = c0 + col / dd; const int k = (int)(col % dd);
+      v = (k < d) ? hist_x[((row0 + it) * nct + c) * d + k] : hist_l[((row0 + it) * nct + c) * 3 + (k - d)];
+    }
+    tile[r][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const long long col = colb + r, it = rowb + threadIdx.x;
+    if (col < ncols && it < nrows) out[it + nrows * col] = tile[threadIdx.x][r];
+  }
+}
+
+}  // namespace
+
+int hb_k3_grid(long long n_local, int d, int nCR, int sm_count, size_t* smem_out) {
+  hb_k3_params p{};
+  p.n_local = n_local; p.d = d; p.nCR = nCR; p.X = nullptr;
+  int nb = 0;
+  if (dispatch(p, sm_count, &nb, smem_out, nullptr) != cudaSuccess) return -1;
+  return nb;
+}
+
+cudaError_t hb_launch_k3(const hb_k3_params& p, int sm_count, int* nblocks_out, size_t* smem_out, cudaStream_t st) {
+  return dispatch(p, sm_count, nblocks_out, smem_out, st);
+}
+
+cudaError_t hb_launch_finalize(const hb_fin_params& p, cudaStream_t st) {
+  hb_finalize_kernel<<<1, 256, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t hb_launch_proxy(const double* lpost_hist, long long nc_local, long long row0, long long row1, long long ld,
+                            double* proxy, cudaStream_t st) {
+  hb_proxy_kernel<<<(unsigned)((nc_local + 255) / 256), 256, 0, st>>>(lpost_hist, nc_local, row0, row1, ld, proxy);
+  return cudaGetLastError();
+}
+
+cudaError_t hb_launch_outlier_reset(double* X, int ldx, int d, double* lpost, double* lpost_hist_row, const int* outl,
+                                    const int* news, int n_out, double* scratch, cudaStream_t st) {
+  (void)scratch;
+  if (n_out <= 0) return cudaSuccess;
+  hb_outlier_reset_kernel<<<n_out, 128, 0, st>>>(X, ldx, d, lpost, lpost_hist_row, outl, news, n_out);
+  return cudaGetLastError();
+}
+
+cudaError_t hb_launch_chain_transpose(const double* hist_x, const double* hist_l, long long out_t_alloc, long long row0,
+                                      long long nrows, long long rows_filled, long long nct, int d, long long c0,
+                                      long long ncs, double* out, cudaStream_t st) {
+  (void)out_t_alloc;
+  const long long ncols = ncs * (d + 3);
+  dim3 grid((unsigned)((ncols + 31) / 32), (unsigned)((nrows + 31) / 32));
+  dim3 block(32, 8);
+  hb_chain_transpose_kernel<<<grid, block, 0, st>>>(hist_x, hist_l, row0, nrows, rows_filled, nct, d, c0, ncs, out);
+  return cudaGetLastError();
+}
+
+cudaError_t hb_launch_init_state(const double* lp_in, const double* ll_raw, const double* fx_in, double* lp, double* ll,
+                                 double* lpost, double* fx, double* lpost_hist_row, long long n, unsigned* err,
+                                 cudaStream_t st) {
+  hb_init_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(lp_in, ll_raw, fx_in, lp, ll, lpost, fx,
+                                                                     lpost_hist_row, n, err);
+  return cudaGetLastError();
+}
+
+cudaError_t hb_launch_prior(const double* X, int ldx, int d, long long n, int prior, const double* pmin,
+                            const double* pmax, double* lp, unsigned* err, cudaStream_t st) {
+  hb_prior_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(X, ldx, d, n, prior, pmin, pmax, lp, err);
+  return cudaGetLastError();
+}
+
+cudaError_t hb_launch_store_row(const double* X, int ldx, int d, long long n, const double* lp, const double* ll,
+                                const double* lpost, const double* fx, double* hist_x, double* hist_l, double* hist_fx,
+                                cudaStream_t st) {
+  const long long tot = n * (d > 1 ? d : 1);
+  hb_store_row_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(X, ldx, d, n, lp, ll, lpost, fx, hist_x, hist_l,
+                                                                      hist_fx);
+  return cudaGetLastError();
+}
+
+cudaError_t hb_launch_colmajor_to_rows(const double* in_colmajor, long long n_rows_total, long long row0, long long n,
+                                       int d, int ldx, double* out, cudaStream_t st) {
+  const long long tot = n * ldx;
+  hb_colmajor_to_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(in_colmajor, n_rows_total, row0, n, d, ldx,
+                                                                             out);
+  return cudaGetLastError();
+}
+
+cudaError_t hb_launch_rows_to_colmajor(const double* in, int ldx, int d, long long n, double* out_colmajor,
+                                       cudaStream_t st) {
+  const long long tot = n * d;
+  hb_rows_to_colmajor_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(in, ldx, d, n, out_colmajor);
+  return cudaGetLastError();
+}
+
+cudaError_t hb_launch_fill(double* p, long long n, double v, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  hb_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, v);
+  return cudaGetLastError();
+}

@@ -1,0 +1,128 @@
+// hb_kernels.h -- host-side launch interface of the population (synchronous sweep) kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "hb_common.cuh"
+
+// device-resident copy of an hb_tape (all pointers are device pointers; rows of generation g start at g*nct)
+struct hb_tape_dev {
+  const double* u_snooker;
+  const uint8_t* D;
+  const int32_t* partners;
+  const uint8_t* id;
+  const double* zt;
+  const double* lambda;
+  const uint8_t* g_is_one;
+  const double* zeta;
+  const double* g_snooker;
+  const double* u_accept;
+  long long nct;
+};
+
+// ---- K1: proposal (calc_prop + bound_par + prior_pdf), R/internals.R:115-219, 89-113, 49-69 -------------
+struct hb_k1_params {
+  const double* X;        // population [nc][ldx]: partner rows (and own row) are read from here
+  const double* Z;        // archive [m_arch][ldx] when past_sample, else nullptr
+  long long m_arch;
+  double* XP;             // proposals of the local shard [n_local][ldx]
+  int* id_out;            // [n_local] crossover index
+  double* lp_xp;          // [n_local] log prior of the proposal (floored)
+  const hb_ctrl* ctrl;    // pCR
+  unsigned* err;
+  long long nc;           // chains per run
+  long long chain0;       // first chain of this rank's shard (within the run)
+  long long n_local;      // chains handled by this launch
+  long long gchain0;      // global chain id of chain 0 of the run (run * nc): Philox counter / tape row
+  int d, ldx;
+  int delta, nCR;
+  double c_val, c_star, p_g, beta0, psnooker;
+  int past_sample;
+  int bound;              // HB_BOUND_* ; 0 when min/max unset
+  int prior;              // HB_PRIOR_*
+  const double* pmin;     // [d] device, or nullptr
+  const double* pmax;
+  uint64_t seed;
+  uint32_t gen;           // R's generation index i (2..t)
+  hb_tape_dev tape;
+  long long tape_g;       // generation row of the tape (i - 2)
+};
+cudaError_t hb_launch_k1(const hb_k1_params& p, bool tape_mode, int sm_count, cudaStream_t st);
+
+// ---- K3: Metropolis accept + update + history + adaptation statistics ----------------------------------
+struct hb_k3_params {
+  double* X;              // [nc][ldx] updated in place (rows of the local shard)
+  const double* XP;       // [n_local][ldx]
+  const int* id;          // [n_local]
+  const double* lp_xp;    // [n_local]
+  const double* ll_raw;   // [n_local] plugin output before the floor
+  const double* fx_xp;    // [n_local] or nullptr
+  double* lp; double* ll; double* lpost; double* fx;   // [n_local] current values
+  double* lpost_hist_row; // [n_local] row i of the lpost history, or nullptr (i > adapt*t)
+  double* hist_x;         // [n_local][d] slot of stored generation, or nullptr when this generation is not stored
+  double* hist_l;         // [n_local][3]
+  double* hist_fx;        // [n_local] or nullptr
+  uint8_t* accept_rec;    // [n_local] or nullptr
+  hb_ctrl* ctrl;
+  const double* shift;    // [d] column shift for the one-pass variance (previous generation's mean)
+  double* partials;       // [nblocks][(nCR+2)*d] block partial sums (adaptation only) or nullptr
+  long long chain0, n_local, gchain0;
+  int d, ldx, nCR;
+  int adapt;              // generation is inside the adaptation period: accumulate std / jump statistics
+  uint64_t seed;
+  uint32_t gen;
+  const double* u_accept; // tape row (device) or nullptr in Philox mode
+};
+// returns the grid size used (partials rows) through *nblocks_out; query with p.X == nullptr to size buffers
+cudaError_t hb_launch_k3(const hb_k3_params& p, int sm_count, int* nblocks_out, size_t* smem_out, cudaStream_t st);
+int hb_k3_grid(long long n_local, int d, int nCR, int sm_count, size_t* smem_out);
+
+// ---- finalize: fold partials into J / n_id / n_acc, refresh shift, pCR update, AR/CR rows ---------------
+struct hb_fin_params {
+  hb_ctrl* ctrl;
+  const double* partials; int nblocks;
+  double* shift;          // [d]
+  double* colsum;         // [2*d] reduced (sum, sumsq) of the shifted columns -- exposed for multi-GPU all-reduce
+  double* qsum;           // [nCR*d]
+  long long nc;
+  int d, nCR;
+  int adapt;              // accumulate J this generation
+  int do_pcr;             // i <= adapt*t && i %% updateInterval == 0  (R/dream_parallel.R:403-411)
+  int do_arcr;            // i %% updateInterval == 0                  (R/dream_parallel.R:425-433)
+  double* out_ar; double* out_cr; long long ar_rows;   // column-major [ar_rows,2] / [ar_rows,nCR+1]
+  int phase;              // 0: reduce partials -> colsum/qsum ; 1: consume colsum/qsum ; 2: both (single GPU)
+  long long n_eval_inc;   // nc (all ranks)
+};
+cudaError_t hb_launch_finalize(const hb_fin_params& p, cudaStream_t st);
+
+// ---- outlier check pieces (R/internals.R:71-87) ---------------------------------------------------------
+cudaError_t hb_launch_proxy(const double* lpost_hist, long long nc_local, long long row0, long long row1,
+                            long long ld, double* proxy, cudaStream_t st);
+cudaError_t hb_launch_outlier_reset(double* X, int ldx, int d, double* lpost, double* lpost_hist_row,
+                                    const int* outl, const int* news, int n_out, double* scratch, cudaStream_t st);
+
+// ---- history transposition into R's chain[out_t, d+3, nc] layout ----------------------------------------
+cudaError_t hb_launch_chain_transpose(const double* hist_x, const double* hist_l, long long out_t_alloc,
+                                      long long row0, long long nrows, long long rows_filled, long long nct, int d,
+                                      long long c0, long long ncs, double* out, cudaStream_t st);
+
+// ---- K4: Gelman-Rubin (R/gelman_rubin.R:21-56) on history [rows][nct][d] ---------------------------------
+cudaError_t hb_launch_rstat(const double* hist_x, long long t_rows, long long nct_stride, long long c0, long long n,
+                            int d, double* xm_scratch, double* ss_scratch, double* out_d, cudaStream_t st);
+// same on an R-layout array x[t, d, n] (column-major)
+cudaError_t hb_launch_rstat_colmajor(const double* x, long long t, int d, long long n, double* xm_scratch,
+                                     double* ss_scratch, double* out_d, cudaStream_t st);
+
+// initial evaluation helpers
+cudaError_t hb_launch_init_state(const double* lp_in, const double* ll_raw, const double* fx_in, double* lp, double* ll,
+                                 double* lpost, double* fx, double* lpost_hist_row, long long n, unsigned* err,
+                                 cudaStream_t st);
+cudaError_t hb_launch_prior(const double* X, int ldx, int d, long long n, int prior, const double* pmin,
+                            const double* pmax, double* lp, unsigned* err, cudaStream_t st);
+cudaError_t hb_launch_store_row(const double* X, int ldx, int d, long long n, const double* lp, const double* ll,
+                                const double* lpost, const double* fx, double* hist_x, double* hist_l, double* hist_fx,
+                                cudaStream_t st);
+cudaError_t hb_launch_colmajor_to_rows(const double* in_colmajor, long long n_rows_total, long long row0, long long n,
+                                       int d, int ldx, double* out, cudaStream_t st);
+cudaError_t hb_launch_rows_to_colmajor(const double* in, int ldx, int d, long long n, double* out_colmajor,
+                                       cudaStream_t st);
+cudaError_t hb_launch_fill(double* p, long long n, double v, cudaStream_t st);

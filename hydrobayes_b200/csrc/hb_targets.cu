@@ -1,0 +1,493 @@
+// hb_targets.cu -- K2: batched per-chain log-density plugins and the name-keyed registry that replaces
+// get(fun)(x, ...) (R/dream_parallel.R:219-227, 278-287) for the package's own test targets.
+//
+//   "mixture"         R/test_mixture.R:16            fused elementwise kernel (density, then calc_ll lik = 1 -> log)
+//   "t_distribution"  R/test_t_distribution.R:19-46  Z = Xp * W (W = chol(C)^-1, upper triangular) on fp64 tensor
+//                                                    cores (mma.sync m8n8k4 f64 -> SASS DMMA), rss = rowsum(Z o Z),
+//                                                    const - (df+d)/2 * log1p(rss/df) in the epilogue; Z never stored
+//   "HydroModel"      R/test_HydroModel.R:17-36      one chain per thread, forcing + obs staged into shared memory by
+//                                                    a 1-D bulk TMA copy (cp.async.bulk + mbarrier), true fp64
+//                                                    division per step, GLUE likelihood (R/internals.R:13-14) folded
+//
+// Plugins return the value BEFORE the -708.396 floor; the sampler (K3) applies calc_ll's floor and finiteness check.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/hydrobayes_b200.h"
+#include "hb_common.cuh"
+
+namespace {
+
+void set_err(char* err, int errlen, const char* msg) {
+  if (err && errlen > 0) snprintf(err, (size_t)errlen, "%s", msg);
+}
+
+// =========================================== mixture ======================================================
+// R's dnorm4 (nmath/dnorm.c, recollection): plain formula for |z| < 5, split exponent beyond, 0 past ~38.57
+__device__ __forceinline__ double dnorm_r(double x, double mu) {
+  const double M_1_SQRT_2PI_ = 0.398942280401432677939946059934;
+  double z = fabs(x - mu);
+  if (!isfinite(z)) return 0.0;
+  if (z < 5.0) return M_1_SQRT_2PI_ * exp(-0.5 * z * z);
+  if (z > 38.56804181549334) return 0.0;   // sqrt(-2*M_LN2*(DBL_MIN_EXP + 1 - DBL_MANT_DIG))
+  const double x1 = rint(z * 65536.0) * (1.0 / 65536.0);
+  const double x2 = z - x1;
+  return M_1_SQRT_2PI_ * (exp(-0.5 * x1 * x1) * exp((-0.5 * x2 - x1) * x2));
+}
+
+__global__ void hb_mixture_kernel(const double* __restrict__ x, long long n, int ldx, int lik, double* __restrict__ ll,
+                                  double* __restrict__ fx) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const double v = x[j * ldx];
+  const double dens = 1.0 / 6.0 * dnorm_r(v, -8.0) + 5.0 / 6.0 * dnorm_r(v, 10.0);   // R/test_mixture.R:16
+  if (fx) fx[j] = dens;
+  ll[j] = (lik == 1) ? log(dens) : dens;                                               // R/internals.R:4-7
+}
+
+struct mixture_ctx { int lik; };
+
+int mixture_init(void** ctx, int d, int lik, const double*, const int64_t*, int, const double*, int64_t, double,
+                 char* err, int errlen) {
+  if (d != 1) { set_err(err, errlen, "mixture() is a 1-d target (R/test_mixture.R:15)"); return HB_ERR_INVALID; }
+  if (lik != 1 && lik != 2) { set_err(err, errlen, "mixture: lik must be 1 (density) or 2"); return HB_ERR_UNSUPPORTED; }
+  auto* c = new mixture_ctx{lik};
+  *ctx = c;
+  return HB_OK;
+}
+int mixture_launch(void* ctx, const double* x, int64_t n, int d, int ldx, double* ll, double* fx, void* stream) {
+  auto* c = (mixture_ctx*)ctx;
+  if (n <= 0) return HB_OK;
+  hb_mixture_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, n, ldx, c->lik, ll, fx);
+  return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
+}
+void mixture_destroy(void* ctx) { delete (mixture_ctx*)ctx; }
+void mixture_work(void*, int, double* flops, double* bytes) { *flops = 40; *bytes = 16; }
+
+// =========================================== t_distribution ===============================================
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// KB k-blocks of 4, NB = ceil(KB/2) n-blocks of 8.  One warp owns 8 chains per iteration:
+//   A (8x4, row): lane holds X[row = lane>>2][k = 4*kb + (lane&3)]   -- all KB fragments loaded up front (MLP = KB)
+//   B (4x8, col): lane holds W[k = 4*kb + (lane&3)][n = 8*nb + (lane>>2)] from shared memory (2 wavefronts, no conflicts)
+//   C (8x8): lane holds row lane>>2, two columns -> squared and reduced over the 4 lanes of a row group.
+// W is upper triangular (z_n = sum_{k<=n} x_k W[k][n]), so n-block nb only needs k-blocks kb <= 2*nb+1: the fully
+// unrolled loop nest drops the others at compile time (about d^2/2 multiply-adds executed, as backsolve does).
+template <int KB>
+__global__ void __launch_bounds__(128) hb_tdist_dmma_kernel(const double* __restrict__ X, long long n, int d, int ldx,
+                                                            const double* __restrict__ Wg, int ldw, double konst,
+                                                            double df, int lik, double* __restrict__ ll,
+                                                            double* __restrict__ fx) {
+  constexpr int NB = (KB + 1) / 2;
+  extern __shared__ double Ws[];
+  const int n_w = 4 * KB * ldw;
+  for (int i = threadIdx.x; i < n_w; i += blockDim.x) Ws[i] = Wg[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int gid = lane >> 2, tig = lane & 3;
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long n_tiles = (n + 7) / 8;
+  for (long long tile = warp_id; tile < n_tiles; tile += n_warps) {
+    const long long row = tile * 8 + gid;
+    const bool rv = row < n;
+    const double* xr = X + (rv ? row : 0) * (long long)ldx;
+    double a[KB];
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb) {
+      const int k = 4 * kb + tig;
+      a[kb] = (rv && k < d) ? xr[k] : 0.0;
+    }
+    double rss = 0.0;
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) {
+        if (kb <= 2 * nb + 1) {
+          const double b = Ws[(4 * kb + tig) * ldw + 8 * nb + gid];
+          dmma884(c0, c1, a[kb], b);
+        }
+      }
+      rss = fma(c0, c0, rss);
+      rss = fma(c1, c1, rss);
+    }
+    rss += __shfl_xor_sync(0xffffffffu, rss, 1);
+    rss += __shfl_xor_sync(0xffffffffu, rss, 2);
+    if (rv && tig == 0) {
+      const double v = konst - 0.5 * (df + (double)d) * log1p(rss / df);   // dmvt, R/test_t_distribution.R:43
+      if (fx) fx[row] = v;
+      ll[row] = (lik == 1) ? log(v) : v;
+    }
+  }
+}
+
+// generic FMA path for d > 128 (and the cross-check of the DMMA kernel in the tests): one warp per chain
+__global__ void hb_tdist_fma_kernel(const double* __restrict__ X, long long n, int d, int ldx,
+                                    const double* __restrict__ Wg, int ldw, double konst, double df, int lik,
+                                    double* __restrict__ ll, double* __restrict__ fx) {
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (long long row = warp_id; row < n; row += n_warps) {
+    const double* xr = X + row * (long long)ldx;
+    double rss = 0.0;
+    for (int nn = lane; nn < d; nn += 32) {
+      double z = 0.0;
+      for (int k = 0; k <= nn; ++k) z = fma(xr[k], Wg[k * ldw + nn], z);
+      rss = fma(z, z, rss);
+    }
+    rss = hb_warp_sum(rss);
+    if (lane == 0) {
+      const double v = konst - 0.5 * (df + (double)d) * log1p(rss / df);
+      if (fx) fx[row] = v;
+      ll[row] = (lik == 1) ? log(v) : v;
+    }
+  }
+}
+
+struct tdist_ctx {
+  int d, lik, KB, ldw;
+  double konst, df;
+  double* W_dev;
+  int sm_count;
+  int force_fma;
+};
+
+// C = (0.5 I + 0.5) o sqrt(i j); R = chol(C) (upper); W = R^-1; all in long double, rounded once
+int tdist_build(int d, std::vector<double>& W, int kp, int ldw, double* konst) {
+  const double df = 60.0;
+  std::vector<long double> C((size_t)d * d), R((size_t)d * d, 0.0L), Wi((size_t)d * d, 0.0L);
+  for (int i = 1; i <= d; ++i)
+    for (int j = 1; j <= d; ++j) C[(size_t)(i - 1) * d + (j - 1)] = (i == j ? 1.0L : 0.5L) * sqrtl((long double)i * j);
+  for (int j = 0; j < d; ++j) {
+    long double s = C[(size_t)j * d + j];
+    for (int k = 0; k < j; ++k) s -= R[(size_t)k * d + j] * R[(size_t)k * d + j];
+    if (!(s > 0)) return -1;
+    const long double rjj = sqrtl(s);
+    R[(size_t)j * d + j] = rjj;
+    for (int i = j + 1; i < d; ++i) {
+      long double v = C[(size_t)j * d + i];
+      for (int k = 0; k < j; ++k) v -= R[(size_t)k * d + j] * R[(size_t)k * d + i];
+      R[(size_t)j * d + i] = v / rjj;
+    }
+  }
+  // W = R^-1 (upper): back substitution column by column
+  for (int j = 0; j < d; ++j) {
+    Wi[(size_t)j * d + j] = 1.0L / R[(size_t)j * d + j];
+    for (int i = j - 1; i >= 0; --i) {
+      long double s = 0;
+      for (int k = i + 1; k <= j; ++k) s += R[(size_t)i * d + k] * Wi[(size_t)k * d + j];
+      Wi[(size_t)i * d + j] = -s / R[(size_t)i * d + i];
+    }
+  }
+  W.assign((size_t)kp * ldw, 0.0);
+  for (int k = 0; k < d; ++k)
+    for (int nn = k; nn < d; ++nn) W[(size_t)k * ldw + nn] = (double)Wi[(size_t)k * d + nn];
+  long double sl = 0;
+  for (int i = 0; i < d; ++i) sl += logl(R[(size_t)i * d + i]);
+  *konst = lgamma((d + df) / 2) - (lgamma(df / 2) + (double)sl + d / 2.0 * log(3.141592653589793238462643383279502884 * df));
+  return 0;
+}
+
+const int kKB[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 13, 16, 20, 25, 32};
+
+int tdist_init(void** ctx, int d, int lik, const double*, const int64_t*, int, const double*, int64_t, double, char* err,
+               int errlen) {
+  if (lik != 2 && lik != 1) { set_err(err, errlen, "t_distribution returns a log-density: use lik = 2"); return HB_ERR_UNSUPPORTED; }
+  auto* c = new tdist_ctx();
+  c->d = d; c->lik = lik; c->df = 60.0; c->force_fma = 0;
+  const int kb_need = (d + 3) / 4;
+  c->KB = 0;
+  for (int v : kKB) if (v >= kb_need) { c->KB = v; break; }
+  const int kp = c->KB ? 4 * c->KB : d;
+  int np = c->KB ? 8 * ((c->KB + 1) / 2) : d;
+  c->ldw = (np % 16 == 8) ? np : np + 8;                    // ldw == 8 (mod 16): conflict-free B-fragment reads
+  if (!c->KB) c->ldw = d;
+  std::vector<double> W;
+  if (tdist_build(d, W, kp, c->ldw, &c->konst)) { delete c; set_err(err, errlen, "chol(C) failed"); return HB_ERR_INVALID; }
+  if (cudaMalloc(&c->W_dev, W.size() * sizeof(double)) != cudaSuccess ||
+      cudaMemcpy(c->W_dev, W.data(), W.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+    delete c; set_err(err, errlen, "cudaMalloc/cudaMemcpy failed for W"); return HB_ERR_CUDA;
+  }
+  int dev = 0; cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  const char* f = getenv("HB_TDIST_FORCE_FMA");
+  if (f && f[0] == '1') c->force_fma = 1;
+  *ctx = c;
+  return HB_OK;
+}
+
+template <int KB>
+int tdist_launch_kb(tdist_ctx* c, const double* x, int64_t n, int ldx, double* ll, double* fx, cudaStream_t st) {
+  const size_t smem = (size_t)4 * KB * c->ldw * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set && smem > 48 * 1024) {
+    if (cudaFuncSetAttribute(hb_tdist_dmma_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return HB_ERR_CUDA;
+    attr_set = true;
+  }
+  const long long tiles = (n + 7) / 8;
+  long long blocks = (tiles + 3) / 4;
+  const long long cap = (long long)c->sm_count * 2;
+  if (blocks > cap) blocks = cap;
+  hb_tdist_dmma_kernel<KB><<<(unsigned)blocks, 128, smem, st>>>(x, n, c->d, ldx, c->W_dev, c->ldw, c->konst, c->df,
+                                                                c->lik, ll, fx);
+  return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
+}
+
+int tdist_launch(void* ctx, const double* x, int64_t n, int d, int ldx, double* ll, double* fx, void* stream) {
+  auto* c = (tdist_ctx*)ctx;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 0) return HB_OK;
+  if (!c->KB || c->force_fma) {
+    long long blocks = (n + 3) / 4;
+    const long long cap = (long long)c->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    hb_tdist_fma_kernel<<<(unsigned)blocks, 128, 0, st>>>(x, n, c->d, ldx, c->W_dev, c->ldw, c->konst, c->df, c->lik, ll, fx);
+    return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
+  }
+  switch (c->KB) {
+#define HB_KB_CASE(K) case K: return tdist_launch_kb<K>(c, x, n, ldx, ll, fx, st);
+    HB_KB_CASE(1) HB_KB_CASE(2) HB_KB_CASE(3) HB_KB_CASE(4) HB_KB_CASE(5) HB_KB_CASE(6) HB_KB_CASE(7) HB_KB_CASE(8)
+    HB_KB_CASE(10) HB_KB_CASE(13) HB_KB_CASE(16) HB_KB_CASE(20) HB_KB_CASE(25) HB_KB_CASE(32)
+#undef HB_KB_CASE
+  }
+  return HB_ERR_INVALID;
+}
+void tdist_destroy(void* ctx) {
+  auto* c = (tdist_ctx*)ctx;
+  if (c) { cudaFree(c->W_dev); delete c; }
+}
+void tdist_work(void*, int d, double* flops, double* bytes) { *flops = (double)d * d + 3.0 * d; *bytes = 8.0 * d + 8; }
+
+// =========================================== HydroModel ====================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// 1-D bulk TMA copy global -> shared, completion on an mbarrier (SASS: UBLKCP.S.G + SYNCS.*)
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// One chain per thread.  P and obs (T_pad doubles each, T_pad even so that the byte count is a multiple of 16) are
+// staged once per CTA.  Per step (R/test_HydroModel.R:30-32): S = (P_i*Dt + S)/(1 + K*Dt), Y_i = K*S with Dt = 1, a
+// true IEEE division.  lik == 31 (R/internals.R:13-14): glue_shape*log(max(1 - sse/sst, 0)); sse is Kahan-summed.
+__global__ void __launch_bounds__(256) hb_hydro_kernel(const double* __restrict__ X, long long n, int ldx,
+                                                       const double* __restrict__ forcing,
+                                                       const double* __restrict__ obs, int T, int T_pad, double sst,
+                                                       double glue_shape, double* __restrict__ ll, unsigned* err) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ __align__(8) uint64_t bar;
+  double* sP = sm;
+  double* sO = sm + T_pad;
+  const uint32_t bytes = (uint32_t)T_pad * 8u;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar, 2 * bytes);
+    tma_load_1d(sP, forcing, bytes, &bar);
+    tma_load_1d(sO, obs, bytes, &bar);
+  }
+  mbar_wait(&bar, 0);
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const double K = X[j * ldx];
+  if (K < 0) { atomicOr(err, HB_FLAG_TARGET_DOMAIN); ll[j] = NAN; return; }   // R/test_HydroModel.R:18-19
+  const double den = 1.0 + K * 1.0;
+  double S = 1.0, sse = 0.0, comp = 0.0;
+#pragma unroll 4
+  for (int i = 0; i < T; ++i) {
+    S = __ddiv_rn(sP[i] * 1.0 + S, den);
+    const double e = K * S - sO[i];
+    const double y = e * e - comp;
+    const double t = sse + y;
+    comp = (t - sse) - y;
+    sse = t;
+  }
+  const double nse = 1.0 - sse / sst;
+  ll[j] = glue_shape * log(nse > 0.0 ? nse : 0.0);
+}
+
+// full series for parity tests of the model itself: out [n][T]
+__global__ void hb_hydro_series_kernel(const double* __restrict__ param, long long n, const double* __restrict__ forcing,
+                                       int T, double* __restrict__ out) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const double K = param[j];
+  const double den = 1.0 + K * 1.0;
+  double S = 1.0;
+  for (int i = 0; i < T; ++i) {
+    S = __ddiv_rn(forcing[i] * 1.0 + S, den);
+    out[j * (long long)T + i] = K * S;
+  }
+}
+
+struct hydro_ctx {
+  int T, T_pad, lik;
+  double sst, glue_shape;
+  double* forcing_dev;
+  double* obs_dev;
+  unsigned* err_dev;
+};
+
+int hydro_init(void** ctx, int d, int lik, const double* data, const int64_t* dims, int ndims, const double* obs,
+               int64_t n_obs, double glue_shape, char* err, int errlen) {
+  if (d != 1) { set_err(err, errlen, "HydroModel(forcing, param) has one parameter (R/test_HydroModel.R:17)"); return HB_ERR_INVALID; }
+  if (lik != 31) { set_err(err, errlen, "HydroModel on the device folds the GLUE likelihood: use lik = 31"); return HB_ERR_UNSUPPORTED; }
+  if (!data || ndims < 1 || dims[0] < 1) { set_err(err, errlen, "HydroModel needs the forcing series"); return HB_ERR_INVALID; }
+  const int64_t T = dims[0];
+  if (!obs || n_obs != T) { set_err(err, errlen, "lik = 31 needs obs of the same length as forcing"); return HB_ERR_INVALID; }
+  for (int64_t i = 0; i < T; ++i)
+    if (data[i] < 0) { set_err(err, errlen, "Values of argument 'forcing' need to be >= zero!"); return HB_ERR_INVALID; }  // :20-21
+  if ((size_t)(T + 1) * 16 > 220 * 1024) { set_err(err, errlen, "forcing series too long for shared-memory staging"); return HB_ERR_UNSUPPORTED; }
+  auto* c = new hydro_ctx();
+  c->T = (int)T; c->T_pad = (int)((T + 1) & ~1LL); c->lik = lik; c->glue_shape = glue_shape;
+  // sum((obs - mean(obs))^2) with R's long-double mean refinement (summary.c, recollection)
+  long double s = 0;
+  for (int64_t i = 0; i < T; ++i) s += obs[i];
+  s /= T;
+  long double r = 0;
+  for (int64_t i = 0; i < T; ++i) r += (obs[i] - s);
+  s += r / T;
+  const double mo = (double)s;
+  long double q = 0;
+  for (int64_t i = 0; i < T; ++i) { const double e = obs[i] - mo; q += (long double)(e * e); }
+  c->sst = (double)q;
+  std::vector<double> buf((size_t)c->T_pad, 0.0);
+  bool ok = cudaMalloc(&c->forcing_dev, sizeof(double) * c->T_pad) == cudaSuccess &&
+            cudaMalloc(&c->obs_dev, sizeof(double) * c->T_pad) == cudaSuccess &&
+            cudaMalloc(&c->err_dev, sizeof(unsigned)) == cudaSuccess;
+  if (ok) {
+    memcpy(buf.data(), data, sizeof(double) * T);
+    ok = cudaMemcpy(c->forcing_dev, buf.data(), sizeof(double) * c->T_pad, cudaMemcpyHostToDevice) == cudaSuccess;
+    memcpy(buf.data(), obs, sizeof(double) * T);
+    ok = ok && cudaMemcpy(c->obs_dev, buf.data(), sizeof(double) * c->T_pad, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMemset(c->err_dev, 0, sizeof(unsigned)) == cudaSuccess;
+  }
+  if (!ok) { set_err(err, errlen, "cudaMalloc/cudaMemcpy failed for forcing/obs"); delete c; return HB_ERR_CUDA; }
+  const size_t smem = (size_t)2 * c->T_pad * sizeof(double);
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(hb_hydro_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    set_err(err, errlen, "cudaFuncSetAttribute failed"); delete c; return HB_ERR_CUDA;
+  }
+  *ctx = c;
+  return HB_OK;
+}
+int hydro_launch(void* ctx, const double* x, int64_t n, int d, int ldx, double* ll, double* fx, void* stream) {
+  auto* c = (hydro_ctx*)ctx;
+  (void)fx;  // the raw series (3653 values per chain) is folded on the device, SURVEY 7.2 item 7
+  if (n <= 0) return HB_OK;
+  const size_t smem = (size_t)2 * c->T_pad * sizeof(double);
+  const int threads = n >= 65536 ? 256 : 128;
+  hb_hydro_kernel<<<(unsigned)((n + threads - 1) / threads), threads, smem, (cudaStream_t)stream>>>(
+      x, n, ldx, c->forcing_dev, c->obs_dev, c->T, c->T_pad, c->sst, c->glue_shape, ll, c->err_dev);
+  return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
+}
+void hydro_destroy(void* ctx) {
+  auto* c = (hydro_ctx*)ctx;
+  if (c) { cudaFree(c->forcing_dev); cudaFree(c->obs_dev); cudaFree(c->err_dev); delete c; }
+}
+void hydro_work(void* ctx, int, double* flops, double* bytes) {
+  auto* c = (hydro_ctx*)ctx;
+  *flops = 5.0 * (c ? c->T : 0); *bytes = 16;
+}
+
+// =========================================== registry =====================================================
+std::mutex g_mu;
+std::vector<hb_target_vtable>& registry() {
+  static std::vector<hb_target_vtable> r = {
+      {"mixture", mixture_init, mixture_launch, mixture_destroy, mixture_work},
+      {"t_distribution", tdist_init, tdist_launch, tdist_destroy, tdist_work},
+      {"HydroModel", hydro_init, hydro_launch, hydro_destroy, hydro_work},
+  };
+  return r;
+}
+std::vector<std::string>& owned_names() { static std::vector<std::string> v; return v; }
+
+}  // namespace
+
+const hb_target_vtable* hb_find_target(const char* name) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto& v : registry())
+    if (name && strcmp(v.name, name) == 0) return &v;
+  return nullptr;
+}
+
+// HydroModel's domain check lives in its own context (the sampler polls it through this hook)
+unsigned hb_hydro_poll_err(void* ctx) {
+  auto* c = (hydro_ctx*)ctx;
+  unsigned v = 0;
+  if (c && cudaMemcpy(&v, c->err_dev, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  return v;
+}
+
+extern "C" int hb_register_target(const hb_target_vtable* vt) {
+  if (!vt || !vt->name || !vt->init || !vt->launch || !vt->destroy) return HB_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto& v : registry())
+    if (strcmp(v.name, vt->name) == 0) return HB_ERR_INVALID;
+  owned_names().reserve(64);
+  owned_names().emplace_back(vt->name);
+  hb_target_vtable c = *vt;
+  c.name = owned_names().back().c_str();
+  registry().push_back(c);
+  return HB_OK;
+}
+
+extern "C" int hb_target_registered(const char* name) { return hb_find_target(name) != nullptr; }
+
+extern "C" int hb_hydromodel_series(const double* forcing, int64_t T, const double* param, int64_t n, double* out,
+                                    char* err, int errlen) {
+  if (!forcing || !param || !out || T < 1 || n < 1) { set_err(err, errlen, "bad arguments"); return HB_ERR_INVALID; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_err(err, errlen, "no CUDA device (there is no CPU fallback)"); return HB_ERR_NO_DEVICE; }
+  for (int64_t i = 0; i < n; ++i) if (param[i] < 0) { set_err(err, errlen, "Argument 'param' has to be >= zero!"); return HB_ERR_INVALID; }
+  for (int64_t i = 0; i < T; ++i) if (forcing[i] < 0) { set_err(err, errlen, "Values of argument 'forcing' need to be >= zero!"); return HB_ERR_INVALID; }
+  double *f = nullptr, *p = nullptr, *o = nullptr;
+  bool ok = cudaMalloc(&f, sizeof(double) * T) == cudaSuccess && cudaMalloc(&p, sizeof(double) * n) == cudaSuccess &&
+            cudaMalloc(&o, sizeof(double) * n * T) == cudaSuccess;
+  ok = ok && cudaMemcpy(f, forcing, sizeof(double) * T, cudaMemcpyHostToDevice) == cudaSuccess &&
+       cudaMemcpy(p, param, sizeof(double) * n, cudaMemcpyHostToDevice) == cudaSuccess;
+  if (ok) {
+    hb_hydro_series_kernel<<<(unsigned)((n + 127) / 128), 128>>>(p, n, f, (int)T, o);
+    ok = cudaGetLastError() == cudaSuccess &&
+         cudaMemcpy(out, o, sizeof(double) * n * T, cudaMemcpyDeviceToHost) == cudaSuccess;
+  }
+  cudaFree(f); cudaFree(p); cudaFree(o);
+  if (!ok) { set_err(err, errlen, cudaGetErrorString(cudaGetLastError())); return HB_ERR_CUDA; }
+  return HB_OK;
+}

@@ -1,0 +1,380 @@
+"""Host-side mirror of HydroBayes' R API on top of the C ABI (include/hydrobayes_b200.h).
+
+``dream_parallel`` / ``dream`` / ``R_stat`` keep the formals, defaults, error behaviour and return structures of
+R/dream_parallel.R:155-163, R/dream.R:126-133 and R/gelman_rubin.R:21; new optional arguments come last and default
+to the reference behaviour.  The thin R drivers that a HydroBayes maintainer would ship are in r-package/ (R is not
+installed in the build image, so this Python mirror is what the parity tests drive).
+
+Everything numerical happens in libhydrobayes_b200.so on the GPU; nothing here computes a proposal, a density or an
+acceptance on the CPU, and there is no fallback when the library or a device is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from typing import Optional
+
+import numpy as np
+
+from . import _abi as A
+
+_dp = C.POINTER(C.c_double)
+
+_PRIOR = {"flat": A.HB_PRIOR_FLAT, "uniform": A.HB_PRIOR_UNIFORM, "normal": A.HB_PRIOR_NORMAL}
+_BOUND = {None: A.HB_BOUND_NONE, "bound": A.HB_BOUND_BOUND, "reflect": A.HB_BOUND_REFLECT, "fold": A.HB_BOUND_FOLD}
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+class Sampler:
+    """Owns an ``hb_handle``.  Thin: every method is one C-ABI call."""
+
+    def __init__(self, cfg: A.HbConfig, device: int = 0):
+        self.L = A.lib()
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        rc = self.L.hb_create(C.byref(cfg), device, C.byref(self.h))
+        if rc != A.HB_OK:
+            raise A.HbError(rc, self.L.hb_last_error(None).decode())
+        self._keep = []
+
+    def _check(self, rc):
+        if rc != A.HB_OK:
+            raise A.HbError(rc, self.L.hb_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            self.L.hb_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- configuration --------------------------------------------------------------------------------
+    def set_bounds(self, par_min, par_max):
+        mn = np.ascontiguousarray(np.atleast_1d(np.asarray(par_min, np.float64)))
+        mx = np.ascontiguousarray(np.atleast_1d(np.asarray(par_max, np.float64)))
+        if mn.size != mx.size:
+            raise ValueError("min and max must have the same length")
+        self._check(self.L.hb_set_bounds(self.h, _ptr(mn), _ptr(mx), int(mn.size)))
+
+    def set_obs(self, obs):
+        o = np.ascontiguousarray(np.asarray(obs, np.float64))
+        self._check(self.L.hb_set_obs(self.h, _ptr(o), o.size))
+
+    def set_target(self, name: str, data=None):
+        if data is None:
+            self._check(self.L.hb_set_target(self.h, name.encode(), None, None, 0))
+        else:
+            a = np.ascontiguousarray(np.asarray(data, np.float64))
+            dims = (C.c_int64 * max(a.ndim, 1))(*(a.shape if a.ndim else (1,)))
+            self._check(self.L.hb_set_target(self.h, name.encode(), _ptr(a), dims, max(a.ndim, 1)))
+
+    def set_initial(self, x0):
+        d = self.cfg.d
+        x = np.asfortranarray(np.asarray(x0, np.float64).reshape(-1, d))
+        self._check(self.L.hb_set_initial(self.h, x.ctypes.data_as(_dp)))
+
+    def set_tape(self, tape_struct: A.HbTape, keepalive=None):
+        self._keep.append(keepalive)
+        self._check(self.L.hb_set_tape(self.h, C.byref(tape_struct)))
+
+    def comm_init(self, rank: int, world: int, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, 128)
+        self._check(self.L.hb_comm_init(self.h, rank, world, buf))
+
+    # -- run ------------------------------------------------------------------------------------------
+    def run(self, n_generations: int) -> int:
+        done = C.c_int64()
+        self._check(self.L.hb_run(self.h, int(n_generations), C.byref(done)))
+        return done.value
+
+    def profile(self, enable: bool):
+        self._check(self.L.hb_profile(self.h, int(enable)))
+
+    def kernel_ms(self, name: str):
+        ms = C.c_double(); n = C.c_int64()
+        self._check(self.L.hb_get_kernel_ms(self.h, name.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def timing(self):
+        ms = C.c_double(); n = C.c_int64()
+        self._check(self.L.hb_get_timing(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    # -- results --------------------------------------------------------------------------------------
+    def out_dims(self):
+        v = [C.c_int64() for _ in range(7)]
+        self._check(self.L.hb_out_dims(self.h, *[C.byref(x) for x in v]))
+        return dict(zip(("out_t", "ar_rows", "ar_cols", "cr_rows", "cr_cols", "fx_m", "rstat_rows"), (x.value for x in v)))
+
+    def ind_out(self) -> int:
+        return self.L.hb_ind_out(self.h)
+
+    def n_local(self) -> int:
+        return self.cfg.nc  # single-GPU; sharded handles override through ShardedSampler
+
+    def fetch_chain(self, n_chains: Optional[int] = None) -> np.ndarray:
+        dm = self.out_dims()
+        n = n_chains or self.n_local()
+        out = np.empty((dm["out_t"], self.cfg.d + 3, n), order="F")
+        self._check(self.L.hb_fetch_chain(self.h, _ptr(out)))
+        return out
+
+    def fetch_chain_rows(self, row0: int, nrows: int, n_chains: Optional[int] = None) -> np.ndarray:
+        n = n_chains or self.n_local()
+        out = np.empty((nrows, self.cfg.d + 3, n), order="F")
+        self._check(self.L.hb_fetch_chain_rows(self.h, row0, nrows, _ptr(out)))
+        return out
+
+    def fetch_fx(self, n_chains: Optional[int] = None) -> np.ndarray:
+        dm = self.out_dims()
+        n = n_chains or self.n_local()
+        out = np.empty((dm["out_t"], n, 1), order="F")
+        self._check(self.L.hb_fetch_fx(self.h, _ptr(out)))
+        return out
+
+    def fetch_ar_cr(self):
+        dm = self.out_dims()
+        ar = np.empty((dm["ar_rows"], dm["ar_cols"]), order="F")
+        cr = np.empty((dm["cr_rows"], dm["cr_cols"]), order="F")
+        self._check(self.L.hb_fetch_ar(self.h, _ptr(ar)))
+        self._check(self.L.hb_fetch_cr(self.h, _ptr(cr)))
+        return ar, cr
+
+    def fetch_rstat(self) -> np.ndarray:
+        dm = self.out_dims()
+        out = np.empty((dm["rstat_rows"], self.cfg.d), order="F")
+        self._check(self.L.hb_fetch_rstat(self.h, _ptr(out)))
+        return out
+
+    def fetch_state(self, n_chains: Optional[int] = None):
+        nc, d = self.cfg.nc, self.cfg.d
+        n = n_chains or self.n_local()
+        xt = np.empty((nc, d), order="F")
+        lp = np.empty(n); ll = np.empty(n); lpost = np.empty(n)
+        self._check(self.L.hb_fetch_state(self.h, _ptr(xt), _ptr(lp), _ptr(ll), _ptr(lpost)))
+        return xt, lp, ll, lpost
+
+    def fetch_accept(self, n_chains: Optional[int] = None) -> np.ndarray:
+        n = n_chains or self.n_local()
+        out = np.zeros((self.cfg.t - 1, n), np.uint8)
+        self._check(self.L.hb_fetch_accept(self.h, out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
+
+    def fetch_outliers(self):
+        n = C.c_int64()
+        self._check(self.L.hb_fetch_outliers(self.h, C.byref(n), None, None, 0))
+        g = np.zeros(max(n.value, 1), np.int64); c = np.zeros(max(n.value, 1), np.int64)
+        i64 = C.POINTER(C.c_int64)
+        self._check(self.L.hb_fetch_outliers(self.h, C.byref(n), g.ctypes.data_as(i64), c.ctypes.data_as(i64), n.value))
+        return list(zip(g[:n.value].tolist(), c[:n.value].tolist()))
+
+    def rstat(self) -> np.ndarray:
+        out = np.empty(self.cfg.d)
+        self._check(self.L.hb_rstat(self.h, _ptr(out)))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# prior_sample (R/internals.R:26-47) stays on the host, exactly as it would in the R driver
+# ---------------------------------------------------------------------------------------------------------
+def prior_sample(par_info: dict, d: int, nc: int, rng: Optional[np.random.Generator] = None) -> np.ndarray:
+    rng = rng or np.random.default_rng()
+    initial = par_info.get("initial")
+    if initial == "uniform":
+        mn = np.broadcast_to(np.asarray(par_info["min"], float), (d,))
+        mx = np.broadcast_to(np.asarray(par_info["max"], float), (d,))
+        xt = rng.uniform(mn, mx, size=(nc, d))                         # :29
+    elif initial == "normal":
+        xt = rng.multivariate_normal(np.asarray(par_info["mu"], float), np.asarray(par_info["cov"], float), size=nc)  # :32
+    elif initial == "latin":
+        mn = np.broadcast_to(np.asarray(par_info["min"], float), (d,))
+        mx = np.broadcast_to(np.asarray(par_info["max"], float), (d,))
+        # lhs::randomLHS: one stratum per point and dimension, uniformly inside the stratum (:34-35)
+        u = (np.stack([rng.permutation(nc) for _ in range(d)], axis=1) + rng.uniform(size=(nc, d))) / nc
+        xt = mn + (mx - mn) * u
+    elif initial == "user":
+        xt = np.asarray(par_info["val_ini"], float)                    # :38
+    else:
+        raise ValueError("Value 'initial' of argument list 'par.info' must be one of "
+                         "{'uniform', 'normal', 'latin', 'user'}!")     # :40
+    return np.asarray(xt, float).reshape(-1, d)                        # :42-43
+
+
+def _make_config(sweep, lik, par_info, nc, t, d, burnin, adapt, updateInterval, delta, c_val, c_star, nCR, p_g, beta0,
+                 thin, outlier_check, glue_shape, past_sample, m0, archive_update, psnooker, mt, checkConvergence,
+                 seed, tape, record_accept, store_fx, default_prior) -> A.HbConfig:
+    if lik is None:
+        raise ValueError("Argument 'lik' has to be one of {1,2,21,22}!")  # calc_ll with lik = NULL errors in R
+    prior = par_info.get("prior", default_prior)
+    if prior not in _PRIOR:
+        raise A.HbError(A.HB_ERR_UNSUPPORTED, f"prior = {prior!r}: user prior functions are R closures and stay off "
+                                              "the device path")
+    bound = par_info.get("bound")
+    if bound not in _BOUND:
+        raise ValueError("Value 'bound' of argument list 'par.info' must be one of {'bound', 'reflect', 'fold'}!")
+    return A.default_config(
+        sweep=sweep, nc=int(nc), t=int(t), d=int(d), lik=int(lik), burnin=float(burnin), adapt=float(adapt),
+        update_interval=int(updateInterval), delta=int(delta), c_val=float(c_val), c_star=float(c_star), nCR=int(nCR),
+        thin=int(thin), p_g=float(p_g), beta0=float(beta0), outlier_check=int(bool(outlier_check)),
+        prior=_PRIOR[prior], bound=_BOUND[bound], past_sample=int(bool(past_sample)),
+        m0=int(m0) if m0 is not None else 0, archive_update=int(archive_update) if archive_update is not None else 0,
+        mt=int(mt), psnooker=float(psnooker), glue_shape=float(glue_shape) if glue_shape is not None else 0.0,
+        rng_mode=A.HB_RNG_TAPE if tape is not None else A.HB_RNG_PHILOX,
+        seed=int(seed) if seed is not None else 1312, record_accept=int(bool(record_accept)),
+        check_convergence=int(bool(checkConvergence)), store_fx=int(bool(store_fx)))
+
+
+def _drive(sweep, fun, extra, lik, par_info, nc, t, d, burnin, adapt, updateInterval, delta, c_val, c_star, nCR, p_g,
+           beta0, thin, outlier_check, obs, abc_rho, abc_e, glue_shape, lik_fun, past_sample, m0, archive_update,
+           psnooker, mt, checkConvergence, verbose, seed, tape, device, record_accept, store_fx, slice_generations,
+           default_prior, forcing):
+    if not isinstance(fun, str):
+        raise A.HbError(A.HB_ERR_UNKNOWN_TARGET, "fun must be the NAME of a registered device target "
+                                                 "(arbitrary closures stay off the GPU path)")
+    par_info = dict(par_info or {})
+    timea = time.time()
+    cfg = _make_config(sweep, lik, par_info, nc, t, d, burnin, adapt, updateInterval, delta, c_val, c_star, nCR, p_g,
+                       beta0, thin, outlier_check, glue_shape, past_sample, m0, archive_update, psnooker, mt,
+                       checkConvergence, seed, tape, record_accept, store_fx and fun != "HydroModel", default_prior)
+    rng = np.random.default_rng(seed)
+    n0 = (m0 if m0 is not None else 10 * d) if past_sample else nc
+    with Sampler(cfg, device) as s:
+        if par_info.get("min") is not None and par_info.get("max") is not None:
+            s.set_bounds(par_info["min"], par_info["max"])
+        if obs is not None:
+            s.set_obs(obs)
+        data = forcing if forcing is not None else (extra[0] if extra else None)
+        s.set_target(fun, data)
+        x0 = prior_sample(par_info, d, n0, rng)
+        if x0.shape[0] != n0:
+            raise ValueError(f"initial sample has {x0.shape[0]} rows, expected {n0}")
+        s.set_initial(x0)
+        if tape is not None:
+            s.set_tape(tape.struct(), keepalive=tape)
+        step = int(slice_generations) if slice_generations else (max(1, t // 50) if verbose else t)
+        done = 1
+        while done < t:
+            done = s.run(step)          # the R driver ticks txtProgressBar / checks interrupts between slices
+        chain = s.fetch_chain()
+        ar, cr = s.fetch_ar_cr()
+        out = {"chain": chain}
+        names = par_info.get("names") or [f"par{k + 1}" for k in range(d)]
+        out["chain_colnames"] = list(names) + ["lp", "ll", "lpost"]
+        out["fx"] = s.fetch_fx() if cfg.store_fx else None
+        pairs = s.fetch_outliers()
+        out["outlier"] = _outlier_list(pairs, cfg, sweep)
+        out["AR"] = ar
+        out["CR"] = cr
+        if sweep == A.HB_SWEEP_SYNCHRONOUS:
+            out["AR_colnames"] = ["n_eval", "accepted"]
+        if checkConvergence:
+            out["R_stat"] = s.fetch_rstat()
+        if record_accept:
+            out["accept"] = s.fetch_accept()
+        loop_ms, launches = s.timing()
+        out["device_loop_seconds"] = loop_ms * 1e-3
+        out["gpu_launches"] = launches
+    out["runtime"] = time.time() - timea
+    return out
+
+
+def _outlier_list(pairs, cfg, sweep):
+    """R: outl[[i]] <- check_out$outliers (integer(0) when none); entries of other generations stay NULL."""
+    last = 0
+    i = cfg.update_interval
+    checks = []
+    while i <= cfg.adapt * cfg.t and i <= cfg.t:
+        checks.append(i)
+        i += cfg.update_interval
+    if not cfg.outlier_check or cfg.past_sample or not checks:
+        return [None]
+    last = checks[-1]
+    lst = [None] * last
+    for g in checks:
+        lst[g - 1] = np.array([c for (gg, c) in pairs if gg == g], dtype=np.int64)
+    return lst
+
+
+def dream_parallel(fun, *extra, lik=None, par_info=None, nc, t, d, burnin=0, adapt=0.1, updateInterval=10, delta=3,
+                   c_val=0.1, c_star=1e-12, nCR=3, p_g=0.2, beta0=1, thin=1, outlier_check=True, obs=None, abc_rho=None,
+                   abc_e=None, glue_shape=None, lik_fun=None, past_sample=False, m0=None, archive_update=None,
+                   psnooker=0, mt=1, ncores=1, checkConvergence=False, verbose=True,
+                   seed=None, tape=None, device=0, record_accept=False, store_fx=True, slice_generations=None,
+                   forcing=None):
+    """DREAM, synchronous population sweep -- drop-in for HydroBayes::dream_parallel (R/dream_parallel.R:155-455).
+
+    ``fun`` is the name of a registered device target ("mixture", "t_distribution", "HydroModel").  ``ncores`` is
+    accepted and ignored.  Chain indices in ``outlier`` are 0-based.
+    """
+    return _drive(A.HB_SWEEP_SYNCHRONOUS, fun, extra, lik, par_info, nc, t, d, burnin, adapt, updateInterval, delta,
+                  c_val, c_star, nCR, p_g, beta0, thin, outlier_check, obs, abc_rho, abc_e, glue_shape, lik_fun,
+                  past_sample, m0, archive_update, psnooker, mt, checkConvergence, verbose, seed, tape, device,
+                  record_accept, store_fx, slice_generations, "flat", forcing)
+
+
+def dream(fun, *extra, lik=None, par_info=None, nc, t, d, burnin=0, adapt=0.1, updateInterval=10, delta=3, c_val=0.1,
+          c_star=1e-12, nCR=3, p_g=0.2, beta0=1, thin=1, outlier_check=True, obs=None, abc_rho=None, abc_e=None,
+          glue_shape=None, lik_fun=None, checkConvergence=False, verbose=True,
+          seed=None, tape=None, device=0, record_accept=False, store_fx=True, slice_generations=None, forcing=None):
+    """DREAM, sequential chain sweep -- drop-in for HydroBayes::dream (R/dream.R:126-316)."""
+    return _drive(A.HB_SWEEP_SEQUENTIAL, fun, extra, lik, par_info, nc, t, d, burnin, adapt, updateInterval, delta,
+                  c_val, c_star, nCR, p_g, beta0, thin, outlier_check, obs, abc_rho, abc_e, glue_shape, lik_fun,
+                  False, None, None, 0, 1, checkConvergence, verbose, seed, tape, device, record_accept, store_fx,
+                  slice_generations, "uniform", forcing)
+
+
+def R_stat(x) -> np.ndarray:
+    """Gelman-Rubin diagnostic of x[samples, parameters, chains] -- drop-in for R_stat (R/gelman_rubin.R:21)."""
+    x = np.asfortranarray(np.asarray(x, np.float64))
+    if x.ndim != 3:
+        raise ValueError("x must be a 3-d array [samples, parameters, chains]")
+    t, d, n = x.shape
+    out = np.empty(d)
+    err = C.create_string_buffer(256)
+    rc = A.lib().hb_rstat_array(x.ctypes.data_as(_dp), t, d, n, _ptr(out), err, 256)
+    if rc != A.HB_OK:
+        raise A.HbError(rc, err.value.decode())
+    return out
+
+
+def log_density(fun: str, x, lik: int, forcing=None, obs=None, glue_shape: float = 0.0):
+    """calc_ll(get(fun)(x_i, ...), lik, obs, glue_shape) for the rows of x on the device (R/internals.R:3-23)."""
+    x = np.atleast_2d(np.asarray(x, np.float64))
+    n, d = x.shape
+    xf = np.asfortranarray(x)
+    ll = np.empty(n); fx = np.empty(n)
+    err = C.create_string_buffer(256)
+    data = None if forcing is None else np.ascontiguousarray(np.asarray(forcing, np.float64))
+    o = None if obs is None else np.ascontiguousarray(np.asarray(obs, np.float64))
+    dims = (C.c_int64 * 1)(data.size if data is not None else 0)
+    rc = A.lib().hb_logdensity(fun.encode(), int(lik), _ptr(data), dims, 1 if data is not None else 0, _ptr(o),
+                               o.size if o is not None else 0, float(glue_shape), xf.ctypes.data_as(_dp), n, d,
+                               _ptr(ll), _ptr(fx), err, 256)
+    if rc != A.HB_OK:
+        raise A.HbError(rc, err.value.decode())
+    return ll, fx
+
+
+def HydroModel(forcing, param) -> np.ndarray:
+    """HydroModel(forcing, param) (R/test_HydroModel.R:17-36) evaluated on the device; param may be a vector."""
+    f = np.ascontiguousarray(np.asarray(forcing, np.float64))
+    p = np.ascontiguousarray(np.atleast_1d(np.asarray(param, np.float64)))
+    out = np.empty((p.size, f.size))
+    err = C.create_string_buffer(256)
+    rc = A.lib().hb_hydromodel_series(_ptr(f), f.size, _ptr(p), p.size, _ptr(out), err, 256)
+    if rc != A.HB_OK:
+        raise A.HbError(rc, err.value.decode())
+    return out[0] if np.ndim(param) == 0 else out

@@ -75,7 +75,7 @@ static inline double u32d(uint32_t x) { return ((double)x + 0.5) * 0x1.0p-32; }
 static inline uint64_t mulhi64(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
 
 /* Philox slot map (must match hydrobayes_b200/csrc/hb_rng.cuh) */
-enum { SLOT_HEAD = 0, SLOT_PARTNER0 = 1, SLOT_CHOICE = 4, SLOT_ACCEPT = 5, SLOT_DIM0 = 8 };
+enum { SLOT_HEAD = 0, SLOT_PARTNER0 = 1, SLOT_CHOICE = 5, SLOT_ACCEPT = 6, SLOT_DIM0 = 8 };
 
 /* ------------------------------------------------------------------------------------------------ */
 /* targets                                                                                           */

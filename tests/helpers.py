@@ -1,0 +1,97 @@
+"""Shared builders for the parity tests: synthetic inputs of SURVEY 8(d) and oracle/device runners."""
+import numpy as np
+
+from hydrobayes_b200 import _abi as A
+
+PHI = 0.6180339887498949
+
+
+def frac(x):
+    return np.modf(x)[0]
+
+
+def x0_mixture(nc):
+    j = np.arange(1, nc + 1)
+    return (-20 + 40 * frac(j * PHI))[:, None]
+
+
+def x0_tdist(nc, d):
+    j = np.arange(1, nc + 1)[:, None]
+    k = np.arange(1, d + 1)[None, :]
+    return -5 + 20 * frac((j * d + k) * PHI)
+
+
+def x0_hydro(nc):
+    j = np.arange(1, nc + 1)
+    return (0.01 + 1.99 * frac(j * PHI))[:, None]
+
+
+def hydro_data(T=3653, catchment=0):
+    """forcing P_t = (u_t < 0.4) * Gamma(0.7, scale 8); obs = HydroModel(P, K_c) + N(0, 0.5^2)  (SURVEY 8d)."""
+    rng = np.random.default_rng(20240101 + catchment)
+    u = rng.uniform(size=T)
+    P = (u < 0.4) * rng.gamma(0.7, 8.0, size=T)
+    K = 0.1 + 0.8 * frac(catchment * PHI)
+    S = 1.0
+    Y = np.empty(T)
+    for i in range(T):
+        S = (P[i] + S) / (1 + K)
+        Y[i] = K * S
+    obs = Y + rng.normal(0, 0.5, size=T)
+    return P, obs
+
+
+def run_device(cfg, target, x0, par_min=None, par_max=None, tape=None, forcing=None, obs=None, device=0,
+               slice_generations=None):
+    """Drives the C ABI through hydrobayes_b200.Sampler and returns the same dict layout as oracle.run()."""
+    from hydrobayes_b200 import Sampler
+    with Sampler(cfg, device) as s:
+        if par_min is not None:
+            s.set_bounds(par_min, par_max)
+        if obs is not None:
+            s.set_obs(obs)
+        s.set_target(target, forcing)
+        s.set_initial(x0)
+        if tape is not None:
+            s.set_tape(tape.struct(), keepalive=tape)
+        done = 1
+        step = slice_generations or cfg.t
+        while done < cfg.t:
+            done = s.run(step)
+        res = {"chain": s.fetch_chain()}
+        res["AR"], res["CR"] = s.fetch_ar_cr()
+        if cfg.record_accept:
+            res["accept"] = s.fetch_accept()
+        if cfg.store_fx:
+            res["fx"] = s.fetch_fx()[:, :, 0]
+        res["outlier"] = s.fetch_outliers()
+        xt, lp, ll, lpost = s.fetch_state()
+        res.update(xt=xt, lp=lp, ll=ll, lpost=lpost)
+        if cfg.check_convergence:
+            res["R_stat"] = s.fetch_rstat()
+        res["timing"] = s.timing()
+    return res
+
+
+def assert_run_parity(dev, ora, rtol=1e-12, atol=0.0, check_fx=True):
+    """accept/reject sequences identical; chain, AR, CR, final state within rtol; outlier lists identical."""
+    assert ora["rc"] == 0, ora["err"]
+    if "accept" in dev:
+        assert np.array_equal(dev["accept"], ora["accept"]), "accept/reject sequences differ"
+    assert dev["outlier"] == ora["outlier"], "outlier sets differ"
+    np.testing.assert_allclose(dev["chain"], ora["chain"], rtol=rtol, atol=atol, equal_nan=True)
+    np.testing.assert_allclose(dev["AR"], ora["AR"], rtol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(dev["CR"], ora["CR"], rtol=1e-10, equal_nan=True)
+    np.testing.assert_allclose(dev["xt"], ora["xt"], rtol=rtol, atol=atol)
+    np.testing.assert_allclose(dev["lpost"], ora["lpost"], rtol=max(rtol, 1e-12))
+    if check_fx and "fx" in dev:
+        np.testing.assert_allclose(dev["fx"], ora["fx"], rtol=max(rtol, 1e-12), equal_nan=True)
+
+
+def copy_cfg(cfg, **kw):
+    c = A.HbConfig()
+    import ctypes
+    ctypes.memmove(ctypes.byref(c), ctypes.byref(cfg), ctypes.sizeof(c))
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c

@@ -1,0 +1,97 @@
+"""CPU-side checks: the C-ABI library loads here (no GPU), exports every symbol include/hydrobayes_b200.h declares,
+fails loudly without a device, and the host-side logic of the R-API mirror."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import hydrobayes_b200 as hb
+from hydrobayes_b200 import _abi as A
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    if not os.path.exists(A.lib_path()):
+        import __graft_entry__ as g
+        g.build()
+    return A.lib()
+
+
+def test_header_symbols_exported(L):
+    hdr = open(os.path.join(ROOT, "include", "hydrobayes_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(hb_[a-z0-9_]+)\s*\(", hdr)) - {"hb_target_vtable"})
+    declared = [s for s in declared if not s.endswith("_t")]
+    assert len(declared) >= 30
+    raw = C.CDLL(A.lib_path())
+    for s in declared:
+        assert hasattr(raw, s), f"{s} is declared in the header but not exported"
+    assert sorted(A.EXPORTED_SYMBOLS) == declared
+
+
+def test_struct_layout_matches_header(L):
+    c = A.HbConfig()
+    L.hb_config_default(C.byref(c))
+    ref = A.default_config()
+    for f, _ in A.HbConfig._fields_:
+        assert getattr(c, f) == getattr(ref, f), f
+    assert c.adapt == 0.1 and c.update_interval == 10 and c.delta == 3 and c.nCR == 3 and c.p_g == 0.2
+    assert c.c_star == 1e-12 and c.seed == 1312 and c.abi_version == A.HB_ABI_VERSION
+
+
+def test_builtin_targets_registered(L):
+    for n in ("mixture", "t_distribution", "HydroModel"):
+        assert L.hb_target_registered(n.encode()) == 1
+    assert L.hb_target_registered(b"some_r_closure") == 0
+
+
+@pytest.mark.skipif(A.lib().hb_device_count() > 0 if os.path.exists(A.lib_path()) else False, reason="GPU present")
+def test_no_cpu_fallback(L):
+    with pytest.raises(hb.HbError) as e:
+        hb.dream_parallel("mixture", lik=1, par_info=dict(initial="user", val_ini=np.zeros((10, 1)), prior="flat"),
+                          nc=10, t=10, d=1, verbose=False)
+    assert e.value.code == A.HB_ERR_NO_DEVICE
+    with pytest.raises(hb.HbError) as e:
+        hb.R_stat(np.zeros((10, 1, 3)))
+    assert e.value.code == A.HB_ERR_NO_DEVICE
+    with pytest.raises(hb.HbError):
+        hb.log_density("mixture", [[0.0]], lik=1)
+
+
+def test_argument_checks_before_device(L):
+    # R/dream.R:136-137 : nc must be > 2*delta -- checked before any device work
+    cfg = A.default_config(nc=6, t=10, d=1, lik=1)
+    h = C.c_void_p()
+    assert L.hb_create(C.byref(cfg), 0, C.byref(h)) == A.HB_ERR_INVALID
+    assert b"'nc' must be > 'delta' * 2" in L.hb_last_error(None)
+    cfg = A.default_config(nc=10, t=10, d=1, lik=7)
+    assert L.hb_create(C.byref(cfg), 0, C.byref(h)) == A.HB_ERR_INVALID
+    assert b"'lik' has to be one of" in L.hb_last_error(None)
+    cfg = A.default_config(nc=10, t=10, d=1, lik=1, mt=3)
+    assert L.hb_create(C.byref(cfg), 0, C.byref(h)) == A.HB_ERR_UNSUPPORTED
+
+
+def test_prior_sample_host_logic():
+    rng = np.random.default_rng(0)
+    x = hb.prior_sample(dict(initial="uniform", min=[-1, 0], max=[1, 10]), 2, 500, rng)
+    assert x.shape == (500, 2) and x[:, 0].min() >= -1 and x[:, 1].max() <= 10
+    x = hb.prior_sample(dict(initial="latin", min=-20, max=20), 1, 40, rng)
+    assert np.array_equal(np.sort(np.floor((x[:, 0] + 20) / 1.0)), np.arange(40))   # one point per stratum
+    x = hb.prior_sample(dict(initial="normal", mu=[0, 5], cov=[[1, 0], [0, 4]]), 2, 4000, rng)
+    assert abs(x[:, 1].mean() - 5) < 0.2 and abs(x[:, 1].std() - 2) < 0.15
+    v = np.arange(6.0).reshape(3, 2)
+    assert np.array_equal(hb.prior_sample(dict(initial="user", val_ini=v), 2, 3), v)
+    with pytest.raises(ValueError):
+        hb.prior_sample(dict(initial="bogus"), 1, 3)
+
+
+def test_outlier_list_structure():
+    from hydrobayes_b200.sampler import _outlier_list
+    cfg = A.default_config(nc=10, t=100, d=1, lik=1)
+    lst = _outlier_list([(10, 3), (10, 7)], cfg, A.HB_SWEEP_SYNCHRONOUS)
+    assert len(lst) == 10 and lst[0] is None and lst[9].tolist() == [3, 7]
+    cfg = A.default_config(nc=10, t=100, d=1, lik=1, outlier_check=0)
+    assert _outlier_list([], cfg, A.HB_SWEEP_SYNCHRONOUS) == [None]

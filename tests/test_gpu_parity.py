@@ -1,0 +1,235 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Run on the B200 box: pytest -m gpu.
+
+Bars (SURVEY 7.4 / BASELINE north_star): accept/reject sequences identical and chain states within 1e-12 relative in
+record/replay (tape) mode; log-densities within 1e-12 relative with identical floor hits; native-RNG runs compared
+draw by draw against the oracle's Philox mode (1e-9 relative: zeta uses fast float intrinsics on the device).
+"""
+import numpy as np
+import pytest
+
+import helpers as H
+from hydrobayes_b200 import _abi as A
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hb():
+    import hydrobayes_b200 as m
+    assert m.lib().hb_device_count() >= 1, "no CUDA device: the product path has no CPU fallback"
+    return m
+
+
+# ---------------------------------------------------------------- K2: log-density plugins --------------------------
+def test_mixture_logdensity(hb, oracle):
+    x = np.concatenate([np.linspace(-25, 25, 2001), [-8, 0, 10, 1, 60.0, -70.0, 48.0, 48.6]])[:, None]
+    ll, fx = hb.log_density("mixture", x, lik=1)
+    ll_o, fx_o, rc = oracle.logdensity("mixture", 1, x)
+    assert rc == 0
+    np.testing.assert_allclose(fx, fx_o, rtol=1e-12, atol=0)
+    np.testing.assert_allclose(ll, ll_o, rtol=1e-12)
+    assert np.array_equal(ll == oracle.log_xmin(), ll_o == oracle.log_xmin())   # identical floor hits
+    assert (ll == oracle.log_xmin()).sum() >= 2
+
+
+@pytest.mark.parametrize("d", [1, 2, 3, 5, 8, 17, 37, 64, 100, 128, 130])
+def test_tdist_logdensity(hb, oracle, d):
+    rng = np.random.default_rng(d)
+    x = np.concatenate([rng.uniform(-5, 15, size=(1001, d)), np.zeros((1, d)), np.ones((1, d)),
+                        rng.normal(size=(30, d)) * np.sqrt(np.arange(1, d + 1))])
+    ll, fx = hb.log_density("t_distribution", x, lik=2)
+    ll_o = oracle.tdist_logpdf(x)
+    np.testing.assert_allclose(ll, ll_o, rtol=1e-12)
+    np.testing.assert_allclose(fx, ll_o, rtol=1e-12)
+
+
+def test_tdist_known_answers(hb):
+    ll, _ = hb.log_density("t_distribution", np.zeros((1, 100)), lik=2)
+    assert ll[0] == pytest.approx(-213.43955272792834, rel=1e-13)
+    ll, _ = hb.log_density("t_distribution", np.ones((1, 100)), lik=2)
+    assert ll[0] == pytest.approx(-218.01512992854524, rel=1e-13)
+
+
+def test_hydromodel_series_bit_exact(hb, oracle):
+    P, _ = H.hydro_data(T=3653)
+    K = np.array([0.01, 0.3, 0.4567, 1.0, 2.0])
+    y = hb.HydroModel(P, K)
+    for i, k in enumerate(K):
+        assert np.array_equal(y[i], oracle.hydromodel(P, k))   # same IEEE operations in the same order
+    np.testing.assert_array_equal(hb.HydroModel([0, 1, 2, 0, 5], 0.5),
+                                  [1 / 3, 5 / 9, 1.037037037037037, 0.691358024691358, 2.1275720164609053])
+    with pytest.raises(hb.HbError):
+        hb.HydroModel([0, 1], -0.5)
+    with pytest.raises(hb.HbError):
+        hb.HydroModel([0, -1], 0.5)
+
+
+@pytest.mark.parametrize("T", [5, 200, 3653])
+def test_hydromodel_glue_logdensity(hb, oracle, T):
+    P, obs = H.hydro_data(T=T)
+    K = np.concatenate([np.linspace(0.01, 2, 333), [0.0]])[:, None]
+    ll, _ = hb.log_density("HydroModel", K, lik=31, forcing=P, obs=obs, glue_shape=50.0)
+    ll_o, _, rc = oracle.logdensity("HydroModel", 31, K, forcing=P, obs=obs, glue_shape=50.0)
+    assert rc == 0
+    np.testing.assert_allclose(ll, ll_o, rtol=1e-11)
+    assert np.array_equal(ll == oracle.log_xmin(), ll_o == oracle.log_xmin())
+    with pytest.raises(hb.HbError):
+        hb.log_density("HydroModel", [[-0.1]], lik=31, forcing=P, obs=obs, glue_shape=50.0)
+
+
+def test_unknown_target(hb):
+    with pytest.raises(hb.HbError) as e:
+        hb.log_density("my_closure", [[0.0]], lik=2)
+    assert e.value.code == A.HB_ERR_UNKNOWN_TARGET
+
+
+# ---------------------------------------------------------------- K4: R_stat -------------------------------------
+@pytest.mark.parametrize("t,d,n", [(51, 1, 3), (100, 2, 4), (201, 5, 16), (64, 100, 8), (1000, 3, 257)])
+def test_rstat_array(hb, oracle, t, d, n):
+    x = np.random.default_rng(t).normal(size=(t, d, n)).cumsum(axis=0)
+    np.testing.assert_allclose(hb.R_stat(x), oracle.rstat(x), rtol=1e-11)
+
+
+def test_rstat_known(hb):
+    i = np.arange(1, 101)[:, None, None]; k = np.arange(1, 3)[None, :, None]; c = np.arange(1, 5)[None, None, :]
+    x = np.sin(0.37 * i * k + 1.3 * c) + 0.1 * c * k
+    np.testing.assert_allclose(hb.R_stat(x), [1.0113185866169283, 1.0735661244327646], rtol=1e-12)
+
+
+# ---------------------------------------------------------------- replay (tape) parity ---------------------------
+def _replay_case(oracle, cfg, target, x0, **kw):
+    """Oracle runs with Philox and records the decision tape; oracle and device then replay the same tape."""
+    rec = oracle.Tape.for_config(cfg)
+    ora0 = oracle.run(cfg, target, x0, record=rec, **kw)
+    assert ora0["rc"] == 0, ora0["err"]
+    cfg_t = H.copy_cfg(cfg, rng_mode=A.HB_RNG_TAPE, record_accept=1)
+    ora = oracle.run(cfg_t, target, x0, tape=rec, **kw)
+    assert np.array_equal(ora["chain"], ora0["chain"], equal_nan=True)
+    dev = H.run_device(cfg_t, target, x0, tape=rec, **kw)
+    return dev, ora
+
+
+def test_replay_mixture_c1(hb, oracle):
+    # BASELINE C1: mixture, nc = 10, t = 5000, d = 1 (dream_parallel semantics)
+    cfg = A.default_config(nc=10, t=5000, d=1, lik=1, seed=1312, store_fx=1)
+    dev, ora = _replay_case(oracle, cfg, "mixture", H.x0_mixture(10))
+    H.assert_run_parity(dev, ora, rtol=1e-12)
+    assert 0.05 < ora["accept"].mean() < 0.9
+
+
+def test_replay_tdist_d100(hb, oracle):
+    cfg = A.default_config(nc=64, t=200, d=100, lik=2, seed=7, store_fx=1)
+    dev, ora = _replay_case(oracle, cfg, "t_distribution", H.x0_tdist(64, 100))
+    H.assert_run_parity(dev, ora, rtol=1e-12)
+
+
+@pytest.mark.parametrize("bound", [A.HB_BOUND_BOUND, A.HB_BOUND_REFLECT, A.HB_BOUND_FOLD])
+def test_replay_hydromodel_glue(hb, oracle, bound):
+    P, obs = H.hydro_data(T=365)
+    cfg = A.default_config(nc=16, t=300, d=1, lik=31, glue_shape=50.0, prior=A.HB_PRIOR_UNIFORM, bound=bound, seed=3)
+    dev, ora = _replay_case(oracle, cfg, "HydroModel", H.x0_hydro(16), par_min=[0.01], par_max=[2.0], forcing=P, obs=obs)
+    H.assert_run_parity(dev, ora, rtol=1e-11)
+
+
+@pytest.mark.parametrize("kw", [dict(thin=5), dict(burnin=0.5), dict(burnin=0.2, thin=4), dict(adapt=0.5, update_interval=7),
+                                dict(delta=1, nCR=1), dict(delta=4, nCR=6, p_g=0.5, beta0=0.7, c_val=0.3, c_star=1e-3)])
+def test_replay_options(hb, oracle, kw):
+    cfg = A.default_config(nc=24, t=400, d=6, lik=2, seed=11, **kw)
+    dev, ora = _replay_case(oracle, cfg, "t_distribution", H.x0_tdist(24, 6))
+    H.assert_run_parity(dev, ora, rtol=1e-12)
+
+
+def test_replay_uniform_prior_unbounded_proposals(hb, oracle):
+    # prior = "uniform" without bound handling: proposals outside the box get lp = -708.396
+    cfg = A.default_config(nc=12, t=300, d=3, lik=2, seed=5, prior=A.HB_PRIOR_UNIFORM)
+    x0 = np.random.default_rng(0).uniform(-1, 1, size=(12, 3))
+    dev, ora = _replay_case(oracle, cfg, "t_distribution", x0, par_min=[-1.5] * 3, par_max=[1.5] * 3)
+    H.assert_run_parity(dev, ora, rtol=1e-12)
+    assert (ora["chain"][:, 3, :] == oracle.log_xmin()).sum() == 0   # stored lp is of accepted states only
+    assert np.isfinite(dev["chain"]).all()
+
+
+def test_replay_forced_outliers(hb, oracle):
+    # two chains start far out in the tail: check_outlier must flag and reset them (R/internals.R:71-87)
+    x0 = H.x0_tdist(32, 4)
+    x0[3] = 400.0; x0[17] = -350.0
+    cfg = A.default_config(nc=32, t=200, d=4, lik=2, seed=21, adapt=0.5)
+    dev, ora = _replay_case(oracle, cfg, "t_distribution", x0)
+    assert len(ora["outlier"]) > 0
+    H.assert_run_parity(dev, ora, rtol=1e-12)
+
+
+def test_replay_sliced_run_equals_single_run(hb, oracle):
+    cfg = A.default_config(nc=16, t=120, d=5, lik=2, seed=2, rng_mode=A.HB_RNG_PHILOX, record_accept=1)
+    x0 = H.x0_tdist(16, 5)
+    a = H.run_device(cfg, "t_distribution", x0)
+    b = H.run_device(cfg, "t_distribution", x0, slice_generations=7)
+    assert np.array_equal(a["chain"], b["chain"]) and np.array_equal(a["accept"], b["accept"])
+
+
+# ---------------------------------------------------------------- native RNG (Philox) vs the oracle's Philox -----
+@pytest.mark.parametrize("case", ["mixture", "tdist", "hydro"])
+def test_native_rng_matches_oracle_philox(hb, oracle, case):
+    if case == "mixture":
+        cfg = A.default_config(nc=64, t=600, d=1, lik=1, seed=99, record_accept=1); tgt = "mixture"; x0 = H.x0_mixture(64); kw = {}
+    elif case == "tdist":
+        cfg = A.default_config(nc=48, t=150, d=100, lik=2, seed=1234567, record_accept=1); tgt = "t_distribution"; x0 = H.x0_tdist(48, 100); kw = {}
+    else:
+        P, obs = H.hydro_data(T=200)
+        cfg = A.default_config(nc=20, t=200, d=1, lik=31, glue_shape=50.0, prior=A.HB_PRIOR_UNIFORM, bound=A.HB_BOUND_REFLECT, seed=8, record_accept=1)
+        tgt = "HydroModel"; x0 = H.x0_hydro(20); kw = dict(par_min=[0.01], par_max=[2.0], forcing=P, obs=obs)
+    ora = oracle.run(cfg, tgt, x0, **kw)
+    dev = H.run_device(cfg, tgt, x0, **kw)
+    H.assert_run_parity(dev, ora, rtol=1e-9, atol=1e-12, check_fx=False)
+
+
+def test_native_mixture_moments(hb):
+    # analytic: mean 7, variance 46, P(x < 1) = 1/6  
+    nc, t = 2048, 1500
+    res = hb.dream_parallel("mixture", lik=1, par_info=dict(initial="uniform", min=-20, max=20, prior="flat"), nc=nc, t=t,
+                            d=1, seed=4, verbose=False)
+    x = res["chain"][t // 2:, 0, :]
+    # batch means over chains give the standard error
+    m = x.mean(axis=0); p = (x < 1).mean(axis=0)
+    assert abs(m.mean() - 7) < 4 * m.std(ddof=1) / np.sqrt(nc) + 0.05
+    assert abs(p.mean() - 1 / 6) < 4 * p.std(ddof=1) / np.sqrt(nc) + 0.003
+    assert abs(x.var() - 46) < 1.5
+    assert res["AR"].shape == (t // 10 + 1, 2) and res["CR"].shape == (t // 10 + 1, 4)
+    assert np.isnan(res["AR"][0, 1]) and res["AR"][0, 0] == nc
+
+
+def test_native_tdist_moments(hb):
+    nc, t, d = 512, 3000, 10
+    res = hb.dream_parallel("t_distribution", lik=2, par_info=dict(initial="uniform", min=-5, max=15, prior="flat"),
+                            nc=nc, t=t, d=d, seed=6, verbose=False, thin=2)
+    x = res["chain"][-600:, :d, :]
+    var = x.var(axis=(0, 2))
+    np.testing.assert_allclose(var, 60 / 58 * np.arange(1, d + 1), rtol=0.08)
+    assert np.abs(x.mean(axis=(0, 2))).max() < 0.15
+
+
+# ---------------------------------------------------------------- full-size properties ----------------------------
+def test_c2_size_properties(hb):
+    # BASELINE C2 shape (nc = 1024, d = 100), a few hundred generations: structure and invariants
+    nc, d, t = 1024, 100, 300
+    cfg = A.default_config(nc=nc, t=t, d=d, lik=2, seed=1, thin=10, record_accept=1)
+    dev = H.run_device(cfg, "t_distribution", H.x0_tdist(nc, d))
+    ch = dev["chain"]
+    assert ch.shape == (t // 10 + 1, d + 3, nc) and np.isfinite(ch).all()
+    np.testing.assert_allclose(ch[:, d + 2, :], ch[:, d, :] + ch[:, d + 1, :], rtol=1e-14)   # lpost = lp + ll
+    assert (ch[:, d, :] == 0).all()                                                          # flat prior
+    ar = dev["AR"]
+    assert np.all(np.diff(ar[:, 0]) == nc * 10)                                              # cumulative n_eval
+    np.testing.assert_allclose(dev["CR"][:, 1:].sum(axis=1), 1.0, rtol=1e-12)                # pCR normalised
+    acc = dev["accept"].reshape(-1, 10, nc)[: (t - 1) // 10]                                  # generations 2..
+    # accepted fraction per AR interval equals the recorded accept mask (intervals end at i %% 10 == 0)
+    a = dev["accept"]
+    for r in range(1, ar.shape[0]):
+        lo, hi = (r - 1) * 10 + (1 if r == 1 else 0), r * 10          # generations lo+1 .. hi  (accept row = i - 2)
+        rows = a[max(lo - 1, 0): hi - 1]
+        assert ar[r, 1] == pytest.approx(rows.mean(), rel=1e-12)
+    # the state equals the last stored row
+    np.testing.assert_array_equal(dev["xt"], ch[-1, :d, :].T)
+    # stored log-density equals a fresh evaluation of the stored state
+    ll, _ = hb.log_density("t_distribution", ch[-1, :d, :].T, lik=2)
+    np.testing.assert_allclose(ch[-1, d + 1, :], ll, rtol=1e-12)
