@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- chain-generations/s of the DREAM generation step (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C4|C2|C3] [--impl reference]
+
+One "step" is one slice of GENS_PER_STEP = 10 synchronous DREAM generations (one updateInterval) of the whole
+population through the C ABI (hb_run): K1 proposal -> K2 log-density plugin -> K3 accept/update [-> finalize].
+Default workload (BASELINE C4, the configuration the north-star metric is quoted on, it fits one GPU): d = 100
+t_distribution, nc = 2^20 chains, t = 1000, thin = 100; at N > 1 the population is sharded across ranks (strong
+scaling) with a per-generation NCCL all-gather of the chain state.  Inputs (839 MB of chain state) are larger than
+the 126 MB L2, so no explicit L2 flush is needed between steps.
+
+`value`  : nc * generations / seconds, state resident in HBM, timed between two barrier+synchronize pairs, max over ranks.
+`e2e`    : the same metric through the public API call dream_parallel() with HOST buffers: x0 upload, the full run,
+           and the device->host fetch of chain / AR / CR inside the timed region.
+`--impl reference`: the CPU oracle (restated reference, NOT R: R is not installed) on all host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+GENS_PER_STEP = 10
+METRIC = "chain-generations/sec"
+UNIT = "chain-generations/s"
+
+
+def workload(name):
+    import helpers as H
+    from hydrobayes_b200 import _abi as A
+    if name == "C4":
+        nc, d, t = 1 << 20, 100, 1000
+        cfg = A.default_config(nc=nc, t=t, d=d, lik=2, thin=100, seed=1312)
+        return dict(cfg=cfg, target="t_distribution", x0=lambda: H.x0_tdist(nc, d), kw={},
+                    desc="C4: dream_parallel t_distribution d=100 nc=2^20 t=1000 thin=100")
+    if name == "C2":
+        nc, d, t = 1024, 100, 20000
+        cfg = A.default_config(nc=nc, t=t, d=d, lik=2, thin=1, seed=1312)
+        return dict(cfg=cfg, target="t_distribution", x0=lambda: H.x0_tdist(nc, d), kw={},
+                    desc="C2: t_distribution d=100 nc=1024 t=20000 (synchronous sweep)")
+    if name == "C3":
+        nc, t = 65536, 500
+        P, obs = H.hydro_data(T=3653)
+        cfg = A.default_config(nc=nc, t=t, d=1, lik=31, glue_shape=50.0, prior=A.HB_PRIOR_UNIFORM, bound=A.HB_BOUND_BOUND,
+                               thin=10, seed=1312)
+        return dict(cfg=cfg, target="HydroModel", x0=lambda: H.x0_hydro(nc),
+                    kw=dict(par_min=[0.01], par_max=[2.0], forcing=P, obs=obs),
+                    desc="C3: HydroModel (d=1, T=3653 daily forcing, GLUE lik=31) nc=65536")
+    raise SystemExit(f"unknown workload {name}")
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local, torch
+
+
+def barrier_sync(torch, world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(torch, world, v):
+    if world == 1:
+        return v
+    import torch.distributed as dist
+    t = torch.tensor([v], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def make_sampler(w, local, rank, world, torch):
+    from hydrobayes_b200 import Sampler, lib
+    cfg = w["cfg"]
+    s = Sampler(cfg, local)
+    kw = w["kw"]
+    if "par_min" in kw:
+        s.set_bounds(kw["par_min"], kw["par_max"])
+    if "obs" in kw:
+        s.set_obs(kw["obs"])
+    s.set_target(w["target"], kw.get("forcing"))
+    if world > 1:
+        import ctypes as C
+        import torch.distributed as dist
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            rc = lib().hb_comm_unique_id(buf)
+            assert rc == 0, lib().hb_last_error(None)
+        obj = [bytes(buf.raw)]
+        dist.broadcast_object_list(obj, src=0)
+        s.comm_init(rank, world, obj[0])
+    s.set_initial(w["x0"]())
+    return s
+
+
+def roofline_for(kname, per_launch_ms, n_local, vt_work, peaks, dmma_peak):
+    """algorithmic bytes/flops per chain-generation x chains per launch / launch duration"""
+    d = 100
+    if kname == "K1":
+        bytes_ = (48 * d + 16) * n_local
+        a = bytes_ / (per_launch_ms * 1e-3) / 1e9
+        return {"kernel": "hb_k1_kernel (proposal)", "bound": "hbm", "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": a / peaks["hbm_gbs"], "peak_source": peaks["source"]}
+    if kname == "K3":
+        bytes_ = (8 * d * (1 + 0.16) + 32) * n_local
+        a = bytes_ / (per_launch_ms * 1e-3) / 1e9
+        return {"kernel": "hb_k3_kernel (accept)", "bound": "hbm", "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": a / peaks["hbm_gbs"], "peak_source": peaks["source"]}
+    flops = vt_work[0] * n_local
+    a = flops / (per_launch_ms * 1e-3) / 1e12
+    return {"kernel": "K2 log-density plugin", "bound": "tensor", "achieved": a, "peak": dmma_peak, "unit": "TFLOP/s",
+            "frac": a / dmma_peak if dmma_peak else None, "peak_source": "fp64 DMMA micro-benchmark hb_fp64_peaks() on this box"}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return {"hbm_gbs": j["hbm_gbs"], "source": "MEASURED_PEAKS.json (measured)"}
+    return {"hbm_gbs": 6650.0, "source": "fallback of B200_PROFILING.md"}
+
+
+def cpu_baseline(w, seconds_budget=20.0, threads=None):
+    """The oracle (restated reference, kind 'port') on the host cores, bounded sample of the same workload."""
+    from oracle import hb_oracle_py as oracle
+    import helpers as H
+    from hydrobayes_b200 import _abi as A
+    cfg = w["cfg"]
+    threads = threads or os.cpu_count() or 1
+    nc_s = min(cfg.nc, 8192 if cfg.d > 1 else 4096)
+    x0 = w["x0"]()[:nc_s]
+    gens = GENS_PER_STEP
+    c = H.copy_cfg(cfg, nc=nc_s, t=gens + 1, thin=1, rng_mode=A.HB_RNG_PHILOX, n_runs=1)
+    kw = dict(w["kw"])
+    t0 = time.time(); done = 0; loop_s = 0.0; reps = 0
+    while time.time() - t0 < seconds_budget and reps < 50:
+        r = oracle.run(c, w["target"], x0, threads=threads, outputs=False, **kw)
+        assert r["rc"] == 0, r["err"]
+        loop_s += r["loop_seconds"]; done += nc_s * gens; reps += 1
+    return {"value": done / loop_s, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{reps} x ({nc_s} chains x {gens} generations) of the same workload, restated CPU oracle (C, OpenMP over "
+                      f"chains), not R (R is not installed)"}, nc_s
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = workload(args.workload)
+    from oracle import hb_oracle_py as oracle
+    import helpers as H
+    from hydrobayes_b200 import _abi as A
+    cfg = w["cfg"]
+    threads = os.cpu_count() or 1
+    nc_s = min(cfg.nc, 8192 if cfg.d > 1 else 4096)
+    x0 = w["x0"]()[:nc_s]
+    c = H.copy_cfg(cfg, nc=nc_s, t=GENS_PER_STEP + 1, thin=1, rng_mode=A.HB_RNG_PHILOX, n_runs=1)
+    for _ in range(args.warmup):
+        oracle.run(c, w["target"], x0, threads=threads, outputs=False, **w["kw"])
+    loop = 0.0
+    for _ in range(args.steps):
+        r = oracle.run(c, w["target"], x0, threads=threads, outputs=False, **w["kw"])
+        assert r["rc"] == 0, r["err"]
+        loop += r["loop_seconds"]
+    value = nc_s * GENS_PER_STEP * args.steps / loop
+    sample = (f"each step = {nc_s} chains x {GENS_PER_STEP} generations of the workload (bounded sample of nc={cfg.nc}); restated "
+              f"CPU oracle (C + OpenMP over chains), not R: R is not installed and the reference has no native code")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": loop / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["desc"], "generations_per_step": GENS_PER_STEP},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def quick_rate(name, local, torch, gens=200, warm=30):
+    """short side measurement of another BASELINE config on one GPU (reported under `other_workloads`)"""
+    w = workload(name)
+    s = make_sampler(w, local, 0, 1, torch)
+    s.run(warm)
+    torch.cuda.synchronize()
+    ms0, l0 = s.timing()
+    t0 = time.perf_counter()
+    s.run(gens)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms1, l1 = s.timing()
+    out = {"workload": w["desc"], "value": w["cfg"].nc * gens / wall, "unit": UNIT, "generations": gens,
+           "us_per_generation": wall / gens * 1e6, "device_us_per_generation": (ms1 - ms0) / gens * 1e3,
+           "gpu_launches": l1 - l0}
+    s.close()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=97)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="C4")
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu_baseline / other workloads (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3 if not args.no_extras else args.warmup
+
+    rank, world, local, torch = dist_setup(args.gpus)
+    import hydrobayes_b200 as hb
+    from hydrobayes_b200 import lib
+    assert lib().hb_device_count() >= 1, "no CUDA device: there is no CPU fallback"
+    w = workload(args.workload)
+    cfg = w["cfg"]
+    need = (args.steps + args.warmup) * GENS_PER_STEP + 1
+    if need > cfg.t:
+        cfg.t = need
+    s = make_sampler(w, local, rank, world, torch)
+    n_local = cfg.nc // world
+
+    for _ in range(args.warmup):
+        s.run(GENS_PER_STEP)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    barrier_sync(torch, world)
+    ms0, l0 = s.timing()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        s.run(GENS_PER_STEP)
+    barrier_sync(torch, world)
+    wall = time.perf_counter() - t0
+    ms1, l1 = s.timing()
+    clk = clocks.stop() if rank == 0 else None
+    wall = max_over_ranks(torch, world, wall)
+    dev_ms = max_over_ranks(torch, world, ms1 - ms0)
+    gens = args.steps * GENS_PER_STEP
+    value = cfg.nc * gens / wall
+
+    # per-kernel durations (CUDA events on the library's stream, after the timed region)
+    roof = None; kernels = {}
+    if not args.no_extras:
+        s.profile(True)
+        s.run(2 * GENS_PER_STEP)
+        s.profile(False)
+        for k in ("K1", "K2", "K3", "FIN", "XCHG", "OUTLIER"):
+            ms, n = s.kernel_ms(k)
+            if n:
+                kernels[k] = {"ms_per_launch": ms / n, "launches": n}
+    s.close()
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": wall / args.steps * 1e3, "device_ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["desc"], "generations_per_step": GENS_PER_STEP, "chains": cfg.nc, "d": cfg.d,
+                       "chains_per_gpu": n_local, "rng": "philox4x32-10", "l2": "inputs larger than L2 (no flush)"
+                       if cfg.nc * cfg.d * 8 > 126e6 else "state is L2-resident by construction (latency-bound config)",
+                       "exchange": "ncclAllGather per generation" if world > 1 else "none"},
+            "gpu_launches": l1 - l0}
+    if rank == 0 and not args.no_extras:
+        peaks = load_peaks()
+        import ctypes as C
+        dm, df = C.c_double(), C.c_double()
+        lib().hb_fp64_peaks(C.byref(dm), C.byref(df))
+        flops = {"t_distribution": (cfg.d * cfg.d + 3.0 * cfg.d,), "HydroModel": (5.0 * 3653,), "mixture": (40.0,)}[w["target"]]
+        if kernels:
+            dom = max(("K1", "K2", "K3"), key=lambda k: kernels.get(k, {"ms_per_launch": 0})["ms_per_launch"])
+            roof = roofline_for(dom, kernels[dom]["ms_per_launch"], n_local, flops, peaks, dm.value)
+            roof["traffic"] = None
+            prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+            if os.path.exists(prof):
+                roof["traffic"] = json.load(open(prof)).get(dom)
+            roof["all_kernels"] = {k: roofline_for(k, kernels[k]["ms_per_launch"], n_local, flops, peaks, dm.value)
+                                   for k in ("K1", "K2", "K3") if k in kernels}
+            roof["kernel_ms_per_launch"] = {k: v["ms_per_launch"] for k, v in kernels.items()}
+            roof["fp64_peaks_measured_tflops"] = {"dmma": dm.value, "dfma": df.value}
+        line["roofline"] = roof
+        line["clocks"] = clk
+    if rank == 0 and world == 1 and not args.no_extras:
+        # end to end through the public API with host buffers (full C4 run: x0 upload, t-1 generations, chain fetch)
+        w2 = workload(args.workload)
+        c2 = w2["cfg"]
+        x0 = w2["x0"]()
+        par = dict(initial="user", val_ini=x0, prior={0: "flat", 1: "uniform"}[c2.prior])
+        if "par_min" in w2["kw"]:
+            par.update(min=w2["kw"]["par_min"], max=w2["kw"]["par_max"], bound="bound")
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = hb.dream_parallel(w2["target"], lik=c2.lik, par_info=par, nc=c2.nc, t=c2.t, d=c2.d, thin=c2.thin,
+                                glue_shape=c2.glue_shape, obs=w2["kw"].get("obs"), forcing=w2["kw"].get("forcing"),
+                                verbose=False, seed=1312, store_fx=False)
+        e2e_s = time.perf_counter() - t0
+        n_steps = (c2.t - 1) / GENS_PER_STEP
+        line["e2e"] = {"value": c2.nc * (c2.t - 1) / e2e_s, "unit": UNIT,
+                       "h2d_bytes_per_step": x0.nbytes / n_steps,
+                       "d2h_bytes_per_step": (res["chain"].nbytes + res["AR"].nbytes + res["CR"].nbytes) / n_steps,
+                       "seconds": e2e_s, "call": "hydrobayes_b200.dream_parallel(...) full run incl. x0 upload and chain fetch"}
+        del res
+        cb, _ = cpu_baseline(w)
+        line["cpu_baseline"] = cb
+        others = {}
+        for name in ("C2", "C3"):
+            if name != args.workload:
+                try:
+                    others[name] = quick_rate(name, local, torch)
+                except Exception as e:  # report, never hide
+                    others[name] = {"error": repr(e)}
+        line["other_workloads"] = others
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -5,11 +5,13 @@
 //   slot 1..4   two 64-bit draws each -> partial Fisher-Yates partner draws 0..7 (delta <= 4)     R/internals.R:134,142
 //   slot 5      words 0-1 -> u_id (crossover index)     words 2-3 -> u_gamma                        R/internals.R:173,192
 //   slot 6      words 0-1 -> u_accept                   words 2-3 -> g_snooker = 1.2 + u            R/internals.R:241,156
-//   slot 8+k    word 0 -> zt_k, word 1 -> lambda_k, words 2-3 -> zeta_k (Box-Muller, float)         R/internals.R:175,188,194
+//   slot 8+k    word 0 -> zt_k, word 1 -> lambda_k, words 2-3 -> zeta_k (hb_rng_normal)            R/internals.R:175,188,194
 //   outlier replacement draws: chain = (0xFFFFFFFF << 32) | run, slot = q >> 1, pair q & 1 (host side) R/internals.R:81
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include "../../include/hydrobayes_b200_rng.h"
 
 #define HB_FLOOR (-708.3964185322641)  // log(.Machine$double.xmin), R/internals.R:19,65
 
@@ -72,16 +74,15 @@ __host__ __device__ __forceinline__ uint64_t hb_pair64(const uint4& w, int which
   return which ? (((uint64_t)w.w << 32) | w.z) : (((uint64_t)w.y << 32) | w.x);
 }
 // open-interval uniforms, identical arithmetic on host and device (exact in binary floating point)
-__host__ __device__ __forceinline__ double hb_u53(uint64_t x) { return (double)(x >> 11) * 0x1.0p-53 + 0x1.0p-54; }
-__host__ __device__ __forceinline__ double hb_u32d(uint32_t x) { return ((double)x + 0.5) * 0x1.0p-32; }
+__host__ __device__ __forceinline__ double hb_u53(uint64_t x) { return hb_rng_u53(x); }
+__host__ __device__ __forceinline__ double hb_u32d(uint32_t x) { return hb_rng_u32(x); }
 
 #ifdef __CUDACC__
 __device__ __forceinline__ uint64_t hb_mulhi64(uint64_t a, uint64_t b) { return __umul64hi(a, b); }
 
-// zeta ~ N(0, c_star^2): Box-Muller in float (zeta is a 1e-12-scale jitter), fast intrinsics
+// zeta ~ N(0, c_star^2): bit-reproducible Box-Muller of include/hydrobayes_b200_rng.h
 __device__ __forceinline__ double hb_zeta(uint32_t w2, uint32_t w3, double c_star) {
-  const float u1 = (float)hb_u32d(w2), u2 = (float)hb_u32d(w3);
-  return c_star * (double)(sqrtf(-2.0f * __logf(u1)) * __cosf(6.283185307179586f * u2));
+  return __dmul_rn(c_star, hb_rng_normal(w2, w3));
 }
 
 // sparse partial Fisher-Yates over 0..n-1 (R's sample(n, k) without replacement: y = x[r]; x[r] = x[--n])

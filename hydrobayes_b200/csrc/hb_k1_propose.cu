@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(256) hb_k1_kernel(const hb_k1_params p) {
               lambda = p.tape.lambda[rix * d + rank];                  // :188 (by rank within A)
               zeta = p.tape.zeta[rix * d + rank];                      // :194
             } else {
-              lambda = __dadd_rn(-p.c_val, __dmul_rn(2.0 * p.c_val, hb_u32d(wl[m])));
+              lambda = hb_rng_lambda(wl[m], p.c_val);
               zeta = hb_zeta(wz2[m], wz3[m], p.c_star);
             }
             // jump_diff <- colSums(r1[,A] - r2[,A])   :196

@@ -16,6 +16,7 @@
  *                  the device kernels use, so a device native-RNG run can be compared draw by draw.
  */
 #include "hb_oracle.h"
+#include "../include/hydrobayes_b200_rng.h" /* native-RNG draw transforms: a spec shared with the device */
 
 #include <float.h>
 #include <math.h>
@@ -70,8 +71,8 @@ static inline uint64_t pair64(const uint32_t w[4], int which) {
   return which ? (((uint64_t)w[3] << 32) | w[2]) : (((uint64_t)w[1] << 32) | w[0]);
 }
 /* uniform in the open interval (0,1) with 53 random bits, like R's runif never returns 0 or 1 */
-static inline double u53(uint64_t x) { return (double)(x >> 11) * 0x1.0p-53 + 0x1.0p-54; }
-static inline double u32d(uint32_t x) { return ((double)x + 0.5) * 0x1.0p-32; }
+static inline double u53(uint64_t x) { return hb_rng_u53(x); }
+static inline double u32d(uint32_t x) { return hb_rng_u32(x); }
 static inline uint64_t mulhi64(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
 
 /* Philox slot map (must match hydrobayes_b200/csrc/hb_rng.cuh) */
@@ -538,8 +539,7 @@ static int calc_prop(const ctx_t* c, int64_t i_gen, int64_t j, const double* x, 
       if (tape_mode) zeta = tp->zeta[rix * d + k];
       else {
         phx_slot(&ph, SLOT_DIM0 + (uint32_t)k, w);
-        float u1 = (float)u32d(w[2]), u2 = (float)u32d(w[3]);
-        zeta = cfg->c_star * (double)(sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2));
+        zeta = cfg->c_star * hb_rng_normal(w[2], w[3]);
         if (rec) { ((double*)rec->zt)[rix * d + k] = u32d(w[0]); ((double*)rec->lambda)[rix * d + k] = 0; }
       }
       if (rec) ((double*)rec->zeta)[rix * d + k] = zeta;
@@ -563,9 +563,8 @@ static int calc_prop(const ctx_t* c, int64_t i_gen, int64_t j, const double* x, 
       else {
         phx_slot(&ph, SLOT_DIM0 + (uint32_t)k, w);
         zt[k] = u32d(w[0]);
-        lam_k[k] = -cfg->c_val + (2 * cfg->c_val) * u32d(w[1]);
-        float u1 = (float)u32d(w[2]), u2 = (float)u32d(w[3]);
-        zeta_k[k] = cfg->c_star * (double)(sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2));
+        lam_k[k] = hb_rng_lambda(w[1], cfg->c_val);
+        zeta_k[k] = cfg->c_star * hb_rng_normal(w[2], w[3]);
       }
       if (rec) ((double*)rec->zt)[rix * d + k] = zt[k];
     }

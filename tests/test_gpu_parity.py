@@ -56,8 +56,9 @@ def test_hydromodel_series_bit_exact(hb, oracle):
     y = hb.HydroModel(P, K)
     for i, k in enumerate(K):
         assert np.array_equal(y[i], oracle.hydromodel(P, k))   # same IEEE operations in the same order
-    np.testing.assert_array_equal(hb.HydroModel([0, 1, 2, 0, 5], 0.5),
-                                  [1 / 3, 5 / 9, 1.037037037037037, 0.691358024691358, 2.1275720164609053])
+    np.testing.assert_array_equal(hb.HydroModel([0, 1, 2, 0, 5], 0.5), oracle.hydromodel([0, 1, 2, 0, 5], 0.5))
+    np.testing.assert_allclose(hb.HydroModel([0, 1, 2, 0, 5], 0.5),
+                               [1 / 3, 5 / 9, 1.037037037037037, 0.691358024691358, 2.1275720164609053], rtol=1e-15)
     with pytest.raises(hb.HbError):
         hb.HydroModel([0, 1], -0.5)
     with pytest.raises(hb.HbError):
@@ -170,6 +171,9 @@ def test_replay_sliced_run_equals_single_run(hb, oracle):
 # ---------------------------------------------------------------- native RNG (Philox) vs the oracle's Philox -----
 @pytest.mark.parametrize("case", ["mixture", "tdist", "hydro"])
 def test_native_rng_matches_oracle_philox(hb, oracle, case):
+    # The draw transforms (include/hydrobayes_b200_rng.h) use correctly rounded IEEE operations only, so the device and
+    # the oracle see bit-identical draws; without that, DREAM's population map (gamma = 1.68 for d = 1) amplifies a
+    # 1e-18 difference in one zeta value to 1e-9 within ~40 generations.
     if case == "mixture":
         cfg = A.default_config(nc=64, t=600, d=1, lik=1, seed=99, record_accept=1); tgt = "mixture"; x0 = H.x0_mixture(64); kw = {}
     elif case == "tdist":
@@ -180,7 +184,7 @@ def test_native_rng_matches_oracle_philox(hb, oracle, case):
         tgt = "HydroModel"; x0 = H.x0_hydro(20); kw = dict(par_min=[0.01], par_max=[2.0], forcing=P, obs=obs)
     ora = oracle.run(cfg, tgt, x0, **kw)
     dev = H.run_device(cfg, tgt, x0, **kw)
-    H.assert_run_parity(dev, ora, rtol=1e-9, atol=1e-12, check_fx=False)
+    H.assert_run_parity(dev, ora, rtol=1e-11, atol=0.0, check_fx=False)
 
 
 def test_native_mixture_moments(hb):
@@ -219,9 +223,8 @@ def test_c2_size_properties(hb):
     np.testing.assert_allclose(ch[:, d + 2, :], ch[:, d, :] + ch[:, d + 1, :], rtol=1e-14)   # lpost = lp + ll
     assert (ch[:, d, :] == 0).all()                                                          # flat prior
     ar = dev["AR"]
-    assert np.all(np.diff(ar[:, 0]) == nc * 10)                                              # cumulative n_eval
+    assert ar[1, 0] == nc * 10 and np.all(np.diff(ar[1:, 0]) == nc * 10)                     # cumulative n_eval (:430)
     np.testing.assert_allclose(dev["CR"][:, 1:].sum(axis=1), 1.0, rtol=1e-12)                # pCR normalised
-    acc = dev["accept"].reshape(-1, 10, nc)[: (t - 1) // 10]                                  # generations 2..
     # accepted fraction per AR interval equals the recorded accept mask (intervals end at i %% 10 == 0)
     a = dev["accept"]
     for r in range(1, ar.shape[0]):
