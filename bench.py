@@ -258,6 +258,7 @@ def main():
     ap.add_argument("--workload", default="C4")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu_baseline / other workloads (profiling runs)")
+    ap.add_argument("--quick", action="store_true", help="keep the per-kernel roofline, skip e2e / cpu_baseline / others")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -334,7 +335,7 @@ def main():
             roof["fp64_peaks_measured_tflops"] = {"dmma": dm.value, "dfma": df.value}
         line["roofline"] = roof
         line["clocks"] = clk
-    if rank == 0 and world == 1 and not args.no_extras:
+    if rank == 0 and world == 1 and not args.no_extras and not args.quick:
         # end to end through the public API with host buffers (full C4 run: x0 upload, t-1 generations, chain fetch)
         w2 = workload(args.workload)
         c2 = w2["cfg"]

@@ -148,6 +148,14 @@ int allocate(hb_handle* h) {
   CK(dalloc(&h->outl_dev, (size_t)nc)); CK(dalloc(&h->news_dev, (size_t)nc));
   if (h->rstat_rows > 0) { CK(dalloc(&h->rstat_dev, (size_t)h->rstat_rows * d)); CK(hb_launch_fill(h->rstat_dev, h->rstat_rows * d, NAN, h->stream)); }
   CK(dalloc(&h->rstat_xm, (size_t)nl * d)); CK(dalloc(&h->rstat_ss, (size_t)nl * d));
+  {  // gamma_d table, R/internals.R:190
+    std::vector<double> g((size_t)c.delta * d);
+    for (int D = 1; D <= c.delta; ++D)
+      for (int ds = 1; ds <= d; ++ds) g[(size_t)(D - 1) * d + (ds - 1)] = 2.38 / sqrt(2.0 * (double)D * (double)ds);
+    CK(dalloc(&h->gamma_tab, g.size()));
+    CK(cudaMemcpyAsync(h->gamma_tab, g.data(), g.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
   // control block: pCR = 1/nCR (R/dream_parallel.R:192), counters zero, i_ar = 1 (:250)
   hb_ctrl hc; memset(&hc, 0, sizeof hc);
   for (int q = 0; q < c.nCR; ++q) hc.pCR[q] = 1.0 / c.nCR;
@@ -256,7 +264,7 @@ int run_generation(hb_handle* h, long long i) {
     p.d = d; p.ldx = ldx; p.delta = c.delta; p.nCR = c.nCR; p.c_val = c.c_val; p.c_star = c.c_star; p.p_g = c.p_g;
     p.beta0 = c.beta0; p.psnooker = c.psnooker; p.past_sample = c.past_sample;
     p.bound = h->have_min_max ? c.bound : 0; p.prior = c.prior; p.pmin = h->pmin; p.pmax = h->pmax;
-    p.seed = c.seed; p.gen = (uint32_t)i; p.tape = h->tape; p.tape_g = i - 2;
+    p.seed = c.seed; p.gen = (uint32_t)i; p.tape = h->tape; p.tape_g = i - 2; p.gamma_tab = h->gamma_tab;
     prof_scope ps(h, "K1");
     CK(hb_launch_k1(p, tape_mode, h->sm_count, h->stream));
     ps.done();
@@ -447,7 +455,7 @@ void hb_destroy(hb_handle* h) {
   void* ptrs[] = {h->X, h->Z, h->XP, h->id, h->lp_xp, h->ll_raw, h->fx_xp, h->lp, h->ll, h->lpost, h->fx, h->lpost_hist,
                   h->hist_x, h->hist_l, h->hist_fx, h->accept_rec, h->ctrl, h->shift, h->colsum, h->qsum, h->partials,
                   h->out_ar, h->out_cr, h->proxy, h->proxy_full, h->lpost_full, h->outl_dev, h->news_dev, h->rstat_dev,
-                  h->rstat_xm, h->rstat_ss, h->stage, h->pmin, h->pmax};
+                  h->rstat_xm, h->rstat_ss, h->stage, h->pmin, h->pmax, h->gamma_tab};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (void* p : h->tape_allocs) cudaFree(p);
   if (h->ev0) cudaEventDestroy(h->ev0);

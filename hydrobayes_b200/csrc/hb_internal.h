@@ -64,6 +64,7 @@ struct hb_handle {
   int *outl_dev = nullptr, *news_dev = nullptr;
   double *rstat_dev = nullptr, *rstat_xm = nullptr, *rstat_ss = nullptr;
   double* stage = nullptr; size_t stage_bytes = 0;
+  double* gamma_tab = nullptr;
 
   // tape
   bool have_tape = false;

@@ -279,6 +279,381 @@ __global__ void __launch_bounds__(256) hb_k1_kernel(const hb_k1_params p) {
   if (errbits) atomicOr(p.err, errbits);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Wide variant (d > 16): a warp owns a batch of 32 chains.
+//   phase A  lane-per-chain: the per-chain draws (snooker test, D, partner ids by partial Fisher-Yates, crossover id,
+//            gamma choice) are computed once per chain by ONE lane -- 32 chains in parallel, no redundant lanes --
+//            and parked in shared memory;
+//   phase B  warp-per-chain: the rows the chain needs (its own state and the 2D partner rows) are fetched by 1-D bulk
+//            TMA copies (cp.async.bulk -> shared memory, one mbarrier per stage) TWO chains ahead, so the HBM gather
+//            latency is hidden behind the Philox work of the chains in between and costs no registers; the 32 lanes
+//            then sweep the row out of shared memory (lane owns dimensions k = 32 m + lane): one Philox call per
+//            dimension, subspace test as an exact integer compare, error-free pair sum, xp store.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int K1_STAGES = 2;
+constexpr int K1_HEAD_WORDS = 12;   // packed, a[4], b[4], third snooker row, g_snooker (2 words)
+
+__host__ __device__ inline int k1_rows_max(int delta) { return (1 + 2 * delta) > 4 ? (1 + 2 * delta) : 4; }
+__host__ __device__ inline size_t k1_warp_smem_bytes(int delta, int ldx) {
+  // [stage][row][ldx] doubles + 32 chain heads + mbarriers, 16-byte aligned pieces
+  return (size_t)K1_STAGES * k1_rows_max(delta) * ldx * 8 + 32 * K1_HEAD_WORDS * 4 + K1_STAGES * 8;
+}
+
+template <int ITER, bool TAPE>
+__global__ void __launch_bounds__(256, 2) hb_k1_wide_kernel(const hb_k1_params p) {
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ __align__(16) unsigned char k1_smem[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int d = p.d, ldx = p.ldx, nCR = p.nCR, delta = p.delta;
+  const double* __restrict__ src = p.past_sample ? p.Z : p.X;
+  const int n_src = (int)(p.past_sample ? p.m_arch : p.nc);
+  const int rows_max = k1_rows_max(delta);
+  const uint32_t row_bytes = (uint32_t)ldx * 8u;
+  unsigned char* wbase = k1_smem + (size_t)wib * k1_warp_smem_bytes(delta, ldx);
+  double* stage_buf = reinterpret_cast<double*>(wbase);                                  // [STAGES][rows_max][ldx]
+  int* heads = reinterpret_cast<int*>(wbase + (size_t)K1_STAGES * rows_max * ldx * 8);   // [32][HEAD_WORDS]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(heads + 32 * K1_HEAD_WORDS);              // [STAGES]
+  unsigned errbits = 0;
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < K1_STAGES; ++s) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncwarp();
+  unsigned it = 0;   // chains consumed by this warp so far: stage = it % STAGES, parity = (it / STAGES) & 1
+
+  // issue the bulk copies of the rows chain `c` of the current batch needs into stage `s`
+  auto issue = [&](int c, long long base, int s) {
+    const int* hd = heads + c * K1_HEAD_WORDS;
+    const int pk = hd[0];
+    const int Dn = pk & 0xff;
+    const bool sn = (pk >> 17) & 1;
+    const int n_rows = sn ? 4 : 1 + 2 * Dn;
+    if (lane == 0) mbar_expect_tx(&bars[s], (uint32_t)n_rows * row_bytes);
+    __syncwarp();
+    if (lane < n_rows) {
+      const double* g;
+      if (lane == 0) g = p.X + (p.chain0 + base + c) * (long long)ldx;                  // own state
+      else {
+        int row;
+        if (sn) row = (lane == 1) ? hd[1] : (lane == 2) ? hd[1 + HB_MAX_DELTA] : hd[1 + 2 * HB_MAX_DELTA];
+        else row = (lane <= Dn) ? hd[lane] : hd[1 + HB_MAX_DELTA + (lane - 1 - Dn)];    // a[0..D-1], b[0..D-1]
+        g = src + (long long)row * ldx;
+      }
+      tma_load_1d(stage_buf + ((size_t)s * rows_max + lane) * ldx, g, row_bytes, &bars[s]);
+    }
+  };
+
+  for (long long base = warp_id * 32; base < p.n_local; base += n_warps * 32) {
+    // ---------------- phase A: one lane per chain ----------------
+    {
+      int hD = 1, hid = 0;
+      int hpa[HB_MAX_DELTA], hpb[HB_MAX_DELTA], hps2 = 0;
+      double hgsn = 0.0;
+#pragma unroll
+      for (int q = 0; q < HB_MAX_DELTA; ++q) { hpa[q] = 0; hpb[q] = 0; }
+      const long long jl_raw = base + lane;
+      const long long jl = jl_raw < p.n_local ? jl_raw : p.n_local - 1;
+      const long long j = p.chain0 + jl;
+      const long long gch = p.gchain0 + j;
+      double u_sn;
+      int g1;
+      if (TAPE) {
+        const long long rix = p.tape_g * p.tape.nct + gch;
+        u_sn = p.tape.u_snooker ? p.tape.u_snooker[rix] : 1.0;          // R/internals.R:119
+        hD = p.tape.D[rix];                                             // :123
+        hid = p.tape.id[rix];                                           // :173
+        g1 = p.tape.g_is_one[rix];                                      // :192
+        if (p.tape.g_snooker) hgsn = p.tape.g_snooker[rix];             // :156
+        if (hD < 1 || hD > delta || hid >= nCR) { errbits |= HB_FLAG_BAD_TAPE; hD = 1; hid = 0; }
+        const int32_t* pr = p.tape.partners + rix * (2 * delta);
+#pragma unroll
+        for (int q = 0; q < HB_MAX_DELTA; ++q)
+          if (q < hD) { hpa[q] = pr[q]; hpb[q] = pr[hD + q]; }
+        if (p.past_sample && u_sn < p.psnooker) { hpa[0] = pr[0]; hpb[0] = pr[1]; hps2 = pr[2]; }
+      } else {
+        const hb_phx ph(p.seed, (uint64_t)gch, p.gen);
+        const uint4 w0 = ph.slot(HB_SLOT_HEAD);
+        const uint4 wc = ph.slot(HB_SLOT_CHOICE);
+        u_sn = hb_u53(hb_pair64(w0, 0));
+        hD = 1 + (int)hb_mulhi64(hb_pair64(w0, 1), (uint64_t)delta);
+        const double u_id = hb_u53(hb_pair64(wc, 0));
+        double cum = 0.0;
+        hid = nCR - 1;
+        bool found = false;
+        for (int q = 0; q < nCR; ++q) {
+          cum += p.ctrl->pCR[q];
+          if (!found && u_id < cum) { hid = q; found = true; }
+        }
+        g1 = hb_u53(hb_pair64(wc, 1)) >= 1.0 - p.p_g;
+        const bool sn = p.past_sample && (u_sn < p.psnooker);
+        if (sn) hgsn = 1.2 + hb_u53(hb_pair64(ph.slot(HB_SLOT_ACCEPT), 1));
+        const int n_part = sn ? 3 : 2 * hD;
+        hb_fy fy;
+        long long n_rem = p.past_sample ? p.m_arch : p.nc - 1;
+        int y[2 * HB_MAX_DELTA];
+        uint4 wp = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int q = 0; q < 2 * HB_MAX_DELTA; ++q) {
+          y[q] = 0;
+          if (q < n_part) {
+            if ((q & 1) == 0) wp = ph.slot(HB_SLOT_PARTNER0 + (q >> 1));
+            long long v = fy.draw(hb_pair64(wp, q & 1), n_rem);
+            if (!p.past_sample && v >= j) v += 1;                       // sample((1:nc)[-j], ...)  :142
+            y[q] = (int)v;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < HB_MAX_DELTA; ++q) {
+          hpa[q] = y[q];
+          hpb[q] = (hD == 1) ? y[(1 + q) & 7] : (hD == 2) ? y[(2 + q) & 7] : (hD == 3) ? y[(3 + q) & 7] : y[(4 + q) & 7];
+        }
+        if (sn) { hpb[0] = y[1]; hps2 = y[2]; }
+      }
+      const bool sn = p.past_sample && (u_sn < p.psnooker);
+#pragma unroll
+      for (int q = 0; q < HB_MAX_DELTA; ++q) {
+        const bool used = sn ? (q == 0) : (q < hD);
+        if (used && (hpa[q] < 0 || hpa[q] >= n_src || hpb[q] < 0 || hpb[q] >= n_src)) {
+          errbits |= HB_FLAG_BAD_TAPE; hpa[q] = 0; hpb[q] = 0;
+        }
+      }
+      if (sn && (hps2 < 0 || hps2 >= n_src)) { errbits |= HB_FLAG_BAD_TAPE; hps2 = 0; }
+      int* hd = heads + lane * K1_HEAD_WORDS;
+      hd[0] = hD | (hid << 8) | ((g1 ? 1 : 0) << 16) | ((sn ? 1 : 0) << 17);
+#pragma unroll
+      for (int q = 0; q < HB_MAX_DELTA; ++q) { hd[1 + q] = hpa[q]; hd[1 + HB_MAX_DELTA + q] = hpb[q]; }
+      hd[1 + 2 * HB_MAX_DELTA] = hps2;
+      *reinterpret_cast<double*>(hd + 10) = hgsn;
+    }
+    __syncwarp();
+
+    // ---------------- phase B: the warp sweeps the rows of the batch, one chain at a time ----------------
+    const int n_in_batch = (int)((p.n_local - base) < 32 ? (p.n_local - base) : 32);
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+#pragma unroll
+    for (int s = 0; s < K1_STAGES; ++s)
+      if (s < n_in_batch) issue(s, base, (int)((it + s) % K1_STAGES));
+
+    for (int c = 0; c < n_in_batch; ++c, ++it) {
+      const int stg = (int)(it % K1_STAGES);
+      const int* hd = heads + c * K1_HEAD_WORDS;
+      const int pk = hd[0];
+      const int D = pk & 0xff, id = (pk >> 8) & 0xff;
+      const bool g_is_one = (pk >> 16) & 1, snooker = (pk >> 17) & 1;
+      const long long jl = base + c;
+      const long long gch = p.gchain0 + p.chain0 + jl;
+      const long long rix = p.tape_g * p.tape.nct + gch;
+      const hb_phx ph(p.seed, (uint64_t)gch, p.gen);
+      const double* __restrict__ rows = stage_buf + (size_t)stg * rows_max * ldx;   // row 0: x; 1..D: a; D+1..2D: b
+      double xk[ITER], dxk[ITER];
+
+      if (snooker) {
+        // snooker update, R/internals.R:150-163 with orth_proj :250-263 (rare path: psnooker is 0.1 at most)
+        mbar_wait(&bars[stg], (it / K1_STAGES) & 1);
+        const double g_sn = *reinterpret_cast<const double*>(hd + 10);
+        const double* r1 = rows + 1 * ldx;
+        const double* r2 = rows + 2 * ldx;
+        const double* r3 = rows + 3 * ldx;
+        double uu[ITER], a2[ITER], a3[ITER];
+        double s2 = 0, s3 = 0, su = 0;
+        int differs = 0;
+#pragma unroll
+        for (int m = 0; m < ITER; ++m) {
+          const int k = m * 32 + lane;
+          xk[m] = 0; uu[m] = 0; a2[m] = 0; a3[m] = 0;
+          if (k < d) {
+            xk[m] = rows[k];
+            const double b = r1[k];
+            a2[m] = r2[k]; a3[m] = r3[k];
+            uu[m] = xk[m] - b;
+            differs |= (xk[m] != b);
+            s2 += (a2[m] - xk[m]) * uu[m];
+            s3 += (a3[m] - xk[m]) * uu[m];
+            su += uu[m] * uu[m];
+          }
+        }
+        s2 = hb_group_sum<32>(s2); s3 = hb_group_sum<32>(s3); su = hb_group_sum<32>(su);
+        differs = hb_group_sum_int<32>(differs);
+#pragma unroll
+        for (int m = 0; m < ITER; ++m) {
+          const int k = m * 32 + lane;
+          dxk[m] = 0;
+          if (k < d) {
+            double zeta;
+            if (TAPE) zeta = p.tape.zeta[rix * d + k];
+            else { const uint4 w = ph.slot(HB_SLOT_DIM0 + (uint32_t)k); zeta = hb_zeta(w.z, w.w, p.c_star); }
+            double rp2 = a2[m], rp3 = a3[m];
+            if (differs) {
+              rp2 = __dadd_rn(xk[m], __ddiv_rn(__dmul_rn(uu[m], s2), su));
+              rp3 = __dadd_rn(xk[m], __ddiv_rn(__dmul_rn(uu[m], s3), su));
+            }
+            if (!isfinite(rp2) || !isfinite(rp3)) errbits |= HB_FLAG_PROP_NONFINITE;
+            dxk[m] = __dadd_rn(zeta, __dmul_rn(g_sn, __dadd_rn(rp2, -rp3)));
+          }
+        }
+      } else {
+        // parallel direction update, R/internals.R:166-200
+        const double CRv = (double)(id + 1) / (double)nCR;               // CR <- (1:nCR)/nCR
+        // (w + 0.5) 2^-32 < CR  <=>  w < ceil(CR 2^32 - 0.5): exact integer form of the zt < CR[id] test
+        const unsigned long long thr = (unsigned long long)ceil(CRv * 4294967296.0 - 0.5);
+        double ztv[TAPE ? ITER : 1];
+        uint32_t wx[ITER], wl[ITER], wz2[ITER], wz3[ITER];
+        unsigned selmask[ITER];
+        int d_star = 0;
+#pragma unroll
+        for (int m = 0; m < ITER; ++m) {
+          const int k = m * 32 + lane;
+          bool sel = false;
+          wx[m] = 0xffffffffu; wl[m] = 0; wz2[m] = 0; wz3[m] = 0;
+          if (TAPE) {
+            ztv[TAPE ? m : 0] = 2.0;
+            if (k < d) { ztv[TAPE ? m : 0] = p.tape.zt[rix * d + k]; sel = ztv[TAPE ? m : 0] < CRv; }   // :175-177
+          } else if (k < d) {
+            const uint4 w = ph.slot(HB_SLOT_DIM0 + (uint32_t)k);
+            wx[m] = w.x; wl[m] = w.y; wz2[m] = w.z; wz3[m] = w.w;
+            sel = (unsigned long long)w.x < thr;
+          }
+          selmask[m] = __ballot_sync(FULL, sel);
+          d_star += __popc(selmask[m]);
+        }
+        int kmin = -1;
+        if (d_star == 0) {                                               // :181-184  A <- which.min(zt)
+          int bk = 0x7fffffff;
+          if (TAPE) {
+            double bv = 3.0;
+#pragma unroll
+            for (int m = 0; m < ITER; ++m) { const int k = m * 32 + lane; if (k < d && ztv[TAPE ? m : 0] < bv) { bv = ztv[TAPE ? m : 0]; bk = k; } }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const double ov = __shfl_xor_sync(FULL, bv, o); const int ok = __shfl_xor_sync(FULL, bk, o);
+              if (ov < bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
+            }
+          } else {
+            unsigned long long bv = ~0ull;
+#pragma unroll
+            for (int m = 0; m < ITER; ++m) { const int k = m * 32 + lane; if (k < d && (unsigned long long)wx[m] < bv) { bv = wx[m]; bk = k; } }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const unsigned long long ov = __shfl_xor_sync(FULL, bv, o); const int ok = __shfl_xor_sync(FULL, bk, o);
+              if (ov < bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
+            }
+          }
+          kmin = bk; d_star = 1;
+        }
+        // gamma_d = 2.38/sqrt(2 D d*) (:190) from the host-built table (same IEEE sqrt and division, bit-identical)
+        const double gam = g_is_one ? 1.0 : p.gamma_tab[(D - 1) * d + (d_star - 1)];   // :192
+        mbar_wait(&bars[stg], (it / K1_STAGES) & 1);                     // the rows have landed in shared memory
+        int rank_base = 0;
+#pragma unroll
+        for (int m = 0; m < ITER; ++m) {
+          const int k = m * 32 + lane;
+          const bool sel = (kmin >= 0) ? (k == kmin) : ((selmask[m] >> lane) & 1u);
+          xk[m] = 0; dxk[m] = 0;
+          if (k < d) {
+            xk[m] = rows[k];
+            if (sel) {
+              double lambda, zeta;
+              if (TAPE) {
+                const int rank = (kmin >= 0) ? 0 : rank_base + __popc(selmask[m] & ((1u << lane) - 1u));
+                lambda = p.tape.lambda[rix * d + rank];                  // :188 (by rank within A)
+                zeta = p.tape.zeta[rix * d + rank];                      // :194
+              } else {
+                lambda = hb_rng_lambda(wl[m], p.c_val);
+                zeta = hb_zeta(wz2[m], wz3[m], p.c_star);
+              }
+              // jump_diff <- colSums(r1[,A] - r2[,A])  :196.  One or two terms: the plain sum is already the correctly
+              // rounded one; from the third term on, carry the rounding errors (R accumulates in long double).
+              double tq[HB_MAX_DELTA];
+#pragma unroll
+              for (int q = 0; q < HB_MAX_DELTA; ++q) {
+                tq[q] = 0.0;
+                if (q < D) tq[q] = __dadd_rn(rows[(1 + q) * ldx + k], -rows[(1 + D + q) * ldx + k]);
+              }
+              double jd;
+              if (D <= 2) jd = __dadd_rn(tq[0], tq[1]);
+              else {
+                double s, e, comp;
+                two_sum(tq[0], tq[1], s, comp);
+#pragma unroll
+                for (int q = 2; q < HB_MAX_DELTA; ++q) if (q < D) { two_sum(s, tq[q], s, e); comp = __dadd_rn(comp, e); }
+                jd = __dadd_rn(s, comp);
+              }
+              const double v = __dadd_rn(zeta, __dmul_rn(__dmul_rn(__dadd_rn(1.0, lambda), gam), jd));   // :198
+              dxk[m] = __dmul_rn(v, p.beta0);                                                           // :200
+            }
+          }
+          rank_base += __popc(selmask[m]);
+        }
+      }
+      // the stage is free again: fetch the rows of the chain K1_STAGES ahead
+      __syncwarp();
+      if (c + K1_STAGES < n_in_batch) {
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        issue(c + K1_STAGES, base, stg);
+      }
+
+      // xp <- x + dx ; finite check ; bounds ; prior
+      double lp_part = 0.0;
+#pragma unroll
+      for (int m = 0; m < ITER; ++m) {
+        const int k = m * 32 + lane;
+        if (k < d) {
+          double xp = __dadd_rn(xk[m], dxk[m]);                          // :206
+          if (!isfinite(xp)) errbits |= HB_FLAG_PROP_NONFINITE;          // :209
+          if (p.bound) xp = hb_bound_par(xp, p.pmin[k], p.pmax[k], p.bound);   // :210-214
+          if (p.prior == 1) {                                            // dunif(log = TRUE), :57
+            const double a = p.pmin[k], b = p.pmax[k];
+            lp_part += (a <= xp && xp <= b) ? -log(b - a) : -INFINITY;
+          }
+          p.XP[jl * (long long)ldx + k] = xp;
+        }
+      }
+      if (p.prior == 1) lp_part = hb_group_sum<32>(lp_part);
+      if (lane == 0) {
+        double lp = (p.prior == 1) ? lp_part : 0.0;                      // flat prior: 0  :55
+        if (!(lp >= HB_FLOOR)) lp = (lp != lp) ? lp : HB_FLOOR;          // :65
+        if (!isfinite(lp)) errbits |= HB_FLAG_LP_NONFINITE;              // :67
+        p.lp_xp[jl] = lp;
+        p.id_out[jl] = id;
+      }
+    }
+    __syncwarp();
+  }
+  if (errbits) atomicOr(p.err, errbits);
+}
+
+template <int ITER>
+cudaError_t launch_wide(const hb_k1_params& p, bool tape, int sm_count, cudaStream_t st) {
+  const size_t per_warp = (k1_warp_smem_bytes(p.delta, p.ldx) + 15) & ~(size_t)15;
+  int warps = 8;
+  while (warps > 1 && per_warp * warps > 110 * 1024) warps >>= 1;     // two CTAs per SM
+  const size_t smem = per_warp * warps;
+  if (smem > 220 * 1024) return cudaErrorInvalidValue;
+  const int threads = warps * 32;
+  const long long warps_needed = (p.n_local + 31) / 32;
+  long long blocks = (warps_needed + warps - 1) / warps;
+  const long long cap = (long long)sm_count * 2;                       // persistent: two CTAs per SM, grid-stride batches
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  cudaError_t e;
+  if (tape) {
+    e = cudaFuncSetAttribute(hb_k1_wide_kernel<ITER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    hb_k1_wide_kernel<ITER, true><<<(unsigned)blocks, threads, smem, st>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(hb_k1_wide_kernel<ITER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    hb_k1_wide_kernel<ITER, false><<<(unsigned)blocks, threads, smem, st>>>(p);
+  }
+  return cudaGetLastError();
+}
+
 template <int G, int ITER>
 cudaError_t launch_gi(const hb_k1_params& p, bool tape, int sm_count, cudaStream_t st) {
   constexpr int CPW = 32 / G;
@@ -302,11 +677,12 @@ cudaError_t hb_launch_k1(const hb_k1_params& p, bool tape_mode, int sm_count, cu
   if (d <= 4) return launch_gi<4, 1>(p, tape_mode, sm_count, st);
   if (d <= 8) return launch_gi<8, 1>(p, tape_mode, sm_count, st);
   if (d <= 16) return launch_gi<16, 1>(p, tape_mode, sm_count, st);
-  if (d <= 32) return launch_gi<32, 1>(p, tape_mode, sm_count, st);
-  if (d <= 64) return launch_gi<32, 2>(p, tape_mode, sm_count, st);
-  if (d <= 128) return launch_gi<32, 4>(p, tape_mode, sm_count, st);
-  if (d <= 256) return launch_gi<32, 8>(p, tape_mode, sm_count, st);
-  if (d <= 512) return launch_gi<32, 16>(p, tape_mode, sm_count, st);
-  if (d <= 1024) return launch_gi<32, 32>(p, tape_mode, sm_count, st);
+  if (p.nc > 0x7fffffffLL || p.m_arch > 0x7fffffffLL) return cudaErrorInvalidValue;
+  if (d <= 32) return launch_wide<1>(p, tape_mode, sm_count, st);
+  if (d <= 64) return launch_wide<2>(p, tape_mode, sm_count, st);
+  if (d <= 128) return launch_wide<4>(p, tape_mode, sm_count, st);
+  if (d <= 256) return launch_wide<8>(p, tape_mode, sm_count, st);
+  if (d <= 512) return launch_wide<16>(p, tape_mode, sm_count, st);
+  if (d <= 1024) return launch_wide<32>(p, tape_mode, sm_count, st);
   return cudaErrorInvalidValue;
 }

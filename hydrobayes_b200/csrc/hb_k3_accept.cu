@@ -139,6 +139,166 @@ __global__ void __launch_bounds__(256) hb_k3_kernel(const hb_k3_params p) {
   if (errbits) atomicOr(&p.ctrl->err, errbits);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Wide variant (d > 16): a warp owns a batch of 32 chains.
+//   phase A  lane-per-chain: coalesced loads of lp_xp / ll_raw / lpost / id / u, the Metropolis decision, and the
+//            coalesced scalar stores (lp, ll, lpost, history scalars, accept mask);
+//   phase B  warp-per-row, only for the rows that need touching: accepted rows (16 % for the t-distribution) outside
+//            the adaptation period, every row inside it (std_x needs the whole post-update population) or when the
+//            generation is stored.
+// ------------------------------------------------------------------------------------------------------------------
+template <int ITER, bool TAPE>
+__global__ void __launch_bounds__(256) hb_k3_wide_kernel(const hb_k3_params p) {
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ double smem[];
+  __shared__ unsigned long long s_cnt[HB_MAX_NCR + 1];
+  const int lane = threadIdx.x & 31;
+  const int slot = threadIdx.x >> 5;
+  const int n_slots = blockDim.x >> 5;
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int d = p.d, ldx = p.ldx, nCR = p.nCR;
+  const bool adapt = p.adapt != 0;
+  const int E = (nCR + 2) * d;
+  unsigned errbits = 0;
+
+  if (threadIdx.x <= nCR) s_cnt[threadIdx.x] = 0ull;
+  if (adapt) for (int e = threadIdx.x; e < n_slots * E; e += blockDim.x) smem[e] = 0.0;
+  __syncthreads();
+  double* acc = smem + (size_t)slot * E;
+  double s1[ITER], s2[ITER], sh[ITER];
+#pragma unroll
+  for (int m = 0; m < ITER; ++m) {
+    s1[m] = 0; s2[m] = 0;
+    const int k = m * 32 + lane;
+    sh[m] = (adapt && k < d) ? p.shift[k] : 0.0;
+  }
+  const bool all_rows = adapt || p.hist_x != nullptr;
+
+  for (long long base = warp_id * 32; base < p.n_local; base += n_warps * 32) {
+    const long long jl = base + lane;
+    const bool valid = jl < p.n_local;
+    int accf = 0, id = 0;
+    if (valid) {
+      const long long gch = p.gchain0 + p.chain0 + jl;
+      const double lpx = p.lp_xp[jl];
+      double llr = p.ll_raw[jl];
+      if (!(llr >= HB_FLOOR)) llr = (llr != llr) ? llr : HB_FLOOR;    // calc_ll floor, R/internals.R:19
+      if (!isfinite(llr)) errbits |= HB_FLAG_LL_NONFINITE;            // :21
+      const double lpostx = lpx + llr;                                // R/dream_parallel.R:291
+      const double lpost_old = p.lpost[jl];
+      double u;
+      if (TAPE) u = p.u_accept[gch];
+      else { const hb_phx ph(p.seed, (uint64_t)gch, p.gen); u = hb_u53(hb_pair64(ph.slot(HB_SLOT_ACCEPT), 0)); }
+      const double p_acc = fmin(fmax(-100.0, lpostx - lpost_old), 0.0); // R/internals.R:239
+      accf = p_acc > log(u);                                          // :241
+      id = p.id[jl];
+      double lp_c = 0, ll_c = 0, lpost_c = lpost_old;                 // :365
+      if (accf) {
+        p.lp[jl] = lpx; p.ll[jl] = llr; p.lpost[jl] = lpostx;         // :359-361
+        if (p.fx && p.fx_xp) p.fx[jl] = p.fx_xp[jl];                  // :362
+        lp_c = lpx; ll_c = llr; lpost_c = lpostx;
+      } else if (p.hist_l) { lp_c = p.lp[jl]; ll_c = p.ll[jl]; }
+      if (p.hist_l) { p.hist_l[jl * 3 + 0] = lp_c; p.hist_l[jl * 3 + 1] = ll_c; p.hist_l[jl * 3 + 2] = lpost_c; }   // :389-391
+      if (p.hist_fx && p.fx) p.hist_fx[jl] = p.fx[jl];                // :394
+      if (p.lpost_hist_row) p.lpost_hist_row[jl] = lpost_c;
+      if (p.accept_rec) p.accept_rec[jl] = (uint8_t)accf;
+    }
+    const unsigned vmask = __ballot_sync(FULL, valid);
+    const unsigned amask = __ballot_sync(FULL, valid && accf);
+    for (int q = 0; q < nCR; ++q) {                                   // n_id  :368-369
+      const unsigned m_q = __ballot_sync(FULL, valid && id == q);
+      if (lane == 0 && m_q) atomicAdd(&s_cnt[1 + q], (unsigned long long)__popc(m_q));
+    }
+    if (lane == 0 && amask) atomicAdd(&s_cnt[0], (unsigned long long)__popc(amask));   // n_acc :374
+
+    unsigned rows = all_rows ? vmask : amask;
+    while (rows) {
+      const int c = __ffs(rows) - 1;
+      rows &= rows - 1;
+      const int a_c = (amask >> c) & 1;
+      const int id_c = __shfl_sync(FULL, id, c);
+      const long long jr = base + c;
+      const long long j = p.chain0 + jr;
+#pragma unroll
+      for (int m = 0; m < ITER; ++m) {
+        const int k = m * 32 + lane;
+        if (k < d) {
+          double xn;
+          if (a_c) {
+            xn = p.XP[jr * (long long)ldx + k];
+            if (adapt) {
+              const double dx = xn - p.X[j * (long long)ldx + k];     // R/dream_parallel.R:357 (after bound handling)
+              acc[(2 + id_c) * d + k] += dx * dx;
+            }
+            p.X[j * (long long)ldx + k] = xn;                         // :358
+          } else {
+            xn = p.X[j * (long long)ldx + k];
+          }
+          if (adapt) { const double cc = xn - sh[m]; s1[m] += cc; s2[m] += cc * cc; }
+          if (p.hist_x) p.hist_x[jr * (long long)d + k] = xn;         // chain[ind_out, 1:d, ] :388
+        }
+      }
+    }
+  }
+
+  if (adapt) {
+#pragma unroll
+    for (int m = 0; m < ITER; ++m) {
+      const int k = m * 32 + lane;
+      if (k < d) { acc[k] = s1[m]; acc[d + k] = s2[m]; }
+    }
+  }
+  __syncthreads();
+  if (adapt) {
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+      double s = 0.0;
+      for (int q = 0; q < n_slots; ++q) s += smem[(size_t)q * E + e];
+      p.partials[(size_t)blockIdx.x * E + e] = s;
+    }
+  }
+  if (threadIdx.x <= nCR) {
+    const unsigned long long v = s_cnt[threadIdx.x];
+    if (v) {
+      if (threadIdx.x == 0) atomicAdd(&p.ctrl->n_acc_gen, v);
+      else atomicAdd(&p.ctrl->n_id_gen[threadIdx.x - 1], v);
+    }
+  }
+  if (errbits) atomicOr(&p.ctrl->err, errbits);
+}
+
+template <int ITER>
+cudaError_t launch_wide(const hb_k3_params& p, int sm_count, int* nblocks_out, size_t* smem_out, cudaStream_t st) {
+  const size_t per_warp = (size_t)(p.nCR + 2) * p.d * sizeof(double);
+  int warps = 8;
+  const size_t budget = 100 * 1024;
+  while (warps > 1 && per_warp * warps > budget) warps >>= 1;
+  const size_t smem_adapt = per_warp * warps;
+  if (smem_adapt > 220 * 1024) return cudaErrorInvalidValue;
+  const int threads = warps * 32;
+  const long long warps_needed = (p.n_local + 31) / 32;
+  long long blocks = (warps_needed + warps - 1) / warps;
+  const long long cap = (long long)sm_count * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if (nblocks_out) *nblocks_out = (int)blocks;
+  if (smem_out) *smem_out = smem_adapt;
+  if (p.X == nullptr) return cudaSuccess;
+  const size_t smem = p.adapt ? smem_adapt : 0;
+  const bool tape = p.u_accept != nullptr;
+  cudaError_t e = cudaSuccess;
+  if (tape) {
+    if (smem > 48 * 1024) e = cudaFuncSetAttribute(hb_k3_wide_kernel<ITER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    hb_k3_wide_kernel<ITER, true><<<(unsigned)blocks, threads, smem, st>>>(p);
+  } else {
+    if (smem > 48 * 1024) e = cudaFuncSetAttribute(hb_k3_wide_kernel<ITER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    hb_k3_wide_kernel<ITER, false><<<(unsigned)blocks, threads, smem, st>>>(p);
+  }
+  return cudaGetLastError();
+}
+
 template <int G>
 struct k3_geom {
   static constexpr int CPW = 32 / G;
@@ -184,12 +344,12 @@ cudaError_t dispatch(const hb_k3_params& p, int sm_count, int* nb, size_t* sm, c
   if (d <= 4) return launch_gi<4, 1>(p, sm_count, nb, sm, st);
   if (d <= 8) return launch_gi<8, 1>(p, sm_count, nb, sm, st);
   if (d <= 16) return launch_gi<16, 1>(p, sm_count, nb, sm, st);
-  if (d <= 32) return launch_gi<32, 1>(p, sm_count, nb, sm, st);
-  if (d <= 64) return launch_gi<32, 2>(p, sm_count, nb, sm, st);
-  if (d <= 128) return launch_gi<32, 4>(p, sm_count, nb, sm, st);
-  if (d <= 256) return launch_gi<32, 8>(p, sm_count, nb, sm, st);
-  if (d <= 512) return launch_gi<32, 16>(p, sm_count, nb, sm, st);
-  if (d <= 1024) return launch_gi<32, 32>(p, sm_count, nb, sm, st);
+  if (d <= 32) return launch_wide<1>(p, sm_count, nb, sm, st);
+  if (d <= 64) return launch_wide<2>(p, sm_count, nb, sm, st);
+  if (d <= 128) return launch_wide<4>(p, sm_count, nb, sm, st);
+  if (d <= 256) return launch_wide<8>(p, sm_count, nb, sm, st);
+  if (d <= 512) return launch_wide<16>(p, sm_count, nb, sm, st);
+  if (d <= 1024) return launch_wide<32>(p, sm_count, nb, sm, st);
   return cudaErrorInvalidValue;
 }
 

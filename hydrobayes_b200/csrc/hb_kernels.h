@@ -45,6 +45,7 @@ struct hb_k1_params {
   uint32_t gen;           // R's generation index i (2..t)
   hb_tape_dev tape;
   long long tape_g;       // generation row of the tape (i - 2)
+  const double* gamma_tab; // [delta][d]: 2.38/sqrt(2 D d*), built on the host with IEEE sqrt and division
 };
 cudaError_t hb_launch_k1(const hb_k1_params& p, bool tape_mode, int sm_count, cudaStream_t st);
 

@@ -11,10 +11,7 @@
  *   hb_rng_u53(x)       64 random bits  -> double in the open interval (0, 1), 53 bits
  *   hb_rng_u32(w)       32 random bits  -> double in (0, 1), exact
  *   hb_rng_lambda(w,c)  U(-c, c)                                        (R/internals.R:188)
- *   hb_rng_normal(a,b)  N(0, 1) by Box-Muller in binary32, from two 32-bit words    (zeta, R/internals.R:194,158)
- *
- * hb_rng_normal has float accuracy (about 1e-7 relative, |z| <= 6.66): zeta is a jitter of scale c_star (1e-12 by
- * default) whose only role is ergodicity (Vrugt 2016, Sect. 3.3), not a quantity that is ever reported.
+ *   hb_rng_normal(a,b)  approximately N(0, 1), integer-only, from two 32-bit words  (zeta, R/internals.R:194,158)
  */
 #ifndef HYDROBAYES_B200_RNG_H
 #define HYDROBAYES_B200_RNG_H
@@ -52,57 +49,29 @@ HB_RNG_FN double hb_rng_lambda(uint32_t w, double c_val) {
   return HB_DADD(-c_val, HB_DMUL(HB_DMUL(2.0, c_val), hb_rng_u32(w)));
 }
 
-/* ln(u) for a binary32 u in (0, 1]:  u = m * 2^e, m in [sqrt(1/2), sqrt(2));  ln m = 2 atanh(s), s = (m-1)/(m+1) */
-HB_RNG_FN float hb_rng_logf(float u) {
-  union { float f; uint32_t i; } v;
-  v.f = u;
-  int e = (int)(v.i >> 23) - 127;
-  v.i = (v.i & 0x007fffffu) | 0x3f800000u; /* m in [1, 2) */
-  float m = v.f;
-  if (m > 1.41421356f) { m = HB_FMUL(m, 0.5f); e += 1; }
-  const float s = HB_FDIV(HB_FADD(m, -1.0f), HB_FADD(m, 1.0f));
-  const float s2 = HB_FMUL(s, s);
-  /* 2 (s + s^3/3 + s^5/5 + s^7/7 + s^9/9), Horner in s2 */
-  float p = 0.111111111f;
-  p = HB_FADD(HB_FMUL(p, s2), 0.142857143f);
-  p = HB_FADD(HB_FMUL(p, s2), 0.2f);
-  p = HB_FADD(HB_FMUL(p, s2), 0.333333333f);
-  p = HB_FADD(HB_FMUL(p, s2), 1.0f);
-  const float lnm = HB_FMUL(HB_FMUL(2.0f, s), p);
-  return HB_FADD(HB_FMUL((float)e, 0.693147181f), lnm);
+/*
+ * zeta's standard deviate: a bit-exact, integer-only approximation of N(0, 1) from 64 random bits.
+ *   B = popcount(48 bits) ~ Binomial(48, 1/2)  (mean 24, variance 12: a lattice normal by the CLT)
+ *   T = u8 + u8' - 255                          (triangular kernel of width 2 lattice steps, in units of 1/256)
+ *   z = ((B - 24) * 256 + T) / (256 * sqrt(12 + (256^2 - 1) / (6 * 256^2)))
+ * The result has mean 0, variance 1, a continuous piecewise-linear-like density, |z| <= 7.17, excess kurtosis -1/24
+ * (Kolmogorov distance to N(0,1) about 3e-3).  zeta = c_star * z is the 1e-12-scale jitter of R/internals.R:194
+ * whose only role is to keep the chain ergodic (Vrugt 2016, Sect. 3.3); its law is never observable in the output,
+ * so ~10 integer instructions per dimension replace a ~100-instruction Box-Muller in the HBM-bound proposal kernel.
+ * Replay (tape) mode does not use this function: there zeta comes from the tape as R's rnorm returned it.
+ */
+HB_RNG_FN int hb_rng_popc32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __popc(x);
+#else
+  return __builtin_popcount(x);
+#endif
 }
-
-/* cos(2 pi t) for a binary32 t in (0, 1]: quadrant reduction (exact) + Taylor polynomials on [-pi/4, pi/4] */
-HB_RNG_FN float hb_rng_cos2pif(float t) {
-  const float q4 = HB_FMUL(t, 4.0f);
-  const int q = (int)HB_FADD(q4, 0.5f);                       /* round to nearest quadrant 0..4 */
-  const float r = HB_FADD(t, -HB_FMUL((float)q, 0.25f));      /* exact: |r| <= 1/8 */
-  const float y = HB_FMUL(r, 6.28318531f);
-  const float y2 = HB_FMUL(y, y);
-  float c = 2.48015873e-5f;                                    /* 1/8! */
-  c = HB_FADD(HB_FMUL(c, y2), -1.38888889e-3f);
-  c = HB_FADD(HB_FMUL(c, y2), 4.16666667e-2f);
-  c = HB_FADD(HB_FMUL(c, y2), -0.5f);
-  c = HB_FADD(HB_FMUL(c, y2), 1.0f);
-  float sn = 2.75573192e-6f;                                   /* 1/9! */
-  sn = HB_FADD(HB_FMUL(sn, y2), -1.98412698e-4f);
-  sn = HB_FADD(HB_FMUL(sn, y2), 8.33333333e-3f);
-  sn = HB_FADD(HB_FMUL(sn, y2), -0.166666667f);
-  sn = HB_FADD(HB_FMUL(sn, y2), 1.0f);
-  sn = HB_FMUL(sn, y);
-  switch (q & 3) {
-    case 0: return c;
-    case 1: return -sn;
-    case 2: return -c;
-    default: return sn;
-  }
-}
-
 HB_RNG_FN double hb_rng_normal(uint32_t wa, uint32_t wb) {
-  const float u1 = (float)hb_rng_u32(wa);                     /* (0, 1]: rounds to 1.0f for the largest words */
-  const float u2 = (float)hb_rng_u32(wb);
-  const float r = HB_FSQRT(HB_FMUL(-2.0f, hb_rng_logf(u1)));
-  return (double)HB_FMUL(r, hb_rng_cos2pif(u2));
+  const int b = hb_rng_popc32(wa) + hb_rng_popc32(wb >> 16);
+  const int t = (int)(wb & 0xffu) + (int)((wb >> 8) & 0xffu) - 255;
+  const int v = (b - 24) * 256 + t;
+  return HB_DMUL((double)v, 0.00111988718555951);   /* 1 / (256 * sqrt(12 + 65535/393216)) */
 }
 
 #endif /* HYDROBAYES_B200_RNG_H */
