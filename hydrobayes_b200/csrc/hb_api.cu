@@ -232,11 +232,13 @@ int outlier_check(hb_handle* h, long long i) {
   std::vector<int> o32(outl.begin(), outl.end()), n32(news.begin(), news.end());
   CK(cudaMemcpyAsync(h->outl_dev, o32.data(), sizeof(int) * o32.size(), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->news_dev, n32.data(), sizeof(int) * n32.size(), cudaMemcpyHostToDevice, h->stream));
-  if (h->world > 1) return fail(h, HB_ERR_UNSUPPORTED, "outlier reset on a sharded population is not wired yet");
   double* hrow = (i <= h->H) ? h->lpost_hist + (i - 1) * nl : nullptr;
   {
     prof_scope ps(h, "OUTLIER");
-    CK(hb_launch_outlier_reset(h->X, h->ldx, h->d, h->lpost, hrow, h->outl_dev, h->news_dev, (int)o32.size(), nullptr, h->stream));
+    // the snapshot of lpost (all chains, pre-reset) keeps the copies independent of the order they run in
+    if (h->world == 1) CK(cudaMemcpyAsync(h->lpost_full, h->lpost, sizeof(double) * nc, cudaMemcpyDeviceToDevice, h->stream));
+    CK(hb_launch_outlier_reset(h->X, h->ldx, h->d, h->lpost, hrow, h->lpost_full, h->chain0, nl, h->outl_dev, h->news_dev,
+                               (int)o32.size(), h->stream));
     ps.done();
   }
   CK(cudaStreamSynchronize(h->stream));

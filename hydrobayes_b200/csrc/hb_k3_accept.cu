@@ -440,16 +440,20 @@ __global__ void hb_proxy_kernel(const double* __restrict__ hist, long long n, lo
 
 // x[outliers,] <- x[new_states,] ; dens[nrow, outliers] <- dens[nrow, new_states]  (R/internals.R:82-83).
 // new_states never contains an outlier, so sources are not modified by this kernel.
-__global__ void hb_outlier_reset_kernel(double* X, int ldx, int d, double* lpost, double* hist_row, const int* outl,
+// X is the full population replica (every rank applies the same copies); lpost / hist_row are the local shard
+// [chain0, chain0 + n_local); lpost_src holds the pre-reset lpost of ALL chains (the local array on one GPU, the
+// all-gathered copy on several).
+__global__ void hb_outlier_reset_kernel(double* X, int ldx, int d, double* lpost, double* hist_row,
+                                        const double* lpost_src, long long chain0, long long n_local, const int* outl,
                                         const int* news, int n_out) {
   const int q = blockIdx.x;
   if (q >= n_out) return;
   const long long dst = outl[q], srcc = news[q];
   for (int k = threadIdx.x; k < d; k += blockDim.x) X[dst * ldx + k] = X[srcc * ldx + k];
-  if (threadIdx.x == 0) {
-    const double v = lpost[srcc];
-    lpost[dst] = v;
-    if (hist_row) hist_row[dst] = v;
+  if (threadIdx.x == 0 && dst >= chain0 && dst < chain0 + n_local) {
+    const double v = lpost_src[srcc];
+    lpost[dst - chain0] = v;
+    if (hist_row) hist_row[dst - chain0] = v;
   }
 }
 
@@ -563,11 +567,12 @@ cudaError_t hb_launch_proxy(const double* lpost_hist, long long nc_local, long l
   return cudaGetLastError();
 }
 
-cudaError_t hb_launch_outlier_reset(double* X, int ldx, int d, double* lpost, double* lpost_hist_row, const int* outl,
-                                    const int* news, int n_out, double* scratch, cudaStream_t st) {
-  (void)scratch;
+cudaError_t hb_launch_outlier_reset(double* X, int ldx, int d, double* lpost, double* lpost_hist_row,
+                                    const double* lpost_src, long long chain0, long long n_local, const int* outl,
+                                    const int* news, int n_out, cudaStream_t st) {
   if (n_out <= 0) return cudaSuccess;
-  hb_outlier_reset_kernel<<<n_out, 128, 0, st>>>(X, ldx, d, lpost, lpost_hist_row, outl, news, n_out);
+  hb_outlier_reset_kernel<<<n_out, 128, 0, st>>>(X, ldx, d, lpost, lpost_hist_row, lpost_src, chain0, n_local, outl,
+                                                 news, n_out);
   return cudaGetLastError();
 }
 

@@ -99,7 +99,8 @@ cudaError_t hb_launch_finalize(const hb_fin_params& p, cudaStream_t st);
 cudaError_t hb_launch_proxy(const double* lpost_hist, long long nc_local, long long row0, long long row1,
                             long long ld, double* proxy, cudaStream_t st);
 cudaError_t hb_launch_outlier_reset(double* X, int ldx, int d, double* lpost, double* lpost_hist_row,
-                                    const int* outl, const int* news, int n_out, double* scratch, cudaStream_t st);
+                                    const double* lpost_src, long long chain0, long long n_local, const int* outl,
+                                    const int* news, int n_out, cudaStream_t st);
 
 // ---- history transposition into R's chain[out_t, d+3, nc] layout ----------------------------------------
 cudaError_t hb_launch_chain_transpose(const double* hist_x, const double* hist_l, long long out_t_alloc,

@@ -378,3 +378,40 @@ def HydroModel(forcing, param) -> np.ndarray:
     if rc != A.HB_OK:
         raise A.HbError(rc, err.value.decode())
     return out[0] if np.ndim(param) == 0 else out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# multi-GPU host plumbing (one process per GPU; torch.distributed is plumbing only)
+# ---------------------------------------------------------------------------------------------------------
+def shard_range(nc: int, rank: int, world: int):
+    """Block partition of the population: rank r owns chains [r*nc/world, (r+1)*nc/world) (hb_comm_init)."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    if nc % world:
+        raise ValueError("nc must be divisible by the number of GPUs")
+    nl = nc // world
+    return rank * nl, nl
+
+
+def broadcast_unique_id(make_id, rank: int, group=None) -> bytes:
+    """Rank 0 creates the 128-byte communicator id (hb_comm_unique_id) and every rank receives it."""
+    import torch.distributed as dist
+    obj = [make_id() if rank == 0 else None]
+    dist.broadcast_object_list(obj, src=0, group=group)
+    if not isinstance(obj[0], (bytes, bytearray)) or len(obj[0]) != 128:
+        raise ValueError("communicator id must be 128 bytes")
+    return bytes(obj[0])
+
+
+def gather_chain(shard: np.ndarray, world: int, group=None) -> np.ndarray:
+    """All ranks contribute chain[out_t, d+3, nc/world]; returns chain[out_t, d+3, nc] (chains are the slowest
+    dimension of R's layout, so rank shards concatenate along the last axis)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(np.ascontiguousarray(np.moveaxis(shard, 2, 0)))          # [nl, out_t, d+3]
+    if dist.get_backend(group) == "nccl":
+        t = t.cuda()
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t, group=group)
+    full = torch.cat(parts, dim=0).cpu().numpy()                                    # [nc, out_t, d+3]
+    return np.asfortranarray(np.moveaxis(full, 0, 2))
