@@ -52,7 +52,7 @@ class HbConfig(C.Structure):
         ("rng_mode", C.c_int32), ("record_accept", C.c_int32),
         ("seed", C.c_uint64),
         ("check_convergence", C.c_int32), ("store_fx", C.c_int32),
-        ("exchange", C.c_int32), ("reserved0", C.c_int32),
+        ("exchange", C.c_int32), ("run_offset", C.c_int32),
     ]
 
 

@@ -13,8 +13,13 @@
 #include "hb_internal.h"
 
 int hb_seq_supported(const hb_config* cfg, std::string& why);   // hb_seq.cu
-int hb_seq_run(hb_handle* h, long long n_generations);          // hb_seq.cu
+int hb_seq_generation(hb_handle* h, long long i);               // hb_seq.cu
+int hb_seq_allocate(hb_handle* h);
+int hb_seq_initialise(hb_handle* h);
 void hb_seq_destroy(hb_handle* h);
+int hb_seq_pull_outliers(hb_handle* h);
+int hb_hydro_init_batched(void** ctx, int d, int lik, const double* data, int64_t T, const double* obs, int64_t n_obs,
+                          long long n_runs, double glue_shape, char* err, int errlen);
 
 namespace {
 
@@ -119,7 +124,7 @@ int check_flags(hb_handle* h) {
 
 int allocate(hb_handle* h) {
   const hb_config& c = h->cfg;
-  const long long nl = h->n_local, nc = h->nc;
+  const long long nl = h->n_local, nc = h->modeb ? h->nct : h->nc;   // batched runs: all runs' chains, run-major
   const int d = h->d, ldx = h->ldx;
   CK(dalloc(&h->X, (size_t)nc * ldx));
   CK(cudaMemsetAsync(h->X, 0, (size_t)nc * ldx * sizeof(double), h->stream));
@@ -135,15 +140,16 @@ int allocate(hb_handle* h) {
   CK(dalloc(&h->hist_l, (size_t)h->out_t * nl * 3));
   if (c.store_fx) CK(dalloc(&h->hist_fx, (size_t)h->out_t * nl));
   if (c.record_accept) { CK(dalloc(&h->accept_rec, (size_t)(h->t - 1) * nl)); CK(cudaMemsetAsync(h->accept_rec, 0, (size_t)(h->t - 1) * nl, h->stream)); }
-  CK(dalloc(&h->ctrl, 1));
+  CK(dalloc(&h->ctrl, (size_t)h->cfg.n_runs));
   CK(dalloc(&h->shift, (size_t)d)); CK(dalloc(&h->colsum, (size_t)2 * d)); CK(dalloc(&h->qsum, (size_t)c.nCR * d));
   size_t smem = 0;
   h->k3_blocks = hb_k3_grid(nl, d, c.nCR, h->sm_count, &smem);
   if (h->k3_blocks < 1) return fail(h, HB_ERR_UNSUPPORTED, "d = %d with nCR = %d exceeds the shared-memory budget of K3", d, c.nCR);
   CK(dalloc(&h->partials, (size_t)h->k3_blocks * (c.nCR + 2) * d));
-  CK(dalloc(&h->out_ar, (size_t)h->ar_rows * h->ar_cols)); CK(dalloc(&h->out_cr, (size_t)h->cr_rows * h->cr_cols));
-  CK(hb_launch_fill(h->out_ar, h->ar_rows * h->ar_cols, NAN, h->stream));
-  CK(hb_launch_fill(h->out_cr, h->cr_rows * h->cr_cols, NAN, h->stream));
+  const long long nr = h->cfg.n_runs;
+  CK(dalloc(&h->out_ar, (size_t)nr * h->ar_rows * h->ar_cols)); CK(dalloc(&h->out_cr, (size_t)nr * h->cr_rows * h->cr_cols));
+  CK(hb_launch_fill(h->out_ar, nr * h->ar_rows * h->ar_cols, NAN, h->stream));
+  CK(hb_launch_fill(h->out_cr, nr * h->cr_rows * h->cr_cols, NAN, h->stream));
   CK(dalloc(&h->proxy, (size_t)nl)); CK(dalloc(&h->proxy_full, (size_t)nc)); CK(dalloc(&h->lpost_full, (size_t)nc));
   CK(dalloc(&h->outl_dev, (size_t)nc)); CK(dalloc(&h->news_dev, (size_t)nc));
   if (h->rstat_rows > 0) { CK(dalloc(&h->rstat_dev, (size_t)h->rstat_rows * d)); CK(hb_launch_fill(h->rstat_dev, h->rstat_rows * d, NAN, h->stream)); }
@@ -159,9 +165,11 @@ int allocate(hb_handle* h) {
   // control block: pCR = 1/nCR (R/dream_parallel.R:192), counters zero, i_ar = 1 (:250)
   hb_ctrl hc; memset(&hc, 0, sizeof hc);
   for (int q = 0; q < c.nCR; ++q) hc.pCR[q] = 1.0 / c.nCR;
-  hc.i_ar = 1; hc.cum_eval = (double)nc;
-  CK(cudaMemcpyAsync(h->ctrl, &hc, sizeof hc, cudaMemcpyHostToDevice, h->stream));
+  hc.i_ar = 1; hc.cum_eval = (double)h->nc;
+  std::vector<hb_ctrl> hcs((size_t)nr, hc);
+  CK(cudaMemcpyAsync(h->ctrl, hcs.data(), sizeof(hb_ctrl) * nr, cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  if (h->modeb) return hb_seq_allocate(h);
   return HB_OK;
 }
 
@@ -173,7 +181,7 @@ int initialise(hb_handle* h) {
   const double* Xl = h->X + h->chain0 * ldx;
   unsigned* errp = &h->ctrl->err;
   CK(hb_launch_prior(Xl, ldx, d, nl, c.prior, h->pmin, h->pmax, h->lp_xp, errp, h->stream)); h->launches++;
-  if (int rc = h->vt->launch(h->tctx, Xl, nl, d, ldx, h->ll_raw, h->fx_xp, h->stream)) return fail(h, rc, "target launch failed");
+  if (int rc = hb_target_launch(h, Xl, nl, h->chain0, 1)) return fail(h, rc, "target launch failed");
   h->launches++;
   CK(hb_launch_init_state(h->lp_xp, h->ll_raw, h->fx_xp, h->lp, h->ll, h->lpost, h->fx, h->lpost_hist, nl, errp, h->stream));
   CK(hb_launch_store_row(Xl, ldx, d, nl, h->lp, h->ll, h->lpost, h->fx, h->hist_x, h->hist_l, h->hist_fx, h->stream));
@@ -181,9 +189,17 @@ int initialise(hb_handle* h) {
   // shift for the one-pass column variance: chain 0 of the run
   CK(cudaMemcpyAsync(h->shift, h->X, sizeof(double) * d, cudaMemcpyDeviceToDevice, h->stream));
   // AR/CR row 1: out_AR[1,1] = out_CR[1,1] = nc ; out_AR[1,2] = NA ; out_CR[1,-1] = pCR   (:245-247)
-  std::vector<double> ar((size_t)h->ar_rows * h->ar_cols, NAN), cr((size_t)h->cr_rows * h->cr_cols, NAN);
-  ar[0] = (double)h->nc; cr[0] = (double)h->nc;
-  for (int q = 0; q < c.nCR; ++q) cr[(size_t)h->cr_rows * (q + 1)] = 1.0 / c.nCR;
+  const long long nr = c.n_runs;
+  const size_t ars = (size_t)h->ar_rows * h->ar_cols, crs = (size_t)h->cr_rows * h->cr_cols;
+  std::vector<double> ar(ars * nr, NAN), cr(crs * nr, NAN);
+  for (long long r = 0; r < nr; ++r) {
+    if (c.sweep == HB_SWEEP_SYNCHRONOUS) {
+      ar[r * ars] = (double)h->nc; cr[r * crs] = (double)h->nc;
+      for (int q = 0; q < c.nCR; ++q) cr[r * crs + (size_t)h->cr_rows * (q + 1)] = 1.0 / c.nCR;
+    } else {   // out_AR[1,] <- rep(0, nCR) ; out_CR[1,] <- pCR   (R/dream.R:193-194)
+      for (int q = 0; q < c.nCR; ++q) { ar[r * ars + (size_t)h->ar_rows * q] = 0.0; cr[r * crs + (size_t)h->cr_rows * q] = 1.0 / c.nCR; }
+    }
+  }
   CK(cudaMemcpyAsync(h->out_ar, ar.data(), ar.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->out_cr, cr.data(), cr.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -246,6 +262,57 @@ int outlier_check(hb_handle* h, long long i) {
   return HB_OK;
 }
 
+}  // namespace
+
+// K1 / K3 parameter blocks for a launch over items i -> chain first + i*stride (see hb_k1_params)
+hb_k1_params hb_make_k1(hb_handle* h, long long i, long long first, long long stride, long long n_items) {
+  const hb_config& c = h->cfg;
+  hb_k1_params p{};
+  p.X = h->X; p.Z = h->Z; p.m_arch = h->m_arch; p.XP = h->XP; p.id_out = h->id; p.lp_xp = h->lp_xp;
+  p.ctrl = h->ctrl; p.err = &h->ctrl->err; p.nc = h->nc; p.chain0 = first; p.stride = stride; p.n_local = n_items;
+  p.n_runs = h->cfg.n_runs; p.gchain0 = (long long)c.run_offset * h->nc;
+  p.d = h->d; p.ldx = h->ldx; p.delta = c.delta; p.nCR = c.nCR; p.c_val = c.c_val; p.c_star = c.c_star; p.p_g = c.p_g;
+  p.beta0 = c.beta0; p.psnooker = c.psnooker; p.past_sample = c.past_sample;
+  p.bound = h->have_min_max ? c.bound : 0; p.prior = c.prior; p.pmin = h->pmin; p.pmax = h->pmax;
+  p.seed = c.seed; p.gen = (uint32_t)i; p.tape = h->tape; p.tape_g = i - 2; p.gamma_tab = h->gamma_tab;
+  return p;
+}
+
+hb_k3_params hb_make_k3(hb_handle* h, long long i, long long first, long long stride, long long n_items, bool store,
+                        bool in_adapt, bool write_dx) {
+  const hb_config& c = h->cfg;
+  const long long nl = h->n_local;
+  const int d = h->d;
+  hb_k3_params p{};
+  p.X = h->X; p.XP = h->XP; p.XP_rw = h->XP; p.id = h->id; p.lp_xp = h->lp_xp; p.ll_raw = h->ll_raw;
+  p.fx_xp = c.store_fx ? h->fx_xp : nullptr;
+  p.lp = h->lp; p.ll = h->ll; p.lpost = h->lpost; p.fx = c.store_fx ? h->fx : nullptr;
+  p.lpost_hist_row = (i <= h->H) ? h->lpost_hist + (i - 1) * nl : nullptr;
+  if (store) {
+    p.hist_x = h->hist_x + (size_t)(h->ind_out - 1) * nl * d;
+    p.hist_l = h->hist_l + (size_t)(h->ind_out - 1) * nl * 3;
+    p.hist_fx = h->hist_fx ? h->hist_fx + (size_t)(h->ind_out - 1) * nl : nullptr;
+  }
+  p.accept_rec = h->accept_rec ? h->accept_rec + (size_t)(i - 2) * nl : nullptr;
+  p.ctrl = h->ctrl; p.shift = h->shift; p.partials = h->partials;
+  p.chain0 = first; p.stride = stride; p.n_local = n_items; p.nc = h->nc; p.n_runs = h->cfg.n_runs;
+  p.state0 = h->chain0; p.gchain0 = (long long)c.run_offset * h->nc;
+  p.d = d; p.ldx = h->ldx; p.nCR = c.nCR;
+  p.adapt = in_adapt; p.write_dx = write_dx; p.seed = c.seed; p.gen = (uint32_t)i;
+  p.u_accept = (c.rng_mode == HB_RNG_TAPE) ? h->tape.u_accept + (size_t)(i - 2) * h->tape.nct : nullptr;
+  return p;
+}
+
+int hb_target_launch(hb_handle* h, const double* x, long long n, long long first, long long stride) {
+  if (h->vt->launch_items && h->cfg.n_runs > 1)
+    return h->vt->launch_items(h->tctx, x, n, h->d, h->ldx, h->ll_raw, h->fx_xp, first, stride, h->nc, h->stream);
+  return h->vt->launch(h->tctx, x, n, h->d, h->ldx, h->ll_raw, h->fx_xp, h->stream);
+}
+
+int hb_fail(hb_handle* h, int code, const char* msg) { if (h) h->err = msg; return code; }
+
+namespace {
+
 int run_generation(hb_handle* h, long long i) {
   const hb_config& c = h->cfg;
   const long long nl = h->n_local;
@@ -259,39 +326,20 @@ int run_generation(hb_handle* h, long long i) {
   const bool upd = (i % c.update_interval == 0);
   const bool tape_mode = (c.rng_mode == HB_RNG_TAPE);
 
+  if (h->modeb) return hb_seq_generation(h, i);
   {  // K1
-    hb_k1_params p{};
-    p.X = h->X; p.Z = h->Z; p.m_arch = h->m_arch; p.XP = h->XP; p.id_out = h->id; p.lp_xp = h->lp_xp;
-    p.ctrl = h->ctrl; p.err = &h->ctrl->err; p.nc = h->nc; p.chain0 = h->chain0; p.n_local = nl; p.gchain0 = 0;
-    p.d = d; p.ldx = ldx; p.delta = c.delta; p.nCR = c.nCR; p.c_val = c.c_val; p.c_star = c.c_star; p.p_g = c.p_g;
-    p.beta0 = c.beta0; p.psnooker = c.psnooker; p.past_sample = c.past_sample;
-    p.bound = h->have_min_max ? c.bound : 0; p.prior = c.prior; p.pmin = h->pmin; p.pmax = h->pmax;
-    p.seed = c.seed; p.gen = (uint32_t)i; p.tape = h->tape; p.tape_g = i - 2; p.gamma_tab = h->gamma_tab;
+    const hb_k1_params p = hb_make_k1(h, i, h->chain0, 1, nl);
     prof_scope ps(h, "K1");
     CK(hb_launch_k1(p, tape_mode, h->sm_count, h->stream));
     ps.done();
   }
   {  // K2: the target plugin
     prof_scope ps(h, "K2");
-    if (int rc = h->vt->launch(h->tctx, h->XP, nl, d, ldx, h->ll_raw, h->fx_xp, h->stream)) return fail(h, rc, "target launch failed");
+    if (int rc = hb_target_launch(h, h->XP, nl, h->chain0, 1)) return fail(h, rc, "target launch failed");
     ps.done();
   }
   {  // K3
-    hb_k3_params p{};
-    p.X = h->X; p.XP = h->XP; p.id = h->id; p.lp_xp = h->lp_xp; p.ll_raw = h->ll_raw;
-    p.fx_xp = c.store_fx ? h->fx_xp : nullptr;
-    p.lp = h->lp; p.ll = h->ll; p.lpost = h->lpost; p.fx = c.store_fx ? h->fx : nullptr;
-    p.lpost_hist_row = (i <= h->H) ? h->lpost_hist + (i - 1) * nl : nullptr;
-    if (store) {
-      p.hist_x = h->hist_x + (size_t)(h->ind_out - 1) * nl * d;
-      p.hist_l = h->hist_l + (size_t)(h->ind_out - 1) * nl * 3;
-      p.hist_fx = h->hist_fx ? h->hist_fx + (size_t)(h->ind_out - 1) * nl : nullptr;
-    }
-    p.accept_rec = h->accept_rec ? h->accept_rec + (size_t)(i - 2) * nl : nullptr;
-    p.ctrl = h->ctrl; p.shift = h->shift; p.partials = h->partials;
-    p.chain0 = h->chain0; p.n_local = nl; p.gchain0 = 0; p.d = d; p.ldx = ldx; p.nCR = c.nCR;
-    p.adapt = in_adapt; p.seed = c.seed; p.gen = (uint32_t)i;
-    p.u_accept = tape_mode ? h->tape.u_accept + (size_t)(i - 2) * h->tape.nct : nullptr;
+    const hb_k3_params p = hb_make_k3(h, i, h->chain0, 1, nl, store, in_adapt, false);
     prof_scope ps(h, "K3");
     int nb = 0;
     CK(hb_launch_k3(p, h->sm_count, &nb, nullptr, h->stream));
@@ -370,7 +418,10 @@ int upload_tape(hb_handle* h, const hb_tape* tp) {
   h->tape.nct = nct;
   h->tape_n_gen = n_gen;
   h->tape_events = tp->n_events;
-  if (tp->outlier_new && tp->n_events > 0) h->tape_outlier_new.assign(tp->outlier_new, tp->outlier_new + (size_t)tp->n_events * nct);
+  if (tp->outlier_new && tp->n_events > 0) {
+    h->tape_outlier_new.assign(tp->outlier_new, tp->outlier_new + (size_t)tp->n_events * nct);
+    if ((rc = up(tp->outlier_new, (size_t)tp->n_events * nct * 4, (const void**)&h->tape_outlier_dev))) return rc;
+  }
   h->have_tape = true;
   return HB_OK;
 }
@@ -436,6 +487,8 @@ int hb_create(const hb_config* cfg, int device, hb_handle** out) {
   if (cfg->sweep == HB_SWEEP_SEQUENTIAL || h->cfg.n_runs > 1) {
     std::string why;
     if (hb_seq_supported(&h->cfg, why) != HB_OK) { g_create_err = why; delete h; return HB_ERR_UNSUPPORTED; }
+    h->modeb = true;
+    h->n_local = h->nct;
   }
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
@@ -505,8 +558,19 @@ int hb_set_target(hb_handle* h, const char* name, const double* data, const int6
   return HB_OK;
 }
 
-int hb_set_target_batched(hb_handle* h, const char*, const double*, int64_t, const double*, int64_t) {
-  return fail(h, HB_ERR_UNSUPPORTED, "batched independent runs are not wired yet");
+int hb_set_target_batched(hb_handle* h, const char* name, const double* data, int64_t len, const double* obs,
+                          int64_t n_obs) {
+  if (!h || !name) return HB_ERR_INVALID;
+  cudaSetDevice(h->device);
+  if (std::string(name) != "HydroModel") return fail(h, HB_ERR_UNSUPPORTED, "only HydroModel takes per-run data; use hb_set_target for '%s'", name);
+  const hb_target_vtable* vt = hb_find_target(name);
+  if (h->vt && h->tctx) { h->vt->destroy(h->tctx); h->tctx = nullptr; }
+  char err[256] = {0};
+  void* ctx = nullptr;
+  const int rc = hb_hydro_init_batched(&ctx, h->d, h->cfg.lik, data, len, obs, n_obs, h->cfg.n_runs, h->cfg.glue_shape, err, (int)sizeof err);
+  if (rc != HB_OK) return fail(h, rc, "%s", err[0] ? err : "target init failed");
+  h->vt = vt; h->tctx = ctx; h->target_name = name; h->target_is_hydro = true;
+  return HB_OK;
 }
 
 int hb_comm_unique_id(void* id128) {
@@ -533,9 +597,8 @@ int hb_set_initial(hb_handle* h, const double* x0) {
   if (!h || !x0) return HB_ERR_INVALID;
   if (h->have_initial) return fail(h, HB_ERR_STATE, "hb_set_initial was already called");
   cudaSetDevice(h->device);
-  if (h->cfg.sweep == HB_SWEEP_SEQUENTIAL || h->cfg.n_runs > 1) return fail(h, HB_ERR_UNSUPPORTED, "sequential sweep / batched runs are not wired yet");
   if (int rc = allocate(h)) return rc;
-  const long long m0 = h->m0, nc = h->nc;
+  const long long m0 = h->modeb ? h->nct : h->m0, nc = h->modeb ? h->nct : h->nc;
   const int d = h->d, ldx = h->ldx;
   double* tmp = nullptr;
   CK(dalloc(&tmp, (size_t)m0 * d));
@@ -566,7 +629,7 @@ int hb_run(hb_handle* h, int64_t n_generations, int64_t* done_total) {
   if (!h->have_initial) return fail(h, HB_ERR_STATE, "hb_run: hb_set_initial has not been called");
   if (h->cfg.rng_mode == HB_RNG_TAPE && !h->have_tape) return fail(h, HB_ERR_STATE, "hb_run: rng_mode is TAPE but no tape was set");
   if (h->cfg.prior == HB_PRIOR_UNIFORM && !h->have_min_max) return fail(h, HB_ERR_INVALID, "prior = 'uniform' needs min and max");
-  if (!h->initialised) { if (int rc = initialise(h)) return rc; }
+  if (!h->initialised) { if (int rc = initialise(h)) return rc; if (h->modeb) { if (int rc2 = hb_seq_initialise(h)) return rc2; } }
   long long last = h->gen + n_generations;
   if (last > h->t) last = h->t;
   CK(cudaEventRecord(h->ev0, h->stream));
@@ -643,13 +706,13 @@ int hb_fetch_fx(hb_handle* h, double* fx) {
 int hb_fetch_ar(hb_handle* h, double* ar) {
   if (!h || !ar) return HB_ERR_INVALID;
   cudaSetDevice(h->device);
-  CK(cudaMemcpy(ar, h->out_ar, sizeof(double) * (size_t)h->ar_rows * h->ar_cols, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(ar, h->out_ar, sizeof(double) * (size_t)h->cfg.n_runs * h->ar_rows * h->ar_cols, cudaMemcpyDeviceToHost));
   return HB_OK;
 }
 int hb_fetch_cr(hb_handle* h, double* cr) {
   if (!h || !cr) return HB_ERR_INVALID;
   cudaSetDevice(h->device);
-  CK(cudaMemcpy(cr, h->out_cr, sizeof(double) * (size_t)h->cr_rows * h->cr_cols, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(cr, h->out_cr, sizeof(double) * (size_t)h->cfg.n_runs * h->cr_rows * h->cr_cols, cudaMemcpyDeviceToHost));
   return HB_OK;
 }
 
@@ -668,7 +731,7 @@ int hb_fetch_state(hb_handle* h, double* xt, double* lp, double* ll, double* lpo
   if (!h) return HB_ERR_INVALID;
   if (!h->have_initial) return fail(h, HB_ERR_STATE, "no state yet");
   cudaSetDevice(h->device);
-  const long long nc = h->nc, nl = h->n_local;
+  const long long nc = h->modeb ? h->nct : h->nc, nl = h->n_local;
   if (xt) {
     double* tmp = nullptr;
     CK(dalloc(&tmp, (size_t)nc * h->d));
@@ -693,6 +756,7 @@ int hb_fetch_accept(hb_handle* h, uint8_t* accept) {
 
 int hb_fetch_outliers(hb_handle* h, int64_t* n_pairs, int64_t* gen, int64_t* chain, int64_t cap) {
   if (!h || !n_pairs) return HB_ERR_INVALID;
+  if (h->modeb) { if (int rc = hb_seq_pull_outliers(h)) return rc; }
   *n_pairs = (int64_t)h->outlier_gen.size();
   if (gen && chain)
     for (int64_t q = 0; q < *n_pairs && q < cap; ++q) { gen[q] = h->outlier_gen[(size_t)q]; chain[q] = h->outlier_chain[(size_t)q]; }

@@ -43,6 +43,9 @@ struct hb_ctrl {
   long long i_ar;                // :250
   unsigned err;                  // HB_FLAG_*
   unsigned pad;
+  // per-crossover acceptance counters of the sequential sweep (R/dream.R:143,241,266)
+  unsigned long long n_acc_id_gen[HB_MAX_NCR];
+  double n_acc_id[HB_MAX_NCR];
 };
 
 __host__ __device__ __forceinline__ uint4 hb_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,

@@ -66,6 +66,13 @@ struct hb_handle {
   double* stage = nullptr; size_t stage_bytes = 0;
   double* gamma_tab = nullptr;
 
+  // sequential sweep / batched independent runs (hb_seq.cu)
+  bool modeb = false;
+  unsigned long long* outl_count_dev = nullptr;
+  long long *outl_gen_dev = nullptr, *outl_chain_dev = nullptr;
+  long long outl_cap = 0;
+  const int32_t* tape_outlier_dev = nullptr;
+
   // tape
   bool have_tape = false;
   hb_tape_dev tape{};
@@ -87,6 +94,12 @@ struct hb_handle {
   std::map<std::string, hb_kstat> kstats;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
+
+hb_k1_params hb_make_k1(hb_handle* h, long long i, long long first, long long stride, long long n_items);
+hb_k3_params hb_make_k3(hb_handle* h, long long i, long long first, long long stride, long long n_items, bool store,
+                        bool in_adapt, bool write_dx);
+int hb_target_launch(hb_handle* h, const double* x, long long n, long long first, long long stride);
+int hb_fail(hb_handle* h, int code, const char* msg);
 
 // hb_comm.cu: NCCL loaded lazily with dlopen (no link-time dependency; single-GPU use needs no NCCL)
 int hb_nccl_unique_id(void* id128, std::string& err);

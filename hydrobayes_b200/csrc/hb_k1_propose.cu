@@ -39,9 +39,12 @@ __global__ void __launch_bounds__(256) hb_k1_kernel(const hb_k1_params p) {
     const long long jl_raw = base + lane / G;
     const bool valid = jl_raw < p.n_local;
     const long long jl = valid ? jl_raw : p.n_local - 1;
-    const long long j = p.chain0 + jl;           // chain within the run
-    const long long gch = p.gchain0 + j;         // global chain id: Philox counter and tape column
-    const long long rix = p.tape_g * p.tape.nct + gch;
+    const long long gl = p.chain0 + jl * p.stride;   // chain index within the handle (run-major)
+    const long long run = p.n_runs > 1 ? gl / p.nc : 0;
+    const long long j = gl - run * p.nc;         // chain within the run
+    const long long rbase = gl - j;              // first chain of the run
+    const long long gch = p.gchain0 + gl;        // global chain id: Philox counter
+    const long long rix = p.tape_g * p.tape.nct + gl;   // tape column
 
     // ---------------- per-chain draws: snooker test, D, partners, crossover id, gamma choice ----------------
     double u_sn, g_sn = 0.0;
@@ -88,7 +91,7 @@ __global__ void __launch_bounds__(256) hb_k1_kernel(const hb_k1_params p) {
       id = nCR - 1;
       bool found = false;
       for (int q = 0; q < nCR; ++q) {
-        cum += p.ctrl->pCR[q];
+        cum += p.ctrl[run].pCR[q];
         if (!found && u_id < cum) { id = q; found = true; }
       }
       g_is_one = hb_u53(hb_pair64(hw[HB_SLOT_CHOICE], 1)) >= 1.0 - p.p_g;
@@ -127,15 +130,16 @@ __global__ void __launch_bounds__(256) hb_k1_kernel(const hb_k1_params p) {
       if (snooker && (ps2 < 0 || ps2 >= n_src)) { errbits |= HB_FLAG_BAD_TAPE; ps2 = 0; }
     }
 
-    const double* __restrict__ xrow = p.X + j * (long long)ldx;
+    const double* __restrict__ xrow = p.X + gl * (long long)ldx;
+    const double* __restrict__ srcr = p.past_sample ? src : src + rbase * (long long)ldx;   // partner rows of this run
     double xk[ITER], dxk[ITER];
     double lp_part = 0.0;
 
     if (snooker) {
       // ---------------- snooker update, R/internals.R:150-163 with orth_proj :250-263 ----------------
-      const double* r1 = src + pa[0] * (long long)ldx;
-      const double* r2 = src + pb[0] * (long long)ldx;
-      const double* r3 = src + ps2 * (long long)ldx;
+      const double* r1 = srcr + pa[0] * (long long)ldx;
+      const double* r2 = srcr + pb[0] * (long long)ldx;
+      const double* r3 = srcr + ps2 * (long long)ldx;
       double uu[ITER], a2[ITER], a3[ITER];
       double s2 = 0, s3 = 0, su = 0;
       int differs = 0;
@@ -235,8 +239,8 @@ __global__ void __launch_bounds__(256) hb_k1_kernel(const hb_k1_params p) {
 #pragma unroll
             for (int q = 0; q < HB_MAX_DELTA; ++q) {
               if (q < D) {
-                const double a = src[pa[q] * (long long)ldx + k];
-                const double b = src[pb[q] * (long long)ldx + k];
+                const double a = srcr[pa[q] * (long long)ldx + k];
+                const double b = srcr[pb[q] * (long long)ldx + k];
                 const double t = __dadd_rn(a, -b);
                 if (q == 0) s = t;
                 else { double e; two_sum(s, t, s, e); comp = __dadd_rn(comp, e); }
@@ -338,12 +342,14 @@ __global__ void __launch_bounds__(256, 2) hb_k1_wide_kernel(const hb_k1_params p
     __syncwarp();
     if (lane < n_rows) {
       const double* g;
-      if (lane == 0) g = p.X + (p.chain0 + base + c) * (long long)ldx;                  // own state
+      const long long gl_c = p.chain0 + (base + c) * p.stride;
+      const long long rbase_c = p.n_runs > 1 ? (gl_c / p.nc) * p.nc : 0;
+      if (lane == 0) g = p.X + gl_c * (long long)ldx;                                   // own state
       else {
         int row;
         if (sn) row = (lane == 1) ? hd[1] : (lane == 2) ? hd[1 + HB_MAX_DELTA] : hd[1 + 2 * HB_MAX_DELTA];
         else row = (lane <= Dn) ? hd[lane] : hd[1 + HB_MAX_DELTA + (lane - 1 - Dn)];    // a[0..D-1], b[0..D-1]
-        g = src + (long long)row * ldx;
+        g = src + ((p.past_sample ? 0 : rbase_c) + (long long)row) * ldx;
       }
       tma_load_1d(stage_buf + ((size_t)s * rows_max + lane) * ldx, g, row_bytes, &bars[s]);
     }
@@ -359,12 +365,14 @@ __global__ void __launch_bounds__(256, 2) hb_k1_wide_kernel(const hb_k1_params p
       for (int q = 0; q < HB_MAX_DELTA; ++q) { hpa[q] = 0; hpb[q] = 0; }
       const long long jl_raw = base + lane;
       const long long jl = jl_raw < p.n_local ? jl_raw : p.n_local - 1;
-      const long long j = p.chain0 + jl;
-      const long long gch = p.gchain0 + j;
+      const long long gl = p.chain0 + jl * p.stride;
+      const long long run = p.n_runs > 1 ? gl / p.nc : 0;
+      const long long j = gl - run * p.nc;
+      const long long gch = p.gchain0 + gl;
       double u_sn;
       int g1;
       if (TAPE) {
-        const long long rix = p.tape_g * p.tape.nct + gch;
+        const long long rix = p.tape_g * p.tape.nct + gl;
         u_sn = p.tape.u_snooker ? p.tape.u_snooker[rix] : 1.0;          // R/internals.R:119
         hD = p.tape.D[rix];                                             // :123
         hid = p.tape.id[rix];                                           // :173
@@ -387,7 +395,7 @@ __global__ void __launch_bounds__(256, 2) hb_k1_wide_kernel(const hb_k1_params p
         hid = nCR - 1;
         bool found = false;
         for (int q = 0; q < nCR; ++q) {
-          cum += p.ctrl->pCR[q];
+          cum += p.ctrl[run].pCR[q];
           if (!found && u_id < cum) { hid = q; found = true; }
         }
         g1 = hb_u53(hb_pair64(wc, 1)) >= 1.0 - p.p_g;
@@ -447,8 +455,9 @@ __global__ void __launch_bounds__(256, 2) hb_k1_wide_kernel(const hb_k1_params p
       const int D = pk & 0xff, id = (pk >> 8) & 0xff;
       const bool g_is_one = (pk >> 16) & 1, snooker = (pk >> 17) & 1;
       const long long jl = base + c;
-      const long long gch = p.gchain0 + p.chain0 + jl;
-      const long long rix = p.tape_g * p.tape.nct + gch;
+      const long long gl = p.chain0 + jl * p.stride;
+      const long long gch = p.gchain0 + gl;
+      const long long rix = p.tape_g * p.tape.nct + gl;
       const hb_phx ph(p.seed, (uint64_t)gch, p.gen);
       const double* __restrict__ rows = stage_buf + (size_t)stg * rows_max * ldx;   // row 0: x; 1..D: a; D+1..2D: b
       double xk[ITER], dxk[ITER];

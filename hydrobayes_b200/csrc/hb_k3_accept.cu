@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(256) hb_k3_kernel(const hb_k3_params p) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int CPW = 32 / G;
   extern __shared__ double smem[];
-  __shared__ unsigned long long s_cnt[HB_MAX_NCR + 1];
+  __shared__ unsigned long long s_cnt[2 * HB_MAX_NCR + 1];
   const int lane = threadIdx.x & 31;
   const int lg = lane & (G - 1);
   const int gbase = lane & ~(G - 1);
@@ -33,8 +33,8 @@ __global__ void __launch_bounds__(256) hb_k3_kernel(const hb_k3_params p) {
   const int E = (nCR + 2) * d;                              // accumulator elements per slot
   unsigned errbits = 0;
 
-  if (threadIdx.x <= nCR) s_cnt[threadIdx.x] = 0ull;
-  if (adapt) {
+  if (threadIdx.x <= 2 * HB_MAX_NCR) s_cnt[threadIdx.x] = 0ull;
+  if (adapt && !p.write_dx) {
     for (int e = threadIdx.x; e < n_slots * E; e += blockDim.x) smem[e] = 0.0;
   }
   __syncthreads();
@@ -50,7 +50,9 @@ __global__ void __launch_bounds__(256) hb_k3_kernel(const hb_k3_params p) {
   for (long long base = warp_id * CPW; base < p.n_local; base += n_warps * CPW) {
     const long long jl = base + lane / G;
     const bool valid = jl < p.n_local;
-    const long long j = p.chain0 + (valid ? jl : 0);
+    const long long j = p.chain0 + (valid ? jl : 0) * p.stride;   // chain index within the handle
+    const long long run = p.n_runs > 1 ? j / p.nc : 0;
+    const long long si = j - p.state0;                            // index into the state / history arrays
     const long long gch = p.gchain0 + j;
     int accf = 0, id = 0;
     double lpx = 0, lln = 0, lpostx = 0, lpost_old = 0;
@@ -61,9 +63,9 @@ __global__ void __launch_bounds__(256) hb_k3_kernel(const hb_k3_params p) {
       if (!isfinite(llr)) errbits |= HB_FLAG_LL_NONFINITE;            // :21
       lln = llr;
       lpostx = lpx + lln;                                             // R/dream_parallel.R:291
-      lpost_old = p.lpost[jl];
+      lpost_old = p.lpost[si];
       double u;
-      if (TAPE) u = p.u_accept[gch];
+      if (TAPE) u = p.u_accept[j];
       else { const hb_phx ph(p.seed, (uint64_t)gch, p.gen); u = hb_u53(hb_pair64(ph.slot(HB_SLOT_ACCEPT), 0)); }
       const double p_acc = fmin(fmax(-100.0, lpostx - lpost_old), 0.0); // R/internals.R:239
       accf = p_acc > log(u);                                          // :241
@@ -81,39 +83,47 @@ __global__ void __launch_bounds__(256) hb_k3_kernel(const hb_k3_params p) {
           xn = p.XP[jl * (long long)ldx + k];
           if (adapt) {
             const double dx = xn - p.X[j * (long long)ldx + k];       // R/dream_parallel.R:357 (after bound handling)
-            acc[(2 + id) * d + k] += dx * dx;
+            if (p.write_dx) p.XP_rw[jl * (long long)ldx + k] = dx;
+            else acc[(2 + id) * d + k] += dx * dx;
           }
           p.X[j * (long long)ldx + k] = xn;                           // :358
-        } else if (need_x) {
-          xn = p.X[j * (long long)ldx + k];
+        } else {
+          if (need_x) xn = p.X[j * (long long)ldx + k];
+          if (adapt && p.write_dx) p.XP_rw[jl * (long long)ldx + k] = 0.0;   // dx stays 0, R/dream_parallel.R:266
         }
-        if (adapt) { const double c = xn - sh[m]; s1[m] += c; s2[m] += c * c; }
-        if (p.hist_x) p.hist_x[jl * (long long)d + k] = xn;           // chain[ind_out, 1:d, ] :388
+        if (adapt && !p.write_dx) { const double c = xn - sh[m]; s1[m] += c; s2[m] += c * c; }
+        if (p.hist_x) p.hist_x[si * (long long)d + k] = xn;           // chain[ind_out, 1:d, ] :388
       }
     }
     if (valid && lg == 0) {
       double lp_c, ll_c, lpost_c;
       if (accf) {
-        p.lp[jl] = lpx; p.ll[jl] = lln; p.lpost[jl] = lpostx;         // :359-361
-        if (p.fx && p.fx_xp) p.fx[jl] = p.fx_xp[jl];                  // :362
+        p.lp[si] = lpx; p.ll[si] = lln; p.lpost[si] = lpostx;         // :359-361
+        if (p.fx && p.fx_xp) p.fx[si] = p.fx_xp[jl];                  // :362
         lp_c = lpx; ll_c = lln; lpost_c = lpostx;
       } else {
         lpost_c = lpost_old;                                          // :365
         lp_c = 0; ll_c = 0;
-        if (p.hist_l) { lp_c = p.lp[jl]; ll_c = p.ll[jl]; }
+        if (p.hist_l) { lp_c = p.lp[si]; ll_c = p.ll[si]; }
       }
       if (p.hist_l) {                                                 // :389-391
-        p.hist_l[jl * 3 + 0] = lp_c; p.hist_l[jl * 3 + 1] = ll_c; p.hist_l[jl * 3 + 2] = lpost_c;
+        p.hist_l[si * 3 + 0] = lp_c; p.hist_l[si * 3 + 1] = ll_c; p.hist_l[si * 3 + 2] = lpost_c;
       }
-      if (p.hist_fx && p.fx) p.hist_fx[jl] = p.fx[jl];                // :394
-      if (p.lpost_hist_row) p.lpost_hist_row[jl] = lpost_c;
-      if (p.accept_rec) p.accept_rec[jl] = (uint8_t)accf;
-      atomicAdd(&s_cnt[1 + id], 1ull);                                // n_id  :368-369
-      if (accf) atomicAdd(&s_cnt[0], 1ull);                           // n_acc :374
+      if (p.hist_fx && p.fx) p.hist_fx[si] = p.fx[si];                // :394
+      if (p.lpost_hist_row) p.lpost_hist_row[si] = lpost_c;
+      if (p.accept_rec) p.accept_rec[si] = (uint8_t)accf;
+      if (p.n_runs > 1) {                                             // batched runs: counters live in the run's block
+        atomicAdd(&p.ctrl[run].n_id_gen[id], 1ull);
+        if (accf) { atomicAdd(&p.ctrl[run].n_acc_gen, 1ull); atomicAdd(&p.ctrl[run].n_acc_id_gen[id], 1ull); }
+      } else {
+        atomicAdd(&s_cnt[1 + id], 1ull);                              // n_id  :368-369
+        if (accf) { atomicAdd(&s_cnt[0], 1ull); atomicAdd(&s_cnt[1 + HB_MAX_NCR + id], 1ull); }   // n_acc :374
+      }
     }
   }
 
-  if (adapt) {
+  const bool block_stats = adapt && !p.write_dx;
+  if (block_stats) {
 #pragma unroll
     for (int m = 0; m < ITER; ++m) {
       const int k = m * G + lg;
@@ -121,7 +131,7 @@ __global__ void __launch_bounds__(256) hb_k3_kernel(const hb_k3_params p) {
     }
   }
   __syncthreads();
-  if (adapt) {
+  if (block_stats) {
     // fixed-order reduction over the block's slots -> one partial row per block
     for (int e = threadIdx.x; e < E; e += blockDim.x) {
       double s = 0.0;
@@ -129,11 +139,12 @@ __global__ void __launch_bounds__(256) hb_k3_kernel(const hb_k3_params p) {
       p.partials[(size_t)blockIdx.x * E + e] = s;
     }
   }
-  if (threadIdx.x <= nCR) {
+  if (threadIdx.x <= 2 * HB_MAX_NCR) {
     const unsigned long long v = s_cnt[threadIdx.x];
     if (v) {
       if (threadIdx.x == 0) atomicAdd(&p.ctrl->n_acc_gen, v);
-      else atomicAdd(&p.ctrl->n_id_gen[threadIdx.x - 1], v);
+      else if (threadIdx.x <= HB_MAX_NCR) atomicAdd(&p.ctrl->n_id_gen[threadIdx.x - 1], v);
+      else atomicAdd(&p.ctrl->n_acc_id_gen[threadIdx.x - 1 - HB_MAX_NCR], v);
     }
   }
   if (errbits) atomicOr(&p.ctrl->err, errbits);
@@ -151,7 +162,7 @@ template <int ITER, bool TAPE>
 __global__ void __launch_bounds__(256) hb_k3_wide_kernel(const hb_k3_params p) {
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ double smem[];
-  __shared__ unsigned long long s_cnt[HB_MAX_NCR + 1];
+  __shared__ unsigned long long s_cnt[2 * HB_MAX_NCR + 1];
   const int lane = threadIdx.x & 31;
   const int slot = threadIdx.x >> 5;
   const int n_slots = blockDim.x >> 5;
@@ -162,8 +173,8 @@ __global__ void __launch_bounds__(256) hb_k3_wide_kernel(const hb_k3_params p) {
   const int E = (nCR + 2) * d;
   unsigned errbits = 0;
 
-  if (threadIdx.x <= nCR) s_cnt[threadIdx.x] = 0ull;
-  if (adapt) for (int e = threadIdx.x; e < n_slots * E; e += blockDim.x) smem[e] = 0.0;
+  if (threadIdx.x <= 2 * HB_MAX_NCR) s_cnt[threadIdx.x] = 0ull;
+  if (adapt && !p.write_dx) for (int e = threadIdx.x; e < n_slots * E; e += blockDim.x) smem[e] = 0.0;
   __syncthreads();
   double* acc = smem + (size_t)slot * E;
   double s1[ITER], s2[ITER], sh[ITER];
@@ -173,44 +184,55 @@ __global__ void __launch_bounds__(256) hb_k3_wide_kernel(const hb_k3_params p) {
     const int k = m * 32 + lane;
     sh[m] = (adapt && k < d) ? p.shift[k] : 0.0;
   }
-  const bool all_rows = adapt || p.hist_x != nullptr;
+  const bool all_rows = adapt || p.hist_x != nullptr;   // (write_dx needs every row too: rejected rows get dx = 0)
 
   for (long long base = warp_id * 32; base < p.n_local; base += n_warps * 32) {
     const long long jl = base + lane;
     const bool valid = jl < p.n_local;
     int accf = 0, id = 0;
+    const long long gj = p.chain0 + (valid ? jl : 0) * p.stride;   // chain index within the handle
+    const long long run = p.n_runs > 1 ? gj / p.nc : 0;
+    const long long si = gj - p.state0;
     if (valid) {
-      const long long gch = p.gchain0 + p.chain0 + jl;
+      const long long gch = p.gchain0 + gj;
       const double lpx = p.lp_xp[jl];
       double llr = p.ll_raw[jl];
       if (!(llr >= HB_FLOOR)) llr = (llr != llr) ? llr : HB_FLOOR;    // calc_ll floor, R/internals.R:19
       if (!isfinite(llr)) errbits |= HB_FLAG_LL_NONFINITE;            // :21
       const double lpostx = lpx + llr;                                // R/dream_parallel.R:291
-      const double lpost_old = p.lpost[jl];
+      const double lpost_old = p.lpost[si];
       double u;
-      if (TAPE) u = p.u_accept[gch];
+      if (TAPE) u = p.u_accept[gj];
       else { const hb_phx ph(p.seed, (uint64_t)gch, p.gen); u = hb_u53(hb_pair64(ph.slot(HB_SLOT_ACCEPT), 0)); }
       const double p_acc = fmin(fmax(-100.0, lpostx - lpost_old), 0.0); // R/internals.R:239
       accf = p_acc > log(u);                                          // :241
       id = p.id[jl];
       double lp_c = 0, ll_c = 0, lpost_c = lpost_old;                 // :365
       if (accf) {
-        p.lp[jl] = lpx; p.ll[jl] = llr; p.lpost[jl] = lpostx;         // :359-361
-        if (p.fx && p.fx_xp) p.fx[jl] = p.fx_xp[jl];                  // :362
+        p.lp[si] = lpx; p.ll[si] = llr; p.lpost[si] = lpostx;         // :359-361
+        if (p.fx && p.fx_xp) p.fx[si] = p.fx_xp[jl];                  // :362
         lp_c = lpx; ll_c = llr; lpost_c = lpostx;
-      } else if (p.hist_l) { lp_c = p.lp[jl]; ll_c = p.ll[jl]; }
-      if (p.hist_l) { p.hist_l[jl * 3 + 0] = lp_c; p.hist_l[jl * 3 + 1] = ll_c; p.hist_l[jl * 3 + 2] = lpost_c; }   // :389-391
-      if (p.hist_fx && p.fx) p.hist_fx[jl] = p.fx[jl];                // :394
-      if (p.lpost_hist_row) p.lpost_hist_row[jl] = lpost_c;
-      if (p.accept_rec) p.accept_rec[jl] = (uint8_t)accf;
+      } else if (p.hist_l) { lp_c = p.lp[si]; ll_c = p.ll[si]; }
+      if (p.hist_l) { p.hist_l[si * 3 + 0] = lp_c; p.hist_l[si * 3 + 1] = ll_c; p.hist_l[si * 3 + 2] = lpost_c; }   // :389-391
+      if (p.hist_fx && p.fx) p.hist_fx[si] = p.fx[si];                // :394
+      if (p.lpost_hist_row) p.lpost_hist_row[si] = lpost_c;
+      if (p.accept_rec) p.accept_rec[si] = (uint8_t)accf;
+      if (p.n_runs > 1) {                                             // batched runs: counters live in the run's block
+        atomicAdd(&p.ctrl[run].n_id_gen[id], 1ull);
+        if (accf) { atomicAdd(&p.ctrl[run].n_acc_gen, 1ull); atomicAdd(&p.ctrl[run].n_acc_id_gen[id], 1ull); }
+      }
     }
     const unsigned vmask = __ballot_sync(FULL, valid);
     const unsigned amask = __ballot_sync(FULL, valid && accf);
-    for (int q = 0; q < nCR; ++q) {                                   // n_id  :368-369
-      const unsigned m_q = __ballot_sync(FULL, valid && id == q);
-      if (lane == 0 && m_q) atomicAdd(&s_cnt[1 + q], (unsigned long long)__popc(m_q));
+    if (p.n_runs == 1) {
+      for (int q = 0; q < nCR; ++q) {                                 // n_id  :368-369
+        const unsigned m_q = __ballot_sync(FULL, valid && id == q);
+        const unsigned a_q = m_q & amask;
+        if (lane == 0 && m_q) atomicAdd(&s_cnt[1 + q], (unsigned long long)__popc(m_q));
+        if (lane == 0 && a_q) atomicAdd(&s_cnt[1 + HB_MAX_NCR + q], (unsigned long long)__popc(a_q));
+      }
+      if (lane == 0 && amask) atomicAdd(&s_cnt[0], (unsigned long long)__popc(amask));   // n_acc :374
     }
-    if (lane == 0 && amask) atomicAdd(&s_cnt[0], (unsigned long long)__popc(amask));   // n_acc :374
 
     unsigned rows = all_rows ? vmask : amask;
     while (rows) {
@@ -219,7 +241,8 @@ __global__ void __launch_bounds__(256) hb_k3_wide_kernel(const hb_k3_params p) {
       const int a_c = (amask >> c) & 1;
       const int id_c = __shfl_sync(FULL, id, c);
       const long long jr = base + c;
-      const long long j = p.chain0 + jr;
+      const long long j = p.chain0 + jr * p.stride;
+      const long long sr = j - p.state0;
 #pragma unroll
       for (int m = 0; m < ITER; ++m) {
         const int k = m * 32 + lane;
@@ -229,20 +252,23 @@ __global__ void __launch_bounds__(256) hb_k3_wide_kernel(const hb_k3_params p) {
             xn = p.XP[jr * (long long)ldx + k];
             if (adapt) {
               const double dx = xn - p.X[j * (long long)ldx + k];     // R/dream_parallel.R:357 (after bound handling)
-              acc[(2 + id_c) * d + k] += dx * dx;
+              if (p.write_dx) p.XP_rw[jr * (long long)ldx + k] = dx;
+              else acc[(2 + id_c) * d + k] += dx * dx;
             }
             p.X[j * (long long)ldx + k] = xn;                         // :358
           } else {
             xn = p.X[j * (long long)ldx + k];
+            if (adapt && p.write_dx) p.XP_rw[jr * (long long)ldx + k] = 0.0;
           }
-          if (adapt) { const double cc = xn - sh[m]; s1[m] += cc; s2[m] += cc * cc; }
-          if (p.hist_x) p.hist_x[jr * (long long)d + k] = xn;         // chain[ind_out, 1:d, ] :388
+          if (adapt && !p.write_dx) { const double cc = xn - sh[m]; s1[m] += cc; s2[m] += cc * cc; }
+          if (p.hist_x) p.hist_x[sr * (long long)d + k] = xn;         // chain[ind_out, 1:d, ] :388
         }
       }
     }
   }
 
-  if (adapt) {
+  const bool block_stats = adapt && !p.write_dx;
+  if (block_stats) {
 #pragma unroll
     for (int m = 0; m < ITER; ++m) {
       const int k = m * 32 + lane;
@@ -250,18 +276,19 @@ __global__ void __launch_bounds__(256) hb_k3_wide_kernel(const hb_k3_params p) {
     }
   }
   __syncthreads();
-  if (adapt) {
+  if (block_stats) {
     for (int e = threadIdx.x; e < E; e += blockDim.x) {
       double s = 0.0;
       for (int q = 0; q < n_slots; ++q) s += smem[(size_t)q * E + e];
       p.partials[(size_t)blockIdx.x * E + e] = s;
     }
   }
-  if (threadIdx.x <= nCR) {
+  if (threadIdx.x <= 2 * HB_MAX_NCR) {
     const unsigned long long v = s_cnt[threadIdx.x];
     if (v) {
       if (threadIdx.x == 0) atomicAdd(&p.ctrl->n_acc_gen, v);
-      else atomicAdd(&p.ctrl->n_id_gen[threadIdx.x - 1], v);
+      else if (threadIdx.x <= HB_MAX_NCR) atomicAdd(&p.ctrl->n_id_gen[threadIdx.x - 1], v);
+      else atomicAdd(&p.ctrl->n_acc_id_gen[threadIdx.x - 1 - HB_MAX_NCR], v);
     }
   }
   if (errbits) atomicOr(&p.ctrl->err, errbits);
@@ -284,7 +311,7 @@ cudaError_t launch_wide(const hb_k3_params& p, int sm_count, int* nblocks_out, s
   if (nblocks_out) *nblocks_out = (int)blocks;
   if (smem_out) *smem_out = smem_adapt;
   if (p.X == nullptr) return cudaSuccess;
-  const size_t smem = p.adapt ? smem_adapt : 0;
+  const size_t smem = (p.adapt && !p.write_dx) ? smem_adapt : 0;
   const bool tape = p.u_accept != nullptr;
   cudaError_t e = cudaSuccess;
   if (tape) {
@@ -322,7 +349,7 @@ cudaError_t launch_gi(const hb_k3_params& p, int sm_count, int* nblocks_out, siz
   if (nblocks_out) *nblocks_out = (int)blocks;
   if (smem_out) *smem_out = smem_adapt;
   if (p.X == nullptr) return cudaSuccess;                   // geometry query only
-  const size_t smem = p.adapt ? smem_adapt : 0;
+  const size_t smem = (p.adapt && !p.write_dx) ? smem_adapt : 0;
   const bool tape = p.u_accept != nullptr;
   cudaError_t e = cudaSuccess;
   if (tape) {

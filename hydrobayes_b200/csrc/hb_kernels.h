@@ -30,9 +30,11 @@ struct hb_k1_params {
   const hb_ctrl* ctrl;    // pCR
   unsigned* err;
   long long nc;           // chains per run
-  long long chain0;       // first chain of this rank's shard (within the run)
-  long long n_local;      // chains handled by this launch
-  long long gchain0;      // global chain id of chain 0 of the run (run * nc): Philox counter / tape row
+  long long chain0;       // item i of this launch is chain chain0 + i*stride of the handle (run-major index);
+  long long stride;       //   synchronous sweep: (shard start, 1) ; sequential sweep, chain j of every run: (j, nc)
+  long long n_local;      // items handled by this launch
+  long long n_runs;       // independent runs batched in the handle (ctrl is an array of n_runs blocks)
+  long long gchain0;      // offset added to the handle's chain index to form the Philox counter (run_offset * nc)
   int d, ldx;
   int delta, nCR;
   double c_val, c_star, p_g, beta0, psnooker;
@@ -53,6 +55,7 @@ cudaError_t hb_launch_k1(const hb_k1_params& p, bool tape_mode, int sm_count, cu
 struct hb_k3_params {
   double* X;              // [nc][ldx] updated in place (rows of the local shard)
   const double* XP;       // [n_local][ldx]
+  double* XP_rw;          // same buffer, writable: receives dx when write_dx
   const int* id;          // [n_local]
   const double* lp_xp;    // [n_local]
   const double* ll_raw;   // [n_local] plugin output before the floor
@@ -66,9 +69,12 @@ struct hb_k3_params {
   hb_ctrl* ctrl;
   const double* shift;    // [d] column shift for the one-pass variance (previous generation's mean)
   double* partials;       // [nblocks][(nCR+2)*d] block partial sums (adaptation only) or nullptr
-  long long chain0, n_local, gchain0;
+  long long chain0, n_local, gchain0;   // item i is chain chain0 + i*stride of the handle (see hb_k1_params)
+  long long stride, nc, n_runs;
+  long long state0;       // lp/ll/lpost/history arrays hold chains [state0, ...): index = chain - state0
   int d, ldx, nCR;
   int adapt;              // generation is inside the adaptation period: accumulate std / jump statistics
+  int write_dx;           // per-run statistics path: overwrite XP[item] with the realised jump dx (0 if rejected)
   uint64_t seed;
   uint32_t gen;
   const double* u_accept; // tape row (device) or nullptr in Philox mode
@@ -94,6 +100,28 @@ struct hb_fin_params {
   long long n_eval_inc;   // nc (all ranks)
 };
 cudaError_t hb_launch_finalize(const hb_fin_params& p, cudaStream_t st);
+
+// ---- per-run bookkeeping (sequential sweep and batched independent runs): one CTA per run ---------------
+struct hb_runfin_params {
+  hb_ctrl* ctrl;          // [n_runs]
+  double* X; int ldx, d, nCR;
+  long long nc, nct, state0;
+  const double* DX;       // XP buffer after K3 (write_dx): realised jumps of this round's items
+  const int* id;          // [items]
+  long long item0, item_run_stride; int items_per_run;   // items of run r: item0 + r*item_run_stride + (0..items_per_run-1)
+  long long n_eval_inc;   // evaluations per run since the last fold
+  int adapt, do_pcr, do_outlier, do_arcr;
+  long long seq_row;      // >= 0: write the sequential sweep's AR/CR row (R/dream.R:266-267) before adapting
+  double* lpost; double* lpost_hist; long long hist_ld, hist_rows;
+  long long gen; int update_interval;
+  const int32_t* tape_outlier;   // device copy of hb_tape::outlier_new, or nullptr (Philox)
+  uint64_t seed; long long run_offset;
+  double* out_ar; double* out_cr; long long ar_rows; int ar_cols, cr_cols;
+  unsigned long long* outlier_count; long long* outlier_gen; long long* outlier_chain; long long outlier_cap;
+  int npow2;              // filled by the launcher
+};
+size_t hb_runfin_smem(int d, long long nc, int* npow2_out);
+cudaError_t hb_launch_runfin(const hb_runfin_params& p, long long n_runs, cudaStream_t st);
 
 // ---- outlier check pieces (R/internals.R:71-87) ---------------------------------------------------------
 cudaError_t hb_launch_proxy(const double* lpost_hist, long long nc_local, long long row0, long long row1,

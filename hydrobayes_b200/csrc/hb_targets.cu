@@ -339,12 +339,43 @@ __global__ void hb_hydro_series_kernel(const double* __restrict__ param, long lo
   }
 }
 
+// batched independent runs: every run has its own forcing / obs series (BASELINE C5: distinct catchments)
+__global__ void __launch_bounds__(128) hb_hydro_items_kernel(const double* __restrict__ X, long long n, int ldx,
+                                                             const double* __restrict__ forcing,
+                                                             const double* __restrict__ obs,
+                                                             const double* __restrict__ sst, int T, int T_pad,
+                                                             double glue_shape, long long chain0, long long stride,
+                                                             long long nc, double* __restrict__ ll, unsigned* err) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long run = (chain0 + i * stride) / nc;
+  const double* __restrict__ P = forcing + run * T_pad;
+  const double* __restrict__ O = obs + run * T_pad;
+  const double K = X[i * ldx];
+  if (K < 0) { atomicOr(err, HB_FLAG_TARGET_DOMAIN); ll[i] = NAN; return; }
+  const double den = 1.0 + K * 1.0;
+  double S = 1.0, sse = 0.0, comp = 0.0;
+#pragma unroll 4
+  for (int t = 0; t < T; ++t) {
+    S = __ddiv_rn(P[t] * 1.0 + S, den);
+    const double e = K * S - O[t];
+    const double y = e * e - comp;
+    const double tt = sse + y;
+    comp = (tt - sse) - y;
+    sse = tt;
+  }
+  const double nse = 1.0 - sse / sst[run];
+  ll[i] = glue_shape * log(nse > 0.0 ? nse : 0.0);
+}
+
 struct hydro_ctx {
   int T, T_pad, lik;
   double sst, glue_shape;
   double* forcing_dev;
   double* obs_dev;
   unsigned* err_dev;
+  double* sst_dev = nullptr;   // batched: [n_runs]
+  long long n_runs = 0;
 };
 
 int hydro_init(void** ctx, int d, int lik, const double* data, const int64_t* dims, int ndims, const double* obs,
@@ -400,9 +431,18 @@ int hydro_launch(void* ctx, const double* x, int64_t n, int d, int ldx, double* 
       x, n, ldx, c->forcing_dev, c->obs_dev, c->T, c->T_pad, c->sst, c->glue_shape, ll, c->err_dev);
   return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
 }
+int hydro_launch_items(void* ctx, const double* x, int64_t n, int d, int ldx, double* ll, double* fx, int64_t chain0,
+                       int64_t stride, int64_t nc, void* stream) {
+  auto* c = (hydro_ctx*)ctx;
+  if (!c->sst_dev) return hydro_launch(ctx, x, n, d, ldx, ll, fx, stream);   // one series shared by all runs
+  if (n <= 0) return HB_OK;
+  hb_hydro_items_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      x, n, ldx, c->forcing_dev, c->obs_dev, c->sst_dev, c->T, c->T_pad, c->glue_shape, chain0, stride, nc, ll, c->err_dev);
+  return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
+}
 void hydro_destroy(void* ctx) {
   auto* c = (hydro_ctx*)ctx;
-  if (c) { cudaFree(c->forcing_dev); cudaFree(c->obs_dev); cudaFree(c->err_dev); delete c; }
+  if (c) { cudaFree(c->forcing_dev); cudaFree(c->obs_dev); cudaFree(c->err_dev); cudaFree(c->sst_dev); delete c; }
 }
 void hydro_work(void* ctx, int, double* flops, double* bytes) {
   auto* c = (hydro_ctx*)ctx;
@@ -413,9 +453,9 @@ void hydro_work(void* ctx, int, double* flops, double* bytes) {
 std::mutex g_mu;
 std::vector<hb_target_vtable>& registry() {
   static std::vector<hb_target_vtable> r = {
-      {"mixture", mixture_init, mixture_launch, mixture_destroy, mixture_work},
-      {"t_distribution", tdist_init, tdist_launch, tdist_destroy, tdist_work},
-      {"HydroModel", hydro_init, hydro_launch, hydro_destroy, hydro_work},
+      {"mixture", mixture_init, mixture_launch, mixture_destroy, mixture_work, nullptr},
+      {"t_distribution", tdist_init, tdist_launch, tdist_destroy, tdist_work, nullptr},
+      {"HydroModel", hydro_init, hydro_launch, hydro_destroy, hydro_work, hydro_launch_items},
   };
   return r;
 }
@@ -428,6 +468,43 @@ const hb_target_vtable* hb_find_target(const char* name) {
   for (auto& v : registry())
     if (name && strcmp(v.name, name) == 0) return &v;
   return nullptr;
+}
+
+// per-run forcing/obs for batched independent runs: data [n_runs][T], obs [n_runs][T] (row-major)
+int hb_hydro_init_batched(void** ctx, int d, int lik, const double* data, int64_t T, const double* obs, int64_t n_obs,
+                          long long n_runs, double glue_shape, char* err, int errlen) {
+  if (d != 1) { set_err(err, errlen, "HydroModel(forcing, param) has one parameter (R/test_HydroModel.R:17)"); return HB_ERR_INVALID; }
+  if (lik != 31) { set_err(err, errlen, "HydroModel on the device folds the GLUE likelihood: use lik = 31"); return HB_ERR_UNSUPPORTED; }
+  if (!data || !obs || T < 1 || n_obs != T || n_runs < 1) { set_err(err, errlen, "batched HydroModel needs forcing and obs of equal length per run"); return HB_ERR_INVALID; }
+  for (int64_t i = 0; i < T * n_runs; ++i)
+    if (data[i] < 0) { set_err(err, errlen, "Values of argument 'forcing' need to be >= zero!"); return HB_ERR_INVALID; }
+  auto* c = new hydro_ctx();
+  c->T = (int)T; c->T_pad = (int)((T + 1) & ~1LL); c->lik = lik; c->glue_shape = glue_shape; c->n_runs = n_runs; c->sst = 0;
+  std::vector<double> F((size_t)n_runs * c->T_pad, 0.0), O((size_t)n_runs * c->T_pad, 0.0), sst((size_t)n_runs);
+  for (long long r = 0; r < n_runs; ++r) {
+    const double* o = obs + r * T;
+    memcpy(&F[(size_t)r * c->T_pad], data + r * T, sizeof(double) * T);
+    memcpy(&O[(size_t)r * c->T_pad], o, sizeof(double) * T);
+    long double s = 0;
+    for (int64_t i = 0; i < T; ++i) s += o[i];
+    s /= T;
+    long double rr = 0;
+    for (int64_t i = 0; i < T; ++i) rr += (o[i] - s);
+    s += rr / T;
+    const double mo = (double)s;
+    long double q = 0;
+    for (int64_t i = 0; i < T; ++i) { const double e = o[i] - mo; q += (long double)(e * e); }
+    sst[(size_t)r] = (double)q;
+  }
+  bool ok = cudaMalloc(&c->forcing_dev, F.size() * 8) == cudaSuccess && cudaMalloc(&c->obs_dev, O.size() * 8) == cudaSuccess &&
+            cudaMalloc(&c->sst_dev, sst.size() * 8) == cudaSuccess && cudaMalloc(&c->err_dev, sizeof(unsigned)) == cudaSuccess;
+  ok = ok && cudaMemcpy(c->forcing_dev, F.data(), F.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+       cudaMemcpy(c->obs_dev, O.data(), O.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+       cudaMemcpy(c->sst_dev, sst.data(), sst.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+       cudaMemset(c->err_dev, 0, sizeof(unsigned)) == cudaSuccess;
+  if (!ok) { set_err(err, errlen, "cudaMalloc/cudaMemcpy failed for batched forcing/obs"); delete c; return HB_ERR_CUDA; }
+  *ctx = c;
+  return HB_OK;
 }
 
 // HydroModel's domain check lives in its own context (the sampler polls it through this hook)

@@ -73,6 +73,13 @@ class Sampler:
         o = np.ascontiguousarray(np.asarray(obs, np.float64))
         self._check(self.L.hb_set_obs(self.h, _ptr(o), o.size))
 
+    def set_target_batched(self, name: str, data, obs):
+        """Per-run target data for batched independent runs: data [n_runs, len], obs [n_runs, n_obs]."""
+        a = np.ascontiguousarray(np.asarray(data, np.float64)); o = np.ascontiguousarray(np.asarray(obs, np.float64))
+        if a.ndim != 2 or o.ndim != 2 or a.shape[0] != self.cfg.n_runs or o.shape[0] != self.cfg.n_runs:
+            raise ValueError("data and obs must be [n_runs, length] arrays")
+        self._check(self.L.hb_set_target_batched(self.h, name.encode(), _ptr(a), a.shape[1], _ptr(o), o.shape[1]))
+
     def set_target(self, name: str, data=None):
         if data is None:
             self._check(self.L.hb_set_target(self.h, name.encode(), None, None, 0))
@@ -123,7 +130,7 @@ class Sampler:
         return self.L.hb_ind_out(self.h)
 
     def n_local(self) -> int:
-        return self.cfg.nc  # single-GPU; sharded handles override through ShardedSampler
+        return self.cfg.nc * max(self.cfg.n_runs, 1)   # sharded handles: pass n_chains = nc / world to the fetchers
 
     def fetch_chain(self, n_chains: Optional[int] = None) -> np.ndarray:
         dm = self.out_dims()
@@ -147,10 +154,14 @@ class Sampler:
 
     def fetch_ar_cr(self):
         dm = self.out_dims()
-        ar = np.empty((dm["ar_rows"], dm["ar_cols"]), order="F")
-        cr = np.empty((dm["cr_rows"], dm["cr_cols"]), order="F")
+        nr = max(self.cfg.n_runs, 1)
+        ar = np.empty((nr, dm["ar_cols"], dm["ar_rows"]))      # run-major blocks of column-major [rows, cols]
+        cr = np.empty((nr, dm["cr_cols"], dm["cr_rows"]))
         self._check(self.L.hb_fetch_ar(self.h, _ptr(ar)))
         self._check(self.L.hb_fetch_cr(self.h, _ptr(cr)))
+        ar = np.transpose(ar, (0, 2, 1)); cr = np.transpose(cr, (0, 2, 1))
+        if nr == 1:
+            return np.asfortranarray(ar[0]), np.asfortranarray(cr[0])
         return ar, cr
 
     def fetch_rstat(self) -> np.ndarray:
@@ -160,7 +171,7 @@ class Sampler:
         return out
 
     def fetch_state(self, n_chains: Optional[int] = None):
-        nc, d = self.cfg.nc, self.cfg.d
+        nc, d = self.n_local(), self.cfg.d
         n = n_chains or self.n_local()
         xt = np.empty((nc, d), order="F")
         lp = np.empty(n); ll = np.empty(n); lpost = np.empty(n)

@@ -99,7 +99,7 @@ typedef struct hb_config {
   int32_t check_convergence; /* compute R_stat rows like dream_test (R/dream_test.R:344); SURVEY F7 */
   int32_t store_fx;        /* keep raw target output per stored generation (only targets with m == 1) */
   int32_t exchange;        /* HB_EXCHANGE_* (multi-GPU only) */
-  int32_t reserved0;
+  int32_t run_offset;      /* global index of this handle's first run: Philox chain id = (run_offset + run)*nc + j */
 } hb_config;
 
 /*
@@ -150,6 +150,10 @@ typedef struct hb_target_vtable {
   void (*destroy)(void* ctx);
   /* algorithmic work per evaluated point, for roofline reports */
   void (*work)(void* ctx, int d, double* flops, double* bytes);
+  /* optional (may be NULL): targets with per-run data in batched independent runs.  Point i is chain
+   * chain0 + i*stride of the handle, i.e. it belongs to run (chain0 + i*stride) / nc. */
+  int (*launch_items)(void* ctx, const double* x_dev, int64_t n, int d, int ldx, double* ll_dev, double* fx_dev,
+                      int64_t chain0, int64_t stride, int64_t nc, void* stream);
 } hb_target_vtable;
 
 int hb_register_target(const hb_target_vtable* vt);       /* user plugins; built-ins are pre-registered */

@@ -168,6 +168,83 @@ def test_replay_sliced_run_equals_single_run(hb, oracle):
     assert np.array_equal(a["chain"], b["chain"]) and np.array_equal(a["accept"], b["accept"])
 
 
+# ---------------------------------------------------------------- sequential sweep: dream()  (R/dream.R:203-295) --
+def _seq_case(oracle, cfg, target, x0, native=False, **kw):
+    if native:
+        ora = oracle.run(cfg, target, x0, **kw)
+        dev = H.run_device(cfg, target, x0, **kw)
+        return dev, ora
+    return _replay_case(oracle, cfg, target, x0, **kw)
+
+
+def test_seq_replay_mixture_c1(hb, oracle):
+    # BASELINE C1 as the reference runs it: dream(), nc = 10, d = 1, sequential chain sweep (shortened t)
+    cfg = A.default_config(nc=10, t=1500, d=1, lik=1, seed=1312, sweep=A.HB_SWEEP_SEQUENTIAL, store_fx=1)
+    dev, ora = _seq_case(oracle, cfg, "mixture", H.x0_mixture(10))
+    H.assert_run_parity(dev, ora, rtol=1e-12)
+    assert dev["AR"].shape == (1500, 3) and np.all(dev["AR"][0] == 0)
+
+
+@pytest.mark.parametrize("native", [False, True])
+def test_seq_tdist(hb, oracle, native):
+    cfg = A.default_config(nc=12, t=120, d=20, lik=2, seed=77, sweep=A.HB_SWEEP_SEQUENTIAL, adapt=0.5, record_accept=1, thin=3)
+    x0 = H.x0_tdist(12, 20); x0[5] = 200.0
+    dev, ora = _seq_case(oracle, cfg, "t_distribution", x0, native=native)
+    H.assert_run_parity(dev, ora, rtol=1e-11 if native else 1e-12, check_fx=False)
+
+
+def test_seq_hydromodel(hb, oracle):
+    P, obs = H.hydro_data(T=200)
+    cfg = A.default_config(nc=10, t=150, d=1, lik=31, glue_shape=50.0, prior=A.HB_PRIOR_UNIFORM, bound=A.HB_BOUND_FOLD,
+                           seed=4, sweep=A.HB_SWEEP_SEQUENTIAL)
+    dev, ora = _seq_case(oracle, cfg, "HydroModel", H.x0_hydro(10), par_min=[0.01], par_max=[2.0], forcing=P, obs=obs)
+    H.assert_run_parity(dev, ora, rtol=1e-11)
+
+
+# ---------------------------------------------------------------- batched independent runs (BASELINE C5) --------
+@pytest.mark.parametrize("sweep", [A.HB_SWEEP_SYNCHRONOUS, A.HB_SWEEP_SEQUENTIAL])
+def test_batched_hydromodel_runs(hb, oracle, sweep):
+    # distinct synthetic catchments, nc = 10 chains per run (examples/script_examples.R:517), each run checked against
+    # the oracle run on its own
+    n_runs, nc, T, t = 6, 10, 120, 90
+    data = [H.hydro_data(T=T, catchment=c) for c in range(n_runs)]
+    P = np.stack([a for a, _ in data]); O = np.stack([b for _, b in data])
+    cfg = A.default_config(nc=nc, t=t, d=1, lik=31, glue_shape=50.0, prior=A.HB_PRIOR_UNIFORM, bound=A.HB_BOUND_BOUND,
+                           seed=31, sweep=sweep, n_runs=n_runs, adapt=0.4, record_accept=1)
+    x0 = np.concatenate([H.x0_hydro(nc) for _ in range(n_runs)])
+    from hydrobayes_b200 import Sampler
+    with Sampler(cfg, 0) as s:
+        s.set_bounds([0.01], [2.0])
+        s.set_target_batched("HydroModel", P, O)
+        s.set_initial(x0)
+        assert s.run(t) == t
+        chain = s.fetch_chain(); ar, cr = s.fetch_ar_cr(); acc = s.fetch_accept(); outl = s.fetch_outliers()
+    assert chain.shape == (t, 4, n_runs * nc)
+    for r in range(n_runs):
+        c1 = H.copy_cfg(cfg, n_runs=n_runs)        # the oracle evaluates one run at a time (chain ids r*nc + j)
+        ora = oracle.run(c1, "HydroModel", H.x0_hydro(nc), par_min=[0.01], par_max=[2.0], forcing=P[r], obs=O[r], run=r)
+        assert ora["rc"] == 0, ora["err"]
+        sl = slice(r * nc, (r + 1) * nc)
+        assert np.array_equal(acc[:, sl], ora["accept"])
+        np.testing.assert_allclose(chain[:, :, sl], ora["chain"], rtol=1e-11, equal_nan=True)
+        np.testing.assert_allclose(ar[r], ora["AR"], rtol=1e-12, equal_nan=True)
+        np.testing.assert_allclose(cr[r], ora["CR"], rtol=1e-10, equal_nan=True)
+        assert [(g, ch - r * nc) for g, ch in outl if r * nc <= ch < (r + 1) * nc] == ora["outlier"]
+
+
+def test_batched_tdist_runs_native(hb, oracle):
+    n_runs, nc, d, t = 4, 16, 8, 100
+    cfg = A.default_config(nc=nc, t=t, d=d, lik=2, seed=13, n_runs=n_runs, adapt=0.5, record_accept=1)
+    x0 = np.concatenate([H.x0_tdist(nc, d) + r for r in range(n_runs)])
+    dev = H.run_device(cfg, "t_distribution", x0)
+    for r in range(n_runs):
+        ora = oracle.run(cfg, "t_distribution", H.x0_tdist(nc, d) + r, run=r)
+        sl = slice(r * nc, (r + 1) * nc)
+        assert np.array_equal(dev["accept"][:, sl], ora["accept"])
+        np.testing.assert_allclose(dev["chain"][:, :, sl], ora["chain"], rtol=1e-11, equal_nan=True)
+        np.testing.assert_allclose(dev["CR"][r], ora["CR"], rtol=1e-10, equal_nan=True)
+
+
 # ---------------------------------------------------------------- native RNG (Philox) vs the oracle's Philox -----
 @pytest.mark.parametrize("case", ["mixture", "tdist", "hydro"])
 def test_native_rng_matches_oracle_philox(hb, oracle, case):
