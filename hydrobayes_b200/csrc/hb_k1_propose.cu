@@ -21,6 +21,25 @@ __device__ __forceinline__ void two_sum(double a, double b, double& s, double& e
   e = __dadd_rn(__dadd_rn(a, -__dadd_rn(s, -bb)), __dadd_rn(b, -bb));
 }
 
+// compensated accumulation / group reduction: the snooker projections are dot products that R sums in long double
+// (R/internals.R:257, sum()); carrying the rounding errors reproduces that sum to the last bit in practice
+__device__ __forceinline__ void comp_add(double& hi, double& lo, double v) {
+  double e;
+  two_sum(hi, v, hi, e);
+  lo = __dadd_rn(lo, e);
+}
+template <int G>
+__device__ __forceinline__ double comp_group_sum(double hi, double lo, unsigned gmask) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) {
+    const double oh = __shfl_xor_sync(gmask, hi, o), ol = __shfl_xor_sync(gmask, lo, o);
+    double e;
+    two_sum(hi, oh, hi, e);
+    lo = __dadd_rn(__dadd_rn(lo, ol), e);
+  }
+  return __dadd_rn(hi, lo);
+}
+
 template <int G, int ITER, bool TAPE>
 __global__ void __launch_bounds__(256) hb_k1_kernel(const hb_k1_params p) {
   constexpr unsigned FULL = 0xffffffffu;
@@ -141,7 +160,7 @@ __global__ void __launch_bounds__(256) hb_k1_kernel(const hb_k1_params p) {
       const double* r2 = srcr + pb[0] * (long long)ldx;
       const double* r3 = srcr + ps2 * (long long)ldx;
       double uu[ITER], a2[ITER], a3[ITER];
-      double s2 = 0, s3 = 0, su = 0;
+      double s2 = 0, s3 = 0, su = 0, l2 = 0, l3 = 0, lu = 0;
       int differs = 0;
 #pragma unroll
       for (int m = 0; m < ITER; ++m) {
@@ -151,14 +170,14 @@ __global__ void __launch_bounds__(256) hb_k1_kernel(const hb_k1_params p) {
           xk[m] = xrow[k];
           const double b = r1[k];
           a2[m] = r2[k]; a3[m] = r3[k];
-          uu[m] = xk[m] - b;
+          uu[m] = __dadd_rn(xk[m], -b);
           differs |= (xk[m] != b);
-          s2 += (a2[m] - xk[m]) * uu[m];
-          s3 += (a3[m] - xk[m]) * uu[m];
-          su += uu[m] * uu[m];
+          comp_add(s2, l2, __dmul_rn(__dadd_rn(a2[m], -xk[m]), uu[m]));
+          comp_add(s3, l3, __dmul_rn(__dadd_rn(a3[m], -xk[m]), uu[m]));
+          comp_add(su, lu, __dmul_rn(uu[m], uu[m]));
         }
       }
-      s2 = hb_group_sum<G>(s2, gmask); s3 = hb_group_sum<G>(s3, gmask); su = hb_group_sum<G>(su, gmask);
+      s2 = comp_group_sum<G>(s2, l2, gmask); s3 = comp_group_sum<G>(s3, l3, gmask); su = comp_group_sum<G>(su, lu, gmask);
       differs = hb_group_sum_int<G>(differs, gmask);
 #pragma unroll
       for (int m = 0; m < ITER; ++m) {
@@ -470,7 +489,7 @@ __global__ void __launch_bounds__(256, 2) hb_k1_wide_kernel(const hb_k1_params p
         const double* r2 = rows + 2 * ldx;
         const double* r3 = rows + 3 * ldx;
         double uu[ITER], a2[ITER], a3[ITER];
-        double s2 = 0, s3 = 0, su = 0;
+        double s2 = 0, s3 = 0, su = 0, l2 = 0, l3 = 0, lu = 0;
         int differs = 0;
 #pragma unroll
         for (int m = 0; m < ITER; ++m) {
@@ -480,14 +499,14 @@ __global__ void __launch_bounds__(256, 2) hb_k1_wide_kernel(const hb_k1_params p
             xk[m] = rows[k];
             const double b = r1[k];
             a2[m] = r2[k]; a3[m] = r3[k];
-            uu[m] = xk[m] - b;
+            uu[m] = __dadd_rn(xk[m], -b);
             differs |= (xk[m] != b);
-            s2 += (a2[m] - xk[m]) * uu[m];
-            s3 += (a3[m] - xk[m]) * uu[m];
-            su += uu[m] * uu[m];
+            comp_add(s2, l2, __dmul_rn(__dadd_rn(a2[m], -xk[m]), uu[m]));
+            comp_add(s3, l3, __dmul_rn(__dadd_rn(a3[m], -xk[m]), uu[m]));
+            comp_add(su, lu, __dmul_rn(uu[m], uu[m]));
           }
         }
-        s2 = hb_group_sum<32>(s2); s3 = hb_group_sum<32>(s3); su = hb_group_sum<32>(su);
+        s2 = comp_group_sum<32>(s2, l2, FULL); s3 = comp_group_sum<32>(s3, l3, FULL); su = comp_group_sum<32>(su, lu, FULL);
         differs = hb_group_sum_int<32>(differs);
 #pragma unroll
         for (int m = 0; m < ITER; ++m) {

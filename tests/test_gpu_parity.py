@@ -168,6 +168,69 @@ def test_replay_sliced_run_equals_single_run(hb, oracle):
     assert np.array_equal(a["chain"], b["chain"]) and np.array_equal(a["accept"], b["accept"])
 
 
+# ---------------------------------------------------------------- DREAM(ZS) archive sampling and snooker
+@pytest.mark.parametrize("psnooker", [0.0, 0.1, 0.5])
+@pytest.mark.parametrize("native", [False, True])
+def test_zs_archive_and_snooker(hb, oracle, psnooker, native):
+    # past_sample = TRUE: partners come from the archive z (m0 = 10 d rows, appended every 10 generations,
+    # R/dream_parallel.R:168-173, 382-383); nc may be as small as 3 (script_examples.R:133-135); no outlier check (:414)
+    nc, d, t = 3, 5, 260
+    cfg = A.default_config(nc=nc, t=t, d=d, lik=2, seed=17, past_sample=1, psnooker=psnooker, record_accept=1)
+    x0 = np.random.default_rng(2).uniform(-5, 15, size=(10 * d, d))        # the archive; chains start at its last nc rows
+    if native:
+        ora = oracle.run(cfg, "t_distribution", x0)
+        dev = H.run_device(cfg, "t_distribution", x0)
+    else:
+        dev, ora = _replay_case(oracle, cfg, "t_distribution", x0)
+    H.assert_run_parity(dev, ora, rtol=1e-11, check_fx=False)
+    assert ora["outlier"] == []
+
+
+def test_zs_wide_kernel(hb, oracle):
+    nc, d, t = 8, 40, 120
+    cfg = A.default_config(nc=nc, t=t, d=d, lik=2, seed=3, past_sample=1, psnooker=0.2, m0=300, archive_update=5, record_accept=1)
+    x0 = np.random.default_rng(5).uniform(-5, 15, size=(300, d))
+    dev, ora = _replay_case(oracle, cfg, "t_distribution", x0)
+    H.assert_run_parity(dev, ora, rtol=1e-11, check_fx=False)
+    ora_n = oracle.run(H.copy_cfg(cfg, rng_mode=A.HB_RNG_PHILOX), "t_distribution", x0)
+    dev_n = H.run_device(H.copy_cfg(cfg, rng_mode=A.HB_RNG_PHILOX), "t_distribution", x0)
+    H.assert_run_parity(dev_n, ora_n, rtol=1e-11, check_fx=False)
+
+
+# ---------------------------------------------------------------- convergence check inside the run ----
+def test_check_convergence_rows(hb, oracle):
+    cfg = A.default_config(nc=8, t=90, d=3, lik=2, seed=23, check_convergence=1)
+    x0 = H.x0_tdist(8, 3)
+    ora = oracle.run(cfg, "t_distribution", x0)
+    dev = H.run_device(cfg, "t_distribution", x0)
+    assert dev["R_stat"].shape == (40, 3)
+    np.testing.assert_allclose(dev["R_stat"], ora["R_stat"], rtol=1e-10)
+    from hydrobayes_b200 import Sampler
+    with Sampler(cfg, 0) as s:
+        s.set_target("t_distribution"); s.set_initial(x0); s.run(60)
+        r = s.rstat()
+        ch = s.fetch_chain()[:61, :3, :]
+    np.testing.assert_allclose(r, oracle.rstat(ch), rtol=1e-10)
+
+
+def test_python_api_dream_and_dream_parallel(hb):
+    # the host mirror of the R API: same formals, defaults and return structures (R/dream.R:126-133, 305-313)
+    res = hb.dream("mixture", lik=1, par_info=dict(initial="latin", min=-20, max=20, prior="flat"), nc=10, t=300, d=1,
+                   seed=1, verbose=False)
+    assert res["chain"].shape == (300, 4, 10) and res["chain_colnames"] == ["par1", "lp", "ll", "lpost"]
+    assert res["AR"].shape == (300, 3) and res["CR"].shape == (300, 3) and res["fx"].shape == (300, 10, 1)
+    assert len(res["outlier"]) == 30 and res["runtime"] > 0
+    res = hb.dream_parallel("t_distribution", lik=2, par_info=dict(initial="normal", mu=np.zeros(4), cov=np.eye(4), names=list("abcd")),
+                            nc=20, t=200, d=4, thin=5, burnin=0.5, seed=2, verbose=False, checkConvergence=False)
+    assert res["chain"].shape == (21, 7, 20) and res["chain_colnames"][:4] == list("abcd")
+    assert res["AR"].shape == (21, 2) and res["CR"].shape == (21, 4) and res["AR_colnames"] == ["n_eval", "accepted"]
+    assert np.isnan(res["chain"]).sum() == 0
+    with pytest.raises(hb.HbError):
+        hb.dream_parallel("no_such_fun", lik=2, par_info=dict(initial="uniform", min=0, max=1), nc=10, t=10, d=1, verbose=False)
+    with pytest.raises(hb.HbError):   # R/dream.R:136-137
+        hb.dream("mixture", lik=1, par_info=dict(initial="uniform", min=0, max=1, prior="flat"), nc=6, t=10, d=1, verbose=False)
+
+
 # ---------------------------------------------------------------- sequential sweep: dream()  (R/dream.R:203-295) --
 def _seq_case(oracle, cfg, target, x0, native=False, **kw):
     if native:
