@@ -275,6 +275,8 @@ hb_k1_params hb_make_k1(hb_handle* h, long long i, long long first, long long st
   p.beta0 = c.beta0; p.psnooker = c.psnooker; p.past_sample = c.past_sample;
   p.bound = h->have_min_max ? c.bound : 0; p.prior = c.prior; p.pmin = h->pmin; p.pmax = h->pmax;
   p.seed = c.seed; p.gen = (uint32_t)i; p.tape = h->tape; p.tape_g = i - 2; p.gamma_tab = h->gamma_tab;
+  hb_philox_key_schedule(c.seed, p.ks);
+  for (int q = 0; q < c.nCR; ++q) p.thr[q] = (unsigned long long)ceil((double)(q + 1) / (double)c.nCR * 4294967296.0 - 0.5);
   return p;
 }
 

@@ -65,6 +65,26 @@ __host__ __device__ __forceinline__ uint4 hb_philox4x32_10(uint32_t c0, uint32_t
   return make_uint4(c0, c1, c2, c3);
 }
 
+// same function with the 10 round keys precomputed (they depend on the seed only): ks[2r], ks[2r+1]
+__host__ __device__ __forceinline__ uint4 hb_philox4x32_10_ks(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                             const uint32_t* __restrict__ ks) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ ks[2 * r];
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ ks[2 * r + 1];
+    const uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+inline void hb_philox_key_schedule(uint64_t seed, uint32_t ks[20]) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  for (int r = 0; r < 10; ++r) { ks[2 * r] = k0; ks[2 * r + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+}
+
 struct hb_phx {
   uint32_t k0, k1, c0, c1, gen;
   __host__ __device__ __forceinline__ hb_phx(uint64_t seed, uint64_t gchain, uint32_t generation)

@@ -341,6 +341,7 @@ __global__ void __launch_bounds__(256, 2) hb_k1_wide_kernel(const hb_k1_params p
   int* heads = reinterpret_cast<int*>(wbase + (size_t)K1_STAGES * rows_max * ldx * 8);   // [32][HEAD_WORDS]
   uint64_t* bars = reinterpret_cast<uint64_t*>(heads + 32 * K1_HEAD_WORDS);              // [STAGES]
   unsigned errbits = 0;
+  const bool bound_or_prior = (p.bound != 0) || (p.prior == 1);
 
   if (lane == 0) {
 #pragma unroll
@@ -370,7 +371,9 @@ __global__ void __launch_bounds__(256, 2) hb_k1_wide_kernel(const hb_k1_params p
         else row = (lane <= Dn) ? hd[lane] : hd[1 + HB_MAX_DELTA + (lane - 1 - Dn)];    // a[0..D-1], b[0..D-1]
         g = src + ((p.past_sample ? 0 : rbase_c) + (long long)row) * ldx;
       }
-      tma_load_1d(stage_buf + ((size_t)s * rows_max + lane) * ldx, g, row_bytes, &bars[s]);
+      // stage rows: 0 = x, 1..D = a, 1+delta.. = b (fixed offsets: no D-dependent address arithmetic in the sweep)
+      const int srow = (sn || lane <= Dn) ? lane : (1 + delta + (lane - 1 - Dn));
+      tma_load_1d(stage_buf + ((size_t)s * rows_max + srow) * ldx, g, row_bytes, &bars[s]);
     }
   };
 
@@ -478,7 +481,9 @@ __global__ void __launch_bounds__(256, 2) hb_k1_wide_kernel(const hb_k1_params p
       const long long gch = p.gchain0 + gl;
       const long long rix = p.tape_g * p.tape.nct + gl;
       const hb_phx ph(p.seed, (uint64_t)gch, p.gen);
-      const double* __restrict__ rows = stage_buf + (size_t)stg * rows_max * ldx;   // row 0: x; 1..D: a; D+1..2D: b
+      const double* __restrict__ rows = stage_buf + (size_t)stg * rows_max * ldx;   // row 0: x; 1..: a; 1+delta..: b
+      const double* __restrict__ rowa = rows + ldx;
+      const double* __restrict__ rowb = rows + (1 + delta) * ldx;
       double xk[ITER], dxk[ITER];
 
       if (snooker) {
@@ -529,7 +534,7 @@ __global__ void __launch_bounds__(256, 2) hb_k1_wide_kernel(const hb_k1_params p
         // parallel direction update, R/internals.R:166-200
         const double CRv = (double)(id + 1) / (double)nCR;               // CR <- (1:nCR)/nCR
         // (w + 0.5) 2^-32 < CR  <=>  w < ceil(CR 2^32 - 0.5): exact integer form of the zt < CR[id] test
-        const unsigned long long thr = (unsigned long long)ceil(CRv * 4294967296.0 - 0.5);
+        const unsigned long long thr = p.thr[id];
         double ztv[TAPE ? ITER : 1];
         uint32_t wx[ITER], wl[ITER], wz2[ITER], wz3[ITER];
         unsigned selmask[ITER];
@@ -543,7 +548,7 @@ __global__ void __launch_bounds__(256, 2) hb_k1_wide_kernel(const hb_k1_params p
             ztv[TAPE ? m : 0] = 2.0;
             if (k < d) { ztv[TAPE ? m : 0] = p.tape.zt[rix * d + k]; sel = ztv[TAPE ? m : 0] < CRv; }   // :175-177
           } else if (k < d) {
-            const uint4 w = ph.slot(HB_SLOT_DIM0 + (uint32_t)k);
+            const uint4 w = hb_philox4x32_10_ks((uint32_t)gch, (uint32_t)((uint64_t)gch >> 32), p.gen, HB_SLOT_DIM0 + (uint32_t)k, p.ks);
             wx[m] = w.x; wl[m] = w.y; wz2[m] = w.z; wz3[m] = w.w;
             sel = (unsigned long long)w.x < thr;
           }
@@ -601,7 +606,7 @@ __global__ void __launch_bounds__(256, 2) hb_k1_wide_kernel(const hb_k1_params p
 #pragma unroll
               for (int q = 0; q < HB_MAX_DELTA; ++q) {
                 tq[q] = 0.0;
-                if (q < D) tq[q] = __dadd_rn(rows[(1 + q) * ldx + k], -rows[(1 + D + q) * ldx + k]);
+                if (q < D) tq[q] = __dadd_rn(rowa[q * ldx + k], -rowb[q * ldx + k]);
               }
               double jd;
               if (D <= 2) jd = __dadd_rn(tq[0], tq[1]);
@@ -628,18 +633,21 @@ __global__ void __launch_bounds__(256, 2) hb_k1_wide_kernel(const hb_k1_params p
 
       // xp <- x + dx ; finite check ; bounds ; prior
       double lp_part = 0.0;
+      double* __restrict__ xp_row = p.XP + jl * (long long)ldx;
 #pragma unroll
       for (int m = 0; m < ITER; ++m) {
         const int k = m * 32 + lane;
         if (k < d) {
           double xp = __dadd_rn(xk[m], dxk[m]);                          // :206
-          if (!isfinite(xp)) errbits |= HB_FLAG_PROP_NONFINITE;          // :209
-          if (p.bound) xp = hb_bound_par(xp, p.pmin[k], p.pmax[k], p.bound);   // :210-214
-          if (p.prior == 1) {                                            // dunif(log = TRUE), :57
-            const double a = p.pmin[k], b = p.pmax[k];
-            lp_part += (a <= xp && xp <= b) ? -log(b - a) : -INFINITY;
+          if (!(fabs(xp) <= 1.7976931348623157e308)) errbits |= HB_FLAG_PROP_NONFINITE;   // :209
+          if (bound_or_prior) {
+            if (p.bound) xp = hb_bound_par(xp, p.pmin[k], p.pmax[k], p.bound);   // :210-214
+            if (p.prior == 1) {                                          // dunif(log = TRUE), :57
+              const double a = p.pmin[k], b = p.pmax[k];
+              lp_part += (a <= xp && xp <= b) ? -log(b - a) : -INFINITY;
+            }
           }
-          p.XP[jl * (long long)ldx + k] = xp;
+          xp_row[k] = xp;
         }
       }
       if (p.prior == 1) lp_part = hb_group_sum<32>(lp_part);
@@ -706,6 +714,15 @@ cudaError_t hb_launch_k1(const hb_k1_params& p, bool tape_mode, int sm_count, cu
   if (d <= 8) return launch_gi<8, 1>(p, tape_mode, sm_count, st);
   if (d <= 16) return launch_gi<16, 1>(p, tape_mode, sm_count, st);
   if (p.nc > 0x7fffffffLL || p.m_arch > 0x7fffffffLL) return cudaErrorInvalidValue;
+  // small populations (fewer 32-chain batches than resident warps): one chain per warp spreads the work over more SMs
+  if (p.n_local < (long long)sm_count * 16 * 32 / 2) {
+    if (d <= 32) return launch_gi<32, 1>(p, tape_mode, sm_count, st);
+    if (d <= 64) return launch_gi<32, 2>(p, tape_mode, sm_count, st);
+    if (d <= 128) return launch_gi<32, 4>(p, tape_mode, sm_count, st);
+    if (d <= 256) return launch_gi<32, 8>(p, tape_mode, sm_count, st);
+    if (d <= 512) return launch_gi<32, 16>(p, tape_mode, sm_count, st);
+    return launch_gi<32, 32>(p, tape_mode, sm_count, st);
+  }
   if (d <= 32) return launch_wide<1>(p, tape_mode, sm_count, st);
   if (d <= 64) return launch_wide<2>(p, tape_mode, sm_count, st);
   if (d <= 128) return launch_wide<4>(p, tape_mode, sm_count, st);

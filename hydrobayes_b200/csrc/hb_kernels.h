@@ -48,6 +48,8 @@ struct hb_k1_params {
   hb_tape_dev tape;
   long long tape_g;       // generation row of the tape (i - 2)
   const double* gamma_tab; // [delta][d]: 2.38/sqrt(2 D d*), built on the host with IEEE sqrt and division
+  uint32_t ks[20];        // Philox round keys of `seed` (constant bank operands in the kernel)
+  unsigned long long thr[HB_MAX_NCR];   // ceil(CR_q 2^32 - 0.5): exact integer form of zt < CR[id]
 };
 cudaError_t hb_launch_k1(const hb_k1_params& p, bool tape_mode, int sm_count, cudaStream_t st);
 
