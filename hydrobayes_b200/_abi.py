@@ -162,6 +162,7 @@ def lib() -> C.CDLL:
                            C.c_int32, _dp, _dp, C.c_char_p, C.c_int], C.c_int),
         "hb_hydromodel_series": ([_dp, C.c_int64, _dp, C.c_int64, _dp, C.c_char_p, C.c_int], C.c_int),
         "hb_fp64_peaks": ([_dp, _dp], C.c_int),
+        "hb_divcheck": ([_dp, _dp, C.c_int64, _i64p], C.c_int),
     }
     for name, (args, res) in sig.items():
         f = getattr(L, name)  # AttributeError here == the library does not export a declared symbol
@@ -177,5 +178,5 @@ EXPORTED_SYMBOLS = [
     "hb_set_initial", "hb_set_tape", "hb_comm_unique_id", "hb_comm_init", "hb_run", "hb_sync", "hb_out_dims",
     "hb_fetch_chain", "hb_fetch_chain_rows", "hb_fetch_fx", "hb_fetch_ar", "hb_fetch_cr", "hb_fetch_rstat",
     "hb_fetch_state", "hb_fetch_accept", "hb_fetch_outliers", "hb_rstat", "hb_ind_out", "hb_get_timing", "hb_profile",
-    "hb_get_kernel_ms", "hb_rstat_array", "hb_logdensity", "hb_hydromodel_series", "hb_fp64_peaks",
+    "hb_get_kernel_ms", "hb_rstat_array", "hb_logdensity", "hb_hydromodel_series", "hb_fp64_peaks", "hb_divcheck",
 ]

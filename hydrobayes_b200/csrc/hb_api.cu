@@ -152,6 +152,11 @@ int allocate(hb_handle* h) {
   CK(hb_launch_fill(h->out_cr, nr * h->cr_rows * h->cr_cols, NAN, h->stream));
   CK(dalloc(&h->proxy, (size_t)nl)); CK(dalloc(&h->proxy_full, (size_t)nc)); CK(dalloc(&h->lpost_full, (size_t)nc));
   CK(dalloc(&h->outl_dev, (size_t)nc)); CK(dalloc(&h->news_dev, (size_t)nc));
+  if (!h->modeb) {
+    h->outl_tmp_bytes = hb_outlier_workspace_bytes(h->nc);
+    CK(cudaMalloc(&h->outl_tmp, h->outl_tmp_bytes ? h->outl_tmp_bytes : 16));
+    CK(dalloc(&h->outl_sorted, (size_t)h->nc)); CK(dalloc(&h->outl_thr, 1)); CK(dalloc(&h->outl_count, 1));
+  }
   if (h->rstat_rows > 0) { CK(dalloc(&h->rstat_dev, (size_t)h->rstat_rows * d)); CK(hb_launch_fill(h->rstat_dev, h->rstat_rows * d, NAN, h->stream)); }
   CK(dalloc(&h->rstat_xm, (size_t)nl * d)); CK(dalloc(&h->rstat_ss, (size_t)nl * d));
   {  // gamma_d table, R/internals.R:190
@@ -217,22 +222,25 @@ int outlier_check(hb_handle* h, long long i) {
     CK(hb_launch_proxy(h->lpost_hist, nl, r0 - 1, i - 1, nl, h->proxy, h->stream));
     ps.done();
   }
-  std::vector<double> proxy((size_t)nc);
+  const double* proxy_all = h->proxy;
   if (h->world > 1) {
     if (int rc = hb_nccl_allgather_f64(h->comm, h->proxy, h->proxy_full, (size_t)nl, h->stream, h->err)) return rc;
     if (int rc = hb_nccl_allgather_f64(h->comm, h->lpost, h->lpost_full, (size_t)nl, h->stream, h->err)) return rc;
-    CK(cudaMemcpyAsync(proxy.data(), h->proxy_full, sizeof(double) * nc, cudaMemcpyDeviceToHost, h->stream));
-  } else {
-    CK(cudaMemcpyAsync(proxy.data(), h->proxy, sizeof(double) * nc, cudaMemcpyDeviceToHost, h->stream));
+    proxy_all = h->proxy_full;
   }
+  {  // quartiles, threshold and the ascending outlier list on the device (R/internals.R:75-78)
+    prof_scope ps(h, "OUTLIER");
+    CK(hb_outlier_device(proxy_all, nc, h->outl_tmp, h->outl_tmp_bytes, h->outl_sorted, h->outl_thr, h->outl_dev,
+                         h->outl_count, h->stream));
+    ps.done(3);
+  }
+  int n_out = 0;
+  CK(cudaMemcpyAsync(&n_out, h->outl_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  std::vector<double> s(proxy);
-  std::sort(s.begin(), s.end());
-  const double q1 = quantile7_sorted(s, 0.25), q3 = quantile7_sorted(s, 0.75);   // :75
-  const double iqr = fabs(q3 - q1);                                               // :76
-  std::vector<long long> outl;
-  for (long long j = 0; j < nc; ++j) if (proxy[(size_t)j] < q1 - 2 * iqr) outl.push_back(j);   // :78
-  if (outl.empty()) return HB_OK;
+  if (n_out == 0) return HB_OK;
+  std::vector<int> o32((size_t)n_out);
+  CK(cudaMemcpy(o32.data(), h->outl_dev, sizeof(int) * n_out, cudaMemcpyDeviceToHost));
+  std::vector<long long> outl(o32.begin(), o32.end());
   std::vector<long long> news;
   if (h->cfg.rng_mode == HB_RNG_TAPE) {
     const long long e = i / h->cfg.update_interval - 1;
@@ -245,8 +253,7 @@ int outlier_check(hb_handle* h, long long i) {
   } else {
     sample_replacements(h, i, outl, news);                                        // :81
   }
-  std::vector<int> o32(outl.begin(), outl.end()), n32(news.begin(), news.end());
-  CK(cudaMemcpyAsync(h->outl_dev, o32.data(), sizeof(int) * o32.size(), cudaMemcpyHostToDevice, h->stream));
+  std::vector<int> n32(news.begin(), news.end());
   CK(cudaMemcpyAsync(h->news_dev, n32.data(), sizeof(int) * n32.size(), cudaMemcpyHostToDevice, h->stream));
   double* hrow = (i <= h->H) ? h->lpost_hist + (i - 1) * nl : nullptr;
   {
@@ -512,7 +519,8 @@ void hb_destroy(hb_handle* h) {
   void* ptrs[] = {h->X, h->Z, h->XP, h->id, h->lp_xp, h->ll_raw, h->fx_xp, h->lp, h->ll, h->lpost, h->fx, h->lpost_hist,
                   h->hist_x, h->hist_l, h->hist_fx, h->accept_rec, h->ctrl, h->shift, h->colsum, h->qsum, h->partials,
                   h->out_ar, h->out_cr, h->proxy, h->proxy_full, h->lpost_full, h->outl_dev, h->news_dev, h->rstat_dev,
-                  h->rstat_xm, h->rstat_ss, h->stage, h->pmin, h->pmax, h->gamma_tab};
+                  h->rstat_xm, h->rstat_ss, h->stage, h->pmin, h->pmax, h->gamma_tab, h->outl_tmp, h->outl_sorted, h->outl_thr,
+                  h->outl_count};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (void* p : h->tape_allocs) cudaFree(p);
   if (h->ev0) cudaEventDestroy(h->ev0);

@@ -65,6 +65,8 @@ struct hb_handle {
   double *rstat_dev = nullptr, *rstat_xm = nullptr, *rstat_ss = nullptr;
   double* stage = nullptr; size_t stage_bytes = 0;
   double* gamma_tab = nullptr;
+  void* outl_tmp = nullptr; size_t outl_tmp_bytes = 0;
+  double *outl_sorted = nullptr, *outl_thr = nullptr; int* outl_count = nullptr;
 
   // sequential sweep / batched independent runs (hb_seq.cu)
   bool modeb = false;

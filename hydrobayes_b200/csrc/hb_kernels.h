@@ -132,6 +132,10 @@ cudaError_t hb_launch_outlier_reset(double* X, int ldx, int d, double* lpost, do
                                     const double* lpost_src, long long chain0, long long n_local, const int* outl,
                                     const int* news, int n_out, cudaStream_t st);
 
+size_t hb_outlier_workspace_bytes(long long nc);
+cudaError_t hb_outlier_device(const double* proxy, long long nc, void* tmp, size_t tmp_bytes, double* sorted,
+                              double* thr, int* list, int* count, cudaStream_t st);
+
 // ---- history transposition into R's chain[out_t, d+3, nc] layout ----------------------------------------
 cudaError_t hb_launch_chain_transpose(const double* hist_x, const double* hist_l, long long out_t_alloc,
                                       long long row0, long long nrows, long long rows_filled, long long nct, int d,

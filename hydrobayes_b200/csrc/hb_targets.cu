@@ -88,10 +88,23 @@ __global__ void __launch_bounds__(256, 2) hb_tdist_dmma_kernel(const double* __r
                                                             double df, int lik, double* __restrict__ ll,
                                                             double* __restrict__ fx) {
   constexpr int NB = (KB + 1) / 2;
-  extern __shared__ double Ws[];
-  const int n_w = 4 * KB * ldw;
-  for (int i = threadIdx.x; i < n_w; i += blockDim.x) Ws[i] = Wg[i];
+  extern __shared__ __align__(16) double Ws[];
+  __shared__ __align__(8) uint64_t wbar;
+  // W (4 KB x ldw doubles, a multiple of 16 bytes) is staged by bulk TMA copies of at most 32 KB each
+  const uint32_t w_bytes = (uint32_t)(4 * KB * ldw) * 8u;
+  if (threadIdx.x == 0) {
+    mbar_init(&wbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
   __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&wbar, w_bytes);
+    for (uint32_t off = 0; off < w_bytes; off += 32768u) {
+      const uint32_t n = (w_bytes - off) < 32768u ? (w_bytes - off) : 32768u;
+      tma_load_1d(reinterpret_cast<char*>(Ws) + off, reinterpret_cast<const char*>(Wg) + off, n, &wbar);
+    }
+  }
+  mbar_wait(&wbar, 0);
   const int lane = threadIdx.x & 31;
   const int gid = lane >> 2, tig = lane & 3;
   const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -283,6 +296,16 @@ void tdist_destroy(void* ctx) {
 void tdist_work(void*, int d, double* flops, double* bytes) { *flops = (double)d * d + 3.0 * d; *bytes = 8.0 * d + 8; }
 
 // =========================================== HydroModel ====================================================
+// a / b for a fixed divisor b with y = RN(1/b) precomputed by a true IEEE division: q0 = RN(a y), r = a - b q0
+// (exact, one FMA), q = RN(q0 + r y).  By Markstein's theorem (correctly rounded reciprocal, faithful q0) q is the
+// correctly rounded quotient, i.e. bit-identical to R's `/` -- the bit-exact series test against the oracle and the
+// randomised check in tests/test_gpu_parity.py::test_division_by_reciprocal_is_exact pin this.
+__device__ __forceinline__ double div_by_recip(double a, double b, double y) {
+  const double q0 = __dmul_rn(a, y);
+  const double r = __fma_rn(-b, q0, a);
+  return __fma_rn(r, y, q0);
+}
+
 // One chain per thread.  P and obs (T_pad doubles each, T_pad even so that the byte count is a multiple of 16) are
 // staged once per CTA.  Per step (R/test_HydroModel.R:30-32): S = (P_i*Dt + S)/(1 + K*Dt), Y_i = K*S with Dt = 1, a
 // true IEEE division.  lik == 31 (R/internals.R:13-14): glue_shape*log(max(1 - sse/sst, 0)); sse is Kahan-summed.
@@ -311,11 +334,12 @@ __global__ void __launch_bounds__(256) hb_hydro_kernel(const double* __restrict_
   const double K = X[j * ldx];
   if (K < 0) { atomicOr(err, HB_FLAG_TARGET_DOMAIN); ll[j] = NAN; return; }   // R/test_HydroModel.R:18-19
   const double den = 1.0 + K * 1.0;
+  const double rden = __ddiv_rn(1.0, den);
   double S = 1.0, sse = 0.0, comp = 0.0;
 #pragma unroll 4
   for (int i = 0; i < T; ++i) {
-    S = __ddiv_rn(sP[i] * 1.0 + S, den);
-    const double e = K * S - sO[i];
+    S = div_by_recip(__dadd_rn(sP[i], S), den, rden);         // (forcing[i]*Dt + S0) / (1 + param*Dt), Dt = 1
+    const double e = __dadd_rn(__dmul_rn(K, S), -sO[i]);      // Y[i] - obs[i]
     const double y = e * e - comp;
     const double t = sse + y;
     comp = (t - sse) - y;
@@ -332,10 +356,11 @@ __global__ void hb_hydro_series_kernel(const double* __restrict__ param, long lo
   if (j >= n) return;
   const double K = param[j];
   const double den = 1.0 + K * 1.0;
+  const double rden = __ddiv_rn(1.0, den);
   double S = 1.0;
   for (int i = 0; i < T; ++i) {
-    S = __ddiv_rn(forcing[i] * 1.0 + S, den);
-    out[j * (long long)T + i] = K * S;
+    S = div_by_recip(__dadd_rn(forcing[i], S), den, rden);
+    out[j * (long long)T + i] = __dmul_rn(K, S);
   }
 }
 
@@ -354,11 +379,12 @@ __global__ void __launch_bounds__(128) hb_hydro_items_kernel(const double* __res
   const double K = X[i * ldx];
   if (K < 0) { atomicOr(err, HB_FLAG_TARGET_DOMAIN); ll[i] = NAN; return; }
   const double den = 1.0 + K * 1.0;
+  const double rden = __ddiv_rn(1.0, den);
   double S = 1.0, sse = 0.0, comp = 0.0;
 #pragma unroll 4
   for (int t = 0; t < T; ++t) {
-    S = __ddiv_rn(P[t] * 1.0 + S, den);
-    const double e = K * S - O[t];
+    S = div_by_recip(__dadd_rn(P[t], S), den, rden);
+    const double e = __dadd_rn(__dmul_rn(K, S), -O[t]);
     const double y = e * e - comp;
     const double tt = sse + y;
     comp = (tt - sse) - y;
@@ -529,6 +555,26 @@ extern "C" int hb_register_target(const hb_target_vtable* vt) {
 }
 
 extern "C" int hb_target_registered(const char* name) { return hb_find_target(name) != nullptr; }
+
+__global__ void hb_divcheck_kernel(const double* a, const double* b, long long n, unsigned long long* bad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double y = __ddiv_rn(1.0, b[i]);
+  if (div_by_recip(a[i], b[i], y) != __ddiv_rn(a[i], b[i])) atomicAdd(bad, 1ull);
+}
+
+// test hook: counts pairs where the reciprocal-based quotient differs from the IEEE division (must be 0)
+extern "C" int hb_divcheck(const double* a, const double* b, int64_t n, int64_t* n_bad) {
+  double *da = nullptr, *db = nullptr; unsigned long long* dbad = nullptr; unsigned long long hb = 0;
+  bool ok = cudaMalloc(&da, n * 8) == cudaSuccess && cudaMalloc(&db, n * 8) == cudaSuccess && cudaMalloc(&dbad, 8) == cudaSuccess;
+  ok = ok && cudaMemcpy(da, a, n * 8, cudaMemcpyHostToDevice) == cudaSuccess && cudaMemcpy(db, b, n * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+       cudaMemset(dbad, 0, 8) == cudaSuccess;
+  if (ok) { hb_divcheck_kernel<<<(unsigned)((n + 255) / 256), 256>>>(da, db, n, dbad); ok = cudaMemcpy(&hb, dbad, 8, cudaMemcpyDeviceToHost) == cudaSuccess; }
+  cudaFree(da); cudaFree(db); cudaFree(dbad);
+  if (!ok) return HB_ERR_CUDA;
+  *n_bad = (int64_t)hb;
+  return HB_OK;
+}
 
 extern "C" int hb_hydromodel_series(const double* forcing, int64_t T, const double* param, int64_t n, double* out,
                                     char* err, int errlen) {

@@ -219,6 +219,9 @@ int hb_logdensity(const char* name, int32_t lik, const double* data, const int64
 int hb_hydromodel_series(const double* forcing, int64_t T, const double* param, int64_t n, double* out, char* err,
                          int errlen);
 
+/* test hook: number of pairs for which HydroModel's reciprocal-based division differs from IEEE a/b (must be 0) */
+int hb_divcheck(const double* a, const double* b, int64_t n, int64_t* n_bad);
+
 /* fp64 pipe micro-benchmarks (TFLOP/s): roofline denominators for the log-density kernels (no reference analogue) */
 int hb_fp64_peaks(double* dmma_tflops, double* dfma_tflops);
 

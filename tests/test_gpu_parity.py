@@ -65,6 +65,27 @@ def test_hydromodel_series_bit_exact(hb, oracle):
         hb.HydroModel([0, -1], 0.5)
 
 
+def test_division_by_reciprocal_is_exact(hb):
+    # HydroModel divides by the constant 1 + K every step; the kernel multiplies by RN(1/(1+K)) and corrects with two
+    # FMAs (Markstein).  The quotient must be the IEEE one, bit for bit: randomised check plus adversarial divisors.
+    import ctypes as C
+    rng = np.random.default_rng(0)
+    n = 1 << 22
+    a = np.concatenate([rng.uniform(0, 200, n), rng.uniform(0, 1e-3, n), np.ldexp(rng.uniform(1, 2, n), rng.integers(-40, 40, n))])
+    b = np.concatenate([1 + rng.uniform(0.01, 2, n), 1 + rng.uniform(0, 1e-6, n), np.nextafter(2.0, 0) - rng.integers(0, 4, n) * 2.0 ** -52])
+    a = np.ascontiguousarray(a); b = np.ascontiguousarray(b)
+    bad = C.c_int64(-1)
+    dp = C.POINTER(C.c_double)
+    assert hb.lib().hb_divcheck(a.ctypes.data_as(dp), b.ctypes.data_as(dp), a.size, C.byref(bad)) == 0
+    assert bad.value == 0
+    P, _ = H.hydro_data(T=3653)
+    K = rng.uniform(0.01, 2.0, 512)
+    y = hb.HydroModel(P, K)
+    from oracle import hb_oracle_py as o
+    for i in range(0, 512, 37):
+        assert np.array_equal(y[i], o.hydromodel(P, K[i]))
+
+
 @pytest.mark.parametrize("T", [5, 200, 3653])
 def test_hydromodel_glue_logdensity(hb, oracle, T):
     P, obs = H.hydro_data(T=T)
