@@ -146,6 +146,8 @@ def make_sampler(w, local, rank, world, torch):
         dist.broadcast_object_list(obj, src=0)
         s.comm_init(rank, world, obj[0])
     s.set_initial(w["x0"]())
+    if world > 1 and cfg.exchange == 1:
+        s.peer_setup(world)
     return s
 
 
@@ -258,6 +260,7 @@ def main():
     ap.add_argument("--workload", default="C4")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu_baseline / other workloads (profiling runs)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "allgather"], help="multi-GPU chain-state exchange")
     ap.add_argument("--quick", action="store_true", help="keep the per-kernel roofline, skip e2e / cpu_baseline / others")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -271,6 +274,8 @@ def main():
     assert lib().hb_device_count() >= 1, "no CUDA device: there is no CPU fallback"
     w = workload(args.workload)
     cfg = w["cfg"]
+    if world > 1 and args.exchange == "peer" and cfg.d > 16:
+        cfg.exchange = 1   # HB_EXCHANGE_PEER
     need = (args.steps + args.warmup) * GENS_PER_STEP + 1
     if need > cfg.t:
         cfg.t = need
@@ -314,7 +319,7 @@ def main():
             "config": {"workload": w["desc"], "generations_per_step": GENS_PER_STEP, "chains": cfg.nc, "d": cfg.d,
                        "chains_per_gpu": n_local, "rng": "philox4x32-10", "l2": "inputs larger than L2 (no flush)"
                        if cfg.nc * cfg.d * 8 > 126e6 else "state is L2-resident by construction (latency-bound config)",
-                       "exchange": "ncclAllGather per generation" if world > 1 else "none"},
+                       "exchange": ("none" if world == 1 else "peer gather over NVLink (bulk TMA reads of partner rows) + 17-word all-reduce per generation" if cfg.exchange == 1 else "ncclAllGather per generation")},
             "gpu_launches": l1 - l0}
     if rank == 0 and not args.no_extras:
         peaks = load_peaks()

@@ -126,8 +126,17 @@ int allocate(hb_handle* h) {
   const hb_config& c = h->cfg;
   const long long nl = h->n_local, nc = h->modeb ? h->nct : h->nc;   // batched runs: all runs' chains, run-major
   const int d = h->d, ldx = h->ldx;
-  CK(dalloc(&h->X, (size_t)nc * ldx));
-  CK(cudaMemsetAsync(h->X, 0, (size_t)nc * ldx * sizeof(double), h->stream));
+  if (h->peer_mode) {   // this rank's shard only, double buffered; X becomes the virtual full-population base
+    for (int b = 0; b < 2; ++b) {
+      CK(dalloc(&h->Xbuf[b], (size_t)nl * ldx));
+      CK(cudaMemsetAsync(h->Xbuf[b], 0, (size_t)nl * ldx * sizeof(double), h->stream));
+    }
+    h->cur = 0;
+    h->X = h->Xbuf[0] - h->chain0 * ldx;
+  } else {
+    CK(dalloc(&h->X, (size_t)nc * ldx));
+    CK(cudaMemsetAsync(h->X, 0, (size_t)nc * ldx * sizeof(double), h->stream));
+  }
   if (c.past_sample) { CK(dalloc(&h->Z, (size_t)h->m_cap * ldx)); }
   CK(dalloc(&h->XP, (size_t)nl * ldx));
   CK(cudaMemsetAsync(h->XP, 0, (size_t)nl * ldx * sizeof(double), h->stream));
@@ -191,8 +200,6 @@ int initialise(hb_handle* h) {
   CK(hb_launch_init_state(h->lp_xp, h->ll_raw, h->fx_xp, h->lp, h->ll, h->lpost, h->fx, h->lpost_hist, nl, errp, h->stream));
   CK(hb_launch_store_row(Xl, ldx, d, nl, h->lp, h->ll, h->lpost, h->fx, h->hist_x, h->hist_l, h->hist_fx, h->stream));
   h->launches += 2;
-  // shift for the one-pass column variance: chain 0 of the run
-  CK(cudaMemcpyAsync(h->shift, h->X, sizeof(double) * d, cudaMemcpyDeviceToDevice, h->stream));
   // AR/CR row 1: out_AR[1,1] = out_CR[1,1] = nc ; out_AR[1,2] = NA ; out_CR[1,-1] = pCR   (:245-247)
   const long long nr = c.n_runs;
   const size_t ars = (size_t)h->ar_rows * h->ar_cols, crs = (size_t)h->cr_rows * h->cr_cols;
@@ -260,10 +267,17 @@ int outlier_check(hb_handle* h, long long i) {
     prof_scope ps(h, "OUTLIER");
     // the snapshot of lpost (all chains, pre-reset) keeps the copies independent of the order they run in
     if (h->world == 1) CK(cudaMemcpyAsync(h->lpost_full, h->lpost, sizeof(double) * nc, cudaMemcpyDeviceToDevice, h->stream));
+    if (h->peer_mode) {
+      hb_peer_ptrs pp;
+      for (int r = 0; r < 8; ++r) pp.p[r] = h->peer_ptr[h->cur][r];
+      CK(hb_launch_outlier_reset_peer(h->Xbuf[h->cur], pp, nl, h->ldx, h->d, h->lpost, hrow, h->lpost_full, h->chain0, nl,
+                                      h->outl_dev, h->news_dev, (int)o32.size(), h->stream));
+    } else
     CK(hb_launch_outlier_reset(h->X, h->ldx, h->d, h->lpost, hrow, h->lpost_full, h->chain0, nl, h->outl_dev, h->news_dev,
                                (int)o32.size(), h->stream));
     ps.done();
   }
+  if (h->peer_mode) { if (int rc = hb_nccl_allreduce_u64(h->comm, h->ctrl->n_id_gen, 1, h->stream, h->err)) return rc; }
   CK(cudaStreamSynchronize(h->stream));
   for (long long j : outl) { h->outlier_gen.push_back(i); h->outlier_chain.push_back(j); }   // outl[[i]]  R/dream_parallel.R:418
   return HB_OK;
@@ -282,6 +296,8 @@ hb_k1_params hb_make_k1(hb_handle* h, long long i, long long first, long long st
   p.beta0 = c.beta0; p.psnooker = c.psnooker; p.past_sample = c.past_sample;
   p.bound = h->have_min_max ? c.bound : 0; p.prior = c.prior; p.pmin = h->pmin; p.pmax = h->pmax;
   p.seed = c.seed; p.gen = (uint32_t)i; p.tape = h->tape; p.tape_g = i - 2; p.gamma_tab = h->gamma_tab;
+  p.n_peers = h->peer_mode ? h->world : 1; p.peer_nl = h->n_local;
+  for (int r = 0; r < 8; ++r) p.peer[r] = h->peer_mode ? h->peer_ptr[h->cur][r] : nullptr;
   hb_philox_key_schedule(c.seed, p.ks);
   for (int q = 0; q < c.nCR; ++q) p.thr[q] = (unsigned long long)ceil((double)(q + 1) / (double)c.nCR * 4294967296.0 - 0.5);
   return p;
@@ -293,7 +309,7 @@ hb_k3_params hb_make_k3(hb_handle* h, long long i, long long first, long long st
   const long long nl = h->n_local;
   const int d = h->d;
   hb_k3_params p{};
-  p.X = h->X; p.XP = h->XP; p.XP_rw = h->XP; p.id = h->id; p.lp_xp = h->lp_xp; p.ll_raw = h->ll_raw;
+  p.X = h->X; p.Xout = h->peer_mode ? h->Xbuf[h->cur ^ 1] - h->chain0 * h->ldx : h->X; p.XP = h->XP; p.XP_rw = h->XP; p.id = h->id; p.lp_xp = h->lp_xp; p.ll_raw = h->ll_raw;
   p.fx_xp = c.store_fx ? h->fx_xp : nullptr;
   p.lp = h->lp; p.ll = h->ll; p.lpost = h->lpost; p.fx = c.store_fx ? h->fx : nullptr;
   p.lpost_hist_row = (i <= h->H) ? h->lpost_hist + (i - 1) * nl : nullptr;
@@ -355,7 +371,8 @@ int run_generation(hb_handle* h, long long i) {
     ps.done();
   }
   h->pending_evals += h->nc;
-  if (in_adapt || upd) {  // finalize: J / n_id / n_acc, pCR adaptation, AR/CR rows
+  if (in_adapt || upd || h->peer_mode) {  // finalize: J / n_id / n_acc, pCR adaptation, AR/CR rows (peer mode: every
+                                          // generation, its counter all-reduce is the generation barrier)
     hb_fin_params f{};
     f.ctrl = h->ctrl; f.partials = h->partials; f.nblocks = h->k3_blocks; f.shift = h->shift; f.colsum = h->colsum;
     f.qsum = h->qsum; f.nc = h->nc; f.d = d; f.nCR = c.nCR; f.adapt = in_adapt; f.do_pcr = in_adapt && upd;
@@ -377,7 +394,10 @@ int run_generation(hb_handle* h, long long i) {
     }
     h->pending_evals = 0;
   }
-  if (h->world > 1) {  // chain-state exchange: every rank needs every row for the next generation's partner draws
+  if (h->peer_mode) {   // K3 wrote every row of the shard into the other buffer; peers read it next generation
+    h->cur ^= 1;
+    h->X = h->Xbuf[h->cur] - h->chain0 * ldx;
+  } else if (h->world > 1) {  // chain-state exchange: every rank needs every row for the next generation's partner draws
     prof_scope ps(h, "XCHG");
     if (int rc = hb_nccl_allgather_f64(h->comm, h->X + h->chain0 * ldx, h->X, (size_t)nl * ldx, h->stream, h->err)) return rc;
     ps.done();
@@ -516,6 +536,11 @@ void hb_destroy(hb_handle* h) {
   hb_seq_destroy(h);
   if (h->vt && h->tctx) h->vt->destroy(h->tctx);
   hb_nccl_destroy(h->comm);
+  if (h->peer_mode) {
+    h->X = nullptr;
+    for (int b = 0; b < 2; ++b) for (int r = 0; r < 8; ++r) if (h->peer_opened[b][r]) cudaIpcCloseMemHandle(h->peer_opened[b][r]);
+    cudaFree(h->Xbuf[0]); cudaFree(h->Xbuf[1]);
+  }
   void* ptrs[] = {h->X, h->Z, h->XP, h->id, h->lp_xp, h->ll_raw, h->fx_xp, h->lp, h->ll, h->lpost, h->fx, h->lpost_hist,
                   h->hist_x, h->hist_l, h->hist_fx, h->accept_rec, h->ctrl, h->shift, h->colsum, h->qsum, h->partials,
                   h->out_ar, h->out_cr, h->proxy, h->proxy_full, h->lpost_full, h->outl_dev, h->news_dev, h->rstat_dev,
@@ -600,6 +625,42 @@ int hb_comm_init(hb_handle* h, int rank, int world, const void* id128) {
   if (world > 1) { if (int rc = hb_nccl_init(&h->comm, rank, world, id128, h->err)) return rc; }
   h->rank = rank; h->world = world;
   h->n_local = h->nc / world; h->chain0 = rank * h->n_local;
+  if (world > 1 && h->cfg.exchange == HB_EXCHANGE_PEER) {
+    if (world > 8) return fail(h, HB_ERR_UNSUPPORTED, "peer exchange supports up to 8 GPUs of one node");
+    if (h->cfg.past_sample) return fail(h, HB_ERR_UNSUPPORTED, "peer exchange does not cover the DREAM-ZS archive; use HB_EXCHANGE_ALLGATHER");
+    if (h->d <= 16) return fail(h, HB_ERR_UNSUPPORTED, "peer exchange needs d > 16; use HB_EXCHANGE_ALLGATHER");
+    h->peer_mode = true;
+  }
+  return HB_OK;
+}
+
+int hb_peer_export(hb_handle* h, void* out128) {
+  if (!h || !out128) return HB_ERR_INVALID;
+  if (!h->peer_mode) return fail(h, HB_ERR_STATE, "hb_peer_export: the handle is not in HB_EXCHANGE_PEER mode");
+  if (!h->have_initial) return fail(h, HB_ERR_STATE, "hb_peer_export must follow hb_set_initial");
+  cudaSetDevice(h->device);
+  cudaIpcMemHandle_t hd[2];
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CK(cudaIpcGetMemHandle(&hd[0], h->Xbuf[0]));
+  CK(cudaIpcGetMemHandle(&hd[1], h->Xbuf[1]));
+  memcpy(out128, hd, 128);
+  return HB_OK;
+}
+
+int hb_peer_import(hb_handle* h, const void* all_handles) {
+  if (!h || !all_handles) return HB_ERR_INVALID;
+  if (!h->peer_mode) return fail(h, HB_ERR_STATE, "hb_peer_import: the handle is not in HB_EXCHANGE_PEER mode");
+  cudaSetDevice(h->device);
+  const cudaIpcMemHandle_t* hd = (const cudaIpcMemHandle_t*)all_handles;
+  for (int r = 0; r < h->world; ++r)
+    for (int b = 0; b < 2; ++b) {
+      if (r == h->rank) { h->peer_ptr[b][r] = h->Xbuf[b]; continue; }
+      void* p = nullptr;
+      CK(cudaIpcOpenMemHandle(&p, hd[2 * r + b], cudaIpcMemLazyEnablePeerAccess));
+      h->peer_opened[b][r] = p;
+      h->peer_ptr[b][r] = (const double*)p;
+    }
+  h->peers_ready = true;
   return HB_OK;
 }
 
@@ -614,8 +675,15 @@ int hb_set_initial(hb_handle* h, const double* x0) {
   CK(dalloc(&tmp, (size_t)m0 * d));
   CK(cudaMemcpyAsync(tmp, x0, sizeof(double) * (size_t)m0 * d, cudaMemcpyHostToDevice, h->stream));
   // xt <- z[(m0-nc+1):m0, ]  (R/dream_parallel.R:213)
-  CK(hb_launch_colmajor_to_rows(tmp, m0, m0 - nc, nc, d, ldx, h->X, h->stream));
+  if (h->peer_mode) CK(hb_launch_colmajor_to_rows(tmp, m0, m0 - nc + h->chain0, h->n_local, d, ldx, h->Xbuf[0], h->stream));
+  else CK(hb_launch_colmajor_to_rows(tmp, m0, m0 - nc, nc, d, ldx, h->X, h->stream));
   if (h->Z) CK(hb_launch_colmajor_to_rows(tmp, m0, 0, m0, d, ldx, h->Z, h->stream));
+  {  // shift of the one-pass column variance: chain 0 of the run (identical on every rank)
+    std::vector<double> sh((size_t)d);
+    for (int k = 0; k < d; ++k) sh[(size_t)k] = x0[(m0 - nc) + m0 * (long long)k];
+    CK(cudaMemcpyAsync(h->shift, sh.data(), sizeof(double) * d, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
   CK(cudaStreamSynchronize(h->stream));
   cudaFree(tmp);
   h->have_initial = true;
@@ -639,6 +707,7 @@ int hb_run(hb_handle* h, int64_t n_generations, int64_t* done_total) {
   if (!h->have_initial) return fail(h, HB_ERR_STATE, "hb_run: hb_set_initial has not been called");
   if (h->cfg.rng_mode == HB_RNG_TAPE && !h->have_tape) return fail(h, HB_ERR_STATE, "hb_run: rng_mode is TAPE but no tape was set");
   if (h->cfg.prior == HB_PRIOR_UNIFORM && !h->have_min_max) return fail(h, HB_ERR_INVALID, "prior = 'uniform' needs min and max");
+  if (h->peer_mode && !h->peers_ready) return fail(h, HB_ERR_STATE, "hb_run: HB_EXCHANGE_PEER needs hb_peer_export / hb_peer_import after hb_set_initial");
   if (!h->initialised) { if (int rc = initialise(h)) return rc; if (h->modeb) { if (int rc2 = hb_seq_initialise(h)) return rc2; } }
   long long last = h->gen + n_generations;
   if (last > h->t) last = h->t;
@@ -741,11 +810,11 @@ int hb_fetch_state(hb_handle* h, double* xt, double* lp, double* ll, double* lpo
   if (!h) return HB_ERR_INVALID;
   if (!h->have_initial) return fail(h, HB_ERR_STATE, "no state yet");
   cudaSetDevice(h->device);
-  const long long nc = h->modeb ? h->nct : h->nc, nl = h->n_local;
-  if (xt) {
+  const long long nc = h->peer_mode ? h->n_local : (h->modeb ? h->nct : h->nc), nl = h->n_local;
+  if (xt) {   // peer mode: the rank's shard [n_local, d]; otherwise the whole population [nc, d]
     double* tmp = nullptr;
     CK(dalloc(&tmp, (size_t)nc * h->d));
-    CK(hb_launch_rows_to_colmajor(h->X, h->ldx, h->d, nc, tmp, h->stream));
+    CK(hb_launch_rows_to_colmajor(h->peer_mode ? h->Xbuf[h->cur] : h->X, h->ldx, h->d, nc, tmp, h->stream));
     CK(cudaMemcpyAsync(xt, tmp, sizeof(double) * (size_t)nc * h->d, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     cudaFree(tmp);

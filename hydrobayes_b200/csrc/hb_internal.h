@@ -36,6 +36,14 @@ struct hb_handle {
   long long chain0 = 0, n_local = 0;
   hb_nccl* comm = nullptr;
 
+  // HB_EXCHANGE_PEER: double-buffered shard + peers' buffers (CUDA IPC); X is then the VIRTUAL base
+  // Xbuf[cur] - chain0*ldx so that X + chain*ldx addresses this rank's rows only
+  bool peer_mode = false, peers_ready = false;
+  double* Xbuf[2] = {nullptr, nullptr};
+  int cur = 0;
+  const double* peer_ptr[2][8] = {};
+  void* peer_opened[2][8] = {};
+
   // bounds / prior
   bool have_min_max = false;
   std::vector<double> pmin_h, pmax_h;

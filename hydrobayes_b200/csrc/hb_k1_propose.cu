@@ -369,7 +369,10 @@ __global__ void __launch_bounds__(256, 2) hb_k1_wide_kernel(const hb_k1_params p
         int row;
         if (sn) row = (lane == 1) ? hd[1] : (lane == 2) ? hd[1 + HB_MAX_DELTA] : hd[1 + 2 * HB_MAX_DELTA];
         else row = (lane <= Dn) ? hd[lane] : hd[1 + HB_MAX_DELTA + (lane - 1 - Dn)];    // a[0..D-1], b[0..D-1]
-        g = src + ((p.past_sample ? 0 : rbase_c) + (long long)row) * ldx;
+        if (p.n_peers > 1) {                      // the row lives in rank rk's shard: NVLink peer pointer
+          const int rk = (int)(row / p.peer_nl);
+          g = p.peer[rk] + (long long)(row - rk * p.peer_nl) * ldx;
+        } else g = src + ((p.past_sample ? 0 : rbase_c) + (long long)row) * ldx;
       }
       // stage rows: 0 = x, 1..D = a, 1+delta.. = b (fixed offsets: no D-dependent address arithmetic in the sweep)
       const int srow = (sn || lane <= Dn) ? lane : (1 + delta + (lane - 1 - Dn));
@@ -715,7 +718,8 @@ cudaError_t hb_launch_k1(const hb_k1_params& p, bool tape_mode, int sm_count, cu
   if (d <= 16) return launch_gi<16, 1>(p, tape_mode, sm_count, st);
   if (p.nc > 0x7fffffffLL || p.m_arch > 0x7fffffffLL) return cudaErrorInvalidValue;
   // small populations (fewer 32-chain batches than resident warps): one chain per warp spreads the work over more SMs
-  if (p.n_local < (long long)sm_count * 16 * 32 / 2) {
+  if (p.n_peers > 1 && d <= 16) return cudaErrorInvalidValue;   // peer gather is implemented in the wide kernel
+  if (p.n_peers <= 1 && p.n_local < (long long)sm_count * 16 * 32 / 2) {
     if (d <= 32) return launch_gi<32, 1>(p, tape_mode, sm_count, st);
     if (d <= 64) return launch_gi<32, 2>(p, tape_mode, sm_count, st);
     if (d <= 128) return launch_gi<32, 4>(p, tape_mode, sm_count, st);

@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(256) hb_k3_kernel(const hb_k3_params p) {
     }
     if (G > 1) { accf = __shfl_sync(FULL, accf, gbase); id = __shfl_sync(FULL, id, gbase); }
 
-    const bool need_x = adapt || p.hist_x != nullptr;
+    const bool copy_all = p.Xout != p.X;
+    const bool need_x = adapt || p.hist_x != nullptr || copy_all;
 #pragma unroll
     for (int m = 0; m < ITER; ++m) {
       const int k = m * G + lg;
@@ -86,9 +87,10 @@ __global__ void __launch_bounds__(256) hb_k3_kernel(const hb_k3_params p) {
             if (p.write_dx) p.XP_rw[jl * (long long)ldx + k] = dx;
             else acc[(2 + id) * d + k] += dx * dx;
           }
-          p.X[j * (long long)ldx + k] = xn;                           // :358
+          p.Xout[j * (long long)ldx + k] = xn;                        // :358
         } else {
           if (need_x) xn = p.X[j * (long long)ldx + k];
+          if (copy_all) p.Xout[j * (long long)ldx + k] = xn;
           if (adapt && p.write_dx) p.XP_rw[jl * (long long)ldx + k] = 0.0;   // dx stays 0, R/dream_parallel.R:266
         }
         if (adapt && !p.write_dx) { const double c = xn - sh[m]; s1[m] += c; s2[m] += c * c; }
@@ -184,7 +186,8 @@ __global__ void __launch_bounds__(256) hb_k3_wide_kernel(const hb_k3_params p) {
     const int k = m * 32 + lane;
     sh[m] = (adapt && k < d) ? p.shift[k] : 0.0;
   }
-  const bool all_rows = adapt || p.hist_x != nullptr;   // (write_dx needs every row too: rejected rows get dx = 0)
+  const bool copy_all = p.Xout != p.X;                  // double-buffered shard: rejected rows are carried over
+  const bool all_rows = adapt || p.hist_x != nullptr || copy_all;   // (write_dx needs every row too: dx = 0)
 
   for (long long base = warp_id * 32; base < p.n_local; base += n_warps * 32) {
     const long long jl = base + lane;
@@ -255,9 +258,10 @@ __global__ void __launch_bounds__(256) hb_k3_wide_kernel(const hb_k3_params p) {
               if (p.write_dx) p.XP_rw[jr * (long long)ldx + k] = dx;
               else acc[(2 + id_c) * d + k] += dx * dx;
             }
-            p.X[j * (long long)ldx + k] = xn;                         // :358
+            p.Xout[j * (long long)ldx + k] = xn;                      // :358
           } else {
             xn = p.X[j * (long long)ldx + k];
+            if (copy_all) p.Xout[j * (long long)ldx + k] = xn;
             if (adapt && p.write_dx) p.XP_rw[jr * (long long)ldx + k] = 0.0;
           }
           if (adapt && !p.write_dx) { const double cc = xn - sh[m]; s1[m] += cc; s2[m] += cc * cc; }
@@ -492,6 +496,24 @@ __global__ void hb_outlier_reset_kernel(double* X, int ldx, int d, double* lpost
   }
 }
 
+// peer variant: every rank owns only its shard; the source row is read from the owning rank through its peer pointer
+__global__ void hb_outlier_reset_peer_kernel(double* Xlocal, hb_peer_ptrs peers, long long peer_nl, int ldx, int d,
+                                             double* lpost, double* hist_row, const double* lpost_src, long long chain0,
+                                             long long n_local, const int* outl, const int* news, int n_out) {
+  const int q = blockIdx.x;
+  if (q >= n_out) return;
+  const long long dst = outl[q], srcc = news[q];
+  if (dst < chain0 || dst >= chain0 + n_local) return;
+  const int rk = (int)(srcc / peer_nl);
+  const double* srow = peers.p[rk] + (srcc - rk * peer_nl) * ldx;
+  for (int k = threadIdx.x; k < d; k += blockDim.x) Xlocal[(dst - chain0) * ldx + k] = srow[k];
+  if (threadIdx.x == 0) {
+    const double v = lpost_src[srcc];
+    lpost[dst - chain0] = v;
+    if (hist_row) hist_row[dst - chain0] = v;
+  }
+}
+
 // ---- misc ------------------------------------------------------------------------------------------------
 __global__ void hb_init_state_kernel(const double* lp_in, const double* ll_raw, const double* fx_in, double* lp,
                                      double* ll, double* lpost, double* fx, double* hist_row, long long n,
@@ -608,6 +630,16 @@ cudaError_t hb_launch_outlier_reset(double* X, int ldx, int d, double* lpost, do
   if (n_out <= 0) return cudaSuccess;
   hb_outlier_reset_kernel<<<n_out, 128, 0, st>>>(X, ldx, d, lpost, lpost_hist_row, lpost_src, chain0, n_local, outl,
                                                  news, n_out);
+  return cudaGetLastError();
+}
+
+cudaError_t hb_launch_outlier_reset_peer(double* Xlocal, hb_peer_ptrs peers, long long peer_nl, int ldx, int d,
+                                         double* lpost, double* lpost_hist_row, const double* lpost_src,
+                                         long long chain0, long long n_local, const int* outl, const int* news,
+                                         int n_out, cudaStream_t st) {
+  if (n_out <= 0) return cudaSuccess;
+  hb_outlier_reset_peer_kernel<<<n_out, 128, 0, st>>>(Xlocal, peers, peer_nl, ldx, d, lpost, lpost_hist_row, lpost_src,
+                                                      chain0, n_local, outl, news, n_out);
   return cudaGetLastError();
 }
 

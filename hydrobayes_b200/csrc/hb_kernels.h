@@ -48,6 +48,8 @@ struct hb_k1_params {
   hb_tape_dev tape;
   long long tape_g;       // generation row of the tape (i - 2)
   const double* gamma_tab; // [delta][d]: 2.38/sqrt(2 D d*), built on the host with IEEE sqrt and division
+  const double* peer[8];  // HB_EXCHANGE_PEER: rank r's shard (current buffer), chains [r*peer_nl, (r+1)*peer_nl)
+  int n_peers; long long peer_nl;
   uint32_t ks[20];        // Philox round keys of `seed` (constant bank operands in the kernel)
   unsigned long long thr[HB_MAX_NCR];   // ceil(CR_q 2^32 - 0.5): exact integer form of zt < CR[id]
 };
@@ -56,6 +58,7 @@ cudaError_t hb_launch_k1(const hb_k1_params& p, bool tape_mode, int sm_count, cu
 // ---- K3: Metropolis accept + update + history + adaptation statistics ----------------------------------
 struct hb_k3_params {
   double* X;              // [nc][ldx] updated in place (rows of the local shard)
+  double* Xout;           // == X (in place) or the next buffer of a double-buffered shard (every row is written)
   const double* XP;       // [n_local][ldx]
   double* XP_rw;          // same buffer, writable: receives dx when write_dx
   const int* id;          // [n_local]
@@ -131,6 +134,11 @@ cudaError_t hb_launch_proxy(const double* lpost_hist, long long nc_local, long l
 cudaError_t hb_launch_outlier_reset(double* X, int ldx, int d, double* lpost, double* lpost_hist_row,
                                     const double* lpost_src, long long chain0, long long n_local, const int* outl,
                                     const int* news, int n_out, cudaStream_t st);
+struct hb_peer_ptrs { const double* p[8]; };
+cudaError_t hb_launch_outlier_reset_peer(double* Xlocal, hb_peer_ptrs peers, long long peer_nl, int ldx, int d,
+                                         double* lpost, double* lpost_hist_row, const double* lpost_src,
+                                         long long chain0, long long n_local, const int* outl, const int* news,
+                                         int n_out, cudaStream_t st);
 
 size_t hb_outlier_workspace_bytes(long long nc);
 cudaError_t hb_outlier_device(const double* proxy, long long nc, void* tmp, size_t tmp_bytes, double* sorted,

@@ -101,6 +101,17 @@ class Sampler:
         buf = C.create_string_buffer(unique_id, 128)
         self._check(self.L.hb_comm_init(self.h, rank, world, buf))
 
+    def peer_setup(self, world: int, group=None):
+        """HB_EXCHANGE_PEER: exchange the CUDA IPC handles of the double-buffered shards between the ranks."""
+        import torch.distributed as dist
+        mine = C.create_string_buffer(128)
+        self._check(self.L.hb_peer_export(self.h, mine))
+        parts = [None] * world
+        dist.all_gather_object(parts, bytes(mine.raw), group=group)
+        allh = C.create_string_buffer(b"".join(parts), 128 * world)
+        self._check(self.L.hb_peer_import(self.h, allh))
+        dist.barrier(group=group)
+
     # -- run ------------------------------------------------------------------------------------------
     def run(self, n_generations: int) -> int:
         done = C.c_int64()
@@ -171,8 +182,10 @@ class Sampler:
         return out
 
     def fetch_state(self, n_chains: Optional[int] = None):
-        nc, d = self.n_local(), self.cfg.d
+        d = self.cfg.d
         n = n_chains or self.n_local()
+        peer_shard = n_chains is not None and self.cfg.exchange == A.HB_EXCHANGE_PEER   # peer mode: the shard only
+        nc = n if peer_shard else self.n_local()
         xt = np.empty((nc, d), order="F")
         lp = np.empty(n); ll = np.empty(n); lpost = np.empty(n)
         self._check(self.L.hb_fetch_state(self.h, _ptr(xt), _ptr(lp), _ptr(ll), _ptr(lpost)))

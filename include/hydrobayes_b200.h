@@ -180,6 +180,13 @@ int hb_set_tape(hb_handle* h, const hb_tape* tape);        /* rng_mode == HB_RNG
 /* multi-GPU: one process per GPU; id is the ncclUniqueId (128 bytes) created by hb_comm_unique_id on rank 0 */
 int hb_comm_unique_id(void* id128);
 int hb_comm_init(hb_handle* h, int rank, int world, const void* id128);
+/* HB_EXCHANGE_PEER: instead of all-gathering the chain state every generation, the proposal kernel fetches the partner
+ * rows it needs straight from the owning GPU through NVLink-mapped peer pointers (bulk TMA reads), and the only
+ * per-generation collective left is a 17-word all-reduce that doubles as the generation barrier.  After
+ * hb_set_initial every rank exports 128 bytes (two CUDA IPC handles: the double-buffered shard), the host gathers
+ * them from all ranks (world*128 bytes, rank order) and hands them to hb_peer_import. */
+int hb_peer_export(hb_handle* h, void* out128);
+int hb_peer_import(hb_handle* h, const void* all_handles);
 
 /* Runs up to n_generations further generations (resumable slices: the R driver ticks its progress bar and polls
  * interrupts between slices).  The first call also evaluates the initial population (R/dream_parallel.R:215-250). */
