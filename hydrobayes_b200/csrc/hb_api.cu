@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "hb_internal.h"
@@ -664,7 +665,7 @@ int hb_peer_import(hb_handle* h, const void* all_handles) {
   return HB_OK;
 }
 
-int hb_set_initial(hb_handle* h, const double* x0) {
+static int set_initial_impl(hb_handle* h, const double* x0, bool row_major) {
   if (!h || !x0) return HB_ERR_INVALID;
   if (h->have_initial) return fail(h, HB_ERR_STATE, "hb_set_initial was already called");
   cudaSetDevice(h->device);
@@ -675,12 +676,19 @@ int hb_set_initial(hb_handle* h, const double* x0) {
   CK(dalloc(&tmp, (size_t)m0 * d));
   CK(cudaMemcpyAsync(tmp, x0, sizeof(double) * (size_t)m0 * d, cudaMemcpyHostToDevice, h->stream));
   // xt <- z[(m0-nc+1):m0, ]  (R/dream_parallel.R:213)
-  if (h->peer_mode) CK(hb_launch_colmajor_to_rows(tmp, m0, m0 - nc + h->chain0, h->n_local, d, ldx, h->Xbuf[0], h->stream));
-  else CK(hb_launch_colmajor_to_rows(tmp, m0, m0 - nc, nc, d, ldx, h->X, h->stream));
-  if (h->Z) CK(hb_launch_colmajor_to_rows(tmp, m0, 0, m0, d, ldx, h->Z, h->stream));
+  if (row_major) {   // rows are already contiguous: strided device copies add the ldx padding
+    const size_t sp = sizeof(double) * d, dp = sizeof(double) * ldx;
+    if (h->peer_mode) CK(cudaMemcpy2DAsync(h->Xbuf[0], dp, tmp + (m0 - nc + h->chain0) * d, sp, sp, (size_t)h->n_local, cudaMemcpyDeviceToDevice, h->stream));
+    else CK(cudaMemcpy2DAsync(h->X, dp, tmp + (m0 - nc) * d, sp, sp, (size_t)nc, cudaMemcpyDeviceToDevice, h->stream));
+    if (h->Z) CK(cudaMemcpy2DAsync(h->Z, dp, tmp, sp, sp, (size_t)m0, cudaMemcpyDeviceToDevice, h->stream));
+  } else {
+    if (h->peer_mode) CK(hb_launch_colmajor_to_rows(tmp, m0, m0 - nc + h->chain0, h->n_local, d, ldx, h->Xbuf[0], h->stream));
+    else CK(hb_launch_colmajor_to_rows(tmp, m0, m0 - nc, nc, d, ldx, h->X, h->stream));
+    if (h->Z) CK(hb_launch_colmajor_to_rows(tmp, m0, 0, m0, d, ldx, h->Z, h->stream));
+  }
   {  // shift of the one-pass column variance: chain 0 of the run (identical on every rank)
     std::vector<double> sh((size_t)d);
-    for (int k = 0; k < d; ++k) sh[(size_t)k] = x0[(m0 - nc) + m0 * (long long)k];
+    for (int k = 0; k < d; ++k) sh[(size_t)k] = row_major ? x0[(m0 - nc) * (long long)d + k] : x0[(m0 - nc) + m0 * (long long)k];
     CK(cudaMemcpyAsync(h->shift, sh.data(), sizeof(double) * d, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
   }
@@ -689,6 +697,9 @@ int hb_set_initial(hb_handle* h, const double* x0) {
   h->have_initial = true;
   return HB_OK;
 }
+
+int hb_set_initial(hb_handle* h, const double* x0) { return set_initial_impl(h, x0, false); }
+int hb_set_initial_rows(hb_handle* h, const double* x0_rowmajor) { return set_initial_impl(h, x0_rowmajor, true); }
 
 int hb_set_tape(hb_handle* h, const hb_tape* tape) {
   if (!h || !tape) return HB_ERR_INVALID;
@@ -754,18 +765,49 @@ int hb_fetch_chain_rows(hb_handle* h, int64_t row0, int64_t nrows, double* out) 
   const long long nl = h->n_local;
   const int dd = h->d + 3;
   const size_t per_chain = (size_t)nrows * dd * sizeof(double);
-  size_t want = std::min<size_t>((size_t)256 << 20, per_chain * (size_t)nl);
+  const size_t total = per_chain * (size_t)nl;
+  // two staging buffers: the transposition of chunk k+1 runs on the device while chunk k travels to the host
+  size_t want = std::min<size_t>((size_t)128 << 20, total);
   if (want < per_chain) want = per_chain;
-  if (h->stage_bytes < want) { if (h->stage) cudaFree(h->stage); h->stage = nullptr; CK(cudaMalloc((void**)&h->stage, want)); h->stage_bytes = want; }
-  const long long chunk = (long long)(h->stage_bytes / per_chain);
-  for (long long c0 = 0; c0 < nl; c0 += chunk) {
-    const long long ncs = std::min(chunk, nl - c0);
-    CK(hb_launch_chain_transpose(h->hist_x, h->hist_l, h->out_t, row0, nrows, h->ind_out, nl, h->d, c0, ncs, h->stage, h->stream));
-    h->launches++;
-    CK(cudaMemcpyAsync(out + (size_t)c0 * dd * nrows, h->stage, per_chain * (size_t)ncs, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+  if (h->stage_bytes < 2 * want) { if (h->stage) cudaFree(h->stage); h->stage = nullptr; CK(cudaMalloc((void**)&h->stage, 2 * want)); h->stage_bytes = 2 * want; }
+  const size_t half = h->stage_bytes / 2;
+  const long long chunk = (long long)(half / per_chain);
+  // a freshly allocated result array (R: allocVector, numpy: empty) has never been touched: fault its pages in with a
+  // few threads instead of letting the single copying thread pay for every page fault
+  std::vector<std::thread> touch;
+  if (total >= ((size_t)256 << 20)) {
+    const int nt = 8;
+    char* base = reinterpret_cast<char*>(out);
+    for (int t = 0; t < nt; ++t)
+      touch.emplace_back([=]() {
+        const size_t lo = total / nt * t, hi = (t == nt - 1) ? total : total / nt * (t + 1);
+        for (size_t o = lo; o < hi; o += 4096) base[o] = 0;
+      });
   }
-  return HB_OK;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  CK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+  int rc = HB_OK;
+  auto launch = [&](long long c0, int b) -> cudaError_t {
+    const long long ncs = std::min(chunk, nl - c0);
+    cudaError_t e = hb_launch_chain_transpose(h->hist_x, h->hist_l, h->out_t, row0, nrows, h->ind_out, nl, h->d, c0, ncs,
+                                              reinterpret_cast<double*>(reinterpret_cast<char*>(h->stage) + (size_t)b * half), h->stream);
+    h->launches++;
+    if (e == cudaSuccess) e = cudaEventRecord(ev[b], h->stream);
+    return e;
+  };
+  int b = 0;
+  cudaError_t e = launch(0, 0);
+  for (auto& t : touch) t.join();
+  for (long long c0 = 0; c0 < nl && e == cudaSuccess; c0 += chunk, b ^= 1) {
+    const long long ncs = std::min(chunk, nl - c0);
+    if (c0 + chunk < nl) e = launch(c0 + chunk, b ^ 1);
+    if (e == cudaSuccess) e = cudaEventSynchronize(ev[b]);
+    if (e == cudaSuccess)
+      e = cudaMemcpy(out + (size_t)c0 * dd * nrows, reinterpret_cast<char*>(h->stage) + (size_t)b * half, per_chain * (size_t)ncs, cudaMemcpyDeviceToHost);
+  }
+  cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+  if (e != cudaSuccess) rc = fail(h, HB_ERR_CUDA, "chain fetch failed: %s", cudaGetErrorString(e));
+  return rc;
 }
 
 int hb_fetch_chain(hb_handle* h, double* chain) { return h ? hb_fetch_chain_rows(h, 0, h->out_t, chain) : HB_ERR_INVALID; }

@@ -90,8 +90,12 @@ class Sampler:
 
     def set_initial(self, x0):
         d = self.cfg.d
-        x = np.asfortranarray(np.asarray(x0, np.float64).reshape(-1, d))
-        self._check(self.L.hb_set_initial(self.h, x.ctypes.data_as(_dp)))
+        x = np.asarray(x0, np.float64).reshape(-1, d)
+        if x.flags["F_CONTIGUOUS"] and not x.flags["C_CONTIGUOUS"]:     # R's layout: pass through
+            self._check(self.L.hb_set_initial(self.h, x.ctypes.data_as(_dp)))
+        else:                                                          # numpy's layout: no host transposition
+            x = np.ascontiguousarray(x)
+            self._check(self.L.hb_set_initial_rows(self.h, x.ctypes.data_as(_dp)))
 
     def set_tape(self, tape_struct: A.HbTape, keepalive=None):
         self._keep.append(keepalive)

@@ -175,6 +175,8 @@ int hb_set_target_batched(hb_handle* h, const char* name, const double* data, in
                           const double* obs, int64_t n_obs);
 /* x0: [n_runs*n0, d] column-major, n0 = m0 if past_sample else nc; prior_sample() stays on the host side */
 int hb_set_initial(hb_handle* h, const double* x0_colmajor);
+/* same, for hosts whose matrices are row-major (C / numpy): x0[j*d + k]; no host-side transposition needed */
+int hb_set_initial_rows(hb_handle* h, const double* x0_rowmajor);
 int hb_set_tape(hb_handle* h, const hb_tape* tape);        /* rng_mode == HB_RNG_TAPE */
 
 /* multi-GPU: one process per GPU; id is the ncclUniqueId (128 bytes) created by hb_comm_unique_id on rank 0 */

@@ -185,7 +185,7 @@ def test_replay_sliced_run_equals_single_run(hb, oracle):
     cfg = A.default_config(nc=16, t=120, d=5, lik=2, seed=2, rng_mode=A.HB_RNG_PHILOX, record_accept=1)
     x0 = H.x0_tdist(16, 5)
     a = H.run_device(cfg, "t_distribution", x0)
-    b = H.run_device(cfg, "t_distribution", x0, slice_generations=7)
+    b = H.run_device(cfg, "t_distribution", np.asfortranarray(x0), slice_generations=7)   # R's column-major layout
     assert np.array_equal(a["chain"], b["chain"]) and np.array_equal(a["accept"], b["accept"])
 
 
