@@ -146,7 +146,7 @@ def make_sampler(w, local, rank, world, torch):
         dist.broadcast_object_list(obj, src=0)
         s.comm_init(rank, world, obj[0])
     s.set_initial(w["x0"]())
-    if world > 1 and cfg.exchange == 1:
+    if world > 1 and cfg.exchange in (1, 2):
         s.peer_setup(world)
     return s
 
@@ -260,7 +260,7 @@ def main():
     ap.add_argument("--workload", default="C4")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu_baseline / other workloads (profiling runs)")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "allgather"], help="multi-GPU chain-state exchange")
+    ap.add_argument("--exchange", default="delta", choices=["delta", "peer", "allgather"], help="multi-GPU chain-state exchange")
     ap.add_argument("--quick", action="store_true", help="keep the per-kernel roofline, skip e2e / cpu_baseline / others")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -276,6 +276,8 @@ def main():
     cfg = w["cfg"]
     if world > 1 and args.exchange == "peer" and cfg.d > 16:
         cfg.exchange = 1   # HB_EXCHANGE_PEER
+    if world > 1 and args.exchange == "delta":
+        cfg.exchange = 2   # HB_EXCHANGE_DELTA
     need = (args.steps + args.warmup) * GENS_PER_STEP + 1
     if need > cfg.t:
         cfg.t = need
@@ -319,7 +321,7 @@ def main():
             "config": {"workload": w["desc"], "generations_per_step": GENS_PER_STEP, "chains": cfg.nc, "d": cfg.d,
                        "chains_per_gpu": n_local, "rng": "philox4x32-10", "l2": "inputs larger than L2 (no flush)"
                        if cfg.nc * cfg.d * 8 > 126e6 else "state is L2-resident by construction (latency-bound config)",
-                       "exchange": ("none" if world == 1 else "peer gather over NVLink (bulk TMA reads of partner rows) + 17-word all-reduce per generation" if cfg.exchange == 1 else "ncclAllGather per generation")},
+                       "exchange": ("none" if world == 1 else "delta: accepted rows pulled from the peers over NVLink + 17-word all-reduce per generation" if cfg.exchange == 2 else "peer gather over NVLink (bulk TMA reads of partner rows) + 17-word all-reduce per generation" if cfg.exchange == 1 else "ncclAllGather per generation")},
             "gpu_launches": l1 - l0}
     if rank == 0 and not args.no_extras:
         peaks = load_peaks()

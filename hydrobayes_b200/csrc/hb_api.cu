@@ -139,6 +139,13 @@ int allocate(hb_handle* h) {
     CK(cudaMemsetAsync(h->X, 0, (size_t)nc * ldx * sizeof(double), h->stream));
   }
   if (c.past_sample) { CK(dalloc(&h->Z, (size_t)h->m_cap * ldx)); }
+  if (h->delta_mode) {   // [count (16 B) | idx[cap] | rows[cap][ldx]] per parity
+    h->delta_idx_off = 16;
+    h->delta_rows_off = (16 + (size_t)nl * sizeof(int) + 255) & ~(size_t)255;
+    h->delta_par_bytes = (h->delta_rows_off + (size_t)nl * ldx * sizeof(double) + 255) & ~(size_t)255;
+    CK(cudaMalloc((void**)&h->delta_buf, 2 * h->delta_par_bytes));
+    CK(cudaMemsetAsync(h->delta_buf, 0, 2 * h->delta_par_bytes, h->stream));
+  }
   CK(dalloc(&h->XP, (size_t)nl * ldx));
   CK(cudaMemsetAsync(h->XP, 0, (size_t)nl * ldx * sizeof(double), h->stream));
   CK(dalloc(&h->id, (size_t)nl));
@@ -323,6 +330,12 @@ hb_k3_params hb_make_k3(hb_handle* h, long long i, long long first, long long st
   p.ctrl = h->ctrl; p.shift = h->shift; p.partials = h->partials;
   p.chain0 = first; p.stride = stride; p.n_local = n_items; p.nc = h->nc; p.n_runs = h->cfg.n_runs;
   p.state0 = h->chain0; p.gchain0 = (long long)c.run_offset * h->nc;
+  if (h->delta_mode) {
+    unsigned char* b = h->delta_buf + (size_t)(i & 1) * h->delta_par_bytes;
+    p.delta_count = reinterpret_cast<unsigned*>(b);
+    p.delta_idx = reinterpret_cast<int*>(b + h->delta_idx_off);
+    p.delta_rows = reinterpret_cast<double*>(b + h->delta_rows_off);
+  }
   p.d = d; p.ldx = h->ldx; p.nCR = c.nCR;
   p.adapt = in_adapt; p.write_dx = write_dx; p.seed = c.seed; p.gen = (uint32_t)i;
   p.u_accept = (c.rng_mode == HB_RNG_TAPE) ? h->tape.u_accept + (size_t)(i - 2) * h->tape.nct : nullptr;
@@ -366,13 +379,14 @@ int run_generation(hb_handle* h, long long i) {
   }
   {  // K3
     const hb_k3_params p = hb_make_k3(h, i, h->chain0, 1, nl, store, in_adapt, false);
+    if (h->delta_mode) CK(cudaMemsetAsync(p.delta_count, 0, 16, h->stream));
     prof_scope ps(h, "K3");
     int nb = 0;
     CK(hb_launch_k3(p, h->sm_count, &nb, nullptr, h->stream));
     ps.done();
   }
   h->pending_evals += h->nc;
-  if (in_adapt || upd || h->peer_mode) {  // finalize: J / n_id / n_acc, pCR adaptation, AR/CR rows (peer mode: every
+  if (in_adapt || upd || h->peer_mode || h->delta_mode) {  // finalize: J / n_id / n_acc, pCR adaptation, AR/CR rows (peer mode: every
                                           // generation, its counter all-reduce is the generation barrier)
     hb_fin_params f{};
     f.ctrl = h->ctrl; f.partials = h->partials; f.nblocks = h->k3_blocks; f.shift = h->shift; f.colsum = h->colsum;
@@ -398,6 +412,12 @@ int run_generation(hb_handle* h, long long i) {
   if (h->peer_mode) {   // K3 wrote every row of the shard into the other buffer; peers read it next generation
     h->cur ^= 1;
     h->X = h->Xbuf[h->cur] - h->chain0 * ldx;
+  } else if (h->delta_mode) {   // pull the rows the peers accepted this generation into the local replica
+    hb_delta_peers dp;
+    for (int r = 0; r < 8; ++r) dp.base[r] = h->delta_peer[r] ? h->delta_peer[r] + (size_t)(i & 1) * h->delta_par_bytes : nullptr;
+    prof_scope ps(h, "XCHG");
+    CK(hb_launch_delta_pull(h->X, ldx, d, dp, h->world, h->rank, nl, h->delta_idx_off, h->delta_rows_off, h->sm_count, h->stream));
+    ps.done();
   } else if (h->world > 1) {  // chain-state exchange: every rank needs every row for the next generation's partner draws
     prof_scope ps(h, "XCHG");
     if (int rc = hb_nccl_allgather_f64(h->comm, h->X + h->chain0 * ldx, h->X, (size_t)nl * ldx, h->stream, h->err)) return rc;
@@ -537,6 +557,7 @@ void hb_destroy(hb_handle* h) {
   hb_seq_destroy(h);
   if (h->vt && h->tctx) h->vt->destroy(h->tctx);
   hb_nccl_destroy(h->comm);
+  if (h->delta_mode) { for (int r = 0; r < 8; ++r) if (h->delta_opened[r]) cudaIpcCloseMemHandle(h->delta_opened[r]); cudaFree(h->delta_buf); }
   if (h->peer_mode) {
     h->X = nullptr;
     for (int b = 0; b < 2; ++b) for (int r = 0; r < 8; ++r) if (h->peer_opened[b][r]) cudaIpcCloseMemHandle(h->peer_opened[b][r]);
@@ -626,6 +647,10 @@ int hb_comm_init(hb_handle* h, int rank, int world, const void* id128) {
   if (world > 1) { if (int rc = hb_nccl_init(&h->comm, rank, world, id128, h->err)) return rc; }
   h->rank = rank; h->world = world;
   h->n_local = h->nc / world; h->chain0 = rank * h->n_local;
+  if (world > 1 && h->cfg.exchange == HB_EXCHANGE_DELTA) {
+    if (world > 8) return fail(h, HB_ERR_UNSUPPORTED, "delta exchange supports up to 8 GPUs of one node");
+    h->delta_mode = true;
+  }
   if (world > 1 && h->cfg.exchange == HB_EXCHANGE_PEER) {
     if (world > 8) return fail(h, HB_ERR_UNSUPPORTED, "peer exchange supports up to 8 GPUs of one node");
     if (h->cfg.past_sample) return fail(h, HB_ERR_UNSUPPORTED, "peer exchange does not cover the DREAM-ZS archive; use HB_EXCHANGE_ALLGATHER");
@@ -637,11 +662,17 @@ int hb_comm_init(hb_handle* h, int rank, int world, const void* id128) {
 
 int hb_peer_export(hb_handle* h, void* out128) {
   if (!h || !out128) return HB_ERR_INVALID;
-  if (!h->peer_mode) return fail(h, HB_ERR_STATE, "hb_peer_export: the handle is not in HB_EXCHANGE_PEER mode");
+  if (!h->peer_mode && !h->delta_mode) return fail(h, HB_ERR_STATE, "hb_peer_export: the handle is not in HB_EXCHANGE_PEER / HB_EXCHANGE_DELTA mode");
   if (!h->have_initial) return fail(h, HB_ERR_STATE, "hb_peer_export must follow hb_set_initial");
   cudaSetDevice(h->device);
   cudaIpcMemHandle_t hd[2];
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (h->delta_mode) {
+    memset(hd, 0, sizeof hd);
+    CK(cudaIpcGetMemHandle(&hd[0], h->delta_buf));
+    memcpy(out128, hd, 128);
+    return HB_OK;
+  }
   CK(cudaIpcGetMemHandle(&hd[0], h->Xbuf[0]));
   CK(cudaIpcGetMemHandle(&hd[1], h->Xbuf[1]));
   memcpy(out128, hd, 128);
@@ -650,9 +681,20 @@ int hb_peer_export(hb_handle* h, void* out128) {
 
 int hb_peer_import(hb_handle* h, const void* all_handles) {
   if (!h || !all_handles) return HB_ERR_INVALID;
-  if (!h->peer_mode) return fail(h, HB_ERR_STATE, "hb_peer_import: the handle is not in HB_EXCHANGE_PEER mode");
+  if (!h->peer_mode && !h->delta_mode) return fail(h, HB_ERR_STATE, "hb_peer_import: the handle is not in HB_EXCHANGE_PEER / HB_EXCHANGE_DELTA mode");
   cudaSetDevice(h->device);
   const cudaIpcMemHandle_t* hd = (const cudaIpcMemHandle_t*)all_handles;
+  if (h->delta_mode) {
+    for (int r = 0; r < h->world; ++r) {
+      if (r == h->rank) { h->delta_peer[r] = h->delta_buf; continue; }
+      void* p = nullptr;
+      CK(cudaIpcOpenMemHandle(&p, hd[2 * r], cudaIpcMemLazyEnablePeerAccess));
+      h->delta_opened[r] = p;
+      h->delta_peer[r] = (const unsigned char*)p;
+    }
+    h->peers_ready = true;
+    return HB_OK;
+  }
   for (int r = 0; r < h->world; ++r)
     for (int b = 0; b < 2; ++b) {
       if (r == h->rank) { h->peer_ptr[b][r] = h->Xbuf[b]; continue; }
@@ -718,7 +760,7 @@ int hb_run(hb_handle* h, int64_t n_generations, int64_t* done_total) {
   if (!h->have_initial) return fail(h, HB_ERR_STATE, "hb_run: hb_set_initial has not been called");
   if (h->cfg.rng_mode == HB_RNG_TAPE && !h->have_tape) return fail(h, HB_ERR_STATE, "hb_run: rng_mode is TAPE but no tape was set");
   if (h->cfg.prior == HB_PRIOR_UNIFORM && !h->have_min_max) return fail(h, HB_ERR_INVALID, "prior = 'uniform' needs min and max");
-  if (h->peer_mode && !h->peers_ready) return fail(h, HB_ERR_STATE, "hb_run: HB_EXCHANGE_PEER needs hb_peer_export / hb_peer_import after hb_set_initial");
+  if ((h->peer_mode || h->delta_mode) && !h->peers_ready) return fail(h, HB_ERR_STATE, "hb_run: HB_EXCHANGE_PEER needs hb_peer_export / hb_peer_import after hb_set_initial");
   if (!h->initialised) { if (int rc = initialise(h)) return rc; if (h->modeb) { if (int rc2 = hb_seq_initialise(h)) return rc2; } }
   long long last = h->gen + n_generations;
   if (last > h->t) last = h->t;

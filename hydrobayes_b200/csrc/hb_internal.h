@@ -44,6 +44,12 @@ struct hb_handle {
   const double* peer_ptr[2][8] = {};
   void* peer_opened[2][8] = {};
 
+  // HB_EXCHANGE_DELTA: per-parity pack buffers [count | idx | rows] in ONE allocation (one IPC handle per rank)
+  bool delta_mode = false;
+  unsigned char* delta_buf = nullptr; size_t delta_par_bytes = 0, delta_idx_off = 0, delta_rows_off = 0;
+  const unsigned char* delta_peer[8] = {};
+  void* delta_opened[8] = {};
+
   // bounds / prior
   bool have_min_max = false;
   std::vector<double> pmin_h, pmax_h;

@@ -72,6 +72,11 @@ __global__ void __launch_bounds__(256) hb_k3_kernel(const hb_k3_params p) {
       id = p.id[jl];
     }
     if (G > 1) { accf = __shfl_sync(FULL, accf, gbase); id = __shfl_sync(FULL, id, gbase); }
+    unsigned dslot = 0;
+    if (p.delta_count) {
+      if (valid && lg == 0 && accf) { dslot = atomicAdd(p.delta_count, 1u); p.delta_idx[dslot] = (int)j; }
+      if (G > 1) dslot = __shfl_sync(FULL, dslot, gbase);
+    }
 
     const bool copy_all = p.Xout != p.X;
     const bool need_x = adapt || p.hist_x != nullptr || copy_all;
@@ -88,6 +93,7 @@ __global__ void __launch_bounds__(256) hb_k3_kernel(const hb_k3_params p) {
             else acc[(2 + id) * d + k] += dx * dx;
           }
           p.Xout[j * (long long)ldx + k] = xn;                        // :358
+          if (p.delta_rows) p.delta_rows[(long long)dslot * ldx + k] = xn;
         } else {
           if (need_x) xn = p.X[j * (long long)ldx + k];
           if (copy_all) p.Xout[j * (long long)ldx + k] = xn;
@@ -237,11 +243,17 @@ __global__ void __launch_bounds__(256) hb_k3_wide_kernel(const hb_k3_params p) {
       if (lane == 0 && amask) atomicAdd(&s_cnt[0], (unsigned long long)__popc(amask));   // n_acc :374
     }
 
+    unsigned dbase = 0;
+    if (p.delta_count && amask) {                                     // one atomic per batch reserves the pack slots
+      if (lane == 0) dbase = atomicAdd(p.delta_count, (unsigned)__popc(amask));
+      dbase = __shfl_sync(FULL, dbase, 0);
+    }
     unsigned rows = all_rows ? vmask : amask;
     while (rows) {
       const int c = __ffs(rows) - 1;
       rows &= rows - 1;
       const int a_c = (amask >> c) & 1;
+      const unsigned dslot = dbase + __popc(amask & ((1u << c) - 1u));
       const int id_c = __shfl_sync(FULL, id, c);
       const long long jr = base + c;
       const long long j = p.chain0 + jr * p.stride;
@@ -259,6 +271,7 @@ __global__ void __launch_bounds__(256) hb_k3_wide_kernel(const hb_k3_params p) {
               else acc[(2 + id_c) * d + k] += dx * dx;
             }
             p.Xout[j * (long long)ldx + k] = xn;                      // :358
+            if (p.delta_rows) p.delta_rows[(long long)dslot * ldx + k] = xn;
           } else {
             xn = p.X[j * (long long)ldx + k];
             if (copy_all) p.Xout[j * (long long)ldx + k] = xn;
@@ -268,6 +281,7 @@ __global__ void __launch_bounds__(256) hb_k3_wide_kernel(const hb_k3_params p) {
           if (p.hist_x) p.hist_x[sr * (long long)d + k] = xn;         // chain[ind_out, 1:d, ] :388
         }
       }
+      if (a_c && p.delta_idx && lane == 0) p.delta_idx[dslot] = (int)j;
     }
   }
 
@@ -514,6 +528,27 @@ __global__ void hb_outlier_reset_peer_kernel(double* Xlocal, hb_peer_ptrs peers,
   }
 }
 
+// HB_EXCHANGE_DELTA: patch this rank's replica with the rows the peers accepted this generation.  One warp per packed
+// row: the chain id and the 8 d bytes of the row are read from the owning GPU through its NVLink peer pointer.
+__global__ void __launch_bounds__(256) hb_delta_pull_kernel(double* __restrict__ X, int ldx, int d, hb_delta_peers peers,
+                                                            int n_peers, int self, long long cap, size_t idx_off,
+                                                            size_t rows_off) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (int r = 0; r < n_peers; ++r) {
+    if (r == self) continue;
+    const unsigned char* b = peers.base[r];
+    const unsigned cnt = *reinterpret_cast<const volatile unsigned*>(b);
+    const int* idx = reinterpret_cast<const int*>(b + idx_off);
+    const double* rows = reinterpret_cast<const double*>(b + rows_off);
+    for (long long s = warp_id; s < (long long)cnt && s < cap; s += n_warps) {
+      const long long j = idx[s];
+      for (int k = lane; k < d; k += 32) X[j * ldx + k] = rows[s * ldx + k];
+    }
+  }
+}
+
 // ---- misc ------------------------------------------------------------------------------------------------
 __global__ void hb_init_state_kernel(const double* lp_in, const double* ll_raw, const double* fx_in, double* lp,
                                      double* ll, double* lpost, double* fx, double* hist_row, long long n,
@@ -640,6 +675,12 @@ cudaError_t hb_launch_outlier_reset_peer(double* Xlocal, hb_peer_ptrs peers, lon
   if (n_out <= 0) return cudaSuccess;
   hb_outlier_reset_peer_kernel<<<n_out, 128, 0, st>>>(Xlocal, peers, peer_nl, ldx, d, lpost, lpost_hist_row, lpost_src,
                                                       chain0, n_local, outl, news, n_out);
+  return cudaGetLastError();
+}
+
+cudaError_t hb_launch_delta_pull(double* X, int ldx, int d, hb_delta_peers peers, int n_peers, int self, long long cap,
+                                 size_t idx_off, size_t rows_off, int sm_count, cudaStream_t st) {
+  hb_delta_pull_kernel<<<sm_count * 4, 256, 0, st>>>(X, ldx, d, peers, n_peers, self, cap, idx_off, rows_off);
   return cudaGetLastError();
 }
 

@@ -60,7 +60,9 @@ enum { HB_BOUND_NONE = 0, HB_BOUND_BOUND = 1, HB_BOUND_REFLECT = 2, HB_BOUND_FOL
 enum { HB_RNG_TAPE = 0, HB_RNG_PHILOX = 1 };
 /* multi-GPU chain-state exchange */
 enum { HB_EXCHANGE_ALLGATHER = 0 /* ncclAllGather of the shard's rows */,
-       HB_EXCHANGE_PEER = 1      /* proposal kernel gathers partner rows through NVLink peer pointers */ };
+       HB_EXCHANGE_PEER = 1      /* proposal kernel gathers partner rows through NVLink peer pointers */,
+       HB_EXCHANGE_DELTA = 2     /* only ACCEPTED rows travel: every rank packs the rows its accept kernel changed, the
+                                    peers pull them over NVLink and patch their replica (traffic x acceptance rate) */ };
 
 /*
  * Mirrors the formals of dream() (R/dream.R:126-133) and dream_parallel()

@@ -18,7 +18,7 @@ import helpers as H
 from hydrobayes_b200 import Sampler, _abi as A, lib
 
 
-def run(cfg, target, x0, local, rank=0, world=1, uid=None, kw={}, peer=False):
+def run(cfg, target, x0, local, rank=0, world=1, uid=None, kw={}, peer=False, shard_state=False):
     with Sampler(cfg, local) as s:
         if "par_min" in kw:
             s.set_bounds(kw["par_min"], kw["par_max"])
@@ -38,7 +38,7 @@ def run(cfg, target, x0, local, rank=0, world=1, uid=None, kw={}, peer=False):
         ar, cr = s.fetch_ar_cr()
         acc = s.fetch_accept(nl)
         xt, lp, ll, lpost = s.fetch_state(nl)
-        if not peer and world > 1:
+        if not shard_state and world > 1:
             xt = xt[rank * nl:(rank + 1) * nl]
         return dict(chain=chain, AR=ar, CR=cr, accept=acc, xt=xt, lpost=lpost, outlier=s.fetch_outliers())
 
@@ -54,16 +54,17 @@ def main():
     cases.append(("tdist d=100", A.default_config(nc=nc, t=150, d=d, lik=2, seed=5, adapt=0.4, record_accept=1), "t_distribution", x0, {}))
     nc1 = 512 * world
     cases.append(("mixture d=1", A.default_config(nc=nc1, t=200, d=1, lik=1, seed=9, adapt=0.3, record_accept=1), "mixture", H.x0_mixture(nc1), {}))
-    cases = [c + (False,) for c in cases] + [c + (True,) for c in cases if c[1].d > 16]
-    for name, cfg, tgt, x0, kw, peer in cases:
-        if peer:
-            cfg = H.copy_cfg(cfg, exchange=A.HB_EXCHANGE_PEER); name += " [peer exchange]"
+    cases = [c + (0,) for c in cases] + [c + (1,) for c in cases if c[1].d > 16] + [c + (2,) for c in cases]
+    for name, cfg, tgt, x0, kw, xmode in cases:
+        peer = xmode != 0
+        if xmode:
+            cfg = H.copy_cfg(cfg, exchange=xmode); name += [" ", " [peer exchange]", " [delta exchange]"][xmode]
         buf = C.create_string_buffer(128)
         if rank == 0:
             assert lib().hb_comm_unique_id(buf) == 0
         obj = [bytes(buf.raw)]
         dist.broadcast_object_list(obj, src=0)
-        sh = run(cfg, tgt, x0, local, rank, world, obj[0], kw, peer=peer)
+        sh = run(cfg, tgt, x0, local, rank, world, obj[0], kw, peer=peer, shard_state=(xmode == 1))
         full = run(cfg, tgt, x0, local, kw=kw)
         nl = cfg.nc // world; lo = rank * nl
         same = (np.array_equal(sh["chain"], full["chain"][:, :, lo:lo + nl], equal_nan=True)
