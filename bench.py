@@ -278,7 +278,7 @@ def main():
         cfg.exchange = 1   # HB_EXCHANGE_PEER
     if world > 1 and args.exchange == "delta":
         cfg.exchange = 2   # HB_EXCHANGE_DELTA
-    need = (args.steps + args.warmup) * GENS_PER_STEP + 1
+    need = (args.steps + args.warmup + (0 if args.no_extras else 2)) * GENS_PER_STEP + 1   # + the profiled generations
     if need > cfg.t:
         cfg.t = need
     s = make_sampler(w, local, rank, world, torch)

@@ -307,7 +307,7 @@ hb_k1_params hb_make_k1(hb_handle* h, long long i, long long first, long long st
   p.n_peers = h->peer_mode ? h->world : 1; p.peer_nl = h->n_local;
   for (int r = 0; r < 8; ++r) p.peer[r] = h->peer_mode ? h->peer_ptr[h->cur][r] : nullptr;
   hb_philox_key_schedule(c.seed, p.ks);
-  for (int q = 0; q < c.nCR; ++q) p.thr[q] = (unsigned long long)ceil((double)(q + 1) / (double)c.nCR * 4294967296.0 - 0.5);
+  for (int q = 0; q < c.nCR; ++q) p.thr16[q] = hb_rng_zt_threshold16((double)(q + 1) / (double)c.nCR);
   return p;
 }
 

@@ -5,7 +5,8 @@
 //   slot 1..4   two 64-bit draws each -> partial Fisher-Yates partner draws 0..7 (delta <= 4)     R/internals.R:134,142
 //   slot 5      words 0-1 -> u_id (crossover index)     words 2-3 -> u_gamma                        R/internals.R:173,192
 //   slot 6      words 0-1 -> u_accept                   words 2-3 -> g_snooker = 1.2 + u            R/internals.R:241,156
-//   slot 8+k    word 0 -> zt_k, word 1 -> lambda_k, words 2-3 -> zeta_k (hb_rng_normal)            R/internals.R:175,188,194
+//   slot 8+(k>>1)  dimension k uses words (0,1) if k is even, (2,3) if odd (slot map v2, hydrobayes_b200_rng.h):
+//               lo bits 0-15 -> zt_k, lo bits 16-31 -> lambda_k, hi -> zeta_k (hb_rng_normal32)   R/internals.R:175,188,194
 //   outlier replacement draws: chain = (0xFFFFFFFF << 32) | run, slot = q >> 1, pair q & 1 (host side) R/internals.R:81
 #pragma once
 #include <cuda_runtime.h>
@@ -103,9 +104,9 @@ __host__ __device__ __forceinline__ double hb_u32d(uint32_t x) { return hb_rng_u
 #ifdef __CUDACC__
 __device__ __forceinline__ uint64_t hb_mulhi64(uint64_t a, uint64_t b) { return __umul64hi(a, b); }
 
-// zeta ~ N(0, c_star^2): bit-reproducible Box-Muller of include/hydrobayes_b200_rng.h
-__device__ __forceinline__ double hb_zeta(uint32_t w2, uint32_t w3, double c_star) {
-  return __dmul_rn(c_star, hb_rng_normal(w2, w3));
+// zeta ~ N(0, c_star^2): bit-reproducible integer-CLT deviate of include/hydrobayes_b200_rng.h
+__device__ __forceinline__ double hb_zeta32(uint32_t hi, double c_star) {
+  return __dmul_rn(c_star, hb_rng_normal32(hi));
 }
 
 // sparse partial Fisher-Yates over 0..n-1 (R's sample(n, k) without replacement: y = x[r]; x[r] = x[--n])

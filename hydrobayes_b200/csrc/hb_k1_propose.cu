@@ -7,8 +7,9 @@
 // m < ITER.  A warp therefore reads a partner row as ITER fully coalesced 256-byte segments, and the rows of the
 // 1 + 2D chains it touches are the only HBM traffic (48d + 16 bytes per chain-generation).  Loads of
 // dimensions outside the crossover subspace are predicated off.  Random draws are either read from the decision
-// tape or generated with Philox4x32-10 keyed by (seed; chain, generation, slot): one Philox call per dimension
-// (zt, lambda, zeta) plus five per chain, the latter computed by five different lanes and broadcast.
+// tape or generated with Philox4x32-10 keyed by (seed; chain, generation, slot): one Philox call per two dimensions
+// (zt, lambda, zeta; slot map v2 in include/hydrobayes_b200_rng.h) plus six per chain, the latter computed by
+// different lanes and broadcast.
 #include "hb_kernels.h"
 
 namespace {
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(256) hb_k1_kernel(const hb_k1_params p) {
         if (k < d) {
           double zeta;
           if (TAPE) zeta = p.tape.zeta[rix * d + k];
-          else { const uint4 w = ph.slot(HB_SLOT_DIM0 + (uint32_t)k); zeta = hb_zeta(w.z, w.w, p.c_star); }
+          else { const uint4 w = ph.slot(HB_SLOT_DIM0 + (uint32_t)(k >> 1)); zeta = hb_zeta32((k & 1) ? w.w : w.y, p.c_star); }
           double rp2 = a2[m], rp3 = a3[m];
           if (differs) {
             rp2 = __dadd_rn(xk[m], __ddiv_rn(__dmul_rn(uu[m], s2), su));   // q <- a + u*sum((p-a)*u)/sum(u*u)
@@ -200,18 +201,19 @@ __global__ void __launch_bounds__(256) hb_k1_kernel(const hb_k1_params p) {
       // ---------------- parallel direction update, R/internals.R:166-200 ----------------
       const double CRv = (double)(id + 1) / (double)nCR;               // CR <- (1:nCR)/nCR
       double ztv[ITER];
-      uint32_t wl[ITER], wz2[ITER], wz3[ITER];
+      uint32_t wl[ITER], wz[ITER];     // slot map v2: one Philox call per two dimensions (lo word: zt | lambda; hi: zeta)
       unsigned selmask[ITER];
       int d_star = 0;
 #pragma unroll
       for (int m = 0; m < ITER; ++m) {
         const int k = m * G + lg;
-        ztv[m] = 2.0; wl[m] = 0; wz2[m] = 0; wz3[m] = 0;
+        ztv[m] = 2.0; wl[m] = 0; wz[m] = 0;
         if (k < d) {
           if (TAPE) ztv[m] = p.tape.zt[rix * d + k];                   // :175
           else {
-            const uint4 w = ph.slot(HB_SLOT_DIM0 + (uint32_t)k);
-            ztv[m] = hb_u32d(w.x); wl[m] = w.y; wz2[m] = w.z; wz3[m] = w.w;
+            const uint4 w = ph.slot(HB_SLOT_DIM0 + (uint32_t)(k >> 1));
+            const uint32_t lo = (k & 1) ? w.z : w.x;
+            ztv[m] = hb_rng_u16(lo); wl[m] = lo >> 16; wz[m] = (k & 1) ? w.w : w.y;
           }
         }
         selmask[m] = hb_group_ballot<G>(k < d && ztv[m] < CRv, lane, gmask); // A <- which(zt < CR[id])  :177
@@ -250,8 +252,8 @@ __global__ void __launch_bounds__(256) hb_k1_kernel(const hb_k1_params p) {
               lambda = p.tape.lambda[rix * d + rank];                  // :188 (by rank within A)
               zeta = p.tape.zeta[rix * d + rank];                      // :194
             } else {
-              lambda = hb_rng_lambda(wl[m], p.c_val);
-              zeta = hb_zeta(wz2[m], wz3[m], p.c_star);
+              lambda = hb_rng_lambda16(wl[m], p.c_val);
+              zeta = hb_zeta32(wz[m], p.c_star);
             }
             // jump_diff <- colSums(r1[,A] - r2[,A])   :196
             double s = 0.0, comp = 0.0;
@@ -304,15 +306,20 @@ __global__ void __launch_bounds__(256) hb_k1_kernel(const hb_k1_params p) {
 
 
 // ------------------------------------------------------------------------------------------------------------------
-// Wide variant (d > 16): a warp owns a batch of 32 chains.
+// Wide variants (d > 16): a warp owns a batch of 32 chains.
 //   phase A  lane-per-chain: the per-chain draws (snooker test, D, partner ids by partial Fisher-Yates, crossover id,
 //            gamma choice) are computed once per chain by ONE lane -- 32 chains in parallel, no redundant lanes --
 //            and parked in shared memory;
 //   phase B  warp-per-chain: the rows the chain needs (its own state and the 2D partner rows) are fetched by 1-D bulk
 //            TMA copies (cp.async.bulk -> shared memory, one mbarrier per stage) TWO chains ahead, so the HBM gather
 //            latency is hidden behind the Philox work of the chains in between and costs no registers; the 32 lanes
-//            then sweep the row out of shared memory (lane owns dimensions k = 32 m + lane): one Philox call per
-//            dimension, subspace test as an exact integer compare, error-free pair sum, xp store.
+//            then sweep the row out of shared memory.
+// Two kernels share this frame:
+//   hb_k1_pair_kernel  native Philox draws.  A lane owns PAIRS of adjacent dimensions (k0 = 2 (32 m + lane), k0 + 1):
+//                      one Philox4x32-10 call serves both (slot map v2: 64 bits per dimension), rows are read with
+//                      128-bit shared loads and xp leaves as 128-bit stores.  The kernel is instruction-issue bound
+//                      (profiles/r01_final_*), so everything is sized in warp instructions per chain.
+//   hb_k1_tape_kernel  replay mode: draws come from the decision tape, lane owns dimensions k = 32 m + lane.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int K1_STAGES = 2;
 constexpr int K1_HEAD_WORDS = 12;   // packed, a[4], b[4], third snooker row, g_snooker (2 words)
@@ -323,8 +330,372 @@ __host__ __device__ inline size_t k1_warp_smem_bytes(int delta, int ldx) {
   return (size_t)K1_STAGES * k1_rows_max(delta) * ldx * 8 + 32 * K1_HEAD_WORDS * 4 + K1_STAGES * 8;
 }
 
-template <int ITER, bool TAPE>
-__global__ void __launch_bounds__(256, 2) hb_k1_wide_kernel(const hb_k1_params p) {
+// phase A: the head of chain base + lane -> heads[lane][...].  Row ids are absolute rows of the source matrix
+// (X: run offset added; Z: archive row), so that phase B turns them into addresses with one multiply.
+template <bool TAPE>
+__device__ __forceinline__ void k1_phase_a(const hb_k1_params& p, long long base, int lane, int n_src, int* heads,
+                                           unsigned& errbits) {
+  const int nCR = p.nCR, delta = p.delta;
+  int hD = 1, hid = 0;
+  int hpa[HB_MAX_DELTA], hpb[HB_MAX_DELTA], hps2 = 0;
+  double hgsn = 0.0;
+#pragma unroll
+  for (int q = 0; q < HB_MAX_DELTA; ++q) { hpa[q] = 0; hpb[q] = 0; }
+  const long long jl_raw = base + lane;
+  const long long jl = jl_raw < p.n_local ? jl_raw : p.n_local - 1;
+  const long long gl = p.chain0 + jl * p.stride;
+  const long long run = p.n_runs > 1 ? gl / p.nc : 0;
+  const long long j = gl - run * p.nc;
+  const long long gch = p.gchain0 + gl;
+  double u_sn;
+  int g1;
+  if (TAPE) {
+    const long long rix = p.tape_g * p.tape.nct + gl;
+    u_sn = p.tape.u_snooker ? p.tape.u_snooker[rix] : 1.0;          // R/internals.R:119
+    hD = p.tape.D[rix];                                             // :123
+    hid = p.tape.id[rix];                                           // :173
+    g1 = p.tape.g_is_one[rix];                                      // :192
+    if (p.tape.g_snooker) hgsn = p.tape.g_snooker[rix];             // :156
+    if (hD < 1 || hD > delta || hid >= nCR) { errbits |= HB_FLAG_BAD_TAPE; hD = 1; hid = 0; }
+    const int32_t* pr = p.tape.partners + rix * (2 * delta);
+#pragma unroll
+    for (int q = 0; q < HB_MAX_DELTA; ++q)
+      if (q < hD) { hpa[q] = pr[q]; hpb[q] = pr[hD + q]; }
+    if (p.past_sample && u_sn < p.psnooker) { hpa[0] = pr[0]; hpb[0] = pr[1]; hps2 = pr[2]; }
+  } else {
+    const hb_phx ph(p.seed, (uint64_t)gch, p.gen);
+    const uint4 w0 = ph.slot(HB_SLOT_HEAD);
+    const uint4 wc = ph.slot(HB_SLOT_CHOICE);
+    u_sn = hb_u53(hb_pair64(w0, 0));
+    hD = 1 + (int)hb_mulhi64(hb_pair64(w0, 1), (uint64_t)delta);
+    const double u_id = hb_u53(hb_pair64(wc, 0));
+    double cum = 0.0;
+    hid = nCR - 1;
+    bool found = false;
+    for (int q = 0; q < nCR; ++q) {
+      cum += p.ctrl[run].pCR[q];
+      if (!found && u_id < cum) { hid = q; found = true; }
+    }
+    g1 = hb_u53(hb_pair64(wc, 1)) >= 1.0 - p.p_g;
+    const bool sn = p.past_sample && (u_sn < p.psnooker);
+    if (sn) hgsn = 1.2 + hb_u53(hb_pair64(ph.slot(HB_SLOT_ACCEPT), 1));
+    const int n_part = sn ? 3 : 2 * hD;
+    hb_fy fy;
+    long long n_rem = p.past_sample ? p.m_arch : p.nc - 1;
+    int y[2 * HB_MAX_DELTA];
+    uint4 wp = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int q = 0; q < 2 * HB_MAX_DELTA; ++q) {
+      y[q] = 0;
+      if (q < n_part) {
+        if ((q & 1) == 0) wp = ph.slot(HB_SLOT_PARTNER0 + (q >> 1));
+        long long v = fy.draw(hb_pair64(wp, q & 1), n_rem);
+        if (!p.past_sample && v >= j) v += 1;                       // sample((1:nc)[-j], ...)  :142
+        y[q] = (int)v;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < HB_MAX_DELTA; ++q) {
+      hpa[q] = y[q];
+      hpb[q] = (hD == 1) ? y[(1 + q) & 7] : (hD == 2) ? y[(2 + q) & 7] : (hD == 3) ? y[(3 + q) & 7] : y[(4 + q) & 7];
+    }
+    if (sn) { hpb[0] = y[1]; hps2 = y[2]; }
+  }
+  const bool sn = p.past_sample && (u_sn < p.psnooker);
+#pragma unroll
+  for (int q = 0; q < HB_MAX_DELTA; ++q) {
+    const bool used = sn ? (q == 0) : (q < hD);
+    if (used && (hpa[q] < 0 || hpa[q] >= n_src || hpb[q] < 0 || hpb[q] >= n_src)) {
+      errbits |= HB_FLAG_BAD_TAPE; hpa[q] = 0; hpb[q] = 0;
+    }
+  }
+  if (sn && (hps2 < 0 || hps2 >= n_src)) { errbits |= HB_FLAG_BAD_TAPE; hps2 = 0; }
+  const int roff = p.past_sample ? 0 : (int)(gl - j);               // first chain of this chain's run
+  int* hd = heads + lane * K1_HEAD_WORDS;
+  hd[0] = hD | (hid << 8) | ((g1 ? 1 : 0) << 16) | ((sn ? 1 : 0) << 17);
+#pragma unroll
+  for (int q = 0; q < HB_MAX_DELTA; ++q) { hd[1 + q] = hpa[q] + roff; hd[1 + HB_MAX_DELTA + q] = hpb[q] + roff; }
+  hd[1 + 2 * HB_MAX_DELTA] = hps2 + roff;
+  *reinterpret_cast<double*>(hd + 10) = hgsn;
+}
+
+// issue the bulk copies of the rows chain `c` of the current batch needs into stage buffer `dst`:
+// stage rows 0 = x, 1..D = a, 1+delta.. = b (fixed offsets: no D-dependent address arithmetic in the sweep)
+__device__ __forceinline__ void k1_issue(const hb_k1_params& p, const double* __restrict__ src, const int* heads, int c,
+                                         long long base, double* dst, uint64_t* bar, int lane, uint32_t row_bytes) {
+  const int* hd = heads + c * K1_HEAD_WORDS;
+  const int pk = hd[0];
+  const int Dn = pk & 0xff;
+  const bool sn = (pk >> 17) & 1;
+  const int n_rows = sn ? 4 : 1 + 2 * Dn;
+  if (lane == 0) mbar_expect_tx(bar, (uint32_t)n_rows * row_bytes);
+  __syncwarp();
+  if (lane < n_rows) {
+    const double* g;
+    if (lane == 0) g = p.X + (p.chain0 + (base + c) * p.stride) * (long long)p.ldx;      // own state
+    else {
+      int row;
+      if (sn) row = (lane == 1) ? hd[1] : (lane == 2) ? hd[1 + HB_MAX_DELTA] : hd[1 + 2 * HB_MAX_DELTA];
+      else row = (lane <= Dn) ? hd[lane] : hd[1 + HB_MAX_DELTA + (lane - 1 - Dn)];      // a[0..D-1], b[0..D-1]
+      if (p.n_peers > 1) {                        // the row lives in rank rk's shard: NVLink peer pointer
+        const int rk = (int)(row / p.peer_nl);
+        g = p.peer[rk] + (long long)(row - rk * p.peer_nl) * p.ldx;
+      } else g = src + (long long)row * p.ldx;
+    }
+    const int srow = (sn || lane <= Dn) ? lane : (1 + p.delta + (lane - 1 - Dn));
+    tma_load_1d(dst + (size_t)srow * p.ldx, g, row_bytes, bar);
+  }
+}
+
+__device__ __forceinline__ double2 lds2(const double* q) { return *reinterpret_cast<const double2*>(q); }
+
+template <int ITER2>
+__global__ void __launch_bounds__(256, 2) hb_k1_pair_kernel(const hb_k1_params p) {
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr bool KEEP = ITER2 <= 4;     // keep the Philox words of the subspace pass in registers (else recompute)
+  extern __shared__ __align__(16) unsigned char k1_smem[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int d = p.d, ldx = p.ldx, delta = p.delta;
+  const double* __restrict__ src = p.past_sample ? p.Z : p.X;
+  const int n_src = (int)(p.past_sample ? p.m_arch : p.nc);
+  const int rows_max = k1_rows_max(delta);
+  const uint32_t row_bytes = (uint32_t)ldx * 8u;
+  unsigned char* wbase = k1_smem + (size_t)wib * k1_warp_smem_bytes(delta, ldx);
+  double* stage_buf = reinterpret_cast<double*>(wbase);                                  // [STAGES][rows_max][ldx]
+  int* heads = reinterpret_cast<int*>(wbase + (size_t)K1_STAGES * rows_max * ldx * 8);   // [32][HEAD_WORDS]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(heads + 32 * K1_HEAD_WORDS);              // [STAGES]
+  unsigned errbits = 0;
+  const bool bound_or_prior = (p.bound != 0) || (p.prior == 1);
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < K1_STAGES; ++s) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncwarp();
+  unsigned it = 0;   // chains consumed by this warp so far: stage = it % STAGES, parity = (it / STAGES) & 1
+
+  for (long long base = warp_id * 32; base < p.n_local; base += n_warps * 32) {
+    k1_phase_a<false>(p, base, lane, n_src, heads, errbits);
+    __syncwarp();
+
+    const int n_in_batch = (int)((p.n_local - base) < 32 ? (p.n_local - base) : 32);
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+#pragma unroll
+    for (int s = 0; s < K1_STAGES; ++s)
+      if (s < n_in_batch) {
+        const int sg = (int)((it + s) % K1_STAGES);
+        k1_issue(p, src, heads, s, base, stage_buf + (size_t)sg * rows_max * ldx, &bars[sg], lane, row_bytes);
+      }
+
+    for (int c = 0; c < n_in_batch; ++c, ++it) {
+      const int stg = (int)(it % K1_STAGES);
+      const int* hd = heads + c * K1_HEAD_WORDS;
+      const int pk = hd[0];
+      const int D = pk & 0xff, id = (pk >> 8) & 0xff;
+      const bool g_is_one = (pk >> 16) & 1, snooker = (pk >> 17) & 1;
+      const long long jl = base + c;
+      const long long gch = p.gchain0 + p.chain0 + jl * p.stride;
+      const uint32_t c0 = (uint32_t)gch, c1 = (uint32_t)((uint64_t)gch >> 32);
+      double* rows = stage_buf + (size_t)stg * rows_max * ldx;          // row 0: x; 1..: a; 1+delta..: b
+      const double* __restrict__ rowa = rows + ldx;
+      const double* __restrict__ rowb = rows + (1 + delta) * ldx;
+      double2 xp2[ITER2];
+
+      if (snooker) {
+        // snooker update, R/internals.R:150-163 with orth_proj :250-263 (rare path: psnooker is 0.1 at most)
+        mbar_wait(&bars[stg], (it / K1_STAGES) & 1);
+        const double g_sn = *reinterpret_cast<const double*>(hd + 10);
+        const double* r1 = rows + 1 * ldx;
+        const double* r2 = rows + 2 * ldx;
+        const double* r3 = rows + 3 * ldx;
+        double xk[ITER2][2], uu[ITER2][2], a2[ITER2][2], a3[ITER2][2];
+        double s2 = 0, s3 = 0, su = 0, l2 = 0, l3 = 0, lu = 0;
+        int differs = 0;
+#pragma unroll
+        for (int m = 0; m < ITER2; ++m) {
+          const int k0 = 2 * (m * 32 + lane);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int k = k0 + h;
+            xk[m][h] = 0; uu[m][h] = 0; a2[m][h] = 0; a3[m][h] = 0;
+            if (k < d) {
+              xk[m][h] = rows[k];
+              const double b = r1[k];
+              a2[m][h] = r2[k]; a3[m][h] = r3[k];
+              uu[m][h] = __dadd_rn(xk[m][h], -b);
+              differs |= (xk[m][h] != b);
+              comp_add(s2, l2, __dmul_rn(__dadd_rn(a2[m][h], -xk[m][h]), uu[m][h]));
+              comp_add(s3, l3, __dmul_rn(__dadd_rn(a3[m][h], -xk[m][h]), uu[m][h]));
+              comp_add(su, lu, __dmul_rn(uu[m][h], uu[m][h]));
+            }
+          }
+        }
+        s2 = comp_group_sum<32>(s2, l2, FULL); s3 = comp_group_sum<32>(s3, l3, FULL); su = comp_group_sum<32>(su, lu, FULL);
+        differs = hb_group_sum_int<32>(differs);
+#pragma unroll
+        for (int m = 0; m < ITER2; ++m) {
+          const int k0 = 2 * (m * 32 + lane);
+          uint4 ww = make_uint4(0, 0, 0, 0);
+          if (k0 < d) ww = hb_philox4x32_10_ks(c0, c1, p.gen, HB_SLOT_DIM0 + (uint32_t)(k0 >> 1), p.ks);
+          double o[2] = {0.0, 0.0};
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int k = k0 + h;
+            if (k < d) {
+              const double zeta = __dmul_rn(p.c_star, hb_rng_normal32(h ? ww.w : ww.y));
+              double rp2 = a2[m][h], rp3 = a3[m][h];
+              if (differs) {
+                rp2 = __dadd_rn(xk[m][h], __ddiv_rn(__dmul_rn(uu[m][h], s2), su));
+                rp3 = __dadd_rn(xk[m][h], __ddiv_rn(__dmul_rn(uu[m][h], s3), su));
+              }
+              if (!isfinite(rp2) || !isfinite(rp3)) errbits |= HB_FLAG_PROP_NONFINITE;
+              o[h] = __dadd_rn(xk[m][h], __dadd_rn(zeta, __dmul_rn(g_sn, __dadd_rn(rp2, -rp3))));
+            }
+          }
+          xp2[m] = make_double2(o[0], o[1]);
+        }
+      } else {
+        // parallel direction update, R/internals.R:166-200
+        const uint32_t thr = p.thr16[id];     // zt_k < CR[id]  <=>  (lo & 0xffff) < thr  (hb_rng_zt_threshold16)
+        uint4 wk[KEEP ? ITER2 : 1];
+        unsigned s0[ITER2], s1[ITER2];
+        int d_star = 0;
+#pragma unroll
+        for (int m = 0; m < ITER2; ++m) {
+          const int k0 = 2 * (m * 32 + lane);
+          bool a = false, b = false;
+          uint4 ww = make_uint4(0, 0, 0, 0);
+          if (k0 < d) {
+            ww = hb_philox4x32_10_ks(c0, c1, p.gen, HB_SLOT_DIM0 + (uint32_t)(k0 >> 1), p.ks);
+            a = (ww.x & 0xffffu) < thr;                                   // :175-177
+            b = (k0 + 1 < d) && ((ww.z & 0xffffu) < thr);
+          }
+          if (KEEP) wk[KEEP ? m : 0] = ww;
+          s0[m] = __ballot_sync(FULL, a);
+          s1[m] = __ballot_sync(FULL, b);
+          d_star += __popc(s0[m]) + __popc(s1[m]);
+        }
+        int kmin = -1;
+        if (d_star == 0) {                                               // :181-184  A <- which.min(zt), first minimum
+          unsigned best = 0xffffffffu;
+#pragma unroll
+          for (int m = 0; m < ITER2; ++m) {
+            const int k0 = 2 * (m * 32 + lane);
+            if (k0 < d) {
+              const uint4 ww = KEEP ? wk[KEEP ? m : 0] : hb_philox4x32_10_ks(c0, c1, p.gen, HB_SLOT_DIM0 + (uint32_t)(k0 >> 1), p.ks);
+              best = min(best, ((ww.x & 0xffffu) << 16) | (unsigned)k0);
+              if (k0 + 1 < d) best = min(best, ((ww.z & 0xffffu) << 16) | (unsigned)(k0 + 1));
+            }
+          }
+          best = __reduce_min_sync(FULL, best);
+          kmin = (int)(best & 0xffffu); d_star = 1;
+        }
+        // gamma_d = 2.38/sqrt(2 D d*) (:190) from the host-built table (same IEEE sqrt and division, bit-identical)
+        const double gam = g_is_one ? 1.0 : p.gamma_tab[(D - 1) * d + (d_star - 1)];   // :192
+        mbar_wait(&bars[stg], (it / K1_STAGES) & 1);                     // the rows have landed in shared memory
+#pragma unroll
+        for (int m = 0; m < ITER2; ++m) {
+          const int k0 = 2 * (m * 32 + lane);
+          xp2[m] = make_double2(0.0, 0.0);
+          if (k0 < d) {
+            const uint4 ww = KEEP ? wk[KEEP ? m : 0] : hb_philox4x32_10_ks(c0, c1, p.gen, HB_SLOT_DIM0 + (uint32_t)(k0 >> 1), p.ks);
+            const bool a = (kmin >= 0) ? (k0 == kmin) : ((s0[m] >> lane) & 1u);
+            const bool b = (kmin >= 0) ? (k0 + 1 == kmin) : ((s1[m] >> lane) & 1u);
+            double2 x = lds2(rows + k0);
+            if (a || b) {
+              // jump_diff <- colSums(r1[,A] - r2[,A])  :196.  One or two terms: the plain sum is already the correctly
+              // rounded one; from the third term on, carry the rounding errors (R accumulates in long double).
+              double2 tq[HB_MAX_DELTA];
+#pragma unroll
+              for (int q = 0; q < HB_MAX_DELTA; ++q) {
+                tq[q] = make_double2(0.0, 0.0);
+                if (q < D) {
+                  const double2 ra = lds2(rowa + q * ldx + k0), rb = lds2(rowb + q * ldx + k0);
+                  tq[q] = make_double2(__dadd_rn(ra.x, -rb.x), __dadd_rn(ra.y, -rb.y));
+                }
+              }
+              double jd0, jd1;
+              if (D <= 2) { jd0 = __dadd_rn(tq[0].x, tq[1].x); jd1 = __dadd_rn(tq[0].y, tq[1].y); }
+              else {
+                double sa, ea, ca, sb, eb, cb;
+                two_sum(tq[0].x, tq[1].x, sa, ca);
+                two_sum(tq[0].y, tq[1].y, sb, cb);
+#pragma unroll
+                for (int q = 2; q < HB_MAX_DELTA; ++q)
+                  if (q < D) {
+                    two_sum(sa, tq[q].x, sa, ea); ca = __dadd_rn(ca, ea);
+                    two_sum(sb, tq[q].y, sb, eb); cb = __dadd_rn(cb, eb);
+                  }
+                jd0 = __dadd_rn(sa, ca); jd1 = __dadd_rn(sb, cb);
+              }
+              if (a) {
+                const double lambda = hb_rng_lambda16(ww.x >> 16, p.c_val);                              // :188
+                const double zeta = __dmul_rn(p.c_star, hb_rng_normal32(ww.y));                          // :194
+                const double v = __dadd_rn(zeta, __dmul_rn(__dmul_rn(__dadd_rn(1.0, lambda), gam), jd0));   // :198
+                x.x = __dadd_rn(x.x, __dmul_rn(v, p.beta0));                                             // :200, :206
+              }
+              if (b) {
+                const double lambda = hb_rng_lambda16(ww.z >> 16, p.c_val);
+                const double zeta = __dmul_rn(p.c_star, hb_rng_normal32(ww.w));
+                const double v = __dadd_rn(zeta, __dmul_rn(__dmul_rn(__dadd_rn(1.0, lambda), gam), jd1));
+                x.y = __dadd_rn(x.y, __dmul_rn(v, p.beta0));
+              }
+            }
+            xp2[m] = x;
+          }
+        }
+      }
+      // the stage is free again: fetch the rows of the chain K1_STAGES ahead
+      __syncwarp();
+      if (c + K1_STAGES < n_in_batch) {
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        k1_issue(p, src, heads, c + K1_STAGES, base, rows, &bars[stg], lane, row_bytes);
+      }
+
+      // finite check ; bounds ; prior ; store
+      double lp_part = 0.0;
+      double* __restrict__ xp_row = p.XP + jl * (long long)ldx;
+#pragma unroll
+      for (int m = 0; m < ITER2; ++m) {
+        const int k0 = 2 * (m * 32 + lane);
+        if (k0 < d) {
+          double2 x = xp2[m];
+          const bool has1 = k0 + 1 < d;
+          if (!(fabs(x.x) <= 1.7976931348623157e308) || !(fabs(x.y) <= 1.7976931348623157e308)) errbits |= HB_FLAG_PROP_NONFINITE;   // :209
+          if (bound_or_prior) {
+            if (p.bound) {                                                       // :210-214
+              x.x = hb_bound_par(x.x, p.pmin[k0], p.pmax[k0], p.bound);
+              if (has1) x.y = hb_bound_par(x.y, p.pmin[k0 + 1], p.pmax[k0 + 1], p.bound);
+            }
+            if (p.prior == 1) {                                                  // dunif(log = TRUE), :57
+              { const double a = p.pmin[k0], b = p.pmax[k0]; lp_part += (a <= x.x && x.x <= b) ? -log(b - a) : -INFINITY; }
+              if (has1) { const double a = p.pmin[k0 + 1], b = p.pmax[k0 + 1]; lp_part += (a <= x.y && x.y <= b) ? -log(b - a) : -INFINITY; }
+            }
+          }
+          *reinterpret_cast<double2*>(xp_row + k0) = x;
+        }
+      }
+      if (p.prior == 1) lp_part = hb_group_sum<32>(lp_part);
+      if (lane == 0) {
+        double lp = (p.prior == 1) ? lp_part : 0.0;                      // flat prior: 0  :55
+        if (!(lp >= HB_FLOOR)) lp = (lp != lp) ? lp : HB_FLOOR;          // :65
+        if (!isfinite(lp)) errbits |= HB_FLAG_LP_NONFINITE;              // :67
+        p.lp_xp[jl] = lp;
+        p.id_out[jl] = id;
+      }
+    }
+    __syncwarp();
+  }
+  if (errbits) atomicOr(p.err, errbits);
+}
+
+// replay mode: the draws come from the decision tape; lane owns dimensions k = 32 m + lane
+template <int ITER>
+__global__ void __launch_bounds__(256, 2) hb_k1_tape_kernel(const hb_k1_params p) {
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(16) unsigned char k1_smem[];
   const int lane = threadIdx.x & 31;
@@ -349,129 +720,20 @@ __global__ void __launch_bounds__(256, 2) hb_k1_wide_kernel(const hb_k1_params p
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncwarp();
-  unsigned it = 0;   // chains consumed by this warp so far: stage = it % STAGES, parity = (it / STAGES) & 1
-
-  // issue the bulk copies of the rows chain `c` of the current batch needs into stage `s`
-  auto issue = [&](int c, long long base, int s) {
-    const int* hd = heads + c * K1_HEAD_WORDS;
-    const int pk = hd[0];
-    const int Dn = pk & 0xff;
-    const bool sn = (pk >> 17) & 1;
-    const int n_rows = sn ? 4 : 1 + 2 * Dn;
-    if (lane == 0) mbar_expect_tx(&bars[s], (uint32_t)n_rows * row_bytes);
-    __syncwarp();
-    if (lane < n_rows) {
-      const double* g;
-      const long long gl_c = p.chain0 + (base + c) * p.stride;
-      const long long rbase_c = p.n_runs > 1 ? (gl_c / p.nc) * p.nc : 0;
-      if (lane == 0) g = p.X + gl_c * (long long)ldx;                                   // own state
-      else {
-        int row;
-        if (sn) row = (lane == 1) ? hd[1] : (lane == 2) ? hd[1 + HB_MAX_DELTA] : hd[1 + 2 * HB_MAX_DELTA];
-        else row = (lane <= Dn) ? hd[lane] : hd[1 + HB_MAX_DELTA + (lane - 1 - Dn)];    // a[0..D-1], b[0..D-1]
-        if (p.n_peers > 1) {                      // the row lives in rank rk's shard: NVLink peer pointer
-          const int rk = (int)(row / p.peer_nl);
-          g = p.peer[rk] + (long long)(row - rk * p.peer_nl) * ldx;
-        } else g = src + ((p.past_sample ? 0 : rbase_c) + (long long)row) * ldx;
-      }
-      // stage rows: 0 = x, 1..D = a, 1+delta.. = b (fixed offsets: no D-dependent address arithmetic in the sweep)
-      const int srow = (sn || lane <= Dn) ? lane : (1 + delta + (lane - 1 - Dn));
-      tma_load_1d(stage_buf + ((size_t)s * rows_max + srow) * ldx, g, row_bytes, &bars[s]);
-    }
-  };
+  unsigned it = 0;
 
   for (long long base = warp_id * 32; base < p.n_local; base += n_warps * 32) {
-    // ---------------- phase A: one lane per chain ----------------
-    {
-      int hD = 1, hid = 0;
-      int hpa[HB_MAX_DELTA], hpb[HB_MAX_DELTA], hps2 = 0;
-      double hgsn = 0.0;
-#pragma unroll
-      for (int q = 0; q < HB_MAX_DELTA; ++q) { hpa[q] = 0; hpb[q] = 0; }
-      const long long jl_raw = base + lane;
-      const long long jl = jl_raw < p.n_local ? jl_raw : p.n_local - 1;
-      const long long gl = p.chain0 + jl * p.stride;
-      const long long run = p.n_runs > 1 ? gl / p.nc : 0;
-      const long long j = gl - run * p.nc;
-      const long long gch = p.gchain0 + gl;
-      double u_sn;
-      int g1;
-      if (TAPE) {
-        const long long rix = p.tape_g * p.tape.nct + gl;
-        u_sn = p.tape.u_snooker ? p.tape.u_snooker[rix] : 1.0;          // R/internals.R:119
-        hD = p.tape.D[rix];                                             // :123
-        hid = p.tape.id[rix];                                           // :173
-        g1 = p.tape.g_is_one[rix];                                      // :192
-        if (p.tape.g_snooker) hgsn = p.tape.g_snooker[rix];             // :156
-        if (hD < 1 || hD > delta || hid >= nCR) { errbits |= HB_FLAG_BAD_TAPE; hD = 1; hid = 0; }
-        const int32_t* pr = p.tape.partners + rix * (2 * delta);
-#pragma unroll
-        for (int q = 0; q < HB_MAX_DELTA; ++q)
-          if (q < hD) { hpa[q] = pr[q]; hpb[q] = pr[hD + q]; }
-        if (p.past_sample && u_sn < p.psnooker) { hpa[0] = pr[0]; hpb[0] = pr[1]; hps2 = pr[2]; }
-      } else {
-        const hb_phx ph(p.seed, (uint64_t)gch, p.gen);
-        const uint4 w0 = ph.slot(HB_SLOT_HEAD);
-        const uint4 wc = ph.slot(HB_SLOT_CHOICE);
-        u_sn = hb_u53(hb_pair64(w0, 0));
-        hD = 1 + (int)hb_mulhi64(hb_pair64(w0, 1), (uint64_t)delta);
-        const double u_id = hb_u53(hb_pair64(wc, 0));
-        double cum = 0.0;
-        hid = nCR - 1;
-        bool found = false;
-        for (int q = 0; q < nCR; ++q) {
-          cum += p.ctrl[run].pCR[q];
-          if (!found && u_id < cum) { hid = q; found = true; }
-        }
-        g1 = hb_u53(hb_pair64(wc, 1)) >= 1.0 - p.p_g;
-        const bool sn = p.past_sample && (u_sn < p.psnooker);
-        if (sn) hgsn = 1.2 + hb_u53(hb_pair64(ph.slot(HB_SLOT_ACCEPT), 1));
-        const int n_part = sn ? 3 : 2 * hD;
-        hb_fy fy;
-        long long n_rem = p.past_sample ? p.m_arch : p.nc - 1;
-        int y[2 * HB_MAX_DELTA];
-        uint4 wp = make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int q = 0; q < 2 * HB_MAX_DELTA; ++q) {
-          y[q] = 0;
-          if (q < n_part) {
-            if ((q & 1) == 0) wp = ph.slot(HB_SLOT_PARTNER0 + (q >> 1));
-            long long v = fy.draw(hb_pair64(wp, q & 1), n_rem);
-            if (!p.past_sample && v >= j) v += 1;                       // sample((1:nc)[-j], ...)  :142
-            y[q] = (int)v;
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < HB_MAX_DELTA; ++q) {
-          hpa[q] = y[q];
-          hpb[q] = (hD == 1) ? y[(1 + q) & 7] : (hD == 2) ? y[(2 + q) & 7] : (hD == 3) ? y[(3 + q) & 7] : y[(4 + q) & 7];
-        }
-        if (sn) { hpb[0] = y[1]; hps2 = y[2]; }
-      }
-      const bool sn = p.past_sample && (u_sn < p.psnooker);
-#pragma unroll
-      for (int q = 0; q < HB_MAX_DELTA; ++q) {
-        const bool used = sn ? (q == 0) : (q < hD);
-        if (used && (hpa[q] < 0 || hpa[q] >= n_src || hpb[q] < 0 || hpb[q] >= n_src)) {
-          errbits |= HB_FLAG_BAD_TAPE; hpa[q] = 0; hpb[q] = 0;
-        }
-      }
-      if (sn && (hps2 < 0 || hps2 >= n_src)) { errbits |= HB_FLAG_BAD_TAPE; hps2 = 0; }
-      int* hd = heads + lane * K1_HEAD_WORDS;
-      hd[0] = hD | (hid << 8) | ((g1 ? 1 : 0) << 16) | ((sn ? 1 : 0) << 17);
-#pragma unroll
-      for (int q = 0; q < HB_MAX_DELTA; ++q) { hd[1 + q] = hpa[q]; hd[1 + HB_MAX_DELTA + q] = hpb[q]; }
-      hd[1 + 2 * HB_MAX_DELTA] = hps2;
-      *reinterpret_cast<double*>(hd + 10) = hgsn;
-    }
+    k1_phase_a<true>(p, base, lane, n_src, heads, errbits);
     __syncwarp();
 
-    // ---------------- phase B: the warp sweeps the rows of the batch, one chain at a time ----------------
     const int n_in_batch = (int)((p.n_local - base) < 32 ? (p.n_local - base) : 32);
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
 #pragma unroll
     for (int s = 0; s < K1_STAGES; ++s)
-      if (s < n_in_batch) issue(s, base, (int)((it + s) % K1_STAGES));
+      if (s < n_in_batch) {
+        const int sg = (int)((it + s) % K1_STAGES);
+        k1_issue(p, src, heads, s, base, stage_buf + (size_t)sg * rows_max * ldx, &bars[sg], lane, row_bytes);
+      }
 
     for (int c = 0; c < n_in_batch; ++c, ++it) {
       const int stg = (int)(it % K1_STAGES);
@@ -481,16 +743,14 @@ __global__ void __launch_bounds__(256, 2) hb_k1_wide_kernel(const hb_k1_params p
       const bool g_is_one = (pk >> 16) & 1, snooker = (pk >> 17) & 1;
       const long long jl = base + c;
       const long long gl = p.chain0 + jl * p.stride;
-      const long long gch = p.gchain0 + gl;
       const long long rix = p.tape_g * p.tape.nct + gl;
-      const hb_phx ph(p.seed, (uint64_t)gch, p.gen);
-      const double* __restrict__ rows = stage_buf + (size_t)stg * rows_max * ldx;   // row 0: x; 1..: a; 1+delta..: b
+      double* rows = stage_buf + (size_t)stg * rows_max * ldx;          // row 0: x; 1..: a; 1+delta..: b
       const double* __restrict__ rowa = rows + ldx;
       const double* __restrict__ rowb = rows + (1 + delta) * ldx;
       double xk[ITER], dxk[ITER];
 
       if (snooker) {
-        // snooker update, R/internals.R:150-163 with orth_proj :250-263 (rare path: psnooker is 0.1 at most)
+        // snooker update, R/internals.R:150-163 with orth_proj :250-263
         mbar_wait(&bars[stg], (it / K1_STAGES) & 1);
         const double g_sn = *reinterpret_cast<const double*>(hd + 10);
         const double* r1 = rows + 1 * ldx;
@@ -521,9 +781,7 @@ __global__ void __launch_bounds__(256, 2) hb_k1_wide_kernel(const hb_k1_params p
           const int k = m * 32 + lane;
           dxk[m] = 0;
           if (k < d) {
-            double zeta;
-            if (TAPE) zeta = p.tape.zeta[rix * d + k];
-            else { const uint4 w = ph.slot(HB_SLOT_DIM0 + (uint32_t)k); zeta = hb_zeta(w.z, w.w, p.c_star); }
+            const double zeta = p.tape.zeta[rix * d + k];
             double rp2 = a2[m], rp3 = a3[m];
             if (differs) {
               rp2 = __dadd_rn(xk[m], __ddiv_rn(__dmul_rn(uu[m], s2), su));
@@ -536,54 +794,32 @@ __global__ void __launch_bounds__(256, 2) hb_k1_wide_kernel(const hb_k1_params p
       } else {
         // parallel direction update, R/internals.R:166-200
         const double CRv = (double)(id + 1) / (double)nCR;               // CR <- (1:nCR)/nCR
-        // (w + 0.5) 2^-32 < CR  <=>  w < ceil(CR 2^32 - 0.5): exact integer form of the zt < CR[id] test
-        const unsigned long long thr = p.thr[id];
-        double ztv[TAPE ? ITER : 1];
-        uint32_t wx[ITER], wl[ITER], wz2[ITER], wz3[ITER];
+        double ztv[ITER];
         unsigned selmask[ITER];
         int d_star = 0;
 #pragma unroll
         for (int m = 0; m < ITER; ++m) {
           const int k = m * 32 + lane;
           bool sel = false;
-          wx[m] = 0xffffffffu; wl[m] = 0; wz2[m] = 0; wz3[m] = 0;
-          if (TAPE) {
-            ztv[TAPE ? m : 0] = 2.0;
-            if (k < d) { ztv[TAPE ? m : 0] = p.tape.zt[rix * d + k]; sel = ztv[TAPE ? m : 0] < CRv; }   // :175-177
-          } else if (k < d) {
-            const uint4 w = hb_philox4x32_10_ks((uint32_t)gch, (uint32_t)((uint64_t)gch >> 32), p.gen, HB_SLOT_DIM0 + (uint32_t)k, p.ks);
-            wx[m] = w.x; wl[m] = w.y; wz2[m] = w.z; wz3[m] = w.w;
-            sel = (unsigned long long)w.x < thr;
-          }
+          ztv[m] = 2.0;
+          if (k < d) { ztv[m] = p.tape.zt[rix * d + k]; sel = ztv[m] < CRv; }   // :175-177
           selmask[m] = __ballot_sync(FULL, sel);
           d_star += __popc(selmask[m]);
         }
         int kmin = -1;
         if (d_star == 0) {                                               // :181-184  A <- which.min(zt)
           int bk = 0x7fffffff;
-          if (TAPE) {
-            double bv = 3.0;
+          double bv = 3.0;
 #pragma unroll
-            for (int m = 0; m < ITER; ++m) { const int k = m * 32 + lane; if (k < d && ztv[TAPE ? m : 0] < bv) { bv = ztv[TAPE ? m : 0]; bk = k; } }
+          for (int m = 0; m < ITER; ++m) { const int k = m * 32 + lane; if (k < d && ztv[m] < bv) { bv = ztv[m]; bk = k; } }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              const double ov = __shfl_xor_sync(FULL, bv, o); const int ok = __shfl_xor_sync(FULL, bk, o);
-              if (ov < bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
-            }
-          } else {
-            unsigned long long bv = ~0ull;
-#pragma unroll
-            for (int m = 0; m < ITER; ++m) { const int k = m * 32 + lane; if (k < d && (unsigned long long)wx[m] < bv) { bv = wx[m]; bk = k; } }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              const unsigned long long ov = __shfl_xor_sync(FULL, bv, o); const int ok = __shfl_xor_sync(FULL, bk, o);
-              if (ov < bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
-            }
+          for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(FULL, bv, o); const int ok = __shfl_xor_sync(FULL, bk, o);
+            if (ov < bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
           }
           kmin = bk; d_star = 1;
         }
-        // gamma_d = 2.38/sqrt(2 D d*) (:190) from the host-built table (same IEEE sqrt and division, bit-identical)
-        const double gam = g_is_one ? 1.0 : p.gamma_tab[(D - 1) * d + (d_star - 1)];   // :192
+        const double gam = g_is_one ? 1.0 : p.gamma_tab[(D - 1) * d + (d_star - 1)];   // :190-192
         mbar_wait(&bars[stg], (it / K1_STAGES) & 1);                     // the rows have landed in shared memory
         int rank_base = 0;
 #pragma unroll
@@ -594,24 +830,16 @@ __global__ void __launch_bounds__(256, 2) hb_k1_wide_kernel(const hb_k1_params p
           if (k < d) {
             xk[m] = rows[k];
             if (sel) {
-              double lambda, zeta;
-              if (TAPE) {
-                const int rank = (kmin >= 0) ? 0 : rank_base + __popc(selmask[m] & ((1u << lane) - 1u));
-                lambda = p.tape.lambda[rix * d + rank];                  // :188 (by rank within A)
-                zeta = p.tape.zeta[rix * d + rank];                      // :194
-              } else {
-                lambda = hb_rng_lambda(wl[m], p.c_val);
-                zeta = hb_zeta(wz2[m], wz3[m], p.c_star);
-              }
-              // jump_diff <- colSums(r1[,A] - r2[,A])  :196.  One or two terms: the plain sum is already the correctly
-              // rounded one; from the third term on, carry the rounding errors (R accumulates in long double).
+              const int rank = (kmin >= 0) ? 0 : rank_base + __popc(selmask[m] & ((1u << lane) - 1u));
+              const double lambda = p.tape.lambda[rix * d + rank];       // :188 (by rank within A)
+              const double zeta = p.tape.zeta[rix * d + rank];           // :194
               double tq[HB_MAX_DELTA];
 #pragma unroll
               for (int q = 0; q < HB_MAX_DELTA; ++q) {
                 tq[q] = 0.0;
                 if (q < D) tq[q] = __dadd_rn(rowa[q * ldx + k], -rowb[q * ldx + k]);
               }
-              double jd;
+              double jd;                                                 // colSums(r1[,A] - r2[,A])  :196
               if (D <= 2) jd = __dadd_rn(tq[0], tq[1]);
               else {
                 double s, e, comp;
@@ -627,14 +855,12 @@ __global__ void __launch_bounds__(256, 2) hb_k1_wide_kernel(const hb_k1_params p
           rank_base += __popc(selmask[m]);
         }
       }
-      // the stage is free again: fetch the rows of the chain K1_STAGES ahead
       __syncwarp();
       if (c + K1_STAGES < n_in_batch) {
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-        issue(c + K1_STAGES, base, stg);
+        k1_issue(p, src, heads, c + K1_STAGES, base, rows, &bars[stg], lane, row_bytes);
       }
 
-      // xp <- x + dx ; finite check ; bounds ; prior
       double lp_part = 0.0;
       double* __restrict__ xp_row = p.XP + jl * (long long)ldx;
 #pragma unroll
@@ -667,29 +893,39 @@ __global__ void __launch_bounds__(256, 2) hb_k1_wide_kernel(const hb_k1_params p
   if (errbits) atomicOr(p.err, errbits);
 }
 
-template <int ITER>
-cudaError_t launch_wide(const hb_k1_params& p, bool tape, int sm_count, cudaStream_t st) {
+inline void k1_wide_geometry(const hb_k1_params& p, int sm_count, int* threads, long long* blocks, size_t* smem) {
   const size_t per_warp = (k1_warp_smem_bytes(p.delta, p.ldx) + 15) & ~(size_t)15;
   int warps = 8;
   while (warps > 1 && per_warp * warps > 110 * 1024) warps >>= 1;     // two CTAs per SM
-  const size_t smem = per_warp * warps;
-  if (smem > 220 * 1024) return cudaErrorInvalidValue;
-  const int threads = warps * 32;
+  *smem = per_warp * warps;
+  *threads = warps * 32;
   const long long warps_needed = (p.n_local + 31) / 32;
-  long long blocks = (warps_needed + warps - 1) / warps;
+  long long b = (warps_needed + warps - 1) / warps;
   const long long cap = (long long)sm_count * 2;                       // persistent: two CTAs per SM, grid-stride batches
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  cudaError_t e;
-  if (tape) {
-    e = cudaFuncSetAttribute(hb_k1_wide_kernel<ITER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    hb_k1_wide_kernel<ITER, true><<<(unsigned)blocks, threads, smem, st>>>(p);
-  } else {
-    e = cudaFuncSetAttribute(hb_k1_wide_kernel<ITER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    hb_k1_wide_kernel<ITER, false><<<(unsigned)blocks, threads, smem, st>>>(p);
-  }
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  *blocks = b;
+}
+
+template <int ITER>
+cudaError_t launch_wide_tape(const hb_k1_params& p, int sm_count, cudaStream_t st) {
+  int threads; long long blocks; size_t smem;
+  k1_wide_geometry(p, sm_count, &threads, &blocks, &smem);
+  if (smem > 220 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(hb_k1_tape_kernel<ITER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  hb_k1_tape_kernel<ITER><<<(unsigned)blocks, threads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <int ITER2>
+cudaError_t launch_wide_pair(const hb_k1_params& p, int sm_count, cudaStream_t st) {
+  int threads; long long blocks; size_t smem;
+  k1_wide_geometry(p, sm_count, &threads, &blocks, &smem);
+  if (smem > 220 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(hb_k1_pair_kernel<ITER2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  hb_k1_pair_kernel<ITER2><<<(unsigned)blocks, threads, smem, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -727,11 +963,20 @@ cudaError_t hb_launch_k1(const hb_k1_params& p, bool tape_mode, int sm_count, cu
     if (d <= 512) return launch_gi<32, 16>(p, tape_mode, sm_count, st);
     return launch_gi<32, 32>(p, tape_mode, sm_count, st);
   }
-  if (d <= 32) return launch_wide<1>(p, tape_mode, sm_count, st);
-  if (d <= 64) return launch_wide<2>(p, tape_mode, sm_count, st);
-  if (d <= 128) return launch_wide<4>(p, tape_mode, sm_count, st);
-  if (d <= 256) return launch_wide<8>(p, tape_mode, sm_count, st);
-  if (d <= 512) return launch_wide<16>(p, tape_mode, sm_count, st);
-  if (d <= 1024) return launch_wide<32>(p, tape_mode, sm_count, st);
+  if (tape_mode) {
+    if (d <= 32) return launch_wide_tape<1>(p, sm_count, st);
+    if (d <= 64) return launch_wide_tape<2>(p, sm_count, st);
+    if (d <= 128) return launch_wide_tape<4>(p, sm_count, st);
+    if (d <= 256) return launch_wide_tape<8>(p, sm_count, st);
+    if (d <= 512) return launch_wide_tape<16>(p, sm_count, st);
+    if (d <= 1024) return launch_wide_tape<32>(p, sm_count, st);
+    return cudaErrorInvalidValue;
+  }
+  if (d <= 64) return launch_wide_pair<1>(p, sm_count, st);      // ITER2 = ceil(ceil(d/2)/32) pairs per lane
+  if (d <= 128) return launch_wide_pair<2>(p, sm_count, st);
+  if (d <= 192) return launch_wide_pair<3>(p, sm_count, st);
+  if (d <= 256) return launch_wide_pair<4>(p, sm_count, st);
+  if (d <= 512) return launch_wide_pair<8>(p, sm_count, st);
+  if (d <= 1024) return launch_wide_pair<16>(p, sm_count, st);
   return cudaErrorInvalidValue;
 }

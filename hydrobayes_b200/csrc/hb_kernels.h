@@ -51,7 +51,7 @@ struct hb_k1_params {
   const double* peer[8];  // HB_EXCHANGE_PEER: rank r's shard (current buffer), chains [r*peer_nl, (r+1)*peer_nl)
   int n_peers; long long peer_nl;
   uint32_t ks[20];        // Philox round keys of `seed` (constant bank operands in the kernel)
-  unsigned long long thr[HB_MAX_NCR];   // ceil(CR_q 2^32 - 0.5): exact integer form of zt < CR[id]
+  uint32_t thr16[HB_MAX_NCR];   // hb_rng_zt_threshold16(CR_q) = ceil(CR_q 2^16 - 0.5): exact integer form of zt < CR[id]
 };
 cudaError_t hb_launch_k1(const hb_k1_params& p, bool tape_mode, int sm_count, cudaStream_t st);
 

@@ -8,10 +8,19 @@
  * draws.  That matters: for d = 1 the DREAM population map has a large Lyapunov exponent (gamma = 1.68), a 1e-18
  * difference in one jitter value grows to 1e-9 within ~40 generations.
  *
- *   hb_rng_u53(x)       64 random bits  -> double in the open interval (0, 1), 53 bits
- *   hb_rng_u32(w)       32 random bits  -> double in (0, 1), exact
- *   hb_rng_lambda(w,c)  U(-c, c)                                        (R/internals.R:188)
- *   hb_rng_normal(a,b)  approximately N(0, 1), integer-only, from two 32-bit words  (zeta, R/internals.R:194,158)
+ *   hb_rng_u53(x)        64 random bits  -> double in the open interval (0, 1), 53 bits
+ *   hb_rng_u32(w)        32 random bits  -> double in (0, 1), exact
+ *   hb_rng_u16(h)        16 random bits  -> double in (0, 1), exact: (h + 0.5) 2^-16
+ *   hb_rng_lambda16(h,c) U(-c, c) on 65536 symmetric levels               (R/internals.R:188)
+ *   hb_rng_normal32(w)   approximately N(0, 1), integer-only, from one 32-bit word  (zeta, R/internals.R:194,158)
+ *
+ * Per-dimension draws (slot map v2): one Philox4x32 call serves TWO dimensions.  For dimension k the call is
+ * slot HB_RNG_SLOT_DIM0 + (k >> 1); dimension k uses words (0,1) when k is even and words (2,3) when k is odd:
+ *   lo word: bits 0-15  -> zt_k      = hb_rng_u16(lo & 0xffff)            (crossover test, R/internals.R:175-177)
+ *            bits 16-31 -> lambda_k  = hb_rng_lambda16(lo >> 16, c_val)   (:188)
+ *   hi word:            -> zeta_k    = c_star * hb_rng_normal32(hi)       (:194; snooker :158)
+ * 64 random bits per dimension: the proposal kernel is instruction-bound on Philox, so the draws are sized to what
+ * the sampler can observe (a crossover probability exact to 2^-16, a jitter on 65536 levels).
  */
 #ifndef HYDROBAYES_B200_RNG_H
 #define HYDROBAYES_B200_RNG_H
@@ -49,6 +58,18 @@ HB_RNG_FN double hb_rng_lambda(uint32_t w, double c_val) {
   return HB_DADD(-c_val, HB_DMUL(HB_DMUL(2.0, c_val), hb_rng_u32(w)));
 }
 
+HB_RNG_FN double hb_rng_u16(uint32_t h) { return HB_DMUL(HB_DADD((double)(h & 0xffffu), 0.5), 0x1.0p-16); }
+HB_RNG_FN double hb_rng_lambda16(uint32_t h, double c_val) {
+  return HB_DADD(-c_val, HB_DMUL(HB_DMUL(2.0, c_val), hb_rng_u16(h)));
+}
+/* zt_k < CR  <=>  (h + 0.5) 2^-16 < CR  <=>  h < ceil(CR 2^16 - 0.5): the exact integer form of the crossover test */
+HB_RNG_FN uint32_t hb_rng_zt_threshold16(double cr) {
+  const double t = HB_DADD(HB_DMUL(cr, 65536.0), -0.5);
+  uint32_t n = (uint32_t)t;                 /* truncation; t >= 0 for cr >= 2^-17 */
+  if ((double)n < t) n += 1u;               /* ceil */
+  return n;
+}
+
 /*
  * zeta's standard deviate: a bit-exact, integer-only approximation of N(0, 1) from 64 random bits.
  *   B = popcount(48 bits) ~ Binomial(48, 1/2)  (mean 24, variance 12: a lattice normal by the CLT)
@@ -73,5 +94,20 @@ HB_RNG_FN double hb_rng_normal(uint32_t wa, uint32_t wb) {
   const int v = (b - 24) * 256 + t;
   return HB_DMUL((double)v, 0.00111988718555951);   /* 1 / (256 * sqrt(12 + 65535/393216)) */
 }
+
+/*
+ * 32-bit variant used by the per-dimension draws (slot map v2):
+ *   B = popcount(24 bits) ~ Binomial(24, 1/2)   (mean 12, variance 6)
+ *   T = n4 + n4' - 15                            (triangular kernel, in units of 1/16 lattice step)
+ *   z = ((B - 12) * 16 + T) / sqrt(6 * 256 + 2 * (16^2 - 1) / 12) = v / sqrt(1578.5)
+ * mean 0, variance 1, |z| <= 5.21, excess kurtosis -0.079, Kolmogorov distance to N(0,1) 1.9e-3.
+ */
+HB_RNG_FN double hb_rng_normal32(uint32_t w) {
+  const int b = hb_rng_popc32(w & 0xffffffu);
+  const int t = (int)((w >> 24) & 0xfu) + (int)(w >> 28) - 15;
+  const int v = (b - 12) * 16 + t;
+  return HB_DMUL((double)v, 0x1.9c614ae8b41e8p-6);   /* 1 / sqrt(1578.5) */
+}
+#define HB_RNG_SLOT_DIM0 8u
 
 #endif /* HYDROBAYES_B200_RNG_H */

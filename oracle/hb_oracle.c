@@ -75,7 +75,7 @@ static inline double u53(uint64_t x) { return hb_rng_u53(x); }
 static inline double u32d(uint32_t x) { return hb_rng_u32(x); }
 static inline uint64_t mulhi64(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
 
-/* Philox slot map (must match hydrobayes_b200/csrc/hb_rng.cuh) */
+/* Philox slot map (must match hydrobayes_b200/csrc/hb_common.cuh and include/hydrobayes_b200_rng.h, slot map v2) */
 enum { SLOT_HEAD = 0, SLOT_PARTNER0 = 1, SLOT_CHOICE = 5, SLOT_ACCEPT = 6, SLOT_DIM0 = 8 };
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -538,9 +538,10 @@ static int calc_prop(const ctx_t* c, int64_t i_gen, int64_t j, const double* x, 
       double zeta;
       if (tape_mode) zeta = tp->zeta[rix * d + k];
       else {
-        phx_slot(&ph, SLOT_DIM0 + (uint32_t)k, w);
-        zeta = cfg->c_star * hb_rng_normal(w[2], w[3]);
-        if (rec) { ((double*)rec->zt)[rix * d + k] = u32d(w[0]); ((double*)rec->lambda)[rix * d + k] = 0; }
+        if ((k & 1) == 0) phx_slot(&ph, SLOT_DIM0 + (uint32_t)(k >> 1), w);   /* one call per two dimensions */
+        const uint32_t lo = w[2 * (k & 1)], hi = w[2 * (k & 1) + 1];
+        zeta = cfg->c_star * hb_rng_normal32(hi);
+        if (rec) { ((double*)rec->zt)[rix * d + k] = hb_rng_u16(lo); ((double*)rec->lambda)[rix * d + k] = 0; }
       }
       if (rec) ((double*)rec->zeta)[rix * d + k] = zeta;
       double rp2, rp3;
@@ -561,10 +562,11 @@ static int calc_prop(const ctx_t* c, int64_t i_gen, int64_t j, const double* x, 
     for (int k = 0; k < d; ++k) {
       if (tape_mode) zt[k] = tp->zt[rix * d + k];
       else {
-        phx_slot(&ph, SLOT_DIM0 + (uint32_t)k, w);
-        zt[k] = u32d(w[0]);
-        lam_k[k] = hb_rng_lambda(w[1], cfg->c_val);
-        zeta_k[k] = cfg->c_star * hb_rng_normal(w[2], w[3]);
+        if ((k & 1) == 0) phx_slot(&ph, SLOT_DIM0 + (uint32_t)(k >> 1), w);   /* one call per two dimensions */
+        const uint32_t lo = w[2 * (k & 1)], hi = w[2 * (k & 1) + 1];
+        zt[k] = hb_rng_u16(lo);
+        lam_k[k] = hb_rng_lambda16(lo >> 16, cfg->c_val);
+        zeta_k[k] = cfg->c_star * hb_rng_normal32(hi);
       }
       if (rec) ((double*)rec->zt)[rix * d + k] = zt[k];
     }
@@ -1014,3 +1016,9 @@ done:
   return rc;
 }
 
+
+/* native-RNG transforms of include/hydrobayes_b200_rng.h (slot map v2), exported for the known-answer tests */
+double hbo_rng_u16(uint32_t h) { return hb_rng_u16(h); }
+double hbo_rng_lambda16(uint32_t h, double c_val) { return hb_rng_lambda16(h, c_val); }
+double hbo_rng_normal32(uint32_t w) { return hb_rng_normal32(w); }
+uint32_t hbo_rng_zt_threshold16(double cr) { return hb_rng_zt_threshold16(cr); }

@@ -63,6 +63,10 @@ typedef struct hbo_io {
 /* constants and scalar helpers */
 double hbo_log_xmin(void);                                  /* log(.Machine$double.xmin)  R/internals.R:19,65 */
 void hbo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+double hbo_rng_u16(uint32_t h);                             /* include/hydrobayes_b200_rng.h, slot map v2 */
+double hbo_rng_lambda16(uint32_t h, double c_val);
+double hbo_rng_normal32(uint32_t w);
+uint32_t hbo_rng_zt_threshold16(double cr);
 double hbo_dnorm(double x, double mu, double sigma);        /* R nmath dnorm4 (recollection) */
 double hbo_mixture(double x);                               /* R/test_mixture.R:16 */
 int hbo_tdist_logpdf(const double* x_colmajor, int64_t n, int32_t d, double* out); /* R/test_t_distribution.R:19-46 */

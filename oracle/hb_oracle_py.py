@@ -66,6 +66,10 @@ def lib() -> C.CDLL:
                               C.POINTER(HbTape), C.POINTER(HboIo)]
         L.hbo_philox4x32_10.argtypes = [C.POINTER(C.c_uint32)] * 3
         L.hbo_set_threads.argtypes = [C.c_int]
+        L.hbo_rng_u16.restype = C.c_double; L.hbo_rng_u16.argtypes = [C.c_uint32]
+        L.hbo_rng_lambda16.restype = C.c_double; L.hbo_rng_lambda16.argtypes = [C.c_uint32, C.c_double]
+        L.hbo_rng_normal32.restype = C.c_double; L.hbo_rng_normal32.argtypes = [C.c_uint32]
+        L.hbo_rng_zt_threshold16.restype = C.c_uint32; L.hbo_rng_zt_threshold16.argtypes = [C.c_double]
         L.hbo_last_loop_seconds.restype = C.c_double
         _LIB = L
     return _LIB

@@ -133,3 +133,33 @@ def test_glue_likelihood(oracle):
         exp = max(50 * math.log(max(nse, 0)) if nse > 0 else -math.inf, oracle.log_xmin())
         ll, fx, rc = oracle.logdensity("HydroModel", 31, [[K]], forcing=P, obs=obs, glue_shape=50.0)
         assert rc == 0 and ll[0] == pytest.approx(exp, rel=1e-12)
+
+
+def test_native_rng_transforms(oracle):
+    """slot map v2 (include/hydrobayes_b200_rng.h): 64 random bits per dimension.  Independent numpy restatement of the
+    three transforms + the properties the sampler relies on (open interval, symmetry, exact integer crossover test)."""
+    L = oracle.lib()
+    hs = [0, 1, 21845, 21846, 32767, 32768, 43690, 43691, 65535]
+    for h in hs:
+        assert L.hbo_rng_u16(h) == (h + 0.5) / 65536.0
+        assert L.hbo_rng_lambda16(h, 0.1) == -0.1 + (2.0 * 0.1) * ((h + 0.5) / 65536.0)
+        assert L.hbo_rng_lambda16(h, 0.1) == pytest.approx(-L.hbo_rng_lambda16(65535 - h, 0.1), abs=1e-16)   # symmetric about 0
+    assert 0.0 < L.hbo_rng_u16(0) and L.hbo_rng_u16(65535) < 1.0
+    # zt < CR  <=>  h < threshold, for every h and every CR of nCR = 1..6
+    h = np.arange(65536)
+    zt = (h + 0.5) / 65536.0
+    for nCR in range(1, 7):
+        for q in range(nCR):
+            cr = (q + 1) / nCR
+            thr = L.hbo_rng_zt_threshold16(cr)
+            assert np.array_equal(zt < cr, h < thr), (nCR, q)
+    # the integer-CLT deviate: restated bit by bit, then its first four moments over a fixed word set
+    rs = np.random.RandomState(7)
+    w = rs.randint(0, 2**32, size=200000, dtype=np.uint64).astype(np.uint32)
+    z = np.array([L.hbo_rng_normal32(int(x)) for x in w[:5000]])
+    b = np.array([bin(int(x) & 0xffffff).count("1") for x in w[:5000]])
+    t = ((w[:5000] >> 24) & 0xf).astype(int) + (w[:5000] >> 28).astype(int) - 15
+    np.testing.assert_array_equal(z, ((b - 12) * 16 + t) * float.fromhex("0x1.9c614ae8b41e8p-6"))
+    assert L.hbo_rng_normal32(0x00000000) == (-12 * 16 - 15) * float.fromhex("0x1.9c614ae8b41e8p-6")
+    assert L.hbo_rng_normal32(0xffffffff) == (12 * 16 + 15) * float.fromhex("0x1.9c614ae8b41e8p-6")
+    assert abs(z.mean()) < 0.05 and abs(z.var() - 1.0) < 0.06
