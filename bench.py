@@ -321,7 +321,7 @@ def main():
             "config": {"workload": w["desc"], "generations_per_step": GENS_PER_STEP, "chains": cfg.nc, "d": cfg.d,
                        "chains_per_gpu": n_local, "rng": "philox4x32-10", "l2": "inputs larger than L2 (no flush)"
                        if cfg.nc * cfg.d * 8 > 126e6 else "state is L2-resident by construction (latency-bound config)",
-                       "exchange": ("none" if world == 1 else "delta: accepted rows pulled from the peers over NVLink + 17-word all-reduce per generation" if cfg.exchange == 2 else "peer gather over NVLink (bulk TMA reads of partner rows) + 17-word all-reduce per generation" if cfg.exchange == 1 else "ncclAllGather per generation")},
+                       "exchange": ("none" if world == 1 else "delta: full replica per GPU, accepted rows pushed into the peers' replicas over NVLink (posted stores in the accept kernel) + two flag barriers per generation" if cfg.exchange == 2 else "peer gather over NVLink (bulk TMA reads of partner rows) + 17-word all-reduce per generation" if cfg.exchange == 1 else "ncclAllGather per generation")},
             "gpu_launches": l1 - l0}
     if rank == 0 and not args.no_extras:
         peaks = load_peaks()

@@ -119,6 +119,7 @@ int check_flags(hb_handle* h) {
   if (e & HB_FLAG_LP_NONFINITE) return fail(h, HB_ERR_NONFINITE, "Calculated log-prior is not finite");
   if (e & HB_FLAG_LL_NONFINITE) return fail(h, HB_ERR_NONFINITE, "Calculated log-likelihood is not finite!");
   if (e & HB_FLAG_TARGET_DOMAIN) return fail(h, HB_ERR_INVALID, "Argument 'param' has to be >= zero!");
+  if (e & HB_FLAG_PEER_TIMEOUT) return fail(h, HB_ERR_NCCL, "HB_EXCHANGE_DELTA: a peer GPU did not reach the generation barrier (timeout)");
   if (e & HB_FLAG_J_NAN) return fail(h, HB_ERR_NONFINITE, "missing value where TRUE/FALSE needed (J is NaN: zero std_x)");
   return fail(h, HB_ERR_INVALID, "device error flags 0x%x", e);
 }
@@ -139,12 +140,9 @@ int allocate(hb_handle* h) {
     CK(cudaMemsetAsync(h->X, 0, (size_t)nc * ldx * sizeof(double), h->stream));
   }
   if (c.past_sample) { CK(dalloc(&h->Z, (size_t)h->m_cap * ldx)); }
-  if (h->delta_mode) {   // [count (16 B) | idx[cap] | rows[cap][ldx]] per parity
-    h->delta_idx_off = 16;
-    h->delta_rows_off = (16 + (size_t)nl * sizeof(int) + 255) & ~(size_t)255;
-    h->delta_par_bytes = (h->delta_rows_off + (size_t)nl * ldx * sizeof(double) + 255) & ~(size_t)255;
-    CK(cudaMalloc((void**)&h->delta_buf, 2 * h->delta_par_bytes));
-    CK(cudaMemsetAsync(h->delta_buf, 0, 2 * h->delta_par_bytes, h->stream));
+  if (h->delta_mode) {   // flag words of the two generation barriers (written by the peers)
+    CK(cudaMalloc((void**)&h->flags, 64 * sizeof(unsigned)));
+    CK(cudaMemsetAsync(h->flags, 0, 64 * sizeof(unsigned), h->stream));
   }
   CK(dalloc(&h->XP, (size_t)nl * ldx));
   CK(cudaMemsetAsync(h->XP, 0, (size_t)nl * ldx * sizeof(double), h->stream));
@@ -330,12 +328,7 @@ hb_k3_params hb_make_k3(hb_handle* h, long long i, long long first, long long st
   p.ctrl = h->ctrl; p.shift = h->shift; p.partials = h->partials;
   p.chain0 = first; p.stride = stride; p.n_local = n_items; p.nc = h->nc; p.n_runs = h->cfg.n_runs;
   p.state0 = h->chain0; p.gchain0 = (long long)c.run_offset * h->nc;
-  if (h->delta_mode) {
-    unsigned char* b = h->delta_buf + (size_t)(i & 1) * h->delta_par_bytes;
-    p.delta_count = reinterpret_cast<unsigned*>(b);
-    p.delta_idx = reinterpret_cast<int*>(b + h->delta_idx_off);
-    p.delta_rows = reinterpret_cast<double*>(b + h->delta_rows_off);
-  }
+  if (h->delta_mode) { p.n_push = h->world; for (int r = 0; r < 8; ++r) p.push[r] = h->peerX[r]; }
   p.d = d; p.ldx = h->ldx; p.nCR = c.nCR;
   p.adapt = in_adapt; p.write_dx = write_dx; p.seed = c.seed; p.gen = (uint32_t)i;
   p.u_accept = (c.rng_mode == HB_RNG_TAPE) ? h->tape.u_accept + (size_t)(i - 2) * h->tape.nct : nullptr;
@@ -371,6 +364,11 @@ int run_generation(hb_handle* h, long long i) {
     prof_scope ps(h, "K1");
     CK(hb_launch_k1(p, tape_mode, h->sm_count, h->stream));
     ps.done();
+    if (h->delta_mode) {   // barrier A, arrive: this rank's K1 of generation i has finished reading its replica
+      hb_flag_peers fp; for (int r = 0; r < 8; ++r) fp.p[r] = h->flags_peer[r];
+      CK(hb_launch_flag_signal(fp, 0, h->rank, h->world, (unsigned)i, h->stream));
+      h->launches++;
+    }
   }
   {  // K2: the target plugin
     prof_scope ps(h, "K2");
@@ -379,14 +377,17 @@ int run_generation(hb_handle* h, long long i) {
   }
   {  // K3
     const hb_k3_params p = hb_make_k3(h, i, h->chain0, 1, nl, store, in_adapt, false);
-    if (h->delta_mode) CK(cudaMemsetAsync(p.delta_count, 0, 16, h->stream));
+    if (h->delta_mode) {   // barrier A: no peer may push generation-i rows into a replica that K1 is still reading
+      CK(hb_launch_flag_wait(h->flags, 0, h->rank, h->world, (unsigned)i, &h->ctrl->err, h->stream));
+      h->launches++;
+    }
     prof_scope ps(h, "K3");
     int nb = 0;
     CK(hb_launch_k3(p, h->sm_count, &nb, nullptr, h->stream));
     ps.done();
   }
   h->pending_evals += h->nc;
-  if (in_adapt || upd || h->peer_mode || h->delta_mode) {  // finalize: J / n_id / n_acc, pCR adaptation, AR/CR rows (peer mode: every
+  if (in_adapt || upd || h->peer_mode) {  // finalize: J / n_id / n_acc, pCR adaptation, AR/CR rows (peer mode: every
                                           // generation, its counter all-reduce is the generation barrier)
     hb_fin_params f{};
     f.ctrl = h->ctrl; f.partials = h->partials; f.nblocks = h->k3_blocks; f.shift = h->shift; f.colsum = h->colsum;
@@ -412,12 +413,12 @@ int run_generation(hb_handle* h, long long i) {
   if (h->peer_mode) {   // K3 wrote every row of the shard into the other buffer; peers read it next generation
     h->cur ^= 1;
     h->X = h->Xbuf[h->cur] - h->chain0 * ldx;
-  } else if (h->delta_mode) {   // pull the rows the peers accepted this generation into the local replica
-    hb_delta_peers dp;
-    for (int r = 0; r < 8; ++r) dp.base[r] = h->delta_peer[r] ? h->delta_peer[r] + (size_t)(i & 1) * h->delta_par_bytes : nullptr;
+  } else if (h->delta_mode) {   // barrier B: the rows every peer accepted this generation have landed in this replica
+    hb_flag_peers fp; for (int r = 0; r < 8; ++r) fp.p[r] = h->flags_peer[r];
     prof_scope ps(h, "XCHG");
-    CK(hb_launch_delta_pull(h->X, ldx, d, dp, h->world, h->rank, nl, h->delta_idx_off, h->delta_rows_off, h->sm_count, h->stream));
-    ps.done();
+    CK(hb_launch_flag_signal(fp, 1, h->rank, h->world, (unsigned)i, h->stream));
+    CK(hb_launch_flag_wait(h->flags, 1, h->rank, h->world, (unsigned)i, &h->ctrl->err, h->stream));
+    ps.done(2);
   } else if (h->world > 1) {  // chain-state exchange: every rank needs every row for the next generation's partner draws
     prof_scope ps(h, "XCHG");
     if (int rc = hb_nccl_allgather_f64(h->comm, h->X + h->chain0 * ldx, h->X, (size_t)nl * ldx, h->stream, h->err)) return rc;
@@ -557,7 +558,13 @@ void hb_destroy(hb_handle* h) {
   hb_seq_destroy(h);
   if (h->vt && h->tctx) h->vt->destroy(h->tctx);
   hb_nccl_destroy(h->comm);
-  if (h->delta_mode) { for (int r = 0; r < 8; ++r) if (h->delta_opened[r]) cudaIpcCloseMemHandle(h->delta_opened[r]); cudaFree(h->delta_buf); }
+  if (h->delta_mode) {
+    for (int r = 0; r < 8; ++r) {
+      if (h->peerX_opened[r]) cudaIpcCloseMemHandle(h->peerX_opened[r]);
+      if (h->flags_opened[r]) cudaIpcCloseMemHandle(h->flags_opened[r]);
+    }
+    cudaFree(h->flags);
+  }
   if (h->peer_mode) {
     h->X = nullptr;
     for (int b = 0; b < 2; ++b) for (int r = 0; r < 8; ++r) if (h->peer_opened[b][r]) cudaIpcCloseMemHandle(h->peer_opened[b][r]);
@@ -668,8 +675,8 @@ int hb_peer_export(hb_handle* h, void* out128) {
   cudaIpcMemHandle_t hd[2];
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   if (h->delta_mode) {
-    memset(hd, 0, sizeof hd);
-    CK(cudaIpcGetMemHandle(&hd[0], h->delta_buf));
+    CK(cudaIpcGetMemHandle(&hd[0], h->X));
+    CK(cudaIpcGetMemHandle(&hd[1], h->flags));
     memcpy(out128, hd, 128);
     return HB_OK;
   }
@@ -686,11 +693,12 @@ int hb_peer_import(hb_handle* h, const void* all_handles) {
   const cudaIpcMemHandle_t* hd = (const cudaIpcMemHandle_t*)all_handles;
   if (h->delta_mode) {
     for (int r = 0; r < h->world; ++r) {
-      if (r == h->rank) { h->delta_peer[r] = h->delta_buf; continue; }
-      void* p = nullptr;
-      CK(cudaIpcOpenMemHandle(&p, hd[2 * r], cudaIpcMemLazyEnablePeerAccess));
-      h->delta_opened[r] = p;
-      h->delta_peer[r] = (const unsigned char*)p;
+      if (r == h->rank) continue;
+      void* px = nullptr; void* pf = nullptr;
+      CK(cudaIpcOpenMemHandle(&px, hd[2 * r], cudaIpcMemLazyEnablePeerAccess));
+      CK(cudaIpcOpenMemHandle(&pf, hd[2 * r + 1], cudaIpcMemLazyEnablePeerAccess));
+      h->peerX_opened[r] = px; h->peerX[r] = (double*)px;
+      h->flags_opened[r] = pf; h->flags_peer[r] = (unsigned*)pf;
     }
     h->peers_ready = true;
     return HB_OK;

@@ -23,7 +23,8 @@ enum : unsigned {
   HB_FLAG_LL_NONFINITE = 4u,     // R/internals.R:21
   HB_FLAG_J_NAN = 8u,            // if(any(J > 0)) on NaN, R/dream_parallel.R:407
   HB_FLAG_BAD_TAPE = 16u,
-  HB_FLAG_TARGET_DOMAIN = 32u    // HydroModel: param < 0, R/test_HydroModel.R:18
+  HB_FLAG_TARGET_DOMAIN = 32u,   // HydroModel: param < 0, R/test_HydroModel.R:18
+  HB_FLAG_PEER_TIMEOUT = 64u     // HB_EXCHANGE_DELTA: a peer GPU did not reach the generation barrier
 };
 
 enum { HB_SLOT_HEAD = 0, HB_SLOT_PARTNER0 = 1, HB_SLOT_CHOICE = 5, HB_SLOT_ACCEPT = 6, HB_SLOT_DIM0 = 8 };

@@ -44,11 +44,15 @@ struct hb_handle {
   const double* peer_ptr[2][8] = {};
   void* peer_opened[2][8] = {};
 
-  // HB_EXCHANGE_DELTA: per-parity pack buffers [count | idx | rows] in ONE allocation (one IPC handle per rank)
+  // HB_EXCHANGE_DELTA: every rank keeps a full replica of X; the accept kernel PUSHES the rows it accepted into the
+  // peers' replicas (posted NVLink stores).  Two flag barriers per generation order the pushes against the proposal
+  // kernel's reads: A = "my K1 of generation i has finished reading", B = "my pushes of generation i have landed".
   bool delta_mode = false;
-  unsigned char* delta_buf = nullptr; size_t delta_par_bytes = 0, delta_idx_off = 0, delta_rows_off = 0;
-  const unsigned char* delta_peer[8] = {};
-  void* delta_opened[8] = {};
+  double* peerX[8] = {};          // peer r's replica base (null for self)
+  void* peerX_opened[8] = {};
+  unsigned* flags = nullptr;      // [2][8] local flag words, written by the peers: flags[which*8 + source rank]
+  unsigned* flags_peer[8] = {};   // peer r's flag array
+  void* flags_opened[8] = {};
 
   // bounds / prior
   bool have_min_max = false;

@@ -72,11 +72,6 @@ __global__ void __launch_bounds__(256) hb_k3_kernel(const hb_k3_params p) {
       id = p.id[jl];
     }
     if (G > 1) { accf = __shfl_sync(FULL, accf, gbase); id = __shfl_sync(FULL, id, gbase); }
-    unsigned dslot = 0;
-    if (p.delta_count) {
-      if (valid && lg == 0 && accf) { dslot = atomicAdd(p.delta_count, 1u); p.delta_idx[dslot] = (int)j; }
-      if (G > 1) dslot = __shfl_sync(FULL, dslot, gbase);
-    }
 
     const bool copy_all = p.Xout != p.X;
     const bool need_x = adapt || p.hist_x != nullptr || copy_all;
@@ -93,7 +88,7 @@ __global__ void __launch_bounds__(256) hb_k3_kernel(const hb_k3_params p) {
             else acc[(2 + id) * d + k] += dx * dx;
           }
           p.Xout[j * (long long)ldx + k] = xn;                        // :358
-          if (p.delta_rows) p.delta_rows[(long long)dslot * ldx + k] = xn;
+          for (int r = 0; r < p.n_push; ++r) if (p.push[r]) p.push[r][j * (long long)ldx + k] = xn;
         } else {
           if (need_x) xn = p.X[j * (long long)ldx + k];
           if (copy_all) p.Xout[j * (long long)ldx + k] = xn;
@@ -243,17 +238,11 @@ __global__ void __launch_bounds__(256) hb_k3_wide_kernel(const hb_k3_params p) {
       if (lane == 0 && amask) atomicAdd(&s_cnt[0], (unsigned long long)__popc(amask));   // n_acc :374
     }
 
-    unsigned dbase = 0;
-    if (p.delta_count && amask) {                                     // one atomic per batch reserves the pack slots
-      if (lane == 0) dbase = atomicAdd(p.delta_count, (unsigned)__popc(amask));
-      dbase = __shfl_sync(FULL, dbase, 0);
-    }
     unsigned rows = all_rows ? vmask : amask;
     while (rows) {
       const int c = __ffs(rows) - 1;
       rows &= rows - 1;
       const int a_c = (amask >> c) & 1;
-      const unsigned dslot = dbase + __popc(amask & ((1u << c) - 1u));
       const int id_c = __shfl_sync(FULL, id, c);
       const long long jr = base + c;
       const long long j = p.chain0 + jr * p.stride;
@@ -271,7 +260,7 @@ __global__ void __launch_bounds__(256) hb_k3_wide_kernel(const hb_k3_params p) {
               else acc[(2 + id_c) * d + k] += dx * dx;
             }
             p.Xout[j * (long long)ldx + k] = xn;                      // :358
-            if (p.delta_rows) p.delta_rows[(long long)dslot * ldx + k] = xn;
+            for (int r = 0; r < p.n_push; ++r) if (p.push[r]) p.push[r][j * (long long)ldx + k] = xn;
           } else {
             xn = p.X[j * (long long)ldx + k];
             if (copy_all) p.Xout[j * (long long)ldx + k] = xn;
@@ -281,7 +270,6 @@ __global__ void __launch_bounds__(256) hb_k3_wide_kernel(const hb_k3_params p) {
           if (p.hist_x) p.hist_x[sr * (long long)d + k] = xn;         // chain[ind_out, 1:d, ] :388
         }
       }
-      if (a_c && p.delta_idx && lane == 0) p.delta_idx[dslot] = (int)j;
     }
   }
 
@@ -528,24 +516,26 @@ __global__ void hb_outlier_reset_peer_kernel(double* Xlocal, hb_peer_ptrs peers,
   }
 }
 
-// HB_EXCHANGE_DELTA: patch this rank's replica with the rows the peers accepted this generation.  One warp per packed
-// row: the chain id and the 8 d bytes of the row are read from the owning GPU through its NVLink peer pointer.
-__global__ void __launch_bounds__(256) hb_delta_pull_kernel(double* __restrict__ X, int ldx, int d, hb_delta_peers peers,
-                                                            int n_peers, int self, long long cap, size_t idx_off,
-                                                            size_t rows_off) {
-  const int lane = threadIdx.x & 31;
-  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (int r = 0; r < n_peers; ++r) {
-    if (r == self) continue;
-    const unsigned char* b = peers.base[r];
-    const unsigned cnt = *reinterpret_cast<const volatile unsigned*>(b);
-    const int* idx = reinterpret_cast<const int*>(b + idx_off);
-    const double* rows = reinterpret_cast<const double*>(b + rows_off);
-    for (long long s = warp_id; s < (long long)cnt && s < cap; s += n_warps) {
-      const long long j = idx[s];
-      for (int k = lane; k < d; k += 32) X[j * ldx + k] = rows[s * ldx + k];
+// HB_EXCHANGE_DELTA generation barriers: flag words in peer-mapped memory, value = generation number (monotonic, so
+// the flags never need resetting).  The signal kernel runs after the producing kernel in stream order, i.e. after all
+// of that kernel's (remote) stores were performed; the fence orders the flag store behind anything this thread saw.
+__global__ void hb_flag_signal_kernel(hb_flag_peers peers, int which, int self, int world, unsigned value) {
+  const int r = threadIdx.x;
+  if (r < world && r != self && peers.p[r]) {
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned*>(peers.p[r] + which * 8 + self) = value;
+  }
+}
+__global__ void hb_flag_wait_kernel(unsigned* flags, int which, int self, int world, unsigned value, unsigned* err) {
+  const int r = threadIdx.x;
+  if (r < world && r != self) {
+    const volatile unsigned* f = flags + which * 8 + r;
+    long long spins = 0;
+    while ((int)(*f - value) < 0) {
+      __nanosleep(64);
+      if (++spins > 40000000LL) { atomicOr(err, HB_FLAG_PEER_TIMEOUT); break; }   // ~ several seconds: a peer died
     }
+    __threadfence_system();
   }
 }
 
@@ -678,9 +668,13 @@ cudaError_t hb_launch_outlier_reset_peer(double* Xlocal, hb_peer_ptrs peers, lon
   return cudaGetLastError();
 }
 
-cudaError_t hb_launch_delta_pull(double* X, int ldx, int d, hb_delta_peers peers, int n_peers, int self, long long cap,
-                                 size_t idx_off, size_t rows_off, int sm_count, cudaStream_t st) {
-  hb_delta_pull_kernel<<<sm_count * 4, 256, 0, st>>>(X, ldx, d, peers, n_peers, self, cap, idx_off, rows_off);
+cudaError_t hb_launch_flag_signal(hb_flag_peers peers, int which, int self, int world, unsigned value, cudaStream_t st) {
+  hb_flag_signal_kernel<<<1, 32, 0, st>>>(peers, which, self, world, value);
+  return cudaGetLastError();
+}
+cudaError_t hb_launch_flag_wait(unsigned* flags, int which, int self, int world, unsigned value, unsigned* err,
+                                cudaStream_t st) {
+  hb_flag_wait_kernel<<<1, 32, 0, st>>>(flags, which, self, world, value, err);
   return cudaGetLastError();
 }
 

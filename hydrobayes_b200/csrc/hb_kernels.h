@@ -79,8 +79,8 @@ struct hb_k3_params {
   long long state0;       // lp/ll/lpost/history arrays hold chains [state0, ...): index = chain - state0
   int d, ldx, nCR;
   int adapt;              // generation is inside the adaptation period: accumulate std / jump statistics
-  // HB_EXCHANGE_DELTA: accepted rows are also packed (row + chain id) for the peers to pull; null when off
-  double* delta_rows; int* delta_idx; unsigned* delta_count;
+  // HB_EXCHANGE_DELTA: accepted rows are also stored into the peers' replicas of X (NVLink posted writes); null = off
+  double* push[8]; int n_push;
   int write_dx;           // per-run statistics path: overwrite XP[item] with the realised jump dx (0 if rejected)
   uint64_t seed;
   uint32_t gen;
@@ -137,10 +137,12 @@ cudaError_t hb_launch_outlier_reset(double* X, int ldx, int d, double* lpost, do
                                     const double* lpost_src, long long chain0, long long n_local, const int* outl,
                                     const int* news, int n_out, cudaStream_t st);
 struct hb_peer_ptrs { const double* p[8]; };
-// HB_EXCHANGE_DELTA pull: peer r's pack buffer = [count (16 B) | idx[cap] | rows[cap][ldx]] ; patches X in place
-struct hb_delta_peers { const unsigned char* base[8]; };
-cudaError_t hb_launch_delta_pull(double* X, int ldx, int d, hb_delta_peers peers, int n_peers, int self, long long cap,
-                                 size_t idx_off, size_t rows_off, int sm_count, cudaStream_t st);
+// HB_EXCHANGE_DELTA flag barriers over NVLink peer memory: signal = store `value` into flags[which*8 + self] of every
+// peer; wait = spin (bounded) until the local flags[which*8 + r] of every peer r reached `value`
+struct hb_flag_peers { unsigned* p[8]; };
+cudaError_t hb_launch_flag_signal(hb_flag_peers peers, int which, int self, int world, unsigned value, cudaStream_t st);
+cudaError_t hb_launch_flag_wait(unsigned* flags, int which, int self, int world, unsigned value, unsigned* err,
+                                cudaStream_t st);
 cudaError_t hb_launch_outlier_reset_peer(double* Xlocal, hb_peer_ptrs peers, long long peer_nl, int ldx, int d,
                                          double* lpost, double* lpost_hist_row, const double* lpost_src,
                                          long long chain0, long long n_local, const int* outl, const int* news,

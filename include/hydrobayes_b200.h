@@ -61,8 +61,9 @@ enum { HB_RNG_TAPE = 0, HB_RNG_PHILOX = 1 };
 /* multi-GPU chain-state exchange */
 enum { HB_EXCHANGE_ALLGATHER = 0 /* ncclAllGather of the shard's rows */,
        HB_EXCHANGE_PEER = 1      /* proposal kernel gathers partner rows through NVLink peer pointers */,
-       HB_EXCHANGE_DELTA = 2     /* only ACCEPTED rows travel: every rank packs the rows its accept kernel changed, the
-                                    peers pull them over NVLink and patch their replica (traffic x acceptance rate) */ };
+       HB_EXCHANGE_DELTA = 2     /* only ACCEPTED rows travel: every rank keeps a full replica and its accept kernel
+                                    stores the rows it accepted into the peers' replicas (posted NVLink writes), two
+                                    flag barriers per generation (traffic x acceptance rate) */ };
 
 /*
  * Mirrors the formals of dream() (R/dream.R:126-133) and dream_parallel()
