@@ -10,6 +10,7 @@
 // tape or generated with Philox4x32-10 keyed by (seed; chain, generation, slot): one Philox call per two dimensions
 // (zt, lambda, zeta; slot map v2 in include/hydrobayes_b200_rng.h) plus six per chain, the latter computed by
 // different lanes and broadcast.
+#include <cstdlib>
 #include "hb_kernels.h"
 
 namespace {
@@ -897,11 +898,14 @@ inline void k1_wide_geometry(const hb_k1_params& p, int sm_count, int* threads, 
   const size_t per_warp = (k1_warp_smem_bytes(p.delta, p.ldx) + 15) & ~(size_t)15;
   int warps = 8;
   while (warps > 1 && per_warp * warps > 110 * 1024) warps >>= 1;     // two CTAs per SM
+  int ctas = 2;
+  if (const char* e = getenv("HB_K1_WARPS")) warps = atoi(e);          // tuning experiments only
+  if (const char* e = getenv("HB_K1_CTAS")) ctas = atoi(e);
   *smem = per_warp * warps;
   *threads = warps * 32;
   const long long warps_needed = (p.n_local + 31) / 32;
   long long b = (warps_needed + warps - 1) / warps;
-  const long long cap = (long long)sm_count * 2;                       // persistent: two CTAs per SM, grid-stride batches
+  const long long cap = (long long)sm_count * ctas;                    // persistent: two CTAs per SM, grid-stride batches
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   *blocks = b;

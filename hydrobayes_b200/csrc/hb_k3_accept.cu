@@ -18,7 +18,7 @@ template <int G, int ITER, bool TAPE>
 __global__ void __launch_bounds__(256) hb_k3_kernel(const hb_k3_params p) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int CPW = 32 / G;
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   __shared__ unsigned long long s_cnt[2 * HB_MAX_NCR + 1];
   const int lane = threadIdx.x & 31;
   const int lg = lane & (G - 1);
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256) hb_k3_kernel(const hb_k3_params p) {
 template <int ITER, bool TAPE>
 __global__ void __launch_bounds__(256) hb_k3_wide_kernel(const hb_k3_params p) {
   constexpr unsigned FULL = 0xffffffffu;
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   __shared__ unsigned long long s_cnt[2 * HB_MAX_NCR + 1];
   const int lane = threadIdx.x & 31;
   const int slot = threadIdx.x >> 5;
@@ -177,7 +177,13 @@ __global__ void __launch_bounds__(256) hb_k3_wide_kernel(const hb_k3_params p) {
   unsigned errbits = 0;
 
   if (threadIdx.x <= 2 * HB_MAX_NCR) s_cnt[threadIdx.x] = 0ull;
-  if (adapt && !p.write_dx) for (int e = threadIdx.x; e < n_slots * E; e += blockDim.x) smem[e] = 0.0;
+  const bool stats = adapt && !p.write_dx;
+  if (stats) for (int e = threadIdx.x; e < n_slots * E; e += blockDim.x) smem[e] = 0.0;
+  // HB_EXCHANGE_DELTA: accepted rows are staged in shared memory (two buffers per warp) and leave as bulk TMA stores
+  // into the peers' replicas -- whole rows per NVLink transaction instead of 32-byte sectors
+  double* pushbuf = smem + (stats ? (((size_t)n_slots * E + 1) & ~(size_t)1) : 0) + (size_t)slot * 2 * ldx;   // 16-byte aligned
+  if (p.n_push > 0) for (int e = lane; e < 2 * ldx; e += 32) pushbuf[e] = 0.0;   // the pad (k >= d) stays zero
+  unsigned n_pushed = 0;
   __syncthreads();
   double* acc = smem + (size_t)slot * E;
   double s1[ITER], s2[ITER], sh[ITER];
@@ -247,6 +253,12 @@ __global__ void __launch_bounds__(256) hb_k3_wide_kernel(const hb_k3_params p) {
       const long long jr = base + c;
       const long long j = p.chain0 + jr * p.stride;
       const long long sr = j - p.state0;
+      const bool push_c = a_c && p.n_push > 0;
+      double* pb = pushbuf + (size_t)(n_pushed & 1u) * ldx;
+      if (push_c && n_pushed >= 2) {        // the bulk stores that read this buffer two rows ago must have drained
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+      }
 #pragma unroll
       for (int m = 0; m < ITER; ++m) {
         const int k = m * 32 + lane;
@@ -260,7 +272,7 @@ __global__ void __launch_bounds__(256) hb_k3_wide_kernel(const hb_k3_params p) {
               else acc[(2 + id_c) * d + k] += dx * dx;
             }
             p.Xout[j * (long long)ldx + k] = xn;                      // :358
-            for (int r = 0; r < p.n_push; ++r) if (p.push[r]) p.push[r][j * (long long)ldx + k] = xn;
+            if (push_c) pb[k] = xn;
           } else {
             xn = p.X[j * (long long)ldx + k];
             if (copy_all) p.Xout[j * (long long)ldx + k] = xn;
@@ -270,8 +282,19 @@ __global__ void __launch_bounds__(256) hb_k3_wide_kernel(const hb_k3_params p) {
           if (p.hist_x) p.hist_x[sr * (long long)d + k] = xn;         // chain[ind_out, 1:d, ] :388
         }
       }
+      if (push_c) {
+        __syncwarp();
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        if (lane == 0) {
+          for (int r = 0; r < p.n_push; ++r)
+            if (p.push[r]) tma_store_1d(p.push[r] + j * (long long)ldx, pb, (uint32_t)ldx * 8u);
+          tma_store_commit();
+        }
+        ++n_pushed;
+      }
     }
   }
+  if (p.n_push > 0 && lane == 0) tma_store_wait<0>();   // all pushed rows have left before the block retires
 
   const bool block_stats = adapt && !p.write_dx;
   if (block_stats) {
@@ -317,7 +340,7 @@ cudaError_t launch_wide(const hb_k3_params& p, int sm_count, int* nblocks_out, s
   if (nblocks_out) *nblocks_out = (int)blocks;
   if (smem_out) *smem_out = smem_adapt;
   if (p.X == nullptr) return cudaSuccess;
-  const size_t smem = (p.adapt && !p.write_dx) ? smem_adapt : 0;
+  const size_t smem = ((p.adapt && !p.write_dx) ? smem_adapt : 0) + (p.n_push > 0 ? (size_t)warps * 2 * p.ldx * sizeof(double) + 16 : 0);
   const bool tape = p.u_accept != nullptr;
   cudaError_t e = cudaSuccess;
   if (tape) {

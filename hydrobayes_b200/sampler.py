@@ -268,7 +268,7 @@ def _make_config(sweep, lik, par_info, nc, t, d, burnin, adapt, updateInterval, 
 def _drive(sweep, fun, extra, lik, par_info, nc, t, d, burnin, adapt, updateInterval, delta, c_val, c_star, nCR, p_g,
            beta0, thin, outlier_check, obs, abc_rho, abc_e, glue_shape, lik_fun, past_sample, m0, archive_update,
            psnooker, mt, checkConvergence, verbose, seed, tape, device, record_accept, store_fx, slice_generations,
-           default_prior, forcing):
+           default_prior, forcing, distributed=False, exchange=None):
     if not isinstance(fun, str):
         raise A.HbError(A.HB_ERR_UNKNOWN_TARGET, "fun must be the NAME of a registered device target "
                                                  "(arbitrary closures stay off the GPU path)")
@@ -279,6 +279,15 @@ def _drive(sweep, fun, extra, lik, par_info, nc, t, d, burnin, adapt, updateInte
                        checkConvergence, seed, tape, record_accept, store_fx and fun != "HydroModel", default_prior)
     rng = np.random.default_rng(seed)
     n0 = (m0 if m0 is not None else 10 * d) if past_sample else nc
+    rank, world = 0, 1
+    if distributed:   # one process per GPU: this rank owns chains [rank*nc/world, (rank+1)*nc/world)
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        if world > 1:
+            if sweep != A.HB_SWEEP_SYNCHRONOUS:
+                raise A.HbError(A.HB_ERR_UNSUPPORTED, "only dream_parallel (synchronous sweep) shards across GPUs")
+            cfg.exchange = (A.HB_EXCHANGE_ALLGATHER if past_sample else A.HB_EXCHANGE_DELTA) if exchange is None else exchange
+    n_shard = shard_range(nc, rank, world)[1] if world > 1 else None
     with Sampler(cfg, device) as s:
         if par_info.get("min") is not None and par_info.get("max") is not None:
             s.set_bounds(par_info["min"], par_info["max"])
@@ -286,22 +295,26 @@ def _drive(sweep, fun, extra, lik, par_info, nc, t, d, burnin, adapt, updateInte
             s.set_obs(obs)
         data = forcing if forcing is not None else (extra[0] if extra else None)
         s.set_target(fun, data)
-        x0 = prior_sample(par_info, d, n0, rng)
+        if world > 1:
+            s.comm_init(rank, world, broadcast_unique_id(lambda: _unique_id(s.L), rank))
+        x0 = prior_sample(par_info, d, n0, rng)   # same seed on every rank: every rank holds the whole initial population
         if x0.shape[0] != n0:
             raise ValueError(f"initial sample has {x0.shape[0]} rows, expected {n0}")
         s.set_initial(x0)
+        if world > 1 and cfg.exchange in (A.HB_EXCHANGE_PEER, A.HB_EXCHANGE_DELTA):
+            s.peer_setup(world)
         if tape is not None:
             s.set_tape(tape.struct(), keepalive=tape)
         step = int(slice_generations) if slice_generations else (max(1, t // 50) if verbose else t)
         done = 1
         while done < t:
             done = s.run(step)          # the R driver ticks txtProgressBar / checks interrupts between slices
-        chain = s.fetch_chain()
+        chain = s.fetch_chain(n_shard)             # sharded: this rank's chains, chain[out_t, d+3, nc/world]
         ar, cr = s.fetch_ar_cr()
-        out = {"chain": chain}
+        out = {"chain": chain, "rank": rank, "world": world}
         names = par_info.get("names") or [f"par{k + 1}" for k in range(d)]
         out["chain_colnames"] = list(names) + ["lp", "ll", "lpost"]
-        out["fx"] = s.fetch_fx() if cfg.store_fx else None
+        out["fx"] = s.fetch_fx(n_shard) if cfg.store_fx else None
         pairs = s.fetch_outliers()
         out["outlier"] = _outlier_list(pairs, cfg, sweep)
         out["AR"] = ar
@@ -311,7 +324,7 @@ def _drive(sweep, fun, extra, lik, par_info, nc, t, d, burnin, adapt, updateInte
         if checkConvergence:
             out["R_stat"] = s.fetch_rstat()
         if record_accept:
-            out["accept"] = s.fetch_accept()
+            out["accept"] = s.fetch_accept(n_shard)
         loop_ms, launches = s.timing()
         out["device_loop_seconds"] = loop_ms * 1e-3
         out["gpu_launches"] = launches
@@ -341,16 +354,20 @@ def dream_parallel(fun, *extra, lik=None, par_info=None, nc, t, d, burnin=0, ada
                    abc_e=None, glue_shape=None, lik_fun=None, past_sample=False, m0=None, archive_update=None,
                    psnooker=0, mt=1, ncores=1, checkConvergence=False, verbose=True,
                    seed=None, tape=None, device=0, record_accept=False, store_fx=True, slice_generations=None,
-                   forcing=None):
+                   forcing=None, distributed=False, exchange=None):
     """DREAM, synchronous population sweep -- drop-in for HydroBayes::dream_parallel (R/dream_parallel.R:155-455).
 
     ``fun`` is the name of a registered device target ("mixture", "t_distribution", "HydroModel").  ``ncores`` is
     accepted and ignored.  Chain indices in ``outlier`` are 0-based.
+
+    ``distributed=True`` (one process per GPU, ``torch.distributed`` initialised): the population is block-partitioned
+    across the ranks, every rank returns the ``chain`` / ``fx`` of its own chains (``gather_chain`` assembles the full
+    array); AR, CR, outlier and R_stat are identical on every rank.
     """
     return _drive(A.HB_SWEEP_SYNCHRONOUS, fun, extra, lik, par_info, nc, t, d, burnin, adapt, updateInterval, delta,
                   c_val, c_star, nCR, p_g, beta0, thin, outlier_check, obs, abc_rho, abc_e, glue_shape, lik_fun,
                   past_sample, m0, archive_update, psnooker, mt, checkConvergence, verbose, seed, tape, device,
-                  record_accept, store_fx, slice_generations, "flat", forcing)
+                  record_accept, store_fx, slice_generations, "flat", forcing, distributed, exchange)
 
 
 def dream(fun, *extra, lik=None, par_info=None, nc, t, d, burnin=0, adapt=0.1, updateInterval=10, delta=3, c_val=0.1,
@@ -411,6 +428,14 @@ def HydroModel(forcing, param) -> np.ndarray:
 # ---------------------------------------------------------------------------------------------------------
 # multi-GPU host plumbing (one process per GPU; torch.distributed is plumbing only)
 # ---------------------------------------------------------------------------------------------------------
+def _unique_id(L) -> bytes:
+    buf = C.create_string_buffer(128)
+    rc = L.hb_comm_unique_id(buf)
+    if rc != A.HB_OK:
+        raise A.HbError(rc, L.hb_last_error(None).decode())
+    return bytes(buf.raw)
+
+
 def shard_range(nc: int, rank: int, world: int):
     """Block partition of the population: rank r owns chains [r*nc/world, (r+1)*nc/world) (hb_comm_init)."""
     if world < 1 or not (0 <= rank < world):
