@@ -157,14 +157,23 @@ __global__ void __launch_bounds__(256) hb_k3_kernel(const hb_k3_params p) {
 // Wide variant (d > 16): a warp owns a batch of 32 chains.
 //   phase A  lane-per-chain: coalesced loads of lp_xp / ll_raw / lpost / id / u, the Metropolis decision, and the
 //            coalesced scalar stores (lp, ll, lpost, history scalars, accept mask);
-//   phase B  warp-per-row, only for the rows that need touching: accepted rows (16 % for the t-distribution) outside
-//            the adaptation period, every row inside it (std_x needs the whole post-update population) or when the
-//            generation is stored.
+//   phase B  only for the rows that need touching -- accepted rows (16 % for the t-distribution) outside the adaptation
+//            period, every row inside it (std_x needs the whole post-update population) or when the generation is
+//            stored.  The rows move through a per-warp ring of shared-memory slots by 1-D bulk TMA: up to eight row
+//            loads are in flight per warp (XP row of an accepted chain, X row otherwise), and an accepted row leaves
+//            the slot it landed in as bulk stores into X and -- HB_EXCHANGE_DELTA -- into every peer's replica over
+//            NVLink, so in the steady state the row data never passes through registers.  The lanes read the slots
+//            (lane owns columns k = 32 m + lane) only for what needs arithmetic: the adaptation statistics, the
+//            realised jump dx, the history copy.
 // ------------------------------------------------------------------------------------------------------------------
+constexpr int K3_SLOTS = 8;
+
+__host__ __device__ inline size_t k3_warp_smem_bytes(int ldx) { return (size_t)K3_SLOTS * ldx * 8 + K3_SLOTS * 8; }
+
 template <int ITER, bool TAPE>
-__global__ void __launch_bounds__(256) hb_k3_wide_kernel(const hb_k3_params p) {
+__global__ void __launch_bounds__(256, 3) hb_k3_wide_kernel(const hb_k3_params p, int warp_smem, int acc_off) {
   constexpr unsigned FULL = 0xffffffffu;
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(16) unsigned char k3_smem[];
   __shared__ unsigned long long s_cnt[2 * HB_MAX_NCR + 1];
   const int lane = threadIdx.x & 31;
   const int slot = threadIdx.x >> 5;
@@ -173,19 +182,26 @@ __global__ void __launch_bounds__(256) hb_k3_wide_kernel(const hb_k3_params p) {
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const int d = p.d, ldx = p.ldx, nCR = p.nCR;
   const bool adapt = p.adapt != 0;
+  const bool stats = adapt && !p.write_dx;
   const int E = (nCR + 2) * d;
+  const uint32_t row_bytes = (uint32_t)ldx * 8u;
   unsigned errbits = 0;
 
+  double* ring = reinterpret_cast<double*>(k3_smem + (size_t)slot * warp_smem);          // [K3_SLOTS][ldx]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)K3_SLOTS * ldx);           // [K3_SLOTS]
+  double* acc_all = reinterpret_cast<double*>(k3_smem + acc_off);                        // [n_slots][E] (stats only)
+  double* acc = acc_all + (size_t)slot * E;
+
   if (threadIdx.x <= 2 * HB_MAX_NCR) s_cnt[threadIdx.x] = 0ull;
-  const bool stats = adapt && !p.write_dx;
-  if (stats) for (int e = threadIdx.x; e < n_slots * E; e += blockDim.x) smem[e] = 0.0;
-  // HB_EXCHANGE_DELTA: accepted rows are staged in shared memory (two buffers per warp) and leave as bulk TMA stores
-  // into the peers' replicas -- whole rows per NVLink transaction instead of 32-byte sectors
-  double* pushbuf = smem + (stats ? (((size_t)n_slots * E + 1) & ~(size_t)1) : 0) + (size_t)slot * 2 * ldx;   // 16-byte aligned
-  if (p.n_push > 0) for (int e = lane; e < 2 * ldx; e += 32) pushbuf[e] = 0.0;   // the pad (k >= d) stays zero
-  unsigned n_pushed = 0;
+  if (stats) for (int e = threadIdx.x; e < n_slots * E; e += blockDim.x) acc_all[e] = 0.0;
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < K3_SLOTS; ++q) mbar_init(&bars[q], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
   __syncthreads();
-  double* acc = smem + (size_t)slot * E;
+  unsigned phase_bits = 0;                              // parity of the next completion of barrier q
+  bool stores_pending = false;                          // lane 0: bulk stores of the previous group may still read the ring
   double s1[ITER], s2[ITER], sh[ITER];
 #pragma unroll
   for (int m = 0; m < ITER; ++m) {
@@ -195,6 +211,9 @@ __global__ void __launch_bounds__(256) hb_k3_wide_kernel(const hb_k3_params p) {
   }
   const bool copy_all = p.Xout != p.X;                  // double-buffered shard: rejected rows are carried over
   const bool all_rows = adapt || p.hist_x != nullptr || copy_all;   // (write_dx needs every row too: dx = 0)
+  const bool need_old = adapt;                          // accepted rows also need the old state: dx = xp - x  (:357)
+  const bool lanes_read = adapt || p.hist_x != nullptr || copy_all; // somebody needs the values in registers
+  const int group = need_old ? K3_SLOTS / 2 : K3_SLOTS; // rows per group (accepted rows take two slots in adaptation)
 
   for (long long base = warp_id * 32; base < p.n_local; base += n_warps * 32) {
     const long long jl = base + lane;
@@ -246,58 +265,76 @@ __global__ void __launch_bounds__(256) hb_k3_wide_kernel(const hb_k3_params p) {
 
     unsigned rows = all_rows ? vmask : amask;
     while (rows) {
-      const int c = __ffs(rows) - 1;
-      rows &= rows - 1;
-      const int a_c = (amask >> c) & 1;
-      const int id_c = __shfl_sync(FULL, id, c);
-      const long long jr = base + c;
-      const long long j = p.chain0 + jr * p.stride;
-      const long long sr = j - p.state0;
-      const bool push_c = a_c && p.n_push > 0;
-      double* pb = pushbuf + (size_t)(n_pushed & 1u) * ldx;
-      if (push_c && n_pushed >= 2) {        // the bulk stores that read this buffer two rows ago must have drained
-        if (lane == 0) tma_store_wait_read<1>();
-        __syncwarp();
-      }
+      // ---- this group's rows: lane q < n_g owns row c_q (ascending chain order) ----
+      int my_c = -1, n_g = 0;
+      {
+        unsigned rr = rows;
 #pragma unroll
-      for (int m = 0; m < ITER; ++m) {
-        const int k = m * 32 + lane;
-        if (k < d) {
-          double xn;
-          if (a_c) {
-            xn = p.XP[jr * (long long)ldx + k];
-            if (adapt) {
-              const double dx = xn - p.X[j * (long long)ldx + k];     // R/dream_parallel.R:357 (after bound handling)
-              if (p.write_dx) p.XP_rw[jr * (long long)ldx + k] = dx;
-              else acc[(2 + id_c) * d + k] += dx * dx;
+        for (int q = 0; q < K3_SLOTS; ++q)
+          if (q < group && rr) { const int c = __ffs(rr) - 1; rr &= rr - 1; if (lane == q) my_c = c; n_g = q + 1; }
+        rows = rr;
+      }
+      if (stores_pending) { if (lane == 0) tma_store_wait_read<0>(); stores_pending = false; }
+      __syncwarp();
+      if (lane < n_g) {                                               // issue the row loads of the group
+        const int a_c = (amask >> my_c) & 1;
+        const long long jr = base + my_c;
+        const long long j = p.chain0 + jr * p.stride;
+        const int sl = need_old ? 2 * lane : lane;
+        const bool two = a_c && need_old;
+        mbar_expect_tx(&bars[lane], two ? 2 * row_bytes : row_bytes);
+        tma_load_1d(ring + (size_t)sl * ldx, a_c ? p.XP + jr * (long long)ldx : p.X + j * (long long)ldx, row_bytes, &bars[lane]);
+        if (two) tma_load_1d(ring + (size_t)(sl + 1) * ldx, p.X + j * (long long)ldx, row_bytes, &bars[lane]);
+      }
+      // ---- consume ----
+#pragma unroll 1
+      for (int q = 0; q < n_g; ++q) {
+        const int c = __shfl_sync(FULL, my_c, q);
+        const int a_c = (amask >> c) & 1;
+        const int id_c = __shfl_sync(FULL, id, c);
+        const long long jr = base + c;
+        const long long j = p.chain0 + jr * p.stride;
+        const long long sr = j - p.state0;
+        const int sl = need_old ? 2 * q : q;
+        const double* __restrict__ rowv = ring + (size_t)sl * ldx;
+        mbar_wait(&bars[q], (phase_bits >> q) & 1u);
+        phase_bits ^= 1u << q;
+        if (lanes_read) {
+#pragma unroll
+          for (int m = 0; m < ITER; ++m) {
+            const int k = m * 32 + lane;
+            if (k < d) {
+              const double xn = rowv[k];
+              if (a_c) {
+                if (adapt) {
+                  const double dx = xn - rowv[ldx + k];                 // R/dream_parallel.R:357 (after bound handling)
+                  if (p.write_dx) p.XP_rw[jr * (long long)ldx + k] = dx;
+                  else acc[(2 + id_c) * d + k] += dx * dx;
+                }
+              } else {
+                if (copy_all) p.Xout[j * (long long)ldx + k] = xn;
+                if (adapt && p.write_dx) p.XP_rw[jr * (long long)ldx + k] = 0.0;
+              }
+              if (stats) { const double cc = xn - sh[m]; s1[m] += cc; s2[m] += cc * cc; }
+              if (p.hist_x) p.hist_x[sr * (long long)d + k] = xn;       // chain[ind_out, 1:d, ] :388
             }
-            p.Xout[j * (long long)ldx + k] = xn;                      // :358
-            if (push_c) pb[k] = xn;
-          } else {
-            xn = p.X[j * (long long)ldx + k];
-            if (copy_all) p.Xout[j * (long long)ldx + k] = xn;
-            if (adapt && p.write_dx) p.XP_rw[jr * (long long)ldx + k] = 0.0;
           }
-          if (adapt && !p.write_dx) { const double cc = xn - sh[m]; s1[m] += cc; s2[m] += cc * cc; }
-          if (p.hist_x) p.hist_x[sr * (long long)d + k] = xn;         // chain[ind_out, 1:d, ] :388
         }
-      }
-      if (push_c) {
-        __syncwarp();
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-        if (lane == 0) {
+        if (a_c && lane == 0) {                                         // :358  xt[accept,] <- xp[accept,]
+          tma_store_1d(p.Xout + j * (long long)ldx, rowv, row_bytes);
           for (int r = 0; r < p.n_push; ++r)
-            if (p.push[r]) tma_store_1d(p.push[r] + j * (long long)ldx, pb, (uint32_t)ldx * 8u);
+            if (p.push[r]) tma_store_1d(p.push[r] + j * (long long)ldx, rowv, row_bytes);
           tma_store_commit();
+          stores_pending = true;
         }
-        ++n_pushed;
       }
+      stores_pending = __shfl_sync(FULL, (int)stores_pending, 0) != 0;
+      __syncwarp();                                                     // every lane is done reading the ring
     }
   }
-  if (p.n_push > 0 && lane == 0) tma_store_wait<0>();   // all pushed rows have left before the block retires
+  if (lane == 0) tma_store_wait<0>();                                   // all rows have left before the block retires
 
-  const bool block_stats = adapt && !p.write_dx;
-  if (block_stats) {
+  if (stats) {
 #pragma unroll
     for (int m = 0; m < ITER; ++m) {
       const int k = m * 32 + lane;
@@ -305,10 +342,11 @@ __global__ void __launch_bounds__(256) hb_k3_wide_kernel(const hb_k3_params p) {
     }
   }
   __syncthreads();
-  if (block_stats) {
+  if (stats) {
+    // fixed-order reduction over the block's warps -> one partial row per block
     for (int e = threadIdx.x; e < E; e += blockDim.x) {
       double s = 0.0;
-      for (int q = 0; q < n_slots; ++q) s += smem[(size_t)q * E + e];
+      for (int q = 0; q < n_slots; ++q) s += acc_all[(size_t)q * E + e];
       p.partials[(size_t)blockIdx.x * E + e] = s;
     }
   }
@@ -325,32 +363,42 @@ __global__ void __launch_bounds__(256) hb_k3_wide_kernel(const hb_k3_params p) {
 
 template <int ITER>
 cudaError_t launch_wide(const hb_k3_params& p, int sm_count, int* nblocks_out, size_t* smem_out, cudaStream_t st) {
-  const size_t per_warp = (size_t)(p.nCR + 2) * p.d * sizeof(double);
+  const size_t per_warp_ring = (k3_warp_smem_bytes(p.ldx) + 15) & ~(size_t)15;
+  const size_t per_warp_acc = (size_t)(p.nCR + 2) * p.d * sizeof(double);
   int warps = 8;
-  const size_t budget = 100 * 1024;
-  while (warps > 1 && per_warp * warps > budget) warps >>= 1;
-  const size_t smem_adapt = per_warp * warps;
-  if (smem_adapt > 220 * 1024) return cudaErrorInvalidValue;
+  while (warps > 1 && (per_warp_ring + per_warp_acc) * warps > 100 * 1024) warps >>= 1;
+  if ((per_warp_ring + per_warp_acc) * warps > 220 * 1024) return cudaErrorInvalidValue;
   const int threads = warps * 32;
   const long long warps_needed = (p.n_local + 31) / 32;
   long long blocks = (warps_needed + warps - 1) / warps;
-  const long long cap = (long long)sm_count * 4;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  if (nblocks_out) *nblocks_out = (int)blocks;
-  if (smem_out) *smem_out = smem_adapt;
-  if (p.X == nullptr) return cudaSuccess;
-  const size_t smem = ((p.adapt && !p.write_dx) ? smem_adapt : 0) + (p.n_push > 0 ? (size_t)warps * 2 * p.ldx * sizeof(double) + 16 : 0);
+  // one resident wave per launch.  The block count reported to the caller (the finalize kernel reduces that many
+  // partial rows) is the adaptation-period one; launches outside the adaptation period write no partials and may use
+  // the larger grid their smaller shared-memory footprint allows.
+  auto wave = [&](size_t smem_block) {
+    long long per_sm = (long long)(224 * 1024 / (smem_block + 1024));
+    if (per_sm > 3) per_sm = 3;                              // __launch_bounds__(256, 3)
+    if (per_sm < 1) per_sm = 1;
+    long long b = blocks;
+    if (b > (long long)sm_count * per_sm) b = (long long)sm_count * per_sm;
+    return b < 1 ? 1 : b;
+  };
+  const size_t smem_full = (per_warp_ring + per_warp_acc) * warps;
+  if (nblocks_out) *nblocks_out = (int)wave(smem_full);
+  if (smem_out) *smem_out = smem_full;
+  if (p.X == nullptr) return cudaSuccess;                   // geometry query only
+  const bool st_acc = p.adapt && !p.write_dx;
+  const size_t smem = per_warp_ring * warps + (st_acc ? per_warp_acc * warps : 0);
+  blocks = wave(st_acc ? smem_full : smem);
   const bool tape = p.u_accept != nullptr;
   cudaError_t e = cudaSuccess;
   if (tape) {
     if (smem > 48 * 1024) e = cudaFuncSetAttribute(hb_k3_wide_kernel<ITER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    hb_k3_wide_kernel<ITER, true><<<(unsigned)blocks, threads, smem, st>>>(p);
+    hb_k3_wide_kernel<ITER, true><<<(unsigned)blocks, threads, smem, st>>>(p, (int)per_warp_ring, (int)(per_warp_ring * warps));
   } else {
     if (smem > 48 * 1024) e = cudaFuncSetAttribute(hb_k3_wide_kernel<ITER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    hb_k3_wide_kernel<ITER, false><<<(unsigned)blocks, threads, smem, st>>>(p);
+    hb_k3_wide_kernel<ITER, false><<<(unsigned)blocks, threads, smem, st>>>(p, (int)per_warp_ring, (int)(per_warp_ring * warps));
   }
   return cudaGetLastError();
 }
