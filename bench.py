@@ -151,7 +151,7 @@ def make_sampler(w, local, rank, world, torch):
     return s
 
 
-def roofline_for(kname, per_launch_ms, n_local, vt_work, peaks, dmma_peak):
+def roofline_for(kname, per_launch_ms, n_local, vt_work, peaks, dmma_peak, acc_rate=0.16):
     """algorithmic bytes/flops per chain-generation x chains per launch / launch duration"""
     d = 100
     if kname == "K1":
@@ -160,7 +160,9 @@ def roofline_for(kname, per_launch_ms, n_local, vt_work, peaks, dmma_peak):
         return {"kernel": "hb_k1_kernel (proposal)", "bound": "hbm", "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": a / peaks["hbm_gbs"], "peak_source": peaks["source"]}
     if kname == "K3":
-        bytes_ = (8 * d * (1 + 0.16) + 32) * n_local
+        # steady state (thin >> 1, outside the adaptation period): only accepted rows move -- read xp, write x -- plus
+        # the per-chain scalars lp_xp, ll_raw, lpost, id and the accepted lp/ll/lpost stores
+        bytes_ = (16 * d * acc_rate + 28 + 24 * acc_rate) * n_local
         a = bytes_ / (per_launch_ms * 1e-3) / 1e9
         return {"kernel": "hb_k3_kernel (accept)", "bound": "hbm", "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": a / peaks["hbm_gbs"], "peak_source": peaks["source"]}
@@ -304,7 +306,7 @@ def main():
     value = cfg.nc * gens / wall
 
     # per-kernel durations (CUDA events on the library's stream, after the timed region)
-    roof = None; kernels = {}
+    roof = None; kernels = {}; acc_rate = 0.16
     if not args.no_extras:
         s.profile(True)
         s.run(2 * GENS_PER_STEP)
@@ -313,6 +315,12 @@ def main():
             ms, n = s.kernel_ms(k)
             if n:
                 kernels[k] = {"ms_per_launch": ms / n, "launches": n}
+        try:   # acceptance rate of the last complete updateInterval (AR column 2, R/dream_parallel.R:431)
+            ar, _ = s.fetch_ar_cr()
+            col = ar[:, 1][np.isfinite(ar[:, 1])]
+            acc_rate = float(col[-1]) if col.size else 0.16
+        except Exception:
+            acc_rate = 0.16
     s.close()
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -331,37 +339,45 @@ def main():
         flops = {"t_distribution": (cfg.d * cfg.d + 3.0 * cfg.d,), "HydroModel": (5.0 * 3653,), "mixture": (40.0,)}[w["target"]]
         if kernels:
             dom = max(("K1", "K2", "K3"), key=lambda k: kernels.get(k, {"ms_per_launch": 0})["ms_per_launch"])
-            roof = roofline_for(dom, kernels[dom]["ms_per_launch"], n_local, flops, peaks, dm.value)
+            roof = roofline_for(dom, kernels[dom]["ms_per_launch"], n_local, flops, peaks, dm.value, acc_rate)
             roof["traffic"] = None
             prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
             if os.path.exists(prof):
                 roof["traffic"] = json.load(open(prof)).get(dom)
-            roof["all_kernels"] = {k: roofline_for(k, kernels[k]["ms_per_launch"], n_local, flops, peaks, dm.value)
+            roof["all_kernels"] = {k: roofline_for(k, kernels[k]["ms_per_launch"], n_local, flops, peaks, dm.value, acc_rate)
                                    for k in ("K1", "K2", "K3") if k in kernels}
             roof["kernel_ms_per_launch"] = {k: v["ms_per_launch"] for k, v in kernels.items()}
             roof["fp64_peaks_measured_tflops"] = {"dmma": dm.value, "dfma": df.value}
+            roof["acceptance_rate"] = acc_rate
         line["roofline"] = roof
         line["clocks"] = clk
-    if rank == 0 and world == 1 and not args.no_extras and not args.quick:
-        # end to end through the public API with host buffers (full C4 run: x0 upload, t-1 generations, chain fetch)
+    if not args.no_extras and not args.quick:
+        # end to end through the public API with host buffers (full C4 run: x0 upload, t-1 generations, chain fetch);
+        # at N > 1 every rank calls dream_parallel(distributed=True) and fetches the chain of its own shard
         w2 = workload(args.workload)
         c2 = w2["cfg"]
         x0 = w2["x0"]()
         par = dict(initial="user", val_ini=x0, prior={0: "flat", 1: "uniform"}[c2.prior])
         if "par_min" in w2["kw"]:
             par.update(min=w2["kw"]["par_min"], max=w2["kw"]["par_max"], bound="bound")
-        torch.cuda.synchronize()
+        barrier_sync(torch, world)
         t0 = time.perf_counter()
         res = hb.dream_parallel(w2["target"], lik=c2.lik, par_info=par, nc=c2.nc, t=c2.t, d=c2.d, thin=c2.thin,
                                 glue_shape=c2.glue_shape, obs=w2["kw"].get("obs"), forcing=w2["kw"].get("forcing"),
-                                verbose=False, seed=1312, store_fx=False)
-        e2e_s = time.perf_counter() - t0
+                                verbose=False, seed=1312, store_fx=False, device=local, distributed=world > 1,
+                                exchange=cfg.exchange if world > 1 else None)
+        barrier_sync(torch, world)
+        e2e_s = max_over_ranks(torch, world, time.perf_counter() - t0)
         n_steps = (c2.t - 1) / GENS_PER_STEP
-        line["e2e"] = {"value": c2.nc * (c2.t - 1) / e2e_s, "unit": UNIT,
-                       "h2d_bytes_per_step": x0.nbytes / n_steps,
-                       "d2h_bytes_per_step": (res["chain"].nbytes + res["AR"].nbytes + res["CR"].nbytes) / n_steps,
-                       "seconds": e2e_s, "call": "hydrobayes_b200.dream_parallel(...) full run incl. x0 upload and chain fetch"}
+        if rank == 0:
+            line["e2e"] = {"value": c2.nc * (c2.t - 1) / e2e_s, "unit": UNIT,
+                           "h2d_bytes_per_step": world * x0.nbytes / n_steps,
+                           "d2h_bytes_per_step": world * (res["chain"].nbytes + res["AR"].nbytes + res["CR"].nbytes) / n_steps,
+                           "seconds": e2e_s,
+                           "call": "hydrobayes_b200.dream_parallel(...) full run incl. x0 upload and chain fetch"
+                                   + (" (distributed=True: every rank uploads x0 and fetches the chain of its shard)" if world > 1 else "")}
         del res
+    if rank == 0 and world == 1 and not args.no_extras and not args.quick:
         cb, _ = cpu_baseline(w)
         line["cpu_baseline"] = cb
         others = {}

@@ -7,6 +7,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdlib>
 #include <string>
 #include <thread>
 #include <vector>
@@ -89,6 +92,17 @@ double quantile7_sorted(const std::vector<double>& s, double p) {
   const double xh = s[(size_t)hi - 1];
   if (index > lo && xh != qs) { const double hh = index - lo; qs = (1 - hh) * qs + hh * xh; }
   return qs;
+}
+
+double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+// HB_TIMING=1: one stderr line per host-side phase (seconds, and GB/s when a byte count is given)
+void timing_note(const char* what, double seconds, double bytes = 0) {
+  static const bool on = getenv("HB_TIMING") && getenv("HB_TIMING")[0] == '1';
+  if (!on) return;
+  if (bytes > 0) fprintf(stderr, "[hb timing] %-14s %8.1f ms  %6.2f GB  %6.1f GB/s\n", what, seconds * 1e3, bytes / 1e9, bytes / 1e9 / seconds);
+  else fprintf(stderr, "[hb timing] %-14s %8.1f ms\n", what, seconds * 1e3);
 }
 
 struct prof_scope {
@@ -553,6 +567,7 @@ int hb_create(const hb_config* cfg, int device, hb_handle** out) {
 
 void hb_destroy(hb_handle* h) {
   if (!h) return;
+  const double t_begin = now_s();
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   hb_seq_destroy(h);
@@ -579,8 +594,10 @@ void hb_destroy(hb_handle* h) {
   for (void* p : h->tape_allocs) cudaFree(p);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->pin) cudaFreeHost(h->pin);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
+  timing_note("destroy", now_s() - t_begin);
 }
 
 int hb_set_bounds(hb_handle* h, const double* par_min, const double* par_max, int n) {
@@ -715,16 +732,50 @@ int hb_peer_import(hb_handle* h, const void* all_handles) {
   return HB_OK;
 }
 
+// pageable host -> device through the pinned ring: a few threads fill pinned[k & 1] while the DMA of chunk k-1 runs
+static int upload_pipelined(hb_handle* h, void* dst_dev, const void* src_host, size_t bytes) {
+  const size_t want = std::min<size_t>((size_t)64 << 20, std::max<size_t>(bytes, 4096));
+  if (bytes < ((size_t)16 << 20)) { CK(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, h->stream)); return HB_OK; }
+  if (h->pin_bytes < 2 * want) { if (h->pin) cudaFreeHost(h->pin); h->pin = nullptr; CK(cudaHostAlloc((void**)&h->pin, 2 * want, cudaHostAllocDefault)); h->pin_bytes = 2 * want; }
+  const size_t half = h->pin_bytes / 2;
+  const size_t n_chunks = (bytes + half - 1) / half;
+  unsigned hw = std::thread::hardware_concurrency();
+  const int n_thr = (int)std::min<unsigned>(8u, hw > 2 ? hw - 1 : 1);
+  std::vector<cudaEvent_t> ev(n_chunks, nullptr);
+  cudaError_t e = cudaSuccess;
+  for (size_t k = 0; k < n_chunks && e == cudaSuccess; ++k) {
+    if (k >= 2) e = cudaEventSynchronize(ev[k - 2]);               // pinned[k & 1] has been consumed by the DMA
+    if (e != cudaSuccess) break;
+    const size_t off = k * half, n = std::min(half, bytes - off);
+    char* pb = reinterpret_cast<char*>(h->pin) + (k & 1) * half;
+    const char* sb = reinterpret_cast<const char*>(src_host) + off;
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_thr; ++t) th.emplace_back([=]() { const size_t lo = n / n_thr * t, hi = (t == n_thr - 1) ? n : n / n_thr * (t + 1); memcpy(pb + lo, sb + lo, hi - lo); });
+    memcpy(pb, sb, n_thr > 1 ? n / n_thr : n);
+    for (auto& x : th) x.join();
+    e = cudaMemcpyAsync(reinterpret_cast<char*>(dst_dev) + off, pb, n, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(ev[k], h->stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  for (auto& x : ev) if (x) cudaEventDestroy(x);
+  if (e != cudaSuccess) return fail(h, HB_ERR_CUDA, "initial-state upload failed: %s", cudaGetErrorString(e));
+  return HB_OK;
+}
+
 static int set_initial_impl(hb_handle* h, const double* x0, bool row_major) {
   if (!h || !x0) return HB_ERR_INVALID;
   if (h->have_initial) return fail(h, HB_ERR_STATE, "hb_set_initial was already called");
   cudaSetDevice(h->device);
+  const double t_begin = now_s();
   if (int rc = allocate(h)) return rc;
+  timing_note("allocate", now_s() - t_begin);
+  const double t_up = now_s();
   const long long m0 = h->modeb ? h->nct : h->m0, nc = h->modeb ? h->nct : h->nc;
   const int d = h->d, ldx = h->ldx;
   double* tmp = nullptr;
   CK(dalloc(&tmp, (size_t)m0 * d));
-  CK(cudaMemcpyAsync(tmp, x0, sizeof(double) * (size_t)m0 * d, cudaMemcpyHostToDevice, h->stream));
+  if (int rc = upload_pipelined(h, tmp, x0, sizeof(double) * (size_t)m0 * d)) { cudaFree(tmp); return rc; }
   // xt <- z[(m0-nc+1):m0, ]  (R/dream_parallel.R:213)
   if (row_major) {   // rows are already contiguous: strided device copies add the ldx padding
     const size_t sp = sizeof(double) * d, dp = sizeof(double) * ldx;
@@ -745,6 +796,7 @@ static int set_initial_impl(hb_handle* h, const double* x0, bool row_major) {
   CK(cudaStreamSynchronize(h->stream));
   cudaFree(tmp);
   h->have_initial = true;
+  timing_note("set_initial", now_s() - t_up, sizeof(double) * (double)m0 * d);
   return HB_OK;
 }
 
@@ -807,57 +859,75 @@ int hb_out_dims(const hb_handle* h, int64_t* out_t, int64_t* ar_rows, int64_t* a
 
 int64_t hb_ind_out(const hb_handle* h) { return h ? h->ind_out : 0; }
 
+// chain[nrows, d+3, n_local] (R layout, generation fastest) -> caller's host array, as a three-stage pipeline:
+//   device   tiled transposition of a chunk of chains from the [generation][chain][column] history into the R layout
+//   DMA      chunk -> pinned host ring (async copy on the handle's stream, full PCIe rate)
+//   host     a few threads copy the chunk from the pinned ring into the caller's (pageable, usually never touched:
+//            R allocVector / numpy empty) array -- the page faults of a fresh 10 GB result are spread over the threads
+//            and overlap the DMA of the next chunk instead of serialising in front of one copying thread.
 int hb_fetch_chain_rows(hb_handle* h, int64_t row0, int64_t nrows, double* out) {
   if (!h || !out) return HB_ERR_INVALID;
   if (!h->initialised) return fail(h, HB_ERR_STATE, "nothing has been run yet");
   if (row0 < 0 || nrows < 1 || row0 + nrows > h->out_t) return fail(h, HB_ERR_INVALID, "row range out of bounds");
   cudaSetDevice(h->device);
+  const double t_begin = now_s();
   const long long nl = h->n_local;
   const int dd = h->d + 3;
   const size_t per_chain = (size_t)nrows * dd * sizeof(double);
   const size_t total = per_chain * (size_t)nl;
-  // two staging buffers: the transposition of chunk k+1 runs on the device while chunk k travels to the host
-  size_t want = std::min<size_t>((size_t)128 << 20, total);
+  size_t want = std::min<size_t>((size_t)64 << 20, total);
   if (want < per_chain) want = per_chain;
   if (h->stage_bytes < 2 * want) { if (h->stage) cudaFree(h->stage); h->stage = nullptr; CK(cudaMalloc((void**)&h->stage, 2 * want)); h->stage_bytes = 2 * want; }
-  const size_t half = h->stage_bytes / 2;
+  if (h->pin_bytes < 2 * want) { if (h->pin) cudaFreeHost(h->pin); h->pin = nullptr; CK(cudaHostAlloc((void**)&h->pin, 2 * want, cudaHostAllocDefault)); h->pin_bytes = 2 * want; }
+  const size_t half = std::min(h->stage_bytes, h->pin_bytes) / 2;
   const long long chunk = (long long)(half / per_chain);
-  // a freshly allocated result array (R: allocVector, numpy: empty) has never been touched: fault its pages in with a
-  // few threads instead of letting the single copying thread pay for every page fault
-  std::vector<std::thread> touch;
-  if (total >= ((size_t)256 << 20)) {
-    const int nt = 8;
-    char* base = reinterpret_cast<char*>(out);
-    for (int t = 0; t < nt; ++t)
-      touch.emplace_back([=]() {
-        const size_t lo = total / nt * t, hi = (t == nt - 1) ? total : total / nt * (t + 1);
-        for (size_t o = lo; o < hi; o += 4096) base[o] = 0;
-      });
-  }
-  cudaEvent_t ev[2] = {nullptr, nullptr};
-  CK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
-  int rc = HB_OK;
-  auto launch = [&](long long c0, int b) -> cudaError_t {
-    const long long ncs = std::min(chunk, nl - c0);
-    cudaError_t e = hb_launch_chain_transpose(h->hist_x, h->hist_l, h->out_t, row0, nrows, h->ind_out, nl, h->d, c0, ncs,
-                                              reinterpret_cast<double*>(reinterpret_cast<char*>(h->stage) + (size_t)b * half), h->stream);
+  const long long n_chunks = (nl + chunk - 1) / chunk;
+  unsigned hw = std::thread::hardware_concurrency();
+  int n_thr = total < ((size_t)32 << 20) ? 1 : (int)std::min<unsigned>(16u, hw > 2 ? hw - 1 : 1);
+  // ready[k] = the DMA of chunk k has landed in pinned buffer k & 1 ; done[k] = copier threads finished with chunk k
+  std::vector<std::atomic<int>> ready((size_t)n_chunks), done((size_t)n_chunks);
+  for (auto& a : ready) a.store(0);
+  for (auto& a : done) a.store(0);
+  std::atomic<int> abort_flag{0};
+  char* pin = reinterpret_cast<char*>(h->pin);
+  char* outb = reinterpret_cast<char*>(out);
+  std::vector<std::thread> copiers;
+  for (int t = 0; t < n_thr; ++t)
+    copiers.emplace_back([&, t]() {
+      for (long long k = 0; k < n_chunks; ++k) {
+        while (!ready[(size_t)k].load(std::memory_order_acquire)) { if (abort_flag.load()) return; std::this_thread::yield(); }
+        const long long c0 = k * chunk, ncs = std::min(chunk, nl - c0);
+        const size_t bytes = per_chain * (size_t)ncs;
+        const size_t lo = bytes / n_thr * t & ~(size_t)63, hi = (t == n_thr - 1) ? bytes : (bytes / n_thr * (t + 1) & ~(size_t)63);
+        if (hi > lo) memcpy(outb + (size_t)c0 * per_chain + lo, pin + (size_t)(k & 1) * half + lo, hi - lo);
+        done[(size_t)k].fetch_add(1, std::memory_order_release);
+      }
+    });
+  std::vector<cudaEvent_t> ev((size_t)n_chunks, nullptr);
+  cudaError_t e = cudaSuccess;
+  auto enqueue = [&](long long k) -> cudaError_t {   // transpose chunk k on the device, then DMA it into pinned[k & 1]
+    const long long c0 = k * chunk, ncs = std::min(chunk, nl - c0);
+    char* dst = reinterpret_cast<char*>(h->stage) + (size_t)(k & 1) * half;
+    cudaError_t r = hb_launch_chain_transpose(h->hist_x, h->hist_l, h->out_t, row0, nrows, h->ind_out, nl, h->d, c0, ncs,
+                                              reinterpret_cast<double*>(dst), h->stream);
     h->launches++;
-    if (e == cudaSuccess) e = cudaEventRecord(ev[b], h->stream);
-    return e;
+    if (r == cudaSuccess) r = cudaMemcpyAsync(pin + (size_t)(k & 1) * half, dst, per_chain * (size_t)ncs, cudaMemcpyDeviceToHost, h->stream);
+    if (r == cudaSuccess) r = cudaEventCreateWithFlags(&ev[(size_t)k], cudaEventDisableTiming);
+    if (r == cudaSuccess) r = cudaEventRecord(ev[(size_t)k], h->stream);
+    return r;
   };
-  int b = 0;
-  cudaError_t e = launch(0, 0);
-  for (auto& t : touch) t.join();
-  for (long long c0 = 0; c0 < nl && e == cudaSuccess; c0 += chunk, b ^= 1) {
-    const long long ncs = std::min(chunk, nl - c0);
-    if (c0 + chunk < nl) e = launch(c0 + chunk, b ^ 1);
-    if (e == cudaSuccess) e = cudaEventSynchronize(ev[b]);
-    if (e == cudaSuccess)
-      e = cudaMemcpy(out + (size_t)c0 * dd * nrows, reinterpret_cast<char*>(h->stage) + (size_t)b * half, per_chain * (size_t)ncs, cudaMemcpyDeviceToHost);
+  for (long long k = 0; k < n_chunks && e == cudaSuccess; ++k) {
+    if (k >= 2) while (done[(size_t)(k - 2)].load(std::memory_order_acquire) < n_thr) std::this_thread::yield();   // pinned[k & 1] is free
+    e = enqueue(k);
+    if (k >= 1 && e == cudaSuccess) { e = cudaEventSynchronize(ev[(size_t)(k - 1)]); ready[(size_t)(k - 1)].store(1, std::memory_order_release); }
   }
-  cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
-  if (e != cudaSuccess) rc = fail(h, HB_ERR_CUDA, "chain fetch failed: %s", cudaGetErrorString(e));
-  return rc;
+  if (e == cudaSuccess && n_chunks >= 1) { e = cudaEventSynchronize(ev[(size_t)(n_chunks - 1)]); ready[(size_t)(n_chunks - 1)].store(1, std::memory_order_release); }
+  if (e != cudaSuccess) abort_flag.store(1);
+  for (auto& t : copiers) t.join();
+  for (auto& x : ev) if (x) cudaEventDestroy(x);
+  if (e != cudaSuccess) return fail(h, HB_ERR_CUDA, "chain fetch failed: %s", cudaGetErrorString(e));
+  timing_note("fetch_chain", now_s() - t_begin, (double)total);
+  return HB_OK;
 }
 
 int hb_fetch_chain(hb_handle* h, double* chain) { return h ? hb_fetch_chain_rows(h, 0, h->out_t, chain) : HB_ERR_INVALID; }

@@ -82,6 +82,7 @@ struct hb_handle {
   int *outl_dev = nullptr, *news_dev = nullptr;
   double *rstat_dev = nullptr, *rstat_xm = nullptr, *rstat_ss = nullptr;
   double* stage = nullptr; size_t stage_bytes = 0;
+  void* pin = nullptr; size_t pin_bytes = 0;      // pinned host ring of the chain fetch / initial-state upload
   double* gamma_tab = nullptr;
   void* outl_tmp = nullptr; size_t outl_tmp_bytes = 0;
   double *outl_sorted = nullptr, *outl_thr = nullptr; int* outl_count = nullptr;
