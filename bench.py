@@ -254,6 +254,33 @@ def quick_rate(name, local, torch, gens=200, warm=30):
     return out
 
 
+def convergence_c5(local, torch, n_runs=4096, nc=10, T=3653, t=3000):
+    """BASELINE config 5 on one GPU: n_runs independent HydroModel DREAM runs (distinct synthetic catchments, nc = 10
+    chains each, dream() = sequential sweep), every run driven until R_stat < 1.2 held at 3 consecutive checks
+    (metric 2 of SURVEY 8d: seconds to Gelman-Rubin R-hat < 1.2)."""
+    import helpers as H
+    from hydrobayes_b200 import Sampler, _abi as A
+    P, O = H.hydro_data_batch(T, n_runs)
+    cfg = A.default_config(nc=nc, t=t, d=1, lik=31, glue_shape=50.0, prior=A.HB_PRIOR_UNIFORM, bound=A.HB_BOUND_BOUND,
+                           seed=1312, sweep=A.HB_SWEEP_SEQUENTIAL, n_runs=n_runs)
+    x0 = np.concatenate([H.x0_hydro(nc) for _ in range(n_runs)])
+    with Sampler(cfg, local) as s:
+        s.set_bounds([0.01], [2.0])
+        s.set_target_batched("HydroModel", P, O)
+        s.set_initial(x0)
+        torch.cuda.synchronize()
+        res = s.run_to_convergence(threshold=1.2, check_every=10, hold=3)
+        ms, launches = s.timing()
+    conv = res["converged_at"]
+    return {"workload": f"C5: {n_runs} independent HydroModel DREAM runs (dream(), nc={nc}, T={T}, lik=31), each to R-hat<1.2",
+            "seconds_to_rhat_below_1.2": res["seconds"], "all_converged": res["all_converged"],
+            "runs_converged": int((conv > 0).sum()), "generations_run": res["generations"],
+            "median_generations_to_converge": float(np.median(conv[conv > 0])) if (conv > 0).any() else None,
+            "value": n_runs * nc * (res["generations"] - 1) / res["seconds"], "unit": UNIT,
+            "device_loop_seconds": ms * 1e-3, "gpu_launches": launches,
+            "rule": "max_k R_stat_k < 1.2 at 3 consecutive checks, every 10 stored generations from ind_out > 50"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -387,6 +414,10 @@ def main():
                     others[name] = quick_rate(name, local, torch)
                 except Exception as e:  # report, never hide
                     others[name] = {"error": repr(e)}
+        try:
+            others["C5"] = convergence_c5(local, torch)
+        except Exception as e:
+            others["C5"] = {"error": repr(e)}
         line["other_workloads"] = others
     if rank == 0:
         print(json.dumps(line))

@@ -1021,6 +1021,24 @@ int hb_rstat(hb_handle* h, double* out_d) {
   return HB_OK;
 }
 
+int hb_rstat_runs(hb_handle* h, double* out) {
+  if (!h || !out) return HB_ERR_INVALID;
+  if (!h->initialised) return fail(h, HB_ERR_STATE, "nothing has been run yet");
+  if (h->ind_out < 3) return fail(h, HB_ERR_INVALID, "R_stat needs at least 3 stored generations");
+  if (h->world > 1) return fail(h, HB_ERR_UNSUPPORTED, "hb_rstat_runs on a sharded population is not wired yet");
+  cudaSetDevice(h->device);
+  const long long nr = h->cfg.n_runs, nct = h->modeb ? h->nct : h->nc;
+  double* o = nullptr;
+  CK(dalloc(&o, (size_t)nr * h->d));
+  prof_scope ps(h, "K4");
+  CK(hb_launch_rstat_runs(h->hist_x, h->ind_out, nct, h->nc, nr, h->d, h->rstat_xm, h->rstat_ss, o, h->stream));
+  ps.done(2);
+  CK(cudaMemcpyAsync(out, o, sizeof(double) * (size_t)nr * h->d, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(o);
+  return HB_OK;
+}
+
 int hb_get_timing(const hb_handle* h, double* loop_ms, int64_t* kernel_launches) {
   if (!h) return HB_ERR_INVALID;
   if (loop_ms) *loop_ms = h->loop_ms;

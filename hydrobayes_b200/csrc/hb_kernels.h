@@ -161,6 +161,9 @@ cudaError_t hb_launch_chain_transpose(const double* hist_x, const double* hist_l
 cudaError_t hb_launch_rstat(const double* hist_x, long long t_rows, long long nct_stride, long long c0, long long n,
                             int d, double* xm_scratch, double* ss_scratch, double* out_d, cudaStream_t st);
 // same on an R-layout array x[t, d, n] (column-major)
+// per-run variant: out[run*d + k] for runs of nc consecutive chains (pass 1 over all chains, pass 2 one warp per (run, k))
+cudaError_t hb_launch_rstat_runs(const double* hist_x, long long t_rows, long long nct, long long nc, long long n_runs,
+                                 int d, double* xm_scratch, double* ss_scratch, double* out_runs_d, cudaStream_t st);
 cudaError_t hb_launch_rstat_colmajor(const double* x, long long t, int d, long long n, double* xm_scratch,
                                      double* ss_scratch, double* out_d, cudaStream_t st);
 

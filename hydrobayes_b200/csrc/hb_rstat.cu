@@ -93,7 +93,40 @@ __global__ void hb_rstat_pass2(const double* __restrict__ xm, const double* __re
   }
 }
 
+// one warp per (run, parameter): W, B, R over the run's nc chains, fixed shuffle order
+__global__ void hb_rstat_pass2_runs(const double* __restrict__ xm, const double* __restrict__ ss, long long t, long long nc,
+                                    long long n_runs, int d, double* __restrict__ out) {
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= n_runs * d) return;
+  const long long run = wid / d; const int k = (int)(wid % d);
+  const double* xmr = xm + run * nc * d; const double* ssr = ss + run * nc * d;
+  double w = 0, m = 0;
+  for (long long c = lane; c < nc; c += 32) { w += ssr[c * d + k]; m += xmr[c * d + k]; }
+  const double wsum = hb_warp_sum(w);
+  const double xmm = hb_warp_sum(m) / (double)nc;
+  double b = 0;
+  for (long long c = lane; c < nc; c += 32) { const double e = xmr[c * d + k] - xmm; b += e * e; }
+  const double bsum = hb_warp_sum(b);
+  if (lane == 0) {
+    const double n = (double)nc;
+    const double W = 2.0 / (n * (double)(t - 2)) * wsum;
+    const double B = 1.0 / (2.0 * (n - 1)) * bsum;
+    const double sigma = (double)(t - 2) / (double)t * W + 2.0 * B;
+    out[wid] = sqrt((n + 1) / n * sigma / W - (double)(t - 2) / (n * (double)t));
+  }
+}
+
 }  // namespace
+
+cudaError_t hb_launch_rstat_runs(const double* hist_x, long long t_rows, long long nct, long long nc, long long n_runs,
+                                 int d, double* xm_scratch, double* ss_scratch, double* out_runs_d, cudaStream_t st) {
+  const long long tot = nct * d;
+  hb_rstat_pass1_hist<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(hist_x, t_rows, nct, 0, nct, d, xm_scratch, ss_scratch);
+  const long long warps = n_runs * d;
+  hb_rstat_pass2_runs<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(xm_scratch, ss_scratch, t_rows, nc, n_runs, d, out_runs_d);
+  return cudaGetLastError();
+}
 
 cudaError_t hb_launch_rstat(const double* hist_x, long long t_rows, long long nct_stride, long long c0, long long n,
                             int d, double* xm_scratch, double* ss_scratch, double* out_d, cudaStream_t st) {

@@ -364,34 +364,98 @@ __global__ void hb_hydro_series_kernel(const double* __restrict__ param, long lo
   }
 }
 
-// batched independent runs: every run has its own forcing / obs series (BASELINE C5: distinct catchments)
+// batched independent runs: every run has its own forcing / obs series (BASELINE C5: distinct catchments).
+// The series are stored tiled and interleaved: PO[run / 32][t][run % 32] = {P_t, obs_t}.  A warp that owns 32
+// consecutive runs (sequential sweep: thread i is run i) reads one contiguous 512-byte line per time step, and a
+// block of time steps of its tile is one contiguous piece of memory -- a single 1-D bulk TMA copy per pipeline stage.
+// (Run-major storage made every thread stream its own 58 KB row: one 32-byte sector per 8 useful bytes.)
+__device__ __forceinline__ long long hydro_po_index(long long run, int t, int T) {
+  return ((run >> 5) * (long long)T + t) * 32 + (run & 31);
+}
+
+__device__ __forceinline__ void hydro_step(double2 v, double K, double den, double rden, double& S, double& sse, double& comp) {
+  S = div_by_recip(__dadd_rn(v.x, S), den, rden);                      // R/test_HydroModel.R:30
+  const double e = __dadd_rn(__dmul_rn(K, S), -v.y);                   // Y_i - obs_i, R/test_HydroModel.R:32
+  const double y = e * e - comp;
+  const double tt = sse + y;
+  comp = (tt - sse) - y;
+  sse = tt;
+}
+
+// generic batched path (any item -> run mapping): direct loads from the tiled layout
 __global__ void __launch_bounds__(128) hb_hydro_items_kernel(const double* __restrict__ X, long long n, int ldx,
-                                                             const double* __restrict__ forcing,
-                                                             const double* __restrict__ obs,
-                                                             const double* __restrict__ sst, int T, int T_pad,
+                                                             const double2* __restrict__ PO,
+                                                             const double* __restrict__ sst, int T,
                                                              double glue_shape, long long chain0, long long stride,
                                                              long long nc, double* __restrict__ ll, unsigned* err) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const long long run = (chain0 + i * stride) / nc;
-  const double* __restrict__ P = forcing + run * T_pad;
-  const double* __restrict__ O = obs + run * T_pad;
   const double K = X[i * ldx];
   if (K < 0) { atomicOr(err, HB_FLAG_TARGET_DOMAIN); ll[i] = NAN; return; }
   const double den = 1.0 + K * 1.0;
   const double rden = __ddiv_rn(1.0, den);
   double S = 1.0, sse = 0.0, comp = 0.0;
-#pragma unroll 4
-  for (int t = 0; t < T; ++t) {
-    S = div_by_recip(__dadd_rn(P[t], S), den, rden);
-    const double e = __dadd_rn(__dmul_rn(K, S), -O[t]);
-    const double y = e * e - comp;
-    const double tt = sse + y;
-    comp = (tt - sse) - y;
-    sse = tt;
-  }
+#pragma unroll 8
+  for (int t = 0; t < T; ++t) hydro_step(PO[hydro_po_index(run, t, T)], K, den, rden, S, sse, comp);
   const double nse = 1.0 - sse / sst[run];
   ll[i] = glue_shape * log(nse > 0.0 ? nse : 0.0);
+}
+
+// sequential sweep (item i is chain j of run i): one warp per tile of 32 runs; the tile's series stream through a
+// two-stage shared-memory ring filled by 1-D bulk TMA copies of HYDRO_TT time steps (32 KB) each, so the recurrence
+// never waits on HBM latency -- what is left is the dependent fp64 chain of the backward-Euler step.
+constexpr int HYDRO_TT = 64;
+__global__ void __launch_bounds__(32) hb_hydro_runs_tma_kernel(const double* __restrict__ X, long long n, int ldx,
+                                                               const double2* __restrict__ PO,
+                                                               const double* __restrict__ sst, int T, double glue_shape,
+                                                               double* __restrict__ ll, unsigned* err) {
+  extern __shared__ __align__(16) unsigned char hy_smem[];
+  double2* ring = reinterpret_cast<double2*>(hy_smem);                                   // [2][HYDRO_TT][32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(hy_smem + 2 * HYDRO_TT * 32 * sizeof(double2));
+  const int lane = threadIdx.x;
+  const long long tile = blockIdx.x;
+  const long long i = tile * 32 + lane;                                                  // item == run
+  const double2* __restrict__ src = PO + tile * (long long)T * 32;
+  const int n_stages = (T + HYDRO_TT - 1) / HYDRO_TT;
+  if (lane == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncwarp();
+  auto issue = [&](int s) {
+    const int t0 = s * HYDRO_TT;
+    const int nt = (T - t0) < HYDRO_TT ? (T - t0) : HYDRO_TT;
+    const uint32_t bytes = (uint32_t)nt * 32u * (uint32_t)sizeof(double2);
+    mbar_expect_tx(&bars[s & 1], bytes);
+    tma_load_1d(ring + (size_t)(s & 1) * HYDRO_TT * 32, src + (long long)t0 * 32, bytes, &bars[s & 1]);
+  };
+  if (lane == 0) { issue(0); if (n_stages > 1) issue(1); }
+  const bool valid = i < n;
+  const double K = valid ? X[i * ldx] : 1.0;
+  const bool bad = valid && K < 0;
+  if (bad) atomicOr(err, HB_FLAG_TARGET_DOMAIN);
+  const double den = 1.0 + K * 1.0;
+  const double rden = __ddiv_rn(1.0, den);
+  double S = 1.0, sse = 0.0, comp = 0.0;
+  for (int s = 0; s < n_stages; ++s) {
+    mbar_wait(&bars[s & 1], (s >> 1) & 1);
+    const double2* __restrict__ buf = ring + (size_t)(s & 1) * HYDRO_TT * 32 + lane;
+    const int t0 = s * HYDRO_TT;
+    const int nt = (T - t0) < HYDRO_TT ? (T - t0) : HYDRO_TT;
+    if (nt == HYDRO_TT) {
+#pragma unroll 8
+      for (int t = 0; t < HYDRO_TT; ++t) hydro_step(buf[t * 32], K, den, rden, S, sse, comp);
+    } else {
+      for (int t = 0; t < nt; ++t) hydro_step(buf[t * 32], K, den, rden, S, sse, comp);
+    }
+    __syncwarp();                                                                        // every lane is done with the stage
+    if (lane == 0 && s + 2 < n_stages) issue(s + 2);
+  }
+  if (valid) {
+    const double nse = 1.0 - sse / sst[i];
+    ll[i] = bad ? NAN : glue_shape * log(nse > 0.0 ? nse : 0.0);
+  }
 }
 
 struct hydro_ctx {
@@ -462,8 +526,19 @@ int hydro_launch_items(void* ctx, const double* x, int64_t n, int d, int ldx, do
   auto* c = (hydro_ctx*)ctx;
   if (!c->sst_dev) return hydro_launch(ctx, x, n, d, ldx, ll, fx, stream);   // one series shared by all runs
   if (n <= 0) return HB_OK;
-  hb_hydro_items_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-      x, n, ldx, c->forcing_dev, c->obs_dev, c->sst_dev, c->T, c->T_pad, c->glue_shape, chain0, stride, nc, ll, c->err_dev);
+  const double2* po = reinterpret_cast<const double2*>(c->forcing_dev);
+  if (stride == nc && chain0 < nc && n == c->n_runs) {   // sequential sweep: item i is chain chain0 of run i
+    const size_t smem = 2 * HYDRO_TT * 32 * sizeof(double2) + 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+      if (cudaFuncSetAttribute(hb_hydro_runs_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return HB_ERR_CUDA;
+      attr_set = true;
+    }
+    hb_hydro_runs_tma_kernel<<<(unsigned)((n + 31) / 32), 32, smem, (cudaStream_t)stream>>>(x, n, ldx, po, c->sst_dev, c->T, c->glue_shape, ll, c->err_dev);
+  } else {
+    hb_hydro_items_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        x, n, ldx, po, c->sst_dev, c->T, c->glue_shape, chain0, stride, nc, ll, c->err_dev);
+  }
   return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
 }
 void hydro_destroy(void* ctx) {
@@ -506,11 +581,15 @@ int hb_hydro_init_batched(void** ctx, int d, int lik, const double* data, int64_
     if (data[i] < 0) { set_err(err, errlen, "Values of argument 'forcing' need to be >= zero!"); return HB_ERR_INVALID; }
   auto* c = new hydro_ctx();
   c->T = (int)T; c->T_pad = (int)((T + 1) & ~1LL); c->lik = lik; c->glue_shape = glue_shape; c->n_runs = n_runs; c->sst = 0;
-  std::vector<double> F((size_t)n_runs * c->T_pad, 0.0), O((size_t)n_runs * c->T_pad, 0.0), sst((size_t)n_runs);
+  const long long n_tiles = (n_runs + 31) / 32;
+  std::vector<double> F((size_t)n_tiles * 32 * T * 2, 0.0), sst((size_t)n_runs);   // PO[run / 32][t][run % 32] = {P, obs}
   for (long long r = 0; r < n_runs; ++r) {
     const double* o = obs + r * T;
-    memcpy(&F[(size_t)r * c->T_pad], data + r * T, sizeof(double) * T);
-    memcpy(&O[(size_t)r * c->T_pad], o, sizeof(double) * T);
+    const double* f = data + r * T;
+    for (int64_t i = 0; i < T; ++i) {
+      const size_t e = (((size_t)(r >> 5) * T + i) * 32 + (r & 31)) * 2;
+      F[e] = f[i]; F[e + 1] = o[i];
+    }
     long double s = 0;
     for (int64_t i = 0; i < T; ++i) s += o[i];
     s /= T;
@@ -522,10 +601,10 @@ int hb_hydro_init_batched(void** ctx, int d, int lik, const double* data, int64_
     for (int64_t i = 0; i < T; ++i) { const double e = o[i] - mo; q += (long double)(e * e); }
     sst[(size_t)r] = (double)q;
   }
-  bool ok = cudaMalloc(&c->forcing_dev, F.size() * 8) == cudaSuccess && cudaMalloc(&c->obs_dev, O.size() * 8) == cudaSuccess &&
+  c->obs_dev = nullptr;
+  bool ok = cudaMalloc(&c->forcing_dev, F.size() * 8) == cudaSuccess &&
             cudaMalloc(&c->sst_dev, sst.size() * 8) == cudaSuccess && cudaMalloc(&c->err_dev, sizeof(unsigned)) == cudaSuccess;
   ok = ok && cudaMemcpy(c->forcing_dev, F.data(), F.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
-       cudaMemcpy(c->obs_dev, O.data(), O.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
        cudaMemcpy(c->sst_dev, sst.data(), sst.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
        cudaMemset(c->err_dev, 0, sizeof(unsigned)) == cudaSuccess;
   if (!ok) { set_err(err, errlen, "cudaMalloc/cudaMemcpy failed for batched forcing/obs"); delete c; return HB_ERR_CUDA; }

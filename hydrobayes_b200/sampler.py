@@ -214,6 +214,37 @@ class Sampler:
         self._check(self.L.hb_rstat(self.h, _ptr(out)))
         return out
 
+    def rstat_runs(self) -> np.ndarray:
+        """R_stat of every independent run of a batched handle: [n_runs, d] (one device launch for all runs)."""
+        out = np.empty((max(self.cfg.n_runs, 1), self.cfg.d))
+        self._check(self.L.hb_rstat_runs(self.h, _ptr(out)))
+        return out
+
+    def run_to_convergence(self, threshold: float = 1.2, check_every: int = 10, hold: int = 3, first_check: int = 50):
+        """Runs until every independent run has max_k R_stat_k < threshold at `hold` consecutive checks (a plain first
+        crossing gives false early convergence when all chains are equally over-dispersed, SURVEY 8d metric 2), checked
+        every `check_every` stored generations from ind_out > first_check (R/dream.R:270).  Returns a dict with the
+        wall seconds, the generation every run converged at (0 = not converged within t) and the last R_stat."""
+        t0 = time.perf_counter()
+        nr = max(self.cfg.n_runs, 1)
+        streak = np.zeros(nr, np.int64); conv_gen = np.zeros(nr, np.int64)
+        done = self.run(max(first_check * self.cfg.thin, 1))
+        r = None
+        while True:
+            if self.ind_out() > first_check:
+                r = self.rstat_runs().max(axis=1)
+                ok = r < threshold                                   # NaN (degenerate run) never counts as converged
+                streak = np.where(ok, streak + 1, 0)
+                newly = (streak >= hold) & (conv_gen == 0)
+                conv_gen[newly] = done
+                if (conv_gen > 0).all():
+                    break
+            if done >= self.cfg.t:
+                break
+            done = self.run(check_every * self.cfg.thin)
+        return {"seconds": time.perf_counter() - t0, "generations": int(done), "converged_at": conv_gen,
+                "all_converged": bool((conv_gen > 0).all()), "R_stat_max": r}
+
 
 # ---------------------------------------------------------------------------------------------------------
 # prior_sample (R/internals.R:26-47) stays on the host, exactly as it would in the R driver

@@ -213,6 +213,9 @@ int hb_fetch_accept(hb_handle* h, uint8_t* accept);        /* [t-1][nct] if reco
 int hb_fetch_outliers(hb_handle* h, int64_t* n_pairs, int64_t* gen, int64_t* chain, int64_t cap);
 /* Gelman-Rubin of the stored chain so far, rows 1..ind_out (R/gelman_rubin.R:21-56 on chain[1:ind_out,1:d,]) */
 int hb_rstat(hb_handle* h, double* out_d);
+/* the same per independent run of a batched handle: out [n_runs][d] row-major, one launch for all runs.  This is the
+ * convergence monitor of BASELINE config 5 ("each run to R-hat < 1.2", SURVEY 8d metric 2) */
+int hb_rstat_runs(hb_handle* h, double* out_runs_d);
 int64_t hb_ind_out(const hb_handle* h);
 /* device time (ms) spent inside the generation loop so far and number of kernels launched by this library */
 int hb_get_timing(const hb_handle* h, double* loop_ms, int64_t* kernel_launches);

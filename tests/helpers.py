@@ -41,6 +41,23 @@ def hydro_data(T=3653, catchment=0):
     return P, obs
 
 
+def hydro_data_batch(T, n_catchments, first=0):
+    """hydro_data() for catchments first..first+n-1, simulated for all catchments at once: P [n, T], obs [n, T]."""
+    P = np.empty((n_catchments, T)); noise = np.empty((n_catchments, T))
+    for i in range(n_catchments):
+        rng = np.random.default_rng(20240101 + first + i)
+        u = rng.uniform(size=T)
+        P[i] = (u < 0.4) * rng.gamma(0.7, 8.0, size=T)
+        noise[i] = rng.normal(0, 0.5, size=T)
+    K = 0.1 + 0.8 * frac((first + np.arange(n_catchments)) * PHI)
+    S = np.ones(n_catchments)
+    Y = np.empty((n_catchments, T))
+    for t in range(T):
+        S = (P[:, t] + S) / (1 + K)
+        Y[:, t] = K * S
+    return P, Y + noise
+
+
 def run_device(cfg, target, x0, par_min=None, par_max=None, tape=None, forcing=None, obs=None, device=0,
                slice_generations=None):
     """Drives the C ABI through hydrobayes_b200.Sampler and returns the same dict layout as oracle.run()."""

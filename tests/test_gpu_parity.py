@@ -316,6 +316,40 @@ def test_batched_hydromodel_runs(hb, oracle, sweep):
         assert [(g, ch - r * nc) for g, ch in outl if r * nc <= ch < (r + 1) * nc] == ora["outlier"]
 
 
+def test_hydro_data_batch_matches_single():
+    P, O = H.hydro_data_batch(60, 3, first=2)
+    for i in range(3):
+        p1, o1 = H.hydro_data(T=60, catchment=2 + i)
+        np.testing.assert_array_equal(P[i], p1)
+        np.testing.assert_allclose(O[i], o1, rtol=1e-13)
+
+
+def test_rstat_runs_and_convergence_monitor(hb, oracle):
+    # per-run R_stat of a batched handle == R_stat (R/gelman_rubin.R:21-56) of each run's stored chain; the monitor stops
+    # when every run held max R_stat < 1.2 at three consecutive checks (SURVEY 8d metric 2)
+    n_runs, nc, T, t = 5, 10, 80, 400
+    P, O = H.hydro_data_batch(T, n_runs)
+    cfg = A.default_config(nc=nc, t=t, d=1, lik=31, glue_shape=50.0, prior=A.HB_PRIOR_UNIFORM, bound=A.HB_BOUND_BOUND,
+                           seed=77, sweep=A.HB_SWEEP_SEQUENTIAL, n_runs=n_runs)
+    x0 = np.concatenate([H.x0_hydro(nc) for _ in range(n_runs)])
+    from hydrobayes_b200 import Sampler
+    with Sampler(cfg, 0) as s:
+        s.set_bounds([0.01], [2.0])
+        s.set_target_batched("HydroModel", P, O)
+        s.set_initial(x0)
+        res = s.run_to_convergence(threshold=1.2, check_every=10, hold=3)
+        r_dev = s.rstat_runs()
+        n_out = s.ind_out()
+        chain = s.fetch_chain()
+    assert r_dev.shape == (n_runs, 1)
+    for r in range(n_runs):
+        r_ora = oracle.rstat(chain[:n_out, :1, r * nc:(r + 1) * nc])
+        np.testing.assert_allclose(r_dev[r], r_ora, rtol=1e-9)
+    assert res["generations"] <= t and res["seconds"] > 0
+    if res["all_converged"]:
+        assert (res["converged_at"] >= 50 + 3 * 10 - 10).all() and (res["R_stat_max"] < 1.2).all()
+
+
 def test_batched_tdist_runs_native(hb, oracle):
     n_runs, nc, d, t = 4, 16, 8, 100
     cfg = A.default_config(nc=nc, t=t, d=d, lik=2, seed=13, n_runs=n_runs, adapt=0.5, record_accept=1)
