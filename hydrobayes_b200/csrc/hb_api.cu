@@ -214,7 +214,9 @@ int initialise(hb_handle* h) {
   const int d = h->d, ldx = h->ldx;
   const double* Xl = h->X + h->chain0 * ldx;
   unsigned* errp = &h->ctrl->err;
-  CK(hb_launch_prior(Xl, ldx, d, nl, c.prior, h->pmin, h->pmax, h->lp_xp, errp, h->stream)); h->launches++;
+  if (c.prior == HB_PRIOR_NORMAL) CK(hb_launch_prior_normal(Xl, ldx, d, nl, h->prior_W, h->prior_mu, h->prior_const, h->lp_xp, errp, h->stream));
+  else CK(hb_launch_prior(Xl, ldx, d, nl, c.prior, h->pmin, h->pmax, h->lp_xp, errp, h->stream));
+  h->launches++;
   if (int rc = hb_target_launch(h, Xl, nl, h->chain0, 1)) return fail(h, rc, "target launch failed");
   h->launches++;
   CK(hb_launch_init_state(h->lp_xp, h->ll_raw, h->fx_xp, h->lp, h->ll, h->lpost, h->fx, h->lpost_hist, nl, errp, h->stream));
@@ -355,6 +357,15 @@ int hb_target_launch(hb_handle* h, const double* x, long long n, long long first
   return h->vt->launch(h->tctx, x, n, h->d, h->ldx, h->ll_raw, h->fx_xp, h->stream);
 }
 
+// prior = "normal": the proposal kernel leaves lp_xp = 0; the quadratic form runs as its own launch over XP
+int hb_prior_after_k1(hb_handle* h, long long n_items) {
+  if (h->cfg.prior != HB_PRIOR_NORMAL) return HB_OK;
+  if (cudaError_t e = hb_launch_prior_normal(h->XP, h->ldx, h->d, n_items, h->prior_W, h->prior_mu, h->prior_const, h->lp_xp,
+                                             &h->ctrl->err, h->stream); e != cudaSuccess) { h->err = cudaGetErrorString(e); return HB_ERR_CUDA; }
+  h->launches++;
+  return HB_OK;
+}
+
 int hb_fail(hb_handle* h, int code, const char* msg) { if (h) h->err = msg; return code; }
 
 namespace {
@@ -378,6 +389,7 @@ int run_generation(hb_handle* h, long long i) {
     prof_scope ps(h, "K1");
     CK(hb_launch_k1(p, tape_mode, h->sm_count, h->stream));
     ps.done();
+    if (int rc = hb_prior_after_k1(h, nl)) return rc;
     if (h->delta_mode) {   // barrier A, arrive: this rank's K1 of generation i has finished reading its replica
       hb_flag_peers fp; for (int r = 0; r < 8; ++r) fp.p[r] = h->flags_peer[r];
       CK(hb_launch_flag_signal(fp, 0, h->rank, h->world, (unsigned)i, h->stream));
@@ -531,7 +543,6 @@ int hb_create(const hb_config* cfg, int device, hb_handle** out) {
   }
   if (cfg->thin < 1 || cfg->update_interval < 1) return fail(h, HB_ERR_INVALID, "thin and updateInterval must be >= 1");
   if (cfg->psnooker > 0 && !cfg->past_sample) return fail(h, HB_ERR_INVALID, "psnooker > 0 can only be applied if past_sample == TRUE");
-  if (cfg->prior == HB_PRIOR_NORMAL) return fail(h, HB_ERR_UNSUPPORTED, "prior = 'normal' is not on the device path yet");
   if (cfg->d > 1024) return fail(h, HB_ERR_UNSUPPORTED, "d > 1024 is not supported on the device");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); return fail(h, HB_ERR_NO_DEVICE, "no CUDA device is available and there is no CPU fallback"); }
@@ -588,7 +599,7 @@ void hb_destroy(hb_handle* h) {
   void* ptrs[] = {h->X, h->Z, h->XP, h->id, h->lp_xp, h->ll_raw, h->fx_xp, h->lp, h->ll, h->lpost, h->fx, h->lpost_hist,
                   h->hist_x, h->hist_l, h->hist_fx, h->accept_rec, h->ctrl, h->shift, h->colsum, h->qsum, h->partials,
                   h->out_ar, h->out_cr, h->proxy, h->proxy_full, h->lpost_full, h->outl_dev, h->news_dev, h->rstat_dev,
-                  h->rstat_xm, h->rstat_ss, h->stage, h->pmin, h->pmax, h->gamma_tab, h->outl_tmp, h->outl_sorted, h->outl_thr,
+                  h->rstat_xm, h->rstat_ss, h->stage, h->pmin, h->pmax, h->prior_W, h->prior_mu, h->gamma_tab, h->outl_tmp, h->outl_sorted, h->outl_thr,
                   h->outl_count};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (void* p : h->tape_allocs) cudaFree(p);
@@ -614,8 +625,44 @@ int hb_set_bounds(hb_handle* h, const double* par_min, const double* par_max, in
   return HB_OK;
 }
 
-int hb_set_prior_normal(hb_handle* h, const double*, const double*) {
-  return fail(h, HB_ERR_UNSUPPORTED, "prior = 'normal' is not on the device path yet");
+// par.info$mu, par.info$cov for prior = "normal" (R/internals.R:58-59): chol(cov) and its inverse in long double on the host
+int hb_set_prior_normal(hb_handle* h, const double* mu, const double* cov_colmajor) {
+  if (!h) return HB_ERR_INVALID;
+  if (!mu || !cov_colmajor) return fail(h, HB_ERR_INVALID, "hb_set_prior_normal: mu and cov must both be given");
+  cudaSetDevice(h->device);
+  const int d = h->d;
+  std::vector<long double> C((size_t)d * d), Rm((size_t)d * d, 0.0L), Wi((size_t)d * d, 0.0L);
+  for (int i = 0; i < d; ++i) for (int j = 0; j < d; ++j) C[(size_t)i * d + j] = cov_colmajor[i + (size_t)d * j];
+  for (int j = 0; j < d; ++j) {                                  // upper Cholesky factor: cov = R^T R
+    long double s = C[(size_t)j * d + j];
+    for (int k = 0; k < j; ++k) s -= Rm[(size_t)k * d + j] * Rm[(size_t)k * d + j];
+    if (!(s > 0)) return fail(h, HB_ERR_INVALID, "'cov' is not positive definite (chol failed)");
+    const long double rjj = sqrtl(s);
+    Rm[(size_t)j * d + j] = rjj;
+    for (int i = j + 1; i < d; ++i) {
+      long double v = C[(size_t)j * d + i];
+      for (int k = 0; k < j; ++k) v -= Rm[(size_t)k * d + j] * Rm[(size_t)k * d + i];
+      Rm[(size_t)j * d + i] = v / rjj;
+    }
+  }
+  for (int j = 0; j < d; ++j) {                                  // W = R^-1 (upper triangular), column by column
+    Wi[(size_t)j * d + j] = 1.0L / Rm[(size_t)j * d + j];
+    for (int i = j - 1; i >= 0; --i) {
+      long double v = 0;
+      for (int k = i + 1; k <= j; ++k) v += Rm[(size_t)i * d + k] * Wi[(size_t)k * d + j];
+      Wi[(size_t)i * d + j] = -v / Rm[(size_t)i * d + i];
+    }
+  }
+  long double sl = 0;
+  for (int i = 0; i < d; ++i) sl += logl(Rm[(size_t)i * d + i]);
+  h->prior_const = -(double)sl - 0.5 * d * log(2.0 * 3.14159265358979323846);
+  std::vector<double> W((size_t)d * d);
+  for (size_t e = 0; e < W.size(); ++e) W[e] = (double)Wi[e];
+  if (!h->prior_W) { CK(dalloc(&h->prior_W, (size_t)d * d)); CK(dalloc(&h->prior_mu, (size_t)d)); }
+  CK(cudaMemcpy(h->prior_W, W.data(), sizeof(double) * W.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->prior_mu, mu, sizeof(double) * d, cudaMemcpyHostToDevice));
+  h->have_prior_normal = true;
+  return HB_OK;
 }
 
 int hb_set_obs(hb_handle* h, const double* obs, int64_t n) {
@@ -820,6 +867,7 @@ int hb_run(hb_handle* h, int64_t n_generations, int64_t* done_total) {
   if (!h->have_initial) return fail(h, HB_ERR_STATE, "hb_run: hb_set_initial has not been called");
   if (h->cfg.rng_mode == HB_RNG_TAPE && !h->have_tape) return fail(h, HB_ERR_STATE, "hb_run: rng_mode is TAPE but no tape was set");
   if (h->cfg.prior == HB_PRIOR_UNIFORM && !h->have_min_max) return fail(h, HB_ERR_INVALID, "prior = 'uniform' needs min and max");
+  if (h->cfg.prior == HB_PRIOR_NORMAL && !h->have_prior_normal) return fail(h, HB_ERR_INVALID, "prior = 'normal' needs mu and cov (hb_set_prior_normal)");
   if ((h->peer_mode || h->delta_mode) && !h->peers_ready) return fail(h, HB_ERR_STATE, "hb_run: HB_EXCHANGE_PEER needs hb_peer_export / hb_peer_import after hb_set_initial");
   if (!h->initialised) { if (int rc = initialise(h)) return rc; if (h->modeb) { if (int rc2 = hb_seq_initialise(h)) return rc2; } }
   long long last = h->gen + n_generations;

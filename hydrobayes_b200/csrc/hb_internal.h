@@ -55,6 +55,10 @@ struct hb_handle {
   void* flags_opened[8] = {};
 
   // bounds / prior
+  bool have_prior_normal = false;     // prior = "normal": dmvnorm(x, mu, cov, log = TRUE), R/internals.R:59
+  double* prior_W = nullptr;          // [d][d] row-major, W = chol(cov)^-1 (upper triangular)
+  double* prior_mu = nullptr;         // [d]
+  double prior_const = 0.0;           // -sum(log(diag(chol(cov)))) - d/2 log(2 pi)
   bool have_min_max = false;
   std::vector<double> pmin_h, pmax_h;
   double *pmin = nullptr, *pmax = nullptr;
@@ -119,6 +123,7 @@ struct hb_handle {
 hb_k1_params hb_make_k1(hb_handle* h, long long i, long long first, long long stride, long long n_items);
 hb_k3_params hb_make_k3(hb_handle* h, long long i, long long first, long long stride, long long n_items, bool store,
                         bool in_adapt, bool write_dx);
+int hb_prior_after_k1(hb_handle* h, long long n_items);
 int hb_target_launch(hb_handle* h, const double* x, long long n, long long first, long long stride);
 int hb_fail(hb_handle* h, int code, const char* msg);
 

@@ -640,6 +640,30 @@ __global__ void hb_prior_kernel(const double* X, int ldx, int d, long long n, in
   lp[j] = s;
 }
 
+// mvtnorm::dmvnorm(x, mu, cov, log = TRUE) (R/internals.R:59): z = (x - mu) W with W = chol(cov)^-1 upper triangular,
+// lp = -sum(log(diag(chol))) - d/2 log(2 pi) - 0.5 sum(z^2).  One warp per row; lane n owns output columns n, n+32, ...
+__global__ void hb_prior_normal_kernel(const double* __restrict__ X, int ldx, int d, long long n,
+                                       const double* __restrict__ W, const double* __restrict__ mu, double konst,
+                                       double* __restrict__ lp, unsigned* err) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const double* xr = X + row * (long long)ldx;
+  double rss = 0.0;
+  for (int nn = lane; nn < d; nn += 32) {
+    double z = 0.0;
+    for (int k = 0; k <= nn; ++k) z = fma(xr[k] - mu[k], W[k * d + nn], z);
+    rss = fma(z, z, rss);
+  }
+  rss = hb_warp_sum(rss);
+  if (lane == 0) {
+    double s = konst - 0.5 * rss;
+    if (!(s >= HB_FLOOR)) s = (s != s) ? s : HB_FLOOR;               // :65
+    if (!isfinite(s)) atomicOr(err, HB_FLAG_LP_NONFINITE);           // :67
+    lp[row] = s;
+  }
+}
+
 __global__ void hb_store_row_kernel(const double* X, int ldx, int d, long long n, const double* lp, const double* ll,
                                     const double* lpost, const double* fx, double* hist_x, double* hist_l,
                                     double* hist_fx) {
@@ -771,6 +795,13 @@ cudaError_t hb_launch_init_state(const double* lp_in, const double* ll_raw, cons
 cudaError_t hb_launch_prior(const double* X, int ldx, int d, long long n, int prior, const double* pmin,
                             const double* pmax, double* lp, unsigned* err, cudaStream_t st) {
   hb_prior_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(X, ldx, d, n, prior, pmin, pmax, lp, err);
+  return cudaGetLastError();
+}
+
+cudaError_t hb_launch_prior_normal(const double* X, int ldx, int d, long long n, const double* W, const double* mu,
+                                   double konst, double* lp, unsigned* err, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  hb_prior_normal_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(X, ldx, d, n, W, mu, konst, lp, err);
   return cudaGetLastError();
 }
 

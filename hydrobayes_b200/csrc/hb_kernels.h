@@ -173,6 +173,9 @@ cudaError_t hb_launch_init_state(const double* lp_in, const double* ll_raw, cons
                                  cudaStream_t st);
 cudaError_t hb_launch_prior(const double* X, int ldx, int d, long long n, int prior, const double* pmin,
                             const double* pmax, double* lp, unsigned* err, cudaStream_t st);
+// prior = "normal" (R/internals.R:59): lp[j] = konst - 0.5 * || (x_j - mu) W ||^2, floored (:65); one warp per row
+cudaError_t hb_launch_prior_normal(const double* X, int ldx, int d, long long n, const double* W, const double* mu,
+                                   double konst, double* lp, unsigned* err, cudaStream_t st);
 cudaError_t hb_launch_store_row(const double* X, int ldx, int d, long long n, const double* lp, const double* ll,
                                 const double* lpost, const double* fx, double* hist_x, double* hist_l, double* hist_fx,
                                 cudaStream_t st);

@@ -96,6 +96,7 @@ int hb_seq_generation(hb_handle* h, long long i) {
   if (c.sweep == HB_SWEEP_SYNCHRONOUS) {
     const hb_k1_params k1 = hb_make_k1(h, i, 0, 1, nct);
     SCK(hb_launch_k1(k1, tape_mode, h->sm_count, h->stream));
+    if (int rc = hb_prior_after_k1(h, nct)) return rc;
     if (int rc = hb_target_launch(h, h->XP, nct, 0, 1)) return hb_fail(h, rc, "target launch failed");
     const hb_k3_params k3 = hb_make_k3(h, i, 0, 1, nct, store, in_adapt, in_adapt);
     SCK(hb_launch_k3(k3, h->sm_count, nullptr, nullptr, h->stream));
@@ -114,6 +115,7 @@ int hb_seq_generation(hb_handle* h, long long i) {
     for (long long j = 0; j < nc; ++j) {                                           // R/dream.R:213
       const hb_k1_params k1 = hb_make_k1(h, i, j, nc, nr);
       SCK(hb_launch_k1(k1, tape_mode, h->sm_count, h->stream));
+      if (int rc = hb_prior_after_k1(h, nr)) return rc;
       if (int rc = hb_target_launch(h, h->XP, nr, j, nc)) return hb_fail(h, rc, "target launch failed");
       const hb_k3_params k3 = hb_make_k3(h, i, j, nc, nr, false, in_adapt, in_adapt);
       SCK(hb_launch_k3(k3, h->sm_count, nullptr, nullptr, h->stream));

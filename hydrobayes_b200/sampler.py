@@ -69,6 +69,13 @@ class Sampler:
             raise ValueError("min and max must have the same length")
         self._check(self.L.hb_set_bounds(self.h, _ptr(mn), _ptr(mx), int(mn.size)))
 
+    def set_prior_normal(self, mu, cov):
+        """par.info$mu / $cov of prior = "normal" (dmvnorm, R/internals.R:58-59)."""
+        d = self.cfg.d
+        m = np.ascontiguousarray(np.asarray(mu, np.float64).reshape(d))
+        c = np.asfortranarray(np.asarray(cov, np.float64).reshape(d, d))
+        self._check(self.L.hb_set_prior_normal(self.h, _ptr(m), _ptr(c)))
+
     def set_obs(self, obs):
         o = np.ascontiguousarray(np.asarray(obs, np.float64))
         self._check(self.L.hb_set_obs(self.h, _ptr(o), o.size))
@@ -322,6 +329,10 @@ def _drive(sweep, fun, extra, lik, par_info, nc, t, d, burnin, adapt, updateInte
     with Sampler(cfg, device) as s:
         if par_info.get("min") is not None and par_info.get("max") is not None:
             s.set_bounds(par_info["min"], par_info["max"])
+        if cfg.prior == A.HB_PRIOR_NORMAL:
+            if par_info.get("mu") is None or par_info.get("cov") is None:
+                raise ValueError("prior = 'normal' needs par.info$mu and par.info$cov")
+            s.set_prior_normal(par_info["mu"], par_info["cov"])
         if obs is not None:
             s.set_obs(obs)
         data = forcing if forcing is not None else (extra[0] if extra else None)

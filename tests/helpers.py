@@ -59,12 +59,14 @@ def hydro_data_batch(T, n_catchments, first=0):
 
 
 def run_device(cfg, target, x0, par_min=None, par_max=None, tape=None, forcing=None, obs=None, device=0,
-               slice_generations=None):
+               slice_generations=None, prior_mu=None, prior_cov=None):
     """Drives the C ABI through hydrobayes_b200.Sampler and returns the same dict layout as oracle.run()."""
     from hydrobayes_b200 import Sampler
     with Sampler(cfg, device) as s:
         if par_min is not None:
             s.set_bounds(par_min, par_max)
+        if prior_mu is not None:
+            s.set_prior_normal(prior_mu, prior_cov)
         if obs is not None:
             s.set_obs(obs)
         s.set_target(target, forcing)

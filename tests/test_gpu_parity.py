@@ -171,6 +171,42 @@ def test_replay_uniform_prior_unbounded_proposals(hb, oracle):
     assert np.isfinite(dev["chain"]).all()
 
 
+@pytest.mark.parametrize("d,nc", [(6, 24), (40, 64)])
+def test_replay_normal_prior(hb, oracle, d, nc):
+    # prior = "normal": dmvnorm(x, mu, cov, log = TRUE) with a correlated covariance (R/internals.R:58-59); the narrow
+    # (d = 6) and the wide (d = 40) kernels, sequential sweep included below
+    rs = np.random.RandomState(4)
+    Aq = rs.normal(size=(d, d)); cov = Aq @ Aq.T / d + np.eye(d); mu = rs.normal(size=d)
+    cfg = A.default_config(nc=nc, t=150, d=d, lik=2, seed=19, prior=A.HB_PRIOR_NORMAL, adapt=0.4)
+    dev, ora = _replay_case(oracle, cfg, "t_distribution", H.x0_tdist(nc, d), prior_mu=mu, prior_cov=cov)
+    H.assert_run_parity(dev, ora, rtol=1e-11)
+    assert np.abs(ora["chain"][:, d, :]).max() > 1.0           # the prior term is really there (column lp)
+    lp_dev = dev["chain"][-1, d, :]
+    from scipy.stats import multivariate_normal
+    x_last = dev["chain"][-1, :d, :].T
+    np.testing.assert_allclose(lp_dev, np.maximum(multivariate_normal(mu, cov).logpdf(x_last), oracle.log_xmin()), rtol=1e-10)   # floor, R/internals.R:65
+
+
+def test_seq_normal_prior(hb, oracle):
+    d, nc = 3, 8
+    cov = np.array([[2.0, 0.6, 0.1], [0.6, 1.0, -0.2], [0.1, -0.2, 0.5]]); mu = np.array([0.5, -1.0, 2.0])
+    cfg = A.default_config(nc=nc, t=120, d=d, lik=2, seed=23, prior=A.HB_PRIOR_NORMAL, sweep=A.HB_SWEEP_SEQUENTIAL, adapt=0.5)
+    dev, ora = _replay_case(oracle, cfg, "t_distribution", H.x0_tdist(nc, d), prior_mu=mu, prior_cov=cov)
+    H.assert_run_parity(dev, ora, rtol=1e-11)
+
+
+def test_normal_prior_needs_mu_cov(hb):
+    from hydrobayes_b200 import Sampler
+    cfg = A.default_config(nc=8, t=10, d=2, lik=2, prior=A.HB_PRIOR_NORMAL)
+    with Sampler(cfg, 0) as s:
+        s.set_target("t_distribution")
+        s.set_initial(H.x0_tdist(8, 2))
+        with pytest.raises(A.HbError, match="mu and cov"):
+            s.run(5)
+        with pytest.raises(A.HbError, match="positive definite"):
+            s.set_prior_normal([0, 0], [[1.0, 2.0], [2.0, 1.0]])
+
+
 def test_replay_forced_outliers(hb, oracle):
     # two chains start far out in the tail: check_outlier must flag and reset them (R/internals.R:71-87)
     x0 = H.x0_tdist(32, 4)
