@@ -135,7 +135,9 @@ def make_sampler(w, local, rank, world, torch):
     if "obs" in kw:
         s.set_obs(kw["obs"])
     s.set_target(w["target"], kw.get("forcing"))
-    if world > 1:
+    if world > 1 and cfg.exchange == 2:      # HB_EXCHANGE_DELTA: no NCCL communicator inside the library
+        s.comm_init(rank, world, None)
+    elif world > 1:
         import ctypes as C
         import torch.distributed as dist
         buf = C.create_string_buffer(128)
@@ -254,29 +256,45 @@ def quick_rate(name, local, torch, gens=200, warm=30):
     return out
 
 
-def convergence_c5(local, torch, n_runs=4096, nc=10, T=3653, t=3000):
+def convergence_c5(local, torch, n_runs=4096, nc=10, T=3653, t=3000, rank=0, world=1):
     """BASELINE config 5 on one GPU: n_runs independent HydroModel DREAM runs (distinct synthetic catchments, nc = 10
     chains each, dream() = sequential sweep), every run driven until R_stat < 1.2 held at 3 consecutive checks
     (metric 2 of SURVEY 8d: seconds to Gelman-Rubin R-hat < 1.2)."""
     import helpers as H
     from hydrobayes_b200 import Sampler, _abi as A
-    P, O = H.hydro_data_batch(T, n_runs)
+    # independent runs shard with no communication: rank r owns catchments [r*n/world, (r+1)*n/world); run_offset keys
+    # the Philox streams by the global run index, so the result does not depend on the number of GPUs
+    n_loc = n_runs // world
+    first = rank * n_loc
+    P, O = H.hydro_data_batch(T, n_loc, first=first)
     cfg = A.default_config(nc=nc, t=t, d=1, lik=31, glue_shape=50.0, prior=A.HB_PRIOR_UNIFORM, bound=A.HB_BOUND_BOUND,
-                           seed=1312, sweep=A.HB_SWEEP_SEQUENTIAL, n_runs=n_runs)
-    x0 = np.concatenate([H.x0_hydro(nc) for _ in range(n_runs)])
+                           seed=1312, sweep=A.HB_SWEEP_SEQUENTIAL, n_runs=n_loc, run_offset=first)
+    x0 = np.concatenate([H.x0_hydro(nc) for _ in range(n_loc)])
     with Sampler(cfg, local) as s:
         s.set_bounds([0.01], [2.0])
         s.set_target_batched("HydroModel", P, O)
         s.set_initial(x0)
-        torch.cuda.synchronize()
+        barrier_sync(torch, world)
+        t0 = time.perf_counter()
         res = s.run_to_convergence(threshold=1.2, check_every=10, hold=3)
+        barrier_sync(torch, world)
+        seconds = max_over_ranks(torch, world, time.perf_counter() - t0)
         ms, launches = s.timing()
     conv = res["converged_at"]
-    return {"workload": f"C5: {n_runs} independent HydroModel DREAM runs (dream(), nc={nc}, T={T}, lik=31), each to R-hat<1.2",
-            "seconds_to_rhat_below_1.2": res["seconds"], "all_converged": res["all_converged"],
-            "runs_converged": int((conv > 0).sum()), "generations_run": res["generations"],
+    n_conv = int((conv > 0).sum()); gens = res["generations"]
+    if world > 1:
+        import torch.distributed as dist
+        tt = torch.tensor([n_conv, gens], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        n_conv = int(tt[0].item()); gens_sum = tt[1].item()
+    else:
+        gens_sum = gens
+    return {"workload": f"C5: {n_runs} independent HydroModel DREAM runs (dream(), nc={nc}, T={T}, lik=31), each to R-hat<1.2"
+                        + (f", {n_loc} runs per GPU, no communication" if world > 1 else ""),
+            "seconds_to_rhat_below_1.2": seconds, "all_converged": n_conv == n_loc * world,
+            "runs_converged": n_conv, "generations_run": gens,
             "median_generations_to_converge": float(np.median(conv[conv > 0])) if (conv > 0).any() else None,
-            "value": n_runs * nc * (res["generations"] - 1) / res["seconds"], "unit": UNIT,
+            "value": n_loc * nc * (gens_sum - world) / seconds, "unit": UNIT,
             "device_loop_seconds": ms * 1e-3, "gpu_launches": launches,
             "rule": "max_k R_stat_k < 1.2 at 3 consecutive checks, every 10 stored generations from ind_out > 50"}
 
@@ -404,6 +422,13 @@ def main():
                            "call": "hydrobayes_b200.dream_parallel(...) full run incl. x0 upload and chain fetch"
                                    + (" (distributed=True: every rank uploads x0 and fetches the chain of its shard)" if world > 1 else "")}
         del res
+    if world > 1 and not args.no_extras and not args.quick:
+        try:
+            c5 = convergence_c5(local, torch, rank=rank, world=world)
+        except Exception as e:  # report, never hide
+            c5 = {"error": repr(e)}
+        if rank == 0:
+            line["other_workloads"] = {"C5": c5}
     if rank == 0 and world == 1 and not args.no_extras and not args.quick:
         cb, _ = cpu_baseline(w)
         line["cpu_baseline"] = cb

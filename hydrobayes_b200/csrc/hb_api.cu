@@ -154,9 +154,14 @@ int allocate(hb_handle* h) {
     CK(cudaMemsetAsync(h->X, 0, (size_t)nc * ldx * sizeof(double), h->stream));
   }
   if (c.past_sample) { CK(dalloc(&h->Z, (size_t)h->m_cap * ldx)); }
-  if (h->delta_mode) {   // flag words of the two generation barriers (written by the peers)
-    CK(cudaMalloc((void**)&h->flags, 64 * sizeof(unsigned)));
-    CK(cudaMemsetAsync(h->flags, 0, 64 * sizeof(unsigned), h->stream));
+  if (h->delta_mode) {   // arena mapped by the peers: barrier flags, all-reduce slots, all-gather area (no NCCL on this path)
+    h->arena_red_off = 256;
+    h->arena_red_bytes = (((size_t)(2 + c.nCR) * d + HB_MAX_NCR + 1) * 8 + 255) & ~(size_t)255;
+    h->arena_gather_off = h->arena_red_off + 2 * h->arena_red_bytes;
+    const size_t bytes = h->arena_gather_off + 2 * (size_t)nl * sizeof(double);
+    CK(cudaMalloc((void**)&h->arena, bytes));
+    CK(cudaMemsetAsync(h->arena, 0, bytes, h->stream));
+    h->flags = reinterpret_cast<unsigned*>(h->arena);
   }
   CK(dalloc(&h->XP, (size_t)nl * ldx));
   CK(cudaMemsetAsync(h->XP, 0, (size_t)nl * ldx * sizeof(double), h->stream));
@@ -252,7 +257,13 @@ int outlier_check(hb_handle* h, long long i) {
     ps.done();
   }
   const double* proxy_all = h->proxy;
-  if (h->world > 1) {
+  if (h->world > 1 && h->delta_mode) {
+    hb_arena_peers ap; for (int r = 0; r < 8; ++r) ap.p[r] = h->arena_peer[r];
+    CK(hb_launch_peer_allgather(ap, h->arena_gather_off, h->proxy, h->lpost, h->proxy_full, h->lpost_full, nl, h->rank, h->world,
+                                ++h->gather_seq, &h->ctrl->err, h->stream));
+    h->launches += 2;
+    proxy_all = h->proxy_full;
+  } else if (h->world > 1) {
     if (int rc = hb_nccl_allgather_f64(h->comm, h->proxy, h->proxy_full, (size_t)nl, h->stream, h->err)) return rc;
     if (int rc = hb_nccl_allgather_f64(h->comm, h->lpost, h->lpost_full, (size_t)nl, h->stream, h->err)) return rc;
     proxy_all = h->proxy_full;
@@ -423,11 +434,22 @@ int run_generation(hb_handle* h, long long i) {
     prof_scope ps(h, "FIN");
     if (h->world > 1) {
       f.phase = 0; CK(hb_launch_finalize(f, h->stream));
-      if (in_adapt) {
-        if (int rc = hb_nccl_allreduce_f64(h->comm, h->colsum, (size_t)2 * d, h->stream, h->err)) return rc;
-        if (int rc = hb_nccl_allreduce_f64(h->comm, h->qsum, (size_t)c.nCR * d, h->stream, h->err)) return rc;
+      if (h->delta_mode) {   // one fused all-reduce over peer memory, summed in rank order
+        hb_arena_peers ap; for (int r = 0; r < 8; ++r) ap.p[r] = h->arena_peer[r];
+        hb_peer_reduce_desc rd{};
+        rd.f64[0] = h->colsum; rd.n_f64[0] = in_adapt ? 2 * d : 0;
+        rd.f64[1] = h->qsum; rd.n_f64[1] = in_adapt ? c.nCR * d : 0;
+        rd.u64 = h->ctrl->n_id_gen; rd.n_u64 = HB_MAX_NCR + 1;
+        ++h->red_seq;
+        CK(hb_launch_peer_allreduce(ap, h->arena_red_off + (size_t)(h->red_seq & 1u) * h->arena_red_bytes, rd, h->rank, h->world,
+                                    h->red_seq, &h->ctrl->err, h->stream));
+      } else {
+        if (in_adapt) {
+          if (int rc = hb_nccl_allreduce_f64(h->comm, h->colsum, (size_t)2 * d, h->stream, h->err)) return rc;
+          if (int rc = hb_nccl_allreduce_f64(h->comm, h->qsum, (size_t)c.nCR * d, h->stream, h->err)) return rc;
+        }
+        if (int rc = hb_nccl_allreduce_u64(h->comm, h->ctrl->n_id_gen, HB_MAX_NCR + 1, h->stream, h->err)) return rc;
       }
-      if (int rc = hb_nccl_allreduce_u64(h->comm, h->ctrl->n_id_gen, HB_MAX_NCR + 1, h->stream, h->err)) return rc;
       f.phase = 1; CK(hb_launch_finalize(f, h->stream));
       ps.done(2);
     } else {
@@ -589,7 +611,7 @@ void hb_destroy(hb_handle* h) {
       if (h->peerX_opened[r]) cudaIpcCloseMemHandle(h->peerX_opened[r]);
       if (h->flags_opened[r]) cudaIpcCloseMemHandle(h->flags_opened[r]);
     }
-    cudaFree(h->flags);
+    cudaFree(h->arena);
   }
   if (h->peer_mode) {
     h->X = nullptr;
@@ -715,7 +737,13 @@ int hb_comm_init(hb_handle* h, int rank, int world, const void* id128) {
   if (h->nc % world) return fail(h, HB_ERR_INVALID, "nc must be divisible by the number of GPUs");
   if (h->cfg.sweep != HB_SWEEP_SYNCHRONOUS || h->cfg.n_runs > 1) return fail(h, HB_ERR_UNSUPPORTED, "only the synchronous single-population sweep shards across GPUs");
   cudaSetDevice(h->device);
-  if (world > 1) { if (int rc = hb_nccl_init(&h->comm, rank, world, id128, h->err)) return rc; }
+  const double t_begin = now_s();
+  // HB_EXCHANGE_DELTA needs no NCCL communicator: its barriers and small collectives run over peer-mapped memory
+  if (world > 1 && h->cfg.exchange != HB_EXCHANGE_DELTA) {
+    if (!id128) return fail(h, HB_ERR_INVALID, "hb_comm_init: this exchange mode needs the communicator id of hb_comm_unique_id");
+    if (int rc = hb_nccl_init(&h->comm, rank, world, id128, h->err)) return rc;
+    timing_note("nccl_init", now_s() - t_begin);
+  }
   h->rank = rank; h->world = world;
   h->n_local = h->nc / world; h->chain0 = rank * h->n_local;
   if (world > 1 && h->cfg.exchange == HB_EXCHANGE_DELTA) {
@@ -740,7 +768,7 @@ int hb_peer_export(hb_handle* h, void* out128) {
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   if (h->delta_mode) {
     CK(cudaIpcGetMemHandle(&hd[0], h->X));
-    CK(cudaIpcGetMemHandle(&hd[1], h->flags));
+    CK(cudaIpcGetMemHandle(&hd[1], h->arena));
     memcpy(out128, hd, 128);
     return HB_OK;
   }
@@ -754,6 +782,8 @@ int hb_peer_import(hb_handle* h, const void* all_handles) {
   if (!h || !all_handles) return HB_ERR_INVALID;
   if (!h->peer_mode && !h->delta_mode) return fail(h, HB_ERR_STATE, "hb_peer_import: the handle is not in HB_EXCHANGE_PEER / HB_EXCHANGE_DELTA mode");
   cudaSetDevice(h->device);
+  const double t_begin = now_s();
+  struct note_at_exit { double t0; ~note_at_exit() { timing_note("peer_import", now_s() - t0); } } note_guard{t_begin};
   const cudaIpcMemHandle_t* hd = (const cudaIpcMemHandle_t*)all_handles;
   if (h->delta_mode) {
     for (int r = 0; r < h->world; ++r) {
@@ -762,8 +792,9 @@ int hb_peer_import(hb_handle* h, const void* all_handles) {
       CK(cudaIpcOpenMemHandle(&px, hd[2 * r], cudaIpcMemLazyEnablePeerAccess));
       CK(cudaIpcOpenMemHandle(&pf, hd[2 * r + 1], cudaIpcMemLazyEnablePeerAccess));
       h->peerX_opened[r] = px; h->peerX[r] = (double*)px;
-      h->flags_opened[r] = pf; h->flags_peer[r] = (unsigned*)pf;
+      h->flags_opened[r] = pf; h->flags_peer[r] = (unsigned*)pf; h->arena_peer[r] = (unsigned char*)pf;
     }
+    h->arena_peer[h->rank] = h->arena;
     h->peers_ready = true;
     return HB_OK;
   }
@@ -882,6 +913,7 @@ int hb_run(hb_handle* h, int64_t n_generations, int64_t* done_total) {
   CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->loop_ms += ms;
   if (done_total) *done_total = h->gen;
+  timing_note("run (slice)", ms * 1e-3);
   return check_flags(h);
 }
 
@@ -931,7 +963,9 @@ int hb_fetch_chain_rows(hb_handle* h, int64_t row0, int64_t nrows, double* out) 
   const long long chunk = (long long)(half / per_chain);
   const long long n_chunks = (nl + chunk - 1) / chunk;
   unsigned hw = std::thread::hardware_concurrency();
-  int n_thr = total < ((size_t)32 << 20) ? 1 : (int)std::min<unsigned>(16u, hw > 2 ? hw - 1 : 1);
+  // the ranks of one node share the host cores: each takes its share of them
+  const unsigned share = (hw > 2 ? hw - 1 : 1) / (unsigned)std::max(1, h->world);
+  int n_thr = total < ((size_t)32 << 20) ? 1 : (int)std::min<unsigned>(16u, std::max(2u, share));
   // ready[k] = the DMA of chunk k has landed in pinned buffer k & 1 ; done[k] = copier threads finished with chunk k
   std::vector<std::atomic<int>> ready((size_t)n_chunks), done((size_t)n_chunks);
   for (auto& a : ready) a.store(0);

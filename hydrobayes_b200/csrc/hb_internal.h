@@ -50,7 +50,11 @@ struct hb_handle {
   bool delta_mode = false;
   double* peerX[8] = {};          // peer r's replica base (null for self)
   void* peerX_opened[8] = {};
-  unsigned* flags = nullptr;      // [2][8] local flag words, written by the peers: flags[which*8 + source rank]
+  unsigned char* arena = nullptr; // [flags 256 B | reduce slot x2 | gather area]; flags = first 64 words
+  unsigned char* arena_peer[8] = {};
+  size_t arena_red_off = 0, arena_red_bytes = 0, arena_gather_off = 0;
+  unsigned red_seq = 0, gather_seq = 0;
+  unsigned* flags = nullptr;      // [4][8] local flag words, written by the peers: flags[which*8 + source rank]
   unsigned* flags_peer[8] = {};   // peer r's flag array
   void* flags_opened[8] = {};
 

@@ -610,6 +610,82 @@ __global__ void hb_flag_wait_kernel(unsigned* flags, int which, int self, int wo
   }
 }
 
+// ---- small collectives over peer-mapped memory (HB_EXCHANGE_DELTA) ----------------------------------------------
+__device__ __forceinline__ void hb_flag_signal_all(hb_arena_peers peers, int which, int self, int world, unsigned value) {
+  const int r = threadIdx.x;
+  if (r < world && r != self && peers.p[r]) {
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned*>(reinterpret_cast<unsigned*>(peers.p[r]) + which * 8 + self) = value;
+  }
+}
+__device__ __forceinline__ void hb_flag_wait_all(const unsigned char* own, int which, int self, int world, unsigned value,
+                                                 unsigned* err) {
+  const int r = threadIdx.x;
+  if (r < world && r != self) {
+    const volatile unsigned* f = reinterpret_cast<const unsigned*>(own) + which * 8 + r;
+    long long spins = 0;
+    while ((int)(*f - value) < 0) {
+      __nanosleep(64);
+      if (++spins > 40000000LL) { atomicOr(err, HB_FLAG_PEER_TIMEOUT); break; }
+    }
+    __threadfence_system();
+  }
+}
+
+__global__ void hb_peer_allreduce_post_kernel(hb_arena_peers peers, size_t slot_off, hb_peer_reduce_desc d, int self,
+                                              int world, unsigned seq) {
+  double* slot = reinterpret_cast<double*>(peers.p[self] + slot_off);
+  int o = 0;
+  for (int v = 0; v < 2; ++v) { for (int e = threadIdx.x; e < d.n_f64[v]; e += blockDim.x) slot[o + e] = d.f64[v][e]; o += d.n_f64[v]; }
+  unsigned long long* us = reinterpret_cast<unsigned long long*>(slot + o);
+  for (int e = threadIdx.x; e < d.n_u64; e += blockDim.x) us[e] = d.u64[e];
+  __threadfence_system();
+  __syncthreads();
+  hb_flag_signal_all(peers, 2, self, world, seq);
+}
+__global__ void hb_peer_allreduce_finish_kernel(hb_arena_peers peers, size_t slot_off, hb_peer_reduce_desc d, int self,
+                                                int world, unsigned seq, unsigned* err) {
+  hb_flag_wait_all(peers.p[self], 2, self, world, seq, err);
+  __syncthreads();
+  int o = 0;
+  for (int v = 0; v < 2; ++v) {
+    for (int e = threadIdx.x; e < d.n_f64[v]; e += blockDim.x) {
+      double s = 0.0;
+      for (int r = 0; r < world; ++r) s += reinterpret_cast<const volatile double*>(peers.p[r] + slot_off)[o + e];   // rank order
+      d.f64[v][e] = s;
+    }
+    o += d.n_f64[v];
+  }
+  for (int e = threadIdx.x; e < d.n_u64; e += blockDim.x) {
+    unsigned long long s = 0;
+    for (int r = 0; r < world; ++r) s += reinterpret_cast<const volatile unsigned long long*>(peers.p[r] + slot_off + (size_t)o * 8)[e];
+    d.u64[e] = s;
+  }
+}
+
+__global__ void hb_peer_allgather_post_kernel(hb_arena_peers peers, size_t area_off, const double* a, const double* b,
+                                              long long n_local, int self, int world, unsigned seq, unsigned* done) {
+  double* area = reinterpret_cast<double*>(peers.p[self] + area_off);
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
+  for (long long e = tid; e < n_local; e += nt) { area[e] = a[e]; area[n_local + e] = b[e]; }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = atomicAdd(done, 1u) == gridDim.x - 1;     // the last block signals
+  __syncthreads();
+  if (last) { if (threadIdx.x == 0) *done = 0; __threadfence_system(); hb_flag_signal_all(peers, 3, self, world, seq); }
+}
+__global__ void hb_peer_allgather_finish_kernel(hb_arena_peers peers, size_t area_off, double* full_a, double* full_b,
+                                                long long n_local, int self, int world, unsigned seq, unsigned* err) {
+  hb_flag_wait_all(peers.p[self], 3, self, world, seq, err);              // every block waits for itself
+  __syncthreads();
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
+  for (int r = 0; r < world; ++r) {
+    const volatile double* area = reinterpret_cast<const volatile double*>(peers.p[r] + area_off);
+    for (long long e = tid; e < n_local; e += nt) { full_a[r * n_local + e] = area[e]; full_b[r * n_local + e] = area[n_local + e]; }
+  }
+}
+
 // ---- misc ------------------------------------------------------------------------------------------------
 __global__ void hb_init_state_kernel(const double* lp_in, const double* ll_raw, const double* fx_in, double* lp,
                                      double* ll, double* lpost, double* fx, double* hist_row, long long n,
@@ -760,6 +836,22 @@ cudaError_t hb_launch_outlier_reset_peer(double* Xlocal, hb_peer_ptrs peers, lon
   if (n_out <= 0) return cudaSuccess;
   hb_outlier_reset_peer_kernel<<<n_out, 128, 0, st>>>(Xlocal, peers, peer_nl, ldx, d, lpost, lpost_hist_row, lpost_src,
                                                       chain0, n_local, outl, news, n_out);
+  return cudaGetLastError();
+}
+
+cudaError_t hb_launch_peer_allreduce(hb_arena_peers peers, size_t slot_off, hb_peer_reduce_desc desc, int self, int world,
+                                     unsigned seq, unsigned* err, cudaStream_t st) {
+  hb_peer_allreduce_post_kernel<<<1, 256, 0, st>>>(peers, slot_off, desc, self, world, seq);
+  hb_peer_allreduce_finish_kernel<<<1, 256, 0, st>>>(peers, slot_off, desc, self, world, seq, err);
+  return cudaGetLastError();
+}
+cudaError_t hb_launch_peer_allgather(hb_arena_peers peers, size_t area_off, const double* local_a, const double* local_b,
+                                     double* full_a, double* full_b, long long n_local, int self, int world, unsigned seq,
+                                     unsigned* err, cudaStream_t st) {
+  unsigned* done = reinterpret_cast<unsigned*>(peers.p[self]) + 63;       // last word of the flag block: block counter
+  const int blocks = (int)((n_local + 1023) / 1024 < 64 ? (n_local + 1023) / 1024 : 64);
+  hb_peer_allgather_post_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, st>>>(peers, area_off, local_a, local_b, n_local, self, world, seq, done);
+  hb_peer_allgather_finish_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, st>>>(peers, area_off, full_a, full_b, n_local, self, world, seq, err);
   return cudaGetLastError();
 }
 

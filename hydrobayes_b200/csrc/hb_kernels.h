@@ -143,6 +143,22 @@ struct hb_flag_peers { unsigned* p[8]; };
 cudaError_t hb_launch_flag_signal(hb_flag_peers peers, int which, int self, int world, unsigned value, cudaStream_t st);
 cudaError_t hb_launch_flag_wait(unsigned* flags, int which, int self, int world, unsigned value, unsigned* err,
                                 cudaStream_t st);
+// HB_EXCHANGE_DELTA small collectives over peer-mapped memory (no NCCL on this path).  Every rank owns an "arena"
+// [flags 64 x u32 | reduce slot parity 0 | reduce slot parity 1 | gather area] that its peers map through CUDA IPC.
+//   all-reduce: post = copy the local vectors into the own reduce slot, then signal flag 2; finish = wait for every
+//   peer's flag, then sum the slots of all ranks IN RANK ORDER (deterministic, identical on every rank).
+//   all-gather: post = copy the local array into the own gather area, signal flag 3; finish = wait, then read every
+//   peer's area into the full-length local array.
+struct hb_arena_peers { unsigned char* p[8]; };
+struct hb_peer_reduce_desc {
+  double* f64[2]; int n_f64[2];           // two double vectors (colsum, qsum), summed as doubles
+  unsigned long long* u64; int n_u64;     // one integer vector (per-generation counters), summed as integers
+};
+cudaError_t hb_launch_peer_allreduce(hb_arena_peers peers, size_t slot_off, hb_peer_reduce_desc desc, int self, int world,
+                                     unsigned seq, unsigned* err, cudaStream_t st);
+cudaError_t hb_launch_peer_allgather(hb_arena_peers peers, size_t area_off, const double* local_a, const double* local_b,
+                                     double* full_a, double* full_b, long long n_local, int self, int world, unsigned seq,
+                                     unsigned* err, cudaStream_t st);
 cudaError_t hb_launch_outlier_reset_peer(double* Xlocal, hb_peer_ptrs peers, long long peer_nl, int ldx, int d,
                                          double* lpost, double* lpost_hist_row, const double* lpost_src,
                                          long long chain0, long long n_local, const int* outl, const int* news,

@@ -108,8 +108,10 @@ class Sampler:
         self._keep.append(keepalive)
         self._check(self.L.hb_set_tape(self.h, C.byref(tape_struct)))
 
-    def comm_init(self, rank: int, world: int, unique_id: bytes):
-        buf = C.create_string_buffer(unique_id, 128)
+    def comm_init(self, rank: int, world: int, unique_id: Optional[bytes] = None):
+        """unique_id: the 128-byte NCCL id of hb_comm_unique_id (not needed for HB_EXCHANGE_DELTA, which runs its
+        barriers and small collectives over peer-mapped memory)."""
+        buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
         self._check(self.L.hb_comm_init(self.h, rank, world, buf))
 
     def peer_setup(self, world: int, group=None):
@@ -338,7 +340,8 @@ def _drive(sweep, fun, extra, lik, par_info, nc, t, d, burnin, adapt, updateInte
         data = forcing if forcing is not None else (extra[0] if extra else None)
         s.set_target(fun, data)
         if world > 1:
-            s.comm_init(rank, world, broadcast_unique_id(lambda: _unique_id(s.L), rank))
+            uid = None if cfg.exchange == A.HB_EXCHANGE_DELTA else broadcast_unique_id(lambda: _unique_id(s.L), rank)
+            s.comm_init(rank, world, uid)
         x0 = prior_sample(par_info, d, n0, rng)   # same seed on every rank: every rank holds the whole initial population
         if x0.shape[0] != n0:
             raise ValueError(f"initial sample has {x0.shape[0]} rows, expected {n0}")
