@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <atomic>
 #include <chrono>
 #include <cstdlib>
@@ -103,6 +104,38 @@ void timing_note(const char* what, double seconds, double bytes = 0) {
   if (!on) return;
   if (bytes > 0) fprintf(stderr, "[hb timing] %-14s %8.1f ms  %6.2f GB  %6.1f GB/s\n", what, seconds * 1e3, bytes / 1e9, bytes / 1e9 / seconds);
   else fprintf(stderr, "[hb timing] %-14s %8.1f ms\n", what, seconds * 1e3);
+}
+
+// Pinned host ring of the upload / fetch pipelines.  cudaHostAlloc of 128 MB costs ~0.1 s, more than the transfer of a
+// typical initial population, so the ring is cached per process: a destroyed handle parks its ring here and the next
+// handle (the next dream() call of the same R / Python session) picks it up.  Freed when the library is unloaded.
+struct pin_cache_t {
+  std::mutex mu; void* p = nullptr; size_t bytes = 0;
+  ~pin_cache_t() { if (p) cudaFreeHost(p); }
+} g_pin_cache;
+int pin_acquire(hb_handle* h, size_t bytes) {
+  if (h->pin_bytes >= bytes) return HB_OK;
+  {
+    std::lock_guard<std::mutex> lk(g_pin_cache.mu);
+    if (g_pin_cache.p && g_pin_cache.bytes >= bytes) {
+      if (h->pin) cudaFreeHost(h->pin);
+      h->pin = g_pin_cache.p; h->pin_bytes = g_pin_cache.bytes; g_pin_cache.p = nullptr; g_pin_cache.bytes = 0;
+      return HB_OK;
+    }
+  }
+  if (h->pin) { cudaFreeHost(h->pin); h->pin = nullptr; h->pin_bytes = 0; }
+  CK(cudaHostAlloc((void**)&h->pin, bytes, cudaHostAllocDefault));
+  h->pin_bytes = bytes;
+  return HB_OK;
+}
+void pin_release(hb_handle* h) {
+  if (!h->pin) return;
+  std::lock_guard<std::mutex> lk(g_pin_cache.mu);
+  if (!g_pin_cache.p || g_pin_cache.bytes < h->pin_bytes) {
+    if (g_pin_cache.p) cudaFreeHost(g_pin_cache.p);
+    g_pin_cache.p = h->pin; g_pin_cache.bytes = h->pin_bytes;
+  } else cudaFreeHost(h->pin);
+  h->pin = nullptr; h->pin_bytes = 0;
 }
 
 struct prof_scope {
@@ -627,7 +660,7 @@ void hb_destroy(hb_handle* h) {
   for (void* p : h->tape_allocs) cudaFree(p);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
-  if (h->pin) cudaFreeHost(h->pin);
+  pin_release(h);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   timing_note("destroy", now_s() - t_begin);
@@ -795,6 +828,17 @@ int hb_peer_import(hb_handle* h, const void* all_handles) {
       h->flags_opened[r] = pf; h->flags_peer[r] = (unsigned*)pf; h->arena_peer[r] = (unsigned char*)pf;
     }
     h->arena_peer[h->rank] = h->arena;
+    if (h->initial_sharded) {   // complete the peers' replicas with this rank's rows (NVLink peer copies), then arrive at
+                                // barrier B with value 1; the first generation waits for every peer's arrival
+      const size_t off = (size_t)h->chain0 * h->ldx, bytes = (size_t)h->n_local * h->ldx * sizeof(double);
+      for (int q = 1; q < h->world; ++q) {
+        const int r = (h->rank + q) % h->world;
+        CK(cudaMemcpyAsync(h->peerX[r] + off, h->X + off, bytes, cudaMemcpyDefault, h->stream));
+      }
+      hb_flag_peers fp; for (int r = 0; r < 8; ++r) fp.p[r] = h->flags_peer[r];
+      CK(hb_launch_flag_signal(fp, 1, h->rank, h->world, 1u, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+    }
     h->peers_ready = true;
     return HB_OK;
   }
@@ -814,7 +858,7 @@ int hb_peer_import(hb_handle* h, const void* all_handles) {
 static int upload_pipelined(hb_handle* h, void* dst_dev, const void* src_host, size_t bytes) {
   const size_t want = std::min<size_t>((size_t)64 << 20, std::max<size_t>(bytes, 4096));
   if (bytes < ((size_t)16 << 20)) { CK(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, h->stream)); return HB_OK; }
-  if (h->pin_bytes < 2 * want) { if (h->pin) cudaFreeHost(h->pin); h->pin = nullptr; CK(cudaHostAlloc((void**)&h->pin, 2 * want, cudaHostAllocDefault)); h->pin_bytes = 2 * want; }
+  if (int rc = pin_acquire(h, 2 * ((size_t)64 << 20) > 2 * want ? 2 * ((size_t)64 << 20) : 2 * want)) return rc;
   const size_t half = h->pin_bytes / 2;
   const size_t n_chunks = (bytes + half - 1) / half;
   unsigned hw = std::thread::hardware_concurrency();
@@ -851,13 +895,19 @@ static int set_initial_impl(hb_handle* h, const double* x0, bool row_major) {
   const double t_up = now_s();
   const long long m0 = h->modeb ? h->nct : h->m0, nc = h->modeb ? h->nct : h->nc;
   const int d = h->d, ldx = h->ldx;
+  // HB_EXCHANGE_DELTA, numpy layout, no archive: every rank uploads only the rows of ITS chains over PCIe; the other
+  // (G-1)/G of the replica arrives over NVLink in hb_peer_import (each rank copies its shard into every peer's X)
+  const bool shard_upload = h->delta_mode && h->world > 1 && row_major && !h->Z && m0 == nc;
+  h->initial_sharded = shard_upload;
+  const long long up_row0 = shard_upload ? h->chain0 : 0, up_rows = shard_upload ? h->n_local : m0;
   double* tmp = nullptr;
-  CK(dalloc(&tmp, (size_t)m0 * d));
-  if (int rc = upload_pipelined(h, tmp, x0, sizeof(double) * (size_t)m0 * d)) { cudaFree(tmp); return rc; }
+  CK(dalloc(&tmp, (size_t)up_rows * d));
+  if (int rc = upload_pipelined(h, tmp, x0 + (size_t)up_row0 * d, sizeof(double) * (size_t)up_rows * d)) { cudaFree(tmp); return rc; }
   // xt <- z[(m0-nc+1):m0, ]  (R/dream_parallel.R:213)
   if (row_major) {   // rows are already contiguous: strided device copies add the ldx padding
     const size_t sp = sizeof(double) * d, dp = sizeof(double) * ldx;
     if (h->peer_mode) CK(cudaMemcpy2DAsync(h->Xbuf[0], dp, tmp + (m0 - nc + h->chain0) * d, sp, sp, (size_t)h->n_local, cudaMemcpyDeviceToDevice, h->stream));
+    else if (shard_upload) CK(cudaMemcpy2DAsync(h->X + h->chain0 * ldx, dp, tmp, sp, sp, (size_t)h->n_local, cudaMemcpyDeviceToDevice, h->stream));
     else CK(cudaMemcpy2DAsync(h->X, dp, tmp + (m0 - nc) * d, sp, sp, (size_t)nc, cudaMemcpyDeviceToDevice, h->stream));
     if (h->Z) CK(cudaMemcpy2DAsync(h->Z, dp, tmp, sp, sp, (size_t)m0, cudaMemcpyDeviceToDevice, h->stream));
   } else {
@@ -874,7 +924,7 @@ static int set_initial_impl(hb_handle* h, const double* x0, bool row_major) {
   CK(cudaStreamSynchronize(h->stream));
   cudaFree(tmp);
   h->have_initial = true;
-  timing_note("set_initial", now_s() - t_up, sizeof(double) * (double)m0 * d);
+  timing_note("set_initial", now_s() - t_up, sizeof(double) * (double)up_rows * d);
   return HB_OK;
 }
 
@@ -900,7 +950,12 @@ int hb_run(hb_handle* h, int64_t n_generations, int64_t* done_total) {
   if (h->cfg.prior == HB_PRIOR_UNIFORM && !h->have_min_max) return fail(h, HB_ERR_INVALID, "prior = 'uniform' needs min and max");
   if (h->cfg.prior == HB_PRIOR_NORMAL && !h->have_prior_normal) return fail(h, HB_ERR_INVALID, "prior = 'normal' needs mu and cov (hb_set_prior_normal)");
   if ((h->peer_mode || h->delta_mode) && !h->peers_ready) return fail(h, HB_ERR_STATE, "hb_run: HB_EXCHANGE_PEER needs hb_peer_export / hb_peer_import after hb_set_initial");
-  if (!h->initialised) { if (int rc = initialise(h)) return rc; if (h->modeb) { if (int rc2 = hb_seq_initialise(h)) return rc2; } }
+  if (!h->initialised) {
+    if (h->initial_sharded)   // every peer has copied its shard of the initial population into this replica
+      CK(hb_launch_flag_wait(h->flags, 1, h->rank, h->world, 1u, &h->ctrl->err, h->stream));
+    if (int rc = initialise(h)) return rc;
+    if (h->modeb) { if (int rc2 = hb_seq_initialise(h)) return rc2; }
+  }
   long long last = h->gen + n_generations;
   if (last > h->t) last = h->t;
   CK(cudaEventRecord(h->ev0, h->stream));
@@ -958,7 +1013,7 @@ int hb_fetch_chain_rows(hb_handle* h, int64_t row0, int64_t nrows, double* out) 
   size_t want = std::min<size_t>((size_t)64 << 20, total);
   if (want < per_chain) want = per_chain;
   if (h->stage_bytes < 2 * want) { if (h->stage) cudaFree(h->stage); h->stage = nullptr; CK(cudaMalloc((void**)&h->stage, 2 * want)); h->stage_bytes = 2 * want; }
-  if (h->pin_bytes < 2 * want) { if (h->pin) cudaFreeHost(h->pin); h->pin = nullptr; CK(cudaHostAlloc((void**)&h->pin, 2 * want, cudaHostAllocDefault)); h->pin_bytes = 2 * want; }
+  if (int rc = pin_acquire(h, 2 * ((size_t)64 << 20) > 2 * want ? 2 * ((size_t)64 << 20) : 2 * want)) return rc;
   const size_t half = std::min(h->stage_bytes, h->pin_bytes) / 2;
   const long long chunk = (long long)(half / per_chain);
   const long long n_chunks = (nl + chunk - 1) / chunk;

@@ -48,6 +48,7 @@ struct hb_handle {
   // peers' replicas (posted NVLink stores).  Two flag barriers per generation order the pushes against the proposal
   // kernel's reads: A = "my K1 of generation i has finished reading", B = "my pushes of generation i have landed".
   bool delta_mode = false;
+  bool initial_sharded = false;   // set_initial uploaded this rank's rows only; peer_import completes the replicas
   double* peerX[8] = {};          // peer r's replica base (null for self)
   void* peerX_opened[8] = {};
   unsigned char* arena = nullptr; // [flags 256 B | reduce slot x2 | gather area]; flags = first 64 words
