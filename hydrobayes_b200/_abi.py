@@ -133,6 +133,7 @@ def lib() -> C.CDLL:
         "hb_last_error": ([hp], cp),
         "hb_set_bounds": ([hp, _dp, _dp, C.c_int], C.c_int),
         "hb_set_prior_normal": ([hp, _dp, _dp], C.c_int),
+        "hb_set_lik_args": ([hp, C.c_char_p, _dp, C.c_int64, C.c_char_p], C.c_int),
         "hb_set_obs": ([hp, _dp, C.c_int64], C.c_int),
         "hb_set_target": ([hp, cp, _dp, _i64p, C.c_int], C.c_int),
         "hb_set_target_batched": ([hp, cp, _dp, C.c_int64, _dp, C.c_int64], C.c_int),
@@ -178,7 +179,7 @@ def lib() -> C.CDLL:
 
 EXPORTED_SYMBOLS = [
     "hb_register_target", "hb_target_registered", "hb_config_default", "hb_device_count", "hb_create", "hb_destroy",
-    "hb_last_error", "hb_set_bounds", "hb_set_prior_normal", "hb_set_obs", "hb_set_target", "hb_set_target_batched",
+    "hb_last_error", "hb_set_bounds", "hb_set_prior_normal", "hb_set_lik_args", "hb_set_obs", "hb_set_target", "hb_set_target_batched",
     "hb_set_initial", "hb_set_initial_rows", "hb_set_tape", "hb_comm_unique_id", "hb_comm_init", "hb_peer_export", "hb_peer_import", "hb_run", "hb_sync", "hb_out_dims",
     "hb_fetch_chain", "hb_fetch_chain_rows", "hb_fetch_fx", "hb_fetch_ar", "hb_fetch_cr", "hb_fetch_rstat",
     "hb_fetch_state", "hb_fetch_accept", "hb_fetch_outliers", "hb_rstat", "hb_rstat_runs", "hb_ind_out", "hb_get_timing", "hb_profile",

@@ -252,8 +252,8 @@ int initialise(hb_handle* h) {
   const int d = h->d, ldx = h->ldx;
   const double* Xl = h->X + h->chain0 * ldx;
   unsigned* errp = &h->ctrl->err;
-  if (c.prior == HB_PRIOR_NORMAL) CK(hb_launch_prior_normal(Xl, ldx, d, nl, h->prior_W, h->prior_mu, h->prior_const, h->lp_xp, errp, h->stream));
-  else CK(hb_launch_prior(Xl, ldx, d, nl, c.prior, h->pmin, h->pmax, h->lp_xp, errp, h->stream));
+  if (c.prior == HB_PRIOR_NORMAL && c.lik != 22) CK(hb_launch_prior_normal(Xl, ldx, d, nl, h->prior_W, h->prior_mu, h->prior_const, h->lp_xp, errp, h->stream));
+  else CK(hb_launch_prior(Xl, ldx, d, nl, c.lik == 22 ? HB_PRIOR_FLAT : c.prior, h->pmin, h->pmax, h->lp_xp, errp, h->stream));
   h->launches++;
   if (int rc = hb_target_launch(h, Xl, nl, h->chain0, 1)) return fail(h, rc, "target launch failed");
   h->launches++;
@@ -360,7 +360,8 @@ hb_k1_params hb_make_k1(hb_handle* h, long long i, long long first, long long st
   p.n_runs = h->cfg.n_runs; p.gchain0 = (long long)c.run_offset * h->nc;
   p.d = h->d; p.ldx = h->ldx; p.delta = c.delta; p.nCR = c.nCR; p.c_val = c.c_val; p.c_star = c.c_star; p.p_g = c.p_g;
   p.beta0 = c.beta0; p.psnooker = c.psnooker; p.past_sample = c.past_sample;
-  p.bound = h->have_min_max ? c.bound : 0; p.prior = c.prior; p.pmin = h->pmin; p.pmax = h->pmax;
+  p.bound = h->have_min_max ? c.bound : 0; p.prior = (c.lik == 22) ? HB_PRIOR_FLAT : c.prior;   // prior_pdf: lik == 22 -> 0, R/internals.R:50-51
+  p.pmin = h->pmin; p.pmax = h->pmax;
   p.seed = c.seed; p.gen = (uint32_t)i; p.tape = h->tape; p.tape_g = i - 2; p.gamma_tab = h->gamma_tab;
   p.n_peers = h->peer_mode ? h->world : 1; p.peer_nl = h->n_local;
   for (int r = 0; r < 8; ++r) p.peer[r] = h->peer_mode ? h->peer_ptr[h->cur][r] : nullptr;
@@ -390,7 +391,7 @@ hb_k3_params hb_make_k3(hb_handle* h, long long i, long long first, long long st
   p.state0 = h->chain0; p.gchain0 = (long long)c.run_offset * h->nc;
   if (h->delta_mode) { p.n_push = h->world; for (int r = 0; r < 8; ++r) p.push[r] = h->peerX[r]; }
   p.d = d; p.ldx = h->ldx; p.nCR = c.nCR;
-  p.adapt = in_adapt; p.write_dx = write_dx; p.seed = c.seed; p.gen = (uint32_t)i;
+  p.adapt = in_adapt; p.write_dx = write_dx; p.lik22 = (c.lik == 22); p.seed = c.seed; p.gen = (uint32_t)i;
   p.u_accept = (c.rng_mode == HB_RNG_TAPE) ? h->tape.u_accept + (size_t)(i - 2) * h->tape.nct : nullptr;
   return p;
 }
@@ -403,7 +404,7 @@ int hb_target_launch(hb_handle* h, const double* x, long long n, long long first
 
 // prior = "normal": the proposal kernel leaves lp_xp = 0; the quadratic form runs as its own launch over XP
 int hb_prior_after_k1(hb_handle* h, long long n_items) {
-  if (h->cfg.prior != HB_PRIOR_NORMAL) return HB_OK;
+  if (h->cfg.prior != HB_PRIOR_NORMAL || h->cfg.lik == 22) return HB_OK;
   if (cudaError_t e = hb_launch_prior_normal(h->XP, h->ldx, h->d, n_items, h->prior_W, h->prior_mu, h->prior_const, h->lp_xp,
                                              &h->ctrl->err, h->stream); e != cudaSuccess) { h->err = cudaGetErrorString(e); return HB_ERR_CUDA; }
   h->launches++;
@@ -592,10 +593,10 @@ int hb_create(const hb_config* cfg, int device, hb_handle** out) {
   if (cfg->mt > 1) return fail(h, HB_ERR_UNSUPPORTED, "mt > 1 (MT-DREAM) is not on the device path");
   if ((cfg->mt > 1 || cfg->psnooker > 0) && (cfg->lik == 21 || cfg->lik == 22))
     return fail(h, HB_ERR_INVALID, "ABC method cannot be combined with MT-DREAM or snooker updating, see Sadegh and Vrugt (2014), WRR!");
-  if (cfg->lik != 1 && cfg->lik != 2 && cfg->lik != 31) {
-    if (cfg->lik == 21 || cfg->lik == 22 || cfg->lik == 99) return fail(h, HB_ERR_UNSUPPORTED, "lik = %d needs an R closure (abc_rho / lik_fun) and stays off the device path", cfg->lik);
+  if (cfg->lik != 1 && cfg->lik != 2 && cfg->lik != 31 && cfg->lik != 21 && cfg->lik != 22 && cfg->lik != 99)
     return fail(h, HB_ERR_INVALID, "Argument 'lik' has to be one of {1,2,21,22}!");
-  }
+  if ((cfg->lik == 21 || cfg->lik == 22 || cfg->lik == 99) && cfg->n_runs > 1)
+    return fail(h, HB_ERR_UNSUPPORTED, "batched independent runs support lik = 1, 2 and 31");
   if (cfg->thin < 1 || cfg->update_interval < 1) return fail(h, HB_ERR_INVALID, "thin and updateInterval must be >= 1");
   if (cfg->psnooker > 0 && !cfg->past_sample) return fail(h, HB_ERR_INVALID, "psnooker > 0 can only be applied if past_sample == TRUE");
   if (cfg->d > 1024) return fail(h, HB_ERR_UNSUPPORTED, "d > 1024 is not supported on the device");
@@ -720,6 +721,20 @@ int hb_set_prior_normal(hb_handle* h, const double* mu, const double* cov_colmaj
   return HB_OK;
 }
 
+int hb_set_lik_args(hb_handle* h, const char* abc_rho, const double* abc_e, int64_t n_abc_e, const char* lik_fun) {
+  if (!h) return HB_ERR_INVALID;
+  if (abc_rho && strcmp(abc_rho, "abc_distfun") != 0)
+    return fail(h, HB_ERR_UNKNOWN_TARGET, "object '%s' of mode 'function' was not found in the device registry of abc_rho functions (registered: abc_distfun)", abc_rho);
+  if (lik_fun && strcmp(lik_fun, "fun_lik") != 0)
+    return fail(h, HB_ERR_UNKNOWN_TARGET, "object '%s' of mode 'function' was not found in the device registry of lik_fun functions (registered: fun_lik)", lik_fun);
+  if (abc_e && n_abc_e < 1) return fail(h, HB_ERR_INVALID, "abc_e must not be empty");
+  h->abc_rho = abc_rho ? abc_rho : "";
+  h->lik_fun = lik_fun ? lik_fun : "";
+  h->abc_e_h.clear();
+  if (abc_e) h->abc_e_h.assign(abc_e, abc_e + n_abc_e);
+  return HB_OK;
+}
+
 int hb_set_obs(hb_handle* h, const double* obs, int64_t n) {
   if (!h || !obs || n < 1) return fail(h, HB_ERR_INVALID, "hb_set_obs: bad arguments");
   h->obs_h.assign(obs, obs + n);
@@ -738,6 +753,16 @@ int hb_set_target(hb_handle* h, const char* name, const double* data, const int6
                           (int64_t)h->obs_h.size(), h->cfg.glue_shape, err, (int)sizeof err);
   if (rc != HB_OK) return fail(h, rc, "%s", err[0] ? err : "target init failed");
   h->vt = vt; h->tctx = ctx; h->target_name = name; h->target_is_hydro = (h->target_name == "HydroModel");
+  const int lik = h->cfg.lik;
+  if (lik == 21 || lik == 22 || lik == 99) {   // the closures calc_ll would get() by name (R/internals.R:10,12,16)
+    if (!h->target_is_hydro) return fail(h, HB_ERR_UNSUPPORTED, "lik = %d is a device epilogue of HydroModel only", lik);
+    if (lik == 99) {
+      if (h->lik_fun.empty()) return fail(h, HB_ERR_INVALID, "lik = 99 needs lik_fun (hb_set_lik_args)");
+    } else {
+      if (h->abc_rho.empty() || h->abc_e_h.empty()) return fail(h, HB_ERR_INVALID, "lik = %d needs abc_rho and abc_e (hb_set_lik_args)", lik);
+      if (int rc2 = hb_hydro_set_abc(ctx, h->abc_e_h.data(), (int64_t)h->abc_e_h.size(), err, (int)sizeof err)) return fail(h, rc2, "%s", err);
+    }
+  }
   return HB_OK;
 }
 

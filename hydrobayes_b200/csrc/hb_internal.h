@@ -11,6 +11,7 @@
 
 const hb_target_vtable* hb_find_target(const char* name);
 unsigned hb_hydro_poll_err(void* ctx);
+int hb_hydro_set_abc(void* ctx, const double* abc_e, int64_t n_e, char* err, int errlen);
 
 struct hb_nccl;  // hb_comm.cu
 
@@ -59,6 +60,9 @@ struct hb_handle {
   unsigned* flags_peer[8] = {};   // peer r's flag array
   void* flags_opened[8] = {};
 
+  // likelihood closures named by the R call: abc_rho / abc_e (lik 21, 22), lik_fun (lik 99)
+  std::string abc_rho, lik_fun;
+  std::vector<double> abc_e_h;
   // bounds / prior
   bool have_prior_normal = false;     // prior = "normal": dmvnorm(x, mu, cov, log = TRUE), R/internals.R:59
   double* prior_W = nullptr;          // [d][d] row-major, W = chol(cov)^-1 (upper triangular)

@@ -81,6 +81,7 @@ struct hb_k3_params {
   int adapt;              // generation is inside the adaptation period: accumulate std / jump statistics
   // HB_EXCHANGE_DELTA: accepted rows are also stored into the peers' replicas of X (NVLink posted writes); null = off
   double* push[8]; int n_push;
+  int lik22;              // lik == 22: deterministic ABC acceptance rule (R/internals.R:222-225), no uniform drawn
   int write_dx;           // per-run statistics path: overwrite XP[item] with the realised jump dx (0 if rejected)
   uint64_t seed;
   uint32_t gen;

@@ -308,15 +308,23 @@ __device__ __forceinline__ double div_by_recip(double a, double b, double y) {
 
 // One chain per thread.  P and obs (T_pad doubles each, T_pad even so that the byte count is a multiple of 16) are
 // staged once per CTA.  Per step (R/test_HydroModel.R:30-32): S = (P_i*Dt + S)/(1 + K*Dt), Y_i = K*S with Dt = 1, a
-// true IEEE division.  lik == 31 (R/internals.R:13-14): glue_shape*log(max(1 - sse/sst, 0)); sse is Kahan-summed.
+// true IEEE division.  The likelihood flag is folded into the sweep as an epilogue (calc_ll, R/internals.R:3-23):
+//   31  glue_shape*log(max(1 - sse/sst, 0))                                   (:13-14)   sse Kahan-summed
+//   21  -m/2 log(2 pi) - sum(log(abc_e)) - 0.5 sum((abc_rho(sim,obs)/abc_e)^2)  (:8-10)  abc_rho = "abc_distfun" = |sim-obs|
+//   22  min(abc_e - abc_rho(sim,obs))                                         (:11-12)
+//   99  lik_fun(sim, obs), lik_fun = "fun_lik" = -n/2 log(sum((sim-obs)^2))    (:15-16; examples/script_examples.R:503-507)
+// EVEC: abc_e is a vector of length T (staged as a third series) instead of a recycled scalar.
+template <int LIK, bool EVEC>
 __global__ void __launch_bounds__(256) hb_hydro_kernel(const double* __restrict__ X, long long n, int ldx,
                                                        const double* __restrict__ forcing,
-                                                       const double* __restrict__ obs, int T, int T_pad, double sst,
-                                                       double glue_shape, double* __restrict__ ll, unsigned* err) {
+                                                       const double* __restrict__ obs, const double* __restrict__ abc_e,
+                                                       int T, int T_pad, double sst, double glue_shape, double e_scalar,
+                                                       double konst, double* __restrict__ ll, unsigned* err) {
   extern __shared__ __align__(16) double sm[];
   __shared__ __align__(8) uint64_t bar;
   double* sP = sm;
   double* sO = sm + T_pad;
+  double* sE = sm + 2 * T_pad;
   const uint32_t bytes = (uint32_t)T_pad * 8u;
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
@@ -324,9 +332,10 @@ __global__ void __launch_bounds__(256) hb_hydro_kernel(const double* __restrict_
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    mbar_expect_tx(&bar, 2 * bytes);
+    mbar_expect_tx(&bar, (EVEC ? 3 : 2) * bytes);
     tma_load_1d(sP, forcing, bytes, &bar);
     tma_load_1d(sO, obs, bytes, &bar);
+    if (EVEC) tma_load_1d(sE, abc_e, bytes, &bar);
   }
   mbar_wait(&bar, 0);
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -335,18 +344,28 @@ __global__ void __launch_bounds__(256) hb_hydro_kernel(const double* __restrict_
   if (K < 0) { atomicOr(err, HB_FLAG_TARGET_DOMAIN); ll[j] = NAN; return; }   // R/test_HydroModel.R:18-19
   const double den = 1.0 + K * 1.0;
   const double rden = __ddiv_rn(1.0, den);
-  double S = 1.0, sse = 0.0, comp = 0.0;
+  double S = 1.0, sse = 0.0, comp = 0.0, vmin = INFINITY;
 #pragma unroll 4
   for (int i = 0; i < T; ++i) {
     S = div_by_recip(__dadd_rn(sP[i], S), den, rden);         // (forcing[i]*Dt + S0) / (1 + param*Dt), Dt = 1
     const double e = __dadd_rn(__dmul_rn(K, S), -sO[i]);      // Y[i] - obs[i]
-    const double y = e * e - comp;
-    const double t = sse + y;
-    comp = (t - sse) - y;
-    sse = t;
+    if (LIK == 22) {
+      const double v = (EVEC ? sE[i] : e_scalar) - fabs(e);   // abc_e - rho
+      if (v < vmin || v != v) vmin = v;
+    } else {
+      double q;
+      if (LIK == 21) { const double r = __ddiv_rn(fabs(e), EVEC ? sE[i] : e_scalar); q = __dmul_rn(r, r); }   // (rho/abc_e)^2
+      else q = e * e;
+      const double y = q - comp;
+      const double t = sse + y;
+      comp = (t - sse) - y;
+      sse = t;
+    }
   }
-  const double nse = 1.0 - sse / sst;
-  ll[j] = glue_shape * log(nse > 0.0 ? nse : 0.0);
+  if (LIK == 31) { const double nse = 1.0 - sse / sst; ll[j] = glue_shape * log(nse > 0.0 ? nse : 0.0); }
+  else if (LIK == 21) ll[j] = konst - 0.5 * sse;              // konst = -m/2 log(2 pi) - sum(log(abc_e)), host long double
+  else if (LIK == 22) ll[j] = vmin;
+  else ll[j] = -(double)T / 2 * log(sse);                     // fun_lik
 }
 
 // full series for parity tests of the model itself: out [n][T]
@@ -463,6 +482,9 @@ struct hydro_ctx {
   double sst, glue_shape;
   double* forcing_dev;
   double* obs_dev;
+  double* abc_e_dev = nullptr;   // lik 21 / 22 with a vector abc_e of length T
+  double e_scalar = 0.0, konst21 = 0.0;
+  bool have_abc = false;
   unsigned* err_dev;
   double* sst_dev = nullptr;   // batched: [n_runs]
   long long n_runs = 0;
@@ -471,13 +493,13 @@ struct hydro_ctx {
 int hydro_init(void** ctx, int d, int lik, const double* data, const int64_t* dims, int ndims, const double* obs,
                int64_t n_obs, double glue_shape, char* err, int errlen) {
   if (d != 1) { set_err(err, errlen, "HydroModel(forcing, param) has one parameter (R/test_HydroModel.R:17)"); return HB_ERR_INVALID; }
-  if (lik != 31) { set_err(err, errlen, "HydroModel on the device folds the GLUE likelihood: use lik = 31"); return HB_ERR_UNSUPPORTED; }
+  if (lik != 31 && lik != 21 && lik != 22 && lik != 99) { set_err(err, errlen, "HydroModel returns the simulated series: use a likelihood flag that folds it (lik = 21, 22, 31 or 99)"); return HB_ERR_UNSUPPORTED; }
   if (!data || ndims < 1 || dims[0] < 1) { set_err(err, errlen, "HydroModel needs the forcing series"); return HB_ERR_INVALID; }
   const int64_t T = dims[0];
-  if (!obs || n_obs != T) { set_err(err, errlen, "lik = 31 needs obs of the same length as forcing"); return HB_ERR_INVALID; }
+  if (!obs || n_obs != T) { set_err(err, errlen, "lik = 21/22/31/99 on HydroModel need obs of the same length as forcing"); return HB_ERR_INVALID; }
   for (int64_t i = 0; i < T; ++i)
     if (data[i] < 0) { set_err(err, errlen, "Values of argument 'forcing' need to be >= zero!"); return HB_ERR_INVALID; }  // :20-21
-  if ((size_t)(T + 1) * 16 > 220 * 1024) { set_err(err, errlen, "forcing series too long for shared-memory staging"); return HB_ERR_UNSUPPORTED; }
+  if ((size_t)(T + 1) * 24 > 220 * 1024) { set_err(err, errlen, "forcing series too long for shared-memory staging"); return HB_ERR_UNSUPPORTED; }
   auto* c = new hydro_ctx();
   c->T = (int)T; c->T_pad = (int)((T + 1) & ~1LL); c->lik = lik; c->glue_shape = glue_shape;
   // sum((obs - mean(obs))^2) with R's long-double mean refinement (summary.c, recollection)
@@ -503,23 +525,37 @@ int hydro_init(void** ctx, int d, int lik, const double* data, const int64_t* di
     ok = ok && cudaMemset(c->err_dev, 0, sizeof(unsigned)) == cudaSuccess;
   }
   if (!ok) { set_err(err, errlen, "cudaMalloc/cudaMemcpy failed for forcing/obs"); delete c; return HB_ERR_CUDA; }
-  const size_t smem = (size_t)2 * c->T_pad * sizeof(double);
-  if (smem > 48 * 1024 &&
-      cudaFuncSetAttribute(hb_hydro_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-    set_err(err, errlen, "cudaFuncSetAttribute failed"); delete c; return HB_ERR_CUDA;
-  }
   *ctx = c;
   return HB_OK;
+}
+
+template <int LIK, bool EVEC>
+int hydro_launch_t(hydro_ctx* c, const double* x, int64_t n, int ldx, double* ll, cudaStream_t st) {
+  const size_t smem = (size_t)(EVEC ? 3 : 2) * c->T_pad * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set && smem > 48 * 1024) {
+    if (cudaFuncSetAttribute(hb_hydro_kernel<LIK, EVEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) return HB_ERR_CUDA;
+    attr_set = true;
+  }
+  const int threads = n >= 65536 ? 256 : 128;
+  hb_hydro_kernel<LIK, EVEC><<<(unsigned)((n + threads - 1) / threads), threads, smem, st>>>(
+      x, n, ldx, c->forcing_dev, c->obs_dev, c->abc_e_dev, c->T, c->T_pad, c->sst, c->glue_shape, c->e_scalar, c->konst21, ll, c->err_dev);
+  return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
 }
 int hydro_launch(void* ctx, const double* x, int64_t n, int d, int ldx, double* ll, double* fx, void* stream) {
   auto* c = (hydro_ctx*)ctx;
   (void)fx;  // the raw series (3653 values per chain) is folded on the device, SURVEY 7.2 item 7
   if (n <= 0) return HB_OK;
-  const size_t smem = (size_t)2 * c->T_pad * sizeof(double);
-  const int threads = n >= 65536 ? 256 : 128;
-  hb_hydro_kernel<<<(unsigned)((n + threads - 1) / threads), threads, smem, (cudaStream_t)stream>>>(
-      x, n, ldx, c->forcing_dev, c->obs_dev, c->T, c->T_pad, c->sst, c->glue_shape, ll, c->err_dev);
-  return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((c->lik == 21 || c->lik == 22) && !c->have_abc) return HB_ERR_STATE;   // hb_set_lik_args was not called
+  const bool ev = c->abc_e_dev != nullptr;
+  switch (c->lik) {
+    case 31: return hydro_launch_t<31, false>(c, x, n, ldx, ll, st);
+    case 99: return hydro_launch_t<99, false>(c, x, n, ldx, ll, st);
+    case 21: return ev ? hydro_launch_t<21, true>(c, x, n, ldx, ll, st) : hydro_launch_t<21, false>(c, x, n, ldx, ll, st);
+    case 22: return ev ? hydro_launch_t<22, true>(c, x, n, ldx, ll, st) : hydro_launch_t<22, false>(c, x, n, ldx, ll, st);
+  }
+  return HB_ERR_UNSUPPORTED;
 }
 int hydro_launch_items(void* ctx, const double* x, int64_t n, int d, int ldx, double* ll, double* fx, int64_t chain0,
                        int64_t stride, int64_t nc, void* stream) {
@@ -543,7 +579,7 @@ int hydro_launch_items(void* ctx, const double* x, int64_t n, int d, int ldx, do
 }
 void hydro_destroy(void* ctx) {
   auto* c = (hydro_ctx*)ctx;
-  if (c) { cudaFree(c->forcing_dev); cudaFree(c->obs_dev); cudaFree(c->err_dev); cudaFree(c->sst_dev); delete c; }
+  if (c) { cudaFree(c->forcing_dev); cudaFree(c->obs_dev); cudaFree(c->abc_e_dev); cudaFree(c->err_dev); cudaFree(c->sst_dev); delete c; }
 }
 void hydro_work(void* ctx, int, double* flops, double* bytes) {
   auto* c = (hydro_ctx*)ctx;
@@ -609,6 +645,25 @@ int hb_hydro_init_batched(void** ctx, int d, int lik, const double* data, int64_
        cudaMemset(c->err_dev, 0, sizeof(unsigned)) == cudaSuccess;
   if (!ok) { set_err(err, errlen, "cudaMalloc/cudaMemcpy failed for batched forcing/obs"); delete c; return HB_ERR_CUDA; }
   *ctx = c;
+  return HB_OK;
+}
+
+// lik 21 / 22: abc_e (n_e == 1 recycled, or n_e == T) for a HydroModel context created with that flag
+int hb_hydro_set_abc(void* ctx, const double* abc_e, int64_t n_e, char* err, int errlen) {
+  auto* c = (hydro_ctx*)ctx;
+  if (!c || !abc_e || (n_e != 1 && n_e != c->T)) { set_err(err, errlen, "abc_e must have length 1 (recycled) or length(obs)"); return HB_ERR_INVALID; }
+  if (c->sst_dev) { set_err(err, errlen, "batched HydroModel runs support lik = 31 only"); return HB_ERR_UNSUPPORTED; }
+  long double sl = 0;
+  for (int64_t i = 0; i < n_e; ++i) sl += logl((long double)abc_e[i]);      // sum(log(abc_e)) over abc_e AS GIVEN (R/internals.R:10)
+  c->konst21 = -(double)c->T / 2 * log(2.0 * 3.14159265358979323846) - (double)sl;
+  c->e_scalar = abc_e[0];
+  if (n_e > 1) {
+    std::vector<double> buf((size_t)c->T_pad, 1.0);
+    memcpy(buf.data(), abc_e, sizeof(double) * (size_t)n_e);
+    if (!c->abc_e_dev && cudaMalloc(&c->abc_e_dev, sizeof(double) * c->T_pad) != cudaSuccess) { set_err(err, errlen, "cudaMalloc failed for abc_e"); return HB_ERR_CUDA; }
+    if (cudaMemcpy(c->abc_e_dev, buf.data(), sizeof(double) * c->T_pad, cudaMemcpyHostToDevice) != cudaSuccess) { set_err(err, errlen, "cudaMemcpy failed for abc_e"); return HB_ERR_CUDA; }
+  }
+  c->have_abc = true;
   return HB_OK;
 }
 

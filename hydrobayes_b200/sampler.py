@@ -76,6 +76,13 @@ class Sampler:
         c = np.asfortranarray(np.asarray(cov, np.float64).reshape(d, d))
         self._check(self.L.hb_set_prior_normal(self.h, _ptr(m), _ptr(c)))
 
+    def set_lik_args(self, abc_rho=None, abc_e=None, lik_fun=None):
+        """abc_rho= / abc_e= (lik 21, 22) and lik_fun= (lik 99): function NAMES resolved in the device registry
+        ("abc_distfun", "fun_lik": the closures of examples/script_examples.R:494, 503-507).  Before set_target."""
+        e = None if abc_e is None else np.ascontiguousarray(np.atleast_1d(np.asarray(abc_e, np.float64)))
+        self._check(self.L.hb_set_lik_args(self.h, abc_rho.encode() if abc_rho else None, _ptr(e), 0 if e is None else e.size,
+                                           lik_fun.encode() if lik_fun else None))
+
     def set_obs(self, obs):
         o = np.ascontiguousarray(np.asarray(obs, np.float64))
         self._check(self.L.hb_set_obs(self.h, _ptr(o), o.size))
@@ -337,6 +344,12 @@ def _drive(sweep, fun, extra, lik, par_info, nc, t, d, burnin, adapt, updateInte
             s.set_prior_normal(par_info["mu"], par_info["cov"])
         if obs is not None:
             s.set_obs(obs)
+        if abc_rho is not None or abc_e is not None or lik_fun is not None:
+            for nm, f in (("abc_rho", abc_rho), ("lik_fun", lik_fun)):
+                if f is not None and not isinstance(f, str):
+                    raise A.HbError(A.HB_ERR_UNKNOWN_TARGET, f"{nm} must be the NAME of a registered device function "
+                                                             "(arbitrary closures stay off the GPU path)")
+            s.set_lik_args(abc_rho, abc_e, lik_fun)
         data = forcing if forcing is not None else (extra[0] if extra else None)
         s.set_target(fun, data)
         if world > 1:

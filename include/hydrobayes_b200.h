@@ -172,6 +172,12 @@ const char* hb_last_error(const hb_handle* h);             /* h may be NULL: las
 int hb_set_bounds(hb_handle* h, const double* par_min, const double* par_max, int n); /* n == 1 (recycled) or d */
 int hb_set_prior_normal(hb_handle* h, const double* mu, const double* cov_colmajor); /* par.info$mu, $cov */
 int hb_set_obs(hb_handle* h, const double* obs, int64_t n);                           /* obs= */
+/* abc_rho=, abc_e= (lik 21 / 22) and lik_fun= (lik 99) of dream()/dream_parallel() (R/dream.R:131-132; calc_ll,
+ * R/internals.R:8-16).  The R API passes these functions BY NAME; like targets they resolve in a device registry:
+ * abc_rho "abc_distfun" = abs(sim - obs) and lik_fun "fun_lik" = -n/2 log(sum((sim-obs)^2)), the two closures of the
+ * reference's example script (examples/script_examples.R:494, 503-507).  Other names -> HB_ERR_UNKNOWN_TARGET (arbitrary
+ * R closures stay off the GPU path).  abc_e: n_abc_e == 1 (recycled) or length(obs).  Call before hb_set_target. */
+int hb_set_lik_args(hb_handle* h, const char* abc_rho, const double* abc_e, int64_t n_abc_e, const char* lik_fun);
 int hb_set_target(hb_handle* h, const char* name, const double* data, const int64_t* dims, int ndims);
 /* per-run target data for batched independent runs: data is [n_runs][len], obs is [n_runs][n_obs] (row-major) */
 int hb_set_target_batched(hb_handle* h, const char* name, const double* data, int64_t len,

@@ -198,6 +198,13 @@ static double r_mean(const double* x, int64_t n) {
 
 /* R/internals.R:3-23 */
 double hbo_calc_ll(const double* res, int64_t m, int32_t lik, const double* obs, double glue_shape, int* err) {
+  return hbo_calc_ll_ex(res, m, lik, obs, glue_shape, NULL, 0, err);
+}
+
+/* R/internals.R:3-23.  abc_rho = "abc_distfun" = abs(sim - obs) and lik_fun = "fun_lik" (SLS) are the two closures the
+ * reference's own example script defines (examples/script_examples.R:494, 503-507); R recycles abc_e over the m distances */
+double hbo_calc_ll_ex(const double* res, int64_t m, int32_t lik, const double* obs, double glue_shape,
+                      const double* abc_e, int64_t n_abc_e, int* err) {
   double out;
   *err = 0;
   if (lik == 1) {
@@ -211,8 +218,23 @@ double hbo_calc_ll(const double* res, int64_t m, int32_t lik, const double* obs,
     for (int64_t i = 0; i < m; ++i) { double e = obs[i] - mo; sst += (long double)(e * e); }
     double nse = 1 - (double)sse / (double)sst;
     out = glue_shape * log(nse > 0 ? nse : 0);
+  } else if (lik == 21) {                                     /* :8-10 */
+    if (!abc_e || n_abc_e < 1 || !obs) { *err = HB_ERR_INVALID; return NAN; }
+    long double sl = 0, q = 0;
+    for (int64_t i = 0; i < n_abc_e; ++i) sl += logl((long double)abc_e[i]);   /* sum(log(abc_e)): over abc_e AS GIVEN */
+    for (int64_t i = 0; i < m; ++i) { double r = fabs(res[i] - obs[i]) / abc_e[i % n_abc_e]; q += (long double)(r * r); }
+    out = -(double)m / 2 * log(2 * HBO_PI) - (double)sl - 0.5 * (double)q;
+  } else if (lik == 22) {                                     /* :11-12  min(abc_e - rho) */
+    if (!abc_e || n_abc_e < 1 || !obs) { *err = HB_ERR_INVALID; return NAN; }
+    out = INFINITY;
+    for (int64_t i = 0; i < m; ++i) { double v = abc_e[i % n_abc_e] - fabs(res[i] - obs[i]); if (v < out || isnan(v)) out = v; }
+  } else if (lik == 99) {                                     /* :15-16  fun_lik: -n/2 * log(sum((sim-obs)^2)) */
+    if (!obs) { *err = HB_ERR_INVALID; return NAN; }
+    long double sse = 0;
+    for (int64_t i = 0; i < m; ++i) { double e = res[i] - obs[i]; sse += (long double)(e * e); }
+    out = -(double)m / 2 * log((double)sse);
   } else {
-    *err = HB_ERR_UNSUPPORTED;                                /* 21, 22, 99 are host-side features */
+    *err = HB_ERR_UNSUPPORTED;
     return NAN;
   }
   double fl = hbo_log_xmin();
@@ -380,7 +402,7 @@ static double eval_target(const ctx_t* c, const double* x, double* scratch, doub
         if (!isfinite(out)) *err = HB_ERR_NONFINITE;
         return out;
       }
-      return hbo_calc_ll(scratch, T, lik, c->tgt->obs, c->cfg->glue_shape, err);
+      return hbo_calc_ll_ex(scratch, T, lik, c->tgt->obs, c->cfg->glue_shape, c->tgt->abc_e, c->tgt->n_abc_e, err);
     }
   }
   *err = HB_ERR_UNKNOWN_TARGET;
@@ -607,6 +629,9 @@ static int calc_prop(const ctx_t* c, int64_t i_gen, int64_t j, const double* x, 
 }
 
 /* R/internals.R:221-247, mt == 1, lik != 22 */
+/* R/internals.R:222-225, lik == 22: modified rule of Sadegh and Vrugt (2014), deterministic -- no uniform is drawn */
+static int metropolis_accept_abc(double p_xp, double p_x) { return (p_xp >= p_x) || (p_xp >= 0); }
+
 static int metropolis_accept(double p_xp, double p_x, double u) {
   double p_acc = fmin(fmax(-100, p_xp - p_x), 0);             /* :239 */
   return p_acc > log(u);                                      /* :241 */
@@ -745,7 +770,8 @@ int hbo_run(const hb_config* cfg, const hbo_target* tgt, const double* par_min, 
   /* argument checks: R/dream.R:136-137, R/dream_parallel.R:166-175 */
   if (!cfg->past_sample && nc <= 2 * (int64_t)cfg->delta) { snprintf(io->err, sizeof io->err, "Argument 'nc' must be > 'delta' * 2!"); return HB_ERR_INVALID; }
   if (cfg->mt > 1) { snprintf(io->err, sizeof io->err, "mt > 1 (MT-DREAM) is not restated"); return HB_ERR_UNSUPPORTED; }
-  if (cfg->lik != 1 && cfg->lik != 2 && cfg->lik != 31) { snprintf(io->err, sizeof io->err, "lik must be one of {1,2,31} here"); return HB_ERR_UNSUPPORTED; }
+  if (cfg->lik != 1 && cfg->lik != 2 && cfg->lik != 31 && cfg->lik != 21 && cfg->lik != 22 && cfg->lik != 99) { snprintf(io->err, sizeof io->err, "Argument 'lik' has to be one of {1,2,21,22}!"); return HB_ERR_INVALID; }
+  if ((cfg->lik == 21 || cfg->lik == 22 || cfg->lik == 99) && tgt->kind != HBO_TARGET_HYDROMODEL) { snprintf(io->err, sizeof io->err, "lik 21/22/99 are restated for HydroModel only"); return HB_ERR_UNSUPPORTED; }
   if (seq && (cfg->past_sample || cfg->psnooker > 0)) { snprintf(io->err, sizeof io->err, "dream() has no archive sampling"); return HB_ERR_INVALID; }
   if (cfg->rng_mode == HB_RNG_TAPE && !tape) { snprintf(io->err, sizeof io->err, "tape mode needs a tape"); return HB_ERR_INVALID; }
   if (cfg->delta > 4 || cfg->delta < 1) { snprintf(io->err, sizeof io->err, "delta must be in 1..4"); return HB_ERR_INVALID; }
@@ -887,8 +913,9 @@ int hbo_run(const hb_config* cfg, const hbo_target* tgt, const double* par_min, 
       int64_t nacc = 0;
       for (int64_t j = 0; j < nc; ++j) {                      /* :343 */
         double lpx = lp_xp[j] + ll_xp[j];                     /* :291 */
-        double u = accept_uniform(&c, i, j);
-        int a = metropolis_accept(lpx, lpost[j], u);
+        int a;
+        if (cfg->lik == 22) a = metropolis_accept_abc(lpx, lpost[j]);
+        else { double u = accept_uniform(&c, i, j); a = metropolis_accept(lpx, lpost[j], u); }
         acc[j] = (uint8_t)a;
         if (a) {                                              /* :356-361 */
           for (int k = 0; k < d; ++k) { dxm[j * d + k] = xp[j * d + k] - xt[j * d + k]; xt[j * d + k] = xp[j * d + k]; }
@@ -921,8 +948,9 @@ int hbo_run(const hb_config* cfg, const hbo_target* tgt, const double* par_min, 
         double llx = eval_target(&c, xpj, scr, &fxx, &e);
         if (e) FAIL(e, e == HB_ERR_NONFINITE ? nonfinite_msg(2) : "target evaluation failed");
         double lpostx = lpx + llx;
-        double u = accept_uniform(&c, i, j);
-        int a = metropolis_accept(lpostx, lpost[j], u);       /* :232 */
+        int a;                                                /* :232 */
+        if (cfg->lik == 22) a = metropolis_accept_abc(lpostx, lpost[j]);
+        else { double u = accept_uniform(&c, i, j); a = metropolis_accept(lpostx, lpost[j], u); }
         acc[j] = (uint8_t)a;
         double* dxj = dxm; /* reuse first row */
         if (a) {

@@ -32,8 +32,13 @@ typedef struct hbo_target {
   int32_t reserved;
   const double* forcing; /* HydroModel: [T] */
   int64_t T;
-  const double* obs;     /* lik == 31: [T] */
+  const double* obs;     /* lik in {21, 22, 31, 99}: [T] */
   int64_t n_obs;
+  /* lik 21 / 22 (ABC, R/internals.R:8-12): abc_rho is the registered distance "abc_distfun" = abs(sim - obs)
+   * (examples/script_examples.R:494); abc_e has n_abc_e entries (1 = recycled, or T).  lik 99: lik_fun is the registered
+   * "fun_lik" = -n/2 * log(sum((sim-obs)^2)) (examples/script_examples.R:503-507). */
+  const double* abc_e;
+  int64_t n_abc_e;
 } hbo_target;
 
 /* caller-allocated outputs (numpy arrays in the tests); any pointer may be NULL to skip */
@@ -71,6 +76,8 @@ double hbo_dnorm(double x, double mu, double sigma);        /* R nmath dnorm4 (r
 double hbo_mixture(double x);                               /* R/test_mixture.R:16 */
 int hbo_tdist_logpdf(const double* x_colmajor, int64_t n, int32_t d, double* out); /* R/test_t_distribution.R:19-46 */
 int hbo_hydromodel(const double* forcing, int64_t T, double param, double* Y);     /* R/test_HydroModel.R:17-36 */
+double hbo_calc_ll_ex(const double* res, int64_t m, int32_t lik, const double* obs, double glue_shape,
+                      const double* abc_e, int64_t n_abc_e, int* err);
 double hbo_calc_ll(const double* res, int64_t m, int32_t lik, const double* obs, double glue_shape,
                    int* err);                               /* R/internals.R:3-23 */
 double hbo_bound_par(double par, double mn, double mx, int32_t handle); /* R/internals.R:89-113 */

@@ -23,7 +23,7 @@ _dp = C.POINTER(C.c_double)
 
 class HboTarget(C.Structure):
     _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("forcing", _dp), ("T", C.c_int64),
-                ("obs", _dp), ("n_obs", C.c_int64)]
+                ("obs", _dp), ("n_obs", C.c_int64), ("abc_e", _dp), ("n_abc_e", C.c_int64)]
 
 
 class HboIo(C.Structure):
@@ -136,7 +136,7 @@ def rstat(x) -> np.ndarray:
     return out
 
 
-def make_target(name, forcing=None, obs=None):
+def make_target(name, forcing=None, obs=None, abc_e=None):
     t = HboTarget()
     t.kind = TARGET_KIND[name]
     keep = []
@@ -146,14 +146,17 @@ def make_target(name, forcing=None, obs=None):
     if obs is not None:
         o = _f64(obs); keep.append(o)
         t.obs = _p(o); t.n_obs = o.size
+    if abc_e is not None:
+        e = _f64(np.atleast_1d(abc_e)); keep.append(e)
+        t.abc_e = _p(e); t.n_abc_e = e.size
     return t, keep
 
 
-def logdensity(name, lik, x, forcing=None, obs=None, glue_shape=0.0):
+def logdensity(name, lik, x, forcing=None, obs=None, glue_shape=0.0, abc_e=None):
     x = np.atleast_2d(np.asarray(x, dtype=np.float64))
     n, d = x.shape
     xf = np.asfortranarray(x)
-    tgt, keep = make_target(name, forcing, obs)
+    tgt, keep = make_target(name, forcing, obs, abc_e)
     ll = np.empty(n); fx = np.empty(n)
     rc = lib().hbo_logdensity(C.byref(tgt), lik, glue_shape, xf.ctypes.data_as(_dp), n, d, _p(ll), _p(fx))
     return ll, fx, rc
@@ -207,13 +210,13 @@ def out_dims(cfg: HbConfig):
 
 
 def run(cfg: HbConfig, target: str, x0, par_min=None, par_max=None, prior_mu=None, prior_cov=None, tape: Tape = None,
-        record: Tape = None, forcing=None, obs=None, run: int = 0, threads: int = 1, outputs: bool = True):
+        record: Tape = None, forcing=None, obs=None, run: int = 0, threads: int = 1, outputs: bool = True, abc_e=None):
     """Run the restated generation loop.  x0: [n0, d] array.  Returns a dict shaped like the reference's list."""
     L = lib()
     d, nc, t = cfg.d, cfg.nc, cfg.t
     out_t, ar_rows, ar_cols, cr_rows, cr_cols = out_dims(cfg)
     x0f = np.asfortranarray(np.asarray(x0, dtype=np.float64).reshape(-1, d))
-    tgt, keep = make_target(target, forcing, obs)
+    tgt, keep = make_target(target, forcing, obs, abc_e)
     io = HboIo()
     res = {}
     if outputs:

@@ -59,7 +59,7 @@ def hydro_data_batch(T, n_catchments, first=0):
 
 
 def run_device(cfg, target, x0, par_min=None, par_max=None, tape=None, forcing=None, obs=None, device=0,
-               slice_generations=None, prior_mu=None, prior_cov=None):
+               slice_generations=None, prior_mu=None, prior_cov=None, abc_e=None, abc_rho="abc_distfun", lik_fun="fun_lik"):
     """Drives the C ABI through hydrobayes_b200.Sampler and returns the same dict layout as oracle.run()."""
     from hydrobayes_b200 import Sampler
     with Sampler(cfg, device) as s:
@@ -69,6 +69,10 @@ def run_device(cfg, target, x0, par_min=None, par_max=None, tape=None, forcing=N
             s.set_prior_normal(prior_mu, prior_cov)
         if obs is not None:
             s.set_obs(obs)
+        if cfg.lik in (21, 22):
+            s.set_lik_args(abc_rho=abc_rho, abc_e=abc_e)
+        elif cfg.lik == 99:
+            s.set_lik_args(lik_fun=lik_fun)
         s.set_target(target, forcing)
         s.set_initial(x0)
         if tape is not None:

@@ -153,6 +153,45 @@ def test_replay_hydromodel_glue(hb, oracle, bound):
     H.assert_run_parity(dev, ora, rtol=1e-11)
 
 
+# ---------------------------------------------------------------- likelihood flags 21 / 22 / 99 on HydroModel
+@pytest.mark.parametrize("sweep", [A.HB_SWEEP_SYNCHRONOUS, A.HB_SWEEP_SEQUENTIAL])
+@pytest.mark.parametrize("lik,abc", [(21, 0.8), (21, "vector"), (22, 2.5), (22, "vector"), (99, None)])
+def test_replay_hydromodel_lik_flags(hb, oracle, lik, abc, sweep):
+    # calc_ll (R/internals.R:8-16) with abc_rho = "abc_distfun" = abs(sim - obs) and lik_fun = "fun_lik" (SLS), the
+    # closures of examples/script_examples.R:494, 503-507; lik = 22 also switches prior_pdf to 0 (:50-51) and the
+    # acceptance to the deterministic rule of :222-225 (no uniform is drawn)
+    T = 150
+    P, obs = H.hydro_data(T=T)
+    e = None if abc is None else (np.linspace(0.6, 3.0, T) if abc == "vector" else abc)
+    cfg = A.default_config(nc=12, t=160, d=1, lik=lik, prior=A.HB_PRIOR_UNIFORM, bound=A.HB_BOUND_REFLECT, seed=29,
+                           sweep=sweep, adapt=0.4)
+    kw = dict(par_min=[0.01], par_max=[2.0], forcing=P, obs=obs)
+    if e is not None:
+        kw["abc_e"] = e
+    dev, ora = _replay_case(oracle, cfg, "HydroModel", H.x0_hydro(12), **kw)
+    H.assert_run_parity(dev, ora, rtol=1e-10)
+    assert 0.02 < ora["accept"].mean() < 0.98
+    if lik == 22:
+        assert (ora["chain"][:, 1, :] == 0).all()              # column lp: prior_pdf is 0 under lik = 22
+
+
+def test_lik_closure_names_resolve_in_registry(hb):
+    from hydrobayes_b200 import Sampler
+    P, obs = H.hydro_data(T=50)
+    cfg = A.default_config(nc=8, t=10, d=1, lik=21, prior=A.HB_PRIOR_UNIFORM)
+    with Sampler(cfg, 0) as s:
+        s.set_bounds([0.01], [2.0]); s.set_obs(obs)
+        with pytest.raises(A.HbError, match="not found in the device registry"):
+            s.set_lik_args(abc_rho="my_r_closure", abc_e=1.0)
+        with pytest.raises(A.HbError, match="needs abc_rho and abc_e"):
+            s.set_target("HydroModel", P)
+        s.set_lik_args(abc_rho="abc_distfun", abc_e=[1.0, 2.0])
+        with pytest.raises(A.HbError, match="length 1 .recycled. or length.obs."):
+            s.set_target("HydroModel", P)
+    with pytest.raises(A.HbError, match="ABC method cannot be combined"):
+        Sampler(A.default_config(nc=8, t=10, d=1, lik=22, past_sample=1, psnooker=0.1), 0)
+
+
 @pytest.mark.parametrize("kw", [dict(thin=5), dict(burnin=0.5), dict(burnin=0.2, thin=4), dict(adapt=0.5, update_interval=7),
                                 dict(delta=1, nCR=1), dict(delta=4, nCR=6, p_g=0.5, beta0=0.7, c_val=0.3, c_star=1e-3)])
 def test_replay_options(hb, oracle, kw):
