@@ -64,6 +64,7 @@ class HbTape(C.Structure):
         ("zt", _dp), ("lambda_", _dp), ("g_is_one", _u8p), ("zeta", _dp),
         ("g_snooker", _dp), ("u_accept", _dp), ("outlier_new", _i32p),
         ("n_events", C.c_int64),
+        ("n_sets", C.c_int32), ("reserved", C.c_int32), ("mt_pick", _u8p),
     ]
 
 

@@ -196,10 +196,17 @@ int allocate(hb_handle* h) {
     CK(cudaMemsetAsync(h->arena, 0, bytes, h->stream));
     h->flags = reinterpret_cast<unsigned*>(h->arena);
   }
-  CK(dalloc(&h->XP, (size_t)nl * ldx));
-  CK(cudaMemsetAsync(h->XP, 0, (size_t)nl * ldx * sizeof(double), h->stream));
-  CK(dalloc(&h->id, (size_t)nl));
-  CK(dalloc(&h->lp_xp, (size_t)nl)); CK(dalloc(&h->ll_raw, (size_t)nl)); CK(dalloc(&h->fx_xp, (size_t)nl));
+  const size_t mtn = (size_t)(c.mt > 1 ? c.mt : 1) * (size_t)nl;   // MT-DREAM: mt proposal sets live side by side, try-major
+  CK(dalloc(&h->XP, mtn * ldx));
+  CK(cudaMemsetAsync(h->XP, 0, mtn * ldx * sizeof(double), h->stream));
+  CK(dalloc(&h->id, mtn));
+  CK(dalloc(&h->lp_xp, mtn)); CK(dalloc(&h->ll_raw, mtn)); CK(dalloc(&h->fx_xp, mtn));
+  if (c.mt > 1) {
+    CK(dalloc(&h->ZT, (size_t)nl * ldx));
+    CK(cudaMemsetAsync(h->ZT, 0, (size_t)nl * ldx * sizeof(double), h->stream));
+    CK(dalloc(&h->lp_zt, (size_t)nl)); CK(dalloc(&h->ll_zt, (size_t)nl)); CK(dalloc(&h->fx_zt, (size_t)nl));
+    CK(dalloc(&h->id_zt, (size_t)nl)); CK(dalloc(&h->mt_p1, (size_t)nl)); CK(dalloc(&h->mt_accept, (size_t)nl));
+  }
   CK(dalloc(&h->lp, (size_t)nl)); CK(dalloc(&h->ll, (size_t)nl)); CK(dalloc(&h->lpost, (size_t)nl));
   CK(dalloc(&h->fx, (size_t)nl));
   CK(dalloc(&h->lpost_hist, (size_t)h->H * nl));
@@ -429,6 +436,44 @@ int run_generation(hb_handle* h, long long i) {
   const bool tape_mode = (c.rng_mode == HB_RNG_TAPE);
 
   if (h->modeb) return hb_seq_generation(h, i);
+  if (c.mt > 1) {
+    // ---------------- MT-DREAM, R/dream_parallel.R:269-341 (hb_mt.cu) ----------------
+    const int mt = c.mt, n_sets = 2 * mt - 1;
+    auto k1_set = [&](int set, int slot, const double* pop) -> int {   // proposal set `set` into try slot `slot`
+      hb_k1_params p = hb_make_k1(h, i, h->chain0, 1, nl);
+      p.X = pop;
+      p.XP = h->XP + (size_t)slot * nl * ldx; p.id_out = h->id + (size_t)slot * nl; p.lp_xp = h->lp_xp + (size_t)slot * nl;
+      p.gen = (uint32_t)i | ((uint32_t)(set + 1) << 24);              // Philox substream of the set
+      p.tape_g = (i - 2) * n_sets + set;                              // tape row g*n_sets + set
+      prof_scope ps(h, "K1");
+      CK(hb_launch_k1(p, tape_mode, h->sm_count, h->stream));
+      ps.done();
+      return HB_OK;
+    };
+    for (int m = 0; m < mt; ++m) if (int rc = k1_set(m, m, h->X)) return rc;                 // :269  around xt
+    if (int rc = hb_prior_after_k1(h, (long long)mt * nl)) return rc;
+    { prof_scope ps(h, "K2"); if (int rc = hb_target_launch(h, h->XP, (long long)mt * nl, h->chain0, 1)) return fail(h, rc, "target launch failed"); ps.done(); }
+    hb_mt_params mp{};
+    mp.mt = mt; mp.n_local = nl; mp.ldx = ldx; mp.XP = h->XP; mp.lp_xp = h->lp_xp; mp.ll_raw = h->ll_raw;
+    mp.fx_xp = c.store_fx ? h->fx_xp : nullptr; mp.id = h->id; mp.ZT = h->ZT; mp.lp_zt = h->lp_zt; mp.ll_zt = h->ll_zt;
+    mp.fx_zt = c.store_fx ? h->fx_zt : nullptr; mp.id_zt = h->id_zt; mp.p1 = h->mt_p1; mp.lpost = h->lpost;
+    mp.accept_out = h->mt_accept; mp.seed = c.seed; mp.gen = (uint32_t)i; mp.gchain0 = (long long)c.run_offset * h->nc + h->chain0;
+    mp.err = &h->ctrl->err;
+    mp.tape_pick = tape_mode ? h->tape_mt_pick + (size_t)(i - 2) * h->tape.nct : nullptr;
+    mp.u_accept = tape_mode ? h->tape.u_accept + (size_t)(i - 2) * h->tape.nct : nullptr;
+    { prof_scope ps(h, "MT"); CK(hb_launch_mt_select(mp, h->stream)); ps.done(); }           // :297-314
+    for (int m = 0; m < mt - 1; ++m) if (int rc = k1_set(mt + m, m, h->ZT)) return rc;       // :316  around zt
+    if (int rc = hb_prior_after_k1(h, (long long)(mt - 1) * nl)) return rc;
+    { prof_scope ps(h, "K2"); if (int rc = hb_target_launch(h, h->XP, (long long)(mt - 1) * nl, h->chain0, 1)) return fail(h, rc, "target launch failed"); ps.done(); }
+    { prof_scope ps(h, "MT"); CK(hb_launch_mt_accept(mp, h->stream)); ps.done(); }           // :340, R/internals.R:229-236
+    hb_k3_params p = hb_make_k3(h, i, h->chain0, 1, nl, store, in_adapt, false);
+    p.XP = h->ZT; p.XP_rw = h->ZT; p.id = h->id_zt; p.lp_xp = h->lp_zt; p.ll_raw = h->ll_zt;   // :349-355 accept the candidates
+    p.fx_xp = c.store_fx ? h->fx_zt : nullptr; p.accept_in = h->mt_accept;
+    prof_scope ps(h, "K3");
+    int nb = 0;
+    CK(hb_launch_k3(p, h->sm_count, &nb, nullptr, h->stream));
+    ps.done();
+  } else {
   {  // K1
     const hb_k1_params p = hb_make_k1(h, i, h->chain0, 1, nl);
     prof_scope ps(h, "K1");
@@ -457,6 +502,7 @@ int run_generation(hb_handle* h, long long i) {
     CK(hb_launch_k3(p, h->sm_count, &nb, nullptr, h->stream));
     ps.done();
   }
+  }   // mt == 1
   h->pending_evals += h->nc;
   if (in_adapt || upd || h->peer_mode) {  // finalize: J / n_id / n_acc, pCR adaptation, AR/CR rows (peer mode: every
                                           // generation, its counter all-reduce is the generation barrier)
@@ -536,7 +582,9 @@ int upload_tape(hb_handle* h, const hb_tape* tp) {
     *dst = p;
     return HB_OK;
   };
-  const size_t n = (size_t)n_gen * nct;
+  const size_t n_sets = h->cfg.mt > 1 ? (size_t)(2 * h->cfg.mt - 1) : 1;
+  const size_t n1 = (size_t)n_gen * nct;         // per generation and chain: u_accept, mt_pick
+  const size_t n = n1 * n_sets;                  // per proposal set
   int rc = HB_OK;
   if ((rc = up(tp->u_snooker, n * 8, (const void**)&h->tape.u_snooker))) return rc;
   if ((rc = up(tp->D, n, (const void**)&h->tape.D))) return rc;
@@ -547,7 +595,8 @@ int upload_tape(hb_handle* h, const hb_tape* tp) {
   if ((rc = up(tp->g_is_one, n, (const void**)&h->tape.g_is_one))) return rc;
   if ((rc = up(tp->zeta, n * d * 8, (const void**)&h->tape.zeta))) return rc;
   if ((rc = up(tp->g_snooker, n * 8, (const void**)&h->tape.g_snooker))) return rc;
-  if ((rc = up(tp->u_accept, n * 8, (const void**)&h->tape.u_accept))) return rc;
+  if ((rc = up(tp->u_accept, n1 * 8, (const void**)&h->tape.u_accept))) return rc;
+  if (h->cfg.mt > 1 && (rc = up(tp->mt_pick, n1, (const void**)&h->tape_mt_pick))) return rc;
   h->tape.nct = nct;
   h->tape_n_gen = n_gen;
   h->tape_events = tp->n_events;
@@ -590,7 +639,11 @@ int hb_create(const hb_config* cfg, int device, hb_handle** out) {
   if (!cfg->past_sample && cfg->nc <= 2 * (long long)cfg->delta) return fail(h, HB_ERR_INVALID, "Argument 'nc' must be > 'delta' * 2!");
   if (cfg->delta < 1 || cfg->delta > HB_MAX_DELTA) return fail(h, HB_ERR_UNSUPPORTED, "delta must be in 1..%d on the device", HB_MAX_DELTA);
   if (cfg->nCR < 1 || cfg->nCR > HB_MAX_NCR) return fail(h, HB_ERR_UNSUPPORTED, "nCR must be in 1..%d on the device", HB_MAX_NCR);
-  if (cfg->mt > 1) return fail(h, HB_ERR_UNSUPPORTED, "mt > 1 (MT-DREAM) is not on the device path");
+  if (cfg->mt > 1) {   // MT-DREAM exists in dream_parallel only (R/dream_parallel.R:295)
+    if (cfg->sweep != HB_SWEEP_SYNCHRONOUS || cfg->n_runs > 1) return fail(h, HB_ERR_UNSUPPORTED, "mt > 1 (MT-DREAM) needs the synchronous sweep of dream_parallel and a single run");
+    if (cfg->mt > 64) return fail(h, HB_ERR_UNSUPPORTED, "mt must be <= 64 on the device");
+    if (cfg->t >= (1 << 24)) return fail(h, HB_ERR_UNSUPPORTED, "mt > 1 needs t < 2^24 (the Philox substream lives in the top byte of the generation word)");
+  }
   if ((cfg->mt > 1 || cfg->psnooker > 0) && (cfg->lik == 21 || cfg->lik == 22))
     return fail(h, HB_ERR_INVALID, "ABC method cannot be combined with MT-DREAM or snooker updating, see Sadegh and Vrugt (2014), WRR!");
   if (cfg->lik != 1 && cfg->lik != 2 && cfg->lik != 31 && cfg->lik != 21 && cfg->lik != 22 && cfg->lik != 99)
@@ -655,7 +708,7 @@ void hb_destroy(hb_handle* h) {
   void* ptrs[] = {h->X, h->Z, h->XP, h->id, h->lp_xp, h->ll_raw, h->fx_xp, h->lp, h->ll, h->lpost, h->fx, h->lpost_hist,
                   h->hist_x, h->hist_l, h->hist_fx, h->accept_rec, h->ctrl, h->shift, h->colsum, h->qsum, h->partials,
                   h->out_ar, h->out_cr, h->proxy, h->proxy_full, h->lpost_full, h->outl_dev, h->news_dev, h->rstat_dev,
-                  h->rstat_xm, h->rstat_ss, h->stage, h->pmin, h->pmax, h->prior_W, h->prior_mu, h->gamma_tab, h->outl_tmp, h->outl_sorted, h->outl_thr,
+                  h->rstat_xm, h->rstat_ss, h->stage, h->pmin, h->pmax, h->prior_W, h->prior_mu, h->ZT, h->lp_zt, h->ll_zt, h->fx_zt, h->id_zt, h->mt_p1, h->mt_accept, h->gamma_tab, h->outl_tmp, h->outl_sorted, h->outl_thr,
                   h->outl_count};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (void* p : h->tape_allocs) cudaFree(p);
@@ -794,6 +847,7 @@ int hb_comm_init(hb_handle* h, int rank, int world, const void* id128) {
   if (world < 1 || rank < 0 || rank >= world) return fail(h, HB_ERR_INVALID, "bad rank/world");
   if (h->nc % world) return fail(h, HB_ERR_INVALID, "nc must be divisible by the number of GPUs");
   if (h->cfg.sweep != HB_SWEEP_SYNCHRONOUS || h->cfg.n_runs > 1) return fail(h, HB_ERR_UNSUPPORTED, "only the synchronous single-population sweep shards across GPUs");
+  if (h->cfg.mt > 1 && world > 1) return fail(h, HB_ERR_UNSUPPORTED, "mt > 1 (MT-DREAM) is single-GPU for now: the candidate population zt would need its own exchange");
   cudaSetDevice(h->device);
   const double t_begin = now_s();
   // HB_EXCHANGE_DELTA needs no NCCL communicator: its barriers and small collectives run over peer-mapped memory
@@ -963,6 +1017,8 @@ int hb_set_tape(hb_handle* h, const hb_tape* tape) {
     return fail(h, HB_ERR_INVALID, "tape geometry does not match the configuration");
   if (!tape->D || !tape->partners || !tape->id || !tape->zt || !tape->lambda || !tape->g_is_one || !tape->zeta || !tape->u_accept)
     return fail(h, HB_ERR_INVALID, "tape is missing a required array");
+  if (h->cfg.mt > 1 && (tape->n_sets != 2 * h->cfg.mt - 1 || !tape->mt_pick))
+    return fail(h, HB_ERR_INVALID, "mt > 1 needs a tape with n_sets = 2*mt - 1 proposal sets per generation and mt_pick");
   return upload_tape(h, tape);
 }
 

@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) hb_k3_kernel(const hb_k3_params p) {
       if (TAPE) u = p.u_accept[j];
       else { const hb_phx ph(p.seed, (uint64_t)gch, p.gen); u = hb_u53(hb_pair64(ph.slot(HB_SLOT_ACCEPT), 0)); }
       const double p_acc = fmin(fmax(-100.0, lpostx - lpost_old), 0.0); // R/internals.R:239
-      accf = p.lik22 ? ((lpostx >= lpost_old) || (lpostx >= 0.0)) : (p_acc > log(u));   // :241 ; ABC rule :224
+      accf = p.accept_in ? (int)p.accept_in[jl] : p.lik22 ? ((lpostx >= lpost_old) || (lpostx >= 0.0)) : (p_acc > log(u));   // :241 ; ABC rule :224 ; mt > 1: hb_mt.cu
       id = p.id[jl];
     }
     if (G > 1) { accf = __shfl_sync(FULL, accf, gbase); id = __shfl_sync(FULL, id, gbase); }
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(256, 3) hb_k3_wide_kernel(const hb_k3_params p
       if (TAPE) u = p.u_accept[gj];
       else { const hb_phx ph(p.seed, (uint64_t)gch, p.gen); u = hb_u53(hb_pair64(ph.slot(HB_SLOT_ACCEPT), 0)); }
       const double p_acc = fmin(fmax(-100.0, lpostx - lpost_old), 0.0); // R/internals.R:239
-      accf = p.lik22 ? ((lpostx >= lpost_old) || (lpostx >= 0.0)) : (p_acc > log(u));   // :241 ; ABC rule :224
+      accf = p.accept_in ? (int)p.accept_in[jl] : p.lik22 ? ((lpostx >= lpost_old) || (lpostx >= 0.0)) : (p_acc > log(u));   // :241 ; ABC rule :224 ; mt > 1: hb_mt.cu
       id = p.id[jl];
       double lp_c = 0, ll_c = 0, lpost_c = lpost_old;                 // :365
       if (accf) {

@@ -55,6 +55,27 @@ struct hb_k1_params {
 };
 cudaError_t hb_launch_k1(const hb_k1_params& p, bool tape_mode, int sm_count, cudaStream_t st);
 
+// ---- MT-DREAM (mt > 1): candidate selection and multi-try acceptance, R/dream_parallel.R:295-341 -----------------
+struct hb_mt_params {
+  int mt; long long n_local; int ldx;
+  const double* XP;        // [mt][n_local][ldx] proposals, try-major
+  const double* lp_xp;     // [mt][n_local]
+  const double* ll_raw;    // [mt][n_local] plugin output before the floor
+  const double* fx_xp;     // [mt][n_local] or nullptr
+  const int* id;           // [mt][n_local]
+  double* ZT;              // [n_local][ldx] selected candidates
+  double* lp_zt; double* ll_zt; double* fx_zt; int* id_zt;   // [n_local]
+  double* p1;              // [n_local] sum(exp(lpost_xp)) over the mt tries (written by select, read by accept)
+  const double* lpost;     // [n_local] current log posterior
+  uint8_t* accept_out;     // [n_local] decisions handed to K3
+  const uint8_t* tape_pick;   // replay: [n_local] recorded sample(1:mt, 1, prob) decisions of this generation, else nullptr
+  const double* u_accept;     // replay: [n_local], else nullptr
+  uint64_t seed; uint32_t gen; long long gchain0;
+  unsigned* err;
+};
+cudaError_t hb_launch_mt_select(const hb_mt_params& p, cudaStream_t st);
+cudaError_t hb_launch_mt_accept(const hb_mt_params& p, cudaStream_t st);
+
 // ---- K3: Metropolis accept + update + history + adaptation statistics ----------------------------------
 struct hb_k3_params {
   double* X;              // [nc][ldx] updated in place (rows of the local shard)
@@ -81,6 +102,7 @@ struct hb_k3_params {
   int adapt;              // generation is inside the adaptation period: accumulate std / jump statistics
   // HB_EXCHANGE_DELTA: accepted rows are also stored into the peers' replicas of X (NVLink posted writes); null = off
   double* push[8]; int n_push;
+  const uint8_t* accept_in;   // MT-DREAM: the decisions were taken by hb_mt_accept_kernel (nullptr otherwise)
   int lik22;              // lik == 22: deterministic ABC acceptance rule (R/internals.R:222-225), no uniform drawn
   int write_dx;           // per-run statistics path: overwrite XP[item] with the realised jump dx (0 if rejected)
   uint64_t seed;

@@ -131,6 +131,14 @@ typedef struct hb_tape {
   const int32_t* outlier_new;/* [n_events][nct] replacement chains (0-based, within run) for the k-th outlier of the
                                 run in ascending order; event e is generation (e+1)*update_interval (R/internals.R:81) */
   int64_t n_events;
+  /* MT-DREAM (mt > 1, R/dream_parallel.R:295-336): every generation draws n_sets = 2*mt - 1 proposal sets -- mt sets
+   * around xt, then mt - 1 around the selected candidates zt.  The per-proposal arrays above then carry a set
+   * dimension, [n_gen][n_sets][nct]... (set s of generation g is row g*n_sets + s); u_accept stays [n_gen][nct].
+   * mt_pick is the decision of sample(1:mt, 1, prob = p) (:306), 0-based try index.  n_sets <= 1 and mt_pick NULL
+   * for mt == 1. */
+  int32_t n_sets;
+  int32_t reserved;
+  const uint8_t* mt_pick;    /* [n_gen][nct] */
 } hb_tape;
 
 typedef struct hb_handle hb_handle;

@@ -334,6 +334,8 @@ typedef struct {
   hb_tape* rec;
   int64_t run;
   int64_t nct;
+  int n_sets, set;   /* MT-DREAM: proposal sets per generation and the set being drawn (tape row g*n_sets + set; Philox
+                        substream = set + 1 in the top byte of the generation word, 0 when mt == 1) */
 } ctx_t;
 
 static inline double bmin(const ctx_t* c, int k) { return c->n_bounds > 1 ? c->pmin[k] : c->pmin[0]; }
@@ -474,9 +476,10 @@ static int calc_prop(const ctx_t* c, int64_t i_gen, int64_t j, const double* x, 
   const int tape_mode = (cfg->rng_mode == HB_RNG_TAPE);
   const hb_tape* tp = c->tape;
   hb_tape* rec = c->rec;
-  const int64_t rix = tape_mode || rec ? (g * c->nct + gch) : 0; /* record index */
+  const int n_sets = c->n_sets > 1 ? c->n_sets : 1;
+  const int64_t rix = tape_mode || rec ? ((g * n_sets + c->set) * c->nct + gch) : 0; /* record index */
   phx_t ph; uint32_t w[4];
-  if (!tape_mode) phx_init(&ph, cfg->seed, (uint64_t)gch, (uint32_t)i_gen);
+  if (!tape_mode) phx_init(&ph, cfg->seed, (uint64_t)gch, (uint32_t)i_gen | (n_sets > 1 ? (uint32_t)(c->set + 1) << 24 : 0u));
 
   /* :119 snooker test uniform is ALWAYS drawn */
   double u_sn; int D;
@@ -765,11 +768,15 @@ int hbo_run(const hb_config* cfg, const hbo_target* tgt, const double* par_min, 
   double *xt = NULL, *xp = NULL, *lp = NULL, *ll = NULL, *lpost = NULL, *lp_xp = NULL, *ll_xp = NULL, *fxv = NULL,
          *fx_xp = NULL, *hist = NULL, *z = NULL, *dxm = NULL, *stdx = NULL, *proxy = NULL, *scr = NULL, *ztb = NULL;
   int64_t *outl = NULL, *news = NULL, *cand = NULL; int* ids = NULL; uint8_t* acc = NULL;
+  const int mt = cfg->mt > 1 ? cfg->mt : 1;
+  double *mt_xp = NULL, *mt_lp = NULL, *mt_ll = NULL, *mt_fx = NULL, *mt_zt = NULL, *mt_lpz = NULL, *mt_llz = NULL, *mt_fxz = NULL, *mt_lpostzp = NULL;
+  int* mt_id = NULL;
   ctx_t c; memset(&c, 0, sizeof c);
 
   /* argument checks: R/dream.R:136-137, R/dream_parallel.R:166-175 */
   if (!cfg->past_sample && nc <= 2 * (int64_t)cfg->delta) { snprintf(io->err, sizeof io->err, "Argument 'nc' must be > 'delta' * 2!"); return HB_ERR_INVALID; }
-  if (cfg->mt > 1) { snprintf(io->err, sizeof io->err, "mt > 1 (MT-DREAM) is not restated"); return HB_ERR_UNSUPPORTED; }
+  if (cfg->mt > 1 && (cfg->sweep == HB_SWEEP_SEQUENTIAL || cfg->n_runs > 1)) { snprintf(io->err, sizeof io->err, "mt > 1 (MT-DREAM) exists in dream_parallel only (R/dream_parallel.R:295)"); return HB_ERR_UNSUPPORTED; }
+  if (cfg->mt > 64) { snprintf(io->err, sizeof io->err, "mt must be <= 64"); return HB_ERR_UNSUPPORTED; }
   if (cfg->lik != 1 && cfg->lik != 2 && cfg->lik != 31 && cfg->lik != 21 && cfg->lik != 22 && cfg->lik != 99) { snprintf(io->err, sizeof io->err, "Argument 'lik' has to be one of {1,2,21,22}!"); return HB_ERR_INVALID; }
   if ((cfg->lik == 21 || cfg->lik == 22 || cfg->lik == 99) && tgt->kind != HBO_TARGET_HYDROMODEL) { snprintf(io->err, sizeof io->err, "lik 21/22/99 are restated for HydroModel only"); return HB_ERR_UNSUPPORTED; }
   if (seq && (cfg->past_sample || cfg->psnooker > 0)) { snprintf(io->err, sizeof io->err, "dream() has no archive sampling"); return HB_ERR_INVALID; }
@@ -825,6 +832,14 @@ int hbo_run(const hb_config* cfg, const hbo_target* tgt, const double* par_min, 
   outl = (int64_t*)malloc(sizeof(int64_t) * nc); news = (int64_t*)malloc(sizeof(int64_t) * nc);
   cand = (int64_t*)malloc(sizeof(int64_t) * nc); ids = (int*)malloc(sizeof(int) * nc);
   acc = (uint8_t*)malloc(nc);
+  if (mt > 1) {
+    mt_xp = (double*)malloc(sizeof(double) * (size_t)mt * nc * d); mt_lp = (double*)malloc(sizeof(double) * (size_t)mt * nc);
+    mt_ll = (double*)malloc(sizeof(double) * (size_t)mt * nc); mt_fx = (double*)malloc(sizeof(double) * (size_t)mt * nc);
+    mt_id = (int*)malloc(sizeof(int) * (size_t)mt * nc); mt_zt = (double*)malloc(sizeof(double) * (size_t)nc * d);
+    mt_lpz = (double*)malloc(sizeof(double) * nc); mt_llz = (double*)malloc(sizeof(double) * nc); mt_fxz = (double*)malloc(sizeof(double) * nc);
+    mt_lpostzp = (double*)malloc(sizeof(double) * (size_t)mt * nc);
+    c.n_sets = 2 * mt - 1;
+  }
   int64_t m_arch = m0, m_cap = m0 + (au ? nc * (t / au + 1) : 0);
   if (cfg->past_sample) z = (double*)malloc(sizeof(double) * (size_t)m_cap * d);
 
@@ -889,6 +904,94 @@ int hbo_run(const hb_config* cfg, const hbo_target* tgt, const double* par_min, 
     if (!seq) {
       /* ---- synchronous sweep: R/dream_parallel.R:269-378 ---- */
       int perr = 0;
+      int64_t nacc = 0;
+      if (mt > 1) {
+        /* ---- MT-DREAM, R/dream_parallel.R:269-336 + metropolis_acceptance R/internals.R:227-236 ---- */
+        /* stage 1: mt proposal sets around xt, try-major (replicate(mt, lapply(1:nc, ...)) :269) */
+        for (int m = 0; m < mt && !perr; ++m) {
+          c.set = m;
+          for (int64_t j = 0; j < nc; ++j) {
+            prop_info_t inf; int e;
+            double* xpm = mt_xp + ((size_t)m * nc + j) * d;
+            e = calc_prop(&c, i, j, xt, z, m_arch, pCR, xpm, &inf, ztb);
+            if (e) { perr = e == HB_ERR_NONFINITE ? -1 : -5; break; }
+            mt_id[(size_t)m * nc + j] = inf.id;
+            mt_lp[(size_t)m * nc + j] = prior_pdf(&c, xpm, &e);                 /* :275 */
+            if (e) { perr = -2; break; }
+            mt_ll[(size_t)m * nc + j] = eval_target(&c, xpm, scr, &mt_fx[(size_t)m * nc + j], &e);   /* :278-289 */
+            if (e) { perr = e == HB_ERR_NONFINITE ? -3 : -6; break; }
+          }
+        }
+        /* candidate selection per chain, :297-307 */
+        for (int64_t j = 0; j < nc && !perr; ++j) {
+          int pick;
+          const int64_t gix = (i - 2) * c.nct + c.run * nc + j;
+          if (cfg->rng_mode == HB_RNG_TAPE) {
+            if (!tape->mt_pick) { perr = -5; break; }
+            pick = tape->mt_pick[gix];
+            if (pick < 0 || pick >= mt) { perr = -5; break; }
+          } else {
+            long double psum = 0;
+            double lps[64];
+            for (int m = 0; m < mt; ++m) { lps[m] = exp(mt_lp[(size_t)m * nc + j] + mt_ll[(size_t)m * nc + j]); psum += (long double)lps[m]; }
+            phx_t ph; uint32_t w[4];
+            phx_init(&ph, cfg->seed, (uint64_t)(c.run * nc + j), (uint32_t)i);
+            phx_slot(&ph, 7, w);                                                  /* slot 7: the multi-try selection uniform */
+            const double u = u53(pair64(w, 0));
+            double cum = 0; pick = mt - 1;
+            for (int m = 0; m < mt; ++m) {
+              cum += (psum == 0) ? 1.0 / mt : lps[m] / (double)psum;              /* :301-305 */
+              if (u < cum) { pick = m; break; }
+            }
+          }
+          if (c.rec && c.rec->mt_pick) ((uint8_t*)c.rec->mt_pick)[gix] = (uint8_t)pick;
+          const size_t sel = (size_t)pick * nc + j;                               /* :308 */
+          for (int k = 0; k < d; ++k) mt_zt[j * d + k] = mt_xp[sel * d + k];
+          mt_lpz[j] = mt_lp[sel]; mt_llz[j] = mt_ll[sel]; mt_fxz[j] = mt_fx[sel]; ids[j] = mt_id[sel];   /* :309-314 */
+        }
+        /* stage 2: mt - 1 proposal sets around the candidates zt (calc_prop(j, zt, ...) :316), only their density is used */
+        for (int m = 0; m < mt - 1 && !perr; ++m) {
+          c.set = mt + m;
+          for (int64_t j = 0; j < nc; ++j) {
+            prop_info_t inf; int e; double fxd;
+            e = calc_prop(&c, i, j, mt_zt, z, m_arch, pCR, xp + j * d, &inf, ztb);
+            if (e) { perr = e == HB_ERR_NONFINITE ? -1 : -5; break; }
+            const double lpz = prior_pdf(&c, xp + j * d, &e);                     /* :321 */
+            if (e) { perr = -2; break; }
+            const double llz = eval_target(&c, xp + j * d, scr, &fxd, &e);        /* :323-331 */
+            if (e) { perr = e == HB_ERR_NONFINITE ? -3 : -6; break; }
+            mt_lpostzp[(size_t)m * nc + j] = lpz + llz;                           /* :333 */
+          }
+        }
+        c.set = 0;
+        if (perr == -1) FAIL(HB_ERR_NONFINITE, nonfinite_msg(0));
+        if (perr == -2) FAIL(HB_ERR_NONFINITE, nonfinite_msg(1));
+        if (perr == -3) FAIL(HB_ERR_NONFINITE, nonfinite_msg(2));
+        if (perr == -5) FAIL(HB_ERR_INVALID, "invalid tape record (D, partner, id or mt_pick out of range)");
+        if (perr == -6) FAIL(HB_ERR_INVALID, "target evaluation failed (HydroModel: Argument 'param' has to be >= zero!)");
+        for (int64_t j = 0; j < nc; ++j) {                                        /* :340-341, R/internals.R:229-236 */
+          long double p1 = 0, p2 = 0;
+          for (int m = 0; m < mt; ++m) p1 += (long double)exp(mt_lp[(size_t)m * nc + j] + mt_ll[(size_t)m * nc + j]);
+          for (int m = 0; m < mt - 1; ++m) p2 += (long double)exp(mt_lpostzp[(size_t)m * nc + j]);
+          p2 += (long double)exp(lpost[j]);                                       /* :335  mt-th value: pdf(xt) */
+          int a = 0;
+          if ((double)p2 != 0) {
+            const double r = (double)p1 / (double)p2;
+            const double p_acc = r < 1 ? r : 1;
+            const double u = accept_uniform(&c, i, j);
+            a = p_acc > u;
+          }
+          acc[j] = (uint8_t)a;
+          if (a) {                                                                /* :349-355 */
+            for (int k = 0; k < d; ++k) { dxm[j * d + k] = mt_zt[j * d + k] - xt[j * d + k]; xt[j * d + k] = mt_zt[j * d + k]; }
+            lp[j] = mt_lpz[j]; ll[j] = mt_llz[j]; lpost[j] = mt_lpz[j] + mt_llz[j]; fxv[j] = mt_fxz[j];
+            nacc++;
+          } else {
+            for (int k = 0; k < d; ++k) dxm[j * d + k] = 0;
+          }
+          n_id[ids[j]] += 1;
+        }
+      } else {
 #pragma omp parallel for schedule(static) num_threads(nthr) if (nthr > 1)
       for (int64_t j = 0; j < nc; ++j) {
 #ifdef _OPENMP
@@ -910,7 +1013,6 @@ int hbo_run(const hb_config* cfg, const hbo_target* tgt, const double* par_min, 
       if (perr == -3) FAIL(HB_ERR_NONFINITE, nonfinite_msg(2));
       if (perr == -5) FAIL(HB_ERR_INVALID, "invalid tape record (D, partner or id out of range)");
       if (perr == -6) FAIL(HB_ERR_INVALID, "target evaluation failed (HydroModel: Argument 'param' has to be >= zero!)");
-      int64_t nacc = 0;
       for (int64_t j = 0; j < nc; ++j) {                      /* :343 */
         double lpx = lp_xp[j] + ll_xp[j];                     /* :291 */
         int a;
@@ -926,6 +1028,7 @@ int hbo_run(const hb_config* cfg, const hbo_target* tgt, const double* par_min, 
         }
         n_id[ids[j]] += 1;                                    /* :368-369 */
       }
+      }   /* mt == 1 */
       n_acc += (double)nacc; n_eval += (double)nc;            /* :374-375 */
       if (in_adapt) {                                         /* J only feeds the pCR update inside the adaptation period */
         col_sd(xt, nc, d, stdx);                              /* :376 post-update state */
@@ -1040,6 +1143,7 @@ done:
   free(xt); free(xp); free(lp); free(ll); free(lpost); free(lp_xp); free(ll_xp); free(fxv); free(fx_xp); free(hist);
   free(z); free(dxm); free(stdx); free(proxy); free(scr); free(ztb); free(outl); free(news); free(cand); free(ids);
   free(acc); free(c.prior_R);
+  free(mt_xp); free(mt_lp); free(mt_ll); free(mt_fx); free(mt_zt); free(mt_lpz); free(mt_llz); free(mt_fxz); free(mt_lpostzp); free(mt_id);
   if (tgt->kind == HBO_TARGET_TDIST) tdist_free(&c.td);
   return rc;
 }

@@ -165,19 +165,22 @@ def logdensity(name, lik, x, forcing=None, obs=None, glue_shape=0.0, abc_e=None)
 class Tape:
     """Owns the numpy arrays behind an hb_tape (layout of SURVEY Appendix D)."""
 
-    def __init__(self, n_gen, nct, d, delta, n_events, snooker=False):
+    def __init__(self, n_gen, nct, d, delta, n_events, snooker=False, mt=1):
         self.n_gen, self.nct, self.d, self.delta, self.n_events = n_gen, nct, d, delta, n_events
-        self.u_snooker = np.ones((n_gen, nct)) if snooker else None
-        self.D = np.zeros((n_gen, nct), np.uint8)
-        self.partners = np.full((n_gen, nct, 2 * delta), -1, np.int32)
-        self.id = np.zeros((n_gen, nct), np.uint8)
-        self.zt = np.zeros((n_gen, nct, d))
-        self.lambda_ = np.zeros((n_gen, nct, d))
-        self.g_is_one = np.zeros((n_gen, nct), np.uint8)
-        self.zeta = np.zeros((n_gen, nct, d))
-        self.g_snooker = np.full((n_gen, nct), 1.7) if snooker else None
+        self.n_sets = 2 * mt - 1 if mt > 1 else 1      # MT-DREAM: proposal sets per generation (hb_tape.n_sets)
+        rows = n_gen * self.n_sets
+        self.u_snooker = np.ones((rows, nct)) if snooker else None
+        self.D = np.zeros((rows, nct), np.uint8)
+        self.partners = np.full((rows, nct, 2 * delta), -1, np.int32)
+        self.id = np.zeros((rows, nct), np.uint8)
+        self.zt = np.zeros((rows, nct, d))
+        self.lambda_ = np.zeros((rows, nct, d))
+        self.g_is_one = np.zeros((rows, nct), np.uint8)
+        self.zeta = np.zeros((rows, nct, d))
+        self.g_snooker = np.full((rows, nct), 1.7) if snooker else None
         self.u_accept = np.zeros((n_gen, nct))
         self.outlier_new = np.full((max(n_events, 1), nct), -1, np.int32)
+        self.mt_pick = np.zeros((n_gen, nct), np.uint8) if mt > 1 else None
 
     def struct(self) -> HbTape:
         t = HbTape()
@@ -194,13 +197,15 @@ class Tape:
         t.g_snooker = _p(self.g_snooker)
         t.u_accept = _p(self.u_accept)
         t.outlier_new = self.outlier_new.ctypes.data_as(i32)
+        t.n_sets = self.n_sets
+        t.mt_pick = self.mt_pick.ctypes.data_as(u8) if self.mt_pick is not None else None
         return t
 
     @classmethod
     def for_config(cls, cfg: HbConfig):
         nct = max(cfg.n_runs, 1) * cfg.nc
         n_events = cfg.t // cfg.update_interval
-        return cls(cfg.t - 1, nct, cfg.d, cfg.delta, n_events, snooker=cfg.psnooker > 0)
+        return cls(cfg.t - 1, nct, cfg.d, cfg.delta, n_events, snooker=cfg.psnooker > 0, mt=max(cfg.mt, 1))
 
 
 def out_dims(cfg: HbConfig):

@@ -153,6 +153,59 @@ def test_replay_hydromodel_glue(hb, oracle, bound):
     H.assert_run_parity(dev, ora, rtol=1e-11)
 
 
+# ---------------------------------------------------------------- MT-DREAM, mt > 1 ----------------
+@pytest.mark.parametrize("mt,d,nc", [(3, 4, 16), (2, 40, 64), (5, 1, 12)])
+def test_replay_multi_try(hb, oracle, mt, d, nc):
+    # R/dream_parallel.R:295-341: mt proposal sets around xt, candidate selection ~ exp(lpost), mt-1 reference sets around
+    # the candidates zt (their partners come from zt, :316), acceptance min(1, sum exp(lpost_xp) / sum exp(lpost_zp))
+    # (R/internals.R:229-236).  The tape carries 2*mt-1 proposal sets per generation and the selection decisions.
+    if d == 1:
+        cfg = A.default_config(nc=nc, t=300, d=1, lik=1, seed=37, mt=mt, adapt=0.3)
+        dev, ora = _replay_case(oracle, cfg, "mixture", H.x0_mixture(nc))
+    else:
+        cfg = A.default_config(nc=nc, t=150, d=d, lik=2, seed=37, mt=mt, adapt=0.4)
+        dev, ora = _replay_case(oracle, cfg, "t_distribution", H.x0_tdist(nc, d))
+    H.assert_run_parity(dev, ora, rtol=1e-12)
+    assert ora["accept"].mean() > 0.1
+
+
+def test_multi_try_native_matches_oracle_philox(hb, oracle):
+    cfg = A.default_config(nc=24, t=200, d=6, lik=2, seed=41, mt=3, adapt=0.3, record_accept=1)
+    x0 = H.x0_tdist(24, 6)
+    dev = H.run_device(cfg, "t_distribution", x0)
+    ora = oracle.run(cfg, "t_distribution", x0)
+    H.assert_run_parity(dev, ora, rtol=1e-9, atol=1e-12)
+
+
+def test_multi_try_zs_snooker(hb, oracle):
+    nc, d = 4, 5
+    cfg = A.default_config(nc=nc, t=200, d=d, lik=2, seed=43, mt=2, past_sample=1, psnooker=0.2)
+    x0 = np.random.default_rng(3).uniform(-5, 15, size=(10 * d, d))
+    dev, ora = _replay_case(oracle, cfg, "t_distribution", x0)
+    H.assert_run_parity(dev, ora, rtol=1e-11)
+
+
+def test_multi_try_raises_acceptance(hb):
+    # the point of MT-DREAM (Laloy and Vrugt 2012): more tries per generation, higher acceptance, same posterior
+    x0 = H.x0_tdist(256, 10)
+    acc = {}
+    for mt in (1, 4):
+        cfg = A.default_config(nc=256, t=600, d=10, lik=2, seed=5, mt=mt, record_accept=1)
+        r = H.run_device(cfg, "t_distribution", x0)
+        acc[mt] = r["accept"][300:].mean()
+        v = r["chain"][300:, :10, :].var(axis=(0, 2))
+        np.testing.assert_allclose(v, 60.0 / 58.0 * np.arange(1, 11), rtol=0.2)      # Var(x_i) = 60/58 * i
+    assert acc[4] > 1.5 * acc[1]
+
+
+def test_multi_try_unsupported_combinations(hb):
+    from hydrobayes_b200 import Sampler
+    with pytest.raises(A.HbError, match="synchronous sweep"):
+        Sampler(A.default_config(nc=8, t=10, d=2, lik=2, mt=3, sweep=A.HB_SWEEP_SEQUENTIAL), 0)
+    with pytest.raises(A.HbError, match="ABC method cannot be combined"):
+        Sampler(A.default_config(nc=8, t=10, d=1, lik=22, mt=3), 0)
+
+
 # ---------------------------------------------------------------- likelihood flags 21 / 22 / 99 on HydroModel
 @pytest.mark.parametrize("sweep", [A.HB_SWEEP_SYNCHRONOUS, A.HB_SWEEP_SEQUENTIAL])
 @pytest.mark.parametrize("lik,abc", [(21, 0.8), (21, "vector"), (22, 2.5), (22, "vector"), (99, None)])
