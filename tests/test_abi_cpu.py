@@ -70,7 +70,7 @@ def test_argument_checks_before_device(L):
     cfg = A.default_config(nc=10, t=10, d=1, lik=7)
     assert L.hb_create(C.byref(cfg), 0, C.byref(h)) == A.HB_ERR_INVALID
     assert b"'lik' has to be one of" in L.hb_last_error(None)
-    cfg = A.default_config(nc=10, t=10, d=1, lik=1, mt=3)
+    cfg = A.default_config(nc=10, t=10, d=1, lik=1, mt=3, sweep=A.HB_SWEEP_SEQUENTIAL)   # MT-DREAM: dream_parallel only
     assert L.hb_create(C.byref(cfg), 0, C.byref(h)) == A.HB_ERR_UNSUPPORTED
 
 
