@@ -23,7 +23,10 @@ dream_parallel <- function(fun, ..., lik = NULL,
   h <- .Call("hbR_create", cfg, as.integer(device))           # argument checks of :166-175 happen inside, same wording
   if (!is.null(par.info$min) && !is.null(par.info$max))
     .Call("hbR_set_bounds", h, as.numeric(par.info$min), as.numeric(par.info$max))
+  if (par.info$prior == "normal") .Call("hbR_set_prior_normal", h, as.numeric(par.info$mu), as.matrix(par.info$cov))
   if (!is.null(obs)) .Call("hbR_set_obs", h, as.numeric(obs))
+  if (!is.null(abc_rho) || !is.null(lik_fun))                   # names, as in the reference: get(abc_rho), get(lik_fun)
+    .Call("hbR_set_lik_args", h, abc_rho, if (is.null(abc_e)) NULL else as.numeric(abc_e), lik_fun)
   dots <- list(...)
   .Call("hbR_set_target", h, fun, if (length(dots)) as.numeric(dots[[1]]) else NULL)   # get(fun)(x, ...) :219
   n0 <- if (past_sample) (if (is.null(m0)) 10 * d else m0) else nc
@@ -43,7 +46,33 @@ dream_parallel <- function(fun, ..., lik = NULL,
   .Call("hbR_fetch_chain", h, chain)
   res <- .Call("hbR_fetch", h)
   out_AR <- res[[2]]; colnames(out_AR) <- c("n_eval", "accepted")
-  list(chain = chain, fx = NULL, runtime = Sys.time() - timea, outlier = list(NULL), AR = out_AR, CR = res[[3]])
+  fx <- if (fun %in% c("mixture", "t_distribution")) .Call("hbR_fetch_fx", h, array(NA_real_, dim = c(out_t, nc, 1))) else NULL
+  op <- .Call("hbR_fetch_outliers", h)                         # outl[[i]] <- check_out$outliers  (:418)
+  n_chk <- floor(adapt * t / updateInterval)
+  outl <- list(NULL)
+  if (outlier_check && !past_sample && n_chk > 0)
+    for (i in updateInterval * seq_len(n_chk)) outl[[i]] <- op[[2]][op[[1]] == i]
+  output <- list(chain = chain, fx = fx, runtime = Sys.time() - timea, outlier = outl, AR = out_AR, CR = res[[3]])
+  if (checkConvergence && out_t > 50)
+    output[["R_stat"]] <- .Call("hbR_fetch_rstat", h, matrix(NA_real_, nrow = out_t - 50, ncol = d))
+  output
+}
+
+# dream(): the same driver with the sequential sweep (R/dream.R:126-316); default prior "uniform" (:127), no archive / MT
+dream <- function(fun, ..., lik = NULL,
+                  par.info = list(initial = NULL, min = NULL, max = NULL, mu = NULL, cov = NULL, val_ini = NULL,
+                                  bound = NULL, names = NULL, prior = "uniform"),
+                  nc, t, d, burnin = 0, adapt = 0.1, updateInterval = 10, delta = 3, c_val = 0.1, c_star = 1e-12,
+                  nCR = 3, p_g = 0.2, beta0 = 1, thin = 1, outlier_check = TRUE, obs = NULL, abc_rho = NULL, abc_e = NULL,
+                  glue_shape = NULL, lik_fun = NULL, checkConvergence = FALSE, verbose = TRUE, seed = 1312, device = 0L) {
+  if (nc <= 2 * delta) stop("Argument 'nc' must be > 'delta' * 2!")      # R/dream.R:136-137
+  .hb_drive(sweep = 1L, fun = fun, ..., lik = lik, par.info = par.info, nc = nc, t = t, d = d, burnin = burnin,
+            adapt = adapt, updateInterval = updateInterval, delta = delta, c_val = c_val, c_star = c_star, nCR = nCR,
+            p_g = p_g, beta0 = beta0, thin = thin, outlier_check = outlier_check, obs = obs, abc_rho = abc_rho,
+            abc_e = abc_e, glue_shape = glue_shape, lik_fun = lik_fun, checkConvergence = checkConvergence,
+            verbose = verbose, seed = seed, device = device)
+  # .hb_drive is the body of dream_parallel() above with cfg$sweep taken from its first argument; AR / CR come back
+  # as [out_t, nCR] (R/dream.R:161-162) -- hb_out_dims reports the shapes for either sweep
 }
 
 R_stat <- function(x) invisible(.Call("hbR_rstat_array", x))   # R/gelman_rubin.R:21

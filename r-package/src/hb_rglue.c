@@ -56,6 +56,16 @@ SEXP hbR_create(SEXP cfg_list, SEXP device) {
 
 SEXP hbR_set_bounds(SEXP p, SEXP mn, SEXP mx) { chk(H(p), hb_set_bounds(H(p), REAL(mn), REAL(mx), length(mn))); return R_NilValue; }
 SEXP hbR_set_obs(SEXP p, SEXP obs) { chk(H(p), hb_set_obs(H(p), REAL(obs), (int64_t)XLENGTH(obs))); return R_NilValue; }
+SEXP hbR_set_prior_normal(SEXP p, SEXP mu, SEXP cov) {   /* par.info$mu, par.info$cov (prior = "normal", R/internals.R:58-59) */
+  chk(H(p), hb_set_prior_normal(H(p), REAL(mu), REAL(cov)));
+  return R_NilValue;
+}
+/* abc_rho=, abc_e=, lik_fun= : function NAMES, resolved in the device registry (R/internals.R:10,12,16) */
+SEXP hbR_set_lik_args(SEXP p, SEXP abc_rho, SEXP abc_e, SEXP lik_fun) {
+  chk(H(p), hb_set_lik_args(H(p), isNull(abc_rho) ? NULL : CHAR(STRING_ELT(abc_rho, 0)), isNull(abc_e) ? NULL : REAL(abc_e),
+                            isNull(abc_e) ? 0 : (int64_t)XLENGTH(abc_e), isNull(lik_fun) ? NULL : CHAR(STRING_ELT(lik_fun, 0))));
+  return R_NilValue;
+}
 SEXP hbR_set_target(SEXP p, SEXP fun, SEXP data) {   /* get(fun)(x, ...) -> name-keyed device plugin */
   int64_t dims[1] = { isNull(data) ? 0 : (int64_t)XLENGTH(data) };
   chk(H(p), hb_set_target(H(p), CHAR(STRING_ELT(fun, 0)), isNull(data) ? NULL : REAL(data), dims, isNull(data) ? 0 : 1));
@@ -78,6 +88,22 @@ SEXP hbR_fetch(SEXP p) {                            /* list(chain, AR, CR [, fx,
   SEXP ar = PROTECT(allocMatrix(REALSXP, (int)ar_r, (int)ar_c)); chk(h, hb_fetch_ar(h, REAL(ar)));
   SEXP cr = PROTECT(allocMatrix(REALSXP, (int)cr_r, (int)cr_c)); chk(h, hb_fetch_cr(h, REAL(cr)));
   SET_VECTOR_ELT(res, 1, ar); SET_VECTOR_ELT(res, 2, cr);
+  UNPROTECT(3);
+  return res;
+}
+SEXP hbR_fetch_fx(SEXP p, SEXP fx) { chk(H(p), hb_fetch_fx(H(p), REAL(fx))); return fx; }            /* fx[out_t, nc, m] :203 */
+SEXP hbR_fetch_rstat(SEXP p, SEXP rs) { chk(H(p), hb_fetch_rstat(H(p), REAL(rs))); return rs; }     /* R_stat[out_t-50, d] */
+SEXP hbR_fetch_outliers(SEXP p) {                   /* two integer vectors: generation i and 1-based chain (outl[[i]], :418) */
+  hb_handle* h = H(p);
+  int64_t n = 0;
+  chk(h, hb_fetch_outliers(h, &n, NULL, NULL, 0));
+  int64_t* g = (int64_t*)R_alloc((size_t)(n > 0 ? n : 1), sizeof(int64_t));
+  int64_t* c = (int64_t*)R_alloc((size_t)(n > 0 ? n : 1), sizeof(int64_t));
+  chk(h, hb_fetch_outliers(h, &n, g, c, n));
+  SEXP res = PROTECT(allocVector(VECSXP, 2));
+  SEXP gi = PROTECT(allocVector(INTSXP, (R_xlen_t)n)), ci = PROTECT(allocVector(INTSXP, (R_xlen_t)n));
+  for (int64_t q = 0; q < n; ++q) { INTEGER(gi)[q] = (int)g[q]; INTEGER(ci)[q] = (int)c[q] + 1; }
+  SET_VECTOR_ELT(res, 0, gi); SET_VECTOR_ELT(res, 1, ci);
   UNPROTECT(3);
   return res;
 }
