@@ -422,6 +422,39 @@ int hb_fail(hb_handle* h, int code, const char* msg) { if (h) h->err = msg; retu
 
 namespace {
 
+// sum `n` doubles over the ranks, in place (HB_EXCHANGE_DELTA: peer-memory all-reduce in rank order; else NCCL)
+int allreduce_small(hb_handle* h, double* buf, int n) {
+  if (h->world <= 1) return HB_OK;
+  if (h->delta_mode) {
+    hb_arena_peers ap; for (int r = 0; r < 8; ++r) ap.p[r] = h->arena_peer[r];
+    hb_peer_reduce_desc rd{};
+    rd.f64[0] = buf; rd.n_f64[0] = n; rd.f64[1] = buf; rd.n_f64[1] = 0; rd.u64 = nullptr; rd.n_u64 = 0;
+    if ((size_t)n * 8 > h->arena_red_bytes) return fail(h, HB_ERR_UNSUPPORTED, "all-reduce of %d doubles exceeds the arena slot", n);
+    ++h->red_seq;
+    CK(hb_launch_peer_allreduce(ap, h->arena_red_off + (size_t)(h->red_seq & 1u) * h->arena_red_bytes, rd, h->rank, h->world,
+                                h->red_seq, &h->ctrl->err, h->stream));
+    return HB_OK;
+  }
+  return hb_nccl_allreduce_f64(h->comm, buf, (size_t)n, h->stream, h->err);
+}
+
+// R_stat(chain[1:t_rows, 1:d, ]) of the whole population into out_dev[d]; on several GPUs the per-chain statistics of
+// the shards are combined with two small all-reduces (sums, then squared deviations from the global mean)
+int rstat_population(hb_handle* h, long long t_rows, double* out_dev) {
+  const long long nl = h->n_local; const int d = h->d;
+  if (h->world <= 1) {
+    CK(hb_launch_rstat(h->hist_x, t_rows, nl, 0, nl, d, h->rstat_xm, h->rstat_ss, out_dev, h->stream));
+    return HB_OK;
+  }
+  if (!h->rstat_sums) CK(dalloc(&h->rstat_sums, (size_t)3 * d));
+  CK(hb_launch_rstat_shard_pass1(h->hist_x, t_rows, nl, d, h->rstat_xm, h->rstat_ss, h->rstat_sums, h->stream));
+  if (int rc = allreduce_small(h, h->rstat_sums, 2 * d)) return rc;
+  CK(hb_launch_rstat_shard_dev(h->rstat_xm, nl, d, h->nc, h->rstat_sums, h->rstat_sums + 2 * d, h->stream));
+  if (int rc = allreduce_small(h, h->rstat_sums + 2 * d, d)) return rc;
+  CK(hb_launch_rstat_shard_final(h->rstat_sums, h->rstat_sums + 2 * d, t_rows, h->nc, d, out_dev, h->stream));
+  return HB_OK;
+}
+
 int run_generation(hb_handle* h, long long i) {
   const hb_config& c = h->cfg;
   const long long nl = h->n_local;
@@ -559,7 +592,7 @@ int run_generation(hb_handle* h, long long i) {
   }
   if (c.check_convergence && store && h->ind_out > 50) {   // R_stat(chain[1:ind_out, 1:d, ]) as R/dream_test.R:344
     prof_scope ps(h, "K4");
-    CK(hb_launch_rstat(h->hist_x, h->ind_out, nl, 0, nl, d, h->rstat_xm, h->rstat_ss, h->rstat_dev + (size_t)(h->ind_out - 51) * d, h->stream));
+    if (int rc = rstat_population(h, h->ind_out, h->rstat_dev + (size_t)(h->ind_out - 51) * d)) return rc;
     ps.done(2);
   }
   if (in_adapt && upd && !c.past_sample && c.outlier_check) {                        // :414-419
@@ -708,7 +741,7 @@ void hb_destroy(hb_handle* h) {
   void* ptrs[] = {h->X, h->Z, h->XP, h->id, h->lp_xp, h->ll_raw, h->fx_xp, h->lp, h->ll, h->lpost, h->fx, h->lpost_hist,
                   h->hist_x, h->hist_l, h->hist_fx, h->accept_rec, h->ctrl, h->shift, h->colsum, h->qsum, h->partials,
                   h->out_ar, h->out_cr, h->proxy, h->proxy_full, h->lpost_full, h->outl_dev, h->news_dev, h->rstat_dev,
-                  h->rstat_xm, h->rstat_ss, h->stage, h->pmin, h->pmax, h->prior_W, h->prior_mu, h->ZT, h->lp_zt, h->ll_zt, h->fx_zt, h->id_zt, h->mt_p1, h->mt_accept, h->gamma_tab, h->outl_tmp, h->outl_sorted, h->outl_thr,
+                  h->rstat_xm, h->rstat_ss, h->stage, h->pmin, h->pmax, h->prior_W, h->prior_mu, h->ZT, h->lp_zt, h->ll_zt, h->fx_zt, h->id_zt, h->mt_p1, h->mt_accept, h->rstat_sums, h->gamma_tab, h->outl_tmp, h->outl_sorted, h->outl_thr,
                   h->outl_count};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (void* p : h->tape_allocs) cudaFree(p);
@@ -1226,12 +1259,11 @@ int hb_rstat(hb_handle* h, double* out_d) {
   if (!h || !out_d) return HB_ERR_INVALID;
   if (!h->initialised) return fail(h, HB_ERR_STATE, "nothing has been run yet");
   if (h->ind_out < 3) return fail(h, HB_ERR_INVALID, "R_stat needs at least 3 stored generations");
-  if (h->world > 1) return fail(h, HB_ERR_UNSUPPORTED, "hb_rstat on a sharded population is not wired yet");
   cudaSetDevice(h->device);
   double* o = nullptr;
   CK(dalloc(&o, (size_t)h->d));
   prof_scope ps(h, "K4");
-  CK(hb_launch_rstat(h->hist_x, h->ind_out, h->n_local, 0, h->n_local, h->d, h->rstat_xm, h->rstat_ss, o, h->stream));
+  if (int rc = rstat_population(h, h->ind_out, o)) { cudaFree(o); return rc; }   // collective on a sharded population
   ps.done(2);
   CK(cudaMemcpyAsync(out_d, o, sizeof(double) * h->d, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));

@@ -63,6 +63,7 @@ struct hb_handle {
   // MT-DREAM (mt > 1): candidate population and its scalars, multi-try sums, decisions
   double* ZT = nullptr; double* lp_zt = nullptr; double* ll_zt = nullptr; double* fx_zt = nullptr; int* id_zt = nullptr;
   double* mt_p1 = nullptr; uint8_t* mt_accept = nullptr;
+  double* rstat_sums = nullptr;   // [3d] scratch of the sharded R_stat (sums, then deviations)
   const uint8_t* tape_mt_pick = nullptr;
   // likelihood closures named by the R call: abc_rho / abc_e (lik 21, 22), lik_fun (lik 99)
   std::string abc_rho, lik_fun;

@@ -200,6 +200,14 @@ cudaError_t hb_launch_chain_transpose(const double* hist_x, const double* hist_l
 cudaError_t hb_launch_rstat(const double* hist_x, long long t_rows, long long nct_stride, long long c0, long long n,
                             int d, double* xm_scratch, double* ss_scratch, double* out_d, cudaStream_t st);
 // same on an R-layout array x[t, d, n] (column-major)
+// sharded population (multi-GPU): pass 1 + local sums [2d] -> (all-reduce) -> squared deviations from the global mean [d]
+// -> (all-reduce) -> R_stat
+cudaError_t hb_launch_rstat_shard_pass1(const double* hist_x, long long t_rows, long long n_local, int d, double* xm,
+                                        double* ss, double* sums2d, cudaStream_t st);
+cudaError_t hb_launch_rstat_shard_dev(const double* xm, long long n_local, int d, long long n_total, const double* sums2d,
+                                      double* bsum, cudaStream_t st);
+cudaError_t hb_launch_rstat_shard_final(const double* sums2d, const double* bsum, long long t_rows, long long n_total, int d,
+                                        double* out_d, cudaStream_t st);
 // per-run variant: out[run*d + k] for runs of nc consecutive chains (pass 1 over all chains, pass 2 one warp per (run, k))
 cudaError_t hb_launch_rstat_runs(const double* hist_x, long long t_rows, long long nct, long long nc, long long n_runs,
                                  int d, double* xm_scratch, double* ss_scratch, double* out_runs_d, cudaStream_t st);

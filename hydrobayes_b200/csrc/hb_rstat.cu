@@ -117,7 +117,58 @@ __global__ void hb_rstat_pass2_runs(const double* __restrict__ xm, const double*
   }
 }
 
+// ---- sharded population: the chains of one R_stat live on several GPUs --------------------------------------------
+// local sums per parameter: out[k] = sum_c ss, out[d + k] = sum_c x_mean_c  (all-reduced by the caller)
+__global__ void hb_rstat_shard_sums(const double* __restrict__ xm, const double* __restrict__ ss, long long n, int d,
+                                    double* __restrict__ out) {
+  __shared__ double red[33];
+  const int k = blockIdx.x;
+  double w = 0, m = 0;
+  for (long long c = threadIdx.x; c < n; c += blockDim.x) { w += ss[c * d + k]; m += xm[c * d + k]; }
+  const double wsum = block_sum(w, red);
+  const double msum = block_sum(m, red);
+  if (threadIdx.x == 0) { out[k] = wsum; out[d + k] = msum; }
+}
+// local sum of squared deviations from the GLOBAL mean of the chain means (second pass, all-reduced by the caller)
+__global__ void hb_rstat_shard_dev(const double* __restrict__ xm, long long n, int d, long long n_total,
+                                   const double* __restrict__ sums, double* __restrict__ out) {
+  __shared__ double red[33];
+  const int k = blockIdx.x;
+  const double xmm = sums[d + k] / (double)n_total;
+  double b = 0;
+  for (long long c = threadIdx.x; c < n; c += blockDim.x) { const double e = xm[c * d + k] - xmm; b += e * e; }
+  const double bsum = block_sum(b, red);
+  if (threadIdx.x == 0) out[k] = bsum;
+}
+__global__ void hb_rstat_shard_final(const double* __restrict__ sums, const double* __restrict__ bsum, long long t,
+                                     long long n, int d, double* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= d) return;
+  const double W = 2.0 / ((double)n * (double)(t - 2)) * sums[k];
+  const double B = 1.0 / (2.0 * (double)(n - 1)) * bsum[k];
+  const double sigma = (double)(t - 2) / (double)t * W + 2.0 * B;
+  out[k] = sqrt((double)(n + 1) / (double)n * sigma / W - (double)(t - 2) / ((double)n * (double)t));
+}
+
 }  // namespace
+
+cudaError_t hb_launch_rstat_shard_pass1(const double* hist_x, long long t_rows, long long n_local, int d, double* xm,
+                                        double* ss, double* sums2d, cudaStream_t st) {
+  const long long tot = n_local * d;
+  hb_rstat_pass1_hist<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(hist_x, t_rows, n_local, 0, n_local, d, xm, ss);
+  hb_rstat_shard_sums<<<d, 256, 0, st>>>(xm, ss, n_local, d, sums2d);
+  return cudaGetLastError();
+}
+cudaError_t hb_launch_rstat_shard_dev(const double* xm, long long n_local, int d, long long n_total, const double* sums2d,
+                                      double* bsum, cudaStream_t st) {
+  hb_rstat_shard_dev<<<d, 256, 0, st>>>(xm, n_local, d, n_total, sums2d, bsum);
+  return cudaGetLastError();
+}
+cudaError_t hb_launch_rstat_shard_final(const double* sums2d, const double* bsum, long long t_rows, long long n_total, int d,
+                                        double* out_d, cudaStream_t st) {
+  hb_rstat_shard_final<<<(d + 127) / 128, 128, 0, st>>>(sums2d, bsum, t_rows, n_total, d, out_d);
+  return cudaGetLastError();
+}
 
 cudaError_t hb_launch_rstat_runs(const double* hist_x, long long t_rows, long long nct, long long nc, long long n_runs,
                                  int d, double* xm_scratch, double* ss_scratch, double* out_runs_d, cudaStream_t st) {

@@ -40,7 +40,10 @@ def run(cfg, target, x0, local, rank=0, world=1, uid=None, kw={}, peer=False, sh
         xt, lp, ll, lpost = s.fetch_state(nl)
         if not shard_state and world > 1:
             xt = xt[rank * nl:(rank + 1) * nl]
-        return dict(chain=chain, AR=ar, CR=cr, accept=acc, xt=xt, lpost=lpost, outlier=s.fetch_outliers())
+        out = dict(chain=chain, AR=ar, CR=cr, accept=acc, xt=xt, lpost=lpost, outlier=s.fetch_outliers())
+        if cfg.check_convergence:   # R_stat of the WHOLE population: collective on a sharded handle
+            out["R_stat"] = s.fetch_rstat(); out["rstat_now"] = s.rstat()
+        return out
 
 
 def main():
@@ -51,7 +54,7 @@ def main():
     cases = []
     nc, d = 64 * world, 100
     x0 = H.x0_tdist(nc, d); x0[3] = 300.0; x0[nc - 2] = -250.0     # forces outlier resets across shards
-    cases.append(("tdist d=100", A.default_config(nc=nc, t=150, d=d, lik=2, seed=5, adapt=0.4, record_accept=1), "t_distribution", x0, {}))
+    cases.append(("tdist d=100", A.default_config(nc=nc, t=150, d=d, lik=2, seed=5, adapt=0.4, record_accept=1, check_convergence=1), "t_distribution", x0, {}))
     nc1 = 512 * world
     cases.append(("mixture d=1", A.default_config(nc=nc1, t=200, d=1, lik=1, seed=9, adapt=0.3, record_accept=1), "mixture", H.x0_mixture(nc1), {}))
     cases = [c + (0,) for c in cases] + [c + (1,) for c in cases if c[1].d > 16] + [c + (2,) for c in cases]
@@ -72,6 +75,11 @@ def main():
                 and np.array_equal(sh["xt"], full["xt"][lo:lo + nl]) and np.array_equal(sh["lpost"], full["lpost"][lo:lo + nl])
                 and sh["outlier"] == full["outlier"])
         close = np.allclose(sh["AR"], full["AR"], rtol=1e-12, equal_nan=True) and np.allclose(sh["CR"], full["CR"], rtol=1e-9, equal_nan=True)
+        if "R_stat" in full:
+            rs_ok = (np.allclose(sh["R_stat"], full["R_stat"], rtol=1e-9, equal_nan=True) and np.isfinite(full["R_stat"]).any()
+                     and np.allclose(sh["rstat_now"], full["rstat_now"], rtol=1e-9))
+            name += f" [sharded R_stat close: {rs_ok}]"
+            close = close and rs_ok
         print(f"[rank {rank}] {name}: shard == single-GPU run: {same}; AR/CR close: {close}; outliers {len(full['outlier'])}; "
               f"accept rate {full['accept'].mean():.3f}", flush=True)
         ok = ok and same and close
