@@ -323,12 +323,17 @@ __global__ void __launch_bounds__(256) hb_k1_kernel(const hb_k1_params p) {
 //   hb_k1_tape_kernel  replay mode: draws come from the decision tape, lane owns dimensions k = 32 m + lane.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int K1_STAGES = 2;
-constexpr int K1_HEAD_WORDS = 12;   // packed, a[4], b[4], third snooker row, g_snooker (2 words)
+constexpr int K1_HEAD_WORDS = 12;   // full layout: packed, a[4], b[4], third snooker row, g_snooker (2 words)
+// Without the archive (no snooker rows, no g_snooker) a head is packed | a[delta] | b[delta], rounded up to an even word
+// count: 8 words for delta = 3 -- the 4 KB per CTA this saves is what lets a ninth warp fit next to the stage buffers.
+__host__ __device__ inline int k1_head_words(int delta, int past_sample) {
+  return past_sample ? K1_HEAD_WORDS : ((1 + 2 * delta + 1) & ~1);
+}
 
 __host__ __device__ inline int k1_rows_max(int delta) { return (1 + 2 * delta) > 4 ? (1 + 2 * delta) : 4; }
-__host__ __device__ inline size_t k1_warp_smem_bytes(int delta, int ldx) {
+__host__ __device__ inline size_t k1_warp_smem_bytes(int delta, int ldx, int past_sample) {
   // [stage][row][ldx] doubles + 32 chain heads + mbarriers, 16-byte aligned pieces
-  return (size_t)K1_STAGES * k1_rows_max(delta) * ldx * 8 + 32 * K1_HEAD_WORDS * 4 + K1_STAGES * 8;
+  return (size_t)K1_STAGES * k1_rows_max(delta) * ldx * 8 + 32 * k1_head_words(delta, past_sample) * 4 + K1_STAGES * 8;
 }
 
 // phase A: the head of chain base + lane -> heads[lane][...].  Row ids are absolute rows of the source matrix
@@ -412,19 +417,24 @@ __device__ __forceinline__ void k1_phase_a(const hb_k1_params& p, long long base
   }
   if (sn && (hps2 < 0 || hps2 >= n_src)) { errbits |= HB_FLAG_BAD_TAPE; hps2 = 0; }
   const int roff = p.past_sample ? 0 : (int)(gl - j);               // first chain of this chain's run
-  int* hd = heads + lane * K1_HEAD_WORDS;
+  const int hw = k1_head_words(delta, p.past_sample);
+  const int boff = p.past_sample ? 1 + HB_MAX_DELTA : 1 + delta;
+  int* hd = heads + lane * hw;
   hd[0] = hD | (hid << 8) | ((g1 ? 1 : 0) << 16) | ((sn ? 1 : 0) << 17);
 #pragma unroll
-  for (int q = 0; q < HB_MAX_DELTA; ++q) { hd[1 + q] = hpa[q] + roff; hd[1 + HB_MAX_DELTA + q] = hpb[q] + roff; }
-  hd[1 + 2 * HB_MAX_DELTA] = hps2 + roff;
-  *reinterpret_cast<double*>(hd + 10) = hgsn;
+  for (int q = 0; q < HB_MAX_DELTA; ++q) if (q < delta) { hd[1 + q] = hpa[q] + roff; hd[boff + q] = hpb[q] + roff; }
+  if (p.past_sample) {
+    hd[1 + 2 * HB_MAX_DELTA] = hps2 + roff;
+    *reinterpret_cast<double*>(hd + 10) = hgsn;
+  }
 }
 
 // issue the bulk copies of the rows chain `c` of the current batch needs into stage buffer `dst`:
 // stage rows 0 = x, 1..D = a, 1+delta.. = b (fixed offsets: no D-dependent address arithmetic in the sweep)
 __device__ __forceinline__ void k1_issue(const hb_k1_params& p, const double* __restrict__ src, const int* heads, int c,
                                          long long base, double* dst, uint64_t* bar, int lane, uint32_t row_bytes) {
-  const int* hd = heads + c * K1_HEAD_WORDS;
+  const int* hd = heads + c * k1_head_words(p.delta, p.past_sample);
+  const int boff = p.past_sample ? 1 + HB_MAX_DELTA : 1 + p.delta;
   const int pk = hd[0];
   const int Dn = pk & 0xff;
   const bool sn = (pk >> 17) & 1;
@@ -437,7 +447,7 @@ __device__ __forceinline__ void k1_issue(const hb_k1_params& p, const double* __
     else {
       int row;
       if (sn) row = (lane == 1) ? hd[1] : (lane == 2) ? hd[1 + HB_MAX_DELTA] : hd[1 + 2 * HB_MAX_DELTA];
-      else row = (lane <= Dn) ? hd[lane] : hd[1 + HB_MAX_DELTA + (lane - 1 - Dn)];      // a[0..D-1], b[0..D-1]
+      else row = (lane <= Dn) ? hd[lane] : hd[boff + (lane - 1 - Dn)];                  // a[0..D-1], b[0..D-1]
       if (p.n_peers > 1) {                        // the row lives in rank rk's shard: NVLink peer pointer
         const int rk = (int)(row / p.peer_nl);
         g = p.peer[rk] + (long long)(row - rk * p.peer_nl) * p.ldx;
@@ -450,8 +460,10 @@ __device__ __forceinline__ void k1_issue(const hb_k1_params& p, const double* __
 
 __device__ __forceinline__ double2 lds2(const double* q) { return *reinterpret_cast<const double2*>(q); }
 
+constexpr int K1_PAIR_WARPS = 8;     // 2 CTAs x 8 warps per SM at 126 registers.  Measured: 9 warps (launch bounds 288 -> 96
+                                     // registers, spills) is 9 % SLOWER (1.174 vs 1.075 ms); 14 warps/SM is 13 % slower
 template <int ITER2>
-__global__ void __launch_bounds__(256, 2) hb_k1_pair_kernel(const hb_k1_params p) {
+__global__ void __launch_bounds__(K1_PAIR_WARPS * 32, 2) hb_k1_pair_kernel(const hb_k1_params p) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr bool KEEP = ITER2 <= 4;     // keep the Philox words of the subspace pass in registers (else recompute)
   extern __shared__ __align__(16) unsigned char k1_smem[];
@@ -464,10 +476,11 @@ __global__ void __launch_bounds__(256, 2) hb_k1_pair_kernel(const hb_k1_params p
   const int n_src = (int)(p.past_sample ? p.m_arch : p.nc);
   const int rows_max = k1_rows_max(delta);
   const uint32_t row_bytes = (uint32_t)ldx * 8u;
-  unsigned char* wbase = k1_smem + (size_t)wib * k1_warp_smem_bytes(delta, ldx);
+  const int hw = k1_head_words(delta, p.past_sample);
+  unsigned char* wbase = k1_smem + (size_t)wib * k1_warp_smem_bytes(delta, ldx, p.past_sample);
   double* stage_buf = reinterpret_cast<double*>(wbase);                                  // [STAGES][rows_max][ldx]
   int* heads = reinterpret_cast<int*>(wbase + (size_t)K1_STAGES * rows_max * ldx * 8);   // [32][HEAD_WORDS]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(heads + 32 * K1_HEAD_WORDS);              // [STAGES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(heads + 32 * hw);                         // [STAGES]
   unsigned errbits = 0;
   const bool bound_or_prior = (p.bound != 0) || (p.prior == 1);
 
@@ -494,7 +507,7 @@ __global__ void __launch_bounds__(256, 2) hb_k1_pair_kernel(const hb_k1_params p
 
     for (int c = 0; c < n_in_batch; ++c, ++it) {
       const int stg = (int)(it % K1_STAGES);
-      const int* hd = heads + c * K1_HEAD_WORDS;
+      const int* hd = heads + c * hw;
       const int pk = hd[0];
       const int D = pk & 0xff, id = (pk >> 8) & 0xff;
       const bool g_is_one = (pk >> 16) & 1, snooker = (pk >> 17) & 1;
@@ -708,10 +721,11 @@ __global__ void __launch_bounds__(256, 2) hb_k1_tape_kernel(const hb_k1_params p
   const int n_src = (int)(p.past_sample ? p.m_arch : p.nc);
   const int rows_max = k1_rows_max(delta);
   const uint32_t row_bytes = (uint32_t)ldx * 8u;
-  unsigned char* wbase = k1_smem + (size_t)wib * k1_warp_smem_bytes(delta, ldx);
+  const int hw = k1_head_words(delta, p.past_sample);
+  unsigned char* wbase = k1_smem + (size_t)wib * k1_warp_smem_bytes(delta, ldx, p.past_sample);
   double* stage_buf = reinterpret_cast<double*>(wbase);                                  // [STAGES][rows_max][ldx]
   int* heads = reinterpret_cast<int*>(wbase + (size_t)K1_STAGES * rows_max * ldx * 8);   // [32][HEAD_WORDS]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(heads + 32 * K1_HEAD_WORDS);              // [STAGES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(heads + 32 * hw);                         // [STAGES]
   unsigned errbits = 0;
   const bool bound_or_prior = (p.bound != 0) || (p.prior == 1);
 
@@ -738,7 +752,7 @@ __global__ void __launch_bounds__(256, 2) hb_k1_tape_kernel(const hb_k1_params p
 
     for (int c = 0; c < n_in_batch; ++c, ++it) {
       const int stg = (int)(it % K1_STAGES);
-      const int* hd = heads + c * K1_HEAD_WORDS;
+      const int* hd = heads + c * hw;
       const int pk = hd[0];
       const int D = pk & 0xff, id = (pk >> 8) & 0xff;
       const bool g_is_one = (pk >> 16) & 1, snooker = (pk >> 17) & 1;
@@ -894,10 +908,10 @@ __global__ void __launch_bounds__(256, 2) hb_k1_tape_kernel(const hb_k1_params p
   if (errbits) atomicOr(p.err, errbits);
 }
 
-inline void k1_wide_geometry(const hb_k1_params& p, int sm_count, int* threads, long long* blocks, size_t* smem) {
-  const size_t per_warp = (k1_warp_smem_bytes(p.delta, p.ldx) + 15) & ~(size_t)15;
-  int warps = 8;
-  while (warps > 1 && per_warp * warps > 110 * 1024) warps >>= 1;     // two CTAs per SM
+inline void k1_wide_geometry(const hb_k1_params& p, int sm_count, int max_warps, int* threads, long long* blocks, size_t* smem) {
+  const size_t per_warp = (k1_warp_smem_bytes(p.delta, p.ldx, p.past_sample) + 15) & ~(size_t)15;
+  int warps = max_warps;                                               // two CTAs per SM
+  while (warps > 1 && per_warp * warps * 2 + 4096 > 227 * 1024) warps = warps > 8 ? 8 : warps >> 1;
   int ctas = 2;
   if (const char* e = getenv("HB_K1_WARPS")) warps = atoi(e);          // tuning experiments only
   if (const char* e = getenv("HB_K1_CTAS")) ctas = atoi(e);
@@ -914,7 +928,7 @@ inline void k1_wide_geometry(const hb_k1_params& p, int sm_count, int* threads, 
 template <int ITER>
 cudaError_t launch_wide_tape(const hb_k1_params& p, int sm_count, cudaStream_t st) {
   int threads; long long blocks; size_t smem;
-  k1_wide_geometry(p, sm_count, &threads, &blocks, &smem);
+  k1_wide_geometry(p, sm_count, 8, &threads, &blocks, &smem);
   if (smem > 220 * 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(hb_k1_tape_kernel<ITER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -925,7 +939,7 @@ cudaError_t launch_wide_tape(const hb_k1_params& p, int sm_count, cudaStream_t s
 template <int ITER2>
 cudaError_t launch_wide_pair(const hb_k1_params& p, int sm_count, cudaStream_t st) {
   int threads; long long blocks; size_t smem;
-  k1_wide_geometry(p, sm_count, &threads, &blocks, &smem);
+  k1_wide_geometry(p, sm_count, K1_PAIR_WARPS, &threads, &blocks, &smem);
   if (smem > 220 * 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(hb_k1_pair_kernel<ITER2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
