@@ -654,6 +654,8 @@ void hb_config_default(hb_config* c) {
   c->mt = 1; c->rng_mode = HB_RNG_PHILOX; c->seed = 1312;
 }
 
+int hb_test_force_wide(int on) { const int prev = g_hb_force_wide; g_hb_force_wide = on ? 1 : 0; return prev; }
+
 int hb_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

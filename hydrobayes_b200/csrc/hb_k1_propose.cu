@@ -963,6 +963,8 @@ cudaError_t launch_gi(const hb_k1_params& p, bool tape, int sm_count, cudaStream
 
 }  // namespace
 
+int g_hb_force_wide = 0;
+
 cudaError_t hb_launch_k1(const hb_k1_params& p, bool tape_mode, int sm_count, cudaStream_t st) {
   const int d = p.d;
   if (d <= 1) return launch_gi<1, 1>(p, tape_mode, sm_count, st);
@@ -973,7 +975,7 @@ cudaError_t hb_launch_k1(const hb_k1_params& p, bool tape_mode, int sm_count, cu
   if (p.nc > 0x7fffffffLL || p.m_arch > 0x7fffffffLL) return cudaErrorInvalidValue;
   // small populations (fewer 32-chain batches than resident warps): one chain per warp spreads the work over more SMs
   if (p.n_peers > 1 && d <= 16) return cudaErrorInvalidValue;   // peer gather is implemented in the wide kernel
-  if (p.n_peers <= 1 && p.n_local < (long long)sm_count * 16 * 32 / 2) {
+  if (p.n_peers <= 1 && !g_hb_force_wide && p.n_local < (long long)sm_count * 16 * 32 / 2) {
     if (d <= 32) return launch_gi<32, 1>(p, tape_mode, sm_count, st);
     if (d <= 64) return launch_gi<32, 2>(p, tape_mode, sm_count, st);
     if (d <= 128) return launch_gi<32, 4>(p, tape_mode, sm_count, st);

@@ -448,7 +448,7 @@ cudaError_t dispatch(const hb_k3_params& p, int sm_count, int* nb, size_t* sm, c
   if (d <= 4) return launch_gi<4, 1>(p, sm_count, nb, sm, st);
   if (d <= 8) return launch_gi<8, 1>(p, sm_count, nb, sm, st);
   if (d <= 16) return launch_gi<16, 1>(p, sm_count, nb, sm, st);
-  if (p.n_local < (long long)sm_count * 16 * 32 / 2) {   // small populations: one chain per warp (see hb_launch_k1)
+  if (!g_hb_force_wide && p.n_local < (long long)sm_count * 16 * 32 / 2) {   // small populations: one chain per warp (see hb_launch_k1)
     if (d <= 32) return launch_gi<32, 1>(p, sm_count, nb, sm, st);
     if (d <= 64) return launch_gi<32, 2>(p, sm_count, nb, sm, st);
     if (d <= 128) return launch_gi<32, 4>(p, sm_count, nb, sm, st);

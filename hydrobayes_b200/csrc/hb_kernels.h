@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include "hb_common.cuh"
 
+extern int g_hb_force_wide;   // hb_test_force_wide(): select the large-population kernels regardless of the population size
+
 // device-resident copy of an hb_tape (all pointers are device pointers; rows of generation g start at g*nct)
 struct hb_tape_dev {
   const double* u_snooker;

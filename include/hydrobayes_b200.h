@@ -237,6 +237,11 @@ int hb_get_timing(const hb_handle* h, double* loop_ms, int64_t* kernel_launches)
 int hb_profile(hb_handle* h, int enable);
 int hb_get_kernel_ms(const hb_handle* h, const char* kernel, double* total_ms, int64_t* launches);
 
+/* testing hook: the kernels written for large populations (warp-per-32-chains proposal and accept kernels) are
+ * normally selected only from ~38 000 chains per GPU upwards; on = 1 selects them for every d > 16 so that the parity
+ * tests can compare them with the oracle at sizes the oracle finishes in seconds.  Returns the previous setting. */
+int hb_test_force_wide(int on);
+
 /* ---- stand-alone device entry points (unit parity tests and drop-ins for exported R functions) ------- */
 /* R_stat(x), x [t, d, n] column-major host array -> out[d]          (R/gelman_rubin.R:21) */
 int hb_rstat_array(const double* x, int64_t t, int32_t d, int64_t n, double* out, char* err, int errlen);

@@ -153,6 +153,57 @@ def test_replay_hydromodel_glue(hb, oracle, bound):
     H.assert_run_parity(dev, ora, rtol=1e-11)
 
 
+# ---------------------------------------------------------------- the large-population kernels at oracle-sized problems ----
+@pytest.fixture
+def force_wide(hb):
+    """hb_test_force_wide: the warp-per-32-chains proposal kernels (hb_k1_pair_kernel, hb_k1_tape_kernel) and the TMA-ring
+    accept kernel (hb_k3_wide_kernel) are normally picked from ~38 000 chains per GPU upwards (BASELINE C4 runs them at
+    2^20); the hook selects them at sizes the oracle finishes in seconds."""
+    prev = hb.lib().hb_test_force_wide(1)
+    yield
+    hb.lib().hb_test_force_wide(prev)
+
+
+@pytest.mark.parametrize("d,nc", [(100, 96), (17, 40), (33, 70), (99, 64), (130, 48), (200, 33), (300, 40)])
+def test_wide_kernels_replay(hb, oracle, force_wide, d, nc):
+    # replay: tape kernel (lane = dimension) + TMA-ring accept kernel, adaptation statistics, outlier resets, thin > 1;
+    # odd d exercises the padded last pair / last lane, nc not a multiple of 32 the ragged last batch
+    x0 = H.x0_tdist(nc, d); x0[1] = 250.0
+    cfg = A.default_config(nc=nc, t=90, d=d, lik=2, seed=51, adapt=0.5, thin=3, store_fx=1)
+    dev, ora = _replay_case(oracle, cfg, "t_distribution", x0)
+    H.assert_run_parity(dev, ora, rtol=1e-12)
+    if d == 100:
+        assert len(ora["outlier"]) > 0          # the outlier reset path is part of this case
+
+
+@pytest.mark.parametrize("d,nc", [(100, 96), (17, 40), (33, 70), (99, 64), (130, 48), (200, 33), (300, 40)])
+def test_wide_kernels_native(hb, oracle, force_wide, d, nc):
+    # native Philox draws: the pair kernel (one Philox call per two dimensions, slot map v2) against the oracle's Philox
+    # mode, and bit-for-bit against the small-population kernel
+    x0 = H.x0_tdist(nc, d)
+    cfg = A.default_config(nc=nc, t=90, d=d, lik=2, seed=53, adapt=0.5, record_accept=1)
+    dev = H.run_device(cfg, "t_distribution", x0)
+    ora = oracle.run(cfg, "t_distribution", x0)
+    H.assert_run_parity(dev, ora, rtol=1e-9, atol=1e-12, check_fx=False)
+    hb.lib().hb_test_force_wide(0)
+    narrow = H.run_device(cfg, "t_distribution", x0)
+    hb.lib().hb_test_force_wide(1)
+    assert np.array_equal(dev["chain"], narrow["chain"], equal_nan=True) and np.array_equal(dev["accept"], narrow["accept"])
+
+
+def test_wide_kernels_bounds_prior_and_zs(hb, oracle, force_wide):
+    d, nc = 40, 48
+    cfg = A.default_config(nc=nc, t=80, d=d, lik=2, seed=55, prior=A.HB_PRIOR_UNIFORM, bound=A.HB_BOUND_FOLD, adapt=0.5)
+    dev, ora = _replay_case(oracle, cfg, "t_distribution", H.x0_tdist(nc, d) * 0.2, par_min=[-3.0] * d, par_max=[3.5] * d)
+    H.assert_run_parity(dev, ora, rtol=1e-12)
+    cfg = A.default_config(nc=8, t=100, d=d, lik=2, seed=57, past_sample=1, psnooker=0.3, m0=200, archive_update=5, record_accept=1)
+    x0 = np.random.default_rng(5).uniform(-5, 15, size=(200, d))
+    dev, ora = _replay_case(oracle, cfg, "t_distribution", x0)
+    H.assert_run_parity(dev, ora, rtol=1e-11, check_fx=False)
+    cfg_n = H.copy_cfg(cfg, rng_mode=A.HB_RNG_PHILOX)
+    H.assert_run_parity(H.run_device(cfg_n, "t_distribution", x0), oracle.run(cfg_n, "t_distribution", x0), rtol=1e-11, check_fx=False)
+
+
 # ---------------------------------------------------------------- MT-DREAM, mt > 1 (SURVEY 8f.3) ----------------
 @pytest.mark.parametrize("mt,d,nc", [(3, 4, 16), (2, 40, 64), (5, 1, 12)])
 def test_replay_multi_try(hb, oracle, mt, d, nc):

@@ -47,5 +47,26 @@ def full(path, out):
                     i = hdr.index(w); f.write(f"{w:70s} {r[i]:>16s} {units[i]}\n")
     print(open(out).read())
 
+def traffic(path, out):
+    """dram__bytes_read.sum + dram__bytes_write.sum per captured launch -> profiles/ncu_traffic.json (bench.py reports it as
+    roofline.traffic next to the algorithmic bytes)."""
+    import json
+    txt = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ir, iw = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum')
+    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    res = {}
+    for r in rows[2:]:
+        k = kname(r[hdr.index('Kernel Name')])
+        key = 'K1' if 'k1_' in k else 'K3' if 'k3_' in k else 'K2'
+        b = float(r[ir].replace(',', '')) * scale[units[ir]] + float(r[iw].replace(',', '')) * scale[units[iw]]
+        res[key] = b
+        res[key + '_kernel'] = k
+    res['_source'] = f'ncu --set full --clock-control none, {path}: dram__bytes_read.sum + dram__bytes_write.sum per launch'
+    json.dump(res, open(out, 'w'), indent=1)
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == '__main__':
-    {'launches': launches, 'full': full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {'launches': launches, 'full': full, 'traffic': traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
