@@ -241,20 +241,37 @@ def run_reference(args):
 
 
 def quick_rate(name, local, torch, gens=200, warm=30):
-    """short side measurement of another BASELINE config on one GPU (reported under `other_workloads`)"""
+    """short side measurement of another BASELINE config on one GPU (reported under `other_workloads`): the rate inside
+    the adaptation period (statistics + finalize every generation, outlier check every updateInterval) and the
+    steady-state rate after it (90 % of a run with the reference's default adapt = 0.1)"""
     w = workload(name)
+    cfg = w["cfg"]
     s = make_sampler(w, local, 0, 1, torch)
+
+    def timed(n):
+        torch.cuda.synchronize()
+        ms0, l0 = s.timing()
+        t0 = time.perf_counter()
+        s.run(n)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ms1, l1 = s.timing()
+        return wall, ms1 - ms0, l1 - l0
+
     s.run(warm)
-    torch.cuda.synchronize()
-    ms0, l0 = s.timing()
-    t0 = time.perf_counter()
-    s.run(gens)
-    torch.cuda.synchronize()
-    wall = time.perf_counter() - t0
-    ms1, l1 = s.timing()
-    out = {"workload": w["desc"], "value": w["cfg"].nc * gens / wall, "unit": UNIT, "generations": gens,
-           "us_per_generation": wall / gens * 1e6, "device_us_per_generation": (ms1 - ms0) / gens * 1e3,
-           "gpu_launches": l1 - l0}
+    adapt_end = int(cfg.adapt * cfg.t)
+    n_adapt = max(0, min(gens, adapt_end - warm - 1))
+    out = {"workload": w["desc"], "unit": UNIT}
+    if n_adapt >= 20:
+        wall, dev, _ = timed(n_adapt)
+        out["adaptation_period"] = {"value": cfg.nc * n_adapt / wall, "generations": n_adapt, "us_per_generation": wall / n_adapt * 1e6}
+    done = warm + n_adapt + 1
+    if done <= adapt_end + 2:
+        s.run(adapt_end + 2 - done)          # leave the adaptation period
+    wall, dev, launches = timed(gens)
+    out.update({"value": cfg.nc * gens / wall, "generations": gens, "us_per_generation": wall / gens * 1e6,
+                "device_us_per_generation": dev / gens * 1e3, "gpu_launches": launches,
+                "note": "steady state (after the adaptation period)"})
     s.close()
     return out
 
