@@ -1,13 +1,13 @@
 # record_reference.R -- records a decision-level tape (SURVEY Appendix D) and the outputs of the REAL HydroBayes
 # package, so that oracle <-> reference parity can be pinned by anyone who has R (R is absent from the build image).
 #
-#   Rscript tools/record_reference.R /path/to/HydroBayes out_prefix
+#   Rscript tools/record_reference.R /path/to/HydroBayes tests/golden/reference_c1
 #
 # It sources the reference's R files, masks runif / rnorm / sample inside that environment with recording wrappers,
 # runs dream_parallel() on the BASELINE C1 call, and writes <out_prefix>_draws.csv (call, n, values) and
-# <out_prefix>_chain.csv.  tests/test_reference_tape.py (skipped when the files are absent) turns the draw log into an
-# hb_tape (resolving sample() results into D / partner ids / crossover id / gamma choice) and replays it through the
-# oracle and the device.
+# <out_prefix>_chain.csv.  tools/reference_tape.py turns the draw log into an hb_tape; tests/test_reference_tape.py
+# (skipped while the two files are absent) replays it through the oracle and compares with the recorded chain: that
+# test is what pins the oracle to the real R package.
 args <- commandArgs(trailingOnly = TRUE)
 ref <- args[1]; out <- args[2]
 env <- new.env()
