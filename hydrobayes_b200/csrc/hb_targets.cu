@@ -80,6 +80,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 //   A (8x4, row): lane holds X[row = lane>>2][k = 4*kb + (lane&3)]   -- all KB fragments loaded up front (MLP = KB)
 //   B (4x8, col): lane holds W[k = 4*kb + (lane&3)][n = 8*nb + (lane>>2)] from shared memory (2 wavefronts, no conflicts)
 //   C (8x8): lane holds row lane>>2, two columns -> squared and reduced over the 4 lanes of a row group.
+// (W's leading dimension ldw == 4 (mod 16) makes these reads conflict-free, see tdist_init.)
 // W is upper triangular (z_n = sum_{k<=n} x_k W[k][n]), so n-block nb only needs k-blocks kb <= 2*nb+1: the fully
 // unrolled loop nest drops the others at compile time (about d^2/2 multiply-adds executed, as backsolve does).
 template <int KB>
@@ -234,7 +235,10 @@ int tdist_init(void** ctx, int d, int lik, const double*, const int64_t*, int, c
   for (int v : kKB) if (v >= kb_need) { c->KB = v; break; }
   const int kp = c->KB ? 4 * c->KB : d;
   int np = c->KB ? 8 * ((c->KB + 1) / 2) : d;
-  c->ldw = (np % 16 == 8) ? np : np + 8;                    // ldw == 8 (mod 16): conflict-free B-fragment reads
+  // B-fragment read of a half-warp (64-bit shared loads are served 16 lanes at a time): lane (gid, tig), gid < 4, reads
+  // double (4kb + tig)*ldw + 8nb + gid -> 16 distinct 8-byte banks iff ldw == 4 (mod 16).  (ldw == 8 (mod 16), the
+  // first layout, put tig = 0, 2 and tig = 1, 3 on the same banks: ncu counted a 2-way conflict on every B load.)
+  c->ldw = np + ((4 - np % 16) + 16) % 16;
   if (!c->KB) c->ldw = d;
   std::vector<double> W;
   if (tdist_build(d, W, kp, c->ldw, &c->konst)) { delete c; set_err(err, errlen, "chol(C) failed"); return HB_ERR_INVALID; }
