@@ -78,21 +78,31 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 
 // KB k-blocks of 4, NB = ceil(KB/2) n-blocks of 8.  One warp owns 8 chains per iteration:
 //   A (8x4, row): lane holds X[row = lane>>2][k = 4*kb + (lane&3)]   -- all KB fragments loaded up front (MLP = KB)
-//   B (4x8, col): lane holds W[k = 4*kb + (lane&3)][n = 8*nb + (lane>>2)] from shared memory (2 wavefronts, no conflicts)
+//   B (4x8, col): lane holds W[k = 4*kb + (lane&3)][n = 8*nb + (lane>>2)] from shared memory
 //   C (8x8): lane holds row lane>>2, two columns -> squared and reduced over the 4 lanes of a row group.
-// (W's leading dimension ldw == 4 (mod 16) makes these reads conflict-free, see tdist_init.)
 // W is upper triangular (z_n = sum_{k<=n} x_k W[k][n]), so n-block nb only needs k-blocks kb <= 2*nb+1: the fully
 // unrolled loop nest drops the others at compile time (about d^2/2 multiply-adds executed, as backsolve does).
+// W is stored BLOCK-TRIANGULAR in fragment order: only the (nb, kb) blocks that are used, 32 doubles each, element
+// `lane` of a block is the B fragment of that lane -- a warp's B load is one contiguous, conflict-free 256-byte line, and
+// the whole operand is 46 KB instead of 91 KB at d = 100, which is what lets three CTAs (24 warps) share an SM: the
+// kernel is bound by the latency of the 25 global loads that open every tile, hidden only by other warps.
+__host__ __device__ constexpr int tdist_blk_base(int nb, int KB) {   // blocks of the n-blocks before nb
+  int s = 0;
+  for (int j = 0; j < nb; ++j) s += (2 * j + 2 < KB) ? 2 * j + 2 : KB;
+  return s;
+}
+__host__ __device__ constexpr int tdist_n_blocks(int KB) { return tdist_blk_base((KB + 1) / 2, KB); }
+
 template <int KB>
-__global__ void __launch_bounds__(256, 2) hb_tdist_dmma_kernel(const double* __restrict__ X, long long n, int d, int ldx,
-                                                            const double* __restrict__ Wg, int ldw, double konst,
+__global__ void __launch_bounds__(256, (KB > 25 ? 2 : 3)) hb_tdist_dmma_kernel(const double* __restrict__ X, long long n, int d, int ldx,
+                                                            const double* __restrict__ Wblk, double konst,
                                                             double df, int lik, double* __restrict__ ll,
                                                             double* __restrict__ fx) {
   constexpr int NB = (KB + 1) / 2;
   extern __shared__ __align__(16) double Ws[];
   __shared__ __align__(8) uint64_t wbar;
-  // W (4 KB x ldw doubles, a multiple of 16 bytes) is staged by bulk TMA copies of at most 32 KB each
-  const uint32_t w_bytes = (uint32_t)(4 * KB * ldw) * 8u;
+  // the block-ordered W (a multiple of 256 bytes) is staged by bulk TMA copies of at most 32 KB each
+  constexpr uint32_t w_bytes = (uint32_t)tdist_n_blocks(KB) * 32u * 8u;
   if (threadIdx.x == 0) {
     mbar_init(&wbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -101,8 +111,8 @@ __global__ void __launch_bounds__(256, 2) hb_tdist_dmma_kernel(const double* __r
   if (threadIdx.x == 0) {
     mbar_expect_tx(&wbar, w_bytes);
     for (uint32_t off = 0; off < w_bytes; off += 32768u) {
-      const uint32_t n = (w_bytes - off) < 32768u ? (w_bytes - off) : 32768u;
-      tma_load_1d(reinterpret_cast<char*>(Ws) + off, reinterpret_cast<const char*>(Wg) + off, n, &wbar);
+      const uint32_t nbytes = (w_bytes - off) < 32768u ? (w_bytes - off) : 32768u;
+      tma_load_1d(reinterpret_cast<char*>(Ws) + off, reinterpret_cast<const char*>(Wblk) + off, nbytes, &wbar);
     }
   }
   mbar_wait(&wbar, 0);
@@ -134,7 +144,7 @@ __global__ void __launch_bounds__(256, 2) hb_tdist_dmma_kernel(const double* __r
         for (int i = 0; i < 4; ++i) {
           const int nb = g0 + i;
           if (nb < NB && kb <= 2 * nb + 1) {
-            const double b = Ws[(4 * kb + tig) * ldw + 8 * nb + gid];
+            const double b = Ws[(tdist_blk_base(nb, KB) + kb) * 32 + lane];
             dmma884(c[i][0], c[i][1], a[kb], b);
           }
         }
@@ -182,7 +192,8 @@ __global__ void hb_tdist_fma_kernel(const double* __restrict__ X, long long n, i
 struct tdist_ctx {
   int d, lik, KB, ldw;
   double konst, df;
-  double* W_dev;
+  double* W_dev;       // [kp][ldw] dense upper triangle (FMA path)
+  double* Wblk_dev;    // block-triangular fragment order (DMMA path), tdist_n_blocks(KB) x 32 doubles
   int sm_count;
   int force_fma;
 };
@@ -246,6 +257,21 @@ int tdist_init(void** ctx, int d, int lik, const double*, const int64_t*, int, c
       cudaMemcpy(c->W_dev, W.data(), W.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
     delete c; set_err(err, errlen, "cudaMalloc/cudaMemcpy failed for W"); return HB_ERR_CUDA;
   }
+  c->Wblk_dev = nullptr;
+  if (c->KB) {   // block-triangular fragment order: block (nb, kb <= 2nb+1), element lane = W[4kb + (lane&3)][8nb + (lane>>2)]
+    const int KB = c->KB, NB = (KB + 1) / 2;
+    std::vector<double> Wb;
+    for (int nb = 0; nb < NB; ++nb)
+      for (int kb = 0; kb < KB && kb <= 2 * nb + 1; ++kb)
+        for (int lane = 0; lane < 32; ++lane) {
+          const int k = 4 * kb + (lane & 3), nn = 8 * nb + (lane >> 2);
+          Wb.push_back((k < kp && nn < c->ldw) ? W[(size_t)k * c->ldw + nn] : 0.0);
+        }
+    if (cudaMalloc(&c->Wblk_dev, Wb.size() * sizeof(double)) != cudaSuccess ||
+        cudaMemcpy(c->Wblk_dev, Wb.data(), Wb.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+      delete c; set_err(err, errlen, "cudaMalloc/cudaMemcpy failed for W blocks"); return HB_ERR_CUDA;
+    }
+  }
   int dev = 0; cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, dev);
   const char* f = getenv("HB_TDIST_FORCE_FMA");
@@ -256,7 +282,7 @@ int tdist_init(void** ctx, int d, int lik, const double*, const int64_t*, int, c
 
 template <int KB>
 int tdist_launch_kb(tdist_ctx* c, const double* x, int64_t n, int ldx, double* ll, double* fx, cudaStream_t st) {
-  const size_t smem = (size_t)4 * KB * c->ldw * sizeof(double);
+  const size_t smem = (size_t)tdist_n_blocks(KB) * 32 * sizeof(double);
   static bool attr_set = false;
   if (!attr_set && smem > 48 * 1024) {
     if (cudaFuncSetAttribute(hb_tdist_dmma_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -267,9 +293,12 @@ int tdist_launch_kb(tdist_ctx* c, const double* x, int64_t n, int ldx, double* l
   const int threads = tiles >= (long long)c->sm_count * 16 ? 256 : 128;   // small populations: spread over more SMs
   const int wpb = threads / 32;
   long long blocks = (tiles + wpb - 1) / wpb;
-  const long long cap = (long long)c->sm_count * 2;
+  long long per_sm = (long long)(224 * 1024 / (smem + 1024));
+  if (per_sm > (KB > 25 ? 2 : 3)) per_sm = (KB > 25 ? 2 : 3);  // __launch_bounds__ of the kernel
+  if (per_sm < 1) per_sm = 1;
+  const long long cap = (long long)c->sm_count * per_sm;
   if (blocks > cap) blocks = cap;
-  hb_tdist_dmma_kernel<KB><<<(unsigned)blocks, threads, smem, st>>>(x, n, c->d, ldx, c->W_dev, c->ldw, c->konst, c->df,
+  hb_tdist_dmma_kernel<KB><<<(unsigned)blocks, threads, smem, st>>>(x, n, c->d, ldx, c->Wblk_dev, c->konst, c->df,
                                                                 c->lik, ll, fx);
   return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
 }
@@ -295,7 +324,7 @@ int tdist_launch(void* ctx, const double* x, int64_t n, int d, int ldx, double* 
 }
 void tdist_destroy(void* ctx) {
   auto* c = (tdist_ctx*)ctx;
-  if (c) { cudaFree(c->W_dev); delete c; }
+  if (c) { cudaFree(c->W_dev); cudaFree(c->Wblk_dev); delete c; }
 }
 void tdist_work(void*, int d, double* flops, double* bytes) { *flops = (double)d * d + 3.0 * d; *bytes = 8.0 * d + 8; }
 
