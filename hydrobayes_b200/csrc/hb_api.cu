@@ -1183,6 +1183,21 @@ int hb_fetch_chain_rows(hb_handle* h, int64_t row0, int64_t nrows, double* out) 
   return HB_OK;
 }
 
+int hb_host_prefault(void* p, size_t bytes, int n_threads) {
+  if (!p) return HB_ERR_INVALID;
+  unsigned hw = std::thread::hardware_concurrency();
+  const int nt = n_threads > 0 ? n_threads : (int)std::max(1u, std::min(8u, hw / 2));
+  char* base = reinterpret_cast<char*>(p);
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; ++t)
+    th.emplace_back([=]() {
+      const size_t lo = bytes / nt * t, hi = (t == nt - 1) ? bytes : bytes / nt * (t + 1);
+      for (size_t o = lo; o < hi; o += 4096) reinterpret_cast<volatile char*>(base)[o] = 0;
+    });
+  for (auto& x : th) x.join();
+  return HB_OK;
+}
+
 int hb_fetch_chain(hb_handle* h, double* chain) { return h ? hb_fetch_chain_rows(h, 0, h->out_t, chain) : HB_ERR_INVALID; }
 
 int hb_fetch_fx(hb_handle* h, double* fx) {

@@ -163,10 +163,27 @@ class Sampler:
     def n_local(self) -> int:
         return self.cfg.nc * max(self.cfg.n_runs, 1)   # sharded handles: pass n_chains = nc / world to the fetchers
 
-    def fetch_chain(self, n_chains: Optional[int] = None) -> np.ndarray:
+    def alloc_chain(self, n_chains: Optional[int] = None, prefault: bool = True):
+        """R allocates chain <- array(NA, c(out_t, d+3, nc)) BEFORE the generation loop (R/dream_parallel.R:201-203), so
+        its pages are resident when the results are written.  Same here: the (uninitialised) result array is allocated up
+        front and its pages are touched by a helper thread while the device runs; returns (array, thread-or-None)."""
+        import threading
         dm = self.out_dims()
         n = n_chains or self.n_local()
         out = np.empty((dm["out_t"], self.cfg.d + 3, n), order="F")
+        th = None
+        if prefault and out.nbytes >= (64 << 20):
+            th = threading.Thread(target=self.L.hb_host_prefault, args=(out.ctypes.data, out.nbytes, 0), daemon=True)
+            th.start()                                   # ctypes releases the GIL for the duration of the call
+        return out, th
+
+    def fetch_chain(self, n_chains: Optional[int] = None, out: Optional[np.ndarray] = None) -> np.ndarray:
+        dm = self.out_dims()
+        n = n_chains or self.n_local()
+        if out is None:
+            out = np.empty((dm["out_t"], self.cfg.d + 3, n), order="F")
+        elif out.shape != (dm["out_t"], self.cfg.d + 3, n) or not out.flags["F_CONTIGUOUS"] or out.dtype != np.float64:
+            raise ValueError("out must be a Fortran-ordered float64 array [out_t, d+3, n_chains]")
         self._check(self.L.hb_fetch_chain(self.h, _ptr(out)))
         return out
 
@@ -364,10 +381,13 @@ def _drive(sweep, fun, extra, lik, par_info, nc, t, d, burnin, adapt, updateInte
         if tape is not None:
             s.set_tape(tape.struct(), keepalive=tape)
         step = int(slice_generations) if slice_generations else (max(1, t // 50) if verbose else t)
+        chain_buf, toucher = s.alloc_chain(n_shard)                 # chain <- array(NA, ...) before the loop, :201-203
         done = 1
         while done < t:
             done = s.run(step)          # the R driver ticks txtProgressBar / checks interrupts between slices
-        chain = s.fetch_chain(n_shard)             # sharded: this rank's chains, chain[out_t, d+3, nc/world]
+        if toucher is not None:
+            toucher.join()
+        chain = s.fetch_chain(n_shard, out=chain_buf)   # sharded: this rank's chains, chain[out_t, d+3, nc/world]
         ar, cr = s.fetch_ar_cr()
         out = {"chain": chain, "rank": rank, "world": world}
         names = par_info.get("names") or [f"par{k + 1}" for k in range(d)]

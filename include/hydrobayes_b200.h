@@ -217,6 +217,11 @@ int hb_out_dims(const hb_handle* h, int64_t* out_t, int64_t* ar_rows, int64_t* a
                 int64_t* cr_cols, int64_t* fx_m, int64_t* rstat_rows);
 int hb_fetch_chain(hb_handle* h, double* chain);           /* [out_t, d+3, nct]; rows not yet written are NaN (R: NA) */
 int hb_fetch_chain_rows(hb_handle* h, int64_t row0, int64_t nrows, double* out); /* [nrows, d+3, nct] */
+/* Touch every page of a freshly allocated host result array with a few threads (blocking; thread-safe; no device work).
+ * The reference allocates `chain <- array(NA, ...)` BEFORE the generation loop (R/dream_parallel.R:201-203), i.e. its
+ * result pages are faulted in up front; a host that allocates uninitialised memory (numpy.empty) can call this from a
+ * helper thread while hb_run is busy, so that hb_fetch_chain copies into resident pages.  n_threads <= 0: default. */
+int hb_host_prefault(void* p, size_t bytes, int n_threads);
 int hb_fetch_fx(hb_handle* h, double* fx);                 /* [out_t, nct, m] */
 int hb_fetch_ar(hb_handle* h, double* ar);                 /* run-major blocks of [ar_rows, ar_cols] */
 int hb_fetch_cr(hb_handle* h, double* cr);
