@@ -611,56 +611,58 @@ __global__ void __launch_bounds__(K1_PAIR_WARPS * 32, 2) hb_k1_pair_kernel(const
         // gamma_d = 2.38/sqrt(2 D d*) (:190) from the host-built table (same IEEE sqrt and division, bit-identical)
         const double gam = g_is_one ? 1.0 : p.gamma_tab[(D - 1) * d + (d_star - 1)];   // :192
         mbar_wait(&bars[stg], (it / K1_STAGES) & 1);                     // the rows have landed in shared memory
+        // Branch-free sweep: every lane computes its pair unconditionally (out-of-range lanes on a clamped address) and
+        // the crossover subspace enters as a select at the end -- unselected lanes would idle through the same warp
+        // instructions anyway, and without the divergent branches the iterations form one basic block whose
+        // independent fp64 chains the scheduler can interleave.  Only the warp-uniform branches on D remain.
 #pragma unroll
         for (int m = 0; m < ITER2; ++m) {
           const int k0 = 2 * (m * 32 + lane);
-          xp2[m] = make_double2(0.0, 0.0);
-          if (k0 < d) {
-            const uint4 ww = KEEP ? wk[KEEP ? m : 0] : hb_philox4x32_10_ks(c0, c1, p.gen, HB_SLOT_DIM0 + (uint32_t)(k0 >> 1), p.ks);
-            const bool a = (kmin >= 0) ? (k0 == kmin) : ((s0[m] >> lane) & 1u);
-            const bool b = (kmin >= 0) ? (k0 + 1 == kmin) : ((s1[m] >> lane) & 1u);
-            double2 x = lds2(rows + k0);
-            if (a || b) {
-              // jump_diff <- colSums(r1[,A] - r2[,A])  :196.  One or two terms: the plain sum is already the correctly
-              // rounded one; from the third term on, carry the rounding errors (R accumulates in long double).
-              double2 tq[HB_MAX_DELTA];
+          const int kc = (k0 < d) ? k0 : 0;
+          const uint4 ww = KEEP ? wk[KEEP ? m : 0] : hb_philox4x32_10_ks(c0, c1, p.gen, HB_SLOT_DIM0 + (uint32_t)(kc >> 1), p.ks);
+          const bool a = (kmin >= 0) ? (k0 == kmin) : ((s0[m] >> lane) & 1u);      // masks are 0 for out-of-range lanes
+          const bool b = (kmin >= 0) ? (k0 + 1 == kmin) : ((s1[m] >> lane) & 1u);
+          double2 x = lds2(rows + kc);
+          // jump_diff <- colSums(r1[,A] - r2[,A])  :196.  One or two terms: the plain sum is already the correctly
+          // rounded one; from the third term on, carry the rounding errors (R accumulates in long double).
+          double2 tq[HB_MAX_DELTA];
 #pragma unroll
-              for (int q = 0; q < HB_MAX_DELTA; ++q) {
-                tq[q] = make_double2(0.0, 0.0);
-                if (q < D) {
-                  const double2 ra = lds2(rowa + q * ldx + k0), rb = lds2(rowb + q * ldx + k0);
-                  tq[q] = make_double2(__dadd_rn(ra.x, -rb.x), __dadd_rn(ra.y, -rb.y));
-                }
-              }
-              double jd0, jd1;
-              if (D <= 2) { jd0 = __dadd_rn(tq[0].x, tq[1].x); jd1 = __dadd_rn(tq[0].y, tq[1].y); }
-              else {
-                double sa, ea, ca, sb, eb, cb;
-                two_sum(tq[0].x, tq[1].x, sa, ca);
-                two_sum(tq[0].y, tq[1].y, sb, cb);
-#pragma unroll
-                for (int q = 2; q < HB_MAX_DELTA; ++q)
-                  if (q < D) {
-                    two_sum(sa, tq[q].x, sa, ea); ca = __dadd_rn(ca, ea);
-                    two_sum(sb, tq[q].y, sb, eb); cb = __dadd_rn(cb, eb);
-                  }
-                jd0 = __dadd_rn(sa, ca); jd1 = __dadd_rn(sb, cb);
-              }
-              if (a) {
-                const double lambda = hb_rng_lambda16(ww.x >> 16, p.c_val);                              // :188
-                const double zeta = __dmul_rn(p.c_star, hb_rng_normal32(ww.y));                          // :194
-                const double v = __dadd_rn(zeta, __dmul_rn(__dmul_rn(__dadd_rn(1.0, lambda), gam), jd0));   // :198
-                x.x = __dadd_rn(x.x, __dmul_rn(v, p.beta0));                                             // :200, :206
-              }
-              if (b) {
-                const double lambda = hb_rng_lambda16(ww.z >> 16, p.c_val);
-                const double zeta = __dmul_rn(p.c_star, hb_rng_normal32(ww.w));
-                const double v = __dadd_rn(zeta, __dmul_rn(__dmul_rn(__dadd_rn(1.0, lambda), gam), jd1));
-                x.y = __dadd_rn(x.y, __dmul_rn(v, p.beta0));
-              }
+          for (int q = 0; q < HB_MAX_DELTA; ++q) {
+            tq[q] = make_double2(0.0, 0.0);
+            if (q < D) {
+              const double2 ra = lds2(rowa + q * ldx + kc), rb = lds2(rowb + q * ldx + kc);
+              tq[q] = make_double2(__dadd_rn(ra.x, -rb.x), __dadd_rn(ra.y, -rb.y));
             }
-            xp2[m] = x;
           }
+          double jd0, jd1;                        // (making these D-branches unconditional was measured 11 % slower)
+          if (D <= 2) { jd0 = __dadd_rn(tq[0].x, tq[1].x); jd1 = __dadd_rn(tq[0].y, tq[1].y); }
+          else {
+            double sa, ea, ca, sb, eb, cb;
+            two_sum(tq[0].x, tq[1].x, sa, ca);
+            two_sum(tq[0].y, tq[1].y, sb, cb);
+#pragma unroll
+            for (int q = 2; q < HB_MAX_DELTA; ++q)
+              if (q < D) {
+                two_sum(sa, tq[q].x, sa, ea); ca = __dadd_rn(ca, ea);
+                two_sum(sb, tq[q].y, sb, eb); cb = __dadd_rn(cb, eb);
+              }
+            jd0 = __dadd_rn(sa, ca); jd1 = __dadd_rn(sb, cb);
+          }
+          {
+            const double lambda = hb_rng_lambda16(ww.x >> 16, p.c_val);                              // :188
+            const double zeta = __dmul_rn(p.c_star, hb_rng_normal32(ww.y));                          // :194
+            const double v = __dadd_rn(zeta, __dmul_rn(__dmul_rn(__dadd_rn(1.0, lambda), gam), jd0));   // :198
+            const double nx = __dadd_rn(x.x, __dmul_rn(v, p.beta0));                                 // :200, :206
+            x.x = a ? nx : x.x;
+          }
+          {
+            const double lambda = hb_rng_lambda16(ww.z >> 16, p.c_val);
+            const double zeta = __dmul_rn(p.c_star, hb_rng_normal32(ww.w));
+            const double v = __dadd_rn(zeta, __dmul_rn(__dmul_rn(__dadd_rn(1.0, lambda), gam), jd1));
+            const double ny = __dadd_rn(x.y, __dmul_rn(v, p.beta0));
+            x.y = b ? ny : x.y;
+          }
+          xp2[m] = x;
         }
       }
       // the stage is free again: fetch the rows of the chain K1_STAGES ahead
