@@ -108,7 +108,19 @@ def dist_setup(n_gpus):
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # stdout carries exactly one JSON line: NCCL prints its banner ("NCCL version ...") to stdout while the first
+        # communicator is created, so file descriptor 1 points at stderr until that has happened
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     return rank, world, local, torch
 
 
