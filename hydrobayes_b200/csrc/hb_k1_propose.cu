@@ -495,6 +495,7 @@ __global__ void __launch_bounds__(K1_PAIR_WARPS * 32, 2) hb_k1_pair_kernel(const
   for (long long base = warp_id * 32; base < p.n_local; base += n_warps * 32) {
     k1_phase_a<false>(p, base, lane, n_src, heads, errbits);
     __syncwarp();
+    double lp_mine = 0.0;
 
     const int n_in_batch = (int)((p.n_local - base) < 32 ? (p.n_local - base) : 32);
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
@@ -695,14 +696,15 @@ __global__ void __launch_bounds__(K1_PAIR_WARPS * 32, 2) hb_k1_pair_kernel(const
           *reinterpret_cast<double2*>(xp_row + k0) = x;
         }
       }
-      if (p.prior == 1) lp_part = hb_group_sum<32>(lp_part);
-      if (lane == 0) {
-        double lp = (p.prior == 1) ? lp_part : 0.0;                      // flat prior: 0  :55
-        if (!(lp >= HB_FLOOR)) lp = (lp != lp) ? lp : HB_FLOOR;          // :65
-        if (!isfinite(lp)) errbits |= HB_FLAG_LP_NONFINITE;              // :67
-        p.lp_xp[jl] = lp;
-        p.id_out[jl] = id;
-      }
+      if (p.prior == 1) { lp_part = hb_group_sum<32>(lp_part); if (lane == c) lp_mine = lp_part; }   // lane c keeps chain c's log prior
+    }
+    // the scalars of the batch leave as coalesced stores: lane c owns chain base + c
+    if (lane < n_in_batch) {
+      double lp = lp_mine;                                               // flat prior: 0  :55
+      if (!(lp >= HB_FLOOR)) lp = (lp != lp) ? lp : HB_FLOOR;            // :65
+      if (!isfinite(lp)) errbits |= HB_FLAG_LP_NONFINITE;                // :67
+      p.lp_xp[base + lane] = lp;
+      p.id_out[base + lane] = (heads[lane * hw] >> 8) & 0xff;
     }
     __syncwarp();
   }
