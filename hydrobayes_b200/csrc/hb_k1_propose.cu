@@ -417,16 +417,17 @@ __device__ __forceinline__ void k1_phase_a(const hb_k1_params& p, long long base
   }
   if (sn && (hps2 < 0 || hps2 >= n_src)) { errbits |= HB_FLAG_BAD_TAPE; hps2 = 0; }
   const int roff = p.past_sample ? 0 : (int)(gl - j);               // first chain of this chain's run
+  // head = packed | the rows to fetch in issue order: a[0..D-1], b[0..D-1] (snooker: r1, r2, r3) | g_snooker at words
+  // 10-11 of the full layout.  Lane r of the issue step reads word r.
   const int hw = k1_head_words(delta, p.past_sample);
-  const int boff = p.past_sample ? 1 + HB_MAX_DELTA : 1 + delta;
   int* hd = heads + lane * hw;
   hd[0] = hD | (hid << 8) | ((g1 ? 1 : 0) << 16) | ((sn ? 1 : 0) << 17);
+  if (sn) { hd[1] = hpa[0] + roff; hd[2] = hpb[0] + roff; hd[3] = hps2 + roff; }
+  else {
 #pragma unroll
-  for (int q = 0; q < HB_MAX_DELTA; ++q) if (q < delta) { hd[1 + q] = hpa[q] + roff; hd[boff + q] = hpb[q] + roff; }
-  if (p.past_sample) {
-    hd[1 + 2 * HB_MAX_DELTA] = hps2 + roff;
-    *reinterpret_cast<double*>(hd + 10) = hgsn;
+    for (int q = 0; q < HB_MAX_DELTA; ++q) if (q < hD) { hd[1 + q] = hpa[q] + roff; hd[1 + hD + q] = hpb[q] + roff; }
   }
+  if (p.past_sample) *reinterpret_cast<double*>(hd + 10) = hgsn;
 }
 
 // issue the bulk copies of the rows chain `c` of the current batch needs into stage buffer `dst`:
@@ -434,7 +435,6 @@ __device__ __forceinline__ void k1_phase_a(const hb_k1_params& p, long long base
 __device__ __forceinline__ void k1_issue(const hb_k1_params& p, const double* __restrict__ src, const int* heads, int c,
                                          long long base, double* dst, uint64_t* bar, int lane, uint32_t row_bytes) {
   const int* hd = heads + c * k1_head_words(p.delta, p.past_sample);
-  const int boff = p.past_sample ? 1 + HB_MAX_DELTA : 1 + p.delta;
   const int pk = hd[0];
   const int Dn = pk & 0xff;
   const bool sn = (pk >> 17) & 1;
@@ -445,9 +445,7 @@ __device__ __forceinline__ void k1_issue(const hb_k1_params& p, const double* __
     const double* g;
     if (lane == 0) g = p.X + (p.chain0 + (base + c) * p.stride) * (long long)p.ldx;      // own state
     else {
-      int row;
-      if (sn) row = (lane == 1) ? hd[1] : (lane == 2) ? hd[1 + HB_MAX_DELTA] : hd[1 + 2 * HB_MAX_DELTA];
-      else row = (lane <= Dn) ? hd[lane] : hd[boff + (lane - 1 - Dn)];                  // a[0..D-1], b[0..D-1]
+      const int row = hd[lane];                                     // a[0..D-1], b[0..D-1] (snooker: r1, r2, r3)
       if (p.n_peers > 1) {                        // the row lives in rank rk's shard: NVLink peer pointer
         const int rk = (int)(row / p.peer_nl);
         g = p.peer[rk] + (long long)(row - rk * p.peer_nl) * p.ldx;
