@@ -58,6 +58,12 @@ def main():
     nc1 = 512 * world
     cases.append(("mixture d=1", A.default_config(nc=nc1, t=200, d=1, lik=1, seed=9, adapt=0.3, record_accept=1), "mixture", H.x0_mixture(nc1), {}))
     cases = [c + (0,) for c in cases] + [c + (1,) for c in cases if c[1].d > 16] + [c + (2,) for c in cases]
+    # DREAM-ZS: archive sampling + snooker on a sharded population (all-gather and delta exchange; the peer gather does not
+    # cover the archive).  x0 is the archive (m0 rows), the chains start at its last nc rows (R/dream_parallel.R:213).
+    ncz, dz, m0 = 8 * world, 12, 200
+    zs = A.default_config(nc=ncz, t=160, d=dz, lik=2, seed=11, past_sample=1, psnooker=0.2, m0=m0, archive_update=5, record_accept=1)
+    xz = np.random.default_rng(7).uniform(-5, 15, size=(m0, dz))
+    cases += [("tdist d=12 ZS+snooker", zs, "t_distribution", xz, {}, 0), ("tdist d=12 ZS+snooker", zs, "t_distribution", xz, {}, 2)]
     for name, cfg, tgt, x0, kw, xmode in cases:
         peer = xmode != 0
         if xmode:
