@@ -25,6 +25,7 @@
 #ifndef HYDROBAYES_B200_H
 #define HYDROBAYES_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
