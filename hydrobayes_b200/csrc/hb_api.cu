@@ -43,8 +43,47 @@ int fail(hb_handle* h, int code, const char* fmt, ...) {
     if (e_ != cudaSuccess) return fail(h, HB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
   } while (0)
 
+// Deferred release of a destroyed handle's device buffers.  cudaFree of the multi-GB history buffers takes 15-350 ms (it
+// unmaps and synchronises), and it sits on the caller's critical path -- dream() returns only after hb_destroy.  The
+// frees therefore run on a reaper thread; an allocation that fails for lack of memory first waits for the reapers.
+void reaper_at_exit();
+struct reaper_t {
+  std::mutex mu;
+  std::vector<std::thread> threads;
+  bool at_exit_set = false;
+  void add(std::thread&& t) {
+    bool prune = false;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      threads.push_back(std::move(t));
+      prune = threads.size() > 8;
+      // registered after the CUDA runtime's own exit handler (a CUDA call always precedes the first destroy), so it runs
+      // BEFORE the runtime is torn down: no cudaFree is in flight during teardown
+      if (!at_exit_set) { at_exit_set = true; atexit(reaper_at_exit); }
+    }
+    if (prune) join_all();   // bounds the number of pending reapers (test suites create hundreds of handles)
+  }
+  void join_all() {
+    std::vector<std::thread> ts;
+    { std::lock_guard<std::mutex> lk(mu); ts.swap(threads); }
+    for (auto& t : ts) if (t.joinable()) t.join();
+  }
+  ~reaper_t() { join_all(); }
+} g_reaper;
+void reaper_at_exit() { g_reaper.join_all(); }
+
+template <typename T>
+cudaError_t dalloc_raw(T** p, size_t n);
+
 template <typename T>
 cudaError_t dalloc(T** p, size_t n) {
+  cudaError_t e = dalloc_raw(p, n);
+  if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); g_reaper.join_all(); e = dalloc_raw(p, n); }
+  return e;
+}
+
+template <typename T>
+cudaError_t dalloc_raw(T** p, size_t n) {
   *p = nullptr;
   if (n == 0) n = 1;
   return cudaMalloc((void**)p, n * sizeof(T));
@@ -654,6 +693,8 @@ void hb_config_default(hb_config* c) {
   c->mt = 1; c->rng_mode = HB_RNG_PHILOX; c->seed = 1312;
 }
 
+void hb_wait_idle(void) { g_reaper.join_all(); }
+
 int hb_test_force_wide(int on) { const int prev = g_hb_force_wide; g_hb_force_wide = on ? 1 : 0; return prev; }
 
 int hb_device_count(void) {
@@ -745,8 +786,13 @@ void hb_destroy(hb_handle* h) {
                   h->out_ar, h->out_cr, h->proxy, h->proxy_full, h->lpost_full, h->outl_dev, h->news_dev, h->rstat_dev,
                   h->rstat_xm, h->rstat_ss, h->stage, h->pmin, h->pmax, h->prior_W, h->prior_mu, h->ZT, h->lp_zt, h->ll_zt, h->fx_zt, h->id_zt, h->mt_p1, h->mt_accept, h->rstat_sums, h->gamma_tab, h->outl_tmp, h->outl_sorted, h->outl_thr,
                   h->outl_count};
-  for (void* p : ptrs) if (p) cudaFree(p);
-  for (void* p : h->tape_allocs) cudaFree(p);
+  {
+    std::vector<void*> dead;
+    for (void* p : ptrs) if (p) dead.push_back(p);
+    for (void* p : h->tape_allocs) dead.push_back(p);
+    const int dev = h->device;
+    g_reaper.add(std::thread([dead, dev]() { cudaSetDevice(dev); for (void* p : dead) cudaFree(p); }));
+  }
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   pin_release(h);

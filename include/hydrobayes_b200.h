@@ -175,7 +175,8 @@ int hb_target_registered(const char* name);               /* 1 / 0 */
 void hb_config_default(hb_config* cfg);                    /* reference defaults of dream_parallel() */
 int hb_device_count(void);                                 /* CUDA devices visible; 0 => nothing will run */
 int hb_create(const hb_config* cfg, int device, hb_handle** out);
-void hb_destroy(hb_handle* h);
+void hb_destroy(hb_handle* h);                             /* device buffers are released by a background thread */
+void hb_wait_idle(void);                                   /* blocks until the releases of destroyed handles are done */
 const char* hb_last_error(const hb_handle* h);             /* h may be NULL: last error of a failed hb_create */
 
 int hb_set_bounds(hb_handle* h, const double* par_min, const double* par_max, int n); /* n == 1 (recycled) or d */
