@@ -11,6 +11,7 @@ acceptance on the CPU, and there is no fallback when the library or a device is 
 from __future__ import annotations
 
 import ctypes as C
+import os
 import time
 from typing import Optional
 
@@ -172,7 +173,7 @@ class Sampler:
         n = n_chains or self.n_local()
         out = np.empty((dm["out_t"], self.cfg.d + 3, n), order="F")
         th = None
-        if prefault and out.nbytes >= (64 << 20):
+        if prefault and out.nbytes >= (64 << 20) and os.environ.get("HB_NO_PREFAULT") != "1":
             th = threading.Thread(target=self.L.hb_host_prefault, args=(out.ctypes.data, out.nbytes, 0), daemon=True)
             th.start()                                   # ctypes releases the GIL for the duration of the call
         return out, th

@@ -8,7 +8,7 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 w = bench.workload("C4"); c = w["cfg"]; x0 = w["x0"]()
 par = dict(initial="user", val_ini=x0, prior="flat")
-for rep in range(2):
+for rep in range(3):
     dist.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     res = hb.dream_parallel(w["target"], lik=c.lik, par_info=par, nc=c.nc, t=c.t, d=c.d, thin=c.thin, verbose=False, seed=1312,
