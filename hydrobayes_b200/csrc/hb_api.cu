@@ -775,6 +775,8 @@ void hb_destroy(hb_handle* h) {
       if (h->flags_opened[r]) cudaIpcCloseMemHandle(h->flags_opened[r]);
     }
     cudaFree(h->arena);
+    cudaFree(h->X); h->X = nullptr;   // IPC-exported buffers are released synchronously, right after this rank closed its
+                                      // own imports (only the private buffers below go to the reaper thread)
   }
   if (h->peer_mode) {
     h->X = nullptr;
