@@ -163,3 +163,47 @@ def test_native_rng_transforms(oracle):
     assert L.hbo_rng_normal32(0x00000000) == (-12 * 16 - 15) * float.fromhex("0x1.9c614ae8b41e8p-6")
     assert L.hbo_rng_normal32(0xffffffff) == (12 * 16 + 15) * float.fromhex("0x1.9c614ae8b41e8p-6")
     assert abs(z.mean()) < 0.05 and abs(z.var() - 1.0) < 0.06
+
+
+def _hydro_np(P, K):
+    S = 1.0; Y = np.empty(len(P))
+    for i, p in enumerate(P):
+        S = (p + S) / (1 + K); Y[i] = K * S
+    return Y
+
+
+def test_calc_ll_abc_and_sls_flags(oracle):
+    # calc_ll, R/internals.R:8-16, restated independently in numpy: lik 21 (sum(log(abc_e)) over abc_e AS GIVEN: a scalar
+    # abc_e is counted once, R recycles only inside the squared term), lik 22 = min(abc_e - rho), lik 99 = fun_lik (SLS)
+    import helpers as H
+    T = 40
+    P, obs = H.hydro_data(T=T)
+    Ks = np.array([[0.05], [0.3], [1.2]])
+    ev = np.linspace(0.5, 2.0, T)
+    fl = oracle.log_xmin()
+    for K in Ks[:, 0]:
+        Y = _hydro_np(P, K); rho = np.abs(Y - obs)
+        exp21s = -T / 2 * np.log(2 * np.pi) - np.log(0.8) - 0.5 * np.sum((rho / 0.8) ** 2)
+        exp21v = -T / 2 * np.log(2 * np.pi) - np.sum(np.log(ev)) - 0.5 * np.sum((rho / ev) ** 2)
+        exp22s = np.min(2.5 - rho); exp22v = np.min(ev - rho)
+        exp99 = -T / 2 * np.log(np.sum((Y - obs) ** 2))
+        x = np.array([[K]])
+        for lik, e, exp in ((21, 0.8, exp21s), (21, ev, exp21v), (22, 2.5, exp22s), (22, ev, exp22v), (99, None, exp99)):
+            ll, _, rc = oracle.logdensity("HydroModel", lik, x, forcing=P, obs=obs, abc_e=e)
+            assert rc == 0
+            assert ll[0] == pytest.approx(max(exp, fl), rel=1e-12)
+
+
+def test_multi_try_oracle_moments(oracle):
+    # MT-DREAM (R/dream_parallel.R:295-341) must leave the posterior unchanged and raise the acceptance rate
+    import helpers as H
+    from hydrobayes_b200 import _abi as A
+    acc = {}
+    for mt in (1, 4):
+        cfg = A.default_config(nc=32, t=1500, d=3, lik=2, seed=8, mt=mt, record_accept=1)
+        r = oracle.run(cfg, "t_distribution", H.x0_tdist(32, 3))
+        assert r["rc"] == 0, r["err"]
+        acc[mt] = r["accept"][500:].mean()
+        v = r["chain"][500:, :3, :].var(axis=(0, 2))
+        np.testing.assert_allclose(v, 60.0 / 58.0 * np.arange(1, 4), rtol=0.15)
+    assert acc[4] > 1.3 * acc[1]
