@@ -1,12 +1,18 @@
 /*
- * hb_rglue.c -- .Call glue between the HydroBayes R drivers and libhydrobayes_b200.so.
+ * hb_rglue.c -- .Call glue between the HydroBayes R drivers (the files under r-package/R) and libhydrobayes_b200.so.
  *
- * NOT COMPILED IN THE BUILD IMAGE (Rinternals.h is absent there); shown as the reference-side binding a HydroBayes
- * maintainer would add (src/ + useDynLib(HydroBayes) in NAMESPACE, PKG_LIBS = -lhydrobayes_b200 in src/Makevars).
- * Every entry point below wraps exactly one function of include/hydrobayes_b200.h.
+ * The reference has no native boundary at all; this is the binding a HydroBayes maintainer adds:
+ * src/hb_rglue.c + src/Makevars, useDynLib(HydroBayes, .registration = TRUE) in NAMESPACE.  Every entry point wraps
+ * exactly one function of include/hydrobayes_b200.h; R owns every result array (allocated by R, garbage collected),
+ * the library owns what is behind the external pointer (finalizer -> hb_destroy).
+ *
+ * R itself is absent from the build image (no Rinternals.h), so this file cannot be compiled against real R there;
+ * tests/test_r_glue.py compiles it against a minimal stand-in for R's C API (tests/mock_r/) and drives the entry points
+ * in the order r-package/R/hb_drive.R calls them -- that checks the glue's own logic, not R.
  */
 #include <R.h>
 #include <Rinternals.h>
+#include <R_ext/Rdynload.h>
 #include <string.h>
 #include "hydrobayes_b200.h"
 
@@ -21,7 +27,7 @@ static hb_handle* H(SEXP ptr) {
 }
 static void chk(hb_handle* h, int rc) { if (rc != HB_OK) error("%s", hb_last_error(h)); }  /* -> stop(<message>) */
 
-/* cfg: named list built by the R driver from the formals of dream()/dream_parallel() */
+/* cfg: named list built by the R driver from the formals of dream()/dream_parallel(); NULL entries keep the default */
 static double num(SEXP l, const char* n, double dflt) {
   SEXP names = getAttrib(l, R_NamesSymbol);
   for (int i = 0; i < length(l); ++i)
@@ -44,6 +50,7 @@ SEXP hbR_create(SEXP cfg_list, SEXP device) {
   c.past_sample = (int)num(cfg_list, "past_sample", 0); c.m0 = (int64_t)num(cfg_list, "m0", 0);
   c.archive_update = (int)num(cfg_list, "archive_update", 0); c.psnooker = num(cfg_list, "psnooker", 0);
   c.mt = (int)num(cfg_list, "mt", 1); c.glue_shape = num(cfg_list, "glue_shape", 0);
+  c.rng_mode = HB_RNG_PHILOX;
   c.seed = (uint64_t)num(cfg_list, "seed", 1312); c.check_convergence = (int)num(cfg_list, "checkConvergence", 0);
   c.store_fx = (int)num(cfg_list, "store_fx", 1);
   hb_handle* h = NULL;
@@ -53,8 +60,13 @@ SEXP hbR_create(SEXP cfg_list, SEXP device) {
   UNPROTECT(1);
   return ptr;
 }
+SEXP hbR_destroy(SEXP p) { hb_finalizer(p); return R_NilValue; }   /* on.exit() of the driver: do not wait for the GC */
 
-SEXP hbR_set_bounds(SEXP p, SEXP mn, SEXP mx) { chk(H(p), hb_set_bounds(H(p), REAL(mn), REAL(mx), length(mn))); return R_NilValue; }
+SEXP hbR_set_bounds(SEXP p, SEXP mn, SEXP mx) {      /* par.info$min / $max: length 1 (recycled, R/internals.R:211-212) or d */
+  if (length(mn) != length(mx)) error("par.info$min and par.info$max must have the same length");
+  chk(H(p), hb_set_bounds(H(p), REAL(mn), REAL(mx), length(mn)));
+  return R_NilValue;
+}
 SEXP hbR_set_obs(SEXP p, SEXP obs) { chk(H(p), hb_set_obs(H(p), REAL(obs), (int64_t)XLENGTH(obs))); return R_NilValue; }
 SEXP hbR_set_prior_normal(SEXP p, SEXP mu, SEXP cov) {   /* par.info$mu, par.info$cov (prior = "normal", R/internals.R:58-59) */
   chk(H(p), hb_set_prior_normal(H(p), REAL(mu), REAL(cov)));
@@ -66,11 +78,12 @@ SEXP hbR_set_lik_args(SEXP p, SEXP abc_rho, SEXP abc_e, SEXP lik_fun) {
                             isNull(abc_e) ? 0 : (int64_t)XLENGTH(abc_e), isNull(lik_fun) ? NULL : CHAR(STRING_ELT(lik_fun, 0))));
   return R_NilValue;
 }
-SEXP hbR_set_target(SEXP p, SEXP fun, SEXP data) {   /* get(fun)(x, ...) -> name-keyed device plugin */
+SEXP hbR_set_target(SEXP p, SEXP fun, SEXP data) {   /* get(fun)(x, ...) -> name-keyed device plugin; data = the `...` */
   int64_t dims[1] = { isNull(data) ? 0 : (int64_t)XLENGTH(data) };
   chk(H(p), hb_set_target(H(p), CHAR(STRING_ELT(fun, 0)), isNull(data) ? NULL : REAL(data), dims, isNull(data) ? 0 : 1));
   return R_NilValue;
 }
+SEXP hbR_target_registered(SEXP fun) { return ScalarLogical(hb_target_registered(CHAR(STRING_ELT(fun, 0)))); }
 SEXP hbR_set_initial(SEXP p, SEXP x0) { chk(H(p), hb_set_initial(H(p), REAL(x0))); return R_NilValue; }  /* R matrices are column-major */
 SEXP hbR_run(SEXP p, SEXP n) {                      /* one slice; the R driver ticks txtProgressBar between slices */
   int64_t done = 0;
@@ -78,22 +91,20 @@ SEXP hbR_run(SEXP p, SEXP n) {                      /* one slice; the R driver t
   R_CheckUserInterrupt();
   return ScalarReal((double)done);
 }
-SEXP hbR_fetch(SEXP p) {                            /* list(chain, AR, CR [, fx, R_stat], outlier pairs) */
-  hb_handle* h = H(p);
-  int64_t out_t, ar_r, ar_c, cr_r, cr_c, fx_m, rs;
-  chk(h, hb_out_dims(h, &out_t, &ar_r, &ar_c, &cr_r, &cr_c, &fx_m, &rs));
-  SEXP res = PROTECT(allocVector(VECSXP, 3));
-  /* dims of chain come from the driver (d+3, nc): allocate with alloc3DArray(REALSXP, out_t, d+3, nc) there and pass
-     REAL(chain) to hb_fetch_chain; shown inline for AR / CR */
-  SEXP ar = PROTECT(allocMatrix(REALSXP, (int)ar_r, (int)ar_c)); chk(h, hb_fetch_ar(h, REAL(ar)));
-  SEXP cr = PROTECT(allocMatrix(REALSXP, (int)cr_r, (int)cr_c)); chk(h, hb_fetch_cr(h, REAL(cr)));
-  SET_VECTOR_ELT(res, 1, ar); SET_VECTOR_ELT(res, 2, cr);
-  UNPROTECT(3);
-  return res;
+SEXP hbR_out_dims(SEXP p) {                         /* c(out_t, ar_rows, ar_cols, cr_rows, cr_cols, fx_m, rstat_rows) */
+  int64_t v[7];
+  chk(H(p), hb_out_dims(H(p), &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6]));
+  SEXP out = PROTECT(allocVector(REALSXP, 7));
+  for (int i = 0; i < 7; ++i) REAL(out)[i] = (double)v[i];
+  UNPROTECT(1);
+  return out;
 }
-SEXP hbR_fetch_fx(SEXP p, SEXP fx) { chk(H(p), hb_fetch_fx(H(p), REAL(fx))); return fx; }            /* fx[out_t, nc, m] :203 */
-SEXP hbR_fetch_rstat(SEXP p, SEXP rs) { chk(H(p), hb_fetch_rstat(H(p), REAL(rs))); return rs; }     /* R_stat[out_t-50, d] */
-SEXP hbR_fetch_outliers(SEXP p) {                   /* two integer vectors: generation i and 1-based chain (outl[[i]], :418) */
+SEXP hbR_fetch_chain(SEXP p, SEXP chain) { chk(H(p), hb_fetch_chain(H(p), REAL(chain))); return chain; }  /* [out_t, d+3, nc] :201 */
+SEXP hbR_fetch_ar(SEXP p, SEXP ar) { chk(H(p), hb_fetch_ar(H(p), REAL(ar))); return ar; }              /* :205 / R/dream.R:161 */
+SEXP hbR_fetch_cr(SEXP p, SEXP cr) { chk(H(p), hb_fetch_cr(H(p), REAL(cr))); return cr; }              /* :204 / R/dream.R:161 */
+SEXP hbR_fetch_fx(SEXP p, SEXP fx) { chk(H(p), hb_fetch_fx(H(p), REAL(fx))); return fx; }              /* fx[out_t, nc, m] :230 */
+SEXP hbR_fetch_rstat(SEXP p, SEXP rs) { chk(H(p), hb_fetch_rstat(H(p), REAL(rs))); return rs; }        /* R_stat[out_t-50, d] */
+SEXP hbR_fetch_outliers(SEXP p) {                   /* list(generation i, 1-based chain): outl[[i]] <- outliers (:418) */
   hb_handle* h = H(p);
   int64_t n = 0;
   chk(h, hb_fetch_outliers(h, &n, NULL, NULL, 0));
@@ -107,13 +118,27 @@ SEXP hbR_fetch_outliers(SEXP p) {                   /* two integer vectors: gene
   UNPROTECT(3);
   return res;
 }
-SEXP hbR_fetch_chain(SEXP p, SEXP chain) { chk(H(p), hb_fetch_chain(H(p), REAL(chain))); return chain; }
-SEXP hbR_rstat_array(SEXP x) {                      /* R_stat(x): x[t, d, n] */
+SEXP hbR_rstat_array(SEXP x) {                      /* R_stat(x): x[t, d, n]  (R/gelman_rubin.R:21) */
   SEXP dim = getAttrib(x, R_DimSymbol);
+  if (isNull(dim) || length(dim) != 3) error("x must be a 3-d array [samples, parameters, chains]");
   int d = INTEGER(dim)[1];
   SEXP out = PROTECT(allocVector(REALSXP, d));
   char err[256];
   if (hb_rstat_array(REAL(x), INTEGER(dim)[0], d, INTEGER(dim)[2], REAL(out), err, sizeof err) != HB_OK) error("%s", err);
   UNPROTECT(1);
   return out;
+}
+
+#define HB_CALLDEF(name, n) { #name, (DL_FUNC)&name, n }
+static const R_CallMethodDef hb_call_entries[] = {
+  HB_CALLDEF(hbR_create, 2), HB_CALLDEF(hbR_destroy, 1), HB_CALLDEF(hbR_set_bounds, 3), HB_CALLDEF(hbR_set_obs, 2),
+  HB_CALLDEF(hbR_set_prior_normal, 3), HB_CALLDEF(hbR_set_lik_args, 4), HB_CALLDEF(hbR_set_target, 3),
+  HB_CALLDEF(hbR_target_registered, 1), HB_CALLDEF(hbR_set_initial, 2), HB_CALLDEF(hbR_run, 2), HB_CALLDEF(hbR_out_dims, 1),
+  HB_CALLDEF(hbR_fetch_chain, 2), HB_CALLDEF(hbR_fetch_ar, 2), HB_CALLDEF(hbR_fetch_cr, 2), HB_CALLDEF(hbR_fetch_fx, 2),
+  HB_CALLDEF(hbR_fetch_rstat, 2), HB_CALLDEF(hbR_fetch_outliers, 1), HB_CALLDEF(hbR_rstat_array, 1),
+  { NULL, NULL, 0 }
+};
+void R_init_HydroBayes(DllInfo* dll) {
+  R_registerRoutines(dll, NULL, hb_call_entries, NULL, NULL);
+  R_useDynamicSymbols(dll, FALSE);
 }

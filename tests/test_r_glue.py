@@ -1,0 +1,175 @@
+"""The reference-side binding (r-package/): `.Call` glue compiled against a stand-in for R's C API (tests/mock_r) --
+R itself is absent from the build image.  CPU tests: the glue compiles, registers every symbol the R drivers `.Call`
+with the arity they pass, and turns a C-ABI failure into an R error (stop) with the library's message.  GPU test: the
+entry points, driven in the order r-package/R/hb_drive.R calls them with R's column-major arrays, give exactly what the
+Python host mirror gives for the same seed (both sit on the same C ABI) and agree with the oracle."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+import helpers as H
+from hydrobayes_b200 import _abi as A
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "mock_r"))
+import rmock  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def R():
+    r = rmock.MockR()
+    yield r
+    r.free_all()
+
+
+def _r_sources():
+    src = {}
+    for f in sorted(os.listdir(os.path.join(ROOT, "r-package", "R"))):
+        src[f] = open(os.path.join(ROOT, "r-package", "R", f)).read()
+    return src
+
+
+def test_every_dotcall_in_the_r_drivers_is_registered_with_matching_arity(R):
+    entries = R.entries()
+    assert R.L.mockR_dynamic_symbols() == 0                       # R_useDynamicSymbols(dll, FALSE)
+    used = {}
+    for f, text in _r_sources().items():
+        for m in re.finditer(r"\.Call\((hbR_\w+)((?:[^()]|\((?:[^()]|\([^()]*\))*\))*)\)", text):
+            name, rest = m.group(1), m.group(2)
+            depth = 0; nargs = 0
+            for ch in rest:                                       # top-level commas = number of arguments after the symbol
+                depth += ch in "([" ; depth -= ch in ")]"
+                nargs += (ch == "," and depth == 0)
+            used.setdefault(name, set()).add(nargs)
+    assert used, "no .Call sites found"
+    for name, arities in used.items():
+        assert name in entries, f"{name} is .Call'ed by the R drivers but not registered in hb_rglue.c"
+        assert arities == {entries[name]}, (name, arities, entries[name])
+    assert set(entries) == set(used), "registered but never called from R: " + ", ".join(sorted(set(entries) - set(used)))
+
+
+def test_r_formals_match_the_reference_signature():
+    # R/dream_parallel.R:155-163 and R/dream.R:126-133: same formals, same order, same defaults; additions come last
+    src = _r_sources()
+    want_par = ["fun", "...", "lik", "par.info", "nc", "t", "d", "burnin", "adapt", "updateInterval", "delta", "c_val", "c_star",
+                "nCR", "p_g", "beta0", "thin", "outlier_check", "obs", "abc_rho", "abc_e", "glue_shape", "lik_fun"]
+    tails = {"dream_parallel.R": ["past_sample", "m0", "archive_update", "psnooker", "mt", "ncores", "checkConvergence", "verbose",
+                                  "seed", "device"],
+             "dream.R": ["checkConvergence", "verbose", "seed", "device"]}
+    for f, tail in tails.items():
+        head = src[f][src[f].index("function(") + 9: src[f].index(") {")]
+        head = re.sub(r"list\([^)]*\)", "LIST", head)
+        names = [a.split("=")[0].strip() for a in head.split(",")]
+        assert names == want_par + tail, (f, names)
+    assert 'prior = "flat"' in src["dream_parallel.R"] and 'prior = "uniform"' in src["dream.R"]
+    for frag in ["burnin = 0", "adapt = 0.1", "updateInterval = 10", "delta = 3", "c_val = 0.1", "c_star = 1e-12", "nCR = 3",
+                 "p_g = 0.2", "beta0 = 1", "thin = 1", "outlier_check = TRUE"]:
+        assert frag in src["dream_parallel.R"] and frag in src["dream.R"], frag
+
+
+def test_dotcall_checks_symbol_and_arity_like_r(R):
+    with pytest.raises(rmock.RError, match="not in DLL"):
+        R.call("hbR_no_such_entry", R.nil)
+    with pytest.raises(rmock.RError, match="Incorrect number of arguments"):
+        R.call("hbR_run", R.nil)
+
+
+@pytest.mark.skipif(A.lib().hb_device_count() > 0, reason="needs a machine WITHOUT a CUDA device")
+def test_no_device_becomes_an_r_error(R):
+    cfg = R.named_list(sweep=0, nc=8, t=10, d=2, lik=2)
+    with pytest.raises(rmock.RError, match="(?i)cuda|device"):     # there is no CPU fallback behind the glue either
+        R.call("hbR_create", cfg, R.integer(0))
+    x = R.real(np.zeros((60, 2, 3)))
+    with pytest.raises(rmock.RError, match="(?i)cuda|device"):
+        R.call("hbR_rstat_array", x)
+    with pytest.raises(rmock.RError, match="3-d array"):
+        R.call("hbR_rstat_array", R.real(np.zeros(10)))
+    assert R.to_numpy(R.call("hbR_target_registered", R.string("t_distribution")))[0] == 1
+    assert R.to_numpy(R.call("hbR_target_registered", R.string("my_r_closure")))[0] == 0
+
+
+def _hb_drive(R, sweep, fun, dots, lik, par_info, nc, t, d, z, seed, adapt=0.1, updateInterval=10, obs=None, glue_shape=None,
+              checkConvergence=False, past_sample=False, prior="flat", bound=None, **cfg_kw):
+    """r-package/R/hb_drive.R, statement by statement, with the mock's .Call."""
+    prior_code = ["flat", "uniform", "normal"].index(prior)
+    bound_code = 0 if bound is None else ["bound", "reflect", "fold"].index(bound) + 1
+    store_fx = fun in ("mixture", "t_distribution")
+    cfg = R.named_list(sweep=sweep, nc=nc, t=t, d=d, lik=lik, adapt=adapt, updateInterval=updateInterval, prior=prior_code,
+                       bound=bound_code, past_sample=past_sample, m0=None, archive_update=None, glue_shape=glue_shape,
+                       seed=seed, checkConvergence=checkConvergence, store_fx=store_fx, **cfg_kw)
+    h = R.call("hbR_create", cfg, R.integer(0))
+    try:
+        if par_info.get("min") is not None:
+            R.call("hbR_set_bounds", h, R.real(np.atleast_1d(par_info["min"])), R.real(np.atleast_1d(par_info["max"])))
+        if obs is not None:
+            R.call("hbR_set_obs", h, R.real(obs))
+        R.call("hbR_set_target", h, R.string(fun), R.real(dots[0]) if dots else R.nil)
+        R.call("hbR_set_initial", h, R.real(z))                     # an R matrix: column-major
+        dims = R.to_numpy(R.call("hbR_out_dims", h)).astype(int)
+        out_t = dims[0]
+        chain = R.real_na(out_t, d + 3, nc)                          # array(NA_real_, dim = c(out_t, d + 3, nc))
+        done, slices = 1, 0
+        while done < t:
+            done = int(R.to_numpy(R.call("hbR_run", h, R.real([max(1, t // 50)])))[0]); slices += 1
+        R.call("hbR_fetch_chain", h, chain)
+        out = dict(chain=R.to_numpy(chain, (out_t, d + 3, nc)), slices=slices)
+        out["AR"] = R.to_numpy(R.call("hbR_fetch_ar", h, R.real_na(dims[1], dims[2])), (dims[1], dims[2]))
+        out["CR"] = R.to_numpy(R.call("hbR_fetch_cr", h, R.real_na(dims[3], dims[4])), (dims[3], dims[4]))
+        if store_fx:
+            out["fx"] = R.to_numpy(R.call("hbR_fetch_fx", h, R.real_na(out_t, nc, 1)), (out_t, nc, 1))
+        op = R.call("hbR_fetch_outliers", h)
+        out["outlier"] = list(zip(R.to_numpy(R.list_elt(op, 0)).tolist(), R.to_numpy(R.list_elt(op, 1)).tolist()))
+        if checkConvergence and dims[6] > 0:
+            out["R_stat"] = R.to_numpy(R.call("hbR_fetch_rstat", h, R.real_na(dims[6], d)), (dims[6], d))
+    finally:
+        R.call("hbR_destroy", h)                                     # on.exit(.Call(hbR_destroy, h))
+    with pytest.raises(rmock.RError, match="already destroyed"):
+        R.call("hbR_run", h, R.real([1.0]))
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sweep", [A.HB_SWEEP_SYNCHRONOUS, A.HB_SWEEP_SEQUENTIAL])
+def test_dotcall_sequence_matches_host_mirror_and_oracle(R, sweep):
+    from oracle import hb_oracle_py as oracle
+    nc, t, d, seed = 24, 130, 6, 77
+    x0 = H.x0_tdist(nc, d)
+    x0[5] = 300.0                                                    # one chain far out: an outlier reset must happen
+    got = _hb_drive(R, sweep, "t_distribution", (), 2, {}, nc, t, d, x0, seed, adapt=0.5, checkConvergence=True)
+    assert got["slices"] == -(-(t - 1) // max(1, t // 50))
+    cfg = A.default_config(nc=nc, t=t, d=d, lik=2, seed=seed, sweep=sweep, adapt=0.5, check_convergence=1, store_fx=1)
+    dev = H.run_device(cfg, "t_distribution", x0)
+    assert np.array_equal(got["chain"], dev["chain"], equal_nan=True)         # same C ABI underneath: bit-identical
+    assert np.array_equal(got["AR"], dev["AR"], equal_nan=True) and np.array_equal(got["CR"], dev["CR"], equal_nan=True)
+    assert np.array_equal(got["fx"][:, :, 0], dev["fx"], equal_nan=True)
+    assert np.array_equal(got["R_stat"], dev["R_stat"], equal_nan=True)
+    assert len(got["outlier"]) > 0
+    assert got["outlier"] == [(g, c + 1) for g, c in dev["outlier"]]             # R side: 1-based chain numbers
+    ora = oracle.run(cfg, "t_distribution", x0)
+    np.testing.assert_allclose(got["chain"], ora["chain"], rtol=1e-9, atol=1e-12, equal_nan=True)
+    r = R.to_numpy(R.call("hbR_rstat_array", R.real(got["chain"][:, :d, :])))  # R_stat(chain[, 1:d, ])
+    np.testing.assert_allclose(r, oracle.rstat(got["chain"][:, :d, :]), rtol=1e-10)
+
+
+@pytest.mark.gpu
+def test_dotcall_hydromodel_with_bounds_and_library_errors(R):
+    from oracle import hb_oracle_py as oracle
+    P, obs = H.hydro_data(T=120)
+    nc, t = 16, 90
+    x0 = H.x0_hydro(nc)
+    got = _hb_drive(R, 0, "HydroModel", (P,), 31, dict(min=0.01, max=2.0), nc, t, 1, x0, 5, adapt=0.4, obs=obs, glue_shape=50.0,
+                    prior="uniform", bound="reflect")
+    cfg = A.default_config(nc=nc, t=t, d=1, lik=31, glue_shape=50.0, prior=A.HB_PRIOR_UNIFORM, bound=A.HB_BOUND_REFLECT, seed=5,
+                           adapt=0.4)
+    ora = oracle.run(cfg, "HydroModel", x0, par_min=[0.01], par_max=[2.0], forcing=P, obs=obs)
+    np.testing.assert_allclose(got["chain"], ora["chain"], rtol=1e-9, atol=1e-12, equal_nan=True)
+    # stop() sites of the reference, worded by the library: nc <= 2 * delta (R/dream_parallel.R:166-167), unknown target
+    with pytest.raises(rmock.RError, match="'nc' must be > 'delta' \\* 2"):
+        R.call("hbR_create", R.named_list(sweep=0, nc=6, t=10, d=2, lik=2), R.integer(0))
+    h = R.call("hbR_create", R.named_list(sweep=0, nc=8, t=10, d=2, lik=2), R.integer(0))
+    with pytest.raises(rmock.RError, match="my_r_closure"):
+        R.call("hbR_set_target", h, R.string("my_r_closure"), R.nil)
+    R.call("hbR_destroy", h)
