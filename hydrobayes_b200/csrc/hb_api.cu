@@ -270,7 +270,7 @@ int allocate(hb_handle* h) {
     CK(cudaMalloc(&h->outl_tmp, h->outl_tmp_bytes ? h->outl_tmp_bytes : 16));
     CK(dalloc(&h->outl_sorted, (size_t)h->nc)); CK(dalloc(&h->outl_thr, 1)); CK(dalloc(&h->outl_count, 1));
   }
-  if (h->rstat_rows > 0) { CK(dalloc(&h->rstat_dev, (size_t)h->rstat_rows * d)); CK(hb_launch_fill(h->rstat_dev, h->rstat_rows * d, NAN, h->stream)); }
+  if (h->rstat_rows > 0) { CK(dalloc(&h->rstat_dev, (size_t)h->rstat_rows * nr * d)); CK(hb_launch_fill(h->rstat_dev, h->rstat_rows * nr * d, NAN, h->stream)); }   // [row][run][d]
   CK(dalloc(&h->rstat_xm, (size_t)nl * d)); CK(dalloc(&h->rstat_ss, (size_t)nl * d));
   {  // gamma_d table, R/internals.R:190
     std::vector<double> g((size_t)c.delta * d);
@@ -1277,10 +1277,14 @@ int hb_fetch_rstat(hb_handle* h, double* rstat) {
   if (!h || !rstat) return HB_ERR_INVALID;
   if (h->rstat_rows < 1) return fail(h, HB_ERR_STATE, "check_convergence was not enabled (or out_t <= 50)");
   cudaSetDevice(h->device);
-  std::vector<double> tmp((size_t)h->rstat_rows * h->d);
+  const long long nr = h->cfg.n_runs, rows = h->rstat_rows;
+  std::vector<double> tmp((size_t)rows * nr * h->d);
+  CK(cudaStreamSynchronize(h->stream));
   CK(cudaMemcpy(tmp.data(), h->rstat_dev, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
-  for (long long r = 0; r < h->rstat_rows; ++r)
-    for (int k = 0; k < h->d; ++k) rstat[r + h->rstat_rows * k] = tmp[(size_t)r * h->d + k];
+  for (long long run = 0; run < nr; ++run)                     // run-major blocks of column-major [rstat_rows, d]
+    for (long long r = 0; r < rows; ++r)
+      for (int k = 0; k < h->d; ++k)
+        rstat[(size_t)run * rows * h->d + r + rows * k] = tmp[((size_t)r * nr + run) * h->d + k];
   return HB_OK;
 }
 

@@ -22,7 +22,6 @@
 int hb_seq_supported(const hb_config* cfg, std::string& why) {
   if (cfg->past_sample || cfg->psnooker > 0) { why = "archive sampling (DREAM-ZS) is only available for a single synchronous population"; return HB_ERR_UNSUPPORTED; }
   if (cfg->nc > 2048) { why = "sequential sweep / batched runs support nc <= 2048 chains per run"; return HB_ERR_UNSUPPORTED; }
-  if (cfg->check_convergence) { why = "checkConvergence is only available for a single synchronous population"; return HB_ERR_UNSUPPORTED; }
   if (cfg->n_runs * cfg->nc > 0x7fffffffLL) { why = "too many chains in one handle"; return HB_ERR_UNSUPPORTED; }
   return HB_OK;
 }
@@ -142,6 +141,14 @@ int hb_seq_generation(hb_handle* h, long long i) {
       SCK(hb_launch_runfin(f, nr, h->stream));
       h->launches++;
     }
+  }
+  if (c.check_convergence && store && h->ind_out > 50) {
+    // out_rstat[ind_out - 50, ] <- R_stat(chain[1:ind_out, 1:d, ]) of every run (R/dream.R:270-271 with out_x := the stored
+    // chain as R/dream_test.R:344); the history rows are not touched by the outlier reset, so the order against
+    // the bookkeeping kernel does not matter.  rstat_dev is [row][run][d].
+    SCK(hb_launch_rstat_runs(h->hist_x, h->ind_out, nct, nc, nr, d, h->rstat_xm, h->rstat_ss,
+                             h->rstat_dev + (size_t)(h->ind_out - 51) * nr * d, h->stream));
+    h->launches += 2;
   }
   h->gen = i;
   return HB_OK;

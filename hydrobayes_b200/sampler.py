@@ -214,10 +214,13 @@ class Sampler:
         return ar, cr
 
     def fetch_rstat(self) -> np.ndarray:
+        """out_rstat[out_t - 50, d] (R/dream.R:163, R/dream_parallel.R:207); batched runs: [n_runs, out_t - 50, d]."""
         dm = self.out_dims()
-        out = np.empty((dm["rstat_rows"], self.cfg.d), order="F")
+        nr = max(self.cfg.n_runs, 1)
+        out = np.empty((nr, self.cfg.d, dm["rstat_rows"]))          # run-major blocks of column-major [rows, d]
         self._check(self.L.hb_fetch_rstat(self.h, _ptr(out)))
-        return out
+        out = np.transpose(out, (0, 2, 1))
+        return np.asfortranarray(out[0]) if nr == 1 else out
 
     def fetch_state(self, n_chains: Optional[int] = None):
         d = self.cfg.d

@@ -44,7 +44,7 @@ enum {
   HB_ERR_UNKNOWN_TARGET = 5, /* name not in the device plugin registry (get(fun) would fail in R) */
   HB_ERR_STATE = 6,        /* call order (e.g. hb_run before hb_set_initial) */
   HB_ERR_NCCL = 7,
-  HB_ERR_UNSUPPORTED = 8   /* a reference feature that is not on the device path (mt>1, lik 21/22/99) */
+  HB_ERR_UNSUPPORTED = 8   /* a combination that is not on the device path (e.g. mt > 1 on several GPUs) */
 };
 
 /* sweep: which reference driver's data dependence to reproduce */
@@ -76,7 +76,7 @@ typedef struct hb_config {
   int64_t nc;              /* chains per run */
   int64_t t;               /* samples per chain (generation 1 is the initial state) */
   int32_t d;               /* parameters */
-  int32_t lik;             /* likelihood flag of calc_ll (R/internals.R:3-23): 1, 2, 31 on device */
+  int32_t lik;             /* likelihood flag of calc_ll (R/internals.R:3-23): 1, 2, 21, 22, 31, 99 */
   int64_t n_runs;          /* independent runs batched in one handle (BASELINE C5); 1 = the reference call */
   double burnin;           /* 0   */
   double adapt;            /* 0.1 */
@@ -94,13 +94,13 @@ typedef struct hb_config {
   int32_t past_sample;     /* DREAM(ZS) archive sampling (dream_parallel only) */
   int64_t m0;              /* 0 = reference default (10*d if past_sample else nc) */
   int32_t archive_update;  /* 0 = reference default (10 if past_sample else never) */
-  int32_t mt;              /* multi-try; only 1 on device */
+  int32_t mt;              /* multi-try (MT-DREAM, R/dream_parallel.R:295-341); synchronous sweep, one GPU */
   double psnooker;         /* 0 */
   double glue_shape;       /* lik == 31 */
   int32_t rng_mode;        /* HB_RNG_* */
   int32_t record_accept;   /* keep the accept mask of every generation (parity tests) */
   uint64_t seed;           /* Philox key */
-  int32_t check_convergence; /* compute R_stat rows like dream_test (R/dream_test.R:344); SURVEY F7 */
+  int32_t check_convergence; /* R_stat rows of the stored chain as dream_test does (R/dream_test.R:344); SURVEY F7 */
   int32_t store_fx;        /* keep raw target output per stored generation (only targets with m == 1) */
   int32_t exchange;        /* HB_EXCHANGE_* (multi-GPU only) */
   int32_t run_offset;      /* global index of this handle's first run: Philox chain id = (run_offset + run)*nc + j */
@@ -227,7 +227,7 @@ int hb_host_prefault(void* p, size_t bytes, int n_threads);
 int hb_fetch_fx(hb_handle* h, double* fx);                 /* [out_t, nct, m] */
 int hb_fetch_ar(hb_handle* h, double* ar);                 /* run-major blocks of [ar_rows, ar_cols] */
 int hb_fetch_cr(hb_handle* h, double* cr);
-int hb_fetch_rstat(hb_handle* h, double* rstat);           /* [rstat_rows, d] per run */
+int hb_fetch_rstat(hb_handle* h, double* rstat);           /* run-major blocks of [rstat_rows, d] (either sweep) */
 int hb_fetch_state(hb_handle* h, double* xt_colmajor, double* lp, double* ll, double* lpost);
 int hb_fetch_accept(hb_handle* h, uint8_t* accept);        /* [t-1][nct] if record_accept */
 /* outlier list (R/dream_parallel.R:418): call with buf == NULL to get the count of (generation, chain) pairs */

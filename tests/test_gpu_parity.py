@@ -398,8 +398,9 @@ def test_zs_wide_kernel(hb, oracle):
 
 
 # ---------------------------------------------------------------- convergence check inside the run ----
-def test_check_convergence_rows(hb, oracle):
-    cfg = A.default_config(nc=8, t=90, d=3, lik=2, seed=23, check_convergence=1)
+@pytest.mark.parametrize("sweep", [A.HB_SWEEP_SYNCHRONOUS, A.HB_SWEEP_SEQUENTIAL])
+def test_check_convergence_rows(hb, oracle, sweep):
+    cfg = A.default_config(nc=8, t=90, d=3, lik=2, seed=23, check_convergence=1, sweep=sweep)
     x0 = H.x0_tdist(8, 3)
     ora = oracle.run(cfg, "t_distribution", x0)
     dev = H.run_device(cfg, "t_distribution", x0)
@@ -411,6 +412,22 @@ def test_check_convergence_rows(hb, oracle):
         r = s.rstat()
         ch = s.fetch_chain()[:61, :3, :]
     np.testing.assert_allclose(r, oracle.rstat(ch), rtol=1e-10)
+
+
+def test_check_convergence_batched_runs(hb, oracle):
+    # checkConvergence on a batched handle: out_rstat rows of every run, each equal to the single-run oracle's
+    nr, nc, d, t = 3, 8, 2, 80
+    cfg = A.default_config(nc=nc, t=t, d=d, lik=2, seed=31, check_convergence=1, n_runs=nr, sweep=A.HB_SWEEP_SEQUENTIAL)
+    x0 = H.x0_tdist(nr * nc, d)
+    from hydrobayes_b200 import Sampler
+    with Sampler(cfg, 0) as s:
+        s.set_target("t_distribution"); s.set_initial(x0); s.run(t)
+        rs = s.fetch_rstat()
+    assert rs.shape == (nr, t - 50, d)
+    for r in range(nr):
+        ora = oracle.run(cfg, "t_distribution", x0[r * nc:(r + 1) * nc], run=r)   # one run at a time (chain ids r*nc + j)
+        assert ora["rc"] == 0, ora["err"]
+        np.testing.assert_allclose(rs[r], ora["R_stat"], rtol=1e-9)
 
 
 def test_python_api_dream_and_dream_parallel(hb):
