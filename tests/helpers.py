@@ -118,3 +118,46 @@ def copy_cfg(cfg, **kw):
     for k, v in kw.items():
         setattr(c, k, v)
     return c
+
+
+def random_case(case):
+    """Seeded sweep over the option space: both sweeps, every bound / prior / likelihood combination of the device path.
+    Returns (cfg, target, x0, extra keyword arguments of oracle.run / run_device)."""
+    rng = np.random.default_rng(1000 + case)
+    sweep = int(rng.integers(0, 2))
+    target = ["mixture", "t_distribution", "HydroModel"][int(rng.integers(0, 3))]
+    delta = int(rng.integers(1, 5)); nCR = int(rng.integers(1, 7))
+    nc = 2 * delta + 1 + int(rng.integers(0, 6))
+    t = int(rng.integers(20, 70))
+    kw = dict(nc=nc, t=t, seed=int(rng.integers(1, 10_000)), sweep=sweep, delta=delta, nCR=nCR,
+              adapt=float(rng.choice([0.0, 0.3, 0.6, 1.0])), update_interval=int(rng.choice([1, 3, 5, 10])),
+              p_g=float(rng.choice([0.0, 0.2, 0.7])), beta0=float(rng.choice([1.0, 0.5])), c_val=float(rng.choice([0.1, 0.4])),
+              c_star=float(rng.choice([1e-12, 1e-3])), outlier_check=int(rng.integers(0, 2)))
+    thin = int(rng.choice([1, 1, 2, 5]))
+    if t % thin == 0:
+        kw["thin"] = thin
+    extra = {}
+    if target == "mixture":
+        kw.update(d=1, lik=1, store_fx=1)
+        x0 = x0_mixture(nc)
+        if rng.integers(0, 2):
+            kw.update(prior=A.HB_PRIOR_UNIFORM, bound=int(rng.integers(0, 4)))
+            extra.update(par_min=[-25.0], par_max=[22.0])
+    elif target == "t_distribution":
+        d = int(rng.integers(1, 6))
+        kw.update(d=d, lik=2, store_fx=1)
+        x0 = x0_tdist(nc, d)
+        if rng.integers(0, 2):
+            kw.update(prior=int(rng.choice([A.HB_PRIOR_FLAT, A.HB_PRIOR_UNIFORM])), bound=int(rng.integers(0, 4)))
+            extra.update(par_min=list(-6.0 - np.arange(d)), par_max=list(16.0 + np.arange(d)))
+    else:
+        T = int(rng.integers(5, 40))
+        P, obs = hydro_data(T=T, catchment=case)
+        lik = int(rng.choice([31, 21, 22, 99]))
+        kw.update(d=1, lik=lik, glue_shape=float(rng.choice([5.0, 50.0])), prior=A.HB_PRIOR_UNIFORM, bound=int(rng.integers(1, 4)))
+        x0 = x0_hydro(nc)
+        extra.update(par_min=[0.01], par_max=[2.0], forcing=P, obs=obs)
+        if lik in (21, 22):
+            extra["abc_e"] = float(rng.uniform(0.5, 3.0)) if rng.integers(0, 2) else rng.uniform(0.5, 3.0, size=T)
+    cfg = A.default_config(**kw)
+    return cfg, target, x0, extra

@@ -130,3 +130,21 @@ def test_identical_chains_give_zero_spread(hb, oracle, sweep):
             np.testing.assert_allclose(s.fetch_chain(), ora["chain"], rtol=1e-12, equal_nan=True)
     cfg0 = A.default_config(nc=nc, t=30, d=d, lik=2, seed=1, sweep=sweep, adapt=0.0, c_star=0.0)   # outside adaptation J is never read
     _native(oracle, cfg0, "t_distribution", x0)
+
+
+@pytest.mark.parametrize("case", range(24))
+def test_random_configurations_device(hb, oracle, case):
+    # the seeded option-space sweep of tests/test_restatement_crosscheck.py, replayed on the device: the oracle records
+    # the decision tape of its Philox run, oracle and device replay it (accept/reject identical, chain within 1e-10)
+    cfg, target, x0, extra = H.random_case(case)
+    rec = oracle.Tape.for_config(cfg)
+    r0 = oracle.run(cfg, target, x0, record=rec, **extra)
+    assert r0["rc"] == 0, r0["err"]
+    cfg_t = H.copy_cfg(cfg, rng_mode=A.HB_RNG_TAPE, record_accept=1)
+    ora = oracle.run(cfg_t, target, x0, tape=rec, **extra)
+    dev = H.run_device(cfg_t, target, x0, tape=rec, **extra)
+    H.assert_run_parity(dev, ora, rtol=1e-10, check_fx=(target != "HydroModel"))
+    # and with native Philox draws
+    cfg_n = H.copy_cfg(cfg, record_accept=1)
+    H.assert_run_parity(H.run_device(cfg_n, target, x0, **extra), oracle.run(cfg_n, target, x0, **extra), rtol=1e-9, atol=1e-12,
+                        check_fx=(target != "HydroModel"))

@@ -589,6 +589,10 @@ def test_native_mixture_moments(hb):
     assert abs(m.mean() - 7) < 4 * m.std(ddof=1) / np.sqrt(nc) + 0.05
     assert abs(p.mean() - 1 / 6) < 4 * p.std(ddof=1) / np.sqrt(nc) + 0.003
     assert abs(x.var() - 46) < 1.5
+    # quantiles of 1/6 N(-8, 1) + 5/6 N(10, 1): p = 0.1 lies in the minor mode (its position is sensitive to the mode weight)
+    from scipy.stats import norm
+    want = [-8 + norm.ppf(0.1 * 6), 10 + norm.ppf((0.5 - 1 / 6) * 6 / 5), 10 + norm.ppf((0.9 - 1 / 6) * 6 / 5)]
+    np.testing.assert_allclose(np.quantile(x, [0.1, 0.5, 0.9]), want, atol=0.25)
     assert res["AR"].shape == (t // 10 + 1, 2) and res["CR"].shape == (t // 10 + 1, 4)
     assert np.isnan(res["AR"][0, 1]) and res["AR"][0, 0] == nc
 
@@ -601,6 +605,12 @@ def test_native_tdist_moments(hb):
     var = x.var(axis=(0, 2))
     np.testing.assert_allclose(var, 60 / 58 * np.arange(1, d + 1), rtol=0.08)
     assert np.abs(x.mean(axis=(0, 2))).max() < 0.15
+    # marginal quantiles: x_i / sqrt(i) ~ Student-t with 60 degrees of freedom (Monte Carlo tolerance 0.15 sd)
+    from scipy.stats import t as student
+    probs = [0.05, 0.25, 0.5, 0.75, 0.95]
+    for k in range(d):
+        q = np.quantile(x[:, k, :], probs) / np.sqrt(k + 1)
+        np.testing.assert_allclose(q, student.ppf(probs, 60), atol=0.15)
 
 
 # ---------------------------------------------------------------- full-size properties ----------------------------

@@ -187,3 +187,12 @@ def test_check_convergence_rows_and_rstat(oracle):
     x = np.sin(0.37 * i * k + 1.3 * c) + 0.1 * c * k
     np.testing.assert_allclose(R.R_stat(x), [1.0113185866169283, 1.0735661244327646], rtol=1e-12)
     np.testing.assert_allclose(oracle.rstat(x), R.R_stat(x), rtol=1e-12)
+
+
+@pytest.mark.parametrize("case", range(24))
+def test_random_configurations(oracle, case):
+    # seeded sweep over the option space (tests/helpers.py: random_case); the same cases run on the device in
+    # tests/test_gpu_edge_cases.py::test_random_configurations_device
+    cfg, target, x0, extra = H.random_case(case)
+    py, ora = _both(oracle, cfg, target, x0, **extra)
+    _agree(py, ora, fx=(target != "HydroModel"))
