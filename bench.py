@@ -472,6 +472,19 @@ def main():
                     others[name] = quick_rate(name, local, torch)
                 except Exception as e:  # report, never hide
                     others[name] = {"error": repr(e)}
+        if "C2" in others and "error" not in others["C2"]:
+            # the opt-in fused small-population kernel (HB_FUSED=1: proposal + log-density + accept in one launch, see
+            # DESIGN.md section 8) measured next to the default three-kernel path; a failure is reported, never hidden
+            os.environ["HB_FUSED"] = "1"
+            try:
+                f = quick_rate("C2", local, torch)
+                others["C2"]["experimental_fused_kernel"] = {k: f[k] for k in ("value", "us_per_generation", "device_us_per_generation",
+                                                                             "gpu_launches", "generations")}
+                others["C2"]["experimental_fused_kernel"]["enable"] = "HB_FUSED=1 (off by default this round)"
+            except Exception as e:
+                others["C2"]["experimental_fused_kernel"] = {"error": repr(e)}
+            finally:
+                os.environ.pop("HB_FUSED", None)
         try:
             others["C5"] = convergence_c5(local, torch)
         except Exception as e:

@@ -494,6 +494,28 @@ int rstat_population(hb_handle* h, long long t_rows, double* out_dev) {
   return HB_OK;
 }
 
+// The fused generation kernel applies to: dream_parallel's synchronous sweep of one population on one GPU, the built-in
+// t_distribution target with lik = 2, flat / uniform prior, no archive, no multi-try, populations below the size where the
+// large-population kernels take over (hb_fused_small_eligible).  EXPERIMENTAL, opt-in with HB_FUSED=1: the first version
+// measured slower than the three-kernel path on BASELINE C2, and its log-density uses the FMA kernel's
+// summation order, so ll differs from the DMMA plugin's in the last bit (the chain states are identical).
+bool fused_available(hb_handle* h) {
+  const hb_config& c = h->cfg;
+  if (h->fused_state == 0) {
+    h->fused_state = -1;
+    const char* e = getenv("HB_FUSED");
+    if ((e && e[0] == '1') && c.sweep == HB_SWEEP_SYNCHRONOUS && !h->modeb && c.mt <= 1 && h->world == 1 && !h->peer_mode &&
+        !h->delta_mode && !c.past_sample && c.lik == 2 && c.prior != HB_PRIOR_NORMAL && h->X &&
+        hb_tdist_fused_info(h->vt, h->tctx, &h->fused_td)) {
+      if (cudaMalloc((void**)&h->Xalt, (size_t)h->nc * h->ldx * sizeof(double)) == cudaSuccess &&
+          cudaMemsetAsync(h->Xalt, 0, (size_t)h->nc * h->ldx * sizeof(double), h->stream) == cudaSuccess)
+        h->fused_state = 1;
+      else cudaGetLastError();
+    }
+  }
+  return h->fused_state == 1 && !h->profile && hb_fused_small_eligible(h->n_local, h->d, h->sm_count);
+}
+
 int run_generation(hb_handle* h, long long i) {
   const hb_config& c = h->cfg;
   const long long nl = h->n_local;
@@ -545,6 +567,15 @@ int run_generation(hb_handle* h, long long i) {
     int nb = 0;
     CK(hb_launch_k3(p, h->sm_count, &nb, nullptr, h->stream));
     ps.done();
+  } else if (!in_adapt && fused_available(h)) {
+    // small population outside the adaptation period: proposal + log-density + accept in one launch, the post-generation
+    // rows go to the second buffer (no grid-wide barrier between the partner reads and the state update)
+    const hb_k1_params p = hb_make_k1(h, i, h->chain0, 1, nl);
+    hb_k3_params q = hb_make_k3(h, i, h->chain0, 1, nl, store, false, false);
+    q.Xout = h->Xalt;
+    CK(hb_launch_fused_small(p, q, h->fused_td, tape_mode, h->sm_count, h->stream));
+    h->launches++;
+    std::swap(h->X, h->Xalt);
   } else {
   {  // K1
     const hb_k1_params p = hb_make_k1(h, i, h->chain0, 1, nl);
@@ -783,7 +814,7 @@ void hb_destroy(hb_handle* h) {
     for (int b = 0; b < 2; ++b) for (int r = 0; r < 8; ++r) if (h->peer_opened[b][r]) cudaIpcCloseMemHandle(h->peer_opened[b][r]);
     cudaFree(h->Xbuf[0]); cudaFree(h->Xbuf[1]);
   }
-  void* ptrs[] = {h->X, h->Z, h->XP, h->id, h->lp_xp, h->ll_raw, h->fx_xp, h->lp, h->ll, h->lpost, h->fx, h->lpost_hist,
+  void* ptrs[] = {h->X, h->Xalt, h->Z, h->XP, h->id, h->lp_xp, h->ll_raw, h->fx_xp, h->lp, h->ll, h->lpost, h->fx, h->lpost_hist,
                   h->hist_x, h->hist_l, h->hist_fx, h->accept_rec, h->ctrl, h->shift, h->colsum, h->qsum, h->partials,
                   h->out_ar, h->out_cr, h->proxy, h->proxy_full, h->lpost_full, h->outl_dev, h->news_dev, h->rstat_dev,
                   h->rstat_xm, h->rstat_ss, h->stage, h->pmin, h->pmax, h->prior_W, h->prior_mu, h->ZT, h->lp_zt, h->ll_zt, h->fx_zt, h->id_zt, h->mt_p1, h->mt_accept, h->rstat_sums, h->gamma_tab, h->outl_tmp, h->outl_sorted, h->outl_thr,

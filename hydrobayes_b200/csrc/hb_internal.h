@@ -86,6 +86,10 @@ struct hb_handle {
 
   // device state
   double *X = nullptr, *Z = nullptr, *XP = nullptr;
+  // fused small-population generation (hb_launch_fused_small): second population buffer, swapped with X every generation
+  double* Xalt = nullptr;
+  int fused_state = 0;                    // 0 undecided, 1 available, -1 not applicable to this handle
+  hb_fused_tdist fused_td{};
   int* id = nullptr;
   double *lp_xp = nullptr, *ll_raw = nullptr, *fx_xp = nullptr;
   double *lp = nullptr, *ll = nullptr, *lpost = nullptr, *fx = nullptr;
@@ -140,6 +144,8 @@ hb_k3_params hb_make_k3(hb_handle* h, long long i, long long first, long long st
 int hb_prior_after_k1(hb_handle* h, long long n_items);
 int hb_target_launch(hb_handle* h, const double* x, long long n, long long first, long long stride);
 int hb_fail(hb_handle* h, int code, const char* msg);
+// hb_targets.cu: true when vt/ctx is the built-in t_distribution plugin; fills the operands of the fused kernel
+bool hb_tdist_fused_info(const hb_target_vtable* vt, void* ctx, hb_fused_tdist* out);
 
 // hb_comm.cu: NCCL loaded lazily with dlopen (no link-time dependency; single-GPU use needs no NCCL)
 int hb_nccl_unique_id(void* id128, std::string& err);

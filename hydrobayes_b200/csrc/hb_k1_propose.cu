@@ -42,241 +42,254 @@ __device__ __forceinline__ double comp_group_sum(double hi, double lo, unsigned 
   return __dadd_rn(hi, lo);
 }
 
+// One chain's jump (calc_prop up to dx, R/internals.R:119-200) for the G lanes that own chain `base + lane / G`: the
+// per-chain draws, the partner gather and dx.  Shared by the proposal kernel and the fused small-population kernel.
 template <int G, int ITER, bool TAPE>
-__global__ void __launch_bounds__(256) hb_k1_kernel(const hb_k1_params p) {
+__device__ __forceinline__ void k1_chain_jump(const hb_k1_params& p, long long base, int lane, double (&xk)[ITER],
+                                              double (&dxk)[ITER], bool& valid, long long& jl, int& id, unsigned& errbits) {
   constexpr unsigned FULL = 0xffffffffu;
-  constexpr int CPW = 32 / G;
-  const int lane = threadIdx.x & 31;
   const int lg = lane & (G - 1);
   const int gbase = lane & ~(G - 1);
   const unsigned gmask = hb_group_mask<G>(lane);
-  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const int d = p.d, ldx = p.ldx, nCR = p.nCR, delta = p.delta;
   const double* __restrict__ src = p.past_sample ? p.Z : p.X;
+  const long long jl_raw = base + lane / G;
+  valid = jl_raw < p.n_local;
+  jl = valid ? jl_raw : p.n_local - 1;
+  const long long gl = p.chain0 + jl * p.stride;   // chain index within the handle (run-major)
+  const long long run = p.n_runs > 1 ? gl / p.nc : 0;
+  const long long j = gl - run * p.nc;         // chain within the run
+  const long long rbase = gl - j;              // first chain of the run
+  const long long gch = p.gchain0 + gl;        // global chain id: Philox counter
+  const long long rix = p.tape_g * p.tape.nct + gl;   // tape column
+
+  // ---------------- per-chain draws: snooker test, D, partners, crossover id, gamma choice ----------------
+  double u_sn, g_sn = 0.0;
+  int D, g_is_one;
+  long long pa[HB_MAX_DELTA], pb[HB_MAX_DELTA];   // a = first D partners, b = next D (R/internals.R:143-144)
+  long long ps2 = 0;                               // third snooker row (:127)
+  const hb_phx ph(p.seed, (uint64_t)gch, p.gen);
+  if (TAPE) {
+    u_sn = p.tape.u_snooker ? p.tape.u_snooker[rix] : 1.0;            // R/internals.R:119
+    D = p.tape.D[rix];                                               // :123
+    id = p.tape.id[rix];                                             // :173
+    g_is_one = p.tape.g_is_one[rix];                                 // :192
+    if (p.tape.g_snooker) g_sn = p.tape.g_snooker[rix];              // :156
+    if (D < 1 || D > delta || id >= nCR) { errbits |= HB_FLAG_BAD_TAPE; D = 1; id = 0; }
+    const int32_t* pr = p.tape.partners + rix * (2 * delta);
+#pragma unroll
+    for (int q = 0; q < HB_MAX_DELTA; ++q) {
+      pa[q] = (q < D) ? pr[q] : 0;
+      pb[q] = (q < D) ? pr[D + q] : 0;
+    }
+    if (p.past_sample && u_sn < p.psnooker) { pa[0] = pr[0]; pb[0] = pr[1]; ps2 = pr[2]; }
+  } else {
+    uint4 hw[6];
+#pragma unroll
+    for (int s0 = 0; s0 < 6; s0 += G) {
+      uint4 w = make_uint4(0, 0, 0, 0);
+      const int s = s0 + lg;
+      if (s < 6) w = ph.slot((uint32_t)s);
+#pragma unroll
+      for (int q = 0; q < G && s0 + q < 6; ++q) {
+        if (G == 1) { hw[s0 + q] = w; }
+        else {
+          hw[s0 + q].x = __shfl_sync(FULL, w.x, gbase + q);
+          hw[s0 + q].y = __shfl_sync(FULL, w.y, gbase + q);
+          hw[s0 + q].z = __shfl_sync(FULL, w.z, gbase + q);
+          hw[s0 + q].w = __shfl_sync(FULL, w.w, gbase + q);
+        }
+      }
+    }
+    u_sn = hb_u53(hb_pair64(hw[HB_SLOT_HEAD], 0));
+    D = 1 + (int)hb_mulhi64(hb_pair64(hw[HB_SLOT_HEAD], 1), (uint64_t)delta);
+    const double u_id = hb_u53(hb_pair64(hw[HB_SLOT_CHOICE], 0));
+    double cum = 0.0;
+    id = nCR - 1;
+    bool found = false;
+    for (int q = 0; q < nCR; ++q) {
+      cum += p.ctrl[run].pCR[q];
+      if (!found && u_id < cum) { id = q; found = true; }
+    }
+    g_is_one = hb_u53(hb_pair64(hw[HB_SLOT_CHOICE], 1)) >= 1.0 - p.p_g;
+    const bool sn = p.past_sample && (u_sn < p.psnooker);
+    if (sn) g_sn = 1.2 + hb_u53(hb_pair64(ph.slot(HB_SLOT_ACCEPT), 1));
+    const int n_part = sn ? 3 : 2 * D;
+    hb_fy fy;
+    long long n_rem = p.past_sample ? p.m_arch : p.nc - 1;
+    long long y[2 * HB_MAX_DELTA];
+#pragma unroll
+    for (int q = 0; q < 2 * HB_MAX_DELTA; ++q) {
+      y[q] = 0;
+      if (q < n_part) {
+        long long v = fy.draw(hb_pair64(hw[HB_SLOT_PARTNER0 + (q >> 1)], q & 1), n_rem);
+        if (!p.past_sample && v >= j) v += 1;                        // sample((1:nc)[-j], ...)  :142
+        y[q] = v;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < HB_MAX_DELTA; ++q) {
+      pa[q] = y[q];
+      pb[q] = (D == 1) ? y[(1 + q) & 7] : (D == 2) ? y[(2 + q) & 7] : (D == 3) ? y[(3 + q) & 7] : y[(4 + q) & 7];
+    }
+    if (sn) { pb[0] = y[1]; ps2 = y[2]; }
+  }
+  const bool snooker = p.past_sample && (u_sn < p.psnooker);
+  {
+    const long long n_src = p.past_sample ? p.m_arch : p.nc;
+#pragma unroll
+    for (int q = 0; q < HB_MAX_DELTA; ++q) {
+      const bool used = snooker ? (q == 0) : (q < D);
+      if (used && (pa[q] < 0 || pa[q] >= n_src || pb[q] < 0 || pb[q] >= n_src)) {
+        errbits |= HB_FLAG_BAD_TAPE; pa[q] = 0; pb[q] = 0;
+      }
+    }
+    if (snooker && (ps2 < 0 || ps2 >= n_src)) { errbits |= HB_FLAG_BAD_TAPE; ps2 = 0; }
+  }
+
+  const double* __restrict__ xrow = p.X + gl * (long long)ldx;
+  const double* __restrict__ srcr = p.past_sample ? src : src + rbase * (long long)ldx;   // partner rows of this run
+
+  if (snooker) {
+    // ---------------- snooker update, R/internals.R:150-163 with orth_proj :250-263 ----------------
+    const double* r1 = srcr + pa[0] * (long long)ldx;
+    const double* r2 = srcr + pb[0] * (long long)ldx;
+    const double* r3 = srcr + ps2 * (long long)ldx;
+    double uu[ITER], a2[ITER], a3[ITER];
+    double s2 = 0, s3 = 0, su = 0, l2 = 0, l3 = 0, lu = 0;
+    int differs = 0;
+#pragma unroll
+    for (int m = 0; m < ITER; ++m) {
+      const int k = m * G + lg;
+      xk[m] = 0; uu[m] = 0; a2[m] = 0; a3[m] = 0;
+      if (k < d) {
+        xk[m] = xrow[k];
+        const double b = r1[k];
+        a2[m] = r2[k]; a3[m] = r3[k];
+        uu[m] = __dadd_rn(xk[m], -b);
+        differs |= (xk[m] != b);
+        comp_add(s2, l2, __dmul_rn(__dadd_rn(a2[m], -xk[m]), uu[m]));
+        comp_add(s3, l3, __dmul_rn(__dadd_rn(a3[m], -xk[m]), uu[m]));
+        comp_add(su, lu, __dmul_rn(uu[m], uu[m]));
+      }
+    }
+    s2 = comp_group_sum<G>(s2, l2, gmask); s3 = comp_group_sum<G>(s3, l3, gmask); su = comp_group_sum<G>(su, lu, gmask);
+    differs = hb_group_sum_int<G>(differs, gmask);
+#pragma unroll
+    for (int m = 0; m < ITER; ++m) {
+      const int k = m * G + lg;
+      dxk[m] = 0;
+      if (k < d) {
+        double zeta;
+        if (TAPE) zeta = p.tape.zeta[rix * d + k];
+        else { const uint4 w = ph.slot(HB_SLOT_DIM0 + (uint32_t)(k >> 1)); zeta = hb_zeta32((k & 1) ? w.w : w.y, p.c_star); }
+        double rp2 = a2[m], rp3 = a3[m];
+        if (differs) {
+          rp2 = __dadd_rn(xk[m], __ddiv_rn(__dmul_rn(uu[m], s2), su));   // q <- a + u*sum((p-a)*u)/sum(u*u)
+          rp3 = __dadd_rn(xk[m], __ddiv_rn(__dmul_rn(uu[m], s3), su));
+        }
+        if (!isfinite(rp2) || !isfinite(rp3)) errbits |= HB_FLAG_PROP_NONFINITE;   // :260
+        dxk[m] = __dadd_rn(zeta, __dmul_rn(g_sn, __dadd_rn(rp2, -rp3)));          // :163
+      }
+    }
+  } else {
+    // ---------------- parallel direction update, R/internals.R:166-200 ----------------
+    const double CRv = (double)(id + 1) / (double)nCR;               // CR <- (1:nCR)/nCR
+    double ztv[ITER];
+    uint32_t wl[ITER], wz[ITER];     // slot map v2: one Philox call per two dimensions (lo word: zt | lambda; hi: zeta)
+    unsigned selmask[ITER];
+    int d_star = 0;
+#pragma unroll
+    for (int m = 0; m < ITER; ++m) {
+      const int k = m * G + lg;
+      ztv[m] = 2.0; wl[m] = 0; wz[m] = 0;
+      if (k < d) {
+        if (TAPE) ztv[m] = p.tape.zt[rix * d + k];                   // :175
+        else {
+          const uint4 w = ph.slot(HB_SLOT_DIM0 + (uint32_t)(k >> 1));
+          const uint32_t lo = (k & 1) ? w.z : w.x;
+          ztv[m] = hb_rng_u16(lo); wl[m] = lo >> 16; wz[m] = (k & 1) ? w.w : w.y;
+        }
+      }
+      selmask[m] = hb_group_ballot<G>(k < d && ztv[m] < CRv, lane, gmask); // A <- which(zt < CR[id])  :177
+      d_star += __popc(selmask[m]);
+    }
+    int kmin = -1;
+    if (d_star == 0) {                             // :181-184  A <- which.min(zt)
+      double bv = 3.0; int bk = 0x7fffffff;
+#pragma unroll
+      for (int m = 0; m < ITER; ++m) {
+        const int k = m * G + lg;
+        if (k < d && ztv[m] < bv) { bv = ztv[m]; bk = k; }
+      }
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(gmask, bv, o);
+        const int ok = __shfl_xor_sync(gmask, bk, o);
+        if (ov < bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
+      }
+      kmin = bk; d_star = 1;
+    }
+    const double gamma_d = 2.38 / sqrt(2.0 * (double)D * (double)d_star);   // :190
+    const double gam = g_is_one ? 1.0 : gamma_d;                            // :192
+    int rank_base = 0;
+#pragma unroll
+    for (int m = 0; m < ITER; ++m) {
+      const int k = m * G + lg;
+      const bool sel = (kmin >= 0) ? (k == kmin) : ((selmask[m] >> lg) & 1u);
+      xk[m] = 0; dxk[m] = 0;
+      if (k < d) {
+        xk[m] = xrow[k];
+        if (sel) {
+          double lambda, zeta;
+          if (TAPE) {
+            const int rank = (kmin >= 0) ? 0 : rank_base + __popc(selmask[m] & ((1u << lg) - 1u));
+            lambda = p.tape.lambda[rix * d + rank];                  // :188 (by rank within A)
+            zeta = p.tape.zeta[rix * d + rank];                      // :194
+          } else {
+            lambda = hb_rng_lambda16(wl[m], p.c_val);
+            zeta = hb_zeta32(wz[m], p.c_star);
+          }
+          // jump_diff <- colSums(r1[,A] - r2[,A])   :196
+          double s = 0.0, comp = 0.0;
+#pragma unroll
+          for (int q = 0; q < HB_MAX_DELTA; ++q) {
+            if (q < D) {
+              const double a = srcr[pa[q] * (long long)ldx + k];
+              const double b = srcr[pb[q] * (long long)ldx + k];
+              const double t = __dadd_rn(a, -b);
+              if (q == 0) s = t;
+              else { double e; two_sum(s, t, s, e); comp = __dadd_rn(comp, e); }
+            }
+          }
+          const double jd = __dadd_rn(s, comp);
+          // dx[A] <- (zeta + (1+lambda)*g*jump_diff) * beta0   :198-200
+          const double v = __dadd_rn(zeta, __dmul_rn(__dmul_rn(__dadd_rn(1.0, lambda), gam), jd));
+          dxk[m] = __dmul_rn(v, p.beta0);
+        }
+      }
+      rank_base += __popc(selmask[m]);
+    }
+  }
+
+}
+
+template <int G, int ITER, bool TAPE>
+__global__ void __launch_bounds__(256) hb_k1_kernel(const hb_k1_params p) {
+  constexpr int CPW = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int lg = lane & (G - 1);
+  const unsigned gmask = hb_group_mask<G>(lane);
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int d = p.d, ldx = p.ldx;
   unsigned errbits = 0;
 
   for (long long base = warp_id * CPW; base < p.n_local; base += n_warps * CPW) {
-    const long long jl_raw = base + lane / G;
-    const bool valid = jl_raw < p.n_local;
-    const long long jl = valid ? jl_raw : p.n_local - 1;
-    const long long gl = p.chain0 + jl * p.stride;   // chain index within the handle (run-major)
-    const long long run = p.n_runs > 1 ? gl / p.nc : 0;
-    const long long j = gl - run * p.nc;         // chain within the run
-    const long long rbase = gl - j;              // first chain of the run
-    const long long gch = p.gchain0 + gl;        // global chain id: Philox counter
-    const long long rix = p.tape_g * p.tape.nct + gl;   // tape column
-
-    // ---------------- per-chain draws: snooker test, D, partners, crossover id, gamma choice ----------------
-    double u_sn, g_sn = 0.0;
-    int D, id, g_is_one;
-    long long pa[HB_MAX_DELTA], pb[HB_MAX_DELTA];   // a = first D partners, b = next D (R/internals.R:143-144)
-    long long ps2 = 0;                               // third snooker row (:127)
-    const hb_phx ph(p.seed, (uint64_t)gch, p.gen);
-    if (TAPE) {
-      u_sn = p.tape.u_snooker ? p.tape.u_snooker[rix] : 1.0;            // R/internals.R:119
-      D = p.tape.D[rix];                                               // :123
-      id = p.tape.id[rix];                                             // :173
-      g_is_one = p.tape.g_is_one[rix];                                 // :192
-      if (p.tape.g_snooker) g_sn = p.tape.g_snooker[rix];              // :156
-      if (D < 1 || D > delta || id >= nCR) { errbits |= HB_FLAG_BAD_TAPE; D = 1; id = 0; }
-      const int32_t* pr = p.tape.partners + rix * (2 * delta);
-#pragma unroll
-      for (int q = 0; q < HB_MAX_DELTA; ++q) {
-        pa[q] = (q < D) ? pr[q] : 0;
-        pb[q] = (q < D) ? pr[D + q] : 0;
-      }
-      if (p.past_sample && u_sn < p.psnooker) { pa[0] = pr[0]; pb[0] = pr[1]; ps2 = pr[2]; }
-    } else {
-      uint4 hw[6];
-#pragma unroll
-      for (int s0 = 0; s0 < 6; s0 += G) {
-        uint4 w = make_uint4(0, 0, 0, 0);
-        const int s = s0 + lg;
-        if (s < 6) w = ph.slot((uint32_t)s);
-#pragma unroll
-        for (int q = 0; q < G && s0 + q < 6; ++q) {
-          if (G == 1) { hw[s0 + q] = w; }
-          else {
-            hw[s0 + q].x = __shfl_sync(FULL, w.x, gbase + q);
-            hw[s0 + q].y = __shfl_sync(FULL, w.y, gbase + q);
-            hw[s0 + q].z = __shfl_sync(FULL, w.z, gbase + q);
-            hw[s0 + q].w = __shfl_sync(FULL, w.w, gbase + q);
-          }
-        }
-      }
-      u_sn = hb_u53(hb_pair64(hw[HB_SLOT_HEAD], 0));
-      D = 1 + (int)hb_mulhi64(hb_pair64(hw[HB_SLOT_HEAD], 1), (uint64_t)delta);
-      const double u_id = hb_u53(hb_pair64(hw[HB_SLOT_CHOICE], 0));
-      double cum = 0.0;
-      id = nCR - 1;
-      bool found = false;
-      for (int q = 0; q < nCR; ++q) {
-        cum += p.ctrl[run].pCR[q];
-        if (!found && u_id < cum) { id = q; found = true; }
-      }
-      g_is_one = hb_u53(hb_pair64(hw[HB_SLOT_CHOICE], 1)) >= 1.0 - p.p_g;
-      const bool sn = p.past_sample && (u_sn < p.psnooker);
-      if (sn) g_sn = 1.2 + hb_u53(hb_pair64(ph.slot(HB_SLOT_ACCEPT), 1));
-      const int n_part = sn ? 3 : 2 * D;
-      hb_fy fy;
-      long long n_rem = p.past_sample ? p.m_arch : p.nc - 1;
-      long long y[2 * HB_MAX_DELTA];
-#pragma unroll
-      for (int q = 0; q < 2 * HB_MAX_DELTA; ++q) {
-        y[q] = 0;
-        if (q < n_part) {
-          long long v = fy.draw(hb_pair64(hw[HB_SLOT_PARTNER0 + (q >> 1)], q & 1), n_rem);
-          if (!p.past_sample && v >= j) v += 1;                        // sample((1:nc)[-j], ...)  :142
-          y[q] = v;
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < HB_MAX_DELTA; ++q) {
-        pa[q] = y[q];
-        pb[q] = (D == 1) ? y[(1 + q) & 7] : (D == 2) ? y[(2 + q) & 7] : (D == 3) ? y[(3 + q) & 7] : y[(4 + q) & 7];
-      }
-      if (sn) { pb[0] = y[1]; ps2 = y[2]; }
-    }
-    const bool snooker = p.past_sample && (u_sn < p.psnooker);
-    {
-      const long long n_src = p.past_sample ? p.m_arch : p.nc;
-#pragma unroll
-      for (int q = 0; q < HB_MAX_DELTA; ++q) {
-        const bool used = snooker ? (q == 0) : (q < D);
-        if (used && (pa[q] < 0 || pa[q] >= n_src || pb[q] < 0 || pb[q] >= n_src)) {
-          errbits |= HB_FLAG_BAD_TAPE; pa[q] = 0; pb[q] = 0;
-        }
-      }
-      if (snooker && (ps2 < 0 || ps2 >= n_src)) { errbits |= HB_FLAG_BAD_TAPE; ps2 = 0; }
-    }
-
-    const double* __restrict__ xrow = p.X + gl * (long long)ldx;
-    const double* __restrict__ srcr = p.past_sample ? src : src + rbase * (long long)ldx;   // partner rows of this run
     double xk[ITER], dxk[ITER];
     double lp_part = 0.0;
-
-    if (snooker) {
-      // ---------------- snooker update, R/internals.R:150-163 with orth_proj :250-263 ----------------
-      const double* r1 = srcr + pa[0] * (long long)ldx;
-      const double* r2 = srcr + pb[0] * (long long)ldx;
-      const double* r3 = srcr + ps2 * (long long)ldx;
-      double uu[ITER], a2[ITER], a3[ITER];
-      double s2 = 0, s3 = 0, su = 0, l2 = 0, l3 = 0, lu = 0;
-      int differs = 0;
-#pragma unroll
-      for (int m = 0; m < ITER; ++m) {
-        const int k = m * G + lg;
-        xk[m] = 0; uu[m] = 0; a2[m] = 0; a3[m] = 0;
-        if (k < d) {
-          xk[m] = xrow[k];
-          const double b = r1[k];
-          a2[m] = r2[k]; a3[m] = r3[k];
-          uu[m] = __dadd_rn(xk[m], -b);
-          differs |= (xk[m] != b);
-          comp_add(s2, l2, __dmul_rn(__dadd_rn(a2[m], -xk[m]), uu[m]));
-          comp_add(s3, l3, __dmul_rn(__dadd_rn(a3[m], -xk[m]), uu[m]));
-          comp_add(su, lu, __dmul_rn(uu[m], uu[m]));
-        }
-      }
-      s2 = comp_group_sum<G>(s2, l2, gmask); s3 = comp_group_sum<G>(s3, l3, gmask); su = comp_group_sum<G>(su, lu, gmask);
-      differs = hb_group_sum_int<G>(differs, gmask);
-#pragma unroll
-      for (int m = 0; m < ITER; ++m) {
-        const int k = m * G + lg;
-        dxk[m] = 0;
-        if (k < d) {
-          double zeta;
-          if (TAPE) zeta = p.tape.zeta[rix * d + k];
-          else { const uint4 w = ph.slot(HB_SLOT_DIM0 + (uint32_t)(k >> 1)); zeta = hb_zeta32((k & 1) ? w.w : w.y, p.c_star); }
-          double rp2 = a2[m], rp3 = a3[m];
-          if (differs) {
-            rp2 = __dadd_rn(xk[m], __ddiv_rn(__dmul_rn(uu[m], s2), su));   // q <- a + u*sum((p-a)*u)/sum(u*u)
-            rp3 = __dadd_rn(xk[m], __ddiv_rn(__dmul_rn(uu[m], s3), su));
-          }
-          if (!isfinite(rp2) || !isfinite(rp3)) errbits |= HB_FLAG_PROP_NONFINITE;   // :260
-          dxk[m] = __dadd_rn(zeta, __dmul_rn(g_sn, __dadd_rn(rp2, -rp3)));          // :163
-        }
-      }
-    } else {
-      // ---------------- parallel direction update, R/internals.R:166-200 ----------------
-      const double CRv = (double)(id + 1) / (double)nCR;               // CR <- (1:nCR)/nCR
-      double ztv[ITER];
-      uint32_t wl[ITER], wz[ITER];     // slot map v2: one Philox call per two dimensions (lo word: zt | lambda; hi: zeta)
-      unsigned selmask[ITER];
-      int d_star = 0;
-#pragma unroll
-      for (int m = 0; m < ITER; ++m) {
-        const int k = m * G + lg;
-        ztv[m] = 2.0; wl[m] = 0; wz[m] = 0;
-        if (k < d) {
-          if (TAPE) ztv[m] = p.tape.zt[rix * d + k];                   // :175
-          else {
-            const uint4 w = ph.slot(HB_SLOT_DIM0 + (uint32_t)(k >> 1));
-            const uint32_t lo = (k & 1) ? w.z : w.x;
-            ztv[m] = hb_rng_u16(lo); wl[m] = lo >> 16; wz[m] = (k & 1) ? w.w : w.y;
-          }
-        }
-        selmask[m] = hb_group_ballot<G>(k < d && ztv[m] < CRv, lane, gmask); // A <- which(zt < CR[id])  :177
-        d_star += __popc(selmask[m]);
-      }
-      int kmin = -1;
-      if (d_star == 0) {                             // :181-184  A <- which.min(zt)
-        double bv = 3.0; int bk = 0x7fffffff;
-#pragma unroll
-        for (int m = 0; m < ITER; ++m) {
-          const int k = m * G + lg;
-          if (k < d && ztv[m] < bv) { bv = ztv[m]; bk = k; }
-        }
-#pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) {
-          const double ov = __shfl_xor_sync(gmask, bv, o);
-          const int ok = __shfl_xor_sync(gmask, bk, o);
-          if (ov < bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
-        }
-        kmin = bk; d_star = 1;
-      }
-      const double gamma_d = 2.38 / sqrt(2.0 * (double)D * (double)d_star);   // :190
-      const double gam = g_is_one ? 1.0 : gamma_d;                            // :192
-      int rank_base = 0;
-#pragma unroll
-      for (int m = 0; m < ITER; ++m) {
-        const int k = m * G + lg;
-        const bool sel = (kmin >= 0) ? (k == kmin) : ((selmask[m] >> lg) & 1u);
-        xk[m] = 0; dxk[m] = 0;
-        if (k < d) {
-          xk[m] = xrow[k];
-          if (sel) {
-            double lambda, zeta;
-            if (TAPE) {
-              const int rank = (kmin >= 0) ? 0 : rank_base + __popc(selmask[m] & ((1u << lg) - 1u));
-              lambda = p.tape.lambda[rix * d + rank];                  // :188 (by rank within A)
-              zeta = p.tape.zeta[rix * d + rank];                      // :194
-            } else {
-              lambda = hb_rng_lambda16(wl[m], p.c_val);
-              zeta = hb_zeta32(wz[m], p.c_star);
-            }
-            // jump_diff <- colSums(r1[,A] - r2[,A])   :196
-            double s = 0.0, comp = 0.0;
-#pragma unroll
-            for (int q = 0; q < HB_MAX_DELTA; ++q) {
-              if (q < D) {
-                const double a = srcr[pa[q] * (long long)ldx + k];
-                const double b = srcr[pb[q] * (long long)ldx + k];
-                const double t = __dadd_rn(a, -b);
-                if (q == 0) s = t;
-                else { double e; two_sum(s, t, s, e); comp = __dadd_rn(comp, e); }
-              }
-            }
-            const double jd = __dadd_rn(s, comp);
-            // dx[A] <- (zeta + (1+lambda)*g*jump_diff) * beta0   :198-200
-            const double v = __dadd_rn(zeta, __dmul_rn(__dmul_rn(__dadd_rn(1.0, lambda), gam), jd));
-            dxk[m] = __dmul_rn(v, p.beta0);
-          }
-        }
-        rank_base += __popc(selmask[m]);
-      }
-    }
+    bool valid; long long jl; int id;
+    k1_chain_jump<G, ITER, TAPE>(p, base, lane, xk, dxk, valid, jl, id, errbits);
 
     // ---------------- xp <- x + dx ; finite check ; bounds ; prior ----------------
 #pragma unroll
@@ -305,6 +318,182 @@ __global__ void __launch_bounds__(256) hb_k1_kernel(const hb_k1_params p) {
   if (errbits) atomicOr(p.err, errbits);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Fused generation for SMALL populations (BASELINE C2: nc = 1024, d = 100): proposal + t-distribution log-density +
+// Metropolis accept/update/store in ONE launch, one warp per chain.  At this size the three kernels of the large-population
+// path take a few microseconds each and the generation time is their launch gaps; fusing them removes two launches and the
+// XP / ll round trips through L2.  The synchronous sweep (R/dream_parallel.R:269, all proposals from the generation-start
+// state) is kept without a grid-wide barrier by double buffering the population: every chain reads partners from X and
+// writes its post-generation row into Xout (its proposal if accepted, its old row otherwise); the host swaps the buffers.
+// Only outside the adaptation period (the std_x / jump statistics need the whole post-update population).
+//   proposal      k1_chain_jump -- the same code, draw for draw, as hb_k1_kernel<32, ITER>
+//   log-density   z_n = sum_{k <= n} xp_k W[k][n], rss = sum z_n^2: the summation order of hb_tdist_fma_kernel (lane owns
+//                 columns n = 32 m + lane, k ascending); xp and W staged in shared memory (W by bulk TMA, once per CTA)
+//   accept        the non-adaptation path of hb_k3_kernel (R/internals.R:239-241, R/dream_parallel.R:348-366, 386-394)
+// ------------------------------------------------------------------------------------------------------------------
+template <int ITER, bool TAPE>
+__global__ void __launch_bounds__(256) hb_fused_small_kernel(const hb_k1_params p, const hb_k3_params q, const hb_fused_tdist td) {
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ __align__(16) double fused_smem[];               // W [d][ldw] | xs [warps][ITER * 32]
+  __shared__ unsigned long long s_cnt[2 * HB_MAX_NCR + 1];
+  __shared__ __align__(8) uint64_t wbar;
+  const int lane = threadIdx.x & 31;
+  double* Ws = fused_smem;
+  double* xs = fused_smem + (size_t)p.d * td.ldw + (size_t)(threadIdx.x >> 5) * (ITER * 32);
+  // W (d * ldw doubles, ldw even: a multiple of 16 bytes) is staged once per CTA by bulk TMA copies of at most 32 KB; it
+  // lands while the warps compute their first proposal (first measured version read W through L1/L2 inside the k loop:
+  // every warp of the SM missed on the same row at the same time, 33 us per generation against 23 us unfused)
+  const uint32_t w_bytes = (uint32_t)p.d * (uint32_t)td.ldw * 8u;
+  if (threadIdx.x == 0) {
+    mbar_init(&wbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int d = p.d, ldx = p.ldx;
+  unsigned errbits = 0;
+  if (threadIdx.x <= 2 * HB_MAX_NCR) s_cnt[threadIdx.x] = 0ull;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&wbar, w_bytes);
+    for (uint32_t off = 0; off < w_bytes; off += 32768u) {
+      const uint32_t nbytes = (w_bytes - off) < 32768u ? (w_bytes - off) : 32768u;
+      tma_load_1d(reinterpret_cast<char*>(Ws) + off, reinterpret_cast<const char*>(td.W) + off, nbytes, &wbar);
+    }
+  }
+
+  for (long long base = warp_id; base < p.n_local; base += n_warps) {
+    // ---------------- proposal (K1) ----------------
+    double xk[ITER], dxk[ITER], xp[ITER];
+    bool valid; long long jl; int id;
+    k1_chain_jump<32, ITER, TAPE>(p, base, lane, xk, dxk, valid, jl, id, errbits);   // one chain per warp: valid == true
+    double lp_part = 0.0;
+#pragma unroll
+    for (int m = 0; m < ITER; ++m) {
+      const int k = m * 32 + lane;
+      xp[m] = 0.0;
+      if (k < d) {
+        double v = __dadd_rn(xk[m], dxk[m]);                            // R/internals.R:206
+        if (!isfinite(v)) errbits |= HB_FLAG_PROP_NONFINITE;            // :209
+        if (p.bound) v = hb_bound_par(v, p.pmin[k], p.pmax[k], p.bound);   // :210-214
+        if (p.prior == 1) {                                             // dunif(log = TRUE), :57
+          const double a = p.pmin[k], b = p.pmax[k];
+          lp_part += (a <= v && v <= b) ? -log(b - a) : -INFINITY;
+        }
+        xp[m] = v;
+      }
+      xs[k] = xp[m];
+    }
+    if (p.prior == 1) lp_part = hb_group_sum<32>(lp_part);
+    double lpx = (p.prior == 1) ? lp_part : 0.0;                        // flat prior: 0  :55
+    if (!(lpx >= HB_FLOOR)) lpx = (lpx != lpx) ? lpx : HB_FLOOR;        // :65
+    if (!isfinite(lpx)) errbits |= HB_FLAG_LP_NONFINITE;                // :67
+    __syncwarp();
+
+    // ---------------- log-density (K2): dmvt, R/test_t_distribution.R:43 ----------------
+    double z[ITER];
+#pragma unroll
+    for (int m = 0; m < ITER; ++m) z[m] = 0.0;
+    mbar_wait(&wbar, 0);                                                // W has landed (returns at once after the first chain)
+#pragma unroll 4
+    for (int k = 0; k < d; ++k) {
+      const double xv = xs[k];
+      const double* wr = Ws + (size_t)k * td.ldw;
+#pragma unroll
+      for (int m = 0; m < ITER; ++m) {
+        const int n = m * 32 + lane;
+        if (n >= k && n < d) z[m] = fma(xv, wr[n], z[m]);
+      }
+    }
+    double rss = 0.0;
+#pragma unroll
+    for (int m = 0; m < ITER; ++m) if (m * 32 + lane < d) rss = fma(z[m], z[m], rss);
+    rss = hb_warp_sum(rss);
+    const double dens = td.konst - 0.5 * (td.df + (double)d) * log1p(rss / td.df);
+    __syncwarp();                                                       // xs is rewritten by the next chain
+
+    // ---------------- accept / update / store (K3, outside the adaptation period) ----------------
+    const long long j = q.chain0 + jl * q.stride;
+    const long long si = j - q.state0;
+    const long long gch = q.gchain0 + j;
+    int accf = 0;
+    double lln = 0, lpostx = 0, lpost_old = 0;
+    if (lane == 0) {
+      double llr = (td.lik == 1) ? log(dens) : dens;                    // calc_ll, R/internals.R:4-7
+      if (!(llr >= HB_FLOOR)) llr = (llr != llr) ? llr : HB_FLOOR;      // :19
+      if (!isfinite(llr)) errbits |= HB_FLAG_LL_NONFINITE;              // :21
+      lln = llr;
+      lpostx = lpx + lln;                                               // R/dream_parallel.R:291
+      lpost_old = q.lpost[si];
+      double u;
+      if (TAPE) u = q.u_accept[j];
+      else { const hb_phx ph(q.seed, (uint64_t)gch, q.gen); u = hb_u53(hb_pair64(ph.slot(HB_SLOT_ACCEPT), 0)); }
+      const double p_acc = fmin(fmax(-100.0, lpostx - lpost_old), 0.0); // R/internals.R:239
+      accf = p_acc > log(u);                                            // :241
+    }
+    accf = __shfl_sync(FULL, accf, 0);
+#pragma unroll
+    for (int m = 0; m < ITER; ++m) {
+      const int k = m * 32 + lane;
+      if (k < d) {
+        const double xn = accf ? xp[m] : xk[m];                         // R/dream_parallel.R:358
+        q.Xout[j * (long long)ldx + k] = xn;
+        if (q.hist_x) q.hist_x[si * (long long)d + k] = xn;             // chain[ind_out, 1:d, ] :388
+      }
+    }
+    if (lane == 0) {
+      double lp_c, ll_c, lpost_c;
+      if (accf) {
+        q.lp[si] = lpx; q.ll[si] = lln; q.lpost[si] = lpostx;           // :359-361
+        if (q.fx) q.fx[si] = dens;                                      // :362
+        lp_c = lpx; ll_c = lln; lpost_c = lpostx;
+      } else {
+        lpost_c = lpost_old;                                            // :365
+        lp_c = 0; ll_c = 0;
+        if (q.hist_l) { lp_c = q.lp[si]; ll_c = q.ll[si]; }
+      }
+      if (q.hist_l) { q.hist_l[si * 3 + 0] = lp_c; q.hist_l[si * 3 + 1] = ll_c; q.hist_l[si * 3 + 2] = lpost_c; }   // :389-391
+      if (q.hist_fx && q.fx) q.hist_fx[si] = q.fx[si];                  // :394
+      if (q.lpost_hist_row) q.lpost_hist_row[si] = lpost_c;
+      if (q.accept_rec) q.accept_rec[si] = (uint8_t)accf;
+      atomicAdd(&s_cnt[1 + id], 1ull);                                  // n_id  :368-369
+      if (accf) { atomicAdd(&s_cnt[0], 1ull); atomicAdd(&s_cnt[1 + HB_MAX_NCR + id], 1ull); }   // n_acc :374
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x <= 2 * HB_MAX_NCR) {
+    const unsigned long long v = s_cnt[threadIdx.x];
+    if (v) {
+      if (threadIdx.x == 0) atomicAdd(&q.ctrl->n_acc_gen, v);
+      else if (threadIdx.x <= HB_MAX_NCR) atomicAdd(&q.ctrl->n_id_gen[threadIdx.x - 1], v);
+      else atomicAdd(&q.ctrl->n_acc_id_gen[threadIdx.x - 1 - HB_MAX_NCR], v);
+    }
+  }
+  if (errbits) atomicOr(&q.ctrl->err, errbits);
+}
+
+template <int ITER>
+cudaError_t launch_fused(const hb_k1_params& p, const hb_k3_params& q, const hb_fused_tdist& td, bool tape, int sm_count,
+                         cudaStream_t st) {
+  const int threads = 256, warps = threads / 32;
+  long long blocks = (p.n_local + warps - 1) / warps;
+  const long long cap = (long long)sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  const size_t smem = ((size_t)p.d * td.ldw + (size_t)warps * ITER * 32) * sizeof(double);
+  if (smem > 220 * 1024 || (((size_t)p.d * td.ldw * 8) & 15)) return cudaErrorInvalidValue;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[tape]) {
+    cudaError_t e = tape ? cudaFuncSetAttribute(hb_fused_small_kernel<ITER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)
+                         : cudaFuncSetAttribute(hb_fused_small_kernel<ITER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set[tape] = true;
+  }
+  if (tape) hb_fused_small_kernel<ITER, true><<<(unsigned)blocks, threads, smem, st>>>(p, q, td);
+  else hb_fused_small_kernel<ITER, false><<<(unsigned)blocks, threads, smem, st>>>(p, q, td);
+  return cudaGetLastError();
+}
 
 // ------------------------------------------------------------------------------------------------------------------
 // Wide variants (d > 16): a warp owns a batch of 32 chains.
@@ -1001,4 +1190,18 @@ cudaError_t hb_launch_k1(const hb_k1_params& p, bool tape_mode, int sm_count, cu
   if (d <= 512) return launch_wide_pair<8>(p, sm_count, st);
   if (d <= 1024) return launch_wide_pair<16>(p, sm_count, st);
   return cudaErrorInvalidValue;
+}
+
+bool hb_fused_small_eligible(long long n_local, int d, int sm_count) {
+  return d > 16 && d <= 128 && !g_hb_force_wide && n_local < (long long)sm_count * 16 * 32 / 2;   // where hb_launch_k1 picks <32, ITER>
+}
+
+cudaError_t hb_launch_fused_small(const hb_k1_params& p, const hb_k3_params& q, const hb_fused_tdist& td, bool tape_mode,
+                                  int sm_count, cudaStream_t st) {
+  if (!hb_fused_small_eligible(p.n_local, p.d, sm_count) || p.past_sample || p.n_peers > 1 || q.adapt || q.n_runs > 1 ||
+      q.accept_in || q.lik22 || q.n_push > 0 || q.Xout == q.X)
+    return cudaErrorInvalidValue;
+  if (p.d <= 32) return launch_fused<1>(p, q, td, tape_mode, sm_count, st);
+  if (p.d <= 64) return launch_fused<2>(p, q, td, tape_mode, sm_count, st);
+  return launch_fused<4>(p, q, td, tape_mode, sm_count, st);
 }

@@ -57,6 +57,13 @@ struct hb_k1_params {
 };
 cudaError_t hb_launch_k1(const hb_k1_params& p, bool tape_mode, int sm_count, cudaStream_t st);
 
+struct hb_k3_params;
+// ---- fused generation for small populations (hb_k1_propose.cu): K1 + t-distribution density + K3 in one launch ----
+struct hb_fused_tdist { const double* W; int ldw; int lik; double konst, df; };   // W = chol(C)^-1, dense upper triangle [d][ldw]
+bool hb_fused_small_eligible(long long n_local, int d, int sm_count);
+cudaError_t hb_launch_fused_small(const hb_k1_params& p, const hb_k3_params& q, const hb_fused_tdist& td, bool tape_mode,
+                                  int sm_count, cudaStream_t st);
+
 // ---- MT-DREAM (mt > 1): candidate selection and multi-try acceptance, R/dream_parallel.R:295-341 -----------------
 struct hb_mt_params {
   int mt; long long n_local; int ldx;

@@ -20,6 +20,7 @@
 
 #include "../../include/hydrobayes_b200.h"
 #include "hb_common.cuh"
+#include "hb_kernels.h"
 
 namespace {
 
@@ -327,6 +328,19 @@ void tdist_destroy(void* ctx) {
   if (c) { cudaFree(c->W_dev); cudaFree(c->Wblk_dev); delete c; }
 }
 void tdist_work(void*, int d, double* flops, double* bytes) { *flops = (double)d * d + 3.0 * d; *bytes = 8.0 * d + 8; }
+
+}  // namespace
+
+// operands of the fused small-population kernel (hb_k1_propose.cu) when the handle's target is this plugin
+bool hb_tdist_fused_info(const hb_target_vtable* vt, void* ctx, hb_fused_tdist* out) {
+  if (!vt || !ctx || vt->launch != tdist_launch) return false;
+  const auto* c = (const tdist_ctx*)ctx;
+  if (c->force_fma) return false;                       // HB_TDIST_FORCE_FMA=1 is a cross-check of the stand-alone kernels
+  out->W = c->W_dev; out->ldw = c->ldw; out->lik = c->lik; out->konst = c->konst; out->df = c->df;
+  return true;
+}
+
+namespace {
 
 // =========================================== HydroModel ====================================================
 // a / b for a fixed divisor b with y = RN(1/b) precomputed by a true IEEE division: q0 = RN(a y), r = a - b q0

@@ -148,3 +148,40 @@ def test_random_configurations_device(hb, oracle, case):
     cfg_n = H.copy_cfg(cfg, record_accept=1)
     H.assert_run_parity(H.run_device(cfg_n, target, x0, **extra), oracle.run(cfg_n, target, x0, **extra), rtol=1e-9, atol=1e-12,
                         check_fx=(target != "HydroModel"))
+
+
+@pytest.mark.parametrize("bound", [A.HB_BOUND_NONE, A.HB_BOUND_BOUND, A.HB_BOUND_REFLECT, A.HB_BOUND_FOLD])
+@pytest.mark.parametrize("native", [False, True])
+@pytest.mark.parametrize("d", [20, 40, 100])
+def test_fused_small_population_generation(hb, oracle, monkeypatch, bound, native, d):
+    # EXPERIMENTAL path, opt-in with HB_FUSED=1: small populations outside the adaptation period run proposal + log-density +
+    # accept as ONE launch with a double-buffered population (hb_fused_small_kernel): parity with the oracle, and identical
+    # decisions to the default three-kernel path
+    nc, t = 37, 90
+    kw = {}
+    cfg = A.default_config(nc=nc, t=t, d=d, lik=2, seed=9 + d, adapt=0.2, thin=3, store_fx=1, record_accept=1,
+                           prior=A.HB_PRIOR_UNIFORM if bound else A.HB_PRIOR_FLAT, bound=bound)
+    if bound:
+        kw.update(par_min=list(-3.0 - 0.01 * np.arange(d)), par_max=list(4.0 + 0.02 * np.arange(d)))    # the box bites
+    x0 = 0.3 * H.x0_tdist(nc, d)
+    monkeypatch.setenv("HB_FUSED", "1")
+    if native:
+        ora = oracle.run(cfg, "t_distribution", x0, **kw)
+        dev = H.run_device(cfg, "t_distribution", x0, **kw)
+        H.assert_run_parity(dev, ora, rtol=1e-9, atol=1e-12)
+        cfg_t, tape_kw = cfg, {}
+    else:
+        rec = oracle.Tape.for_config(cfg)
+        assert oracle.run(cfg, "t_distribution", x0, record=rec, **kw)["rc"] == 0
+        cfg_t = H.copy_cfg(cfg, rng_mode=A.HB_RNG_TAPE)
+        ora = oracle.run(cfg_t, "t_distribution", x0, tape=rec, **kw)
+        dev = H.run_device(cfg_t, "t_distribution", x0, tape=rec, slice_generations=7, **kw)
+        H.assert_run_parity(dev, ora, rtol=1e-11)
+        tape_kw = dict(tape=rec)
+    assert 0.03 < ora["accept"].mean() < 0.9
+    monkeypatch.delenv("HB_FUSED")                                 # the same run through K1 / K2 / K3 (the default)
+    ref = H.run_device(cfg_t, "t_distribution", x0, **tape_kw, **kw)
+    assert np.array_equal(ref["accept"], dev["accept"])
+    np.testing.assert_allclose(dev["chain"], ref["chain"], rtol=1e-12, equal_nan=True)
+    np.testing.assert_array_equal(dev["AR"], ref["AR"])
+    assert dev["timing"][1] < ref["timing"][1] - (t - 1 - int(0.2 * t)) , "the fused path was not taken"
