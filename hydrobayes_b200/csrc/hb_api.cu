@@ -123,17 +123,6 @@ void sample_replacements(const hb_handle* h, long long gen, const std::vector<lo
   }
 }
 
-// stats::quantile type 7 on a sorted copy (recollection): (1-h)*x[lo] + h*x[hi]
-double quantile7_sorted(const std::vector<double>& s, double p) {
-  const long long n = (long long)s.size();
-  const double index = 1 + (double)(n > 1 ? n - 1 : 0) * p;
-  const double lo = floor(index), hi = ceil(index);
-  double qs = s[(size_t)lo - 1];
-  const double xh = s[(size_t)hi - 1];
-  if (index > lo && xh != qs) { const double hh = index - lo; qs = (1 - hh) * qs + hh * xh; }
-  return qs;
-}
-
 double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }

@@ -44,16 +44,16 @@ def r_sd(v):                                      # sd(): sqrt(var), two-pass wi
     return float(np.sqrt(np.sum((v - m) ** 2) / LD(n - 1)))
 
 
-def quantile7(x, p):                              # stats::quantile default type 7
+def quantile7(x, p):                              # stats::quantile, default type 7 (its own branch in quantile.default)
     x = np.sort(np.asarray(x, dtype=np.float64))
     n = x.size
-    h = (n - 1) * p
-    lo = math.floor(h + 4 * np.finfo(float).eps)
-    g = h - lo
-    if abs(g) < 4 * np.finfo(float).eps:
-        g = 0.0
-    hi = min(lo + 1, n - 1)
-    return x[lo] + g * (x[hi] - x[lo]) if g != 0.0 else x[lo]
+    index = 1 + max(n - 1, 0) * p                 # 1-based
+    lo, hi = math.floor(index), math.ceil(index)
+    qs = x[lo - 1]
+    if index > lo and x[hi - 1] != qs:
+        h = index - lo
+        qs = (1 - h) * qs + h * x[hi - 1]
+    return qs
 
 
 # ---- targets (R/test_mixture.R:16, R/test_t_distribution.R:19-46, R/test_HydroModel.R:17-36) ----------------------
