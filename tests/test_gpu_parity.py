@@ -190,8 +190,8 @@ def test_wide_kernels_native(hb, oracle, force_wide, d, nc):
     hb.lib().hb_test_force_wide(1)
     # the chain states and the decisions do not depend on the kernel variant, bit for bit; lp / ll / lpost agree to 1e-13
     # (identical today; the opt-in fused small-population kernel sums the quadratic form in a different order)
-    assert np.array_equal(dev["chain"][:, :d, :], narrow["chain"][:, :d, :]) and np.array_equal(dev["accept"], narrow["accept"])
-    np.testing.assert_allclose(dev["chain"][:, d:, :], narrow["chain"][:, d:, :], rtol=1e-13)
+    assert np.array_equal(dev["chain"][:, :d, :], narrow["chain"][:, :d, :], equal_nan=True) and np.array_equal(dev["accept"], narrow["accept"])
+    np.testing.assert_allclose(dev["chain"][:, d:, :], narrow["chain"][:, d:, :], rtol=1e-13, equal_nan=True)
 
 
 def test_wide_kernels_bounds_prior_and_zs(hb, oracle, force_wide):
