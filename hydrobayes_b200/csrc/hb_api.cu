@@ -908,7 +908,7 @@ int hb_set_target(hb_handle* h, const char* name, const double* data, const int6
   const int rc = vt->init(&ctx, h->d, h->cfg.lik, data, dims, ndims, h->obs_h.empty() ? nullptr : h->obs_h.data(),
                           (int64_t)h->obs_h.size(), h->cfg.glue_shape, err, (int)sizeof err);
   if (rc != HB_OK) return fail(h, rc, "%s", err[0] ? err : "target init failed");
-  h->vt = vt; h->tctx = ctx; h->target_name = name; h->target_is_hydro = (h->target_name == "HydroModel");
+  h->vt = vt; h->tctx = ctx; h->target_name = name; h->target_is_hydro = (h->target_name == "HydroModel" || h->target_name == "fun_wrap_glue");
   const int lik = h->cfg.lik;
   if (lik == 21 || lik == 22 || lik == 99) {   // the closures calc_ll would get() by name (R/internals.R:10,12,16)
     if (!h->target_is_hydro) return fail(h, HB_ERR_UNSUPPORTED, "lik = %d is a device epilogue of HydroModel only", lik);
@@ -1439,7 +1439,7 @@ int hb_logdensity(const char* name, int32_t lik, const double* data, const int64
   ok = ok && cudaMemcpy(ll_out, ll, (size_t)n * 8, cudaMemcpyDeviceToHost) == cudaSuccess;
   if (ok && fx_out) ok = cudaMemcpy(fx_out, fx, (size_t)n * 8, cudaMemcpyDeviceToHost) == cudaSuccess;
   unsigned dom = 0;
-  if (ok && strcmp(name, "HydroModel") == 0) dom = hb_hydro_poll_err(ctx);
+  if (ok && (strcmp(name, "HydroModel") == 0 || strcmp(name, "fun_wrap_glue") == 0)) dom = hb_hydro_poll_err(ctx);
   vt->destroy(ctx);
   cudaFree(xc); cudaFree(xr); cudaFree(ll); cudaFree(fx);
   if (!ok) { set_msg(err, errlen, rc ? "target launch failed" : cudaGetErrorString(cudaGetLastError())); return rc ? rc : HB_ERR_CUDA; }

@@ -640,6 +640,10 @@ std::vector<hb_target_vtable>& registry() {
       {"mixture", mixture_init, mixture_launch, mixture_destroy, mixture_work, nullptr},
       {"t_distribution", tdist_init, tdist_launch, tdist_destroy, tdist_work, nullptr},
       {"HydroModel", hydro_init, hydro_launch, hydro_destroy, hydro_work, hydro_launch_items},
+      // the wrapper of the reference's own example script, fun_wrap_glue(x, forc) = HydroModel(forcing = forc, param = x["K"])
+      // (examples/script_examples.R:495-501): registered under its name so that the example's dream(fun = "fun_wrap_glue",
+      // lik = 99 | 31, forc = ...) call resolves like abc_rho = "abc_distfun" and lik_fun = "fun_lik" do
+      {"fun_wrap_glue", hydro_init, hydro_launch, hydro_destroy, hydro_work, hydro_launch_items},
   };
   return r;
 }

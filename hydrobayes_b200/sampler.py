@@ -309,6 +309,10 @@ def prior_sample(par_info: dict, d: int, nc: int, rng: Optional[np.random.Genera
     return np.asarray(xt, float).reshape(-1, d)                        # :42-43
 
 
+# targets whose raw output is a whole series (m = T): fx[out_t, nc, m] is not kept on the device for them
+_SERIES_TARGETS = ("HydroModel", "fun_wrap_glue")
+
+
 def _make_config(sweep, lik, par_info, nc, t, d, burnin, adapt, updateInterval, delta, c_val, c_star, nCR, p_g, beta0,
                  thin, outlier_check, glue_shape, past_sample, m0, archive_update, psnooker, mt, checkConvergence,
                  seed, tape, record_accept, store_fx, default_prior) -> A.HbConfig:
@@ -344,7 +348,7 @@ def _drive(sweep, fun, extra, lik, par_info, nc, t, d, burnin, adapt, updateInte
     timea = time.time()
     cfg = _make_config(sweep, lik, par_info, nc, t, d, burnin, adapt, updateInterval, delta, c_val, c_star, nCR, p_g,
                        beta0, thin, outlier_check, glue_shape, past_sample, m0, archive_update, psnooker, mt,
-                       checkConvergence, seed, tape, record_accept, store_fx and fun != "HydroModel", default_prior)
+                       checkConvergence, seed, tape, record_accept, store_fx and fun not in _SERIES_TARGETS, default_prior)
     rng = np.random.default_rng(seed)
     n0 = (m0 if m0 is not None else 10 * d) if past_sample else nc
     rank, world = 0, 1
@@ -439,7 +443,8 @@ def dream_parallel(fun, *extra, lik=None, par_info=None, nc, t, d, burnin=0, ada
                    forcing=None, distributed=False, exchange=None):
     """DREAM, synchronous population sweep -- drop-in for HydroBayes::dream_parallel (R/dream_parallel.R:155-455).
 
-    ``fun`` is the name of a registered device target ("mixture", "t_distribution", "HydroModel").  ``ncores`` is
+    ``fun`` is the name of a registered device target ("mixture", "t_distribution", "HydroModel", or "fun_wrap_glue", the
+    HydroModel wrapper of the reference's example script).  ``ncores`` is
     accepted and ignored.  Chain indices in ``outlier`` are 0-based.
 
     ``distributed=True`` (one process per GPU, ``torch.distributed`` initialised): the population is block-partitioned

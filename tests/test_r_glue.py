@@ -89,6 +89,8 @@ def test_no_device_becomes_an_r_error(R):
         R.call("hbR_rstat_array", R.real(np.zeros(10)))
     assert R.to_numpy(R.call("hbR_target_registered", R.string("t_distribution")))[0] == 1
     assert R.to_numpy(R.call("hbR_target_registered", R.string("my_r_closure")))[0] == 0
+    # the wrapper name of the reference's example script resolves like the package's own targets (script_examples.R:495-501)
+    assert R.to_numpy(R.call("hbR_target_registered", R.string("fun_wrap_glue")))[0] == 1
 
 
 def _hb_drive(R, sweep, fun, dots, lik, par_info, nc, t, d, z, seed, adapt=0.1, updateInterval=10, obs=None, glue_shape=None,
