@@ -492,8 +492,10 @@ bool fused_available(hb_handle* h) {
   const hb_config& c = h->cfg;
   if (h->fused_state == 0) {
     h->fused_state = -1;
-    const char* e = getenv("HB_FUSED");
-    if ((e && e[0] == '1') && c.sweep == HB_SWEEP_SYNCHRONOUS && !h->modeb && c.mt <= 1 && h->world == 1 && !h->peer_mode &&
+    const char* e = getenv("HB_FUSED");                        // "1" on, "0" off, unset: kFusedDefault
+    constexpr bool kFusedDefault = false;
+    const bool want = e ? (e[0] == '1') : kFusedDefault;
+    if (want && c.sweep == HB_SWEEP_SYNCHRONOUS && !h->modeb && c.mt <= 1 && h->world == 1 && !h->peer_mode &&
         !h->delta_mode && !c.past_sample && c.lik == 2 && c.prior != HB_PRIOR_NORMAL && h->X &&
         hb_tdist_fused_info(h->vt, h->tctx, &h->fused_td)) {
       if (cudaMalloc((void**)&h->Xalt, (size_t)h->nc * h->ldx * sizeof(double)) == cudaSuccess &&

@@ -179,7 +179,7 @@ def test_fused_small_population_generation(hb, oracle, monkeypatch, bound, nativ
         H.assert_run_parity(dev, ora, rtol=1e-11)
         tape_kw = dict(tape=rec)
     assert 0.03 < ora["accept"].mean() < 0.9
-    monkeypatch.delenv("HB_FUSED")                                 # the same run through K1 / K2 / K3 (the default)
+    monkeypatch.setenv("HB_FUSED", "0")                            # the same run through K1 / K2 / K3 (the default)
     ref = H.run_device(cfg_t, "t_distribution", x0, **tape_kw, **kw)
     assert np.array_equal(ref["accept"], dev["accept"])
     np.testing.assert_allclose(dev["chain"], ref["chain"], rtol=1e-12, equal_nan=True)
