@@ -95,3 +95,48 @@ def test_outlier_list_structure():
     assert len(lst) == 10 and lst[0] is None and lst[9].tolist() == [3, 7]
     cfg = A.default_config(nc=10, t=100, d=1, lik=1, outlier_check=0)
     assert _outlier_list([], cfg, A.HB_SWEEP_SYNCHRONOUS) == [None]
+
+
+def test_header_is_plain_c_and_a_c_consumer_links(tmp_path):
+    # the boundary is a C ABI: the public headers must compile as C99 and as C++ on their own, and a plain C program (what
+    # the R glue, cgo or JNI would be) links against the shared library with nothing but -lhydrobayes_b200
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    for hdr, cxx in (("hydrobayes_b200.h", "c++11"), ("hydrobayes_b200_rng.h", "c++17")):   # the draw spec uses hex float literals
+        subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", os.path.join(inc, hdr)], check=True)
+        subprocess.run(["g++", "-std=" + cxx, "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", os.path.join(inc, hdr)], check=True)
+    src = tmp_path / "consumer.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "hydrobayes_b200.h"
+int main(void) {
+  hb_config c;
+  hb_config_default(&c);
+  if (c.abi_version != HB_ABI_VERSION || c.delta != 3 || c.nCR != 3 || c.update_interval != 10 || c.thin != 1) return 10;
+  c.nc = 8; c.t = 10; c.d = 2; c.lik = 2;
+  hb_handle* h = NULL;
+  int rc = hb_create(&c, 0, &h);
+  if (hb_device_count() == 0) {                 /* no CUDA device: must fail loudly, there is no CPU path */
+    if (rc != HB_ERR_NO_DEVICE || h != NULL) return 11;
+    if (!strstr(hb_last_error(NULL), "no CPU fallback")) return 12;
+  } else {
+    if (rc != HB_OK || h == NULL) return 13;
+    hb_destroy(h);
+    hb_wait_idle();
+  }
+  c.nc = 6;                                     /* nc <= 2 * delta: the reference's stop() wording (R/dream.R:136-137) */
+  rc = hb_create(&c, 0, &h);
+  if (rc != HB_ERR_INVALID || !strstr(hb_last_error(NULL), "'nc' must be > 'delta' * 2")) return 14;
+  printf("targets: %d %d %d %d\n", hb_target_registered("mixture"), hb_target_registered("t_distribution"),
+         hb_target_registered("HydroModel"), hb_target_registered("no_such_closure"));
+  return 0;
+}
+''')
+    exe = tmp_path / "consumer"
+    libdir = os.path.join(ROOT, "hydrobayes_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I" + inc, str(src), "-o", str(exe), "-L" + libdir, "-lhydrobayes_b200",
+                    "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert r.stdout.strip() == "targets: 1 1 1 0"
