@@ -28,7 +28,7 @@ int hb_hydro_init_batched(void** ctx, int d, int lik, const double* data, int64_
 
 namespace {
 
-std::string g_create_err;
+thread_local std::string g_create_err;   // last hb_create failure of the calling thread (hb_last_error(NULL))
 
 int fail(hb_handle* h, int code, const char* fmt, ...) {
   char buf[512];
