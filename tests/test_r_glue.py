@@ -56,18 +56,22 @@ def test_r_formals_match_the_reference_signature():
     src = _r_sources()
     want_par = ["fun", "...", "lik", "par.info", "nc", "t", "d", "burnin", "adapt", "updateInterval", "delta", "c_val", "c_star",
                 "nCR", "p_g", "beta0", "thin", "outlier_check", "obs", "abc_rho", "abc_e", "glue_shape", "lik_fun"]
-    tails = {"dream_parallel.R": ["past_sample", "m0", "archive_update", "psnooker", "mt", "ncores", "checkConvergence", "verbose",
-                                  "seed", "device"],
-             "dream.R": ["checkConvergence", "verbose", "seed", "device"]}
-    for f, tail in tails.items():
-        head = src[f][src[f].index("function(") + 9: src[f].index(") {")]
+    tails = {"dream_parallel": ["past_sample", "m0", "archive_update", "psnooker", "mt", "ncores", "checkConvergence", "verbose",
+                                "seed", "device"],
+             "dream": ["checkConvergence", "verbose", "seed", "device"]}
+    text = src["hb_entry_points.R"]
+    heads = {}
+    for fn, tail in tails.items():
+        start = text.index(fn + " <- function(") + len(fn + " <- function(")
+        head = text[start: text.index(") {", start)]
+        heads[fn] = head
         head = re.sub(r"list\([^)]*\)", "LIST", head)
         names = [a.split("=")[0].strip() for a in head.split(",")]
-        assert names == want_par + tail, (f, names)
-    assert 'prior = "flat"' in src["dream_parallel.R"] and 'prior = "uniform"' in src["dream.R"]
+        assert names == want_par + tail, (fn, names)
+    assert 'prior = "flat"' in heads["dream_parallel"] and 'prior = "uniform"' in heads["dream"]
     for frag in ["burnin = 0", "adapt = 0.1", "updateInterval = 10", "delta = 3", "c_val = 0.1", "c_star = 1e-12", "nCR = 3",
                  "p_g = 0.2", "beta0 = 1", "thin = 1", "outlier_check = TRUE"]:
-        assert frag in src["dream_parallel.R"] and frag in src["dream.R"], frag
+        assert frag in heads["dream_parallel"] and frag in heads["dream"], frag
 
 
 def test_dotcall_checks_symbol_and_arity_like_r(R):
