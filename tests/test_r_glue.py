@@ -179,3 +179,38 @@ def test_dotcall_hydromodel_with_bounds_and_library_errors(R):
     with pytest.raises(rmock.RError, match="my_r_closure"):
         R.call("hbR_set_target", h, R.string("my_r_closure"), R.nil)
     R.call("hbR_destroy", h)
+
+
+def test_r_sources_are_lexically_balanced():
+    # no R parser here: at least every bracket of the R drivers closes (strings and comments skipped), the files end at
+    # top level, and every function the drivers call is either base R, the reference's own (kept) internals, or defined here
+    for f, text in _r_sources().items():
+        stack, i, n = [], 0, len(text)
+        pairs = {")": "(", "]": "[", "}": "{"}
+        while i < n:
+            ch = text[i]
+            if ch == "#":
+                while i < n and text[i] != "\n":
+                    i += 1
+                continue
+            if ch in "\"'":
+                q = ch; i += 1
+                while i < n and text[i] != q:
+                    i += 2 if text[i] == "\\" else 1
+            elif ch in "([{":
+                stack.append((ch, text.count("\n", 0, i) + 1))
+            elif ch in ")]}":
+                assert stack and stack[-1][0] == pairs[ch], f"{f}: unbalanced {ch!r} at line {text.count(chr(10), 0, i) + 1}"
+                stack.pop()
+            i += 1
+        assert not stack, f"{f}: unclosed {stack[-1][0]!r} opened at line {stack[-1][1]}"
+    text = "\n".join(_r_sources().values())
+    defined = set(re.findall(r"^([.\w]+) <- function\(", text, flags=re.M))
+    assert {"dream", "dream_parallel", "R_stat", ".hb_drive"} <= defined
+    called = set(re.findall(r"(?<![\w.$])([.A-Za-z][\w.]*)\(", re.sub(r"#.*", "", text)))
+    known = defined | {"function", "list", "c", "if", "for", "while", "stop", "match", "is.na", "is.null", "is.character", "as.integer",
+                       "as.numeric", "as.matrix", "array", "matrix", "paste0", "dimnames", "colnames", "length", "floor", "max",
+                       "seq_len", "invisible", "on.exit", "Sys.time", "sample.int", "txtProgressBar", "setTxtProgressBar", "close",
+                       "prior_sample"}      # prior_sample: the reference's own R/internals.R:26-47, kept
+    unknown = {c for c in called if c not in known and not c.startswith(".Call")}
+    assert not unknown, f"R drivers call functions that are neither base R nor defined in the package: {sorted(unknown)}"
