@@ -122,7 +122,7 @@ typedef struct { int d; double* R; double konst; } tdist_t;
 static int tdist_setup(tdist_t* td, int d) {
   const double df = 60;
   td->d = d;
-  double* C = (double*)malloc(sizeof(double) * (size_t)d * d);
+  double* C = (double*)calloc((size_t)d * d, sizeof(double));
   td->R = (double*)malloc(sizeof(double) * (size_t)d * d);
   for (int i = 1; i <= d; ++i)
     for (int j = 1; j <= d; ++j) {
@@ -797,7 +797,7 @@ int hbo_run(const hb_config* cfg, const hbo_target* tgt, const double* par_min, 
   if (cfg->prior == HB_PRIOR_NORMAL) {
     if (!prior_mu || !prior_cov) { snprintf(io->err, sizeof io->err, "normal prior needs mu and cov"); return HB_ERR_INVALID; }
     c.prior_R = (double*)malloc(sizeof(double) * (size_t)d * d);
-    double* Cm = (double*)malloc(sizeof(double) * (size_t)d * d);
+    double* Cm = (double*)calloc((size_t)d * d, sizeof(double));
     for (int i = 0; i < d; ++i) for (int j = 0; j < d; ++j) Cm[i * d + j] = prior_cov[i + d * j];
     int ch = chol_upper(Cm, d, c.prior_R);
     free(Cm);
