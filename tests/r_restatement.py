@@ -150,7 +150,7 @@ def prior_pdf(x, par_info, lik):
 
 def check_outlier(dens, x, N, draw_new_states):
     """dens [w, N] (rows ceiling(i/2)..i of lpost); returns (x, last row of dens, outliers 0-based ascending)."""
-    proxy = np.array([r_mean(dens[:, c]) for c in range(N)])                 # colMeans
+    proxy = np.array([float(np.sum(dens[:, c].astype(LD)) / LD(dens.shape[0])) for c in range(N)])   # colMeans: long double sum / n, no second pass
     q1, q3 = quantile7(proxy, 0.25), quantile7(proxy, 0.75)
     iqr = abs(q3 - q1)
     outliers = np.nonzero(proxy < q1 - 2 * iqr)[0]
