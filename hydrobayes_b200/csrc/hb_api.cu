@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
 #include <mutex>
 #include <atomic>
 #include <chrono>
@@ -167,14 +168,14 @@ void pin_release(hb_handle* h) {
 }
 
 struct prof_scope {
-  hb_handle* h; const char* name; cudaEvent_t a = nullptr, b = nullptr;
-  prof_scope(hb_handle* h_, const char* n) : h(h_), name(n) {
-    if (h->profile) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, h->stream); }
+  hb_handle* h; const char* name; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+  prof_scope(hb_handle* h_, const char* n, cudaStream_t st_ = nullptr) : h(h_), name(n), st(st_ ? st_ : h_->stream) {
+    if (h->profile) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
   }
   void done(int launches = 1) {
     h->launches += launches;
     if (h->profile) {
-      cudaEventRecord(b, h->stream); cudaEventSynchronize(b);
+      cudaEventRecord(b, st); cudaEventSynchronize(b);
       float ms = 0; cudaEventElapsedTime(&ms, a, b);
       auto& k = h->kstats[name]; k.ms += ms; k.launches += launches;
       cudaEventDestroy(a); cudaEventDestroy(b);
@@ -215,14 +216,49 @@ int allocate(hb_handle* h) {
     CK(cudaMemsetAsync(h->X, 0, (size_t)nc * ldx * sizeof(double), h->stream));
   }
   if (c.past_sample) { CK(dalloc(&h->Z, (size_t)h->m_cap * ldx)); }
-  if (h->delta_mode) {   // arena mapped by the peers: barrier flags, all-reduce slots, all-gather area (no NCCL on this path)
-    h->arena_red_off = 256;
-    h->arena_red_bytes = (((size_t)(2 + c.nCR) * d + HB_MAX_NCR + 1) * 8 + 255) & ~(size_t)255;
-    h->arena_gather_off = h->arena_red_off + 2 * h->arena_red_bytes;
-    const size_t bytes = h->arena_gather_off + 2 * (size_t)nl * sizeof(double);
+  h->wide = g_hb_force_wide || nl >= (long long)h->sm_count * 16 * 32 / 2;   // the threshold of hb_launch_k1 / hb_launch_k3
+  h->pieces = 1; h->piece_n = nl;
+  if (h->delta_mode) {
+    // pieces per generation: the send of piece p overlaps the kernels of piece p + 1, so only the last piece's transfer is
+    // exposed; a piece must still fill the device (>= 16 384 chains).  HB_PIECES overrides (tests run tiny populations).
+    int P = 1;
+    if (h->wide) { P = 4; while (P > 1 && nl / P < 16384) P >>= 1; }
+    if (const char* e = getenv("HB_PIECES")) { const int v = atoi(e); if (v >= 1 && v <= HB_MAX_PIECES) P = v; }
+    if ((long long)P > nl) P = (int)nl;
+    h->pieces = P;
+    h->piece_n = (nl + P - 1) / P;
+    if (P > 1) h->piece_n = (h->piece_n + 31) & ~31LL;
+    // the send kernel (256 threads, <= 64 registers) runs next to the persistent proposal grid: the proposal kernel leaves
+    // `reserve_ctas` of its 2-per-SM CTA slots free, each of which hosts two send CTAs
+    h->send_ctas = 32;
+    if (const char* e = getenv("HB_SEND_CTAS")) { const int v = atoi(e); if (v >= 1 && v <= 1024) h->send_ctas = v; }
+    h->reserve_ctas = h->wide ? (h->send_ctas + 1) / 2 : 0;
+    // arena mapped by the peers: flags, error slots, all-reduce slots, all-gather area, delta boxes (no NCCL on this path)
+    const size_t E = (size_t)(2 + c.nCR) * d;
+    h->arena_red_bytes = ((E * (size_t)c.update_interval + HB_MAX_NCR + 1 + 3 * (size_t)d) * 8 + 255) & ~(size_t)255;
+    h->arena_gather_off = HB_ARENA_RED_OFF + 2 * h->arena_red_bytes;
+    h->arena_box_off = (h->arena_gather_off + 2 * (size_t)nl * sizeof(double) + 255) & ~(size_t)255;
+    const long long cap = h->piece_n * P;                                       // log slots per box
+    h->box_idx_off = 256;                                                       // counts[HB_MAX_PIECES] live in the first 64 bytes
+    h->box_rows_off = (h->box_idx_off + (size_t)cap * 4 + 255) & ~(size_t)255;
+    h->box_bytes = (h->box_rows_off + (size_t)cap * ldx * 8 + 255) & ~(size_t)255;
+    const size_t bytes = h->arena_box_off + 2 * (size_t)h->world * h->box_bytes;
     CK(cudaMalloc((void**)&h->arena, bytes));
-    CK(cudaMemsetAsync(h->arena, 0, bytes, h->stream));
-    h->flags = reinterpret_cast<unsigned*>(h->arena);
+    CK(cudaMemsetAsync(h->arena, 0, h->arena_box_off, h->stream));
+    for (int b = 0; b < 2 * h->world; ++b) CK(cudaMemsetAsync(h->arena + h->arena_box_off + (size_t)b * h->box_bytes, 0, 256, h->stream));
+    h->arena_peer[h->rank] = h->arena;
+    CK(dalloc(&h->log_ctr, (size_t)3 * HB_MAX_PIECES));
+    CK(cudaMemsetAsync(h->log_ctr, 0, sizeof(unsigned) * 3 * HB_MAX_PIECES, h->stream));
+    CK(dalloc(&h->ibuf, E * (size_t)c.update_interval));
+    if (!h->side) {
+      int lo = 0, hi = 0;
+      CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CK(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi));
+    }
+    for (int q = 0; q < P; ++q) CK(cudaEventCreateWithFlags(&h->ev_piece[q], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_sent, cudaEventDisableTiming));
+  } else if (h->world > 1) {
+    CK(dalloc(&h->errbits_dev, 16));
   }
   const size_t mtn = (size_t)(c.mt > 1 ? c.mt : 1) * (size_t)nl;   // MT-DREAM: mt proposal sets live side by side, try-major
   CK(dalloc(&h->XP, mtn * ldx));
@@ -245,9 +281,11 @@ int allocate(hb_handle* h) {
   CK(dalloc(&h->ctrl, (size_t)h->cfg.n_runs));
   CK(dalloc(&h->shift, (size_t)d)); CK(dalloc(&h->colsum, (size_t)2 * d)); CK(dalloc(&h->qsum, (size_t)c.nCR * d));
   size_t smem = 0;
-  h->k3_blocks = hb_k3_grid(nl, d, c.nCR, h->sm_count, &smem);
-  if (h->k3_blocks < 1) return fail(h, HB_ERR_UNSUPPORTED, "d = %d with nCR = %d exceeds the shared-memory budget of K3", d, c.nCR);
+  h->k3_blocks_piece = hb_k3_grid(h->piece_n, d, c.nCR, h->sm_count, h->wide ? 1 : 0, &smem);
+  if (h->k3_blocks_piece < 1) return fail(h, HB_ERR_UNSUPPORTED, "d = %d with nCR = %d exceeds the shared-memory budget of K3", d, c.nCR);
+  h->k3_blocks = h->k3_blocks_piece * h->pieces;        // rows the finalize kernel reduces (rows a short last piece leaves unwritten stay 0)
   CK(dalloc(&h->partials, (size_t)h->k3_blocks * (c.nCR + 2) * d));
+  CK(cudaMemsetAsync(h->partials, 0, sizeof(double) * (size_t)h->k3_blocks * (c.nCR + 2) * d, h->stream));
   const long long nr = h->cfg.n_runs;
   CK(dalloc(&h->out_ar, (size_t)nr * h->ar_rows * h->ar_cols)); CK(dalloc(&h->out_cr, (size_t)nr * h->cr_rows * h->cr_cols));
   CK(hb_launch_fill(h->out_ar, nr * h->ar_rows * h->ar_cols, NAN, h->stream));
@@ -311,31 +349,93 @@ int initialise(hb_handle* h) {
   CK(cudaMemcpyAsync(h->out_cr, cr.data(), cr.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->gen = 1; h->ind_out = 1; h->initialised = true;
-  return check_flags(h);
+  // sharded population: a failure of this rank's initial evaluation is reported at the end of the slice, after the error
+  // masks were OR-ed over the ranks -- returning here would leave the peers waiting at their first barrier
+  return h->world > 1 ? HB_OK : check_flags(h);
 }
 
-// check_outlier (R/internals.R:71-87) at generation i: proxies and copies on the device, order statistics and the
-// without-replacement draw on the host (runs at most adapt*t/updateInterval times per run)
-int outlier_check(hb_handle* h, long long i) {
+// One generation is built as a PROGRAM: a list of stages, each a list of host steps that enqueue device work.  A stage
+// boundary (cut) sits wherever the next step waits for something the PEERS signal (a delta piece flag, the flag of a small
+// collective).  Real ranks simply run all stages in order.  A rank emulation on one device (hb_group_run) runs stage s of
+// every rank before stage s + 1 of any rank, on one stream, so every signal is enqueued before the wait that needs it and
+// no kernel ever spins on another kernel of the same device.
+struct gen_prog {
+  std::vector<std::vector<std::function<int()>>> stages;
+  gen_prog() { stages.emplace_back(); }
+  void then(std::function<int()> f) { stages.back().push_back(std::move(f)); }
+  void cut() { stages.emplace_back(); }
+};
+
+hb_arena_peers arena_peers(const hb_handle* h) {
+  hb_arena_peers ap; for (int r = 0; r < 8; ++r) ap.p[r] = h->arena_peer[r];
+  return ap;
+}
+
+// sum `n` doubles over the ranks, in place (HB_EXCHANGE_DELTA: peer-memory all-reduce in rank order; else NCCL)
+int allreduce_post(hb_handle* h, hb_peer_reduce_desc rd) {
+  const size_t need = ((size_t)rd.n_f64[0] + rd.n_f64[1] + rd.n_u64) * 8;
+  if (need > h->arena_red_bytes) return fail(h, HB_ERR_UNSUPPORTED, "all-reduce of %zu bytes exceeds the arena slot", need);
+  ++h->red_seq;
+  CK(hb_launch_peer_allreduce_post(arena_peers(h), HB_ARENA_RED_OFF + (size_t)(h->red_seq & 1u) * h->arena_red_bytes, rd, h->rank,
+                                   h->world, h->red_seq, h->stream));
+  h->launches++;
+  return HB_OK;
+}
+int allreduce_finish(hb_handle* h, hb_peer_reduce_desc rd) {
+  CK(hb_launch_peer_allreduce_finish(arena_peers(h), HB_ARENA_RED_OFF + (size_t)(h->red_seq & 1u) * h->arena_red_bytes, rd, h->rank,
+                                     h->world, h->red_seq, &h->ctrl->err, h->stream));
+  h->launches++;
+  return HB_OK;
+}
+// appended to a program: buf[0..n) summed over the ranks (no-op on one GPU)
+void prog_allreduce_f64(hb_handle* h, gen_prog& g, double* buf, int n) {
+  if (h->world <= 1) return;
+  if (h->delta_mode) {
+    hb_peer_reduce_desc rd{};
+    rd.f64[0] = buf; rd.n_f64[0] = n; rd.f64[1] = buf; rd.n_f64[1] = 0; rd.u64 = nullptr; rd.n_u64 = 0;
+    g.then([=]() -> int { return allreduce_post(h, rd); });
+    g.cut();
+    g.then([=]() -> int { return allreduce_finish(h, rd); });
+  } else {
+    g.then([=]() -> int { return hb_nccl_allreduce_f64(h->comm, buf, (size_t)n, h->stream, h->err); });
+  }
+}
+
+// R_stat(chain[1:t_rows, 1:d, ]) of the whole population into out_dev[d]; on several GPUs the per-chain statistics of
+// the shards are combined with two small all-reduces (sums, then squared deviations from the global mean)
+void prog_rstat_population(hb_handle* h, gen_prog& g, long long t_rows, double* out_dev) {
+  const long long nl = h->n_local; const int d = h->d;
+  if (h->world <= 1) {
+    g.then([=]() -> int { CK(hb_launch_rstat(h->hist_x, t_rows, nl, 0, nl, d, h->rstat_xm, h->rstat_ss, out_dev, h->stream)); h->launches += 2; return HB_OK; });
+    return;
+  }
+  g.then([=]() -> int {
+    if (!h->rstat_sums) CK(dalloc(&h->rstat_sums, (size_t)3 * d));
+    CK(hb_launch_rstat_shard_pass1(h->hist_x, t_rows, nl, d, h->rstat_xm, h->rstat_ss, h->rstat_sums, h->stream));
+    h->launches++;
+    return HB_OK;
+  });
+  // rstat_sums is allocated by the first step; the all-reduce steps read the pointer when they run
+  if (h->delta_mode) {
+    g.then([=]() -> int { hb_peer_reduce_desc rd{}; rd.f64[0] = h->rstat_sums; rd.n_f64[0] = 2 * d; rd.f64[1] = h->rstat_sums; return allreduce_post(h, rd); });
+    g.cut();
+    g.then([=]() -> int { hb_peer_reduce_desc rd{}; rd.f64[0] = h->rstat_sums; rd.n_f64[0] = 2 * d; rd.f64[1] = h->rstat_sums; return allreduce_finish(h, rd); });
+  } else g.then([=]() -> int { return hb_nccl_allreduce_f64(h->comm, h->rstat_sums, (size_t)2 * d, h->stream, h->err); });
+  g.then([=]() -> int { CK(hb_launch_rstat_shard_dev(h->rstat_xm, nl, d, h->nc, h->rstat_sums, h->rstat_sums + 2 * d, h->stream)); h->launches++; return HB_OK; });
+  if (h->delta_mode) {
+    g.then([=]() -> int { hb_peer_reduce_desc rd{}; rd.f64[0] = h->rstat_sums + 2 * d; rd.n_f64[0] = d; rd.f64[1] = h->rstat_sums; return allreduce_post(h, rd); });
+    g.cut();
+    g.then([=]() -> int { hb_peer_reduce_desc rd{}; rd.f64[0] = h->rstat_sums + 2 * d; rd.n_f64[0] = d; rd.f64[1] = h->rstat_sums; return allreduce_finish(h, rd); });
+  } else g.then([=]() -> int { return hb_nccl_allreduce_f64(h->comm, h->rstat_sums + 2 * d, (size_t)d, h->stream, h->err); });
+  g.then([=]() -> int { CK(hb_launch_rstat_shard_final(h->rstat_sums, h->rstat_sums + 2 * d, t_rows, h->nc, d, out_dev, h->stream)); h->launches++; return HB_OK; });
+}
+
+// check_outlier (R/internals.R:71-87) at generation i: proxies, order statistics, the outlier list and the row copies on
+// the device; only the without-replacement draw of the replacement chains runs on the host (it runs at most
+// adapt*t/updateInterval times per run)
+int outlier_select_and_reset(hb_handle* h, long long i) {
   const long long nc = h->nc, nl = h->n_local;
-  const long long r0 = (i + 1) / 2;   // ceiling(i/2), 1-based
-  {
-    prof_scope ps(h, "OUTLIER");
-    CK(hb_launch_proxy(h->lpost_hist, nl, r0 - 1, i - 1, nl, h->proxy, h->stream));
-    ps.done();
-  }
-  const double* proxy_all = h->proxy;
-  if (h->world > 1 && h->delta_mode) {
-    hb_arena_peers ap; for (int r = 0; r < 8; ++r) ap.p[r] = h->arena_peer[r];
-    CK(hb_launch_peer_allgather(ap, h->arena_gather_off, h->proxy, h->lpost, h->proxy_full, h->lpost_full, nl, h->rank, h->world,
-                                ++h->gather_seq, &h->ctrl->err, h->stream));
-    h->launches += 2;
-    proxy_all = h->proxy_full;
-  } else if (h->world > 1) {
-    if (int rc = hb_nccl_allgather_f64(h->comm, h->proxy, h->proxy_full, (size_t)nl, h->stream, h->err)) return rc;
-    if (int rc = hb_nccl_allgather_f64(h->comm, h->lpost, h->lpost_full, (size_t)nl, h->stream, h->err)) return rc;
-    proxy_all = h->proxy_full;
-  }
+  const double* proxy_all = h->world > 1 ? h->proxy_full : h->proxy;
   {  // quartiles, threshold and the ascending outlier list on the device (R/internals.R:75-78)
     prof_scope ps(h, "OUTLIER");
     CK(hb_outlier_device(proxy_all, nc, h->outl_tmp, h->outl_tmp_bytes, h->outl_sorted, h->outl_thr, h->outl_dev,
@@ -384,6 +484,37 @@ int outlier_check(hb_handle* h, long long i) {
   return HB_OK;
 }
 
+void prog_outlier_check(hb_handle* h, gen_prog& g, long long i) {
+  const long long nl = h->n_local;
+  const long long r0 = (i + 1) / 2;   // ceiling(i/2), 1-based
+  g.then([=]() -> int {
+    prof_scope ps(h, "OUTLIER");
+    CK(hb_launch_proxy(h->lpost_hist, nl, r0 - 1, i - 1, nl, h->proxy, h->stream));
+    ps.done();
+    return HB_OK;
+  });
+  if (h->world > 1 && h->delta_mode) {
+    g.then([=]() -> int {
+      CK(hb_launch_peer_allgather_post(arena_peers(h), h->arena_gather_off, h->proxy, h->lpost, nl, h->rank, h->world, ++h->gather_seq, h->stream));
+      h->launches++;
+      return HB_OK;
+    });
+    g.cut();
+    g.then([=]() -> int {
+      CK(hb_launch_peer_allgather_finish(arena_peers(h), h->arena_gather_off, h->proxy_full, h->lpost_full, nl, h->rank, h->world,
+                                         h->gather_seq, &h->ctrl->err, h->stream));
+      h->launches++;
+      return HB_OK;
+    });
+  } else if (h->world > 1) {
+    g.then([=]() -> int {
+      if (int rc = hb_nccl_allgather_f64(h->comm, h->proxy, h->proxy_full, (size_t)nl, h->stream, h->err)) return rc;
+      return hb_nccl_allgather_f64(h->comm, h->lpost, h->lpost_full, (size_t)nl, h->stream, h->err);
+    });
+  }
+  g.then([=]() -> int { return outlier_select_and_reset(h, i); });
+}
+
 }  // namespace
 
 // K1 / K3 parameter blocks for a launch over items i -> chain first + i*stride (see hb_k1_params)
@@ -400,6 +531,7 @@ hb_k1_params hb_make_k1(hb_handle* h, long long i, long long first, long long st
   p.seed = c.seed; p.gen = (uint32_t)i; p.tape = h->tape; p.tape_g = i - 2; p.gamma_tab = h->gamma_tab;
   p.n_peers = h->peer_mode ? h->world : 1; p.peer_nl = h->n_local;
   for (int r = 0; r < 8; ++r) p.peer[r] = h->peer_mode ? h->peer_ptr[h->cur][r] : nullptr;
+  p.force_wide = (h->delta_mode && h->wide) ? 1 : 0; p.batch = 32; p.reserve_ctas = 0;
   hb_philox_key_schedule(c.seed, p.ks);
   for (int q = 0; q < c.nCR; ++q) p.thr16[q] = hb_rng_zt_threshold16((double)(q + 1) / (double)c.nCR);
   return p;
@@ -424,24 +556,25 @@ hb_k3_params hb_make_k3(hb_handle* h, long long i, long long first, long long st
   p.ctrl = h->ctrl; p.shift = h->shift; p.partials = h->partials;
   p.chain0 = first; p.stride = stride; p.n_local = n_items; p.nc = h->nc; p.n_runs = h->cfg.n_runs;
   p.state0 = h->chain0; p.gchain0 = (long long)c.run_offset * h->nc;
-  if (h->delta_mode) { p.n_push = h->world; for (int r = 0; r < 8; ++r) p.push[r] = h->peerX[r]; }
+  p.force_wide = (h->delta_mode && h->wide) ? 1 : 0;
   p.d = d; p.ldx = h->ldx; p.nCR = c.nCR;
   p.adapt = in_adapt; p.write_dx = write_dx; p.lik22 = (c.lik == 22); p.seed = c.seed; p.gen = (uint32_t)i;
   p.u_accept = (c.rng_mode == HB_RNG_TAPE) ? h->tape.u_accept + (size_t)(i - 2) * h->tape.nct : nullptr;
   return p;
 }
 
-int hb_target_launch(hb_handle* h, const double* x, long long n, long long first, long long stride) {
+// `off`: the launch covers proposals XP[off ...] of the shard (one piece); ll_raw / fx_xp are written at the same offset
+int hb_target_launch(hb_handle* h, const double* x, long long n, long long first, long long stride, long long off) {
   if (h->vt->launch_items && h->cfg.n_runs > 1)
-    return h->vt->launch_items(h->tctx, x, n, h->d, h->ldx, h->ll_raw, h->fx_xp, first, stride, h->nc, h->stream);
-  return h->vt->launch(h->tctx, x, n, h->d, h->ldx, h->ll_raw, h->fx_xp, h->stream);
+    return h->vt->launch_items(h->tctx, x, n, h->d, h->ldx, h->ll_raw + off, h->fx_xp + off, first, stride, h->nc, h->stream);
+  return h->vt->launch(h->tctx, x, n, h->d, h->ldx, h->ll_raw + off, h->fx_xp + off, h->stream);
 }
 
 // prior = "normal": the proposal kernel leaves lp_xp = 0; the quadratic form runs as its own launch over XP
-int hb_prior_after_k1(hb_handle* h, long long n_items) {
+int hb_prior_after_k1(hb_handle* h, long long n_items, long long off) {
   if (h->cfg.prior != HB_PRIOR_NORMAL || h->cfg.lik == 22) return HB_OK;
-  if (cudaError_t e = hb_launch_prior_normal(h->XP, h->ldx, h->d, n_items, h->prior_W, h->prior_mu, h->prior_const, h->lp_xp,
-                                             &h->ctrl->err, h->stream); e != cudaSuccess) { h->err = cudaGetErrorString(e); return HB_ERR_CUDA; }
+  if (cudaError_t e = hb_launch_prior_normal(h->XP + off * h->ldx, h->ldx, h->d, n_items, h->prior_W, h->prior_mu, h->prior_const,
+                                             h->lp_xp + off, &h->ctrl->err, h->stream); e != cudaSuccess) { h->err = cudaGetErrorString(e); return HB_ERR_CUDA; }
   h->launches++;
   return HB_OK;
 }
@@ -450,44 +583,9 @@ int hb_fail(hb_handle* h, int code, const char* msg) { if (h) h->err = msg; retu
 
 namespace {
 
-// sum `n` doubles over the ranks, in place (HB_EXCHANGE_DELTA: peer-memory all-reduce in rank order; else NCCL)
-int allreduce_small(hb_handle* h, double* buf, int n) {
-  if (h->world <= 1) return HB_OK;
-  if (h->delta_mode) {
-    hb_arena_peers ap; for (int r = 0; r < 8; ++r) ap.p[r] = h->arena_peer[r];
-    hb_peer_reduce_desc rd{};
-    rd.f64[0] = buf; rd.n_f64[0] = n; rd.f64[1] = buf; rd.n_f64[1] = 0; rd.u64 = nullptr; rd.n_u64 = 0;
-    if ((size_t)n * 8 > h->arena_red_bytes) return fail(h, HB_ERR_UNSUPPORTED, "all-reduce of %d doubles exceeds the arena slot", n);
-    ++h->red_seq;
-    CK(hb_launch_peer_allreduce(ap, h->arena_red_off + (size_t)(h->red_seq & 1u) * h->arena_red_bytes, rd, h->rank, h->world,
-                                h->red_seq, &h->ctrl->err, h->stream));
-    return HB_OK;
-  }
-  return hb_nccl_allreduce_f64(h->comm, buf, (size_t)n, h->stream, h->err);
-}
-
-// R_stat(chain[1:t_rows, 1:d, ]) of the whole population into out_dev[d]; on several GPUs the per-chain statistics of
-// the shards are combined with two small all-reduces (sums, then squared deviations from the global mean)
-int rstat_population(hb_handle* h, long long t_rows, double* out_dev) {
-  const long long nl = h->n_local; const int d = h->d;
-  if (h->world <= 1) {
-    CK(hb_launch_rstat(h->hist_x, t_rows, nl, 0, nl, d, h->rstat_xm, h->rstat_ss, out_dev, h->stream));
-    return HB_OK;
-  }
-  if (!h->rstat_sums) CK(dalloc(&h->rstat_sums, (size_t)3 * d));
-  CK(hb_launch_rstat_shard_pass1(h->hist_x, t_rows, nl, d, h->rstat_xm, h->rstat_ss, h->rstat_sums, h->stream));
-  if (int rc = allreduce_small(h, h->rstat_sums, 2 * d)) return rc;
-  CK(hb_launch_rstat_shard_dev(h->rstat_xm, nl, d, h->nc, h->rstat_sums, h->rstat_sums + 2 * d, h->stream));
-  if (int rc = allreduce_small(h, h->rstat_sums + 2 * d, d)) return rc;
-  CK(hb_launch_rstat_shard_final(h->rstat_sums, h->rstat_sums + 2 * d, t_rows, h->nc, d, out_dev, h->stream));
-  return HB_OK;
-}
-
 // The fused generation kernel applies to: dream_parallel's synchronous sweep of one population on one GPU, the built-in
 // t_distribution target with lik = 2, flat / uniform prior, no archive, no multi-try, populations below the size where the
-// large-population kernels take over (hb_fused_small_eligible).  EXPERIMENTAL, opt-in with HB_FUSED=1: the first version
-// measured slower than the three-kernel path on BASELINE C2, and its log-density uses the FMA kernel's
-// summation order, so ll differs from the DMMA plugin's in the last bit (the chain states are identical).
+// large-population kernels take over (hb_fused_small_eligible).  HB_FUSED=0 switches it off.
 bool fused_available(hb_handle* h) {
   const hb_config& c = h->cfg;
   if (h->fused_state == 0) {
@@ -507,7 +605,134 @@ bool fused_available(hb_handle* h) {
   return h->fused_state == 1 && !h->profile && hb_fused_small_eligible(h->n_local, h->d, h->sm_count);
 }
 
-int run_generation(hb_handle* h, long long i) {
+// MT-DREAM, R/dream_parallel.R:269-341 (hb_mt.cu): the whole generation as one host step
+int mt_generation(hb_handle* h, long long i, bool store, bool in_adapt, bool tape_mode) {
+  const hb_config& c = h->cfg;
+  const long long nl = h->n_local;
+  const int ldx = h->ldx;
+  const int mt = c.mt, n_sets = 2 * mt - 1;
+  auto k1_set = [&](int set, int slot, const double* pop) -> int {   // proposal set `set` into try slot `slot`
+    hb_k1_params p = hb_make_k1(h, i, h->chain0, 1, nl);
+    p.X = pop;
+    p.XP = h->XP + (size_t)slot * nl * ldx; p.id_out = h->id + (size_t)slot * nl; p.lp_xp = h->lp_xp + (size_t)slot * nl;
+    p.gen = (uint32_t)i | ((uint32_t)(set + 1) << 24);              // Philox substream of the set
+    p.tape_g = (i - 2) * n_sets + set;                              // tape row g*n_sets + set
+    prof_scope ps(h, "K1");
+    CK(hb_launch_k1(p, tape_mode, h->sm_count, h->stream));
+    ps.done();
+    return HB_OK;
+  };
+  for (int m = 0; m < mt; ++m) if (int rc = k1_set(m, m, h->X)) return rc;                 // :269  around xt
+  if (int rc = hb_prior_after_k1(h, (long long)mt * nl)) return rc;
+  { prof_scope ps(h, "K2"); if (int rc = hb_target_launch(h, h->XP, (long long)mt * nl, h->chain0, 1)) return fail(h, rc, "target launch failed"); ps.done(); }
+  hb_mt_params mp{};
+  mp.mt = mt; mp.n_local = nl; mp.ldx = ldx; mp.XP = h->XP; mp.lp_xp = h->lp_xp; mp.ll_raw = h->ll_raw;
+  mp.fx_xp = c.store_fx ? h->fx_xp : nullptr; mp.id = h->id; mp.ZT = h->ZT; mp.lp_zt = h->lp_zt; mp.ll_zt = h->ll_zt;
+  mp.fx_zt = c.store_fx ? h->fx_zt : nullptr; mp.id_zt = h->id_zt; mp.p1 = h->mt_p1; mp.lpost = h->lpost;
+  mp.accept_out = h->mt_accept; mp.seed = c.seed; mp.gen = (uint32_t)i; mp.gchain0 = (long long)c.run_offset * h->nc + h->chain0;
+  mp.err = &h->ctrl->err;
+  mp.tape_pick = tape_mode ? h->tape_mt_pick + (size_t)(i - 2) * h->tape.nct : nullptr;
+  mp.u_accept = tape_mode ? h->tape.u_accept + (size_t)(i - 2) * h->tape.nct : nullptr;
+  { prof_scope ps(h, "MT"); CK(hb_launch_mt_select(mp, h->stream)); ps.done(); }           // :297-314
+  for (int m = 0; m < mt - 1; ++m) if (int rc = k1_set(mt + m, m, h->ZT)) return rc;       // :316  around zt
+  if (int rc = hb_prior_after_k1(h, (long long)(mt - 1) * nl)) return rc;
+  { prof_scope ps(h, "K2"); if (int rc = hb_target_launch(h, h->XP, (long long)(mt - 1) * nl, h->chain0, 1)) return fail(h, rc, "target launch failed"); ps.done(); }
+  { prof_scope ps(h, "MT"); CK(hb_launch_mt_accept(mp, h->stream)); ps.done(); }           // :340, R/internals.R:229-236
+  hb_k3_params p = hb_make_k3(h, i, h->chain0, 1, nl, store, in_adapt, false);
+  p.XP = h->ZT; p.XP_rw = h->ZT; p.id = h->id_zt; p.lp_xp = h->lp_zt; p.ll_raw = h->ll_zt;   // :349-355 accept the candidates
+  p.fx_xp = c.store_fx ? h->fx_zt : nullptr; p.accept_in = h->mt_accept;
+  prof_scope ps(h, "K3");
+  int nb = 0;
+  CK(hb_launch_k3(p, h->sm_count, &nb, nullptr, h->stream));
+  ps.done();
+  return HB_OK;
+}
+
+// K1 -> K2 -> K3 over chains [off, off + n) of the shard (the whole shard, or one piece of it in delta mode)
+int piece_kernels(hb_handle* h, long long i, int piece, long long off, long long n, bool store, bool in_adapt, bool tape_mode) {
+  const hb_config& c = h->cfg;
+  const int d = h->d, ldx = h->ldx;
+  {  // K1
+    hb_k1_params p = hb_make_k1(h, i, h->chain0 + off, 1, n);
+    p.XP += off * ldx; p.id_out += off; p.lp_xp += off;
+    p.reserve_ctas = h->reserve_ctas;
+    prof_scope ps(h, "K1");
+    CK(hb_launch_k1(p, tape_mode, h->sm_count, h->stream));
+    ps.done();
+    if (int rc = hb_prior_after_k1(h, n, off)) return rc;
+  }
+  {  // K2: the target plugin
+    prof_scope ps(h, "K2");
+    if (int rc = hb_target_launch(h, h->XP + off * ldx, n, h->chain0 + off, 1, off)) return fail(h, rc, "target launch failed");
+    ps.done();
+  }
+  {  // K3
+    hb_k3_params p = hb_make_k3(h, i, h->chain0 + off, 1, n, store, in_adapt, false);
+    p.XP += off * ldx; p.XP_rw += off * ldx; p.id += off; p.lp_xp += off; p.ll_raw += off;
+    if (p.fx_xp) p.fx_xp += off;
+    p.partials = h->partials + (size_t)piece * h->k3_blocks_piece * (c.nCR + 2) * d;
+    if (h->delta_mode) {   // accepted rows go to this rank's delta log: box (parity, self), slots of this piece
+      unsigned char* box = h->arena + h->arena_box_off + ((size_t)(i & 1) * h->world + h->rank) * h->box_bytes;
+      p.log_rows = reinterpret_cast<double*>(box + h->box_rows_off) + (size_t)piece * h->piece_n * ldx;
+      p.log_idx = reinterpret_cast<int*>(box + h->box_idx_off) + (size_t)piece * h->piece_n;
+      p.log_count = h->log_ctr + (size_t)(i & 1) * HB_MAX_PIECES + piece;
+    }
+    prof_scope ps(h, "K3");
+    int nb = 0;
+    CK(hb_launch_k3(p, h->sm_count, &nb, nullptr, h->stream));
+    ps.done();
+  }
+  return HB_OK;
+}
+
+// ship piece `piece` of generation i's delta log to every peer (side stream: overlaps the next piece's kernels)
+int piece_send(hb_handle* h, long long i, int piece) {
+  hb_delta_send_params sp{};
+  for (int r = 0; r < h->world; ++r) {
+    sp.arena[r] = h->arena_peer[r];
+    sp.box[r] = h->arena_peer[r] + h->arena_box_off + ((size_t)(i & 1) * h->world + h->rank) * h->box_bytes;
+  }
+  sp.idx_off = h->box_idx_off; sp.rows_off = h->box_rows_off; sp.piece_off = (long long)piece * h->piece_n;
+  sp.piece = piece; sp.ldx = h->ldx; sp.self = h->rank; sp.world = h->world;
+  sp.log_count = h->log_ctr + (size_t)(i & 1) * HB_MAX_PIECES + piece;
+  sp.done_ctr = h->log_ctr + 2 * HB_MAX_PIECES + piece;
+  sp.flag_value = (unsigned)i * HB_MAX_PIECES + (unsigned)piece + 1u;
+  if (h->side != h->stream) {
+    CK(cudaEventRecord(h->ev_piece[piece], h->stream));
+    CK(cudaStreamWaitEvent(h->side, h->ev_piece[piece], 0));
+  }
+  prof_scope ps(h, "XCHG", h->side);
+  CK(hb_launch_delta_send(sp, h->send_ctas, h->side));
+  ps.done();
+  return HB_OK;
+}
+
+// fold the delta logs of pieces [p0, p1) of generation i -- this rank's and every peer's -- into the replica
+int delta_apply(hb_handle* h, long long i, int p0, int p1) {
+  hb_delta_apply_params ap{};
+  for (int r = 0; r < h->world; ++r) ap.box[r] = h->arena + h->arena_box_off + ((size_t)(i & 1) * h->world + r) * h->box_bytes;
+  ap.idx_off = h->box_idx_off; ap.rows_off = h->box_rows_off; ap.piece_cap = h->piece_n; ap.p0 = p0; ap.p1 = p1;
+  ap.ldx = h->ldx; ap.self = h->rank; ap.world = h->world; ap.nc = h->nc; ap.X = h->X;
+  ap.flags = reinterpret_cast<const unsigned*>(h->arena); ap.flag_value = (unsigned)i * HB_MAX_PIECES + (unsigned)p1;
+  ap.err = &h->ctrl->err; ap.timeout_ns = hb_peer_timeout_ns();
+  prof_scope ps(h, "APPLY");
+  CK(hb_launch_delta_apply(ap, h->sm_count, h->stream));
+  ps.done();
+  return HB_OK;
+}
+
+hb_fin_params make_fin(hb_handle* h, bool in_adapt, bool upd) {
+  const hb_config& c = h->cfg;
+  hb_fin_params f{};
+  f.ctrl = h->ctrl; f.partials = h->partials; f.nblocks = h->k3_blocks; f.shift = h->shift; f.colsum = h->colsum;
+  f.qsum = h->qsum; f.nc = h->nc; f.d = h->d; f.nCR = c.nCR; f.adapt = in_adapt; f.do_pcr = in_adapt && upd;
+  f.do_arcr = upd; f.out_ar = h->out_ar; f.out_cr = h->out_cr; f.ar_rows = h->ar_rows;
+  f.n_eval_inc = h->pending_evals; f.n_slots = 1; f.slot_stride = 0;
+  return f;
+}
+
+// the program of generation i of the synchronous sweep (R/dream_parallel.R:257-435)
+int build_generation(hb_handle* h, long long i, gen_prog& g) {
   const hb_config& c = h->cfg;
   const long long nl = h->n_local;
   const int d = h->d, ldx = h->ldx;
@@ -520,146 +745,168 @@ int run_generation(hb_handle* h, long long i) {
   const bool upd = (i % c.update_interval == 0);
   const bool tape_mode = (c.rng_mode == HB_RNG_TAPE);
 
-  if (h->modeb) return hb_seq_generation(h, i);
+  if (h->modeb) { g.then([=]() -> int { return hb_seq_generation(h, i); }); return HB_OK; }
   if (c.mt > 1) {
-    // ---------------- MT-DREAM, R/dream_parallel.R:269-341 (hb_mt.cu) ----------------
-    const int mt = c.mt, n_sets = 2 * mt - 1;
-    auto k1_set = [&](int set, int slot, const double* pop) -> int {   // proposal set `set` into try slot `slot`
-      hb_k1_params p = hb_make_k1(h, i, h->chain0, 1, nl);
-      p.X = pop;
-      p.XP = h->XP + (size_t)slot * nl * ldx; p.id_out = h->id + (size_t)slot * nl; p.lp_xp = h->lp_xp + (size_t)slot * nl;
-      p.gen = (uint32_t)i | ((uint32_t)(set + 1) << 24);              // Philox substream of the set
-      p.tape_g = (i - 2) * n_sets + set;                              // tape row g*n_sets + set
-      prof_scope ps(h, "K1");
-      CK(hb_launch_k1(p, tape_mode, h->sm_count, h->stream));
-      ps.done();
-      return HB_OK;
-    };
-    for (int m = 0; m < mt; ++m) if (int rc = k1_set(m, m, h->X)) return rc;                 // :269  around xt
-    if (int rc = hb_prior_after_k1(h, (long long)mt * nl)) return rc;
-    { prof_scope ps(h, "K2"); if (int rc = hb_target_launch(h, h->XP, (long long)mt * nl, h->chain0, 1)) return fail(h, rc, "target launch failed"); ps.done(); }
-    hb_mt_params mp{};
-    mp.mt = mt; mp.n_local = nl; mp.ldx = ldx; mp.XP = h->XP; mp.lp_xp = h->lp_xp; mp.ll_raw = h->ll_raw;
-    mp.fx_xp = c.store_fx ? h->fx_xp : nullptr; mp.id = h->id; mp.ZT = h->ZT; mp.lp_zt = h->lp_zt; mp.ll_zt = h->ll_zt;
-    mp.fx_zt = c.store_fx ? h->fx_zt : nullptr; mp.id_zt = h->id_zt; mp.p1 = h->mt_p1; mp.lpost = h->lpost;
-    mp.accept_out = h->mt_accept; mp.seed = c.seed; mp.gen = (uint32_t)i; mp.gchain0 = (long long)c.run_offset * h->nc + h->chain0;
-    mp.err = &h->ctrl->err;
-    mp.tape_pick = tape_mode ? h->tape_mt_pick + (size_t)(i - 2) * h->tape.nct : nullptr;
-    mp.u_accept = tape_mode ? h->tape.u_accept + (size_t)(i - 2) * h->tape.nct : nullptr;
-    { prof_scope ps(h, "MT"); CK(hb_launch_mt_select(mp, h->stream)); ps.done(); }           // :297-314
-    for (int m = 0; m < mt - 1; ++m) if (int rc = k1_set(mt + m, m, h->ZT)) return rc;       // :316  around zt
-    if (int rc = hb_prior_after_k1(h, (long long)(mt - 1) * nl)) return rc;
-    { prof_scope ps(h, "K2"); if (int rc = hb_target_launch(h, h->XP, (long long)(mt - 1) * nl, h->chain0, 1)) return fail(h, rc, "target launch failed"); ps.done(); }
-    { prof_scope ps(h, "MT"); CK(hb_launch_mt_accept(mp, h->stream)); ps.done(); }           // :340, R/internals.R:229-236
-    hb_k3_params p = hb_make_k3(h, i, h->chain0, 1, nl, store, in_adapt, false);
-    p.XP = h->ZT; p.XP_rw = h->ZT; p.id = h->id_zt; p.lp_xp = h->lp_zt; p.ll_raw = h->ll_zt;   // :349-355 accept the candidates
-    p.fx_xp = c.store_fx ? h->fx_zt : nullptr; p.accept_in = h->mt_accept;
-    prof_scope ps(h, "K3");
-    int nb = 0;
-    CK(hb_launch_k3(p, h->sm_count, &nb, nullptr, h->stream));
-    ps.done();
+    g.then([=]() -> int { return mt_generation(h, i, store, in_adapt, tape_mode); });
   } else if (!in_adapt && fused_available(h)) {
     // small population outside the adaptation period: proposal + log-density + accept in one launch, the post-generation
     // rows go to the second buffer (no grid-wide barrier between the partner reads and the state update)
-    const hb_k1_params p = hb_make_k1(h, i, h->chain0, 1, nl);
-    hb_k3_params q = hb_make_k3(h, i, h->chain0, 1, nl, store, false, false);
-    q.Xout = h->Xalt;
-    CK(hb_launch_fused_small(p, q, h->fused_td, tape_mode, h->sm_count, h->stream));
-    h->launches++;
-    std::swap(h->X, h->Xalt);
+    g.then([=]() -> int {
+      const hb_k1_params p = hb_make_k1(h, i, h->chain0, 1, nl);
+      hb_k3_params q = hb_make_k3(h, i, h->chain0, 1, nl, store, false, false);
+      q.Xout = h->Xalt;
+      CK(hb_launch_fused_small(p, q, h->fused_td, tape_mode, h->sm_count, h->stream));
+      h->launches++;
+      std::swap(h->X, h->Xalt);
+      return HB_OK;
+    });
+  } else if (h->delta_mode) {
+    // sharded population, stage-and-apply exchange (hb_delta.cu): piece p's log travels while piece p + 1 computes
+    const int P = h->pieces;
+    g.then([=]() -> int {
+      for (int p = 0; p < P; ++p) {
+        const long long off = (long long)p * h->piece_n, n = std::min(h->piece_n, nl - off);
+        if (n > 0) { if (int rc = piece_kernels(h, i, p, off, n, store, in_adapt, tape_mode)) return rc; }
+        if (int rc = piece_send(h, i, p)) return rc;        // an empty piece still raises its flag
+      }
+      if (h->side != h->stream) {                           // the apply kernel reads this rank's own log and counts
+        CK(cudaEventRecord(h->ev_sent, h->side));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_sent, 0));
+      }
+      return HB_OK;
+    });
+    g.cut();
+    g.then([=]() -> int { return delta_apply(h, i, 0, P); });
   } else {
-  {  // K1
-    const hb_k1_params p = hb_make_k1(h, i, h->chain0, 1, nl);
-    prof_scope ps(h, "K1");
-    CK(hb_launch_k1(p, tape_mode, h->sm_count, h->stream));
-    ps.done();
-    if (int rc = hb_prior_after_k1(h, nl)) return rc;
-    if (h->delta_mode) {   // barrier A, arrive: this rank's K1 of generation i has finished reading its replica
-      hb_flag_peers fp; for (int r = 0; r < 8; ++r) fp.p[r] = h->flags_peer[r];
-      CK(hb_launch_flag_signal(fp, 0, h->rank, h->world, (unsigned)i, h->stream));
-      h->launches++;
-    }
+    g.then([=]() -> int { return piece_kernels(h, i, 0, 0, nl, store, in_adapt, tape_mode); });
   }
-  {  // K2: the target plugin
-    prof_scope ps(h, "K2");
-    if (int rc = hb_target_launch(h, h->XP, nl, h->chain0, 1)) return fail(h, rc, "target launch failed");
-    ps.done();
-  }
-  {  // K3
-    const hb_k3_params p = hb_make_k3(h, i, h->chain0, 1, nl, store, in_adapt, false);
-    if (h->delta_mode) {   // barrier A: no peer may push generation-i rows into a replica that K1 is still reading
-      CK(hb_launch_flag_wait(h->flags, 0, h->rank, h->world, (unsigned)i, &h->ctrl->err, h->stream));
-      h->launches++;
-    }
-    prof_scope ps(h, "K3");
-    int nb = 0;
-    CK(hb_launch_k3(p, h->sm_count, &nb, nullptr, h->stream));
-    ps.done();
-  }
-  }   // mt == 1
   h->pending_evals += h->nc;
-  if (in_adapt || upd || h->peer_mode) {  // finalize: J / n_id / n_acc, pCR adaptation, AR/CR rows (peer mode: every
-                                          // generation, its counter all-reduce is the generation barrier)
-    hb_fin_params f{};
-    f.ctrl = h->ctrl; f.partials = h->partials; f.nblocks = h->k3_blocks; f.shift = h->shift; f.colsum = h->colsum;
-    f.qsum = h->qsum; f.nc = h->nc; f.d = d; f.nCR = c.nCR; f.adapt = in_adapt; f.do_pcr = in_adapt && upd;
-    f.do_arcr = upd; f.out_ar = h->out_ar; f.out_cr = h->out_cr; f.ar_rows = h->ar_rows;
-    f.n_eval_inc = h->pending_evals;
-    prof_scope ps(h, "FIN");
-    if (h->world > 1) {
-      f.phase = 0; CK(hb_launch_finalize(f, h->stream));
-      if (h->delta_mode) {   // one fused all-reduce over peer memory, summed in rank order
-        hb_arena_peers ap; for (int r = 0; r < 8; ++r) ap.p[r] = h->arena_peer[r];
-        hb_peer_reduce_desc rd{};
-        rd.f64[0] = h->colsum; rd.n_f64[0] = in_adapt ? 2 * d : 0;
-        rd.f64[1] = h->qsum; rd.n_f64[1] = in_adapt ? c.nCR * d : 0;
-        rd.u64 = h->ctrl->n_id_gen; rd.n_u64 = HB_MAX_NCR + 1;
-        ++h->red_seq;
-        CK(hb_launch_peer_allreduce(ap, h->arena_red_off + (size_t)(h->red_seq & 1u) * h->arena_red_bytes, rd, h->rank, h->world,
-                                    h->red_seq, &h->ctrl->err, h->stream));
-      } else {
+
+  // finalize: J / n_id / n_acc, pCR adaptation, AR/CR rows
+  if (h->delta_mode) {
+    // the adaptation sums of every generation are parked in a slot of the interval buffer; one all-reduce per
+    // updateInterval carries them (and the integer counters), then they are folded in generation order
+    const int E = (c.nCR + 2) * d;
+    if (in_adapt) {
+      const int slot = h->islot++;
+      g.then([=]() -> int {
+        hb_fin_params f = make_fin(h, true, false);
+        f.phase = 0; f.colsum = h->ibuf + (size_t)slot * E; f.qsum = f.colsum + 2 * d;
+        prof_scope ps(h, "FIN");
+        CK(hb_launch_finalize(f, h->stream));
+        ps.done();
+        return HB_OK;
+      });
+    }
+    if (upd) {
+      const int n_slots = in_adapt ? h->islot : 0;
+      h->islot = 0;
+      hb_fin_params f = make_fin(h, in_adapt, true);
+      f.phase = 1; f.colsum = h->ibuf; f.qsum = h->ibuf + 2 * d; f.n_slots = n_slots; f.slot_stride = E;
+      h->pending_evals = 0;
+      hb_peer_reduce_desc rd{};
+      rd.f64[0] = h->ibuf; rd.n_f64[0] = n_slots * E; rd.f64[1] = h->ibuf; rd.n_f64[1] = 0;
+      rd.u64 = h->ctrl->n_id_gen; rd.n_u64 = HB_MAX_NCR + 1;
+      g.then([=]() -> int { return allreduce_post(h, rd); });
+      g.cut();
+      g.then([=]() -> int {
+        if (int rc = allreduce_finish(h, rd)) return rc;
+        prof_scope ps(h, "FIN");
+        CK(hb_launch_finalize(f, h->stream));
+        ps.done();
+        return HB_OK;
+      });
+    }
+  } else if (in_adapt || upd || h->peer_mode) {   // (peer mode: every generation, its counter all-reduce is the generation barrier)
+    hb_fin_params f = make_fin(h, in_adapt, upd);
+    h->pending_evals = 0;
+    g.then([=]() -> int {
+      hb_fin_params ff = f;
+      prof_scope ps(h, "FIN");
+      if (h->world > 1) {
+        ff.phase = 0; CK(hb_launch_finalize(ff, h->stream));
         if (in_adapt) {
           if (int rc = hb_nccl_allreduce_f64(h->comm, h->colsum, (size_t)2 * d, h->stream, h->err)) return rc;
           if (int rc = hb_nccl_allreduce_f64(h->comm, h->qsum, (size_t)c.nCR * d, h->stream, h->err)) return rc;
         }
         if (int rc = hb_nccl_allreduce_u64(h->comm, h->ctrl->n_id_gen, HB_MAX_NCR + 1, h->stream, h->err)) return rc;
+        ff.phase = 1; CK(hb_launch_finalize(ff, h->stream));
+        ps.done(2);
+      } else {
+        ff.phase = 2; CK(hb_launch_finalize(ff, h->stream));
+        ps.done();
       }
-      f.phase = 1; CK(hb_launch_finalize(f, h->stream));
-      ps.done(2);
-    } else {
-      f.phase = 2; CK(hb_launch_finalize(f, h->stream));
-      ps.done();
-    }
-    h->pending_evals = 0;
+      return HB_OK;
+    });
   }
   if (h->peer_mode) {   // K3 wrote every row of the shard into the other buffer; peers read it next generation
-    h->cur ^= 1;
-    h->X = h->Xbuf[h->cur] - h->chain0 * ldx;
-  } else if (h->delta_mode) {   // barrier B: the rows every peer accepted this generation have landed in this replica
-    hb_flag_peers fp; for (int r = 0; r < 8; ++r) fp.p[r] = h->flags_peer[r];
-    prof_scope ps(h, "XCHG");
-    CK(hb_launch_flag_signal(fp, 1, h->rank, h->world, (unsigned)i, h->stream));
-    CK(hb_launch_flag_wait(h->flags, 1, h->rank, h->world, (unsigned)i, &h->ctrl->err, h->stream));
-    ps.done(2);
-  } else if (h->world > 1) {  // chain-state exchange: every rank needs every row for the next generation's partner draws
-    prof_scope ps(h, "XCHG");
-    if (int rc = hb_nccl_allgather_f64(h->comm, h->X + h->chain0 * ldx, h->X, (size_t)nl * ldx, h->stream, h->err)) return rc;
-    ps.done();
+    g.then([=]() -> int { h->cur ^= 1; h->X = h->Xbuf[h->cur] - h->chain0 * ldx; return HB_OK; });
+  } else if (h->world > 1 && !h->delta_mode) {  // chain-state exchange: every rank needs every row for the next generation's partner draws
+    g.then([=]() -> int {
+      prof_scope ps(h, "XCHG");
+      if (int rc = hb_nccl_allgather_f64(h->comm, h->X + h->chain0 * ldx, h->X, (size_t)nl * ldx, h->stream, h->err)) return rc;
+      ps.done();
+      return HB_OK;
+    });
   }
   if (c.past_sample && h->archive_update > 0 && (i % h->archive_update == 0)) {     // :382-383  z <- rbind(z, xt)
-    if (h->m_arch + h->nc > h->m_cap) return fail(h, HB_ERR_STATE, "archive capacity exceeded");
-    CK(cudaMemcpyAsync(h->Z + (size_t)h->m_arch * ldx, h->X, sizeof(double) * (size_t)h->nc * ldx, cudaMemcpyDeviceToDevice, h->stream));
-    h->m_arch += h->nc;
+    g.then([=]() -> int {
+      if (h->m_arch + h->nc > h->m_cap) return fail(h, HB_ERR_STATE, "archive capacity exceeded");
+      CK(cudaMemcpyAsync(h->Z + (size_t)h->m_arch * ldx, h->X, sizeof(double) * (size_t)h->nc * ldx, cudaMemcpyDeviceToDevice, h->stream));
+      h->m_arch += h->nc;
+      return HB_OK;
+    });
   }
-  if (c.check_convergence && store && h->ind_out > 50) {   // R_stat(chain[1:ind_out, 1:d, ]) as R/dream_test.R:344
-    prof_scope ps(h, "K4");
-    if (int rc = rstat_population(h, h->ind_out, h->rstat_dev + (size_t)(h->ind_out - 51) * d)) return rc;
-    ps.done(2);
+  if (c.check_convergence && store && h->ind_out > 50)   // R_stat(chain[1:ind_out, 1:d, ]) as R/dream_test.R:344
+    prog_rstat_population(h, g, h->ind_out, h->rstat_dev + (size_t)(h->ind_out - 51) * d);
+  if (in_adapt && upd && !c.past_sample && c.outlier_check)                          // :414-419
+    prog_outlier_check(h, g, i);
+  g.then([=]() -> int { h->gen = i; return HB_OK; });
+  return HB_OK;
+}
+
+// end of a slice on several GPUs: OR the ranks' error masks so that every rank returns the same status (a shard-local
+// condition -- a non-finite density, a bad tape record -- must not leave the other ranks waiting in the next slice)
+void prog_err_reduce(hb_handle* h, gen_prog& g) {
+  if (h->world <= 1) return;
+  if (h->delta_mode) {
+    g.then([=]() -> int {
+      unsigned extra = 0u;
+      if (h->target_is_hydro) { CK(cudaStreamSynchronize(h->stream)); extra = hb_hydro_poll_err(h->tctx); }
+      CK(hb_launch_peer_err_post(arena_peers(h), HB_ARENA_ERR_OFF, &h->ctrl->err, extra, h->rank, h->world, ++h->err_seq, h->stream));
+      return HB_OK;
+    });
+    g.cut();
+    g.then([=]() -> int { CK(hb_launch_peer_err_finish(arena_peers(h), HB_ARENA_ERR_OFF, &h->ctrl->err, h->rank, h->world, h->err_seq, h->stream)); return HB_OK; });
+  } else {
+    g.then([=]() -> int {
+      unsigned extra = 0u;
+      if (h->target_is_hydro) { CK(cudaStreamSynchronize(h->stream)); extra = hb_hydro_poll_err(h->tctx); }
+      CK(hb_launch_err_expand(&h->ctrl->err, extra, h->errbits_dev, h->stream));
+      if (int rc = hb_nccl_allreduce_u64(h->comm, h->errbits_dev, 16, h->stream, h->err)) return rc;
+      CK(hb_launch_err_collapse(&h->ctrl->err, h->errbits_dev, h->stream));
+      return HB_OK;
+    });
   }
-  if (in_adapt && upd && !c.past_sample && c.outlier_check) {                        // :414-419
-    if (int rc = outlier_check(h, i)) return rc;
-  }
-  h->gen = i;
+}
+
+// start of a slice in delta mode: one flag barrier absorbs the host-side skew between the ranks (allocation, page
+// faults, garbage collection between slices), so the waits inside the slice only ever see in-slice skew
+void prog_slice_barrier(hb_handle* h, gen_prog& g) {
+  if (h->world <= 1 || !h->delta_mode) return;
+  g.then([=]() -> int { CK(hb_launch_flag_signal(arena_peers(h), 0, h->rank, h->world, ++h->slice_seq, h->stream)); h->launches++; return HB_OK; });
+  g.cut();
+  g.then([=]() -> int { CK(hb_launch_flag_wait(h->arena, 0, h->rank, h->world, h->slice_seq, &h->ctrl->err, h->stream)); h->launches++; return HB_OK; });
+}
+
+// runs a set of programs (one per rank handle) stage by stage: stage s of every rank before stage s + 1 of any
+int run_programs(std::vector<hb_handle*>& hs, std::vector<gen_prog>& gs) {
+  const size_t n_st = gs[0].stages.size();
+  for (size_t r = 1; r < gs.size(); ++r)
+    if (gs[r].stages.size() != n_st) return fail(hs[r], HB_ERR_STATE, "rank programs diverged (%zu vs %zu stages)", gs[r].stages.size(), n_st);
+  for (size_t st = 0; st < n_st; ++st)
+    for (size_t r = 0; r < gs.size(); ++r)
+      for (auto& f : gs[r].stages[st]) if (int rc = f()) return rc;
   return HB_OK;
 }
 
@@ -787,18 +1034,25 @@ void hb_destroy(hb_handle* h) {
   if (!h) return;
   const double t_begin = now_s();
   cudaSetDevice(h->device);
-  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->group_member) cudaDeviceSynchronize();   // the shared stream of a rank emulation may already be gone with rank 0's handle
+  else if (h->stream) cudaStreamSynchronize(h->stream);
   hb_seq_destroy(h);
   if (h->vt && h->tctx) h->vt->destroy(h->tctx);
   hb_nccl_destroy(h->comm);
   if (h->delta_mode) {
     for (int r = 0; r < 8; ++r) {
       if (h->peerX_opened[r]) cudaIpcCloseMemHandle(h->peerX_opened[r]);
-      if (h->flags_opened[r]) cudaIpcCloseMemHandle(h->flags_opened[r]);
+      if (h->arena_opened[r]) cudaIpcCloseMemHandle(h->arena_opened[r]);
     }
     cudaFree(h->arena);
     cudaFree(h->X); h->X = nullptr;   // IPC-exported buffers are released synchronously, right after this rank closed its
                                       // own imports (only the private buffers below go to the reaper thread)
+    if (h->side && h->side != h->stream) cudaStreamDestroy(h->side);
+    for (int q = 0; q < HB_MAX_PIECES; ++q) if (h->ev_piece[q]) cudaEventDestroy(h->ev_piece[q]);
+    if (h->ev_sent) cudaEventDestroy(h->ev_sent);
+  }
+  if (h->group_member && h->own_stream) {   // rank emulation: the shared stream belongs to rank 0's handle
+    h->stream = h->own_stream; h->own_stream = nullptr;
   }
   if (h->peer_mode) {
     h->X = nullptr;
@@ -808,7 +1062,7 @@ void hb_destroy(hb_handle* h) {
   void* ptrs[] = {h->X, h->Xalt, h->Z, h->XP, h->id, h->lp_xp, h->ll_raw, h->fx_xp, h->lp, h->ll, h->lpost, h->fx, h->lpost_hist,
                   h->hist_x, h->hist_l, h->hist_fx, h->accept_rec, h->ctrl, h->shift, h->colsum, h->qsum, h->partials,
                   h->out_ar, h->out_cr, h->proxy, h->proxy_full, h->lpost_full, h->outl_dev, h->news_dev, h->rstat_dev,
-                  h->rstat_xm, h->rstat_ss, h->stage, h->pmin, h->pmax, h->prior_W, h->prior_mu, h->ZT, h->lp_zt, h->ll_zt, h->fx_zt, h->id_zt, h->mt_p1, h->mt_accept, h->rstat_sums, h->gamma_tab, h->outl_tmp, h->outl_sorted, h->outl_thr,
+                  h->rstat_xm, h->rstat_ss, h->stage, h->log_ctr, h->ibuf, h->errbits_dev, h->pmin, h->pmax, h->prior_W, h->prior_mu, h->ZT, h->lp_zt, h->ll_zt, h->fx_zt, h->id_zt, h->mt_p1, h->mt_accept, h->rstat_sums, h->gamma_tab, h->outl_tmp, h->outl_sorted, h->outl_thr,
                   h->outl_count};
   {
     std::vector<void*> dead;
@@ -829,6 +1083,11 @@ int hb_set_bounds(hb_handle* h, const double* par_min, const double* par_max, in
   if (!h) return HB_ERR_INVALID;
   if (!par_min || !par_max) return fail(h, HB_ERR_INVALID, "hb_set_bounds: min and max must both be given (R/internals.R:210)");
   if (n != 1 && n != h->d) return fail(h, HB_ERR_INVALID, "hb_set_bounds: n must be 1 or d");
+  for (int k = 0; k < n; ++k) {
+    if (!(par_min[k] <= par_max[k])) return fail(h, HB_ERR_INVALID, "hb_set_bounds: min must be <= max (parameter %d: min = %g, max = %g)", k + 1, par_min[k], par_max[k]);
+    if (par_min[k] == par_max[k] && (h->cfg.bound == HB_BOUND_REFLECT || h->cfg.bound == HB_BOUND_FOLD))
+      return fail(h, HB_ERR_INVALID, "hb_set_bounds: bound = 'reflect' / 'fold' need min < max (parameter %d): R's while loop would not end", k + 1);
+  }
   cudaSetDevice(h->device);
   h->pmin_h.resize((size_t)h->d); h->pmax_h.resize((size_t)h->d);
   for (int k = 0; k < h->d; ++k) { h->pmin_h[k] = par_min[n > 1 ? k : 0]; h->pmax_h[k] = par_max[n > 1 ? k : 0]; }   // :211-212
@@ -976,6 +1235,20 @@ int hb_comm_init(hb_handle* h, int rank, int world, const void* id128) {
   return HB_OK;
 }
 
+// HB_EXCHANGE_DELTA with a sharded upload: complete the peers' replicas with this rank's rows (NVLink peer copies), then
+// arrive at flag 1 with value 1; the first generation waits for every peer's arrival
+static int complete_replicas(hb_handle* h) {
+  if (!h->initial_sharded) return HB_OK;
+  const size_t off = (size_t)h->chain0 * h->ldx, bytes = (size_t)h->n_local * h->ldx * sizeof(double);
+  for (int q = 1; q < h->world; ++q) {
+    const int r = (h->rank + q) % h->world;
+    CK(cudaMemcpyAsync(h->peerX[r] + off, h->X + off, bytes, cudaMemcpyDefault, h->stream));
+  }
+  hb_arena_peers ap; for (int r = 0; r < 8; ++r) ap.p[r] = h->arena_peer[r];
+  CK(hb_launch_flag_signal(ap, 1, h->rank, h->world, 1u, h->stream));
+  return HB_OK;
+}
+
 int hb_peer_export(hb_handle* h, void* out128) {
   if (!h || !out128) return HB_ERR_INVALID;
   if (!h->peer_mode && !h->delta_mode) return fail(h, HB_ERR_STATE, "hb_peer_export: the handle is not in HB_EXCHANGE_PEER / HB_EXCHANGE_DELTA mode");
@@ -1009,20 +1282,11 @@ int hb_peer_import(hb_handle* h, const void* all_handles) {
       CK(cudaIpcOpenMemHandle(&px, hd[2 * r], cudaIpcMemLazyEnablePeerAccess));
       CK(cudaIpcOpenMemHandle(&pf, hd[2 * r + 1], cudaIpcMemLazyEnablePeerAccess));
       h->peerX_opened[r] = px; h->peerX[r] = (double*)px;
-      h->flags_opened[r] = pf; h->flags_peer[r] = (unsigned*)pf; h->arena_peer[r] = (unsigned char*)pf;
+      h->arena_opened[r] = pf; h->arena_peer[r] = (unsigned char*)pf;
     }
     h->arena_peer[h->rank] = h->arena;
-    if (h->initial_sharded) {   // complete the peers' replicas with this rank's rows (NVLink peer copies), then arrive at
-                                // barrier B with value 1; the first generation waits for every peer's arrival
-      const size_t off = (size_t)h->chain0 * h->ldx, bytes = (size_t)h->n_local * h->ldx * sizeof(double);
-      for (int q = 1; q < h->world; ++q) {
-        const int r = (h->rank + q) % h->world;
-        CK(cudaMemcpyAsync(h->peerX[r] + off, h->X + off, bytes, cudaMemcpyDefault, h->stream));
-      }
-      hb_flag_peers fp; for (int r = 0; r < 8; ++r) fp.p[r] = h->flags_peer[r];
-      CK(hb_launch_flag_signal(fp, 1, h->rank, h->world, 1u, h->stream));
-      CK(cudaStreamSynchronize(h->stream));
-    }
+    if (int rc = complete_replicas(h)) return rc;
+    CK(cudaStreamSynchronize(h->stream));
     h->peers_ready = true;
     return HB_OK;
   }
@@ -1056,7 +1320,7 @@ static int upload_pipelined(hb_handle* h, void* dst_dev, const void* src_host, s
     char* pb = reinterpret_cast<char*>(h->pin) + (k & 1) * half;
     const char* sb = reinterpret_cast<const char*>(src_host) + off;
     std::vector<std::thread> th;
-    for (int t = 1; t < n_thr; ++t) th.emplace_back([=]() { const size_t lo = n / n_thr * t, hi = (t == n_thr - 1) ? n : n / n_thr * (t + 1); memcpy(pb + lo, sb + lo, hi - lo); });
+    for (int t = 1; t < n_thr; ++t) th.emplace_back([=]() -> int { const size_t lo = n / n_thr * t, hi = (t == n_thr - 1) ? n : n / n_thr * (t + 1); memcpy(pb + lo, sb + lo, hi - lo); });
     memcpy(pb, sb, n_thr > 1 ? n / n_thr : n);
     for (auto& x : th) x.join();
     e = cudaMemcpyAsync(reinterpret_cast<char*>(dst_dev) + off, pb, n, cudaMemcpyHostToDevice, h->stream);
@@ -1127,35 +1391,105 @@ int hb_set_tape(hb_handle* h, const hb_tape* tape) {
   return upload_tape(h, tape);
 }
 
-int hb_run(hb_handle* h, int64_t n_generations, int64_t* done_total) {
-  if (!h) return HB_ERR_INVALID;
-  cudaSetDevice(h->device);
-  if (!h->vt) return fail(h, HB_ERR_STATE, "hb_run: no target set");
-  if (!h->have_initial) return fail(h, HB_ERR_STATE, "hb_run: hb_set_initial has not been called");
-  if (h->cfg.rng_mode == HB_RNG_TAPE && !h->have_tape) return fail(h, HB_ERR_STATE, "hb_run: rng_mode is TAPE but no tape was set");
-  if (h->cfg.prior == HB_PRIOR_UNIFORM && !h->have_min_max) return fail(h, HB_ERR_INVALID, "prior = 'uniform' needs min and max");
-  if (h->cfg.prior == HB_PRIOR_NORMAL && !h->have_prior_normal) return fail(h, HB_ERR_INVALID, "prior = 'normal' needs mu and cov (hb_set_prior_normal)");
-  if ((h->peer_mode || h->delta_mode) && !h->peers_ready) return fail(h, HB_ERR_STATE, "hb_run: HB_EXCHANGE_PEER needs hb_peer_export / hb_peer_import after hb_set_initial");
-  if (!h->initialised) {
+// One slice of generations for a set of rank handles driven in lockstep: a single handle (hb_run: one process per GPU) or
+// the ranks of an emulation on one device (hb_group_run).
+static int run_slice(std::vector<hb_handle*>& hs, int64_t n_generations) {
+  for (hb_handle* h : hs) {
+    cudaSetDevice(h->device);
+    if (!h->vt) return fail(h, HB_ERR_STATE, "hb_run: no target set");
+    if (!h->have_initial) return fail(h, HB_ERR_STATE, "hb_run: hb_set_initial has not been called");
+    if (h->cfg.rng_mode == HB_RNG_TAPE && !h->have_tape) return fail(h, HB_ERR_STATE, "hb_run: rng_mode is TAPE but no tape was set");
+    if (h->cfg.prior == HB_PRIOR_UNIFORM && !h->have_min_max) return fail(h, HB_ERR_INVALID, "prior = 'uniform' needs min and max");
+    if (h->cfg.prior == HB_PRIOR_NORMAL && !h->have_prior_normal) return fail(h, HB_ERR_INVALID, "prior = 'normal' needs mu and cov (hb_set_prior_normal)");
+    if ((h->peer_mode || h->delta_mode) && !h->peers_ready) return fail(h, HB_ERR_STATE, "hb_run: HB_EXCHANGE_PEER / HB_EXCHANGE_DELTA need hb_peer_export / hb_peer_import after hb_set_initial");
+    if (h->group_member && hs.size() == 1 && h->world > 1) return fail(h, HB_ERR_STATE, "hb_run: the handle belongs to a rank emulation, use hb_group_run");
+    if (h->gen != hs[0]->gen || h->t != hs[0]->t) return fail(h, HB_ERR_STATE, "hb_group_run: the handles are not at the same generation");
+  }
+  for (hb_handle* h : hs) {
+    if (h->initialised) continue;
     if (h->initial_sharded)   // every peer has copied its shard of the initial population into this replica
-      CK(hb_launch_flag_wait(h->flags, 1, h->rank, h->world, 1u, &h->ctrl->err, h->stream));
+      CK(hb_launch_flag_wait(h->arena, 1, h->rank, h->world, 1u, &h->ctrl->err, h->stream));
     if (int rc = initialise(h)) return rc;
     if (h->modeb) { if (int rc2 = hb_seq_initialise(h)) return rc2; }
   }
-  long long last = h->gen + n_generations;
-  if (last > h->t) last = h->t;
-  CK(cudaEventRecord(h->ev0, h->stream));
-  for (long long i = h->gen + 1; i <= last; ++i) {
-    if (int rc = run_generation(h, i)) return rc;
+  {
+    std::vector<gen_prog> gs(hs.size());
+    for (size_t r = 0; r < hs.size(); ++r) prog_slice_barrier(hs[r], gs[r]);
+    if (int rc = run_programs(hs, gs)) return rc;
   }
-  CK(cudaEventRecord(h->ev1, h->stream));
-  CK(cudaEventSynchronize(h->ev1));
-  float ms = 0;
-  CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-  h->loop_ms += ms;
+  long long last = hs[0]->gen + n_generations;
+  if (last > hs[0]->t) last = hs[0]->t;
+  for (hb_handle* h : hs) CK(cudaEventRecord(h->ev0, h->stream));
+  for (long long i = hs[0]->gen + 1; i <= last; ++i) {
+    std::vector<gen_prog> gs(hs.size());
+    for (size_t r = 0; r < hs.size(); ++r) if (int rc = build_generation(hs[r], i, gs[r])) return rc;
+    if (int rc = run_programs(hs, gs)) return rc;
+  }
+  {
+    std::vector<gen_prog> gs(hs.size());
+    for (size_t r = 0; r < hs.size(); ++r) prog_err_reduce(hs[r], gs[r]);
+    if (int rc = run_programs(hs, gs)) return rc;
+  }
+  int rc_all = HB_OK;
+  for (hb_handle* h : hs) {
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaEventSynchronize(h->ev1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->loop_ms += ms;
+    timing_note("run (slice)", ms * 1e-3);
+    const int rc = check_flags(h);
+    if (rc && !rc_all) rc_all = rc;
+  }
+  return rc_all;
+}
+
+int hb_run(hb_handle* h, int64_t n_generations, int64_t* done_total) {
+  if (!h) return HB_ERR_INVALID;
+  std::vector<hb_handle*> hs{h};
+  const int rc = run_slice(hs, n_generations);
   if (done_total) *done_total = h->gen;
-  timing_note("run (slice)", ms * 1e-3);
-  return check_flags(h);
+  return rc;
+}
+
+// ---- rank emulation on ONE device (testing hook; the driver's one-GPU test box exercises the sharded path with it) ----
+// n handles created with hb_comm_init(rank r, world n), HB_EXCHANGE_DELTA, after hb_set_initial: wires the peers' buffers
+// in-process (plain device pointers instead of CUDA IPC mappings) and moves all handles onto the first handle's stream.
+int hb_group_attach(hb_handle** hs, int n) {
+  if (!hs || n < 1 || n > 8) return HB_ERR_INVALID;
+  for (int r = 0; r < n; ++r) {
+    hb_handle* h = hs[r];
+    if (!h) return HB_ERR_INVALID;
+    if (!h->delta_mode || h->world != n || h->rank != r) return fail(h, HB_ERR_STATE, "hb_group_attach: handle %d must be rank %d of %d in HB_EXCHANGE_DELTA mode", r, r, n);
+    if (!h->have_initial) return fail(h, HB_ERR_STATE, "hb_group_attach must follow hb_set_initial");
+    if (h->device != hs[0]->device) return fail(h, HB_ERR_INVALID, "hb_group_attach: all handles must live on one device");
+    if (h->peers_ready) return fail(h, HB_ERR_STATE, "hb_group_attach: the handle is already attached");
+  }
+  cudaSetDevice(hs[0]->device);
+  for (int r = 0; r < n; ++r) {   // the uploads of hb_set_initial ran on the handles' own streams
+    hb_handle* h = hs[r];
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  for (int r = 0; r < n; ++r) {
+    hb_handle* h = hs[r];
+    h->group_member = true;
+    if (r > 0) { h->own_stream = h->stream; h->stream = hs[0]->stream; }
+    if (h->side) cudaStreamDestroy(h->side);
+    h->side = h->stream;                                   // one stream: the emulation is sequential by construction
+    for (int q = 0; q < n; ++q) { h->arena_peer[q] = hs[q]->arena; h->peerX[q] = (q == r) ? nullptr : hs[q]->X; }
+  }
+  for (int r = 0; r < n; ++r) if (int rc = complete_replicas(hs[r])) return rc;
+  for (int r = 0; r < n; ++r) hs[r]->peers_ready = true;
+  return HB_OK;
+}
+
+int hb_group_run(hb_handle** hs, int n, int64_t n_generations, int64_t* done_total) {
+  if (!hs || n < 1 || n > 8) return HB_ERR_INVALID;
+  std::vector<hb_handle*> v(hs, hs + n);
+  for (hb_handle* h : v) if (!h || !h->group_member) return h ? fail(h, HB_ERR_STATE, "hb_group_run: call hb_group_attach first") : HB_ERR_INVALID;
+  const int rc = run_slice(v, n_generations);
+  if (done_total) *done_total = v[0]->gen;
+  return rc;
 }
 
 int hb_sync(hb_handle* h) {
@@ -1260,7 +1594,7 @@ int hb_host_prefault(void* p, size_t bytes, int n_threads) {
   char* base = reinterpret_cast<char*>(p);
   std::vector<std::thread> th;
   for (int t = 0; t < nt; ++t)
-    th.emplace_back([=]() {
+    th.emplace_back([=]() -> int {
       const size_t lo = bytes / nt * t, hi = (t == nt - 1) ? bytes : bytes / nt * (t + 1);
       for (size_t o = lo; o < hi; o += 4096) reinterpret_cast<volatile char*>(base)[o] = 0;
     });
@@ -1353,9 +1687,15 @@ int hb_rstat(hb_handle* h, double* out_d) {
   cudaSetDevice(h->device);
   double* o = nullptr;
   CK(dalloc(&o, (size_t)h->d));
-  prof_scope ps(h, "K4");
-  if (int rc = rstat_population(h, h->ind_out, o)) { cudaFree(o); return rc; }   // collective on a sharded population
-  ps.done(2);
+  if (h->group_member && h->world > 1) { cudaFree(o); return fail(h, HB_ERR_UNSUPPORTED, "hb_rstat on a rank emulation: use check_convergence (the collective needs all ranks in lockstep)"); }
+  {
+    prof_scope ps(h, "K4");
+    gen_prog g;
+    prog_rstat_population(h, g, h->ind_out, o);   // collective on a sharded population
+    std::vector<hb_handle*> hs{h}; std::vector<gen_prog> gs{g};
+    if (int rc = run_programs(hs, gs)) { cudaFree(o); return rc; }
+    ps.done(0);
+  }
   CK(cudaMemcpyAsync(out_d, o, sizeof(double) * h->d, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   cudaFree(o);

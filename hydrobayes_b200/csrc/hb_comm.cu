@@ -90,7 +90,3 @@ int hb_nccl_allreduce_f64(hb_nccl* c, double* buf, size_t count, cudaStream_t st
 int hb_nccl_allreduce_u64(hb_nccl* c, unsigned long long* buf, size_t count, cudaStream_t st, std::string& err) {
   return check(g.AllReduce(buf, buf, count, ncclUint64, ncclSum, c->comm, st), "ncclAllReduce", err);
 }
-int hb_nccl_allreduce_u32_bor(hb_nccl* c, unsigned* buf, size_t count, cudaStream_t st, std::string& err) {
-  // error flags are small bit masks: max() of per-rank masks loses bits, so reduce each bit as a sum instead
-  return check(g.AllReduce(buf, buf, count, ncclUint32, ncclMax, c->comm, st), "ncclAllReduce", err);
-}

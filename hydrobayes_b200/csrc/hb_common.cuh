@@ -136,21 +136,40 @@ struct hb_fy {
   }
 };
 
-// bound_par, R/internals.R:89-113
+// bound_par, R/internals.R:89-113.  reflect / fold are R's literal while-loops for up to HB_BOUND_MAX_ITER passes (bit-identical
+// to the reference wherever the reference terminates in reasonable time: a proposal up to that many box widths outside);
+// beyond that the remaining whole periods are removed in closed form (fmod on the 2w period of reflect, w of fold) and the
+// loop finishes the job, so a gamma = 1 jump of an over-dispersed population cannot spin a kernel for 1e15 iterations.
+// A non-finite value (already flagged as HB_FLAG_PROP_NONFINITE by the caller) is returned unchanged: R's loop would never
+// end on it.  hb_set_bounds rejects min > max, and min == max for reflect / fold.
+#define HB_BOUND_MAX_ITER 1024
 __device__ __forceinline__ double hb_bound_par(double par, double mn, double mx, int handle) {
   double o = par;
   if (par < mn || par > mx) {
     if (handle == 1) {
       o = fmax(fmin(par, mx), mn);
-    } else if (handle == 2) {
-      while (o < mn || o > mx) {
-        if (o < mn) o = mn + fabs(mn - o);
-        if (o > mx) o = mx - fabs(mx - o);
-      }
-    } else if (handle == 3) {
-      while (o < mn || o > mx) {
-        if (o < mn) o = mx - fabs(mn - o);
-        if (o > mx) o = mn + fabs(mx - o);
+    } else if (handle == 2 || handle == 3) {
+      if (!(fabs(par) <= 1.7976931348623157e308)) return par;
+      const double w = mx - mn;
+      for (int pass = 0; pass < 2; ++pass) {
+        int it = 0;
+        if (handle == 2) {
+          while ((o < mn || o > mx) && it < HB_BOUND_MAX_ITER) {
+            if (o < mn) o = mn + fabs(mn - o);
+            if (o > mx) o = mx - fabs(mx - o);
+            ++it;
+          }
+        } else {
+          while ((o < mn || o > mx) && it < HB_BOUND_MAX_ITER) {
+            if (o < mn) o = mx - fabs(mn - o);
+            if (o > mx) o = mn + fabs(mx - o);
+            ++it;
+          }
+        }
+        if (!(o < mn || o > mx) || pass == 1) break;
+        // still outside after HB_BOUND_MAX_ITER passes: drop the whole periods, then let the loop finish
+        const double period = (handle == 2) ? 2.0 * w : w;
+        if (o > mx) o = mx + fmod(o - mx, period); else o = mn - fmod(mn - o, period);
       }
     }
   }

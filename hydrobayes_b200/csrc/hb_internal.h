@@ -45,20 +45,35 @@ struct hb_handle {
   const double* peer_ptr[2][8] = {};
   void* peer_opened[2][8] = {};
 
-  // HB_EXCHANGE_DELTA: every rank keeps a full replica of X; the accept kernel PUSHES the rows it accepted into the
-  // peers' replicas (posted NVLink stores).  Two flag barriers per generation order the pushes against the proposal
-  // kernel's reads: A = "my K1 of generation i has finished reading", B = "my pushes of generation i have landed".
+  // HB_EXCHANGE_DELTA (hb_delta.cu): every rank keeps a full replica of X.  The shard is processed in `pieces` pieces per
+  // generation; K3 appends the rows it accepted to this rank's delta log, a send kernel on the side stream ships every
+  // piece's log into the peers' arenas while the next piece computes, and an apply kernel folds all logs into the replica.
   bool delta_mode = false;
   bool initial_sharded = false;   // set_initial uploaded this rank's rows only; peer_import completes the replicas
-  double* peerX[8] = {};          // peer r's replica base (null for self)
+  double* peerX[8] = {};          // peer r's replica base (null for self); only used to complete the initial replicas
   void* peerX_opened[8] = {};
-  unsigned char* arena = nullptr; // [flags 256 B | reduce slot x2 | gather area]; flags = first 64 words
-  unsigned char* arena_peer[8] = {};
-  size_t arena_red_off = 0, arena_red_bytes = 0, arena_gather_off = 0;
-  unsigned red_seq = 0, gather_seq = 0;
-  unsigned* flags = nullptr;      // [4][8] local flag words, written by the peers: flags[which*8 + source rank]
-  unsigned* flags_peer[8] = {};   // peer r's flag array
-  void* flags_opened[8] = {};
+  unsigned char* arena = nullptr; // [flags | err slots | reduce slot x2 | gather area | delta boxes], see hb_kernels.h
+  unsigned char* arena_peer[8] = {};   // every rank's arena as mapped here (own entry = arena)
+  void* arena_opened[8] = {};
+  size_t arena_red_bytes = 0, arena_gather_off = 0, arena_box_off = 0;
+  size_t box_bytes = 0, box_idx_off = 0, box_rows_off = 0;
+  unsigned red_seq = 0, gather_seq = 0, err_seq = 0, slice_seq = 0;
+  int pieces = 1;                 // pieces per generation (1 unless delta_mode)
+  long long piece_n = 0;          // chains per piece (the last piece may be shorter)
+  int k3_blocks_piece = 0;        // partial-sum rows K3 writes per piece
+  bool wide = false;              // the shard is large enough for the large-population kernels (decided on n_local, not per piece)
+  int reserve_ctas = 0;           // CTAs the persistent proposal grid leaves free for the concurrent send kernel
+  int send_ctas = 0;
+  unsigned* log_ctr = nullptr;    // [2 parities][HB_MAX_PIECES] slot counters + [HB_MAX_PIECES] CTA completion counters
+  double* ibuf = nullptr;         // [update_interval][(2 + nCR) d] per-generation adaptation sums of the current interval
+  int islot = 0;
+  cudaStream_t side = nullptr;    // high-priority stream of the send kernels (== stream in a rank emulation)
+  cudaEvent_t ev_piece[HB_MAX_PIECES] = {};
+  cudaEvent_t ev_sent = nullptr;
+  unsigned long long* errbits_dev = nullptr;   // NCCL modes: error mask expanded to one word per bit for the sum all-reduce
+  // rank emulation on one device (hb_group_attach): the handles share one stream and reference each other's buffers
+  bool group_member = false;
+  cudaStream_t own_stream = nullptr;
 
   // MT-DREAM (mt > 1): candidate population and its scalars, multi-try sums, decisions
   double* ZT = nullptr; double* lp_zt = nullptr; double* ll_zt = nullptr; double* fx_zt = nullptr; int* id_zt = nullptr;
@@ -141,8 +156,8 @@ struct hb_handle {
 hb_k1_params hb_make_k1(hb_handle* h, long long i, long long first, long long stride, long long n_items);
 hb_k3_params hb_make_k3(hb_handle* h, long long i, long long first, long long stride, long long n_items, bool store,
                         bool in_adapt, bool write_dx);
-int hb_prior_after_k1(hb_handle* h, long long n_items);
-int hb_target_launch(hb_handle* h, const double* x, long long n, long long first, long long stride);
+int hb_prior_after_k1(hb_handle* h, long long n_items, long long off = 0);
+int hb_target_launch(hb_handle* h, const double* x, long long n, long long first, long long stride, long long off = 0);
 int hb_fail(hb_handle* h, int code, const char* msg);
 // hb_targets.cu: true when vt/ctx is the built-in t_distribution plugin; fills the operands of the fused kernel
 bool hb_tdist_fused_info(const hb_target_vtable* vt, void* ctx, hb_fused_tdist* out);
@@ -154,4 +169,3 @@ void hb_nccl_destroy(hb_nccl* c);
 int hb_nccl_allgather_f64(hb_nccl* c, const double* send, double* recv, size_t count, cudaStream_t st, std::string& err);
 int hb_nccl_allreduce_f64(hb_nccl* c, double* buf, size_t count, cudaStream_t st, std::string& err);
 int hb_nccl_allreduce_u64(hb_nccl* c, unsigned long long* buf, size_t count, cudaStream_t st, std::string& err);
-int hb_nccl_allreduce_u32_bor(hb_nccl* c, unsigned* buf, size_t count, cudaStream_t st, std::string& err);

@@ -679,12 +679,13 @@ __global__ void __launch_bounds__(K1_PAIR_WARPS * 32, 2) hb_k1_pair_kernel(const
   __syncwarp();
   unsigned it = 0;   // chains consumed by this warp so far: stage = it % STAGES, parity = (it / STAGES) & 1
 
-  for (long long base = warp_id * 32; base < p.n_local; base += n_warps * 32) {
+  const int B = p.batch;   // chains per batch: 32, or fewer when the launch has fewer 32-chain batches than resident warps
+  for (long long base = warp_id * B; base < p.n_local; base += n_warps * B) {
     k1_phase_a<false>(p, base, lane, n_src, heads, errbits);
     __syncwarp();
     double lp_mine = 0.0;
 
-    const int n_in_batch = (int)((p.n_local - base) < 32 ? (p.n_local - base) : 32);
+    const int n_in_batch = (int)((p.n_local - base) < B ? (p.n_local - base) : B);
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
 #pragma unroll
     for (int s = 0; s < K1_STAGES; ++s)
@@ -928,11 +929,12 @@ __global__ void __launch_bounds__(256, 2) hb_k1_tape_kernel(const hb_k1_params p
   __syncwarp();
   unsigned it = 0;
 
-  for (long long base = warp_id * 32; base < p.n_local; base += n_warps * 32) {
+  const int B = p.batch;
+  for (long long base = warp_id * B; base < p.n_local; base += n_warps * B) {
     k1_phase_a<true>(p, base, lane, n_src, heads, errbits);
     __syncwarp();
 
-    const int n_in_batch = (int)((p.n_local - base) < 32 ? (p.n_local - base) : 32);
+    const int n_in_batch = (int)((p.n_local - base) < B ? (p.n_local - base) : B);
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
 #pragma unroll
     for (int s = 0; s < K1_STAGES; ++s)
@@ -1099,7 +1101,7 @@ __global__ void __launch_bounds__(256, 2) hb_k1_tape_kernel(const hb_k1_params p
   if (errbits) atomicOr(p.err, errbits);
 }
 
-inline void k1_wide_geometry(const hb_k1_params& p, int sm_count, int max_warps, int* threads, long long* blocks, size_t* smem) {
+inline void k1_wide_geometry(hb_k1_params& p, int sm_count, int max_warps, int* threads, long long* blocks, size_t* smem) {
   const size_t per_warp = (k1_warp_smem_bytes(p.delta, p.ldx, p.past_sample) + 15) & ~(size_t)15;
   int warps = max_warps;                                               // two CTAs per SM
   while (warps > 1 && per_warp * warps * 2 + 4096 > 227 * 1024) warps = warps > 8 ? 8 : warps >> 1;
@@ -1108,16 +1110,23 @@ inline void k1_wide_geometry(const hb_k1_params& p, int sm_count, int max_warps,
   if (const char* e = getenv("HB_K1_CTAS")) ctas = atoi(e);
   *smem = per_warp * warps;
   *threads = warps * 32;
-  const long long warps_needed = (p.n_local + 31) / 32;
+  long long cap = (long long)sm_count * ctas - p.reserve_ctas;          // persistent: two CTAs per SM, grid-stride batches
+  if (cap < 1) cap = 1;
+  // a warp works through its batch chain by chain, so a launch with fewer 32-chain batches than resident warps (one piece
+  // of a multi-GPU shard) would leave warps idle for a whole batch time: halve the batch until the warps are covered
+  int B = 32;
+  while (B > 8 && (p.n_local + B - 1) / B < cap * warps) B >>= 1;
+  if (const char* e = getenv("HB_K1_BATCH")) B = atoi(e);
+  p.batch = B;
+  const long long warps_needed = (p.n_local + B - 1) / B;
   long long b = (warps_needed + warps - 1) / warps;
-  const long long cap = (long long)sm_count * ctas;                    // persistent: two CTAs per SM, grid-stride batches
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   *blocks = b;
 }
 
 template <int ITER>
-cudaError_t launch_wide_tape(const hb_k1_params& p, int sm_count, cudaStream_t st) {
+cudaError_t launch_wide_tape(hb_k1_params p, int sm_count, cudaStream_t st) {
   int threads; long long blocks; size_t smem;
   k1_wide_geometry(p, sm_count, 8, &threads, &blocks, &smem);
   if (smem > 220 * 1024) return cudaErrorInvalidValue;
@@ -1128,7 +1137,7 @@ cudaError_t launch_wide_tape(const hb_k1_params& p, int sm_count, cudaStream_t s
 }
 
 template <int ITER2>
-cudaError_t launch_wide_pair(const hb_k1_params& p, int sm_count, cudaStream_t st) {
+cudaError_t launch_wide_pair(hb_k1_params p, int sm_count, cudaStream_t st) {
   int threads; long long blocks; size_t smem;
   k1_wide_geometry(p, sm_count, K1_PAIR_WARPS, &threads, &blocks, &smem);
   if (smem > 220 * 1024) return cudaErrorInvalidValue;
@@ -1166,7 +1175,7 @@ cudaError_t hb_launch_k1(const hb_k1_params& p, bool tape_mode, int sm_count, cu
   if (p.nc > 0x7fffffffLL || p.m_arch > 0x7fffffffLL) return cudaErrorInvalidValue;
   // small populations (fewer 32-chain batches than resident warps): one chain per warp spreads the work over more SMs
   if (p.n_peers > 1 && d <= 16) return cudaErrorInvalidValue;   // peer gather is implemented in the wide kernel
-  if (p.n_peers <= 1 && !g_hb_force_wide && p.n_local < (long long)sm_count * 16 * 32 / 2) {
+  if (p.n_peers <= 1 && !g_hb_force_wide && !p.force_wide && p.n_local < (long long)sm_count * 16 * 32 / 2) {
     if (d <= 32) return launch_gi<32, 1>(p, tape_mode, sm_count, st);
     if (d <= 64) return launch_gi<32, 2>(p, tape_mode, sm_count, st);
     if (d <= 128) return launch_gi<32, 4>(p, tape_mode, sm_count, st);
@@ -1199,7 +1208,7 @@ bool hb_fused_small_eligible(long long n_local, int d, int sm_count) {
 cudaError_t hb_launch_fused_small(const hb_k1_params& p, const hb_k3_params& q, const hb_fused_tdist& td, bool tape_mode,
                                   int sm_count, cudaStream_t st) {
   if (!hb_fused_small_eligible(p.n_local, p.d, sm_count) || p.past_sample || p.n_peers > 1 || q.adapt || q.n_runs > 1 ||
-      q.accept_in || q.lik22 || q.n_push > 0 || q.Xout == q.X)
+      q.accept_in || q.lik22 || q.log_rows || q.Xout == q.X)
     return cudaErrorInvalidValue;
   if (p.d <= 32) return launch_fused<1>(p, q, td, tape_mode, sm_count, st);
   if (p.d <= 64) return launch_fused<2>(p, q, td, tape_mode, sm_count, st);

@@ -71,7 +71,11 @@ __global__ void __launch_bounds__(256) hb_k3_kernel(const hb_k3_params p) {
       accf = p.accept_in ? (int)p.accept_in[jl] : p.lik22 ? ((lpostx >= lpost_old) || (lpostx >= 0.0)) : (p_acc > log(u));   // :241 ; ABC rule :224 ; mt > 1: hb_mt.cu
       id = p.id[jl];
     }
-    if (G > 1) { accf = __shfl_sync(FULL, accf, gbase); id = __shfl_sync(FULL, id, gbase); }
+    int log_slot = -1;                                                // delta log: slot of this chain's accepted row
+    if (p.log_rows && valid && lg == 0 && accf) { log_slot = (int)atomicAdd(p.log_count, 1u); p.log_idx[log_slot] = (int)j; }
+    if (G > 1) { accf = __shfl_sync(FULL, accf, gbase); id = __shfl_sync(FULL, id, gbase); log_slot = __shfl_sync(FULL, log_slot, gbase); }
+    if (log_slot >= 0)                                                // the padding columns travel with the row: keep them finite
+      for (int k = d + lg; k < ldx; k += G) p.log_rows[(long long)log_slot * ldx + k] = 0.0;
 
     const bool copy_all = p.Xout != p.X;
     const bool need_x = adapt || p.hist_x != nullptr || copy_all;
@@ -87,8 +91,8 @@ __global__ void __launch_bounds__(256) hb_k3_kernel(const hb_k3_params p) {
             if (p.write_dx) p.XP_rw[jl * (long long)ldx + k] = dx;
             else acc[(2 + id) * d + k] += dx * dx;
           }
-          p.Xout[j * (long long)ldx + k] = xn;                        // :358
-          for (int r = 0; r < p.n_push; ++r) if (p.push[r]) p.push[r][j * (long long)ldx + k] = xn;
+          if (log_slot >= 0) p.log_rows[(long long)log_slot * ldx + k] = xn;   // :358 deferred: hb_delta_apply_kernel
+          else p.Xout[j * (long long)ldx + k] = xn;                   // :358
         } else {
           if (need_x) xn = p.X[j * (long long)ldx + k];
           if (copy_all) p.Xout[j * (long long)ldx + k] = xn;
@@ -253,6 +257,12 @@ __global__ void __launch_bounds__(256, 3) hb_k3_wide_kernel(const hb_k3_params p
     }
     const unsigned vmask = __ballot_sync(FULL, valid);
     const unsigned amask = __ballot_sync(FULL, valid && accf);
+    int log_base = 0;                                                 // delta log: popc(amask) consecutive slots for this batch
+    if (p.log_rows && amask) {
+      if (lane == 0) log_base = (int)atomicAdd(p.log_count, (unsigned)__popc(amask));
+      log_base = __shfl_sync(FULL, log_base, 0);
+      if (valid && accf) p.log_idx[log_base + __popc(amask & ((1u << lane) - 1u))] = (int)gj;
+    }
     if (p.n_runs == 1) {
       for (int q = 0; q < nCR; ++q) {                                 // n_id  :368-369
         const unsigned m_q = __ballot_sync(FULL, valid && id == q);
@@ -321,9 +331,8 @@ __global__ void __launch_bounds__(256, 3) hb_k3_wide_kernel(const hb_k3_params p
           }
         }
         if (a_c && lane == 0) {                                         // :358  xt[accept,] <- xp[accept,]
-          tma_store_1d(p.Xout + j * (long long)ldx, rowv, row_bytes);
-          for (int r = 0; r < p.n_push; ++r)
-            if (p.push[r]) tma_store_1d(p.push[r] + j * (long long)ldx, rowv, row_bytes);
+          if (p.log_rows) tma_store_1d(p.log_rows + (long long)(log_base + __popc(amask & ((1u << c) - 1u))) * ldx, rowv, row_bytes);
+          else tma_store_1d(p.Xout + j * (long long)ldx, rowv, row_bytes);
           tma_store_commit();
           stores_pending = true;
         }
@@ -448,7 +457,7 @@ cudaError_t dispatch(const hb_k3_params& p, int sm_count, int* nb, size_t* sm, c
   if (d <= 4) return launch_gi<4, 1>(p, sm_count, nb, sm, st);
   if (d <= 8) return launch_gi<8, 1>(p, sm_count, nb, sm, st);
   if (d <= 16) return launch_gi<16, 1>(p, sm_count, nb, sm, st);
-  if (!g_hb_force_wide && p.n_local < (long long)sm_count * 16 * 32 / 2) {   // small populations: one chain per warp (see hb_launch_k1)
+  if (!g_hb_force_wide && !p.force_wide && p.n_local < (long long)sm_count * 16 * 32 / 2) {   // small populations: one chain per warp (see hb_launch_k1)
     if (d <= 32) return launch_gi<32, 1>(p, sm_count, nb, sm, st);
     if (d <= 64) return launch_gi<32, 2>(p, sm_count, nb, sm, st);
     if (d <= 128) return launch_gi<32, 4>(p, sm_count, nb, sm, st);
@@ -480,15 +489,20 @@ __global__ void __launch_bounds__(256) hb_finalize_kernel(const hb_fin_params p)
   }
   if (p.phase == 0) return;
   __syncthreads();
-  if (p.adapt) {
+  // Multi-GPU: the per-generation sums of one updateInterval are parked in slots and all-reduced once (nothing between
+  // two pCR updates consumes J, n_id or std_x: R/dream_parallel.R:403-411); they are folded here in generation order.
+  const int n_slots = p.adapt ? (p.n_slots > 0 ? p.n_slots : 1) : 0;
+  for (int sl = 0; sl < n_slots; ++sl) {
+    const double* colsum = p.colsum + (size_t)sl * p.slot_stride;
+    const double* qsum = p.qsum + (size_t)sl * p.slot_stride;
     // var_k of the post-update population (n-1 denominator), R/dream_parallel.R:376
     const double n = (double)p.nc;
     for (int q = 0; q < nCR; ++q) {
       double part = 0.0;
       for (int k = threadIdx.x; k < d; k += blockDim.x) {
-        const double a = p.colsum[k], b = p.colsum[d + k];
+        const double a = colsum[k], b = colsum[d + k];
         const double var = (b - a * a / n) / (n - 1.0);
-        part += p.qsum[q * d + k] / var;                    // sum_j (dx_jk/std_k)^2 over chains with id == q
+        part += qsum[q * d + k] / var;                      // sum_j (dx_jk/std_k)^2 over chains with id == q
       }
       red[threadIdx.x] = part;
       __syncthreads();
@@ -499,7 +513,8 @@ __global__ void __launch_bounds__(256) hb_finalize_kernel(const hb_fin_params p)
       if (threadIdx.x == 0) c->J[q] += red[0];              // :377-378
       __syncthreads();
     }
-    for (int k = threadIdx.x; k < d; k += blockDim.x) p.shift[k] += p.colsum[k] / n;   // next generation's shift
+    // next generation's shift (the sums of every slot of an interval were taken against the same, interval-start shift)
+    if (sl == n_slots - 1) for (int k = threadIdx.x; k < d; k += blockDim.x) p.shift[k] += colsum[k] / n;
   }
   if (threadIdx.x == 0) {
     for (int q = 0; q < nCR; ++q) { c->n_id[q] += (double)c->n_id_gen[q]; c->n_id_gen[q] = 0ull; }   // :368-369
@@ -584,105 +599,6 @@ __global__ void hb_outlier_reset_peer_kernel(double* Xlocal, hb_peer_ptrs peers,
     const double v = lpost_src[srcc];
     lpost[dst - chain0] = v;
     if (hist_row) hist_row[dst - chain0] = v;
-  }
-}
-
-// HB_EXCHANGE_DELTA generation barriers: flag words in peer-mapped memory, value = generation number (monotonic, so
-// the flags never need resetting).  The signal kernel runs after the producing kernel in stream order, i.e. after all
-// of that kernel's (remote) stores were performed; the fence orders the flag store behind anything this thread saw.
-__global__ void hb_flag_signal_kernel(hb_flag_peers peers, int which, int self, int world, unsigned value) {
-  const int r = threadIdx.x;
-  if (r < world && r != self && peers.p[r]) {
-    __threadfence_system();
-    *reinterpret_cast<volatile unsigned*>(peers.p[r] + which * 8 + self) = value;
-  }
-}
-__global__ void hb_flag_wait_kernel(unsigned* flags, int which, int self, int world, unsigned value, unsigned* err) {
-  const int r = threadIdx.x;
-  if (r < world && r != self) {
-    const volatile unsigned* f = flags + which * 8 + r;
-    long long spins = 0;
-    while ((int)(*f - value) < 0) {
-      __nanosleep(64);
-      if (++spins > 40000000LL) { atomicOr(err, HB_FLAG_PEER_TIMEOUT); break; }   // ~ several seconds: a peer died
-    }
-    __threadfence_system();
-  }
-}
-
-// ---- small collectives over peer-mapped memory (HB_EXCHANGE_DELTA) ----------------------------------------------
-__device__ __forceinline__ void hb_flag_signal_all(hb_arena_peers peers, int which, int self, int world, unsigned value) {
-  const int r = threadIdx.x;
-  if (r < world && r != self && peers.p[r]) {
-    __threadfence_system();
-    *reinterpret_cast<volatile unsigned*>(reinterpret_cast<unsigned*>(peers.p[r]) + which * 8 + self) = value;
-  }
-}
-__device__ __forceinline__ void hb_flag_wait_all(const unsigned char* own, int which, int self, int world, unsigned value,
-                                                 unsigned* err) {
-  const int r = threadIdx.x;
-  if (r < world && r != self) {
-    const volatile unsigned* f = reinterpret_cast<const unsigned*>(own) + which * 8 + r;
-    long long spins = 0;
-    while ((int)(*f - value) < 0) {
-      __nanosleep(64);
-      if (++spins > 40000000LL) { atomicOr(err, HB_FLAG_PEER_TIMEOUT); break; }
-    }
-    __threadfence_system();
-  }
-}
-
-__global__ void hb_peer_allreduce_post_kernel(hb_arena_peers peers, size_t slot_off, hb_peer_reduce_desc d, int self,
-                                              int world, unsigned seq) {
-  double* slot = reinterpret_cast<double*>(peers.p[self] + slot_off);
-  int o = 0;
-  for (int v = 0; v < 2; ++v) { for (int e = threadIdx.x; e < d.n_f64[v]; e += blockDim.x) slot[o + e] = d.f64[v][e]; o += d.n_f64[v]; }
-  unsigned long long* us = reinterpret_cast<unsigned long long*>(slot + o);
-  for (int e = threadIdx.x; e < d.n_u64; e += blockDim.x) us[e] = d.u64[e];
-  __threadfence_system();
-  __syncthreads();
-  hb_flag_signal_all(peers, 2, self, world, seq);
-}
-__global__ void hb_peer_allreduce_finish_kernel(hb_arena_peers peers, size_t slot_off, hb_peer_reduce_desc d, int self,
-                                                int world, unsigned seq, unsigned* err) {
-  hb_flag_wait_all(peers.p[self], 2, self, world, seq, err);
-  __syncthreads();
-  int o = 0;
-  for (int v = 0; v < 2; ++v) {
-    for (int e = threadIdx.x; e < d.n_f64[v]; e += blockDim.x) {
-      double s = 0.0;
-      for (int r = 0; r < world; ++r) s += reinterpret_cast<const volatile double*>(peers.p[r] + slot_off)[o + e];   // rank order
-      d.f64[v][e] = s;
-    }
-    o += d.n_f64[v];
-  }
-  for (int e = threadIdx.x; e < d.n_u64; e += blockDim.x) {
-    unsigned long long s = 0;
-    for (int r = 0; r < world; ++r) s += reinterpret_cast<const volatile unsigned long long*>(peers.p[r] + slot_off + (size_t)o * 8)[e];
-    d.u64[e] = s;
-  }
-}
-
-__global__ void hb_peer_allgather_post_kernel(hb_arena_peers peers, size_t area_off, const double* a, const double* b,
-                                              long long n_local, int self, int world, unsigned seq, unsigned* done) {
-  double* area = reinterpret_cast<double*>(peers.p[self] + area_off);
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
-  for (long long e = tid; e < n_local; e += nt) { area[e] = a[e]; area[n_local + e] = b[e]; }
-  __threadfence_system();
-  __syncthreads();
-  __shared__ bool last;
-  if (threadIdx.x == 0) last = atomicAdd(done, 1u) == gridDim.x - 1;     // the last block signals
-  __syncthreads();
-  if (last) { if (threadIdx.x == 0) *done = 0; __threadfence_system(); hb_flag_signal_all(peers, 3, self, world, seq); }
-}
-__global__ void hb_peer_allgather_finish_kernel(hb_arena_peers peers, size_t area_off, double* full_a, double* full_b,
-                                                long long n_local, int self, int world, unsigned seq, unsigned* err) {
-  hb_flag_wait_all(peers.p[self], 3, self, world, seq, err);              // every block waits for itself
-  __syncthreads();
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
-  for (int r = 0; r < world; ++r) {
-    const volatile double* area = reinterpret_cast<const volatile double*>(peers.p[r] + area_off);
-    for (long long e = tid; e < n_local; e += nt) { full_a[r * n_local + e] = area[e]; full_b[r * n_local + e] = area[n_local + e]; }
   }
 }
 
@@ -797,9 +713,9 @@ __global__ void hb_chain_transpose_kernel(const double* __restrict__ hist_x, con
 
 }  // namespace
 
-int hb_k3_grid(long long n_local, int d, int nCR, int sm_count, size_t* smem_out) {
+int hb_k3_grid(long long n_local, int d, int nCR, int sm_count, int force_wide, size_t* smem_out) {
   hb_k3_params p{};
-  p.n_local = n_local; p.d = d; p.nCR = nCR; p.X = nullptr;
+  p.n_local = n_local; p.d = d; p.ldx = d == 1 ? 1 : (d + 3) & ~3; p.nCR = nCR; p.X = nullptr; p.force_wide = force_wide;
   int nb = 0;
   if (dispatch(p, sm_count, &nb, smem_out, nullptr) != cudaSuccess) return -1;
   return nb;
@@ -836,32 +752,6 @@ cudaError_t hb_launch_outlier_reset_peer(double* Xlocal, hb_peer_ptrs peers, lon
   if (n_out <= 0) return cudaSuccess;
   hb_outlier_reset_peer_kernel<<<n_out, 128, 0, st>>>(Xlocal, peers, peer_nl, ldx, d, lpost, lpost_hist_row, lpost_src,
                                                       chain0, n_local, outl, news, n_out);
-  return cudaGetLastError();
-}
-
-cudaError_t hb_launch_peer_allreduce(hb_arena_peers peers, size_t slot_off, hb_peer_reduce_desc desc, int self, int world,
-                                     unsigned seq, unsigned* err, cudaStream_t st) {
-  hb_peer_allreduce_post_kernel<<<1, 256, 0, st>>>(peers, slot_off, desc, self, world, seq);
-  hb_peer_allreduce_finish_kernel<<<1, 256, 0, st>>>(peers, slot_off, desc, self, world, seq, err);
-  return cudaGetLastError();
-}
-cudaError_t hb_launch_peer_allgather(hb_arena_peers peers, size_t area_off, const double* local_a, const double* local_b,
-                                     double* full_a, double* full_b, long long n_local, int self, int world, unsigned seq,
-                                     unsigned* err, cudaStream_t st) {
-  unsigned* done = reinterpret_cast<unsigned*>(peers.p[self]) + 63;       // last word of the flag block: block counter
-  const int blocks = (int)((n_local + 1023) / 1024 < 64 ? (n_local + 1023) / 1024 : 64);
-  hb_peer_allgather_post_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, st>>>(peers, area_off, local_a, local_b, n_local, self, world, seq, done);
-  hb_peer_allgather_finish_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, st>>>(peers, area_off, full_a, full_b, n_local, self, world, seq, err);
-  return cudaGetLastError();
-}
-
-cudaError_t hb_launch_flag_signal(hb_flag_peers peers, int which, int self, int world, unsigned value, cudaStream_t st) {
-  hb_flag_signal_kernel<<<1, 32, 0, st>>>(peers, which, self, world, value);
-  return cudaGetLastError();
-}
-cudaError_t hb_launch_flag_wait(unsigned* flags, int which, int self, int world, unsigned value, unsigned* err,
-                                cudaStream_t st) {
-  hb_flag_wait_kernel<<<1, 32, 0, st>>>(flags, which, self, world, value, err);
   return cudaGetLastError();
 }
 

@@ -52,6 +52,9 @@ struct hb_k1_params {
   const double* gamma_tab; // [delta][d]: 2.38/sqrt(2 D d*), built on the host with IEEE sqrt and division
   const double* peer[8];  // HB_EXCHANGE_PEER: rank r's shard (current buffer), chains [r*peer_nl, (r+1)*peer_nl)
   int n_peers; long long peer_nl;
+  int force_wide;         // host decision: use the large-population kernels (the launch may be one PIECE of a big shard)
+  int batch;              // wide kernels: chains a warp takes per batch (32, or 16 / 8 for pieces with fewer batches than warps)
+  int reserve_ctas;       // wide kernels: CTAs left out of the persistent grid (room for the concurrent send kernel)
   uint32_t ks[20];        // Philox round keys of `seed` (constant bank operands in the kernel)
   uint32_t thr16[HB_MAX_NCR];   // hb_rng_zt_threshold16(CR_q) = ceil(CR_q 2^16 - 0.5): exact integer form of zt < CR[id]
 };
@@ -109,8 +112,13 @@ struct hb_k3_params {
   long long state0;       // lp/ll/lpost/history arrays hold chains [state0, ...): index = chain - state0
   int d, ldx, nCR;
   int adapt;              // generation is inside the adaptation period: accumulate std / jump statistics
-  // HB_EXCHANGE_DELTA: accepted rows are also stored into the peers' replicas of X (NVLink posted writes); null = off
-  double* push[8]; int n_push;
+  // HB_EXCHANGE_DELTA (stage-and-apply): accepted rows are NOT written into X but appended to this rank's delta log
+  // (row data + chain index, slot taken from a device counter); hb_delta_send_kernel ships the log to every peer's inbox
+  // and hb_delta_apply_kernel copies all logs into the replica once every rank's proposals of the generation are done.
+  double* log_rows;       // [cap][ldx] or nullptr (= update X in place)
+  int* log_idx;           // [cap] chain index (within the handle) of every logged row
+  unsigned* log_count;    // device counter of the piece
+  int force_wide;         // host decision: use the large-population kernel (the launch may be one piece of a big shard)
   const uint8_t* accept_in;   // MT-DREAM: the decisions were taken by hb_mt_accept_kernel (nullptr otherwise)
   int lik22;              // lik == 22: deterministic ABC acceptance rule (R/internals.R:222-225), no uniform drawn
   int write_dx;           // per-run statistics path: overwrite XP[item] with the realised jump dx (0 if rejected)
@@ -120,7 +128,7 @@ struct hb_k3_params {
 };
 // returns the grid size used (partials rows) through *nblocks_out; query with p.X == nullptr to size buffers
 cudaError_t hb_launch_k3(const hb_k3_params& p, int sm_count, int* nblocks_out, size_t* smem_out, cudaStream_t st);
-int hb_k3_grid(long long n_local, int d, int nCR, int sm_count, size_t* smem_out);
+int hb_k3_grid(long long n_local, int d, int nCR, int sm_count, int force_wide, size_t* smem_out);
 
 // ---- finalize: fold partials into J / n_id / n_acc, refresh shift, pCR update, AR/CR rows ---------------
 struct hb_fin_params {
@@ -136,6 +144,8 @@ struct hb_fin_params {
   int do_arcr;            // i %% updateInterval == 0                  (R/dream_parallel.R:425-433)
   double* out_ar; double* out_cr; long long ar_rows;   // column-major [ar_rows,2] / [ar_rows,nCR+1]
   int phase;              // 0: reduce partials -> colsum/qsum ; 1: consume colsum/qsum ; 2: both (single GPU)
+  int n_slots;            // phase 1: number of per-generation (colsum, qsum) slots to fold, slot s at + s*slot_stride (0 = 1)
+  long long slot_stride;
   long long n_eval_inc;   // nc (all ranks)
 };
 cudaError_t hb_launch_finalize(const hb_fin_params& p, cudaStream_t st);
@@ -169,28 +179,73 @@ cudaError_t hb_launch_outlier_reset(double* X, int ldx, int d, double* lpost, do
                                     const double* lpost_src, long long chain0, long long n_local, const int* outl,
                                     const int* news, int n_out, cudaStream_t st);
 struct hb_peer_ptrs { const double* p[8]; };
-// HB_EXCHANGE_DELTA flag barriers over NVLink peer memory: signal = store `value` into flags[which*8 + self] of every
-// peer; wait = spin (bounded) until the local flags[which*8 + r] of every peer r reached `value`
-struct hb_flag_peers { unsigned* p[8]; };
-cudaError_t hb_launch_flag_signal(hb_flag_peers peers, int which, int self, int world, unsigned value, cudaStream_t st);
-cudaError_t hb_launch_flag_wait(unsigned* flags, int which, int self, int world, unsigned value, unsigned* err,
+// ---- HB_EXCHANGE_DELTA over peer-mapped memory (hb_delta.cu; no NCCL on this path) -----------------------------------
+// Every rank owns an "arena" that its peers map through CUDA IPC:
+//   [0, 256)     flags: 64 x u32, flags[which * 8 + source rank], monotonic values (never reset)
+//                which = 0 slice barrier, 1 delta pieces, 2 all-reduce, 3 all-gather, 4 error reduce; word 63 = block counter
+//   [256, 512)   error-reduce slots (two parities)
+//   reduce slots (two parities) | gather area | delta boxes [parity][source rank] (see hb_delta.cu)
+#define HB_MAX_PIECES 16
+#define HB_ARENA_ERR_OFF 256
+#define HB_ARENA_RED_OFF 512
+struct hb_arena_peers { unsigned char* p[8]; };
+unsigned long long hb_peer_timeout_ns();   // HB_PEER_TIMEOUT_S (default 120): wall-clock bound of every device-side wait
+// signal = store `value` into flags[which*8 + self] of every peer; wait = spin (bounded) until the local
+// flags[which*8 + r] of every peer r reached `value`
+cudaError_t hb_launch_flag_signal(hb_arena_peers peers, int which, int self, int world, unsigned value, cudaStream_t st);
+cudaError_t hb_launch_flag_wait(const unsigned char* own_arena, int which, int self, int world, unsigned value, unsigned* err,
                                 cudaStream_t st);
-// HB_EXCHANGE_DELTA small collectives over peer-mapped memory (no NCCL on this path).  Every rank owns an "arena"
-// [flags 64 x u32 | reduce slot parity 0 | reduce slot parity 1 | gather area] that its peers map through CUDA IPC.
+// small collectives, split into a POST and a FINISH launch (a rank emulation on one device runs every rank's post before
+// any finish; real ranks just launch them back to back):
 //   all-reduce: post = copy the local vectors into the own reduce slot, then signal flag 2; finish = wait for every
 //   peer's flag, then sum the slots of all ranks IN RANK ORDER (deterministic, identical on every rank).
-//   all-gather: post = copy the local array into the own gather area, signal flag 3; finish = wait, then read every
-//   peer's area into the full-length local array.
-struct hb_arena_peers { unsigned char* p[8]; };
+//   all-gather: post = copy the local arrays into the own gather area, signal flag 3; finish = wait, then read every
+//   peer's area into the full-length local arrays.
 struct hb_peer_reduce_desc {
-  double* f64[2]; int n_f64[2];           // two double vectors (colsum, qsum), summed as doubles
+  double* f64[2]; int n_f64[2];           // two double vectors, summed as doubles
   unsigned long long* u64; int n_u64;     // one integer vector (per-generation counters), summed as integers
 };
-cudaError_t hb_launch_peer_allreduce(hb_arena_peers peers, size_t slot_off, hb_peer_reduce_desc desc, int self, int world,
-                                     unsigned seq, unsigned* err, cudaStream_t st);
-cudaError_t hb_launch_peer_allgather(hb_arena_peers peers, size_t area_off, const double* local_a, const double* local_b,
-                                     double* full_a, double* full_b, long long n_local, int self, int world, unsigned seq,
-                                     unsigned* err, cudaStream_t st);
+cudaError_t hb_launch_peer_allreduce_post(hb_arena_peers peers, size_t slot_off, hb_peer_reduce_desc desc, int self, int world,
+                                          unsigned seq, cudaStream_t st);
+cudaError_t hb_launch_peer_allreduce_finish(hb_arena_peers peers, size_t slot_off, hb_peer_reduce_desc desc, int self, int world,
+                                            unsigned seq, unsigned* err, cudaStream_t st);
+cudaError_t hb_launch_peer_allgather_post(hb_arena_peers peers, size_t area_off, const double* local_a, const double* local_b,
+                                          long long n_local, int self, int world, unsigned seq, cudaStream_t st);
+cudaError_t hb_launch_peer_allgather_finish(hb_arena_peers peers, size_t area_off, double* full_a, double* full_b,
+                                            long long n_local, int self, int world, unsigned seq, unsigned* err, cudaStream_t st);
+// bitwise OR of the ranks' error words into every rank's control block (hb_run returns the same status everywhere)
+cudaError_t hb_launch_peer_err_post(hb_arena_peers peers, size_t slot_off, const unsigned* err, unsigned extra, int self, int world,
+                                    unsigned seq, cudaStream_t st);
+cudaError_t hb_launch_peer_err_finish(hb_arena_peers peers, size_t slot_off, unsigned* err, int self, int world, unsigned seq,
+                                      cudaStream_t st);
+// NCCL exchange modes: error mask <-> one word per bit (summed by ncclAllReduce)
+cudaError_t hb_launch_err_expand(const unsigned* err, unsigned extra, unsigned long long* bits16, cudaStream_t st);
+cudaError_t hb_launch_err_collapse(unsigned* err, const unsigned long long* bits16, cudaStream_t st);
+// delta log (stage-and-apply exchange of the accepted rows, see hb_delta.cu)
+struct hb_delta_send_params {
+  unsigned char* box[8];   // box (parity, self) inside every rank's arena; box[self] is local and holds the log K3 wrote
+  unsigned char* arena[8]; // every rank's arena base (flags)
+  size_t idx_off, rows_off;   // offsets of idx[cap] (i32) and rows[cap][ldx] (f64) inside a box; counts[HB_MAX_PIECES] at 0
+  long long piece_off;     // first log slot of the piece
+  int piece, ldx, self, world;
+  unsigned* log_count;     // device counter K3 allocated the piece's slots from (reset by the kernel)
+  unsigned* done_ctr;      // CTA completion counter (zero between launches)
+  unsigned flag_value;     // generation * HB_MAX_PIECES + piece + 1
+};
+cudaError_t hb_launch_delta_send(const hb_delta_send_params& p, int ctas, cudaStream_t st);
+struct hb_delta_apply_params {
+  const unsigned char* box[8];   // the LOCAL boxes (parity, r), r = 0..world-1
+  size_t idx_off, rows_off;
+  long long piece_cap;     // log slots per piece
+  int p0, p1;              // pieces [p0, p1)
+  int ldx, self, world;
+  long long nc;
+  double* X;               // this rank's replica
+  const unsigned* flags;   // own arena
+  unsigned flag_value;     // generation * HB_MAX_PIECES + p1: every peer has shipped its pieces < p1
+  unsigned* err; unsigned long long timeout_ns;
+};
+cudaError_t hb_launch_delta_apply(const hb_delta_apply_params& p, int sm_count, cudaStream_t st);
 cudaError_t hb_launch_outlier_reset_peer(double* Xlocal, hb_peer_ptrs peers, long long peer_nl, int ldx, int d,
                                          double* lpost, double* lpost_hist_row, const double* lpost_src,
                                          long long chain0, long long n_local, const int* outl, const int* news,

@@ -283,6 +283,52 @@ class Sampler:
                 "all_converged": bool((conv_gen > 0).all()), "R_stat_max": r}
 
 
+class GroupSampler:
+    """Rank emulation on ONE device (testing hook: ``hb_group_attach`` / ``hb_group_run``): ``world`` handles, rank r owning
+    chains [r*nc/world, (r+1)*nc/world), HB_EXCHANGE_DELTA, driven in lockstep on one stream.  The kernels and the arena
+    protocol are those of ``world`` processes on ``world`` GPUs; a one-GPU box uses it to check that the shards of a
+    sharded run equal the single-GPU run bit for bit."""
+
+    def __init__(self, cfg: A.HbConfig, world: int, device: int = 0, configure=None):
+        self.world = world
+        self.ranks = []
+        for r in range(world):
+            c = A.HbConfig.from_buffer_copy(bytes(cfg))
+            c.exchange = A.HB_EXCHANGE_DELTA
+            s = Sampler(c, device)
+            if configure is not None:
+                configure(s)
+            s.comm_init(r, world, None)
+            self.ranks.append(s)
+        self.L = A.lib()
+        self._arr = (C.c_void_p * world)(*[s.h for s in self.ranks])
+
+    def set_initial(self, x0):
+        for s in self.ranks:
+            s.set_initial(x0)
+        rc = self.L.hb_group_attach(self._arr, self.world)
+        if rc != A.HB_OK:
+            raise A.HbError(rc, "; ".join(self.L.hb_last_error(s.h).decode() for s in self.ranks))
+
+    def run(self, n_generations: int) -> int:
+        done = C.c_int64()
+        rc = self.L.hb_group_run(self._arr, self.world, int(n_generations), C.byref(done))
+        if rc != A.HB_OK:
+            raise A.HbError(rc, "; ".join(self.L.hb_last_error(s.h).decode() for s in self.ranks))
+        return done.value
+
+    def close(self):
+        for s in self.ranks:
+            s.close()
+        self.ranks = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
 # ---------------------------------------------------------------------------------------------------------
 # prior_sample (R/internals.R:26-47) stays on the host, exactly as it would in the R driver
 # ---------------------------------------------------------------------------------------------------------

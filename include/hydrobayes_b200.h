@@ -62,9 +62,11 @@ enum { HB_RNG_TAPE = 0, HB_RNG_PHILOX = 1 };
 /* multi-GPU chain-state exchange */
 enum { HB_EXCHANGE_ALLGATHER = 0 /* ncclAllGather of the shard's rows */,
        HB_EXCHANGE_PEER = 1      /* proposal kernel gathers partner rows through NVLink peer pointers */,
-       HB_EXCHANGE_DELTA = 2     /* only ACCEPTED rows travel: every rank keeps a full replica and its accept kernel
-                                    stores the rows it accepted into the peers' replicas (posted NVLink writes), two
-                                    flag barriers per generation (traffic x acceptance rate) */ };
+       HB_EXCHANGE_DELTA = 2     /* only ACCEPTED rows travel: every rank keeps a full replica; the accept kernel appends
+                                    the rows it accepted to a delta log, a send kernel ships the log of one piece of the
+                                    shard into the peers' arenas over NVLink (posted stores) while the next piece
+                                    computes, an apply kernel folds all logs into the replica (traffic x acceptance
+                                    rate, no barrier between proposals and exchange) */ };
 
 /*
  * Mirrors the formals of dream() (R/dream.R:126-133) and dream_parallel()
@@ -208,6 +210,14 @@ int hb_comm_init(hb_handle* h, int rank, int world, const void* id128);
  * them from all ranks (world*128 bytes, rank order) and hands them to hb_peer_import. */
 int hb_peer_export(hb_handle* h, void* out128);
 int hb_peer_import(hb_handle* h, const void* all_handles);
+
+/* Testing hook -- rank emulation on ONE device: hs[r] is rank r of n (hb_comm_init(hs[r], r, n, NULL), HB_EXCHANGE_DELTA,
+ * hb_set_initial done).  hb_group_attach wires the handles to each other in-process (plain device pointers where real ranks
+ * use CUDA IPC mappings) and puts them on one stream; hb_group_run drives them in lockstep: the same kernels and the same
+ * arena protocol as n processes on n GPUs, with every rank's signalling step enqueued before any rank's waiting step, so
+ * a one-GPU box can check that the shards of a sharded run equal the single-GPU run bit for bit. */
+int hb_group_attach(hb_handle** hs, int n);
+int hb_group_run(hb_handle** hs, int n, int64_t n_generations, int64_t* generations_done_total);
 
 /* Runs up to n_generations further generations (resumable slices: the R driver ticks its progress bar and polls
  * interrupts between slices).  The first call also evaluates the initial population (R/dream_parallel.R:215-250). */

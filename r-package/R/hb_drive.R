@@ -34,6 +34,9 @@
   .Call(hbR_set_target, h, fun, if (length(dots)) as.numeric(dots[[1]]) else NULL)   # get(fun)(x, ...) :219
   n0 <- if (past_sample) (if (is.null(m0)) 10 * d else m0) else nc   # :168-171
   z <- prior_sample(par.info, d, n0)                                 # unchanged R/internals.R:26-47
+  z <- as.matrix(z); storage.mode(z) <- "double"                     # the glue reads n0 * d doubles: check before handing over
+  if (nrow(z) != n0 || ncol(z) != d)
+    stop("initial sample has dimension ", nrow(z), " x ", ncol(z), ", expected ", n0, " x ", d, " (par.info$val_ini)")
   .Call(hbR_set_initial, h, z)
 
   dims <- .Call(hbR_out_dims, h)                                     # out_t, AR rows/cols, CR rows/cols, fx_m, R_stat rows
@@ -50,7 +53,7 @@
   }
   if (verbose) close(pb)
 
-  .Call(hbR_fetch_chain, h, chain)
+  chain <- .Call(hbR_fetch_chain, h, chain)                          # the glue fills and returns the array (no reliance on in-place mutation)
   out_AR <- .Call(hbR_fetch_ar, h, matrix(NA_real_, dims[2], dims[3]))
   out_CR <- .Call(hbR_fetch_cr, h, matrix(NA_real_, dims[4], dims[5]))
   if (sweep == 0L) colnames(out_AR) <- c("n_eval", "accepted")       # R/dream_parallel.R:205

@@ -84,7 +84,11 @@ SEXP hbR_set_target(SEXP p, SEXP fun, SEXP data) {   /* get(fun)(x, ...) -> name
   return R_NilValue;
 }
 SEXP hbR_target_registered(SEXP fun) { return ScalarLogical(hb_target_registered(CHAR(STRING_ELT(fun, 0)))); }
-SEXP hbR_set_initial(SEXP p, SEXP x0) { chk(H(p), hb_set_initial(H(p), REAL(x0))); return R_NilValue; }  /* R matrices are column-major */
+SEXP hbR_set_initial(SEXP p, SEXP x0) {             /* R matrices are column-major; the driver has checked dim(x0) == c(n0, d) */
+  if (TYPEOF(x0) != REALSXP) error("hbR_set_initial: x0 must be a double matrix");
+  chk(H(p), hb_set_initial(H(p), REAL(x0)));
+  return R_NilValue;
+}
 SEXP hbR_run(SEXP p, SEXP n) {                      /* one slice; the R driver ticks txtProgressBar between slices */
   int64_t done = 0;
   chk(H(p), hb_run(H(p), (int64_t)asReal(n), &done));

@@ -30,6 +30,7 @@ int* LOGICAL(SEXP x);
 int length(SEXP x);
 R_xlen_t XLENGTH(SEXP x);
 int isNull(SEXP x);
+int TYPEOF(SEXP x);
 SEXP STRING_ELT(SEXP x, R_xlen_t i);
 void SET_STRING_ELT(SEXP x, R_xlen_t i, SEXP v);
 SEXP VECTOR_ELT(SEXP x, R_xlen_t i);

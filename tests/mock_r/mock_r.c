@@ -56,6 +56,7 @@ int* LOGICAL(SEXP x) { want(x, LGLSXP, "LOGICAL"); return (int*)x->data; }
 int length(SEXP x) { return (int)x->n; }
 R_xlen_t XLENGTH(SEXP x) { return x->n; }
 int isNull(SEXP x) { return x->type == NILSXP; }
+int TYPEOF(SEXP x) { return x->type; }
 static void bounds(SEXP x, R_xlen_t i) { if (i < 0 || i >= x->n) Rf_error("subscript out of bounds"); }
 SEXP STRING_ELT(SEXP x, R_xlen_t i) { want(x, STRSXP, "STRING_ELT"); bounds(x, i); return ((SEXP*)x->data)[i]; }
 void SET_STRING_ELT(SEXP x, R_xlen_t i, SEXP v) { want(x, STRSXP, "SET_STRING_ELT"); bounds(x, i); ((SEXP*)x->data)[i] = v; }
