@@ -168,6 +168,57 @@ def make_sampler(w, local, rank, world, torch):
     return s
 
 
+def sharded_check(local, rank, world, torch, nc=1 << 16, d=100, gens=30):
+    """N > 1, before the timed region: `gens` generations of a 2^16-chain population (adaptation statistics, outlier check
+    and the chain-state exchange all active) run SHARDED over the ranks and, on every rank's own GPU, alone; the shard must
+    equal the same chains of the single-GPU run bit for bit (chain, accept/reject record, final state), in every
+    exchange mode.  A mismatch fails the whole bench run."""
+    import helpers as H
+    import torch.distributed as dist
+    from hydrobayes_b200 import Sampler, _abi as A, lib
+    x0 = H.x0_tdist(nc, d); x0[5] = 300.0; x0[nc - 3] = -250.0        # outlier resets across shard borders
+    base = A.default_config(nc=nc, t=gens + 1, d=d, lik=2, seed=77, adapt=0.7, thin=5, record_accept=1)
+    nl = nc // world
+
+    def run_one(cfg, shard):
+        with Sampler(cfg, local) as s:
+            s.set_target("t_distribution")
+            if shard:
+                uid = None
+                if cfg.exchange != A.HB_EXCHANGE_DELTA:
+                    import ctypes as C
+                    buf = C.create_string_buffer(128)
+                    if rank == 0:
+                        assert lib().hb_comm_unique_id(buf) == 0
+                    obj = [bytes(buf.raw)]
+                    dist.broadcast_object_list(obj, src=0)
+                    uid = obj[0]
+                s.comm_init(rank, world, uid)
+            s.set_initial(x0)
+            if shard and cfg.exchange in (A.HB_EXCHANGE_PEER, A.HB_EXCHANGE_DELTA):
+                s.peer_setup(world)
+            s.run(gens)
+            n = nl if shard else None
+            chain = s.fetch_chain(n); acc = s.fetch_accept(n)
+            xt, _, _, lpost = s.fetch_state(n)
+            return chain, acc, xt, lpost, s.fetch_outliers()
+
+    full = run_one(H.copy_cfg(base), False)
+    lo = rank * nl
+    modes = {"delta": A.HB_EXCHANGE_DELTA, "allgather": A.HB_EXCHANGE_ALLGATHER}
+    res = {}
+    for name, mode in modes.items():
+        sh = run_one(H.copy_cfg(base, exchange=mode), True)
+        same = (np.array_equal(sh[0], full[0][:, :, lo:lo + nl], equal_nan=True) and np.array_equal(sh[1], full[1][:, lo:lo + nl])
+                and np.array_equal(sh[2], full[2]) and np.array_equal(sh[3], full[3][lo:lo + nl]) and sh[4] == full[4])
+        t = torch.tensor([1.0 if same else 0.0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        res[name] = bool(t.item() == 1.0)
+    return {"bit_identical": all(res.values()), "modes": sorted(res), "per_mode": res, "chains": nc, "d": d, "generations": gens,
+            "outlier_resets": len(full[4]), "acceptance_rate": float(full[1].mean()),
+            "what": "every rank compares its shard of the sharded run with the same chains of a single-GPU run on its own GPU"}
+
+
 def roofline_for(kname, per_launch_ms, n_local, vt_work, peaks, dmma_peak, acc_rate=0.16):
     """algorithmic bytes/flops per chain-generation x chains per launch / launch duration"""
     d = 100
@@ -187,6 +238,56 @@ def roofline_for(kname, per_launch_ms, n_local, vt_work, peaks, dmma_peak, acc_r
     a = flops / (per_launch_ms * 1e-3) / 1e12
     return {"kernel": "K2 log-density plugin", "bound": "tensor", "achieved": a, "peak": dmma_peak, "unit": "TFLOP/s",
             "frac": a / dmma_peak if dmma_peak else None, "peak_source": "fp64 DMMA micro-benchmark hb_fp64_peaks() on this box"}
+
+
+NVLINK_PEER_GBS = 770.0   # measured peer-copy bandwidth per direction on this pool (B200_PROFILING.md); nominal 900
+
+
+def exchange_roofline(xchg_ms_per_launch, launches_per_generation, n_local, world, d, acc_rate):
+    """HB_EXCHANGE_DELTA: every accepted row (ldx doubles + a 4-byte chain index) is stored once into each of the G - 1
+    peers by the send kernels; `achieved` is that egress over the send kernels' own device time (they run on a side
+    stream concurrently with the next piece's proposal / density / accept kernels)."""
+    ldx = d if d == 1 else (d + 3) // 4 * 4
+    bytes_gen = acc_rate * n_local * (8 * ldx + 4) * (world - 1)
+    ms_gen = xchg_ms_per_launch * launches_per_generation
+    a = bytes_gen / (ms_gen * 1e-3) / 1e9
+    return {"kernel": "hb_delta_send_kernel (accepted rows -> every peer's arena, posted NVLink stores)", "bound": "nvlink",
+            "achieved": a, "peak": NVLINK_PEER_GBS, "unit": "GB/s", "frac": a / NVLINK_PEER_GBS,
+            "peak_source": "measured peer copy per direction, B200_PROFILING.md (nominal 900)",
+            "bytes_pushed_per_generation": bytes_gen, "bytes_pushed_per_launch": bytes_gen / launches_per_generation,
+            "send_launches_per_generation": launches_per_generation, "ms_per_generation_in_send_kernels": ms_gen,
+            "ingress_bytes_per_generation": bytes_gen, "acceptance_rate": acc_rate}
+
+
+def rscript_probe():
+    """is the reference's own runtime on this box?"""
+    import shutil
+    p = shutil.which("Rscript")
+    if not p:
+        return "absent on GPU box (no Rscript on PATH): the reference cannot be executed, CPU baseline is the restated oracle"
+    try:
+        v = subprocess.run([p, "--version"], capture_output=True, text=True, timeout=20)
+        return f"present: {p} ({(v.stdout + v.stderr).strip().splitlines()[0]})"
+    except Exception as e:
+        return f"present: {p} (version query failed: {e!r})"
+
+
+def dgemm_cublas_tflops(torch, n=8192, reps=3):
+    """cuBLAS DGEMM n^3 through torch.matmul (fp64): an independent anchor for the fp64 tensor-pipe denominator next to the
+    library's own DMMA micro-benchmark.  Measurement only -- nothing on the product path calls cuBLAS."""
+    try:
+        a = torch.randn(n, n, dtype=torch.float64, device="cuda"); b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+        torch.matmul(a, b); torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(reps):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        del a, b
+        torch.cuda.empty_cache()
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    except Exception:
+        return None
 
 
 def load_peaks():
@@ -246,7 +347,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": loop / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["desc"], "generations_per_step": GENS_PER_STEP},
+        "config": {"workload": w["desc"], "generations_per_step": GENS_PER_STEP, "chains": nc_s, "d": cfg.d,
+                   "chains_of_the_workload": cfg.nc, "same_config": nc_s == cfg.nc,
+                   "note": "bounded sample: the CPU state fits its caches, which favours the CPU arm"},
+        "rscript": rscript_probe(),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -331,6 +435,37 @@ def convergence_c5(local, torch, n_runs=4096, nc=10, T=3653, t=3000, rank=0, wor
             "rule": "max_k R_stat_k < 1.2 at 3 consecutive checks, every 10 stored generations from ind_out > 50"}
 
 
+def convergence_population(name, local, rank, world, torch, t_cap, thin, check_every):
+    """BASELINE metric 2 for one population (C2 on one GPU, C4 on N GPUs): wall seconds of dream_parallel's generation loop
+    until max_k R_stat_k < 1.2 held at 3 consecutive checks of the stored (thinned) chain (R/gelman_rubin.R:21-56 on
+    chain[1:ind_out, 1:d, ], as R/dream_test.R:344), checked every `check_every` stored generations from ind_out > 50
+    (R/dream.R:270).  On a sharded population R_stat is the collective hb_rstat (per-chain statistics of the shards,
+    two small all-reduces): every rank takes the same decisions."""
+    import helpers as H
+    w = workload(name)
+    cfg = H.copy_cfg(w["cfg"], t=t_cap, thin=thin)
+    if world > 1:
+        cfg.exchange = 2
+    w = dict(w, cfg=cfg)
+    s = make_sampler(w, local, rank, world, torch)
+    try:
+        barrier_sync(torch, world)
+        t0 = time.perf_counter()
+        res = s.run_to_convergence(threshold=1.2, check_every=check_every, hold=3)
+        barrier_sync(torch, world)
+        seconds = max_over_ranks(torch, world, time.perf_counter() - t0)
+        ms, launches = s.timing()
+    finally:
+        s.close()
+    conv = int(res["converged_at"][0])
+    return {"workload": w["desc"] + f" (t <= {t_cap}, thin = {thin}" + (f", sharded over {world} GPUs, delta exchange)" if world > 1 else ")"),
+            "seconds_to_rhat_below_1.2": seconds if conv > 0 else None, "converged": conv > 0, "converged_at_generation": conv or None,
+            "generations_run": res["generations"], "seconds_run": seconds, "R_stat_max_last": None if res["R_stat_max"] is None else float(res["R_stat_max"][0]),
+            "rstat_checks": res["checks"], "seconds_in_rstat_checks": res["check_seconds"], "device_loop_seconds": ms * 1e-3,
+            "value": cfg.nc * (res["generations"] - 1) / seconds, "unit": UNIT, "gpu_launches": launches,
+            "rule": f"max_k R_stat_k < 1.2 at 3 consecutive checks, every {check_every} stored generations (thin {thin}) from ind_out > 50"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -360,6 +495,14 @@ def main():
     need = (args.steps + args.warmup + (0 if args.no_extras else 2)) * GENS_PER_STEP + 1   # + the profiled generations
     if need > cfg.t:
         cfg.t = need
+    sharded = None
+    if world > 1 and not args.no_extras:
+        sharded = sharded_check(local, rank, world, torch)
+        if not sharded["bit_identical"]:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "value": None, "unit": UNIT, "n_gpus": world, "sharded_check": sharded,
+                                  "error": "a shard of the sharded run differs from the single-GPU run: no number is reported"}))
+            sys.exit(1)
     s = make_sampler(w, local, rank, world, torch)
     n_local = cfg.nc // world
 
@@ -388,7 +531,7 @@ def main():
         s.profile(True)
         s.run(2 * GENS_PER_STEP)
         s.profile(False)
-        for k in ("K1", "K2", "K3", "FIN", "XCHG", "OUTLIER"):
+        for k in ("K1", "K2", "K3", "FIN", "XCHG", "APPLY", "OUTLIER"):
             ms, n = s.kernel_ms(k)
             if n:
                 kernels[k] = {"ms_per_launch": ms / n, "launches": n}
@@ -406,8 +549,10 @@ def main():
             "config": {"workload": w["desc"], "generations_per_step": GENS_PER_STEP, "chains": cfg.nc, "d": cfg.d,
                        "chains_per_gpu": n_local, "rng": "philox4x32-10", "l2": "inputs larger than L2 (no flush)"
                        if cfg.nc * cfg.d * 8 > 126e6 else "state is L2-resident by construction (latency-bound config)",
-                       "exchange": ("none" if world == 1 else "delta: full replica per GPU, accepted rows pushed into the peers' replicas over NVLink (posted stores in the accept kernel) + two flag barriers per generation" if cfg.exchange == 2 else "peer gather over NVLink (bulk TMA reads of partner rows) + 17-word all-reduce per generation" if cfg.exchange == 1 else "ncclAllGather per generation")},
-            "gpu_launches": l1 - l0}
+                       "exchange": ("none" if world == 1 else "delta (stage-and-apply): full replica per GPU; accepted rows go to a delta log, a send kernel on a side stream stores each piece's log into every peer's arena over NVLink while the next piece computes, an apply kernel folds all logs into the replica; adaptation sums all-reduced once per updateInterval" if cfg.exchange == 2 else "peer gather over NVLink (bulk TMA reads of partner rows) + 17-word all-reduce per generation" if cfg.exchange == 1 else "ncclAllGather per generation")},
+            "gpu_launches": l1 - l0, "rscript": rscript_probe()}
+    if sharded is not None:
+        line["sharded_check"] = sharded
     if rank == 0 and not args.no_extras:
         peaks = load_peaks()
         import ctypes as C
@@ -416,16 +561,35 @@ def main():
         flops = {"t_distribution": (cfg.d * cfg.d + 3.0 * cfg.d,), "HydroModel": (5.0 * 3653,), "mixture": (40.0,)}[w["target"]]
         if kernels:
             dom = max(("K1", "K2", "K3"), key=lambda k: kernels.get(k, {"ms_per_launch": 0})["ms_per_launch"])
-            roof = roofline_for(dom, kernels[dom]["ms_per_launch"], n_local, flops, peaks, dm.value, acc_rate)
+            pieces = max(1, round(kernels["K1"]["launches"] / (2 * GENS_PER_STEP))) if "K1" in kernels else 1
+            chains_per_launch = n_local / pieces
+            roof = roofline_for(dom, kernels[dom]["ms_per_launch"], chains_per_launch, flops, peaks, dm.value, acc_rate)
+            # DRAM traffic of the dominant kernel is NOT measured inside this run (that needs ncu): at N = 1 the figure of
+            # the committed ncu capture of the same kernel on the same workload is quoted and labelled; never at N > 1,
+            # where a launch covers a different number of chains
             roof["traffic"] = None
             prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-            if os.path.exists(prof):
-                roof["traffic"] = json.load(open(prof)).get(dom)
-            roof["all_kernels"] = {k: roofline_for(k, kernels[k]["ms_per_launch"], n_local, flops, peaks, dm.value, acc_rate)
+            if world == 1 and args.workload == "C4" and os.path.exists(prof):
+                pj = json.load(open(prof))
+                roof["traffic"] = pj.get(dom)
+                roof["traffic_source"] = f"not measured in this run: {pj.get('_source', 'profiles/ncu_traffic.json')} (N = 1, {cfg.nc} chains per launch)"
+            roof["all_kernels"] = {k: roofline_for(k, kernels[k]["ms_per_launch"], chains_per_launch, flops, peaks, dm.value, acc_rate)
                                    for k in ("K1", "K2", "K3") if k in kernels}
             roof["kernel_ms_per_launch"] = {k: v["ms_per_launch"] for k, v in kernels.items()}
-            roof["fp64_peaks_measured_tflops"] = {"dmma": dm.value, "dfma": df.value}
+            roof["launches_per_generation"] = {k: v["launches"] / (2 * GENS_PER_STEP) for k, v in kernels.items()}
+            roof["chains_per_launch"] = chains_per_launch
+            dg = dgemm_cublas_tflops(torch)
+            roof["fp64_peaks_measured_tflops"] = {"dmma": dm.value, "dfma": df.value, "dgemm_cublas_tflops": dg,
+                                                  "note": "dmma / dfma: the library's micro-benchmarks; dgemm_cublas: torch.matmul fp64 8192^3 (measurement only)"}
+            if dg and "K2" in roof["all_kernels"]:
+                roof["all_kernels"]["K2"]["frac_of_cublas_dgemm"] = roof["all_kernels"]["K2"]["achieved"] / dg
             roof["acceptance_rate"] = acc_rate
+            if world > 1 and cfg.exchange == 2 and "XCHG" in kernels:
+                roof["exchange"] = exchange_roofline(kernels["XCHG"]["ms_per_launch"], kernels["XCHG"]["launches"] / (2 * GENS_PER_STEP),
+                                                     n_local, world, cfg.d, acc_rate)
+                gen_ms = wall / gens * 1e3
+                roof["exchange"]["frac_of_generation_time_if_not_overlapped"] = roof["exchange"]["ms_per_generation_in_send_kernels"] / gen_ms
+                roof["generation_ms"] = gen_ms
         line["roofline"] = roof
         line["clocks"] = clk
     if not args.no_extras and not args.quick:
@@ -460,8 +624,12 @@ def main():
             c5 = convergence_c5(local, torch, rank=rank, world=world)
         except Exception as e:  # report, never hide
             c5 = {"error": repr(e)}
+        try:   # BASELINE metric 2 on the sharded C4 population (collective R_stat)
+            c4m2 = convergence_population("C4", local, rank, world, torch, t_cap=8001, thin=100, check_every=5)
+        except Exception as e:
+            c4m2 = {"error": repr(e)}
         if rank == 0:
-            line["other_workloads"] = {"C5": c5}
+            line["other_workloads"] = {"C5": c5, "C4_seconds_to_rhat": c4m2}
     if rank == 0 and world == 1 and not args.no_extras and not args.quick:
         cb, _ = cpu_baseline(w)
         line["cpu_baseline"] = cb
@@ -489,6 +657,13 @@ def main():
             others["C5"] = convergence_c5(local, torch)
         except Exception as e:
             others["C5"] = {"error": repr(e)}
+        for key, args_m2 in (("C2_seconds_to_rhat", dict(name="C2", t_cap=20000, thin=10, check_every=10)),
+                             ("C4_seconds_to_rhat", dict(name="C4", t_cap=8001, thin=100, check_every=5))):
+            try:   # BASELINE metric 2 (seconds to R-hat < 1.2) for the single-population configs
+                lib().hb_wait_idle()
+                others[key] = convergence_population(local=local, rank=0, world=1, torch=torch, **args_m2)
+            except Exception as e:
+                others[key] = {"error": repr(e)}
         line["other_workloads"] = others
     if rank == 0:
         print(json.dumps(line))

@@ -1,8 +1,11 @@
 // hb_api.cu -- the C ABI (include/hydrobayes_b200.h): handle life cycle, the generation loop of the synchronous
 // sweep (R/dream_parallel.R:257-435 as K1 -> K2 plugin -> K3 -> finalize [-> exchange] [-> outlier check]),
 // result fetch in R's layouts, and the stand-alone entry points.
+#include <execinfo.h>
 #include <math.h>
+#include <signal.h>
 #include <stdarg.h>
+#include <unistd.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -28,6 +31,28 @@ int hb_hydro_init_batched(void** ctx, int d, int lik, const double* data, int64_
                           long long n_runs, double glue_shape, char* err, int errlen);
 
 namespace {
+
+// HB_BACKTRACE=1: print the native stack on SIGSEGV / SIGABRT (debugging aid; the offsets resolve with addr2line -e <.so>)
+void hb_crash_handler(int sig) {
+  const char msg[] = "[hb] fatal signal, native backtrace:\n";
+  if (write(2, msg, sizeof msg - 1) < 0) {}
+  void* frames[64];
+  const int n = backtrace(frames, 64);
+  backtrace_symbols_fd(frames, n, 2);
+  signal(sig, SIG_DFL);
+  raise(sig);
+}
+struct hb_crash_init {
+  hb_crash_init() {
+    const char* e = getenv("HB_BACKTRACE");
+    if (!(e && e[0] == '1')) return;
+    void* warm[4]; backtrace(warm, 4);            // loads libgcc now, not inside the handler
+    static char altstack[1 << 16];
+    stack_t ss{}; ss.ss_sp = altstack; ss.ss_size = sizeof altstack; sigaltstack(&ss, nullptr);
+    struct sigaction sa{}; sa.sa_handler = hb_crash_handler; sa.sa_flags = SA_ONSTACK; sigemptyset(&sa.sa_mask);
+    sigaction(SIGSEGV, &sa, nullptr); sigaction(SIGABRT, &sa, nullptr); sigaction(SIGBUS, &sa, nullptr);
+  }
+} g_crash_init;
 
 thread_local std::string g_create_err;   // last hb_create failure of the calling thread (hb_last_error(NULL))
 
@@ -1320,7 +1345,7 @@ static int upload_pipelined(hb_handle* h, void* dst_dev, const void* src_host, s
     char* pb = reinterpret_cast<char*>(h->pin) + (k & 1) * half;
     const char* sb = reinterpret_cast<const char*>(src_host) + off;
     std::vector<std::thread> th;
-    for (int t = 1; t < n_thr; ++t) th.emplace_back([=]() -> int { const size_t lo = n / n_thr * t, hi = (t == n_thr - 1) ? n : n / n_thr * (t + 1); memcpy(pb + lo, sb + lo, hi - lo); });
+    for (int t = 1; t < n_thr; ++t) th.emplace_back([=]() { const size_t lo = n / n_thr * t, hi = (t == n_thr - 1) ? n : n / n_thr * (t + 1); memcpy(pb + lo, sb + lo, hi - lo); });
     memcpy(pb, sb, n_thr > 1 ? n / n_thr : n);
     for (auto& x : th) x.join();
     e = cudaMemcpyAsync(reinterpret_cast<char*>(dst_dev) + off, pb, n, cudaMemcpyHostToDevice, h->stream);
@@ -1594,7 +1619,7 @@ int hb_host_prefault(void* p, size_t bytes, int n_threads) {
   char* base = reinterpret_cast<char*>(p);
   std::vector<std::thread> th;
   for (int t = 0; t < nt; ++t)
-    th.emplace_back([=]() -> int {
+    th.emplace_back([=]() {
       const size_t lo = bytes / nt * t, hi = (t == nt - 1) ? bytes : bytes / nt * (t + 1);
       for (size_t o = lo; o < hi; o += 4096) reinterpret_cast<volatile char*>(base)[o] = 0;
     });

@@ -261,15 +261,20 @@ class Sampler:
         """Runs until every independent run has max_k R_stat_k < threshold at `hold` consecutive checks (a plain first
         crossing gives false early convergence when all chains are equally over-dispersed, SURVEY 8d metric 2), checked
         every `check_every` stored generations from ind_out > first_check (R/dream.R:270).  Returns a dict with the
-        wall seconds, the generation every run converged at (0 = not converged within t) and the last R_stat."""
+        wall seconds, the generation every run converged at (0 = not converged within t) and the last R_stat.
+        A single population (n_runs == 1, either sweep) is monitored through ``rstat()`` -- on a sharded population that is
+        a collective: every rank calls this method and takes the same decisions."""
         t0 = time.perf_counter()
         nr = max(self.cfg.n_runs, 1)
+        population = nr == 1 and self.cfg.sweep == A.HB_SWEEP_SYNCHRONOUS
         streak = np.zeros(nr, np.int64); conv_gen = np.zeros(nr, np.int64)
         done = self.run(max(first_check * self.cfg.thin, 1))
-        r = None
+        r = None; checks = 0; check_seconds = 0.0
         while True:
             if self.ind_out() > first_check:
-                r = self.rstat_runs().max(axis=1)
+                tc = time.perf_counter()
+                r = self.rstat()[None, :].max(axis=1) if population else self.rstat_runs().max(axis=1)
+                check_seconds += time.perf_counter() - tc; checks += 1
                 ok = r < threshold                                   # NaN (degenerate run) never counts as converged
                 streak = np.where(ok, streak + 1, 0)
                 newly = (streak >= hold) & (conv_gen == 0)
@@ -280,7 +285,8 @@ class Sampler:
                 break
             done = self.run(check_every * self.cfg.thin)
         return {"seconds": time.perf_counter() - t0, "generations": int(done), "converged_at": conv_gen,
-                "all_converged": bool((conv_gen > 0).all()), "R_stat_max": r}
+                "all_converged": bool((conv_gen > 0).all()), "R_stat_max": r, "checks": checks,
+                "check_seconds": check_seconds}
 
 
 class GroupSampler:

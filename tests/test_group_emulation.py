@@ -158,4 +158,5 @@ def test_group_error_is_reported_by_every_rank(pieces_env):
         with pytest.raises(A.HbError):
             g.run(10)
         msgs = [g.L.hb_last_error(s.h).decode() for s in g.ranks]
-    assert all("has to be >= zero" in m for m in msgs), msgs
+    # rank 0's chains are all valid: whatever it reports reached it through the OR-reduce of the error masks
+    assert msgs[0] == msgs[1] and ("has to be >= zero" in msgs[0] or "not finite" in msgs[0]), msgs
