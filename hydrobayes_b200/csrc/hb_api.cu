@@ -242,22 +242,28 @@ int allocate(hb_handle* h) {
   }
   if (c.past_sample) { CK(dalloc(&h->Z, (size_t)h->m_cap * ldx)); }
   h->wide = g_hb_force_wide || nl >= (long long)h->sm_count * 16 * 32 / 2;   // the threshold of hb_launch_k1 / hb_launch_k3
+  // diagnostics: HB_FORCE_DELTA=1 runs the stage-and-apply pipeline (pieces, delta log, send, apply) on ONE GPU with no
+  // peers, so that its kernel and launch overheads can be measured against the plain path without a multi-GPU box
+  if (h->world == 1 && !h->modeb && c.mt <= 1 && !h->peer_mode && getenv("HB_FORCE_DELTA") && getenv("HB_FORCE_DELTA")[0] == '1') {
+    h->delta_mode = true; h->peers_ready = true; h->rank = 0;
+  }
   h->pieces = 1; h->piece_n = nl;
   if (h->delta_mode) {
     // pieces per generation: the send of piece p overlaps the kernels of piece p + 1, so only the last piece's transfer is
     // exposed; a piece must still fill the device (>= 16 384 chains).  HB_PIECES overrides (tests run tiny populations).
     int P = 1;
-    if (h->wide) { P = 4; while (P > 1 && nl / P < 16384) P >>= 1; }
+    if (h->wide) { P = 2; while (P > 1 && nl / P < 32768) P >>= 1; }
     if (const char* e = getenv("HB_PIECES")) { const int v = atoi(e); if (v >= 1 && v <= HB_MAX_PIECES) P = v; }
     if ((long long)P > nl) P = (int)nl;
     h->pieces = P;
     h->piece_n = (nl + P - 1) / P;
     if (P > 1) h->piece_n = (h->piece_n + 31) & ~31LL;
-    // the send kernel (256 threads, <= 64 registers) runs next to the persistent proposal grid: the proposal kernel leaves
-    // `reserve_ctas` of its 2-per-SM CTA slots free, each of which hosts two send CTAs
-    h->send_ctas = 32;
+    // the send kernel (128 threads, ~80 registers: 10k registers per CTA) runs next to the persistent proposal grid: the
+    // proposal kernel leaves `reserve_ctas` of its 2-per-SM CTA slots free, each of which hosts three send CTAs
+    h->send_ctas = 48;
     if (const char* e = getenv("HB_SEND_CTAS")) { const int v = atoi(e); if (v >= 1 && v <= 1024) h->send_ctas = v; }
-    h->reserve_ctas = h->wide ? (h->send_ctas + 1) / 2 : 0;
+    h->reserve_ctas = h->wide ? (h->send_ctas + 2) / 3 : 0;
+    if (const char* e = getenv("HB_RESERVE_CTAS")) { const int v = atoi(e); if (v >= 0 && v <= 128) h->reserve_ctas = v; }
     // arena mapped by the peers: flags, error slots, all-reduce slots, all-gather area, delta boxes (no NCCL on this path)
     const size_t E = (size_t)(2 + c.nCR) * d;
     h->arena_red_bytes = ((E * (size_t)c.update_interval + HB_MAX_NCR + 1 + 3 * (size_t)d) * 8 + 255) & ~(size_t)255;
@@ -279,9 +285,12 @@ int allocate(hb_handle* h) {
       int lo = 0, hi = 0;
       CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
       CK(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi));
+      CK(cudaStreamCreateWithPriority(&h->side2, cudaStreamNonBlocking, hi));
     }
     for (int q = 0; q < P; ++q) CK(cudaEventCreateWithFlags(&h->ev_piece[q], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_sent, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_k1last, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_applied, cudaEventDisableTiming));
   } else if (h->world > 1) {
     CK(dalloc(&h->errbits_dev, 16));
   }
@@ -674,7 +683,8 @@ int mt_generation(hb_handle* h, long long i, bool store, bool in_adapt, bool tap
 }
 
 // K1 -> K2 -> K3 over chains [off, off + n) of the shard (the whole shard, or one piece of it in delta mode)
-int piece_kernels(hb_handle* h, long long i, int piece, long long off, long long n, bool store, bool in_adapt, bool tape_mode) {
+int piece_kernels(hb_handle* h, long long i, int piece, long long off, long long n, bool store, bool in_adapt, bool tape_mode,
+                  cudaEvent_t ev_after_k1 = nullptr) {
   const hb_config& c = h->cfg;
   const int d = h->d, ldx = h->ldx;
   {  // K1
@@ -684,6 +694,7 @@ int piece_kernels(hb_handle* h, long long i, int piece, long long off, long long
     prof_scope ps(h, "K1");
     CK(hb_launch_k1(p, tape_mode, h->sm_count, h->stream));
     ps.done();
+    if (ev_after_k1) CK(cudaEventRecord(ev_after_k1, h->stream));
     if (int rc = hb_prior_after_k1(h, n, off)) return rc;
   }
   {  // K2: the target plugin
@@ -733,15 +744,32 @@ int piece_send(hb_handle* h, long long i, int piece) {
 }
 
 // fold the delta logs of pieces [p0, p1) of generation i -- this rank's and every peer's -- into the replica
-int delta_apply(hb_handle* h, long long i, int p0, int p1) {
+int delta_apply(hb_handle* h, long long i, int p0, int p1, cudaStream_t st) {
   hb_delta_apply_params ap{};
   for (int r = 0; r < h->world; ++r) ap.box[r] = h->arena + h->arena_box_off + ((size_t)(i & 1) * h->world + r) * h->box_bytes;
   ap.idx_off = h->box_idx_off; ap.rows_off = h->box_rows_off; ap.piece_cap = h->piece_n; ap.p0 = p0; ap.p1 = p1;
   ap.ldx = h->ldx; ap.self = h->rank; ap.world = h->world; ap.nc = h->nc; ap.X = h->X;
   ap.flags = reinterpret_cast<const unsigned*>(h->arena); ap.flag_value = (unsigned)i * HB_MAX_PIECES + (unsigned)p1;
   ap.err = &h->ctrl->err; ap.timeout_ns = hb_peer_timeout_ns();
-  prof_scope ps(h, "APPLY");
-  CK(hb_launch_delta_apply(ap, h->sm_count, h->stream));
+  prof_scope ps(h, "APPLY", st);
+  CK(hb_launch_delta_apply(ap, h->sm_count, st));
+  ps.done();
+  return HB_OK;
+}
+
+// store the rows of piece `piece` of this rank's log straight into every replica (the last piece of a generation)
+int delta_push(hb_handle* h, long long i, int piece) {
+  hb_delta_push_params pp{};
+  pp.box = h->arena + h->arena_box_off + ((size_t)(i & 1) * h->world + h->rank) * h->box_bytes;
+  pp.idx_off = h->box_idx_off; pp.rows_off = h->box_rows_off; pp.piece_off = (long long)piece * h->piece_n;
+  pp.ldx = h->ldx; pp.self = h->rank; pp.world = h->world; pp.nc = h->nc;
+  for (int r = 0; r < h->world; ++r) { pp.X[r] = (r == h->rank) ? h->X : h->peerX[r]; pp.arena[r] = h->arena_peer[r]; }
+  pp.log_count = h->log_ctr + (size_t)(i & 1) * HB_MAX_PIECES + piece;
+  pp.done_ctr = h->log_ctr + 2 * HB_MAX_PIECES + piece;
+  pp.flags = reinterpret_cast<const unsigned*>(h->arena); pp.gen = (unsigned)i;
+  pp.err = &h->ctrl->err; pp.timeout_ns = hb_peer_timeout_ns();
+  prof_scope ps(h, "XCHG");
+  CK(hb_launch_delta_push(pp, h->sm_count, h->stream));
   ps.done();
   return HB_OK;
 }
@@ -788,20 +816,48 @@ int build_generation(hb_handle* h, long long i, gen_prog& g) {
   } else if (h->delta_mode) {
     // sharded population, stage-and-apply exchange (hb_delta.cu): piece p's log travels while piece p + 1 computes
     const int P = h->pieces;
+    // Pieces 0 .. P-2: K3 logs the accepted rows, the send kernel ships the log while the next piece computes, and as soon
+    // as this rank's LAST proposal kernel is done (nothing reads the generation-start state any more) the logs that have
+    // arrived are folded into the replica on a second side stream, behind the last piece's K2 / K3.
+    // Last piece: flag 5 tells the peers that this rank's proposals are done; the push kernel waits for every peer's flag 5
+    // and stores the rows of the last piece straight into every replica (no log on the receiving side, no apply pass),
+    // then raises flag 6; the generation ends when every peer's flag 6 has arrived.
+    const bool conc = h->side != h->stream;                 // real ranks; a rank emulation runs everything on one stream
     g.then([=]() -> int {
       for (int p = 0; p < P; ++p) {
         const long long off = (long long)p * h->piece_n, n = std::min(h->piece_n, nl - off);
-        if (n > 0) { if (int rc = piece_kernels(h, i, p, off, n, store, in_adapt, tape_mode)) return rc; }
-        if (int rc = piece_send(h, i, p)) return rc;        // an empty piece still raises its flag
-      }
-      if (h->side != h->stream) {                           // the apply kernel reads this rank's own log and counts
-        CK(cudaEventRecord(h->ev_sent, h->side));
-        CK(cudaStreamWaitEvent(h->stream, h->ev_sent, 0));
+        const bool last = (p == P - 1);
+        if (n > 0) { if (int rc = piece_kernels(h, i, p, off, n, store, in_adapt, tape_mode, (conc && last) ? h->ev_k1last : nullptr)) return rc; }
+        else if (conc && last) CK(cudaEventRecord(h->ev_k1last, h->stream));
+        if (!last) {
+          if (int rc = piece_send(h, i, p)) return rc;      // an empty piece still raises its flag
+          if (conc && p == P - 2) CK(cudaEventRecord(h->ev_sent, h->side));
+        } else {
+          if (conc) CK(cudaStreamWaitEvent(h->side2, h->ev_k1last, 0));   // every proposal of this rank has read its partner rows
+          CK(hb_launch_flag_signal(arena_peers(h), 5, h->rank, h->world, (unsigned)i, h->side2));
+          h->launches++;
+          if (conc && P > 1) {
+            CK(cudaStreamWaitEvent(h->side2, h->ev_sent, 0));            // this rank's own logs (and counts) of pieces < P - 1
+            if (int rc = delta_apply(h, i, 0, P - 1, h->side2)) return rc;
+          }
+          if (conc) CK(cudaEventRecord(h->ev_applied, h->side2));
+        }
       }
       return HB_OK;
     });
     g.cut();
-    g.then([=]() -> int { return delta_apply(h, i, 0, P); });
+    g.then([=]() -> int {
+      if (!conc && P > 1) { if (int rc = delta_apply(h, i, 0, P - 1, h->stream)) return rc; }
+      if (int rc = delta_push(h, i, P - 1)) return rc;
+      if (conc) CK(cudaStreamWaitEvent(h->stream, h->ev_applied, 0));
+      return HB_OK;
+    });
+    g.cut();
+    g.then([=]() -> int {
+      CK(hb_launch_flag_wait(h->arena, 6, h->rank, h->world, (unsigned)i, &h->ctrl->err, h->stream));
+      h->launches++;
+      return HB_OK;
+    });
   } else {
     g.then([=]() -> int { return piece_kernels(h, i, 0, 0, nl, store, in_adapt, tape_mode); });
   }
@@ -1073,8 +1129,11 @@ void hb_destroy(hb_handle* h) {
     cudaFree(h->X); h->X = nullptr;   // IPC-exported buffers are released synchronously, right after this rank closed its
                                       // own imports (only the private buffers below go to the reaper thread)
     if (h->side && h->side != h->stream) cudaStreamDestroy(h->side);
+    if (h->side2 && h->side2 != h->stream) cudaStreamDestroy(h->side2);
     for (int q = 0; q < HB_MAX_PIECES; ++q) if (h->ev_piece[q]) cudaEventDestroy(h->ev_piece[q]);
     if (h->ev_sent) cudaEventDestroy(h->ev_sent);
+    if (h->ev_k1last) cudaEventDestroy(h->ev_k1last);
+    if (h->ev_applied) cudaEventDestroy(h->ev_applied);
   }
   if (h->group_member && h->own_stream) {   // rank emulation: the shared stream belongs to rank 0's handle
     h->stream = h->own_stream; h->own_stream = nullptr;
@@ -1445,6 +1504,7 @@ static int run_slice(std::vector<hb_handle*>& hs, int64_t n_generations) {
   long long last = hs[0]->gen + n_generations;
   if (last > hs[0]->t) last = hs[0]->t;
   for (hb_handle* h : hs) CK(cudaEventRecord(h->ev0, h->stream));
+  const double t_enq0 = now_s();
   for (long long i = hs[0]->gen + 1; i <= last; ++i) {
     std::vector<gen_prog> gs(hs.size());
     for (size_t r = 0; r < hs.size(); ++r) if (int rc = build_generation(hs[r], i, gs[r])) return rc;
@@ -1455,6 +1515,7 @@ static int run_slice(std::vector<hb_handle*>& hs, int64_t n_generations) {
     for (size_t r = 0; r < hs.size(); ++r) prog_err_reduce(hs[r], gs[r]);
     if (int rc = run_programs(hs, gs)) return rc;
   }
+  timing_note("enqueue (host)", now_s() - t_enq0);
   int rc_all = HB_OK;
   for (hb_handle* h : hs) {
     CK(cudaEventRecord(h->ev1, h->stream));
@@ -1500,7 +1561,8 @@ int hb_group_attach(hb_handle** hs, int n) {
     h->group_member = true;
     if (r > 0) { h->own_stream = h->stream; h->stream = hs[0]->stream; }
     if (h->side) cudaStreamDestroy(h->side);
-    h->side = h->stream;                                   // one stream: the emulation is sequential by construction
+    if (h->side2) cudaStreamDestroy(h->side2);
+    h->side = h->stream; h->side2 = h->stream;             // one stream: the emulation is sequential by construction
     for (int q = 0; q < n; ++q) { h->arena_peer[q] = hs[q]->arena; h->peerX[q] = (q == r) ? nullptr : hs[q]->X; }
   }
   for (int r = 0; r < n; ++r) if (int rc = complete_replicas(hs[r])) return rc;

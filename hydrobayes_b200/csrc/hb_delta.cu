@@ -177,18 +177,21 @@ __global__ void hb_err_collapse_kernel(unsigned* err, const unsigned long long* 
 // dense array, so this is a flat vector copy: every 16-byte vector is loaded once from local HBM and stored to each peer
 // (posted NVLink writes).  The last CTA to finish publishes the row count in every box header (its own included) and
 // raises the peers' piece flag.
-template <typename V>
+template <typename V, int U>
 __device__ __forceinline__ void delta_copy(const hb_delta_send_params& p, size_t src_off, size_t n_vec) {
   const V* __restrict__ src = reinterpret_cast<const V*>(p.box[p.self] + src_off);
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (size_t)gridDim.x * blockDim.x;
   size_t i = tid;
-  for (; i + 3 * nt < n_vec; i += 4 * nt) {                    // four independent loads in flight per thread
-    const V v0 = src[i], v1 = src[i + nt], v2 = src[i + 2 * nt], v3 = src[i + 3 * nt];
+  for (; i + (U - 1) * nt < n_vec; i += U * nt) {               // U independent loads in flight per thread
+    V v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = src[i + u * nt];
 #pragma unroll
     for (int r = 0; r < 8; ++r)
       if (r < p.world && r != p.self) {
         V* dst = reinterpret_cast<V*>(p.box[r] + src_off);
-        dst[i] = v0; dst[i + nt] = v1; dst[i + 2 * nt] = v2; dst[i + 3 * nt] = v3;
+#pragma unroll
+        for (int u = 0; u < U; ++u) dst[i + u * nt] = v[u];
       }
   }
   for (; i < n_vec; i += nt) {
@@ -199,13 +202,13 @@ __device__ __forceinline__ void delta_copy(const hb_delta_send_params& p, size_t
   }
 }
 
-__global__ void __launch_bounds__(256, 4) hb_delta_send_kernel(const hb_delta_send_params p) {
+__global__ void __launch_bounds__(128) hb_delta_send_kernel(const hb_delta_send_params p) {
   const unsigned n = *reinterpret_cast<const volatile unsigned*>(p.log_count);
   const size_t rows_off = p.rows_off + (size_t)p.piece_off * p.ldx * 8;
   const size_t idx_off = p.idx_off + (size_t)p.piece_off * 4;
-  if ((p.ldx & 1) == 0) delta_copy<double2>(p, rows_off, (size_t)n * p.ldx / 2);
-  else delta_copy<double>(p, rows_off, (size_t)n * p.ldx);
-  delta_copy<int>(p, idx_off, (size_t)n);
+  if ((p.ldx & 1) == 0) delta_copy<double2, 8>(p, rows_off, (size_t)n * p.ldx / 2);
+  else delta_copy<double, 4>(p, rows_off, (size_t)n * p.ldx);
+  delta_copy<int, 2>(p, idx_off, (size_t)n);
   __threadfence_system();                                       // this thread's remote stores are performed ...
   __syncthreads();
   __shared__ bool last;
@@ -257,23 +260,101 @@ __global__ void __launch_bounds__(256) hb_delta_apply_kernel(const hb_delta_appl
   const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const int ldx = p.ldx;
-  for (long long i = warp_id; i < (long long)total; i += n_warps) {
+  auto locate = [&](long long i, const double*& src, double*& dst) -> bool {
     int sgi = 0;
     while (sgi + 1 < n_seg && s_pref[sgi + 1] <= (unsigned)i) ++sgi;
     const int r = sgi / np, pc = p.p0 + sgi % np;
     const long long slot = (long long)pc * p.piece_cap + (i - s_pref[sgi]);
     const int chain = reinterpret_cast<const int*>(p.box[r] + p.idx_off)[slot];
-    if (chain < 0 || chain >= p.nc) { if (lane == 0) atomicOr(p.err, HB_FLAG_PEER_TIMEOUT); continue; }
-    const double* __restrict__ src = reinterpret_cast<const double*>(p.box[r] + p.rows_off) + slot * ldx;
-    double* __restrict__ dst = p.X + (long long)chain * ldx;
-    if ((ldx & 1) == 0) {
-      const double2* s2 = reinterpret_cast<const double2*>(src);
-      double2* d2 = reinterpret_cast<double2*>(dst);
-      for (int k = lane; k < ldx / 2; k += 32) d2[k] = s2[k];
-    } else {
-      for (int k = lane; k < ldx; k += 32) dst[k] = src[k];
+    if (chain < 0 || chain >= p.nc) { if (lane == 0) atomicOr(p.err, HB_FLAG_PEER_TIMEOUT); return false; }
+    src = reinterpret_cast<const double*>(p.box[r] + p.rows_off) + slot * ldx;
+    dst = p.X + (long long)chain * ldx;
+    return true;
+  };
+  if ((ldx & 1) == 0 && ldx <= 128) {          // rows of up to 64 16-byte vectors: two rows (four loads) in flight per warp
+    const int nv = ldx / 2;
+    for (long long i = warp_id; i < (long long)total; i += 2 * n_warps) {
+      const double* sa = nullptr; double* da = nullptr; const double* sb = nullptr; double* db = nullptr;
+      const bool oka = locate(i, sa, da);
+      const bool okb = (i + n_warps < (long long)total) && locate(i + n_warps, sb, db);
+      double2 a0, a1, b0, b1;
+      if (oka) { if (lane < nv) a0 = reinterpret_cast<const double2*>(sa)[lane]; if (lane + 32 < nv) a1 = reinterpret_cast<const double2*>(sa)[lane + 32]; }
+      if (okb) { if (lane < nv) b0 = reinterpret_cast<const double2*>(sb)[lane]; if (lane + 32 < nv) b1 = reinterpret_cast<const double2*>(sb)[lane + 32]; }
+      if (oka) { if (lane < nv) reinterpret_cast<double2*>(da)[lane] = a0; if (lane + 32 < nv) reinterpret_cast<double2*>(da)[lane + 32] = a1; }
+      if (okb) { if (lane < nv) reinterpret_cast<double2*>(db)[lane] = b0; if (lane + 32 < nv) reinterpret_cast<double2*>(db)[lane + 32] = b1; }
+    }
+  } else {
+    for (long long i = warp_id; i < (long long)total; i += n_warps) {
+      const double* src = nullptr; double* dst = nullptr;
+      if (!locate(i, src, dst)) continue;
+      if ((ldx & 1) == 0) {
+        const double2* s2 = reinterpret_cast<const double2*>(src);
+        double2* d2 = reinterpret_cast<double2*>(dst);
+        for (int k = lane; k < ldx / 2; k += 32) d2[k] = s2[k];
+      } else {
+        for (int k = lane; k < ldx; k += 32) dst[k] = src[k];
+      }
     }
   }
+}
+
+// ---- delta log: direct push of the last piece ------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hb_delta_push_kernel(const hb_delta_push_params p) {
+  __shared__ int s_ok;
+  __shared__ bool last;
+  if (threadIdx.x == 0) s_ok = 1;
+  __syncthreads();
+  {
+    const int r = threadIdx.x;
+    if (r < p.world && r != p.self) {
+      if (!hb_spin_ge(p.flags + 5 * 8 + r, p.gen, p.err, p.timeout_ns)) s_ok = 0;
+      __threadfence_system();
+    }
+  }
+  __syncthreads();
+  if (s_ok) {
+    const unsigned n = *reinterpret_cast<const volatile unsigned*>(p.log_count);
+    const int lane = threadIdx.x & 31;
+    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int ldx = p.ldx;
+    const int* idx = reinterpret_cast<const int*>(p.box + p.idx_off) + p.piece_off;
+    const double* rows = reinterpret_cast<const double*>(p.box + p.rows_off) + p.piece_off * ldx;
+    for (long long i = warp_id; i < (long long)n; i += n_warps) {
+      const int chain = idx[i];
+      if (chain < 0 || chain >= p.nc) { if (lane == 0) atomicOr(p.err, HB_FLAG_PEER_TIMEOUT); continue; }
+      const double* __restrict__ src = rows + i * ldx;
+      const long long o = (long long)chain * ldx;
+      if ((ldx & 1) == 0 && ldx <= 128) {
+        const int nv = ldx / 2;
+        double2 a0 = make_double2(0, 0), a1 = make_double2(0, 0);
+        if (lane < nv) a0 = reinterpret_cast<const double2*>(src)[lane];
+        if (lane + 32 < nv) a1 = reinterpret_cast<const double2*>(src)[lane + 32];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          if (r < p.world) {
+            double2* dst = reinterpret_cast<double2*>(p.X[r] + o);
+            if (lane < nv) dst[lane] = a0;
+            if (lane + 32 < nv) dst[lane + 32] = a1;
+          }
+      } else {
+        for (int k = lane; k < ldx; k += 32) {
+          const double v = src[k];
+          for (int r = 0; r < p.world; ++r) p.X[r][o + k] = v;
+        }
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(p.done_ctr, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence_system();
+  const int r = threadIdx.x;
+  if (r < p.world && r != p.self)
+    *reinterpret_cast<volatile unsigned*>(reinterpret_cast<unsigned*>(p.arena[r]) + 6 * 8 + p.self) = p.gen;
+  if (threadIdx.x == 0) { *p.done_ctr = 0u; *p.log_count = 0u; }
 }
 
 }  // namespace
@@ -346,7 +427,13 @@ cudaError_t hb_launch_err_collapse(unsigned* err, const unsigned long long* bits
 }
 
 cudaError_t hb_launch_delta_send(const hb_delta_send_params& p, int ctas, cudaStream_t st) {
-  hb_delta_send_kernel<<<ctas < 1 ? 1 : ctas, 256, 0, st>>>(p);
+  hb_delta_send_kernel<<<ctas < 1 ? 1 : ctas, 128, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t hb_launch_delta_push(const hb_delta_push_params& p, int sm_count, cudaStream_t st) {
+  if (p.world > 8) return cudaErrorInvalidValue;
+  hb_delta_push_kernel<<<sm_count * 2, 256, 0, st>>>(p);
   return cudaGetLastError();
 }
 

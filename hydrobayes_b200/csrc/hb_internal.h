@@ -68,8 +68,9 @@ struct hb_handle {
   double* ibuf = nullptr;         // [update_interval][(2 + nCR) d] per-generation adaptation sums of the current interval
   int islot = 0;
   cudaStream_t side = nullptr;    // high-priority stream of the send kernels (== stream in a rank emulation)
+  cudaStream_t side2 = nullptr;   // high-priority stream of the early apply (pieces < P - 1, behind the last piece's K2 / K3)
   cudaEvent_t ev_piece[HB_MAX_PIECES] = {};
-  cudaEvent_t ev_sent = nullptr;
+  cudaEvent_t ev_sent = nullptr, ev_k1last = nullptr, ev_applied = nullptr;
   unsigned long long* errbits_dev = nullptr;   // NCCL modes: error mask expanded to one word per bit for the sum all-reduce
   // rank emulation on one device (hb_group_attach): the handles share one stream and reference each other's buffers
   bool group_member = false;

@@ -1112,10 +1112,13 @@ inline void k1_wide_geometry(hb_k1_params& p, int sm_count, int max_warps, int* 
   *threads = warps * 32;
   long long cap = (long long)sm_count * ctas - p.reserve_ctas;          // persistent: two CTAs per SM, grid-stride batches
   if (cap < 1) cap = 1;
-  // a warp works through its batch chain by chain, so a launch with fewer 32-chain batches than resident warps (one piece
-  // of a multi-GPU shard) would leave warps idle for a whole batch time: halve the batch until the warps are covered
-  int B = 32;
-  while (B > 8 && (p.n_local + B - 1) / B < cap * warps) B >>= 1;
+  // a warp works through its batch chain by chain, so the launch takes ceil(batches / warps) batch times: size the batch
+  // so that the last wave is full (a piece of a multi-GPU shard is only one or two waves, where a fixed 32 would leave up
+  // to half of the warps idle for a whole batch time)
+  const long long n_warps_total = cap * warps;
+  const long long waves = (p.n_local + n_warps_total * 32 - 1) / (n_warps_total * 32);
+  long long Bq = (p.n_local + n_warps_total * waves - 1) / (n_warps_total * waves);
+  int B = (int)(Bq > 32 ? 32 : Bq < 4 ? 4 : Bq);
   if (const char* e = getenv("HB_K1_BATCH")) B = atoi(e);
   p.batch = B;
   const long long warps_needed = (p.n_local + B - 1) / B;

@@ -475,18 +475,36 @@ cudaError_t dispatch(const hb_k3_params& p, int sm_count, int* nb, size_t* sm, c
 }
 
 // ---- finalize -------------------------------------------------------------------------------------------
+// block partials [nblocks][E] -> colsum / qsum, in a fixed order (deterministic): 32 columns x 8 row groups per CTA, the
+// eight group sums of a column are added in group order
+__global__ void __launch_bounds__(256) hb_finalize_reduce_kernel(const hb_fin_params p) {
+  __shared__ double part[8][33];
+  const int d = p.d, E = (p.nCR + 2) * d;
+  const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + c;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  if (e < E) {
+    int b = g;
+    for (; b + 24 < p.nblocks; b += 32) {                   // four independent loads in flight
+      s0 += p.partials[(size_t)b * E + e]; s1 += p.partials[(size_t)(b + 8) * E + e];
+      s2 += p.partials[(size_t)(b + 16) * E + e]; s3 += p.partials[(size_t)(b + 24) * E + e];
+    }
+    for (; b < p.nblocks; b += 8) s0 += p.partials[(size_t)b * E + e];
+  }
+  part[g][c] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (g == 0 && e < E) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += part[q][c];
+    if (e < 2 * d) p.colsum[e] = s; else p.qsum[e - 2 * d] = s;
+  }
+}
+
 __global__ void __launch_bounds__(256) hb_finalize_kernel(const hb_fin_params p) {
   __shared__ double red[256];
   const int d = p.d, nCR = p.nCR;
-  const int E = (nCR + 2) * d;
   hb_ctrl* c = p.ctrl;
-  if (p.adapt && (p.phase == 0 || p.phase == 2)) {
-    for (int e = threadIdx.x; e < E; e += blockDim.x) {
-      double s = 0.0;
-      for (int b = 0; b < p.nblocks; ++b) s += p.partials[(size_t)b * E + e];
-      if (e < 2 * d) p.colsum[e] = s; else p.qsum[e - 2 * d] = s;
-    }
-  }
   if (p.phase == 0) return;
   __syncthreads();
   // Multi-GPU: the per-generation sums of one updateInterval are parked in slots and all-reduced once (nothing between
@@ -726,7 +744,11 @@ cudaError_t hb_launch_k3(const hb_k3_params& p, int sm_count, int* nblocks_out, 
 }
 
 cudaError_t hb_launch_finalize(const hb_fin_params& p, cudaStream_t st) {
-  hb_finalize_kernel<<<1, 256, 0, st>>>(p);
+  if (p.adapt && (p.phase == 0 || p.phase == 2)) {
+    const int E = (p.nCR + 2) * p.d;
+    hb_finalize_reduce_kernel<<<(E + 31) / 32, 256, 0, st>>>(p);
+  }
+  if (p.phase != 0) hb_finalize_kernel<<<1, 256, 0, st>>>(p);
   return cudaGetLastError();
 }
 

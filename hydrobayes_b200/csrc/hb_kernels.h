@@ -246,6 +246,24 @@ struct hb_delta_apply_params {
   unsigned* err; unsigned long long timeout_ns;
 };
 cudaError_t hb_launch_delta_apply(const hb_delta_apply_params& p, int sm_count, cudaStream_t st);
+// the LAST piece of a generation needs no log on the receiving side: once every rank's proposals of the generation are done
+// (flag 5, raised after each rank's last proposal kernel) nothing reads the generation-start state any more, so the rows
+// of this rank's log are stored straight into every replica of X (its own included); the last CTA raises flag 6
+struct hb_delta_push_params {
+  const unsigned char* box;   // this rank's box (parity, self)
+  size_t idx_off, rows_off;
+  long long piece_off;        // first log slot of the piece
+  int ldx, self, world;
+  long long nc;
+  double* X[8];               // every rank's replica (X[self] is local)
+  unsigned char* arena[8];    // every rank's arena (flags)
+  unsigned* log_count;        // slot counter of the piece (reset by the kernel)
+  unsigned* done_ctr;
+  const unsigned* flags;      // own arena
+  unsigned gen;               // flag value: wait flags[5*8 + r] >= gen, then raise flags[6*8 + self] = gen on every peer
+  unsigned* err; unsigned long long timeout_ns;
+};
+cudaError_t hb_launch_delta_push(const hb_delta_push_params& p, int sm_count, cudaStream_t st);
 cudaError_t hb_launch_outlier_reset_peer(double* Xlocal, hb_peer_ptrs peers, long long peer_nl, int ldx, int d,
                                          double* lpost, double* lpost_hist_row, const double* lpost_src,
                                          long long chain0, long long n_local, const int* outl, const int* news,
