@@ -492,7 +492,8 @@ def main():
         cfg.exchange = 1   # HB_EXCHANGE_PEER
     if world > 1 and args.exchange == "delta":
         cfg.exchange = 2   # HB_EXCHANGE_DELTA
-    need = (args.steps + args.warmup + (0 if args.no_extras else 2)) * GENS_PER_STEP + 1   # + the profiled generations
+    steady_steps = 0 if args.no_extras else 20             # a second, steady-state window after the profiled generations
+    need = (args.steps + args.warmup + (0 if args.no_extras else 2) + steady_steps) * GENS_PER_STEP + 1   # + the profiled generations
     if need > cfg.t:
         cfg.t = need
     sharded = None
@@ -535,6 +536,21 @@ def main():
             ms, n = s.kernel_ms(k)
             if n:
                 kernels[k] = {"ms_per_launch": ms / n, "launches": n}
+        # steady state: `value` above is timed right after the warm-up, i.e. partly inside the adaptation period (statistics
+        # pass over every row, outlier checks, and twice the acceptance rate = twice the rows to exchange); this second
+        # window lies behind it (and behind the profiled generations)
+        steady = None
+        adapt_end = int(cfg.adapt * cfg.t)
+        done_gens = 1 + (args.warmup + args.steps + 2) * GENS_PER_STEP
+        if done_gens > adapt_end + GENS_PER_STEP:
+            barrier_sync(torch, world)
+            t0s = time.perf_counter()
+            for _ in range(steady_steps):
+                s.run(GENS_PER_STEP)
+            barrier_sync(torch, world)
+            ws = max_over_ranks(torch, world, time.perf_counter() - t0s)
+            steady = {"value": cfg.nc * steady_steps * GENS_PER_STEP / ws, "unit": UNIT, "ms_per_generation": ws / (steady_steps * GENS_PER_STEP) * 1e3,
+                      "generations": f"{done_gens + 1}..{done_gens + steady_steps * GENS_PER_STEP} (the adaptation period ends at {adapt_end})"}
         try:   # acceptance rate of the last complete updateInterval (AR column 2, R/dream_parallel.R:431)
             ar, _ = s.fetch_ar_cr()
             col = ar[:, 1][np.isfinite(ar[:, 1])]
@@ -553,6 +569,10 @@ def main():
             "gpu_launches": l1 - l0, "rscript": rscript_probe()}
     if sharded is not None:
         line["sharded_check"] = sharded
+    if not args.no_extras and steady is not None:
+        line["steady_state"] = steady
+        line["timed_window"] = (f"generations {2 + args.warmup * GENS_PER_STEP}..{1 + (args.warmup + args.steps) * GENS_PER_STEP}; the adaptation "
+                                f"period (statistics pass, outlier checks, higher acceptance rate) ends at generation {int(cfg.adapt * cfg.t)}")
     if rank == 0 and not args.no_extras:
         peaks = load_peaks()
         import ctypes as C
@@ -641,18 +661,19 @@ def main():
                 except Exception as e:  # report, never hide
                     others[name] = {"error": repr(e)}
         if "C2" in others and "error" not in others["C2"]:
-            # the opt-in fused small-population kernel (HB_FUSED=1: proposal + log-density + accept in one launch, see
-            # DESIGN.md section 8) measured next to the default three-kernel path; a failure is reported, never hidden
-            os.environ["HB_FUSED"] = "1"
-            try:
-                f = quick_rate("C2", local, torch)
-                others["C2"]["experimental_fused_kernel"] = {k: f[k] for k in ("value", "us_per_generation", "device_us_per_generation",
-                                                                             "gpu_launches", "generations")}
-                others["C2"]["experimental_fused_kernel"]["enable"] = "HB_FUSED=1 (off by default this round)"
-            except Exception as e:
-                others["C2"]["experimental_fused_kernel"] = {"error": repr(e)}
-            finally:
-                os.environ.pop("HB_FUSED", None)
+            # the default C2 path is the persistent generation loop (one cooperative launch per slice); next to it the
+            # one-launch-per-generation fused kernel and the three-kernel path; a failure is reported, never hidden
+            for label, env in (("fused_one_launch_per_generation", {"HB_PERSIST": "0"}), ("three_kernel_path", {"HB_FUSED": "0"})):
+                os.environ.update(env)
+                try:
+                    f = quick_rate("C2", local, torch)
+                    others["C2"][label] = {k: f[k] for k in ("value", "us_per_generation", "device_us_per_generation", "gpu_launches", "generations")}
+                    others["C2"][label]["enable"] = " ".join(f"{k}={v}" for k, v in env.items())
+                except Exception as e:
+                    others["C2"][label] = {"error": repr(e)}
+                finally:
+                    for k in env:
+                        os.environ.pop(k, None)
         try:
             others["C5"] = convergence_c5(local, torch)
         except Exception as e:

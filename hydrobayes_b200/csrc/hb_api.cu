@@ -625,7 +625,7 @@ bool fused_available(hb_handle* h) {
   if (h->fused_state == 0) {
     h->fused_state = -1;
     const char* e = getenv("HB_FUSED");                        // "1" on, "0" off, unset: kFusedDefault
-    constexpr bool kFusedDefault = false;
+    constexpr bool kFusedDefault = true;
     const bool want = e ? (e[0] == '1') : kFusedDefault;
     if (want && c.sweep == HB_SWEEP_SYNCHRONOUS && !h->modeb && c.mt <= 1 && h->world == 1 && !h->peer_mode &&
         !h->delta_mode && !c.past_sample && c.lik == 2 && c.prior != HB_PRIOR_NORMAL && h->X &&
@@ -637,6 +637,50 @@ bool fused_available(hb_handle* h) {
     }
   }
   return h->fused_state == 1 && !h->profile && hb_fused_small_eligible(h->n_local, h->d, h->sm_count);
+}
+
+// Persistent generation loop (hb_persist_small_kernel): generations [i0, i1) of a small population, all behind the adaptation
+// period, in ONE cooperative launch.  Returns HB_OK with *taken = false when the handle cannot use it (the caller then runs
+// the generations one by one).
+int run_persistent(hb_handle* h, long long i0, long long i1, bool* taken) {
+  const hb_config& c = h->cfg;
+  *taken = false;
+  if (h->persist_state < 0 || i1 <= i0 || c.check_convergence) return HB_OK;
+  if (h->persist_state == 0) {
+    const char* e = getenv("HB_PERSIST");                      // "0" off
+    if (e && e[0] == '0') { h->persist_state = -1; return HB_OK; }
+    if (cudaMalloc((void**)&h->grid_bar, 2 * sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); h->persist_state = -1; return HB_OK; }
+    h->persist_state = 1;
+  }
+  const long long nl = h->n_local;
+  long long n_store = 0;
+  for (long long i = i0; i < i1; ++i) if (((double)i > c.burnin * (double)h->t) && (i % c.thin == 0)) ++n_store;   // :263, :386
+  if (h->ind_out + n_store > h->out_t) return fail(h, HB_ERR_INVALID, "subscript out of bounds (non-integer out_t, R/dream_parallel.R:195)");
+  const bool tape_mode = (c.rng_mode == HB_RNG_TAPE);
+  const hb_k1_params p = hb_make_k1(h, i0, h->chain0, 1, nl);
+  hb_k3_params q = hb_make_k3(h, i0, h->chain0, 1, nl, false, false, false);
+  q.Xout = h->Xalt;
+  hb_persist_params pp{};
+  pp.i0 = i0; pp.i1 = i1; pp.XA = h->X; pp.XB = h->Xalt; pp.t = h->t; pp.burnin = c.burnin; pp.thin = c.thin;
+  pp.update_interval = c.update_interval; pp.ind_out0 = h->ind_out;
+  pp.hist_x = h->hist_x; pp.hist_l = h->hist_l; pp.hist_fx = h->hist_fx; pp.lpost_hist = h->lpost_hist; pp.H = h->H;
+  pp.accept_rec = h->accept_rec; pp.u_accept = tape_mode ? h->tape.u_accept : nullptr; pp.tape_nct = h->tape.nct;
+  pp.pending0 = h->pending_evals; pp.out_ar = h->out_ar; pp.out_cr = h->out_cr; pp.ar_rows = h->ar_rows; pp.bar = h->grid_bar;
+  { const char* e = getenv("HB_PERSIST_TRACE"); pp.trace = (e && e[0] == '1') ? 1 : 0; }
+  CK(cudaMemsetAsync(h->grid_bar, 0, 2 * sizeof(unsigned), h->stream));
+  const cudaError_t e = hb_launch_persist_small(p, q, h->fused_td, pp, tape_mode, h->sm_count, h->stream);
+  if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorInvalidValue || e == cudaErrorNotSupported) {
+    cudaGetLastError(); h->persist_state = -1; return HB_OK;   // population too large for one co-resident grid: per-generation launches
+  }
+  if (e != cudaSuccess) return fail(h, HB_ERR_CUDA, "persistent generation kernel: %s", cudaGetErrorString(e));
+  *taken = true;
+  h->launches++;
+  h->ind_out += n_store;
+  long long last_upd = ((i1 - 1) / c.update_interval) * c.update_interval;       // largest multiple of updateInterval below i1
+  h->pending_evals = (last_upd >= i0) ? h->nc * (i1 - 1 - last_upd) : h->pending_evals + h->nc * (i1 - i0);
+  if ((i1 - i0) & 1) std::swap(h->X, h->Xalt);
+  h->gen = i1 - 1;
+  return HB_OK;
 }
 
 // MT-DREAM, R/dream_parallel.R:269-341 (hb_mt.cu): the whole generation as one host step
@@ -1146,7 +1190,7 @@ void hb_destroy(hb_handle* h) {
   void* ptrs[] = {h->X, h->Xalt, h->Z, h->XP, h->id, h->lp_xp, h->ll_raw, h->fx_xp, h->lp, h->ll, h->lpost, h->fx, h->lpost_hist,
                   h->hist_x, h->hist_l, h->hist_fx, h->accept_rec, h->ctrl, h->shift, h->colsum, h->qsum, h->partials,
                   h->out_ar, h->out_cr, h->proxy, h->proxy_full, h->lpost_full, h->outl_dev, h->news_dev, h->rstat_dev,
-                  h->rstat_xm, h->rstat_ss, h->stage, h->log_ctr, h->ibuf, h->errbits_dev, h->pmin, h->pmax, h->prior_W, h->prior_mu, h->ZT, h->lp_zt, h->ll_zt, h->fx_zt, h->id_zt, h->mt_p1, h->mt_accept, h->rstat_sums, h->gamma_tab, h->outl_tmp, h->outl_sorted, h->outl_thr,
+                  h->rstat_xm, h->rstat_ss, h->stage, h->log_ctr, h->ibuf, h->errbits_dev, h->grid_bar, h->pmin, h->pmax, h->prior_W, h->prior_mu, h->ZT, h->lp_zt, h->ll_zt, h->fx_zt, h->id_zt, h->mt_p1, h->mt_accept, h->rstat_sums, h->gamma_tab, h->outl_tmp, h->outl_sorted, h->outl_thr,
                   h->outl_count};
   {
     std::vector<void*> dead;
@@ -1506,6 +1550,15 @@ static int run_slice(std::vector<hb_handle*>& hs, int64_t n_generations) {
   for (hb_handle* h : hs) CK(cudaEventRecord(h->ev0, h->stream));
   const double t_enq0 = now_s();
   for (long long i = hs[0]->gen + 1; i <= last; ++i) {
+    if (hs.size() == 1) {   // small population behind the adaptation period: the rest of the slice in one persistent launch
+      hb_handle* h = hs[0];
+      const bool in_adapt = ((double)i <= h->cfg.adapt * (double)h->t);
+      if (!in_adapt && !h->modeb && h->cfg.mt <= 1 && fused_available(h)) {
+        bool taken = false;
+        if (int rc = run_persistent(h, i, last + 1, &taken)) return rc;
+        if (taken) break;
+      }
+    }
     std::vector<gen_prog> gs(hs.size());
     for (size_t r = 0; r < hs.size(); ++r) if (int rc = build_generation(hs[r], i, gs[r])) return rc;
     if (int rc = run_programs(hs, gs)) return rc;

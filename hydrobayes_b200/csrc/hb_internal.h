@@ -105,6 +105,8 @@ struct hb_handle {
   // fused small-population generation (hb_launch_fused_small): second population buffer, swapped with X every generation
   double* Xalt = nullptr;
   int fused_state = 0;                    // 0 undecided, 1 available, -1 not applicable to this handle
+  int persist_state = 0;                  // persistent generation loop (one cooperative launch per slice): same convention
+  unsigned* grid_bar = nullptr;           // [2] grid barrier words of the persistent kernel
   hb_fused_tdist fused_td{};
   int* id = nullptr;
   double *lp_xp = nullptr, *ll_raw = nullptr, *fx_xp = nullptr;

@@ -10,6 +10,7 @@
 // tape or generated with Philox4x32-10 keyed by (seed; chain, generation, slot): one Philox call per two dimensions
 // (zt, lambda, zeta; slot map v2 in include/hydrobayes_b200_rng.h) plus six per chain, the latter computed by
 // different lanes and broadcast.
+#include <cstdio>
 #include <cstdlib>
 #include "hb_kernels.h"
 
@@ -44,31 +45,46 @@ __device__ __forceinline__ double comp_group_sum(double hi, double lo, unsigned 
 
 // One chain's jump (calc_prop up to dx, R/internals.R:119-200) for the G lanes that own chain `base + lane / G`: the
 // per-chain draws, the partner gather and dx.  Shared by the proposal kernel and the fused small-population kernel.
-template <int G, int ITER, bool TAPE>
-__device__ __forceinline__ void k1_chain_jump(const hb_k1_params& p, long long base, int lane, double (&xk)[ITER],
-                                              double (&dxk)[ITER], bool& valid, long long& jl, int& id, unsigned& errbits) {
+// population loads of the proposal: plain loads, or L2-coherent loads (ld.global.cg) inside the persistent kernel, where the
+// population is rewritten by other CTAs of the SAME launch between generations (L1 / the read-only path could be stale)
+template <bool CG>
+__device__ __forceinline__ double k1_ld(const double* q) { return CG ? __ldcg(q) : *q; }
+
+// The per-chain draws of a proposal (R/internals.R:119-146, 173, 192): everything calc_prop decides before it touches the
+// population.  Split from the sweep so that the persistent kernel can compute generation i + 1's draws while the grid barrier
+// of generation i is in flight.
+struct k1_headv {
+  double g_sn;
+  int D, g_is_one, id;
+  bool snooker, valid;
+  long long pa[HB_MAX_DELTA], pb[HB_MAX_DELTA], ps2;   // a = first D partners, b = next D (R/internals.R:143-144); third snooker row
+  long long jl, gl, rbase, rix, gch;
+};
+
+template <int G, bool TAPE>
+__device__ __forceinline__ void k1_chain_head(const hb_k1_params& p, uint32_t gen, long long tape_g, long long base, int lane,
+                                              k1_headv& hv, unsigned& errbits) {
   constexpr unsigned FULL = 0xffffffffu;
   const int lg = lane & (G - 1);
   const int gbase = lane & ~(G - 1);
   const unsigned gmask = hb_group_mask<G>(lane);
-  const int d = p.d, ldx = p.ldx, nCR = p.nCR, delta = p.delta;
-  const double* __restrict__ src = p.past_sample ? p.Z : p.X;
+  const int nCR = p.nCR, delta = p.delta;
   const long long jl_raw = base + lane / G;
-  valid = jl_raw < p.n_local;
-  jl = valid ? jl_raw : p.n_local - 1;
+  const bool valid = jl_raw < p.n_local;
+  const long long jl = valid ? jl_raw : p.n_local - 1;
   const long long gl = p.chain0 + jl * p.stride;   // chain index within the handle (run-major)
   const long long run = p.n_runs > 1 ? gl / p.nc : 0;
   const long long j = gl - run * p.nc;         // chain within the run
   const long long rbase = gl - j;              // first chain of the run
   const long long gch = p.gchain0 + gl;        // global chain id: Philox counter
-  const long long rix = p.tape_g * p.tape.nct + gl;   // tape column
+  const long long rix = tape_g * p.tape.nct + gl;   // tape column
 
   // ---------------- per-chain draws: snooker test, D, partners, crossover id, gamma choice ----------------
   double u_sn, g_sn = 0.0;
-  int D, g_is_one;
+  int D, g_is_one, id;
   long long pa[HB_MAX_DELTA], pb[HB_MAX_DELTA];   // a = first D partners, b = next D (R/internals.R:143-144)
   long long ps2 = 0;                               // third snooker row (:127)
-  const hb_phx ph(p.seed, (uint64_t)gch, p.gen);
+  const hb_phx ph(p.seed, (uint64_t)gch, gen);
   if (TAPE) {
     u_sn = p.tape.u_snooker ? p.tape.u_snooker[rix] : 1.0;            // R/internals.R:119
     D = p.tape.D[rix];                                               // :123
@@ -147,14 +163,75 @@ __device__ __forceinline__ void k1_chain_jump(const hb_k1_params& p, long long b
     if (snooker && (ps2 < 0 || ps2 >= n_src)) { errbits |= HB_FLAG_BAD_TAPE; ps2 = 0; }
   }
 
-  const double* __restrict__ xrow = p.X + gl * (long long)ldx;
-  const double* __restrict__ srcr = p.past_sample ? src : src + rbase * (long long)ldx;   // partner rows of this run
+  hv.g_sn = g_sn; hv.D = D; hv.g_is_one = g_is_one; hv.id = id; hv.snooker = snooker; hv.valid = valid; hv.ps2 = ps2;
+#pragma unroll
+  for (int q = 0; q < HB_MAX_DELTA; ++q) { hv.pa[q] = pa[q]; hv.pb[q] = pb[q]; }
+  hv.jl = jl; hv.gl = gl; hv.rbase = rbase; hv.rix = rix; hv.gch = gch;
+}
+
+// The sweep of a proposal (R/internals.R:150-200): partner rows, crossover subspace, dx.
+// STAGE (one chain per warp, G == 32): the rows the chain needs -- its own state and the 2D partner rows -- are fetched into
+// a per-warp shared-memory stage by 1-D bulk TMA copies first, the Philox work of the crossover pass runs while they are in
+// flight, and the sweep reads shared memory.
+// stage: [1 + 2 delta (>= 4)][ldx] doubles, rows 0 = x, 1.. = a, 1 + delta.. = b (snooker: 1, 2, 3); sbar: its mbarrier;
+// sphase: completions so far (parity of the next wait).  Bulk copies read through L2, so they are coherent with rows other
+// CTAs of a persistent kernel wrote before the last grid barrier.
+template <int G, int ITER, bool TAPE, bool CG = false, bool STAGE = false>
+__device__ __forceinline__ void k1_chain_body(const hb_k1_params& p, uint32_t gen, const k1_headv& hv, int lane, double (&xk)[ITER],
+                                              double (&dxk)[ITER], unsigned& errbits,
+                                              double* stage = nullptr, uint64_t* sbar = nullptr, unsigned* sphase = nullptr) {
+  static_assert(!STAGE || G == 32, "row staging is written for one chain per warp");
+  const int lg = lane & (G - 1);
+  const unsigned gmask = hb_group_mask<G>(lane);
+  const int d = p.d, ldx = p.ldx, nCR = p.nCR, delta = p.delta;
+  const double* src = p.past_sample ? p.Z : p.X;
+  const double g_sn = hv.g_sn;
+  const int D = hv.D, g_is_one = hv.g_is_one, id = hv.id;
+  const bool snooker = hv.snooker;
+  const long long ps2 = hv.ps2, gl = hv.gl, rbase = hv.rbase, rix = hv.rix;
+  long long pa[HB_MAX_DELTA], pb[HB_MAX_DELTA];
+#pragma unroll
+  for (int q = 0; q < HB_MAX_DELTA; ++q) { pa[q] = hv.pa[q]; pb[q] = hv.pb[q]; }
+  const hb_phx ph(p.seed, (uint64_t)hv.gch, gen);
+  const double* xrow = p.X + gl * (long long)ldx;
+  const double* srcr = p.past_sample ? src : src + rbase * (long long)ldx;   // partner rows of this run
+  // row q of the a / b partner sets (global memory, or the staged copy)
+  auto row_a = [&](int q) -> const double* { return STAGE ? stage + (size_t)(1 + q) * ldx : srcr + pa[q] * (long long)ldx; };
+  auto row_b = [&](int q) -> const double* { return STAGE ? stage + (size_t)(1 + delta + q) * ldx : srcr + pb[q] * (long long)ldx; };
+  if (STAGE) {
+    const uint32_t row_bytes = (uint32_t)ldx * 8u;
+    const int n_rows = snooker ? 4 : 1 + 2 * D;
+    __syncwarp();
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // the previous chain's reads of the stage precede these copies
+    if (lane == 0) mbar_expect_tx(sbar, (uint32_t)n_rows * row_bytes);
+    __syncwarp();
+    if (lane < n_rows) {
+      const double* g = xrow;
+      int srow = 0;
+      if (snooker) {
+        if (lane == 1) g = srcr + pa[0] * (long long)ldx;
+        if (lane == 2) g = srcr + pb[0] * (long long)ldx;
+        if (lane == 3) g = srcr + ps2 * (long long)ldx;
+        srow = lane;
+      } else {
+#pragma unroll
+        for (int q = 0; q < HB_MAX_DELTA; ++q) {
+          if (q < D && lane == 1 + q) { g = srcr + pa[q] * (long long)ldx; srow = 1 + q; }
+          if (q < D && lane == 1 + D + q) { g = srcr + pb[q] * (long long)ldx; srow = 1 + delta + q; }
+        }
+      }
+      tma_load_1d(stage + (size_t)srow * ldx, g, row_bytes, sbar);
+    }
+    xrow = stage;
+  }
+  auto rows_ready = [&]() { if (STAGE) { mbar_wait(sbar, *sphase & 1u); *sphase += 1u; } };
 
   if (snooker) {
     // ---------------- snooker update, R/internals.R:150-163 with orth_proj :250-263 ----------------
-    const double* r1 = srcr + pa[0] * (long long)ldx;
-    const double* r2 = srcr + pb[0] * (long long)ldx;
-    const double* r3 = srcr + ps2 * (long long)ldx;
+    const double* r1 = STAGE ? stage + (size_t)1 * ldx : srcr + pa[0] * (long long)ldx;
+    const double* r2 = STAGE ? stage + (size_t)2 * ldx : srcr + pb[0] * (long long)ldx;
+    const double* r3 = STAGE ? stage + (size_t)3 * ldx : srcr + ps2 * (long long)ldx;
+    rows_ready();
     double uu[ITER], a2[ITER], a3[ITER];
     double s2 = 0, s3 = 0, su = 0, l2 = 0, l3 = 0, lu = 0;
     int differs = 0;
@@ -163,9 +240,9 @@ __device__ __forceinline__ void k1_chain_jump(const hb_k1_params& p, long long b
       const int k = m * G + lg;
       xk[m] = 0; uu[m] = 0; a2[m] = 0; a3[m] = 0;
       if (k < d) {
-        xk[m] = xrow[k];
-        const double b = r1[k];
-        a2[m] = r2[k]; a3[m] = r3[k];
+        xk[m] = k1_ld<CG && !STAGE>(xrow + k);
+        const double b = k1_ld<CG && !STAGE>(r1 + k);
+        a2[m] = k1_ld<CG && !STAGE>(r2 + k); a3[m] = k1_ld<CG && !STAGE>(r3 + k);
         uu[m] = __dadd_rn(xk[m], -b);
         differs |= (xk[m] != b);
         comp_add(s2, l2, __dmul_rn(__dadd_rn(a2[m], -xk[m]), uu[m]));
@@ -232,6 +309,7 @@ __device__ __forceinline__ void k1_chain_jump(const hb_k1_params& p, long long b
     }
     const double gamma_d = 2.38 / sqrt(2.0 * (double)D * (double)d_star);   // :190
     const double gam = g_is_one ? 1.0 : gamma_d;                            // :192
+    rows_ready();
     int rank_base = 0;
 #pragma unroll
     for (int m = 0; m < ITER; ++m) {
@@ -239,7 +317,7 @@ __device__ __forceinline__ void k1_chain_jump(const hb_k1_params& p, long long b
       const bool sel = (kmin >= 0) ? (k == kmin) : ((selmask[m] >> lg) & 1u);
       xk[m] = 0; dxk[m] = 0;
       if (k < d) {
-        xk[m] = xrow[k];
+        xk[m] = k1_ld<CG && !STAGE>(xrow + k);
         if (sel) {
           double lambda, zeta;
           if (TAPE) {
@@ -255,8 +333,8 @@ __device__ __forceinline__ void k1_chain_jump(const hb_k1_params& p, long long b
 #pragma unroll
           for (int q = 0; q < HB_MAX_DELTA; ++q) {
             if (q < D) {
-              const double a = srcr[pa[q] * (long long)ldx + k];
-              const double b = srcr[pb[q] * (long long)ldx + k];
+              const double a = k1_ld<CG && !STAGE>(row_a(q) + k);
+              const double b = k1_ld<CG && !STAGE>(row_b(q) + k);
               const double t = __dadd_rn(a, -b);
               if (q == 0) s = t;
               else { double e; two_sum(s, t, s, e); comp = __dadd_rn(comp, e); }
@@ -272,6 +350,17 @@ __device__ __forceinline__ void k1_chain_jump(const hb_k1_params& p, long long b
     }
   }
 
+}
+
+
+template <int G, int ITER, bool TAPE, bool CG = false, bool STAGE = false>
+__device__ __forceinline__ void k1_chain_jump(const hb_k1_params& p, long long base, int lane, double (&xk)[ITER],
+                                              double (&dxk)[ITER], bool& valid, long long& jl, int& id, unsigned& errbits,
+                                              double* stage = nullptr, uint64_t* sbar = nullptr, unsigned* sphase = nullptr) {
+  k1_headv hv;
+  k1_chain_head<G, TAPE>(p, p.gen, p.tape_g, base, lane, hv, errbits);
+  k1_chain_body<G, ITER, TAPE, CG, STAGE>(p, p.gen, hv, lane, xk, dxk, errbits, stage, sbar, sphase);
+  valid = hv.valid; jl = hv.jl; id = hv.id;
 }
 
 template <int G, int ITER, bool TAPE>
@@ -319,55 +408,21 @@ __global__ void __launch_bounds__(256) hb_k1_kernel(const hb_k1_params p) {
 }
 
 
-// ------------------------------------------------------------------------------------------------------------------
-// Fused generation for SMALL populations (BASELINE C2: nc = 1024, d = 100): proposal + t-distribution log-density +
-// Metropolis accept/update/store in ONE launch, one warp per chain.  At this size the three kernels of the large-population
-// path take a few microseconds each and the generation time is their launch gaps; fusing them removes two launches and the
-// XP / ll round trips through L2.  The synchronous sweep (R/dream_parallel.R:269, all proposals from the generation-start
-// state) is kept without a grid-wide barrier by double buffering the population: every chain reads partners from X and
-// writes its post-generation row into Xout (its proposal if accepted, its old row otherwise); the host swaps the buffers.
-// Only outside the adaptation period (the std_x / jump statistics need the whole post-update population).
-//   proposal      k1_chain_jump -- the same code, draw for draw, as hb_k1_kernel<32, ITER>
-//   log-density   z_n = sum_{k <= n} xp_k W[k][n], rss = sum z_n^2: the summation order of hb_tdist_fma_kernel (lane owns
-//                 columns n = 32 m + lane, k ascending); xp and W staged in shared memory (W by bulk TMA, once per CTA)
-//   accept        the non-adaptation path of hb_k3_kernel (R/internals.R:239-241, R/dream_parallel.R:348-366, 386-394)
-// ------------------------------------------------------------------------------------------------------------------
-template <int ITER, bool TAPE>
-__global__ void __launch_bounds__(256) hb_fused_small_kernel(const hb_k1_params p, const hb_k3_params q, const hb_fused_tdist td) {
+// One chain's whole generation for the warp that owns it: proposal, t-distribution log-density, Metropolis decision, state
+// update into q.Xout and history store.  Shared by the one-launch-per-generation kernel and the persistent kernel below.
+template <int ITER, bool TAPE, bool CG = false>
+__device__ __forceinline__ void fused_chain_step(const hb_k1_params& p, const hb_k3_params& q, const hb_fused_tdist& td,
+                                                 const double* __restrict__ Ws, double* __restrict__ xs, uint64_t* wbar, bool& w_ready,
+                                                 const k1_headv& hv, int lane, unsigned long long* s_cnt, unsigned& errbits,
+                                                 double* stage, uint64_t* sbar, unsigned& sphase, long long* tm = nullptr) {
   constexpr unsigned FULL = 0xffffffffu;
-  extern __shared__ __align__(16) double fused_smem[];               // W [d][ldw] | xs [warps][ITER * 32]
-  __shared__ unsigned long long s_cnt[2 * HB_MAX_NCR + 1];
-  __shared__ __align__(8) uint64_t wbar;
-  const int lane = threadIdx.x & 31;
-  double* Ws = fused_smem;
-  double* xs = fused_smem + (size_t)p.d * td.ldw + (size_t)(threadIdx.x >> 5) * (ITER * 32);
-  // W (d * ldw doubles, ldw even: a multiple of 16 bytes) is staged once per CTA by bulk TMA copies of at most 32 KB; it
-  // lands while the warps compute their first proposal (first measured version read W through L1/L2 inside the k loop:
-  // every warp of the SM missed on the same row at the same time, 33 us per generation against 23 us unfused)
-  const uint32_t w_bytes = (uint32_t)p.d * (uint32_t)td.ldw * 8u;
-  if (threadIdx.x == 0) {
-    mbar_init(&wbar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  }
-  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const int d = p.d, ldx = p.ldx;
-  unsigned errbits = 0;
-  if (threadIdx.x <= 2 * HB_MAX_NCR) s_cnt[threadIdx.x] = 0ull;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(&wbar, w_bytes);
-    for (uint32_t off = 0; off < w_bytes; off += 32768u) {
-      const uint32_t nbytes = (w_bytes - off) < 32768u ? (w_bytes - off) : 32768u;
-      tma_load_1d(reinterpret_cast<char*>(Ws) + off, reinterpret_cast<const char*>(td.W) + off, nbytes, &wbar);
-    }
-  }
-
-  for (long long base = warp_id; base < p.n_local; base += n_warps) {
     // ---------------- proposal (K1) ----------------
     double xk[ITER], dxk[ITER], xp[ITER];
-    bool valid; long long jl; int id;
-    k1_chain_jump<32, ITER, TAPE>(p, base, lane, xk, dxk, valid, jl, id, errbits);   // one chain per warp: valid == true
+    const long long jl = hv.jl; const int id = hv.id;                    // one chain per warp: hv.valid == true
+    if (tm) tm[0] = clock64();
+    k1_chain_body<32, ITER, TAPE, CG, true>(p, p.gen, hv, lane, xk, dxk, errbits, stage, sbar, &sphase);
+    if (tm) tm[1] = clock64();
     double lp_part = 0.0;
 #pragma unroll
     for (int m = 0; m < ITER; ++m) {
@@ -392,26 +447,62 @@ __global__ void __launch_bounds__(256) hb_fused_small_kernel(const hb_k1_params 
     __syncwarp();
 
     // ---------------- log-density (K2): dmvt, R/test_t_distribution.R:43 ----------------
-    double z[ITER];
-#pragma unroll
-    for (int m = 0; m < ITER; ++m) z[m] = 0.0;
-    mbar_wait(&wbar, 0);                                                // W has landed (returns at once after the first chain)
-#pragma unroll 4
-    for (int k = 0; k < d; ++k) {
-      const double xv = xs[k];
-      const double* wr = Ws + (size_t)k * td.ldw;
+    // z_n = sum_{k <= n} xp_k W[k][n], lane owns columns n = 32 m + lane.  On B200 a dependent fp64 FMA chain advances one
+    // link per ~60 cycles (measured here: 6 500 cycles for 100 links; the plugin's DMMA sequence for a single chain is worse,
+    // 30 000 cycles, its tensor pipe lives on many independent tiles), so the chain is what bounds a warp-per-chain kernel:
+    // every column keeps FOUR partial sums over k = 4 j + r (16 independent chains per lane, 25 links each), folded as
+    // (s0 + s1) + (s2 + s3).  The strict lower triangle of W is stored as zeros (tdist_build), so no term needs a predicate:
+    // column block m runs k = 0 .. 32 m + 31 and the terms with k > n add xp_k * 0.  ll therefore differs from the DMMA
+    // plugin's in the last bits (<= 1e-13 relative); states and decisions are the same.
+    if (!w_ready) { mbar_wait(wbar, 0); w_ready = true; }                // W has landed (first chain of the launch only)
+    if (tm) tm[2] = clock64();
+    double rss = 0.0;
+    {
+      double z[ITER][4];
+      int ncol[ITER];
 #pragma unroll
       for (int m = 0; m < ITER; ++m) {
-        const int n = m * 32 + lane;
-        if (n >= k && n < d) z[m] = fma(xv, wr[n], z[m]);
-      }
-    }
-    double rss = 0.0;
+        const int n = m * 32 + lane; ncol[m] = n < d ? n : d - 1;        // lanes past d: a valid column, result unused
 #pragma unroll
-    for (int m = 0; m < ITER; ++m) if (m * 32 + lane < d) rss = fma(z[m], z[m], rss);
-    rss = hb_warp_sum(rss);
+        for (int r = 0; r < 4; ++r) z[m][r] = 0.0;
+      }
+#pragma unroll
+      for (int sgm = 0; sgm < ITER; ++sgm) {
+        const int kbeg = sgm * 32;
+        if (kbeg + 32 <= d) {            // a full segment: straight-line code
+#pragma unroll
+          for (int k4 = 0; k4 < 32; k4 += 4) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const double xv = xs[kbeg + k4 + r];
+              const double* wr = Ws + (size_t)(kbeg + k4 + r) * td.ldw;
+#pragma unroll
+              for (int m = sgm; m < ITER; ++m) z[m][r] = fma(xv, wr[ncol[m]], z[m][r]);
+            }
+          }
+        } else {
+          for (int k4 = kbeg; k4 < d; k4 += 4) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const int k = k4 + r;
+              const double xv = k < d ? xs[k] : 0.0;
+              const double* wr = Ws + (size_t)(k < d ? k : d - 1) * td.ldw;
+#pragma unroll
+              for (int m = sgm; m < ITER; ++m) z[m][r] = fma(xv, wr[ncol[m]], z[m][r]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < ITER; ++m) {
+        const double zz = (z[m][0] + z[m][1]) + (z[m][2] + z[m][3]);
+        if (m * 32 + lane < d) rss = fma(zz, zz, rss);
+      }
+      rss = hb_warp_sum(rss);
+    }
     const double dens = td.konst - 0.5 * (td.df + (double)d) * log1p(rss / td.df);
     __syncwarp();                                                       // xs is rewritten by the next chain
+    if (tm) tm[3] = clock64();
 
     // ---------------- accept / update / store (K3, outside the adaptation period) ----------------
     const long long j = q.chain0 + jl * q.stride;
@@ -460,6 +551,63 @@ __global__ void __launch_bounds__(256) hb_fused_small_kernel(const hb_k1_params 
       atomicAdd(&s_cnt[1 + id], 1ull);                                  // n_id  :368-369
       if (accf) { atomicAdd(&s_cnt[0], 1ull); atomicAdd(&s_cnt[1 + HB_MAX_NCR + id], 1ull); }   // n_acc :374
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Fused generation for SMALL populations (BASELINE C2: nc = 1024, d = 100): proposal + t-distribution log-density +
+// Metropolis accept/update/store in ONE launch, one warp per chain.  At this size the three kernels of the large-population
+// path take a few microseconds each and the generation time is their launch gaps; fusing them removes two launches and the
+// XP / ll round trips through L2.  The synchronous sweep (R/dream_parallel.R:269, all proposals from the generation-start
+// state) is kept without a grid-wide barrier by double buffering the population: every chain reads partners from X and
+// writes its post-generation row into Xout (its proposal if accepted, its old row otherwise); the host swaps the buffers.
+// Only outside the adaptation period (the std_x / jump statistics need the whole post-update population).
+//   proposal      k1_chain_jump -- the same code, draw for draw, as hb_k1_kernel<32, ITER>
+//   log-density   z_n = sum_{k <= n} xp_k W[k][n], rss = sum z_n^2: the summation order of hb_tdist_fma_kernel (lane owns
+//                 columns n = 32 m + lane, k ascending); xp and W staged in shared memory (W by bulk TMA, once per CTA)
+//   accept        the non-adaptation path of hb_k3_kernel (R/internals.R:239-241, R/dream_parallel.R:348-366, 386-394)
+// ------------------------------------------------------------------------------------------------------------------
+template <int ITER, bool TAPE>
+__global__ void __launch_bounds__(256) hb_fused_small_kernel(const hb_k1_params p, const hb_k3_params q, const hb_fused_tdist td) {
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ __align__(16) double fused_smem[];               // W [d][ldw] | xs [warps][ITER * 32] | row stages [warps][rows][ldx]
+  __shared__ unsigned long long s_cnt[2 * HB_MAX_NCR + 1];
+  __shared__ __align__(8) uint64_t wbar;
+  __shared__ __align__(8) uint64_t sbars[8];
+  const int lane = threadIdx.x & 31;
+  const int n_wib = blockDim.x >> 5, wib = threadIdx.x >> 5;
+  const int stage_rows = (1 + 2 * p.delta) > 4 ? (1 + 2 * p.delta) : 4;
+  double* Ws = fused_smem;
+  double* xs = fused_smem + (size_t)p.d * td.ldw + (size_t)wib * (ITER * 32);
+  double* stage = fused_smem + (size_t)p.d * td.ldw + (size_t)n_wib * (ITER * 32) + (size_t)wib * stage_rows * p.ldx;
+  unsigned sphase = 0;
+  if (lane == 0) { mbar_init(&sbars[wib], 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+  // W (d * ldw doubles, ldw even: a multiple of 16 bytes) is staged once per CTA by bulk TMA copies of at most 32 KB; it
+  // lands while the warps compute their first proposal (first measured version read W through L1/L2 inside the k loop:
+  // every warp of the SM missed on the same row at the same time, 33 us per generation against 23 us unfused)
+  const uint32_t w_bytes = (uint32_t)p.d * (uint32_t)td.ldw * 8u;
+  if (threadIdx.x == 0) {
+    mbar_init(&wbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int d = p.d, ldx = p.ldx;
+  unsigned errbits = 0;
+  if (threadIdx.x <= 2 * HB_MAX_NCR) s_cnt[threadIdx.x] = 0ull;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&wbar, w_bytes);
+    for (uint32_t off = 0; off < w_bytes; off += 32768u) {
+      const uint32_t nbytes = (w_bytes - off) < 32768u ? (w_bytes - off) : 32768u;
+      tma_load_1d(reinterpret_cast<char*>(Ws) + off, reinterpret_cast<const char*>(td.W) + off, nbytes, &wbar);
+    }
+  }
+
+  bool w_ready = false;
+  for (long long base = warp_id; base < p.n_local; base += n_warps) {
+    k1_headv hv;
+    k1_chain_head<32, TAPE>(p, p.gen, p.tape_g, base, lane, hv, errbits);
+    fused_chain_step<ITER, TAPE>(p, q, td, Ws, xs, &wbar, w_ready, hv, lane, s_cnt, errbits, stage, &sbars[wib], sphase);
   }
   __syncthreads();
   if (threadIdx.x <= 2 * HB_MAX_NCR) {
@@ -481,8 +629,9 @@ cudaError_t launch_fused(const hb_k1_params& p, const hb_k3_params& q, const hb_
   const long long cap = (long long)sm_count * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  const size_t smem = ((size_t)p.d * td.ldw + (size_t)warps * ITER * 32) * sizeof(double);
-  if (smem > 220 * 1024 || (((size_t)p.d * td.ldw * 8) & 15)) return cudaErrorInvalidValue;
+  const int stage_rows = (1 + 2 * p.delta) > 4 ? (1 + 2 * p.delta) : 4;
+  const size_t smem = ((size_t)p.d * td.ldw + (size_t)warps * ITER * 32 + (size_t)warps * stage_rows * p.ldx) * sizeof(double);
+  if (smem > 220 * 1024 || (((size_t)p.d * td.ldw * 8) & 15) || (p.ldx & 1)) return cudaErrorInvalidValue;
   static bool attr_set[2] = {false, false};
   if (!attr_set[tape]) {
     cudaError_t e = tape ? cudaFuncSetAttribute(hb_fused_small_kernel<ITER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)
@@ -493,6 +642,151 @@ cudaError_t launch_fused(const hb_k1_params& p, const hb_k3_params& q, const hb_
   if (tape) hb_fused_small_kernel<ITER, true><<<(unsigned)blocks, threads, smem, st>>>(p, q, td);
   else hb_fused_small_kernel<ITER, false><<<(unsigned)blocks, threads, smem, st>>>(p, q, td);
   return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Persistent generation loop for small populations (BASELINE C2 is latency bound: 20 000 strictly dependent generations of
+// 1 024 chains).  ONE cooperative launch runs all generations of a slice that lie behind the adaptation
+// period: one warp per chain, W staged in shared memory once for the whole run, the population double buffered (generation
+// i reads buffer A and writes B, i + 1 the other way round), and a grid-wide barrier per generation in place of a kernel
+// boundary -- every CTA arrives on a counter, CTA 0 waits for all of them, folds the AR / CR bookkeeping at
+// updateInterval boundaries (R/dream_parallel.R:425-433; the non-adaptation part of hb_finalize_kernel), then releases
+// the others.  The per-chain step is fused_chain_step, i.e. draw for draw and operation for operation the
+// one-launch-per-generation kernel; the population is read with L2-coherent loads (other CTAs rewrite it between barriers).
+// ------------------------------------------------------------------------------------------------------------------
+template <int ITER, bool TAPE>
+__global__ void __launch_bounds__(256) hb_persist_small_kernel(const hb_k1_params p0, const hb_k3_params q0, const hb_fused_tdist td,
+                                                               const hb_persist_params pp) {
+  extern __shared__ __align__(16) double fused_smem[];               // W [d][ldw] | xs [warps][ITER * 32]
+  __shared__ hb_k1_params sp;                                         // this generation's parameter blocks
+  __shared__ hb_k3_params sq;
+  __shared__ unsigned long long s_cnt[2 * HB_MAX_NCR + 1];
+  __shared__ __align__(8) uint64_t wbar;
+  __shared__ __align__(8) uint64_t sbars[8];
+  const int lane = threadIdx.x & 31;
+  const int n_wib = blockDim.x >> 5, wib = threadIdx.x >> 5;
+  const int stage_rows = (1 + 2 * p0.delta) > 4 ? (1 + 2 * p0.delta) : 4;
+  double* Ws = fused_smem;
+  double* xs = fused_smem + (size_t)p0.d * td.ldw + (size_t)wib * (ITER * 32);
+  double* stage = fused_smem + (size_t)p0.d * td.ldw + (size_t)n_wib * (ITER * 32) + (size_t)wib * stage_rows * p0.ldx;
+  unsigned sphase = 0;
+  if (lane == 0) { mbar_init(&sbars[wib], 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+  const uint32_t w_bytes = (uint32_t)p0.d * (uint32_t)td.ldw * 8u;
+  if (threadIdx.x == 0) {
+    mbar_init(&wbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  {  // copy the parameter blocks into shared memory (word by word: they are kernel parameters)
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(&p0); uint32_t* b = reinterpret_cast<uint32_t*>(&sp);
+    for (int w = threadIdx.x; w < (int)(sizeof(hb_k1_params) / 4); w += blockDim.x) b[w] = a[w];
+    const uint32_t* c = reinterpret_cast<const uint32_t*>(&q0); uint32_t* e = reinterpret_cast<uint32_t*>(&sq);
+    for (int w = threadIdx.x; w < (int)(sizeof(hb_k3_params) / 4); w += blockDim.x) e[w] = c[w];
+  }
+  if (threadIdx.x <= 2 * HB_MAX_NCR) s_cnt[threadIdx.x] = 0ull;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&wbar, w_bytes);
+    for (uint32_t off = 0; off < w_bytes; off += 32768u) {
+      const uint32_t nbytes = (w_bytes - off) < 32768u ? (w_bytes - off) : 32768u;
+      tma_load_1d(reinterpret_cast<char*>(Ws) + off, reinterpret_cast<const char*>(td.W) + off, nbytes, &wbar);
+    }
+  }
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nl = p0.n_local;
+  const bool active = warp_id < nl;      // one chain per warp (the launcher sizes the grid that way)
+  unsigned errbits = 0;
+  bool w_ready = false;
+  long long ind_out = pp.ind_out0, pending = pp.pending0;
+  k1_headv hv;
+  if (active) k1_chain_head<32, TAPE>(sp, (uint32_t)pp.i0, pp.i0 - 2, warp_id, lane, hv, errbits);
+
+  for (long long i = pp.i0; i < pp.i1; ++i) {
+    const bool store = ((double)i > pp.burnin * (double)pp.t) && (i % pp.thin == 0);   // R/dream_parallel.R:263, :386
+    if (store) ind_out++;
+    if (threadIdx.x == 0) {
+      const bool flip = ((i - pp.i0) & 1) != 0;
+      double* xin = flip ? pp.XB : pp.XA; double* xout = flip ? pp.XA : pp.XB;
+      sp.X = xin; sp.gen = (uint32_t)i; sp.tape_g = i - 2;
+      sq.X = xin; sq.Xout = xout; sq.gen = (uint32_t)i;
+      sq.hist_x = (store && pp.hist_x) ? pp.hist_x + (size_t)(ind_out - 1) * nl * p0.d : nullptr;
+      sq.hist_l = (store && pp.hist_l) ? pp.hist_l + (size_t)(ind_out - 1) * nl * 3 : nullptr;
+      sq.hist_fx = (store && pp.hist_fx) ? pp.hist_fx + (size_t)(ind_out - 1) * nl : nullptr;
+      sq.lpost_hist_row = (i <= pp.H && pp.lpost_hist) ? pp.lpost_hist + (size_t)(i - 1) * nl : nullptr;
+      sq.accept_rec = pp.accept_rec ? pp.accept_rec + (size_t)(i - 2) * nl : nullptr;
+      sq.u_accept = pp.u_accept ? pp.u_accept + (size_t)(i - 2) * pp.tape_nct : nullptr;
+    }
+    __syncthreads();
+    long long tm[8];
+    const bool tr = pp.trace && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && i >= pp.i0 + 2 && i < pp.i0 + 6;
+    if (tr) tm[4] = clock64();
+    if (active)
+      fused_chain_step<ITER, TAPE, true>(sp, sq, td, Ws, xs, &wbar, w_ready, hv, lane, s_cnt, errbits, stage, &sbars[wib], sphase, tr ? tm : nullptr);
+    if (tr) tm[5] = clock64();
+    __syncthreads();
+    if (tr) tm[6] = clock64();
+    const bool upd = (i % pp.update_interval == 0);
+    pending += p0.nc;
+    // the per-generation counters stay in shared memory and reach the control block only when somebody reads them: at
+    // updateInterval boundaries (AR / CR rows) and at the end of the launch
+    if ((upd || i == pp.i1 - 1) && threadIdx.x <= 2 * HB_MAX_NCR) {
+      const unsigned long long v = s_cnt[threadIdx.x];
+      if (v) {
+        if (threadIdx.x == 0) atomicAdd(&q0.ctrl->n_acc_gen, v);
+        else if (threadIdx.x <= HB_MAX_NCR) atomicAdd(&q0.ctrl->n_id_gen[threadIdx.x - 1], v);
+        else atomicAdd(&q0.ctrl->n_acc_id_gen[threadIdx.x - 1 - HB_MAX_NCR], v);
+        s_cnt[threadIdx.x] = 0ull;
+      }
+    }
+    if (upd || i == pp.i1 - 1) __syncthreads();
+    // ---- grid-wide barrier: arrive, compute the NEXT generation's draws (they do not depend on the population) while the
+    // other CTAs arrive, then wait.  At updateInterval boundaries CTA 0 folds the AR / CR bookkeeping before it releases
+    // the others (they must not add the next generation's counts before the fold has zeroed the counters).
+    const unsigned round = (unsigned)(i - pp.i0 + 1);
+    if (threadIdx.x == 0) { __threadfence(); atomicAdd(&pp.bar[0], 1u); }
+    if (active && i + 1 < pp.i1) k1_chain_head<32, TAPE>(sp, (uint32_t)(i + 1), i - 1, warp_id, lane, hv, errbits);
+    if (threadIdx.x == 0) {
+      const unsigned target = gridDim.x * round;
+      if (!upd) {
+        while (*reinterpret_cast<volatile unsigned*>(&pp.bar[0]) < target) {}
+      } else if (blockIdx.x == 0) {
+        while (*reinterpret_cast<volatile unsigned*>(&pp.bar[0]) < target) {}
+        __threadfence();
+        hb_fin_params f{};
+        f.ctrl = q0.ctrl; f.nCR = p0.nCR; f.do_arcr = 1; f.out_ar = pp.out_ar; f.out_cr = pp.out_cr; f.ar_rows = pp.ar_rows;
+        f.n_eval_inc = pending;
+        hb_fin_counters(f);
+        __threadfence();
+        *reinterpret_cast<volatile unsigned*>(&pp.bar[1]) = round;
+      } else {
+        while (*reinterpret_cast<volatile unsigned*>(&pp.bar[1]) < round) {}
+      }
+      __threadfence();
+    }
+    if (upd) pending = 0;
+    __syncthreads();
+    if (tr) printf("[persist trace] gen %lld cta %d: setup %lld | sweep %lld | xp %lld | density %lld | accept+store %lld | block sync %lld | barrier+next head %lld cycles\n",
+                   i, (int)blockIdx.x, tm[0] - tm[4], tm[1] - tm[0], tm[2] - tm[1], tm[3] - tm[2], tm[5] - tm[3], tm[6] - tm[5], clock64() - tm[6]);
+  }
+  if (errbits) atomicOr(&q0.ctrl->err, errbits);
+}
+
+template <int ITER>
+cudaError_t launch_persist(const hb_k1_params& p, const hb_k3_params& q, const hb_fused_tdist& td, const hb_persist_params& pp,
+                           bool tape, int sm_count, cudaStream_t st) {
+  const int threads = 256, warps = threads / 32;
+  const long long blocks = (p.n_local + warps - 1) / warps;
+  const int stage_rows = (1 + 2 * p.delta) > 4 ? (1 + 2 * p.delta) : 4;
+  const size_t smem = ((size_t)p.d * td.ldw + (size_t)warps * ITER * 32 + (size_t)warps * stage_rows * p.ldx) * sizeof(double);
+  if (smem > 220 * 1024 || (((size_t)p.d * td.ldw * 8) & 15) || (p.ldx & 1)) return cudaErrorInvalidValue;
+  const void* fn = tape ? (const void*)hb_persist_small_kernel<ITER, true> : (const void*)hb_persist_small_kernel<ITER, false>;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem);
+  if (e != cudaSuccess) return e;
+  if (blocks > (long long)per_sm * sm_count) return cudaErrorCooperativeLaunchTooLarge;   // the grid barrier needs every CTA resident
+  void* args[] = {(void*)&p, (void*)&q, (void*)&td, (void*)&pp};
+  return cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(threads), args, smem, st);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1206,6 +1500,16 @@ cudaError_t hb_launch_k1(const hb_k1_params& p, bool tape_mode, int sm_count, cu
 
 bool hb_fused_small_eligible(long long n_local, int d, int sm_count) {
   return d > 16 && d <= 128 && !g_hb_force_wide && n_local < (long long)sm_count * 16 * 32 / 2;   // where hb_launch_k1 picks <32, ITER>
+}
+
+cudaError_t hb_launch_persist_small(const hb_k1_params& p, const hb_k3_params& q, const hb_fused_tdist& td,
+                                    const hb_persist_params& pp, bool tape_mode, int sm_count, cudaStream_t st) {
+  if (!hb_fused_small_eligible(p.n_local, p.d, sm_count) || p.past_sample || p.n_peers > 1 || q.adapt || q.n_runs > 1 ||
+      q.accept_in || q.lik22 || q.log_rows || pp.XA == pp.XB || pp.i1 <= pp.i0)
+    return cudaErrorInvalidValue;
+  if (p.d <= 32) return launch_persist<1>(p, q, td, pp, tape_mode, sm_count, st);
+  if (p.d <= 64) return launch_persist<2>(p, q, td, pp, tape_mode, sm_count, st);
+  return launch_persist<4>(p, q, td, pp, tape_mode, sm_count, st);
 }
 
 cudaError_t hb_launch_fused_small(const hb_k1_params& p, const hb_k3_params& q, const hb_fused_tdist& td, bool tape_mode,

@@ -534,37 +534,7 @@ __global__ void __launch_bounds__(256) hb_finalize_kernel(const hb_fin_params p)
     // next generation's shift (the sums of every slot of an interval were taken against the same, interval-start shift)
     if (sl == n_slots - 1) for (int k = threadIdx.x; k < d; k += blockDim.x) p.shift[k] += colsum[k] / n;
   }
-  if (threadIdx.x == 0) {
-    for (int q = 0; q < nCR; ++q) { c->n_id[q] += (double)c->n_id_gen[q]; c->n_id_gen[q] = 0ull; }   // :368-369
-    c->n_acc += (double)c->n_acc_gen; c->n_acc_gen = 0ull;                                          // :374
-    c->n_eval += (double)p.n_eval_inc;                                                              // :375
-    if (p.do_pcr) {                                         // R/dream_parallel.R:407-411
-      bool anypos = false, anynan = false;
-      for (int q = 0; q < nCR; ++q) { if (c->J[q] != c->J[q]) anynan = true; if (c->J[q] > 0) anypos = true; }
-      if (anynan) atomicOr(&c->err, HB_FLAG_J_NAN);
-      else if (anypos) {
-        double s = 0.0;
-        for (int q = 0; q < nCR; ++q) {
-          double v = c->J[q] / c->n_id[q];
-          if (v != v) v = 1.0 / nCR;                        // n_id == 0 -> NaN -> 1/nCR
-          c->pCR[q] = v; s += v;
-        }
-        for (int q = 0; q < nCR; ++q) c->pCR[q] = c->pCR[q] / s;
-      }
-    }
-    if (p.do_arcr) {                                        // :425-433
-      c->i_ar += 1;
-      const long long r = c->i_ar - 1;
-      c->cum_eval += c->n_eval;
-      if (r < p.ar_rows) {
-        p.out_ar[r + p.ar_rows] = c->n_acc / c->n_eval;
-        p.out_ar[r] = c->cum_eval;
-        p.out_cr[r] = c->cum_eval;
-        for (int q = 0; q < nCR; ++q) p.out_cr[r + p.ar_rows * (q + 1)] = c->pCR[q];
-      }
-      c->n_acc = 0; c->n_eval = 0;
-    }
-  }
+  if (threadIdx.x == 0) hb_fin_counters(p);
 }
 
 // ---- outlier pieces -------------------------------------------------------------------------------------

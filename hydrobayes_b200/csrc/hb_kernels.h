@@ -62,10 +62,30 @@ cudaError_t hb_launch_k1(const hb_k1_params& p, bool tape_mode, int sm_count, cu
 
 struct hb_k3_params;
 // ---- fused generation for small populations (hb_k1_propose.cu): K1 + t-distribution density + K3 in one launch ----
-struct hb_fused_tdist { const double* W; int ldw; int lik; double konst, df; };   // W = chol(C)^-1, dense upper triangle [d][ldw]
+struct hb_fused_tdist { const double* W; int ldw; int lik; double konst, df; };   // W = chol(C)^-1, dense upper triangle [d][ldw], zeros below
 bool hb_fused_small_eligible(long long n_local, int d, int sm_count);
 cudaError_t hb_launch_fused_small(const hb_k1_params& p, const hb_k3_params& q, const hb_fused_tdist& td, bool tape_mode,
                                   int sm_count, cudaStream_t st);
+
+// persistent variant: ONE cooperative launch runs generations [i0, i1) (all behind the adaptation period), grid barrier per
+// generation; the kernel derives the per-generation pointers itself
+struct hb_persist_params {
+  long long i0, i1;
+  double* XA; double* XB;   // generation i reads XA when (i - i0) is even, XB otherwise, and writes the other one
+  long long t; double burnin; int thin; int update_interval;
+  long long ind_out0;       // stored rows before generation i0
+  double* hist_x; double* hist_l; double* hist_fx;   // bases of the history arrays
+  double* lpost_hist; long long H;
+  uint8_t* accept_rec;      // base [t-1][n_local] or nullptr
+  const double* u_accept;   // tape base [n_gen][nct] or nullptr
+  long long tape_nct;
+  long long pending0;       // evaluations since the last AR / CR fold
+  double* out_ar; double* out_cr; long long ar_rows;
+  unsigned* bar;            // [2], zero at launch: arrivals, released round
+  int trace;                // HB_PERSIST_TRACE=1: per-phase clock counts of a few generations on stdout (diagnostics)
+};
+cudaError_t hb_launch_persist_small(const hb_k1_params& p, const hb_k3_params& q, const hb_fused_tdist& td,
+                                    const hb_persist_params& pp, bool tape_mode, int sm_count, cudaStream_t st);
 
 // ---- MT-DREAM (mt > 1): candidate selection and multi-try acceptance, R/dream_parallel.R:295-341 -----------------
 struct hb_mt_params {
@@ -149,6 +169,43 @@ struct hb_fin_params {
   long long n_eval_inc;   // nc (all ranks)
 };
 cudaError_t hb_launch_finalize(const hb_fin_params& p, cudaStream_t st);
+#ifdef __CUDACC__
+// the scalar part of the finalize step (one thread): fold the per-generation integer counters into n_id / n_acc / n_eval
+// (R/dream_parallel.R:368-375), the pCR update (:407-411) and the AR / CR rows (:425-433)
+__device__ __forceinline__ void hb_fin_counters(const hb_fin_params& p) {
+  hb_ctrl* c = p.ctrl;
+  const int nCR = p.nCR;
+  for (int q = 0; q < nCR; ++q) { c->n_id[q] += (double)c->n_id_gen[q]; c->n_id_gen[q] = 0ull; }   // :368-369
+  c->n_acc += (double)c->n_acc_gen; c->n_acc_gen = 0ull;                                          // :374
+  c->n_eval += (double)p.n_eval_inc;                                                              // :375
+  if (p.do_pcr) {                                         // R/dream_parallel.R:407-411
+    bool anypos = false, anynan = false;
+    for (int q = 0; q < nCR; ++q) { if (c->J[q] != c->J[q]) anynan = true; if (c->J[q] > 0) anypos = true; }
+    if (anynan) atomicOr(&c->err, HB_FLAG_J_NAN);
+    else if (anypos) {
+      double s = 0.0;
+      for (int q = 0; q < nCR; ++q) {
+        double v = c->J[q] / c->n_id[q];
+        if (v != v) v = 1.0 / nCR;                        // n_id == 0 -> NaN -> 1/nCR
+        c->pCR[q] = v; s += v;
+      }
+      for (int q = 0; q < nCR; ++q) c->pCR[q] = c->pCR[q] / s;
+    }
+  }
+  if (p.do_arcr) {                                        // :425-433
+    c->i_ar += 1;
+    const long long r = c->i_ar - 1;
+    c->cum_eval += c->n_eval;
+    if (r < p.ar_rows) {
+      p.out_ar[r + p.ar_rows] = c->n_acc / c->n_eval;
+      p.out_ar[r] = c->cum_eval;
+      p.out_cr[r] = c->cum_eval;
+      for (int q = 0; q < nCR; ++q) p.out_cr[r + p.ar_rows * (q + 1)] = c->pCR[q];
+    }
+    c->n_acc = 0; c->n_eval = 0;
+  }
+}
+#endif
 
 // ---- per-run bookkeeping (sequential sweep and batched independent runs): one CTA per run ---------------
 struct hb_runfin_params {

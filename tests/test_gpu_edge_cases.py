@@ -153,10 +153,13 @@ def test_random_configurations_device(hb, oracle, case):
 @pytest.mark.parametrize("bound", [A.HB_BOUND_NONE, A.HB_BOUND_BOUND, A.HB_BOUND_REFLECT, A.HB_BOUND_FOLD])
 @pytest.mark.parametrize("native", [False, True])
 @pytest.mark.parametrize("d", [20, 40, 100])
-def test_fused_small_population_generation(hb, oracle, monkeypatch, bound, native, d):
-    # EXPERIMENTAL path, opt-in with HB_FUSED=1: small populations outside the adaptation period run proposal + log-density +
-    # accept as ONE launch with a double-buffered population (hb_fused_small_kernel): parity with the oracle, and identical
-    # decisions to the default three-kernel path
+@pytest.mark.parametrize("persist", ["1", "0"])
+def test_fused_small_population_generation(hb, oracle, monkeypatch, bound, native, d, persist):
+    # Small populations outside the adaptation period (the default path for them): proposal + log-density + accept fused
+    # with a double-buffered population -- as ONE cooperative launch per slice with a grid barrier per generation
+    # (hb_persist_small_kernel, HB_PERSIST unset / 1) or one launch per generation (hb_fused_small_kernel, HB_PERSIST=0):
+    # parity with the oracle, and identical decisions to the three-kernel path (HB_FUSED=0)
+    monkeypatch.setenv("HB_PERSIST", persist)
     nc, t = 37, 90
     kw = {}
     cfg = A.default_config(nc=nc, t=t, d=d, lik=2, seed=9 + d, adapt=0.2, thin=3, store_fx=1, record_accept=1,
@@ -179,7 +182,7 @@ def test_fused_small_population_generation(hb, oracle, monkeypatch, bound, nativ
         H.assert_run_parity(dev, ora, rtol=1e-11)
         tape_kw = dict(tape=rec)
     assert 0.03 < ora["accept"].mean() < 0.9
-    monkeypatch.setenv("HB_FUSED", "0")                            # the same run through K1 / K2 / K3 (the default)
+    monkeypatch.setenv("HB_FUSED", "0")                            # the same run through K1 / K2 / K3
     ref = H.run_device(cfg_t, "t_distribution", x0, **tape_kw, **kw)
     assert np.array_equal(ref["accept"], dev["accept"])
     np.testing.assert_allclose(dev["chain"], ref["chain"], rtol=1e-12, equal_nan=True)

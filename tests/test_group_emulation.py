@@ -66,12 +66,17 @@ def _compare(full, shards, cfg, world):
 
 @pytest.fixture
 def pieces_env():
-    old = os.environ.get("HB_PIECES")
+    # bit-for-bit comparisons need the same kernel variant on both sides: the single-handle reference run is forced onto the
+    # three-kernel path the sharded run uses (a small single population would otherwise take the fused generation kernel,
+    # whose log-density sums the quadratic form in FMA order -- same decisions, last-bit differences in ll)
+    old = {k: os.environ.get(k) for k in ("HB_PIECES", "HB_FUSED")}
+    os.environ["HB_FUSED"] = "0"
     yield
-    if old is None:
-        os.environ.pop("HB_PIECES", None)
-    else:
-        os.environ["HB_PIECES"] = old
+    for k, v in old.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
 
 
 @pytest.mark.parametrize("world,pieces", [(2, 1), (2, 3), (4, 2), (8, 1)])

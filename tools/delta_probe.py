@@ -19,7 +19,12 @@ for name, force, pieces in modes:
     cfg = A.default_config(nc=nc, t=t, d=d, lik=2, seed=1, thin=100)
     with Sampler(cfg, 0) as s:
         s.set_target("t_distribution"); s.set_initial(x0)
-        s.run(100)                                   # adaptation period (70 generations) + warm-up
+        s.run(19)
+        ta = time.perf_counter(); s.run(40); ta = (time.perf_counter() - ta) / 40      # generations 21..60: adaptation period (i <= 70)
+        s.profile(True); s.run(10); s.profile(False)
+        ka = {k: round(s.kernel_ms(k)[0] / max(s.kernel_ms(k)[1], 1) * 1e3, 1) for k in ("K1", "K2", "K3", "FIN", "OUTLIER", "XCHG", "APPLY") if s.kernel_ms(k)[1]}
+        print(f"{name:12s}: adaptation period {ta * 1e6:8.1f} us/gen wall; us/launch {ka}", flush=True)
+        s.run(31)                                    # leave the adaptation period (70 generations) + warm-up
         l0 = s.timing()
         t0 = time.perf_counter(); s.run(500); dt = time.perf_counter() - t0
         l1 = s.timing()

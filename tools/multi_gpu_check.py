@@ -47,6 +47,9 @@ def run(cfg, target, x0, local, rank=0, world=1, uid=None, kw={}, peer=False, sh
 
 
 def main():
+    # same kernel variant on both sides of the bit-for-bit comparison (the single-GPU reference run of these small
+    # populations would otherwise take the fused generation kernel: same decisions, last-bit differences in ll)
+    os.environ["HB_FUSED"] = "0"
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))

@@ -5,7 +5,8 @@ for f in sys.argv[1:]:
     except Exception as e:
         print(f, "unreadable", e); continue
     r = j.get("roofline") or {}
-    print(f"{f}: N={j['n_gpus']} value={j['value']/1e9:.3f} G  ms/gen={j['ms_per_step']/10:.4f}  launches={j['gpu_launches']}  e2e={(j.get('e2e') or {}).get('value', 0)/1e9:.3f} G")
+    ss=j.get("steady_state") or {}
+    print(f"{f}: steady={ss.get('value',0)/1e9:.3f} G ({ss.get('ms_per_generation',0):.4f} ms/gen) N={j['n_gpus']} value={j['value']/1e9:.3f} G  ms/gen={j['ms_per_step']/10:.4f}  launches={j['gpu_launches']}  e2e={(j.get('e2e') or {}).get('value', 0)/1e9:.3f} G")
     if r:
         print("   ms/launch", {k: round(v, 4) for k, v in r["kernel_ms_per_launch"].items()})
         print("   launches/gen", r.get("launches_per_generation"))
