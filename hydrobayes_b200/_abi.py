@@ -163,6 +163,8 @@ def lib() -> C.CDLL:
         "hb_rstat_runs": ([hp, _dp], C.c_int),
         "hb_wait_idle": ([], None),
         "hb_host_prefault": ([C.c_void_p, C.c_size_t, C.c_int], C.c_int),
+        "hb_host_register": ([C.c_void_p, C.c_size_t], C.c_int),
+        "hb_host_unregister": ([C.c_void_p], C.c_int),
         "hb_test_force_wide": ([C.c_int], C.c_int),
         "hb_ind_out": ([hp], C.c_int64),
         "hb_get_timing": ([hp, _dp, _i64p], C.c_int),
@@ -188,6 +190,6 @@ EXPORTED_SYMBOLS = [
     "hb_last_error", "hb_set_bounds", "hb_set_prior_normal", "hb_set_lik_args", "hb_set_obs", "hb_set_target", "hb_set_target_batched",
     "hb_set_initial", "hb_set_initial_rows", "hb_set_tape", "hb_comm_unique_id", "hb_comm_init", "hb_peer_export", "hb_peer_import", "hb_run", "hb_group_attach", "hb_group_run", "hb_sync", "hb_out_dims",
     "hb_fetch_chain", "hb_fetch_chain_rows", "hb_fetch_fx", "hb_fetch_ar", "hb_fetch_cr", "hb_fetch_rstat",
-    "hb_fetch_state", "hb_fetch_accept", "hb_fetch_outliers", "hb_rstat", "hb_rstat_runs", "hb_wait_idle", "hb_host_prefault", "hb_test_force_wide", "hb_ind_out", "hb_get_timing", "hb_profile",
+    "hb_fetch_state", "hb_fetch_accept", "hb_fetch_outliers", "hb_rstat", "hb_rstat_runs", "hb_wait_idle", "hb_host_prefault", "hb_host_register", "hb_host_unregister", "hb_test_force_wide", "hb_ind_out", "hb_get_timing", "hb_profile",
     "hb_get_kernel_ms", "hb_rstat_array", "hb_logdensity", "hb_hydromodel_series", "hb_fp64_peaks", "hb_divcheck",
 ]

@@ -1164,14 +1164,16 @@ void hb_destroy(hb_handle* h) {
   hb_seq_destroy(h);
   if (h->vt && h->tctx) h->vt->destroy(h->tctx);
   hb_nccl_destroy(h->comm);
+  std::vector<void*> ipc_close;       // peers' buffers mapped here, and this rank's exported buffers: released by the reaper thread
+  std::vector<void*> exported;        // (unmapping / freeing 1-3 GB takes 0.1-0.2 s and sat on the caller's critical path)
   if (h->delta_mode) {
     for (int r = 0; r < 8; ++r) {
-      if (h->peerX_opened[r]) cudaIpcCloseMemHandle(h->peerX_opened[r]);
-      if (h->arena_opened[r]) cudaIpcCloseMemHandle(h->arena_opened[r]);
+      if (h->peerX_opened[r]) ipc_close.push_back(h->peerX_opened[r]);
+      if (h->arena_opened[r]) ipc_close.push_back(h->arena_opened[r]);
     }
-    cudaFree(h->arena);
-    cudaFree(h->X); h->X = nullptr;   // IPC-exported buffers are released synchronously, right after this rank closed its
-                                      // own imports (only the private buffers below go to the reaper thread)
+    if (h->arena) exported.push_back(h->arena);
+    if (h->X) exported.push_back(h->X);
+    h->X = nullptr;
     if (h->side && h->side != h->stream) cudaStreamDestroy(h->side);
     if (h->side2 && h->side2 != h->stream) cudaStreamDestroy(h->side2);
     for (int q = 0; q < HB_MAX_PIECES; ++q) if (h->ev_piece[q]) cudaEventDestroy(h->ev_piece[q]);
@@ -1197,7 +1199,12 @@ void hb_destroy(hb_handle* h) {
     for (void* p : ptrs) if (p) dead.push_back(p);
     for (void* p : h->tape_allocs) dead.push_back(p);
     const int dev = h->device;
-    g_reaper.add(std::thread([dead, dev]() { cudaSetDevice(dev); for (void* p : dead) cudaFree(p); }));
+    g_reaper.add(std::thread([dead, ipc_close, exported, dev]() {
+      cudaSetDevice(dev);
+      for (void* p : ipc_close) cudaIpcCloseMemHandle(p);   // this rank's imports first, then its own exported buffers
+      for (void* p : exported) cudaFree(p);
+      for (void* p : dead) cudaFree(p);
+    }));
   }
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1673,6 +1680,35 @@ int hb_fetch_chain_rows(hb_handle* h, int64_t row0, int64_t nrows, double* out) 
   size_t want = std::min<size_t>((size_t)64 << 20, total);
   if (want < per_chain) want = per_chain;
   if (h->stage_bytes < 2 * want) { if (h->stage) cudaFree(h->stage); h->stage = nullptr; CK(cudaMalloc((void**)&h->stage, 2 * want)); h->stage_bytes = 2 * want; }
+  {  // a page-locked destination (hb_host_register, cudaHostAlloc): the transposed chunks go straight into it by DMA at
+     // PCIe rate, no pinned ring and no copier threads (which the ranks of a node would have to share)
+    cudaPointerAttributes at{};
+    const bool pinned_dst = cudaPointerGetAttributes(&at, out) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned_dst) {
+      const size_t half = h->stage_bytes / 2;
+      const long long chunk = (long long)(half / per_chain);
+      const long long n_chunks = (nl + chunk - 1) / chunk;
+      cudaEvent_t ev[2] = {nullptr, nullptr};
+      cudaError_t e = cudaSuccess;
+      for (long long k = 0; k < n_chunks && e == cudaSuccess; ++k) {
+        const long long c0 = k * chunk, ncs = std::min(chunk, nl - c0);
+        char* dst = reinterpret_cast<char*>(h->stage) + (size_t)(k & 1) * half;
+        if (ev[k & 1]) e = cudaStreamWaitEvent(h->stream, ev[k & 1], 0);   // stream order already covers it; kept for clarity
+        if (e == cudaSuccess) e = hb_launch_chain_transpose(h->hist_x, h->hist_l, h->out_t, row0, nrows, h->ind_out, nl, h->d, c0, ncs,
+                                                            reinterpret_cast<double*>(dst), h->stream);
+        h->launches++;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(reinterpret_cast<char*>(out) + (size_t)c0 * per_chain, dst, per_chain * (size_t)ncs, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess && !ev[k & 1]) e = cudaEventCreateWithFlags(&ev[k & 1], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(ev[k & 1], h->stream);
+      }
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+      for (auto& x : ev) if (x) cudaEventDestroy(x);
+      if (e != cudaSuccess) return fail(h, HB_ERR_CUDA, "chain fetch (direct) failed: %s", cudaGetErrorString(e));
+      timing_note("fetch (direct)", now_s() - t_begin, (double)total);
+      return HB_OK;
+    }
+  }
   if (int rc = pin_acquire(h, 2 * ((size_t)64 << 20) > 2 * want ? 2 * ((size_t)64 << 20) : 2 * want)) return rc;
   const size_t half = std::min(h->stage_bytes, h->pin_bytes) / 2;
   const long long chunk = (long long)(half / per_chain);
@@ -1739,6 +1775,22 @@ int hb_host_prefault(void* p, size_t bytes, int n_threads) {
       for (size_t o = lo; o < hi; o += 4096) reinterpret_cast<volatile char*>(base)[o] = 0;
     });
   for (auto& x : th) x.join();
+  return HB_OK;
+}
+
+// Page-lock a host result array (after hb_host_prefault, from the same helper thread, while hb_run is busy) so that
+// hb_fetch_chain moves it by direct DMA.  Returns HB_ERR_CUDA when the pages cannot be locked (RLIMIT_MEMLOCK): the
+// caller simply keeps the pageable array and the fetch takes the pinned-ring path.
+int hb_host_register(void* p, size_t bytes) {
+  if (!p || !bytes) return HB_ERR_INVALID;
+  const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+  if (e != cudaSuccess) { cudaGetLastError(); return HB_ERR_CUDA; }
+  return HB_OK;
+}
+int hb_host_unregister(void* p) {
+  if (!p) return HB_ERR_INVALID;
+  const cudaError_t e = cudaHostUnregister(p);
+  if (e != cudaSuccess) { cudaGetLastError(); return HB_ERR_CUDA; }
   return HB_OK;
 }
 

@@ -29,6 +29,22 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(_dp)
 
 
+_PINNED = {}     # page-locked result arrays (address -> array) waiting for their background cudaHostUnregister
+
+
+def _unpin_later(arr):
+    """The result array was page-locked for the fetch; unlocking 10 GB takes a few 100 ms, so it happens on a helper thread
+    after the call has returned (the array stays valid and usable throughout; the thread holds a reference to it)."""
+    import threading
+    if _PINNED.pop(arr.ctypes.data, None) is None:
+        return
+    L = A.lib()
+
+    def work(a=arr):
+        L.hb_host_unregister(a.ctypes.data)
+    threading.Thread(target=work, daemon=False).start()
+
+
 class Sampler:
     """Owns an ``hb_handle``.  Thin: every method is one C-ABI call."""
 
@@ -174,8 +190,18 @@ class Sampler:
         out = np.empty((dm["out_t"], self.cfg.d + 3, n), order="F")
         th = None
         if prefault and out.nbytes >= (64 << 20) and os.environ.get("HB_NO_PREFAULT") != "1":
-            th = threading.Thread(target=self.L.hb_host_prefault, args=(out.ctypes.data, out.nbytes, 0), daemon=True)
-            th.start()                                   # ctypes releases the GIL for the duration of the call
+            L = self.L
+            # page-locking the result for a direct-DMA fetch is OFF by default: measured on the C4 result (9.5 GB),
+            # cudaHostRegister pins at ~5 GB/s and serialises with the kernel launches of the running loop (the enqueue of
+            # 999 generations took 1.3 s instead of 0.06 s), which costs more than the 35 ms the direct fetch saves
+            pin = os.environ.get("HB_PIN") == "1"
+
+            def touch_and_pin():                          # ctypes releases the GIL for the duration of the calls
+                L.hb_host_prefault(out.ctypes.data, out.nbytes, 0)
+                if pin and L.hb_host_register(out.ctypes.data, out.nbytes) == A.HB_OK:
+                    _PINNED[out.ctypes.data] = out        # hb_fetch_chain then writes it by direct DMA; released by _unpin_later
+            th = threading.Thread(target=touch_and_pin, daemon=True)
+            th.start()
         return out, th
 
     def fetch_chain(self, n_chains: Optional[int] = None, out: Optional[np.ndarray] = None) -> np.ndarray:
@@ -448,6 +474,7 @@ def _drive(sweep, fun, extra, lik, par_info, nc, t, d, burnin, adapt, updateInte
         if toucher is not None:
             toucher.join()
         chain = s.fetch_chain(n_shard, out=chain_buf)   # sharded: this rank's chains, chain[out_t, d+3, nc/world]
+        _unpin_later(chain_buf)
         ar, cr = s.fetch_ar_cr()
         out = {"chain": chain, "rank": rank, "world": world}
         names = par_info.get("names") or [f"par{k + 1}" for k in range(d)]

@@ -234,6 +234,11 @@ int hb_fetch_chain_rows(hb_handle* h, int64_t row0, int64_t nrows, double* out);
  * result pages are faulted in up front; a host that allocates uninitialised memory (numpy.empty) can call this from a
  * helper thread while hb_run is busy, so that hb_fetch_chain copies into resident pages.  n_threads <= 0: default. */
 int hb_host_prefault(void* p, size_t bytes, int n_threads);
+/* Page-lock / release a host result array (cudaHostRegister): hb_fetch_chain then writes it by direct DMA at PCIe rate
+ * instead of through the pinned ring and copier threads.  Optional; meant to run in the same helper thread as
+ * hb_host_prefault while hb_run is busy.  HB_ERR_CUDA = the pages could not be locked (keep the pageable array). */
+int hb_host_register(void* p, size_t bytes);
+int hb_host_unregister(void* p);
 int hb_fetch_fx(hb_handle* h, double* fx);                 /* [out_t, nct, m] */
 int hb_fetch_ar(hb_handle* h, double* ar);                 /* run-major blocks of [ar_rows, ar_cols] */
 int hb_fetch_cr(hb_handle* h, double* cr);
