@@ -353,10 +353,23 @@ __device__ __forceinline__ double div_by_recip(double a, double b, double y) {
   return __fma_rn(r, y, q0);
 }
 
+// Sum of squared residuals over the series.  ncu (profiles/r02_c3_hydro_full.txt) shows the HydroModel kernels bound by
+// the fp64 pipe (74 % of its cycles active, 11 fp64 instructions per time step), so the sum is kept cheap: FOUR running
+// sums, term t goes to sum t mod 4 as one FMA (e*e + s), folded at the end as (s0 + s1) + (s2 + s3).  A Kahan sum cost four
+// dependent fp64 instructions per term; four plain sums of ~900 positive terms each stay within ~1e-14 relative of the
+// oracle's long-double sum (the tests hold 1e-12).  Every HydroModel kernel uses the same slots, so the single-run and the
+// batched kernels return identical values for the same series.
+struct hydro_sum {
+  double s[4];
+  __device__ __forceinline__ hydro_sum() { s[0] = 0.0; s[1] = 0.0; s[2] = 0.0; s[3] = 0.0; }
+  template <int R> __device__ __forceinline__ void add_sq(double e) { s[R] = __fma_rn(e, e, s[R]); }
+  __device__ __forceinline__ double total() const { return (s[0] + s[1]) + (s[2] + s[3]); }
+};
+
 // One chain per thread.  P and obs (T_pad doubles each, T_pad even so that the byte count is a multiple of 16) are
 // staged once per CTA.  Per step (R/test_HydroModel.R:30-32): S = (P_i*Dt + S)/(1 + K*Dt), Y_i = K*S with Dt = 1, a
 // true IEEE division.  The likelihood flag is folded into the sweep as an epilogue (calc_ll, R/internals.R:3-23):
-//   31  glue_shape*log(max(1 - sse/sst, 0))                                   (:13-14)   sse Kahan-summed
+//   31  glue_shape*log(max(1 - sse/sst, 0))                                   (:13-14)   sse: hydro_sum
 //   21  -m/2 log(2 pi) - sum(log(abc_e)) - 0.5 sum((abc_rho(sim,obs)/abc_e)^2)  (:8-10)  abc_rho = "abc_distfun" = |sim-obs|
 //   22  min(abc_e - abc_rho(sim,obs))                                         (:11-12)
 //   99  lik_fun(sim, obs), lik_fun = "fun_lik" = -n/2 log(sum((sim-obs)^2))    (:15-16; examples/script_examples.R:503-507)
@@ -391,24 +404,30 @@ __global__ void __launch_bounds__(256) hb_hydro_kernel(const double* __restrict_
   if (K < 0) { atomicOr(err, HB_FLAG_TARGET_DOMAIN); ll[j] = NAN; return; }   // R/test_HydroModel.R:18-19
   const double den = 1.0 + K * 1.0;
   const double rden = __ddiv_rn(1.0, den);
-  double S = 1.0, sse = 0.0, comp = 0.0, vmin = INFINITY;
-#pragma unroll 4
-  for (int i = 0; i < T; ++i) {
+  double S = 1.0, vmin = INFINITY;
+  hydro_sum acc;
+  auto step = [&](int i, auto slot) {
+    constexpr int R = decltype(slot)::value;
     S = div_by_recip(__dadd_rn(sP[i], S), den, rden);         // (forcing[i]*Dt + S0) / (1 + param*Dt), Dt = 1
-    const double e = __dadd_rn(__dmul_rn(K, S), -sO[i]);      // Y[i] - obs[i]
+    const double e = __fma_rn(K, S, -sO[i]);                  // Y[i] - obs[i]  (one rounding instead of two: <= 1 ulp of Y)
     if (LIK == 22) {
       const double v = (EVEC ? sE[i] : e_scalar) - fabs(e);   // abc_e - rho
       if (v < vmin || v != v) vmin = v;
+    } else if (LIK == 21) {
+      acc.template add_sq<R>(__ddiv_rn(fabs(e), EVEC ? sE[i] : e_scalar));   // (rho/abc_e)^2
     } else {
-      double q;
-      if (LIK == 21) { const double r = __ddiv_rn(fabs(e), EVEC ? sE[i] : e_scalar); q = __dmul_rn(r, r); }   // (rho/abc_e)^2
-      else q = e * e;
-      const double y = q - comp;
-      const double t = sse + y;
-      comp = (t - sse) - y;
-      sse = t;
+      acc.template add_sq<R>(e);
     }
+  };
+  int i = 0;
+  for (; i + 4 <= T; i += 4) {
+    step(i, std::integral_constant<int, 0>()); step(i + 1, std::integral_constant<int, 1>());
+    step(i + 2, std::integral_constant<int, 2>()); step(i + 3, std::integral_constant<int, 3>());
   }
+  if (i < T) step(i, std::integral_constant<int, 0>());
+  if (i + 1 < T) step(i + 1, std::integral_constant<int, 1>());
+  if (i + 2 < T) step(i + 2, std::integral_constant<int, 2>());
+  const double sse = acc.total();
   if (LIK == 31) { const double nse = 1.0 - sse / sst; ll[j] = glue_shape * log(nse > 0.0 ? nse : 0.0); }
   else if (LIK == 21) ll[j] = konst - 0.5 * sse;              // konst = -m/2 log(2 pi) - sum(log(abc_e)), host long double
   else if (LIK == 22) ll[j] = vmin;
@@ -439,13 +458,23 @@ __device__ __forceinline__ long long hydro_po_index(long long run, int t, int T)
   return ((run >> 5) * (long long)T + t) * 32 + (run & 31);
 }
 
-__device__ __forceinline__ void hydro_step(double2 v, double K, double den, double rden, double& S, double& sse, double& comp) {
+template <int R>
+__device__ __forceinline__ void hydro_step(double2 v, double K, double den, double rden, double& S, hydro_sum& acc) {
   S = div_by_recip(__dadd_rn(v.x, S), den, rden);                      // R/test_HydroModel.R:30
-  const double e = __dadd_rn(__dmul_rn(K, S), -v.y);                   // Y_i - obs_i, R/test_HydroModel.R:32
-  const double y = e * e - comp;
-  const double tt = sse + y;
-  comp = (tt - sse) - y;
-  sse = tt;
+  acc.add_sq<R>(__fma_rn(K, S, -v.y));                                 // (Y_i - obs_i)^2, R/test_HydroModel.R:32
+}
+// n consecutive time steps t0 .. t0 + n - 1 (t0 a multiple of 4) of one run; `at(t)` returns {P_t, obs_t}
+template <typename F>
+__device__ __forceinline__ void hydro_steps(F at, int n, double K, double den, double rden, double& S, hydro_sum& acc) {
+  int t = 0;
+#pragma unroll 2
+  for (; t + 4 <= n; t += 4) {
+    hydro_step<0>(at(t), K, den, rden, S, acc); hydro_step<1>(at(t + 1), K, den, rden, S, acc);
+    hydro_step<2>(at(t + 2), K, den, rden, S, acc); hydro_step<3>(at(t + 3), K, den, rden, S, acc);
+  }
+  if (t < n) hydro_step<0>(at(t), K, den, rden, S, acc);
+  if (t + 1 < n) hydro_step<1>(at(t + 1), K, den, rden, S, acc);
+  if (t + 2 < n) hydro_step<2>(at(t + 2), K, den, rden, S, acc);
 }
 
 // generic batched path (any item -> run mapping): direct loads from the tiled layout
@@ -461,10 +490,10 @@ __global__ void __launch_bounds__(128) hb_hydro_items_kernel(const double* __res
   if (K < 0) { atomicOr(err, HB_FLAG_TARGET_DOMAIN); ll[i] = NAN; return; }
   const double den = 1.0 + K * 1.0;
   const double rden = __ddiv_rn(1.0, den);
-  double S = 1.0, sse = 0.0, comp = 0.0;
-#pragma unroll 8
-  for (int t = 0; t < T; ++t) hydro_step(PO[hydro_po_index(run, t, T)], K, den, rden, S, sse, comp);
-  const double nse = 1.0 - sse / sst[run];
+  double S = 1.0;
+  hydro_sum acc;
+  hydro_steps([&](int t) { return PO[hydro_po_index(run, t, T)]; }, T, K, den, rden, S, acc);
+  const double nse = 1.0 - acc.total() / sst[run];
   ll[i] = glue_shape * log(nse > 0.0 ? nse : 0.0);
 }
 
@@ -503,23 +532,20 @@ __global__ void __launch_bounds__(32) hb_hydro_runs_tma_kernel(const double* __r
   if (bad) atomicOr(err, HB_FLAG_TARGET_DOMAIN);
   const double den = 1.0 + K * 1.0;
   const double rden = __ddiv_rn(1.0, den);
-  double S = 1.0, sse = 0.0, comp = 0.0;
+  static_assert(HYDRO_TT % 4 == 0, "a stage must hold whole groups of the four running sums");
+  double S = 1.0;
+  hydro_sum acc;
   for (int s = 0; s < n_stages; ++s) {
     mbar_wait(&bars[s & 1], (s >> 1) & 1);
     const double2* __restrict__ buf = ring + (size_t)(s & 1) * HYDRO_TT * 32 + lane;
     const int t0 = s * HYDRO_TT;
     const int nt = (T - t0) < HYDRO_TT ? (T - t0) : HYDRO_TT;
-    if (nt == HYDRO_TT) {
-#pragma unroll 8
-      for (int t = 0; t < HYDRO_TT; ++t) hydro_step(buf[t * 32], K, den, rden, S, sse, comp);
-    } else {
-      for (int t = 0; t < nt; ++t) hydro_step(buf[t * 32], K, den, rden, S, sse, comp);
-    }
+    hydro_steps([&](int t) { return buf[t * 32]; }, nt, K, den, rden, S, acc);
     __syncwarp();                                                                        // every lane is done with the stage
     if (lane == 0 && s + 2 < n_stages) issue(s + 2);
   }
   if (valid) {
-    const double nse = 1.0 - sse / sst[i];
+    const double nse = 1.0 - acc.total() / sst[i];
     ll[i] = bad ? NAN : glue_shape * log(nse > 0.0 ? nse : 0.0);
   }
 }

@@ -40,14 +40,36 @@ def test_drawlog_roundtrip(oracle, tmp_path):
     assert r1["outlier"] == r0["outlier"]
 
 
-def test_oracle_reproduces_real_r_run(oracle):
-    draws = os.path.join(GOLD, "reference_c1_draws.csv"); chain = os.path.join(GOLD, "reference_c1_chain.csv")
+def _reference_cases():
+    d = 100
+    P_obs = np.loadtxt(os.path.join(GOLD, "reference_hydro_inputs.csv"), delimiter=",", skiprows=1)
+    return {
+        "c1": (A.default_config(nc=10, t=5000, d=1, lik=1, seed=1312, rng_mode=A.HB_RNG_TAPE), "mixture", H.x0_mixture(10), {}),
+        "tdist": (A.default_config(nc=64, t=200, d=d, lik=2, seed=1312, rng_mode=A.HB_RNG_TAPE), "t_distribution", H.x0_tdist(64, d), {}),
+        "hydro": (A.default_config(nc=10, t=300, d=1, lik=31, glue_shape=50.0, prior=A.HB_PRIOR_UNIFORM, bound=A.HB_BOUND_BOUND,
+                                   seed=1312, rng_mode=A.HB_RNG_TAPE), "HydroModel", H.x0_hydro(10),
+                  dict(par_min=[0.01], par_max=[2.0], forcing=P_obs[:, 0], obs=P_obs[:, 1])),
+    }
+
+
+def test_reference_hydro_inputs_are_the_harness_series():
+    """the series the R recorder reads (tests/golden/reference_hydro_inputs.csv) is the harness's own synthetic catchment"""
+    P, obs = H.hydro_data(T=200)
+    got = np.loadtxt(os.path.join(GOLD, "reference_hydro_inputs.csv"), delimiter=",", skiprows=1)
+    np.testing.assert_array_equal(got[:, 0], P)
+    np.testing.assert_array_equal(got[:, 1], obs)
+
+
+@pytest.mark.parametrize("case", ["c1", "tdist", "hydro"])
+def test_oracle_reproduces_real_r_run(oracle, case):
+    """c1 pins the sampler logic, tdist pins mvtnorm::dmvt (d = 100), hydro pins HydroModel + the GLUE epilogue + bound_par"""
+    draws = os.path.join(GOLD, f"reference_{case}_draws.csv"); chain = os.path.join(GOLD, f"reference_{case}_chain.csv")
     if not (os.path.exists(draws) and os.path.exists(chain)):
-        pytest.skip("no recorded R run (Rscript tools/record_reference.R <HydroBayes> tests/golden/reference_c1): "
-                    "oracle <-> reference parity stays unpinned")
-    cfg = A.default_config(nc=10, t=5000, d=1, lik=1, seed=1312, rng_mode=A.HB_RNG_TAPE)
+        pytest.skip(f"no recorded R run (Rscript tools/record_reference.R <HydroBayes> tests/golden {case}): "
+                    "oracle <-> reference parity stays unpinned (Rscript is absent from the build image and the GPU boxes)")
+    cfg, target, x0, kw = _reference_cases()[case]
     tape, _ = RT.drawlog_to_tape(draws, cfg, oracle.Tape)
-    res = oracle.run(cfg, "mixture", H.x0_mixture(10), tape=tape)
+    res = oracle.run(cfg, target, x0, tape=tape, **kw)
     assert res["rc"] == 0, res["err"]
-    ref = np.loadtxt(chain, delimiter=",", skiprows=1)         # write.csv of res$chain[, , ]: [t, (d+3)*nc]
-    np.testing.assert_allclose(res["chain"].reshape(5000, -1, order="F"), ref, rtol=1e-12, equal_nan=True)
+    ref = np.loadtxt(chain, delimiter=",", skiprows=1)         # write.csv of matrix(res$chain, nrow = out_t): [t, (d+3)*nc]
+    np.testing.assert_allclose(res["chain"].reshape(cfg.t, -1, order="F"), ref, rtol=1e-12, equal_nan=True)
