@@ -418,7 +418,7 @@ def _make_config(sweep, lik, par_info, nc, t, d, burnin, adapt, updateInterval, 
 def _drive(sweep, fun, extra, lik, par_info, nc, t, d, burnin, adapt, updateInterval, delta, c_val, c_star, nCR, p_g,
            beta0, thin, outlier_check, obs, abc_rho, abc_e, glue_shape, lik_fun, past_sample, m0, archive_update,
            psnooker, mt, checkConvergence, verbose, seed, tape, device, record_accept, store_fx, slice_generations,
-           default_prior, forcing, distributed=False, exchange=None):
+           default_prior, forcing, distributed=False, exchange=None, series_fx=False):
     if not isinstance(fun, str):
         raise A.HbError(A.HB_ERR_UNKNOWN_TARGET, "fun must be the NAME of a registered device target "
                                                  "(arbitrary closures stay off the GPU path)")
@@ -479,7 +479,13 @@ def _drive(sweep, fun, extra, lik, par_info, nc, t, d, burnin, adapt, updateInte
         out = {"chain": chain, "rank": rank, "world": world}
         names = par_info.get("names") or [f"par{k + 1}" for k in range(d)]
         out["chain_colnames"] = list(names) + ["lp", "ll", "lpost"]
+        # fx[out_t, nc, m] (R/dream_parallel.R:230, 394): scalar targets as in the reference; series targets (HydroModel,
+        # m == T) return None unless series_fx=True, which rebuilds fx[it, c, :] = HydroModel(forcing, chain[it, 0, c]) on the
+        # device from the stored chain (the reference's values except for the stale rows of SURVEY F9, see r-package/R/hb_drive.R)
         out["fx"] = s.fetch_fx(n_shard) if cfg.store_fx else None
+        if out["fx"] is None and series_fx and fun in _SERIES_TARGETS and d == 1 and data is not None:
+            ser = HydroModel(data, np.ascontiguousarray(chain[:, 0, :]).ravel())          # [out_t * n, T]
+            out["fx"] = ser.reshape(chain.shape[0], chain.shape[2], -1)
         pairs = s.fetch_outliers()
         out["outlier"] = _outlier_list(pairs, cfg, sweep)
         out["AR"] = ar
@@ -519,7 +525,7 @@ def dream_parallel(fun, *extra, lik=None, par_info=None, nc, t, d, burnin=0, ada
                    abc_e=None, glue_shape=None, lik_fun=None, past_sample=False, m0=None, archive_update=None,
                    psnooker=0, mt=1, ncores=1, checkConvergence=False, verbose=True,
                    seed=None, tape=None, device=0, record_accept=False, store_fx=True, slice_generations=None,
-                   forcing=None, distributed=False, exchange=None):
+                   forcing=None, distributed=False, exchange=None, series_fx=False):
     """DREAM, synchronous population sweep -- drop-in for HydroBayes::dream_parallel (R/dream_parallel.R:155-455).
 
     ``fun`` is the name of a registered device target ("mixture", "t_distribution", "HydroModel", or "fun_wrap_glue", the
@@ -533,18 +539,19 @@ def dream_parallel(fun, *extra, lik=None, par_info=None, nc, t, d, burnin=0, ada
     return _drive(A.HB_SWEEP_SYNCHRONOUS, fun, extra, lik, par_info, nc, t, d, burnin, adapt, updateInterval, delta,
                   c_val, c_star, nCR, p_g, beta0, thin, outlier_check, obs, abc_rho, abc_e, glue_shape, lik_fun,
                   past_sample, m0, archive_update, psnooker, mt, checkConvergence, verbose, seed, tape, device,
-                  record_accept, store_fx, slice_generations, "flat", forcing, distributed, exchange)
+                  record_accept, store_fx, slice_generations, "flat", forcing, distributed, exchange, series_fx)
 
 
 def dream(fun, *extra, lik=None, par_info=None, nc, t, d, burnin=0, adapt=0.1, updateInterval=10, delta=3, c_val=0.1,
           c_star=1e-12, nCR=3, p_g=0.2, beta0=1, thin=1, outlier_check=True, obs=None, abc_rho=None, abc_e=None,
           glue_shape=None, lik_fun=None, checkConvergence=False, verbose=True,
-          seed=None, tape=None, device=0, record_accept=False, store_fx=True, slice_generations=None, forcing=None):
+          seed=None, tape=None, device=0, record_accept=False, store_fx=True, slice_generations=None, forcing=None,
+          series_fx=False):
     """DREAM, sequential chain sweep -- drop-in for HydroBayes::dream (R/dream.R:126-316)."""
     return _drive(A.HB_SWEEP_SEQUENTIAL, fun, extra, lik, par_info, nc, t, d, burnin, adapt, updateInterval, delta,
                   c_val, c_star, nCR, p_g, beta0, thin, outlier_check, obs, abc_rho, abc_e, glue_shape, lik_fun,
                   False, None, None, 0, 1, checkConvergence, verbose, seed, tape, device, record_accept, store_fx,
-                  slice_generations, "uniform", forcing)
+                  slice_generations, "uniform", forcing, series_fx=series_fx)
 
 
 def R_stat(x) -> np.ndarray:

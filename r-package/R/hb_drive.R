@@ -5,7 +5,7 @@
 # call sequence is exercised through tests/mock_r (tests/test_r_glue.py).
 .hb_drive <- function(sweep, fun, dots, lik, par.info, nc, t, d, burnin, adapt, updateInterval, delta, c_val, c_star, nCR,
                       p_g, beta0, thin, outlier_check, obs, abc_rho, abc_e, glue_shape, lik_fun, past_sample, m0,
-                      archive_update, psnooker, mt, checkConvergence, verbose, seed, device) {
+                      archive_update, psnooker, mt, checkConvergence, verbose, seed, device, series_fx = FALSE) {
   timea <- Sys.time()
   if (is.null(lik)) stop("Argument 'lik' has to be one of {1,2,21,22}!")
   if (!is.character(fun) || !.Call(hbR_target_registered, fun))     # get(fun) of an arbitrary closure stays on the R path
@@ -57,7 +57,17 @@
   out_AR <- .Call(hbR_fetch_ar, h, matrix(NA_real_, dims[2], dims[3]))
   out_CR <- .Call(hbR_fetch_cr, h, matrix(NA_real_, dims[4], dims[5]))
   if (sweep == 0L) colnames(out_AR) <- c("n_eval", "accepted")       # R/dream_parallel.R:205
+  # fx: the reference keeps the raw target output of every stored state, fx[out_t, nc, m] (R/dream_parallel.R:230, 394).
+  # Targets with scalar output (m == 1) return it as in the reference.  For series targets (HydroModel: m == T values per
+  # chain and stored generation) the device keeps no series; fx is NULL unless series_fx = TRUE, which rebuilds
+  # fx[it, c, ] = HydroModel(forcing, chain[it, 1:d, c]) on the device from the stored chain -- the reference's values,
+  # except for the rows of a chain between an outlier reset and its next accepted proposal, where the reference's fx is
+  # the stale series of the replaced state (SURVEY F9).
   fx <- if (store_fx) .Call(hbR_fetch_fx, h, array(NA_real_, dim = c(out_t, nc, 1))) else NULL
+  if (is.null(fx) && series_fx && fun %in% c("HydroModel", "fun_wrap_glue") && d == 1 && length(dots)) {
+    ser <- .Call(hbR_hydromodel_series, as.numeric(dots[[1]]), as.numeric(chain[, 1, ]))   # [T, out_t * nc]
+    fx <- aperm(array(ser, dim = c(nrow(ser), out_t, nc)), c(2, 3, 1))
+  }
   op <- .Call(hbR_fetch_outliers, h)                                 # outl[[i]] <- check_out$outliers  (:418)
   outl <- list(NULL)
   n_chk <- floor(adapt * t / updateInterval)

@@ -133,6 +133,16 @@ SEXP hbR_rstat_array(SEXP x) {                      /* R_stat(x): x[t, d, n]  (R
   return out;
 }
 
+SEXP hbR_hydromodel_series(SEXP forcing, SEXP param) {   /* HydroModel(forcing, param_i) for every param_i: matrix [T, n] (R/test_HydroModel.R:17-36) */
+  if (TYPEOF(forcing) != REALSXP || TYPEOF(param) != REALSXP) error("forcing and param must be double vectors");
+  const R_xlen_t T = XLENGTH(forcing), n = XLENGTH(param);
+  SEXP out = PROTECT(allocMatrix(REALSXP, (int)T, (int)n));      /* column i = series of param_i: the library's [n][T] row-major */
+  char err[256];
+  if (hb_hydromodel_series(REAL(forcing), (int64_t)T, REAL(param), (int64_t)n, REAL(out), err, sizeof err) != HB_OK) error("%s", err);
+  UNPROTECT(1);
+  return out;
+}
+
 #define HB_CALLDEF(name, n) { #name, (DL_FUNC)&name, n }
 static const R_CallMethodDef hb_call_entries[] = {
   HB_CALLDEF(hbR_create, 2), HB_CALLDEF(hbR_destroy, 1), HB_CALLDEF(hbR_set_bounds, 3), HB_CALLDEF(hbR_set_obs, 2),
@@ -140,6 +150,7 @@ static const R_CallMethodDef hb_call_entries[] = {
   HB_CALLDEF(hbR_target_registered, 1), HB_CALLDEF(hbR_set_initial, 2), HB_CALLDEF(hbR_run, 2), HB_CALLDEF(hbR_out_dims, 1),
   HB_CALLDEF(hbR_fetch_chain, 2), HB_CALLDEF(hbR_fetch_ar, 2), HB_CALLDEF(hbR_fetch_cr, 2), HB_CALLDEF(hbR_fetch_fx, 2),
   HB_CALLDEF(hbR_fetch_rstat, 2), HB_CALLDEF(hbR_fetch_outliers, 1), HB_CALLDEF(hbR_rstat_array, 1),
+  HB_CALLDEF(hbR_hydromodel_series, 2),
   { NULL, NULL, 0 }
 };
 void R_init_HydroBayes(DllInfo* dll) {

@@ -188,3 +188,21 @@ def test_fused_small_population_generation(hb, oracle, monkeypatch, bound, nativ
     np.testing.assert_allclose(dev["chain"], ref["chain"], rtol=1e-12, equal_nan=True)
     np.testing.assert_array_equal(dev["AR"], ref["AR"])
     assert dev["timing"][1] < ref["timing"][1] - (t - 1 - int(0.2 * t)) , "the fused path was not taken"
+
+
+def test_series_fx_opt_in(hb, oracle):
+    """fx of a series target (HydroModel: m = T values per stored state, R/dream_parallel.R:230, 394) is not kept on the
+    device; series_fx=True rebuilds it from the stored chain, and it equals the reference's fx wherever that is not stale
+    (no outlier reset in this run, so everywhere)."""
+    P, obs = H.hydro_data(T=60)
+    nc, t = 12, 40
+    par = dict(initial="user", val_ini=H.x0_hydro(nc), prior="uniform", min=[0.01], max=[2.0], bound="bound")
+    kw = dict(lik=31, par_info=par, nc=nc, t=t, d=1, glue_shape=50.0, obs=obs, forcing=P, seed=3, verbose=False, outlier_check=False)
+    res = hb.dream_parallel("HydroModel", **kw)
+    assert res["fx"] is None
+    res = hb.dream_parallel("HydroModel", series_fx=True, **kw)
+    assert res["fx"].shape == (t, nc, 60)
+    np.testing.assert_array_equal(res["fx"][7, 3], hb.HydroModel(P, res["chain"][7, 0, 3]))
+    cfg = A.default_config(nc=nc, t=t, d=1, lik=31, glue_shape=50.0, prior=A.HB_PRIOR_UNIFORM, bound=A.HB_BOUND_BOUND, seed=3, outlier_check=0)
+    ora = oracle.run(cfg, "HydroModel", H.x0_hydro(nc), par_min=[0.01], par_max=[2.0], forcing=P, obs=obs)
+    np.testing.assert_allclose(res["chain"], ora["chain"], rtol=1e-9, equal_nan=True)

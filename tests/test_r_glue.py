@@ -57,8 +57,8 @@ def test_r_formals_match_the_reference_signature():
     want_par = ["fun", "...", "lik", "par.info", "nc", "t", "d", "burnin", "adapt", "updateInterval", "delta", "c_val", "c_star",
                 "nCR", "p_g", "beta0", "thin", "outlier_check", "obs", "abc_rho", "abc_e", "glue_shape", "lik_fun"]
     tails = {"dream_parallel": ["past_sample", "m0", "archive_update", "psnooker", "mt", "ncores", "checkConvergence", "verbose",
-                                "seed", "device"],
-             "dream": ["checkConvergence", "verbose", "seed", "device"]}
+                                "seed", "device", "series_fx"],
+             "dream": ["checkConvergence", "verbose", "seed", "device", "series_fx"]}
     text = src["hb_entry_points.R"]
     heads = {}
     for fn, tail in tails.items():
@@ -209,7 +209,7 @@ def test_r_sources_are_lexically_balanced():
     assert {"dream", "dream_parallel", "R_stat", ".hb_drive"} <= defined
     called = set(re.findall(r"(?<![\w.$])([.A-Za-z][\w.]*)\(", re.sub(r"#.*", "", text)))
     known = defined | {"function", "list", "c", "if", "for", "while", "stop", "match", "is.na", "is.null", "is.character", "as.integer",
-                       "as.numeric", "as.matrix", "nrow", "ncol", "storage.mode", "array", "matrix", "paste0", "dimnames", "colnames", "length", "floor", "max",
+                       "as.numeric", "as.matrix", "aperm", "nrow", "ncol", "storage.mode", "array", "matrix", "paste0", "dimnames", "colnames", "length", "floor", "max",
                        "seq_len", "invisible", "on.exit", "Sys.time", "sample.int", "txtProgressBar", "setTxtProgressBar", "close",
                        "prior_sample"}      # prior_sample: the reference's own R/internals.R:26-47, kept
     unknown = {c for c in called if c not in known and not c.startswith(".Call")}
