@@ -179,12 +179,14 @@ __device__ __forceinline__ void k1_chain_head(const hb_k1_params& p, uint32_t ge
 template <int G, int ITER, bool TAPE, bool CG = false, bool STAGE = false>
 __device__ __forceinline__ void k1_chain_body(const hb_k1_params& p, uint32_t gen, const k1_headv& hv, int lane, double (&xk)[ITER],
                                               double (&dxk)[ITER], unsigned& errbits,
-                                              double* stage = nullptr, uint64_t* sbar = nullptr, unsigned* sphase = nullptr) {
+                                              double* stage = nullptr, uint64_t* sbar = nullptr, unsigned* sphase = nullptr,
+                                              const double* Xcur = nullptr) {
   static_assert(!STAGE || G == 32, "row staging is written for one chain per warp");
   const int lg = lane & (G - 1);
   const unsigned gmask = hb_group_mask<G>(lane);
   const int d = p.d, ldx = p.ldx, nCR = p.nCR, delta = p.delta;
-  const double* src = p.past_sample ? p.Z : p.X;
+  const double* Xpop = Xcur ? Xcur : p.X;   // the persistent kernel alternates between two population buffers
+  const double* src = p.past_sample ? p.Z : Xpop;
   const double g_sn = hv.g_sn;
   const int D = hv.D, g_is_one = hv.g_is_one, id = hv.id;
   const bool snooker = hv.snooker;
@@ -193,7 +195,7 @@ __device__ __forceinline__ void k1_chain_body(const hb_k1_params& p, uint32_t ge
 #pragma unroll
   for (int q = 0; q < HB_MAX_DELTA; ++q) { pa[q] = hv.pa[q]; pb[q] = hv.pb[q]; }
   const hb_phx ph(p.seed, (uint64_t)hv.gch, gen);
-  const double* xrow = p.X + gl * (long long)ldx;
+  const double* xrow = Xpop + gl * (long long)ldx;
   const double* srcr = p.past_sample ? src : src + rbase * (long long)ldx;   // partner rows of this run
   // row q of the a / b partner sets (global memory, or the staged copy)
   auto row_a = [&](int q) -> const double* { return STAGE ? stage + (size_t)(1 + q) * ldx : srcr + pa[q] * (long long)ldx; };
@@ -408,27 +410,50 @@ __global__ void __launch_bounds__(256) hb_k1_kernel(const hb_k1_params p) {
 }
 
 
+// what changes from one generation to the next in the fused kernels (kept in registers; everything else is read from the
+// kernel parameters in the constant bank)
+struct fused_gen {
+  const double* Xin; double* Xout;          // population read by the proposals / written by the update
+  double* hist_x; double* hist_l; double* hist_fx; double* lpost_hist_row; uint8_t* accept_rec;
+  const double* u_accept;                    // tape row (replay) or nullptr
+  uint32_t gen;
+};
+__device__ __forceinline__ fused_gen fused_gen_of(const hb_k3_params& q) {
+  fused_gen g;
+  g.Xin = q.X; g.Xout = q.Xout; g.hist_x = q.hist_x; g.hist_l = q.hist_l; g.hist_fx = q.hist_fx;
+  g.lpost_hist_row = q.lpost_hist_row; g.accept_rec = q.accept_rec; g.u_accept = q.u_accept; g.gen = q.gen;
+  return g;
+}
+
 // One chain's whole generation for the warp that owns it: proposal, t-distribution log-density, Metropolis decision, state
 // update into q.Xout and history store.  Shared by the one-launch-per-generation kernel and the persistent kernel below.
 template <int ITER, bool TAPE, bool CG = false>
-__device__ __forceinline__ void fused_chain_step(const hb_k1_params& p, const hb_k3_params& q, const hb_fused_tdist& td,
+__device__ __forceinline__ void fused_chain_step(const hb_k1_params& p, const hb_k3_params& q, const hb_fused_tdist& td, const fused_gen& fg,
                                                  const double* __restrict__ Ws, double* __restrict__ xs, uint64_t* wbar, bool& w_ready,
                                                  const k1_headv& hv, int lane, unsigned long long* s_cnt, unsigned& errbits,
-                                                 double* stage, uint64_t* sbar, unsigned& sphase, long long* tm = nullptr) {
+                                                 double* stage, uint64_t* sbar, unsigned& sphase,
+                                                 const double* __restrict__ xs_all, double* __restrict__ zpart, bool has_chain,
+                                                 long long* tm = nullptr) {
+  // BLOCK-COLLECTIVE: every warp of the CTA calls this once per round (has_chain = false for a warp without a chain); the
+  // log-density of the CTA's eight proposals is computed cooperatively between two __syncthreads().
   constexpr unsigned FULL = 0xffffffffu;
+  constexpr int LDW_S = ITER * 32 + 4;   // row stride of W in shared memory: a compile-time constant, so the unrolled density
+                                         // loop addresses W with immediate offsets (no per-load address arithmetic)
   const int d = p.d, ldx = p.ldx;
     // ---------------- proposal (K1) ----------------
     double xk[ITER], dxk[ITER], xp[ITER];
-    const long long jl = hv.jl; const int id = hv.id;                    // one chain per warp: hv.valid == true
+    const long long jl = has_chain ? hv.jl : 0; const int id = has_chain ? hv.id : 0;
     if (tm) tm[0] = clock64();
-    k1_chain_body<32, ITER, TAPE, CG, true>(p, p.gen, hv, lane, xk, dxk, errbits, stage, sbar, &sphase);
+#pragma unroll
+    for (int m = 0; m < ITER; ++m) { xk[m] = 0.0; dxk[m] = 0.0; }
+    if (has_chain) k1_chain_body<32, ITER, TAPE, CG, true>(p, fg.gen, hv, lane, xk, dxk, errbits, stage, sbar, &sphase, fg.Xin);
     if (tm) tm[1] = clock64();
     double lp_part = 0.0;
 #pragma unroll
     for (int m = 0; m < ITER; ++m) {
       const int k = m * 32 + lane;
       xp[m] = 0.0;
-      if (k < d) {
+      if (k < d && has_chain) {
         double v = __dadd_rn(xk[m], dxk[m]);                            // R/internals.R:206
         if (!isfinite(v)) errbits |= HB_FLAG_PROP_NONFINITE;            // :209
         if (p.bound) v = hb_bound_par(v, p.pmin[k], p.pmax[k], p.bound);   // :210-214
@@ -447,59 +472,65 @@ __device__ __forceinline__ void fused_chain_step(const hb_k1_params& p, const hb
     __syncwarp();
 
     // ---------------- log-density (K2): dmvt, R/test_t_distribution.R:43 ----------------
-    // z_n = sum_{k <= n} xp_k W[k][n], lane owns columns n = 32 m + lane.  On B200 a dependent fp64 FMA chain advances one
-    // link per ~60 cycles (measured here: 6 500 cycles for 100 links; the plugin's DMMA sequence for a single chain is worse,
-    // 30 000 cycles, its tensor pipe lives on many independent tiles), so the chain is what bounds a warp-per-chain kernel:
-    // every column keeps FOUR partial sums over k = 4 j + r (16 independent chains per lane, 25 links each), folded as
-    // (s0 + s1) + (s2 + s3).  The strict lower triangle of W is stored as zeros (tdist_build), so no term needs a predicate:
-    // column block m runs k = 0 .. 32 m + 31 and the terms with k > n add xp_k * 0.  ll therefore differs from the DMMA
-    // plugin's in the last bits (<= 1e-13 relative); states and decisions are the same.
-    if (!w_ready) { mbar_wait(wbar, 0); w_ready = true; }                // W has landed (first chain of the launch only)
+    // z_n = sum_{k <= n} xp_k W[k][n] for the EIGHT proposals of the CTA at once.  A warp that streams W from shared memory
+    // for its own chain alone moves 75 KB per chain: eight warps saturate the SM's shared-memory bandwidth (measured: 6 500
+    // cycles of a 21 000-cycle generation, whatever the FMA arrangement).  Instead warp w takes work unit (m, h) = (w % ITER... ,
+    // half h of the k range of column block m): each W element is read once per CTA and feeds eight accumulators, the
+    // proposals come in as shared-memory broadcasts.  The two halves of a column meet in zpart and the warp that owns the
+    // chain folds them, squares and reduces.  The strict lower triangle of W is stored as zeros (tdist_build), so no term
+    // needs a predicate.  ll differs from the DMMA plugin's in the last bits (<= 1e-13 relative); states and decisions agree.
+    if (!w_ready) { mbar_wait(wbar, 0); w_ready = true; }                // W has landed (first round of the launch only)
+    __syncthreads();                                                     // the eight proposals are in xs_all
     if (tm) tm[2] = clock64();
-    double rss = 0.0;
     {
-      double z[ITER][4];
-      int ncol[ITER];
+      const int wib = threadIdx.x >> 5;
+      if (wib < 2 * ITER) {
+        const int m = wib >> 1, h = wib & 1;
+        const int kend = (m * 32 + 32 < d) ? m * 32 + 32 : d;
+        const int kmid = ((kend + 1) / 2 + 3) & ~3;                      // a multiple of four: whole unrolled groups in the first half
+        const int k0 = h ? (kmid < kend ? kmid : kend) : 0, k1 = h ? kend : (kmid < kend ? kmid : kend);
+        const int n = m * 32 + lane;
+        const double* wcol = Ws + (n < d ? n : d - 1);                   // lanes past d: a valid column, result unused
+        double acc[8];
 #pragma unroll
-      for (int m = 0; m < ITER; ++m) {
-        const int n = m * 32 + lane; ncol[m] = n < d ? n : d - 1;        // lanes past d: a valid column, result unused
+        for (int c = 0; c < 8; ++c) acc[c] = 0.0;
+        int k = k0;
+        for (; k + 4 <= k1; k += 4) {
+          double w4[4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) z[m][r] = 0.0;
-      }
+          for (int u = 0; u < 4; ++u) w4[u] = wcol[(size_t)(k + u) * LDW_S];
 #pragma unroll
-      for (int sgm = 0; sgm < ITER; ++sgm) {
-        const int kbeg = sgm * 32;
-        if (kbeg + 32 <= d) {            // a full segment: straight-line code
-#pragma unroll
-          for (int k4 = 0; k4 < 32; k4 += 4) {
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              const double xv = xs[kbeg + k4 + r];
-              const double* wr = Ws + (size_t)(kbeg + k4 + r) * td.ldw;
-#pragma unroll
-              for (int m = sgm; m < ITER; ++m) z[m][r] = fma(xv, wr[ncol[m]], z[m][r]);
-            }
-          }
-        } else {
-          for (int k4 = kbeg; k4 < d; k4 += 4) {
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              const int k = k4 + r;
-              const double xv = k < d ? xs[k] : 0.0;
-              const double* wr = Ws + (size_t)(k < d ? k : d - 1) * td.ldw;
-#pragma unroll
-              for (int m = sgm; m < ITER; ++m) z[m][r] = fma(xv, wr[ncol[m]], z[m][r]);
-            }
+          for (int c = 0; c < 8; ++c) {       // four proposals' coordinates per chain as two 128-bit broadcasts (the loop is bound
+                                               // by shared-memory instructions, not by the FMAs)
+            const double2 xa = *reinterpret_cast<const double2*>(xs_all + c * (ITER * 32) + k);
+            const double2 xb = *reinterpret_cast<const double2*>(xs_all + c * (ITER * 32) + k + 2);
+            acc[c] = fma(xa.x, w4[0], acc[c]); acc[c] = fma(xa.y, w4[1], acc[c]);
+            acc[c] = fma(xb.x, w4[2], acc[c]); acc[c] = fma(xb.y, w4[3], acc[c]);
           }
         }
+        for (; k < k1; ++k) {
+          const double w1 = wcol[(size_t)k * LDW_S];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[c] = fma(xs_all[c * (ITER * 32) + k], w1, acc[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) zpart[(size_t)(h * 8 + c) * (ITER * 32) + n] = acc[c];
       }
+    }
+    __syncthreads();                                                     // both halves of every column are in zpart
+    double rss = 0.0;
+    {
+      const int wib = threadIdx.x >> 5;
 #pragma unroll
       for (int m = 0; m < ITER; ++m) {
-        const double zz = (z[m][0] + z[m][1]) + (z[m][2] + z[m][3]);
-        if (m * 32 + lane < d) rss = fma(zz, zz, rss);
+        const int n = m * 32 + lane;
+        const double zz = zpart[(size_t)wib * (ITER * 32) + n] + zpart[(size_t)(8 + wib) * (ITER * 32) + n];
+        if (n < d) rss = fma(zz, zz, rss);
       }
       rss = hb_warp_sum(rss);
     }
+    if (!has_chain) return;
+    if (tm) tm[7] = clock64();
     const double dens = td.konst - 0.5 * (td.df + (double)d) * log1p(rss / td.df);
     __syncwarp();                                                       // xs is rewritten by the next chain
     if (tm) tm[3] = clock64();
@@ -518,8 +549,8 @@ __device__ __forceinline__ void fused_chain_step(const hb_k1_params& p, const hb
       lpostx = lpx + lln;                                               // R/dream_parallel.R:291
       lpost_old = q.lpost[si];
       double u;
-      if (TAPE) u = q.u_accept[j];
-      else { const hb_phx ph(q.seed, (uint64_t)gch, q.gen); u = hb_u53(hb_pair64(ph.slot(HB_SLOT_ACCEPT), 0)); }
+      if (TAPE) u = fg.u_accept[j];
+      else { const hb_phx ph(q.seed, (uint64_t)gch, fg.gen); u = hb_u53(hb_pair64(ph.slot(HB_SLOT_ACCEPT), 0)); }
       const double p_acc = fmin(fmax(-100.0, lpostx - lpost_old), 0.0); // R/internals.R:239
       accf = p_acc > log(u);                                            // :241
     }
@@ -529,8 +560,8 @@ __device__ __forceinline__ void fused_chain_step(const hb_k1_params& p, const hb
       const int k = m * 32 + lane;
       if (k < d) {
         const double xn = accf ? xp[m] : xk[m];                         // R/dream_parallel.R:358
-        q.Xout[j * (long long)ldx + k] = xn;
-        if (q.hist_x) q.hist_x[si * (long long)d + k] = xn;             // chain[ind_out, 1:d, ] :388
+        fg.Xout[j * (long long)ldx + k] = xn;
+        if (fg.hist_x) fg.hist_x[si * (long long)d + k] = xn;             // chain[ind_out, 1:d, ] :388
       }
     }
     if (lane == 0) {
@@ -542,12 +573,12 @@ __device__ __forceinline__ void fused_chain_step(const hb_k1_params& p, const hb
       } else {
         lpost_c = lpost_old;                                            // :365
         lp_c = 0; ll_c = 0;
-        if (q.hist_l) { lp_c = q.lp[si]; ll_c = q.ll[si]; }
+        if (fg.hist_l) { lp_c = q.lp[si]; ll_c = q.ll[si]; }
       }
-      if (q.hist_l) { q.hist_l[si * 3 + 0] = lp_c; q.hist_l[si * 3 + 1] = ll_c; q.hist_l[si * 3 + 2] = lpost_c; }   // :389-391
-      if (q.hist_fx && q.fx) q.hist_fx[si] = q.fx[si];                  // :394
-      if (q.lpost_hist_row) q.lpost_hist_row[si] = lpost_c;
-      if (q.accept_rec) q.accept_rec[si] = (uint8_t)accf;
+      if (fg.hist_l) { fg.hist_l[si * 3 + 0] = lp_c; fg.hist_l[si * 3 + 1] = ll_c; fg.hist_l[si * 3 + 2] = lpost_c; }   // :389-391
+      if (fg.hist_fx && q.fx) fg.hist_fx[si] = q.fx[si];                  // :394
+      if (fg.lpost_hist_row) fg.lpost_hist_row[si] = lpost_c;
+      if (fg.accept_rec) fg.accept_rec[si] = (uint8_t)accf;
       atomicAdd(&s_cnt[1 + id], 1ull);                                  // n_id  :368-369
       if (accf) { atomicAdd(&s_cnt[0], 1ull); atomicAdd(&s_cnt[1 + HB_MAX_NCR + id], 1ull); }   // n_acc :374
     }
@@ -576,9 +607,13 @@ __global__ void __launch_bounds__(256) hb_fused_small_kernel(const hb_k1_params 
   const int lane = threadIdx.x & 31;
   const int n_wib = blockDim.x >> 5, wib = threadIdx.x >> 5;
   const int stage_rows = (1 + 2 * p.delta) > 4 ? (1 + 2 * p.delta) : 4;
+  constexpr int LDW_S = ITER * 32 + 4;
+  const int W_D = p.d;
   double* Ws = fused_smem;
-  double* xs = fused_smem + (size_t)p.d * td.ldw + (size_t)wib * (ITER * 32);
-  double* stage = fused_smem + (size_t)p.d * td.ldw + (size_t)n_wib * (ITER * 32) + (size_t)wib * stage_rows * p.ldx;
+  double* xs = fused_smem + (size_t)p.d * LDW_S + (size_t)wib * (ITER * 32);
+  const double* xs_all = fused_smem + (size_t)p.d * LDW_S;
+  double* zpart = fused_smem + (size_t)p.d * LDW_S + (size_t)n_wib * (ITER * 32);                      // [2][8][ITER * 32]
+  double* stage = zpart + (size_t)16 * (ITER * 32) + (size_t)wib * stage_rows * p.ldx;
   unsigned sphase = 0;
   if (lane == 0) { mbar_init(&sbars[wib], 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
   // W (d * ldw doubles, ldw even: a multiple of 16 bytes) is staged once per CTA by bulk TMA copies of at most 32 KB; it
@@ -595,19 +630,20 @@ __global__ void __launch_bounds__(256) hb_fused_small_kernel(const hb_k1_params 
   unsigned errbits = 0;
   if (threadIdx.x <= 2 * HB_MAX_NCR) s_cnt[threadIdx.x] = 0ull;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(&wbar, w_bytes);
-    for (uint32_t off = 0; off < w_bytes; off += 32768u) {
-      const uint32_t nbytes = (w_bytes - off) < 32768u ? (w_bytes - off) : 32768u;
-      tma_load_1d(reinterpret_cast<char*>(Ws) + off, reinterpret_cast<const char*>(td.W) + off, nbytes, &wbar);
-    }
-  }
+  // W: d rows of ldw doubles in global memory -> rows of LDW_S doubles in shared memory, one bulk copy per row
+  if (threadIdx.x == 0) mbar_expect_tx(&wbar, w_bytes);
+  __syncthreads();
+  for (int k = threadIdx.x; k < W_D; k += blockDim.x)
+    tma_load_1d(Ws + (size_t)k * LDW_S, td.W + (size_t)k * td.ldw, (uint32_t)td.ldw * 8u, &wbar);
 
   bool w_ready = false;
-  for (long long base = warp_id; base < p.n_local; base += n_warps) {
+  for (long long base0 = (long long)blockIdx.x * n_wib; base0 < p.n_local; base0 += n_warps) {   // one round = this CTA's next 8 chains
+    const long long base = base0 + wib;
+    const bool has_chain = base < p.n_local;
     k1_headv hv;
-    k1_chain_head<32, TAPE>(p, p.gen, p.tape_g, base, lane, hv, errbits);
-    fused_chain_step<ITER, TAPE>(p, q, td, Ws, xs, &wbar, w_ready, hv, lane, s_cnt, errbits, stage, &sbars[wib], sphase);
+    if (has_chain) k1_chain_head<32, TAPE>(p, p.gen, p.tape_g, base, lane, hv, errbits);
+    fused_chain_step<ITER, TAPE>(p, q, td, fused_gen_of(q), Ws, xs, &wbar, w_ready, hv, lane, s_cnt, errbits, stage, &sbars[wib], sphase,
+                                 xs_all, zpart, has_chain);
   }
   __syncthreads();
   if (threadIdx.x <= 2 * HB_MAX_NCR) {
@@ -630,8 +666,8 @@ cudaError_t launch_fused(const hb_k1_params& p, const hb_k3_params& q, const hb_
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   const int stage_rows = (1 + 2 * p.delta) > 4 ? (1 + 2 * p.delta) : 4;
-  const size_t smem = ((size_t)p.d * td.ldw + (size_t)warps * ITER * 32 + (size_t)warps * stage_rows * p.ldx) * sizeof(double);
-  if (smem > 220 * 1024 || (((size_t)p.d * td.ldw * 8) & 15) || (p.ldx & 1)) return cudaErrorInvalidValue;
+  const size_t smem = ((size_t)p.d * (ITER * 32 + 4) + (size_t)warps * ITER * 32 + (size_t)16 * ITER * 32 + (size_t)warps * stage_rows * p.ldx) * sizeof(double);
+  if (smem > 220 * 1024 || (td.ldw & 1) || td.ldw > ITER * 32 + 4 || (p.ldx & 1)) return cudaErrorInvalidValue;
   static bool attr_set[2] = {false, false};
   if (!attr_set[tape]) {
     cudaError_t e = tape ? cudaFuncSetAttribute(hb_fused_small_kernel<ITER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)
@@ -658,17 +694,19 @@ template <int ITER, bool TAPE>
 __global__ void __launch_bounds__(256) hb_persist_small_kernel(const hb_k1_params p0, const hb_k3_params q0, const hb_fused_tdist td,
                                                                const hb_persist_params pp) {
   extern __shared__ __align__(16) double fused_smem[];               // W [d][ldw] | xs [warps][ITER * 32]
-  __shared__ hb_k1_params sp;                                         // this generation's parameter blocks
-  __shared__ hb_k3_params sq;
   __shared__ unsigned long long s_cnt[2 * HB_MAX_NCR + 1];
   __shared__ __align__(8) uint64_t wbar;
   __shared__ __align__(8) uint64_t sbars[8];
   const int lane = threadIdx.x & 31;
   const int n_wib = blockDim.x >> 5, wib = threadIdx.x >> 5;
   const int stage_rows = (1 + 2 * p0.delta) > 4 ? (1 + 2 * p0.delta) : 4;
+  constexpr int LDW_S = ITER * 32 + 4;
+  const int W_D = p0.d;
   double* Ws = fused_smem;
-  double* xs = fused_smem + (size_t)p0.d * td.ldw + (size_t)wib * (ITER * 32);
-  double* stage = fused_smem + (size_t)p0.d * td.ldw + (size_t)n_wib * (ITER * 32) + (size_t)wib * stage_rows * p0.ldx;
+  double* xs = fused_smem + (size_t)p0.d * LDW_S + (size_t)wib * (ITER * 32);
+  const double* xs_all = fused_smem + (size_t)p0.d * LDW_S;
+  double* zpart = fused_smem + (size_t)p0.d * LDW_S + (size_t)n_wib * (ITER * 32);                     // [2][8][ITER * 32]
+  double* stage = zpart + (size_t)16 * (ITER * 32) + (size_t)wib * stage_rows * p0.ldx;
   unsigned sphase = 0;
   if (lane == 0) { mbar_init(&sbars[wib], 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
   const uint32_t w_bytes = (uint32_t)p0.d * (uint32_t)td.ldw * 8u;
@@ -676,21 +714,13 @@ __global__ void __launch_bounds__(256) hb_persist_small_kernel(const hb_k1_param
     mbar_init(&wbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  {  // copy the parameter blocks into shared memory (word by word: they are kernel parameters)
-    const uint32_t* a = reinterpret_cast<const uint32_t*>(&p0); uint32_t* b = reinterpret_cast<uint32_t*>(&sp);
-    for (int w = threadIdx.x; w < (int)(sizeof(hb_k1_params) / 4); w += blockDim.x) b[w] = a[w];
-    const uint32_t* c = reinterpret_cast<const uint32_t*>(&q0); uint32_t* e = reinterpret_cast<uint32_t*>(&sq);
-    for (int w = threadIdx.x; w < (int)(sizeof(hb_k3_params) / 4); w += blockDim.x) e[w] = c[w];
-  }
   if (threadIdx.x <= 2 * HB_MAX_NCR) s_cnt[threadIdx.x] = 0ull;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(&wbar, w_bytes);
-    for (uint32_t off = 0; off < w_bytes; off += 32768u) {
-      const uint32_t nbytes = (w_bytes - off) < 32768u ? (w_bytes - off) : 32768u;
-      tma_load_1d(reinterpret_cast<char*>(Ws) + off, reinterpret_cast<const char*>(td.W) + off, nbytes, &wbar);
-    }
-  }
+  // W: d rows of ldw doubles in global memory -> rows of LDW_S doubles in shared memory, one bulk copy per row
+  if (threadIdx.x == 0) mbar_expect_tx(&wbar, w_bytes);
+  __syncthreads();
+  for (int k = threadIdx.x; k < W_D; k += blockDim.x)
+    tma_load_1d(Ws + (size_t)k * LDW_S, td.W + (size_t)k * td.ldw, (uint32_t)td.ldw * 8u, &wbar);
   const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nl = p0.n_local;
   const bool active = warp_id < nl;      // one chain per warp (the launcher sizes the grid that way)
@@ -698,29 +728,27 @@ __global__ void __launch_bounds__(256) hb_persist_small_kernel(const hb_k1_param
   bool w_ready = false;
   long long ind_out = pp.ind_out0, pending = pp.pending0;
   k1_headv hv;
-  if (active) k1_chain_head<32, TAPE>(sp, (uint32_t)pp.i0, pp.i0 - 2, warp_id, lane, hv, errbits);
+  if (active) k1_chain_head<32, TAPE>(p0, (uint32_t)pp.i0, pp.i0 - 2, warp_id, lane, hv, errbits);
 
   for (long long i = pp.i0; i < pp.i1; ++i) {
     const bool store = ((double)i > pp.burnin * (double)pp.t) && (i % pp.thin == 0);   // R/dream_parallel.R:263, :386
     if (store) ind_out++;
-    if (threadIdx.x == 0) {
+    fused_gen fg;                             // this generation's pointers (uniform; every thread derives them itself)
+    {
       const bool flip = ((i - pp.i0) & 1) != 0;
-      double* xin = flip ? pp.XB : pp.XA; double* xout = flip ? pp.XA : pp.XB;
-      sp.X = xin; sp.gen = (uint32_t)i; sp.tape_g = i - 2;
-      sq.X = xin; sq.Xout = xout; sq.gen = (uint32_t)i;
-      sq.hist_x = (store && pp.hist_x) ? pp.hist_x + (size_t)(ind_out - 1) * nl * p0.d : nullptr;
-      sq.hist_l = (store && pp.hist_l) ? pp.hist_l + (size_t)(ind_out - 1) * nl * 3 : nullptr;
-      sq.hist_fx = (store && pp.hist_fx) ? pp.hist_fx + (size_t)(ind_out - 1) * nl : nullptr;
-      sq.lpost_hist_row = (i <= pp.H && pp.lpost_hist) ? pp.lpost_hist + (size_t)(i - 1) * nl : nullptr;
-      sq.accept_rec = pp.accept_rec ? pp.accept_rec + (size_t)(i - 2) * nl : nullptr;
-      sq.u_accept = pp.u_accept ? pp.u_accept + (size_t)(i - 2) * pp.tape_nct : nullptr;
+      fg.Xin = flip ? pp.XB : pp.XA; fg.Xout = flip ? pp.XA : pp.XB; fg.gen = (uint32_t)i;
+      fg.hist_x = (store && pp.hist_x) ? pp.hist_x + (size_t)(ind_out - 1) * nl * p0.d : nullptr;
+      fg.hist_l = (store && pp.hist_l) ? pp.hist_l + (size_t)(ind_out - 1) * nl * 3 : nullptr;
+      fg.hist_fx = (store && pp.hist_fx) ? pp.hist_fx + (size_t)(ind_out - 1) * nl : nullptr;
+      fg.lpost_hist_row = (i <= pp.H && pp.lpost_hist) ? pp.lpost_hist + (size_t)(i - 1) * nl : nullptr;
+      fg.accept_rec = pp.accept_rec ? pp.accept_rec + (size_t)(i - 2) * nl : nullptr;
+      fg.u_accept = pp.u_accept ? pp.u_accept + (size_t)(i - 2) * pp.tape_nct : nullptr;
     }
-    __syncthreads();
     long long tm[8];
     const bool tr = pp.trace && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && i >= pp.i0 + 2 && i < pp.i0 + 6;
     if (tr) tm[4] = clock64();
-    if (active)
-      fused_chain_step<ITER, TAPE, true>(sp, sq, td, Ws, xs, &wbar, w_ready, hv, lane, s_cnt, errbits, stage, &sbars[wib], sphase, tr ? tm : nullptr);
+    fused_chain_step<ITER, TAPE, true>(p0, q0, td, fg, Ws, xs, &wbar, w_ready, hv, lane, s_cnt, errbits, stage, &sbars[wib], sphase,
+                                       xs_all, zpart, active, tr ? tm : nullptr);
     if (tr) tm[5] = clock64();
     __syncthreads();
     if (tr) tm[6] = clock64();
@@ -743,7 +771,7 @@ __global__ void __launch_bounds__(256) hb_persist_small_kernel(const hb_k1_param
     // the others (they must not add the next generation's counts before the fold has zeroed the counters).
     const unsigned round = (unsigned)(i - pp.i0 + 1);
     if (threadIdx.x == 0) { __threadfence(); atomicAdd(&pp.bar[0], 1u); }
-    if (active && i + 1 < pp.i1) k1_chain_head<32, TAPE>(sp, (uint32_t)(i + 1), i - 1, warp_id, lane, hv, errbits);
+    if (active && i + 1 < pp.i1) k1_chain_head<32, TAPE>(p0, (uint32_t)(i + 1), i - 1, warp_id, lane, hv, errbits);
     if (threadIdx.x == 0) {
       const unsigned target = gridDim.x * round;
       if (!upd) {
@@ -764,8 +792,8 @@ __global__ void __launch_bounds__(256) hb_persist_small_kernel(const hb_k1_param
     }
     if (upd) pending = 0;
     __syncthreads();
-    if (tr) printf("[persist trace] gen %lld cta %d: setup %lld | sweep %lld | xp %lld | density %lld | accept+store %lld | block sync %lld | barrier+next head %lld cycles\n",
-                   i, (int)blockIdx.x, tm[0] - tm[4], tm[1] - tm[0], tm[2] - tm[1], tm[3] - tm[2], tm[5] - tm[3], tm[6] - tm[5], clock64() - tm[6]);
+    if (tr) printf("[persist trace] gen %lld cta %d: setup %lld | sweep %lld | xp %lld | product %lld + log1p %lld | accept+store %lld | block sync %lld | barrier+next head %lld cycles\n",
+                   i, (int)blockIdx.x, tm[0] - tm[4], tm[1] - tm[0], tm[2] - tm[1], tm[7] - tm[2], tm[3] - tm[7], tm[5] - tm[3], tm[6] - tm[5], clock64() - tm[6]);
   }
   if (errbits) atomicOr(&q0.ctrl->err, errbits);
 }
@@ -776,8 +804,8 @@ cudaError_t launch_persist(const hb_k1_params& p, const hb_k3_params& q, const h
   const int threads = 256, warps = threads / 32;
   const long long blocks = (p.n_local + warps - 1) / warps;
   const int stage_rows = (1 + 2 * p.delta) > 4 ? (1 + 2 * p.delta) : 4;
-  const size_t smem = ((size_t)p.d * td.ldw + (size_t)warps * ITER * 32 + (size_t)warps * stage_rows * p.ldx) * sizeof(double);
-  if (smem > 220 * 1024 || (((size_t)p.d * td.ldw * 8) & 15) || (p.ldx & 1)) return cudaErrorInvalidValue;
+  const size_t smem = ((size_t)p.d * (ITER * 32 + 4) + (size_t)warps * ITER * 32 + (size_t)16 * ITER * 32 + (size_t)warps * stage_rows * p.ldx) * sizeof(double);
+  if (smem > 220 * 1024 || (td.ldw & 1) || td.ldw > ITER * 32 + 4 || (p.ldx & 1)) return cudaErrorInvalidValue;
   const void* fn = tape ? (const void*)hb_persist_small_kernel<ITER, true> : (const void*)hb_persist_small_kernel<ITER, false>;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
