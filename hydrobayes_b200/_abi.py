@@ -26,6 +26,7 @@ HB_PRIOR_FLAT, HB_PRIOR_UNIFORM, HB_PRIOR_NORMAL = 0, 1, 2
 HB_BOUND_NONE, HB_BOUND_BOUND, HB_BOUND_REFLECT, HB_BOUND_FOLD = 0, 1, 2, 3
 HB_RNG_TAPE, HB_RNG_PHILOX = 0, 1
 HB_EXCHANGE_ALLGATHER, HB_EXCHANGE_PEER, HB_EXCHANGE_DELTA = 0, 1, 2
+HB_PEER_EXPORT_BYTES = 640   # 10 CUDA IPC handles of 64 bytes (include/hydrobayes_b200.h)
 
 _dp = C.POINTER(C.c_double)
 _u8p = C.POINTER(C.c_uint8)

@@ -273,10 +273,13 @@ int allocate(hb_handle* h) {
     h->box_idx_off = 256;                                                       // counts[HB_MAX_PIECES] live in the first 64 bytes
     h->box_rows_off = (h->box_idx_off + (size_t)cap * 4 + 255) & ~(size_t)255;
     h->box_bytes = (h->box_rows_off + (size_t)cap * ldx * 8 + 255) & ~(size_t)255;
-    const size_t bytes = h->arena_box_off + 2 * (size_t)h->world * h->box_bytes;
-    CK(cudaMalloc((void**)&h->arena, bytes));
+    CK(cudaMalloc((void**)&h->arena, h->arena_box_off));
     CK(cudaMemsetAsync(h->arena, 0, h->arena_box_off, h->stream));
-    for (int b = 0; b < 2 * h->world; ++b) CK(cudaMemsetAsync(h->arena + h->arena_box_off + (size_t)b * h->box_bytes, 0, 256, h->stream));
+    for (int r = 0; r < h->world; ++r) {
+      CK(cudaMalloc((void**)&h->boxmem[r], 2 * h->box_bytes));
+      for (int b = 0; b < 2; ++b) CK(cudaMemsetAsync(h->boxmem[r] + (size_t)b * h->box_bytes, 0, 256, h->stream));   // the piece counts
+    }
+    h->peer_box[h->rank] = h->boxmem[h->rank];
     h->arena_peer[h->rank] = h->arena;
     CK(dalloc(&h->log_ctr, (size_t)3 * HB_MAX_PIECES));
     CK(cudaMemsetAsync(h->log_ctr, 0, sizeof(unsigned) * 3 * HB_MAX_PIECES, h->stream));
@@ -752,7 +755,7 @@ int piece_kernels(hb_handle* h, long long i, int piece, long long off, long long
     if (p.fx_xp) p.fx_xp += off;
     p.partials = h->partials + (size_t)piece * h->k3_blocks_piece * (c.nCR + 2) * d;
     if (h->delta_mode) {   // accepted rows go to this rank's delta log: box (parity, self), slots of this piece
-      unsigned char* box = h->arena + h->arena_box_off + ((size_t)(i & 1) * h->world + h->rank) * h->box_bytes;
+      unsigned char* box = h->boxmem[h->rank] + (size_t)(i & 1) * h->box_bytes;
       p.log_rows = reinterpret_cast<double*>(box + h->box_rows_off) + (size_t)piece * h->piece_n * ldx;
       p.log_idx = reinterpret_cast<int*>(box + h->box_idx_off) + (size_t)piece * h->piece_n;
       p.log_count = h->log_ctr + (size_t)(i & 1) * HB_MAX_PIECES + piece;
@@ -770,7 +773,7 @@ int piece_send(hb_handle* h, long long i, int piece) {
   hb_delta_send_params sp{};
   for (int r = 0; r < h->world; ++r) {
     sp.arena[r] = h->arena_peer[r];
-    sp.box[r] = h->arena_peer[r] + h->arena_box_off + ((size_t)(i & 1) * h->world + h->rank) * h->box_bytes;
+    sp.box[r] = h->peer_box[r] + (size_t)(i & 1) * h->box_bytes;        // rank r's box for this rank's log
   }
   sp.idx_off = h->box_idx_off; sp.rows_off = h->box_rows_off; sp.piece_off = (long long)piece * h->piece_n;
   sp.piece = piece; sp.ldx = h->ldx; sp.self = h->rank; sp.world = h->world;
@@ -790,7 +793,7 @@ int piece_send(hb_handle* h, long long i, int piece) {
 // fold the delta logs of pieces [p0, p1) of generation i -- this rank's and every peer's -- into the replica
 int delta_apply(hb_handle* h, long long i, int p0, int p1, cudaStream_t st) {
   hb_delta_apply_params ap{};
-  for (int r = 0; r < h->world; ++r) ap.box[r] = h->arena + h->arena_box_off + ((size_t)(i & 1) * h->world + r) * h->box_bytes;
+  for (int r = 0; r < h->world; ++r) ap.box[r] = h->boxmem[r] + (size_t)(i & 1) * h->box_bytes;
   ap.idx_off = h->box_idx_off; ap.rows_off = h->box_rows_off; ap.piece_cap = h->piece_n; ap.p0 = p0; ap.p1 = p1;
   ap.ldx = h->ldx; ap.self = h->rank; ap.world = h->world; ap.nc = h->nc; ap.X = h->X;
   ap.flags = reinterpret_cast<const unsigned*>(h->arena); ap.flag_value = (unsigned)i * HB_MAX_PIECES + (unsigned)p1;
@@ -804,7 +807,7 @@ int delta_apply(hb_handle* h, long long i, int p0, int p1, cudaStream_t st) {
 // store the rows of piece `piece` of this rank's log straight into every replica (the last piece of a generation)
 int delta_push(hb_handle* h, long long i, int piece) {
   hb_delta_push_params pp{};
-  pp.box = h->arena + h->arena_box_off + ((size_t)(i & 1) * h->world + h->rank) * h->box_bytes;
+  pp.box = h->boxmem[h->rank] + (size_t)(i & 1) * h->box_bytes;
   pp.idx_off = h->box_idx_off; pp.rows_off = h->box_rows_off; pp.piece_off = (long long)piece * h->piece_n;
   pp.ldx = h->ldx; pp.self = h->rank; pp.world = h->world; pp.nc = h->nc;
   for (int r = 0; r < h->world; ++r) { pp.X[r] = (r == h->rank) ? h->X : h->peerX[r]; pp.arena[r] = h->arena_peer[r]; }
@@ -1170,6 +1173,8 @@ void hb_destroy(hb_handle* h) {
     for (int r = 0; r < 8; ++r) {
       if (h->peerX_opened[r]) ipc_close.push_back(h->peerX_opened[r]);
       if (h->arena_opened[r]) ipc_close.push_back(h->arena_opened[r]);
+      if (h->peer_box_opened[r]) ipc_close.push_back(h->peer_box_opened[r]);
+      if (h->boxmem[r]) exported.push_back(h->boxmem[r]);
     }
     if (h->arena) exported.push_back(h->arena);
     if (h->X) exported.push_back(h->X);
@@ -1389,17 +1394,19 @@ int hb_peer_export(hb_handle* h, void* out128) {
   if (!h->peer_mode && !h->delta_mode) return fail(h, HB_ERR_STATE, "hb_peer_export: the handle is not in HB_EXCHANGE_PEER / HB_EXCHANGE_DELTA mode");
   if (!h->have_initial) return fail(h, HB_ERR_STATE, "hb_peer_export must follow hb_set_initial");
   cudaSetDevice(h->device);
-  cudaIpcMemHandle_t hd[2];
+  cudaIpcMemHandle_t hd[HB_PEER_EXPORT_HANDLES];
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-  if (h->delta_mode) {
+  memset(hd, 0, sizeof hd);
+  if (h->delta_mode) {   // X | arena | box of source rank 0 .. 7
     CK(cudaIpcGetMemHandle(&hd[0], h->X));
     CK(cudaIpcGetMemHandle(&hd[1], h->arena));
-    memcpy(out128, hd, 128);
+    for (int r = 0; r < h->world; ++r) if (r != h->rank) CK(cudaIpcGetMemHandle(&hd[2 + r], h->boxmem[r]));
+    memcpy(out128, hd, sizeof hd);
     return HB_OK;
   }
   CK(cudaIpcGetMemHandle(&hd[0], h->Xbuf[0]));
   CK(cudaIpcGetMemHandle(&hd[1], h->Xbuf[1]));
-  memcpy(out128, hd, 128);
+  memcpy(out128, hd, sizeof hd);
   return HB_OK;
 }
 
@@ -1413,11 +1420,14 @@ int hb_peer_import(hb_handle* h, const void* all_handles) {
   if (h->delta_mode) {
     for (int r = 0; r < h->world; ++r) {
       if (r == h->rank) continue;
-      void* px = nullptr; void* pf = nullptr;
-      CK(cudaIpcOpenMemHandle(&px, hd[2 * r], cudaIpcMemLazyEnablePeerAccess));
-      CK(cudaIpcOpenMemHandle(&pf, hd[2 * r + 1], cudaIpcMemLazyEnablePeerAccess));
+      void* px = nullptr; void* pf = nullptr; void* pb = nullptr;
+      const cudaIpcMemHandle_t* hr = hd + (size_t)r * HB_PEER_EXPORT_HANDLES;
+      CK(cudaIpcOpenMemHandle(&px, hr[0], cudaIpcMemLazyEnablePeerAccess));
+      CK(cudaIpcOpenMemHandle(&pf, hr[1], cudaIpcMemLazyEnablePeerAccess));
+      CK(cudaIpcOpenMemHandle(&pb, hr[2 + h->rank], cudaIpcMemLazyEnablePeerAccess));   // only the box this rank writes
       h->peerX_opened[r] = px; h->peerX[r] = (double*)px;
       h->arena_opened[r] = pf; h->arena_peer[r] = (unsigned char*)pf;
+      h->peer_box_opened[r] = pb; h->peer_box[r] = (unsigned char*)pb;
     }
     h->arena_peer[h->rank] = h->arena;
     if (int rc = complete_replicas(h)) return rc;
@@ -1429,7 +1439,7 @@ int hb_peer_import(hb_handle* h, const void* all_handles) {
     for (int b = 0; b < 2; ++b) {
       if (r == h->rank) { h->peer_ptr[b][r] = h->Xbuf[b]; continue; }
       void* p = nullptr;
-      CK(cudaIpcOpenMemHandle(&p, hd[2 * r + b], cudaIpcMemLazyEnablePeerAccess));
+      CK(cudaIpcOpenMemHandle(&p, hd[(size_t)r * HB_PEER_EXPORT_HANDLES + b], cudaIpcMemLazyEnablePeerAccess));
       h->peer_opened[b][r] = p;
       h->peer_ptr[b][r] = (const double*)p;
     }
@@ -1623,7 +1633,7 @@ int hb_group_attach(hb_handle** hs, int n) {
     if (h->side) cudaStreamDestroy(h->side);
     if (h->side2) cudaStreamDestroy(h->side2);
     h->side = h->stream; h->side2 = h->stream;             // one stream: the emulation is sequential by construction
-    for (int q = 0; q < n; ++q) { h->arena_peer[q] = hs[q]->arena; h->peerX[q] = (q == r) ? nullptr : hs[q]->X; }
+    for (int q = 0; q < n; ++q) { h->arena_peer[q] = hs[q]->arena; h->peerX[q] = (q == r) ? nullptr : hs[q]->X; h->peer_box[q] = hs[q]->boxmem[r]; }
   }
   for (int r = 0; r < n; ++r) if (int rc = complete_replicas(hs[r])) return rc;
   for (int r = 0; r < n; ++r) hs[r]->peers_ready = true;

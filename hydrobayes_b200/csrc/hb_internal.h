@@ -57,6 +57,12 @@ struct hb_handle {
   void* arena_opened[8] = {};
   size_t arena_red_bytes = 0, arena_gather_off = 0, arena_box_off = 0;
   size_t box_bytes = 0, box_idx_off = 0, box_rows_off = 0;
+  // delta boxes: boxmem[src] = [2 parities][box_bytes], the log this rank RECEIVES from rank src (boxmem[rank]: its own log).
+  // One allocation per source, so that a peer maps only the box it writes (CUDA IPC maps whole allocations, and mapping
+  // costs time in proportion to the size: 0.35 s per rank at 8 GPUs when every peer mapped all eight boxes).
+  unsigned char* boxmem[8] = {};
+  unsigned char* peer_box[8] = {};     // rank r's boxmem[this rank], as mapped here (own entry = boxmem[rank])
+  void* peer_box_opened[8] = {};
   unsigned red_seq = 0, gather_seq = 0, err_seq = 0, slice_seq = 0;
   int pieces = 1;                 // pieces per generation (1 unless delta_mode)
   long long piece_n = 0;          // chains per piece (the last piece may be shorter)

@@ -141,11 +141,11 @@ class Sampler:
     def peer_setup(self, world: int, group=None):
         """HB_EXCHANGE_PEER: exchange the CUDA IPC handles of the double-buffered shards between the ranks."""
         import torch.distributed as dist
-        mine = C.create_string_buffer(128)
+        mine = C.create_string_buffer(A.HB_PEER_EXPORT_BYTES)
         self._check(self.L.hb_peer_export(self.h, mine))
         parts = [None] * world
         dist.all_gather_object(parts, bytes(mine.raw), group=group)
-        allh = C.create_string_buffer(b"".join(parts), 128 * world)
+        allh = C.create_string_buffer(b"".join(parts), A.HB_PEER_EXPORT_BYTES * world)
         self._check(self.L.hb_peer_import(self.h, allh))
         dist.barrier(group=group)
 

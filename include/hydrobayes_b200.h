@@ -206,9 +206,13 @@ int hb_comm_init(hb_handle* h, int rank, int world, const void* id128);
 /* HB_EXCHANGE_PEER: instead of all-gathering the chain state every generation, the proposal kernel fetches the partner
  * rows it needs straight from the owning GPU through NVLink-mapped peer pointers (bulk TMA reads), and the only
  * per-generation collective left is a 17-word all-reduce that doubles as the generation barrier.  After
- * hb_set_initial every rank exports 128 bytes (two CUDA IPC handles: the double-buffered shard), the host gathers
- * them from all ranks (world*128 bytes, rank order) and hands them to hb_peer_import. */
-int hb_peer_export(hb_handle* h, void* out128);
+ * hb_set_initial every rank exports HB_PEER_EXPORT_BYTES bytes of CUDA IPC handles, the host gathers them from all ranks
+ * (rank order) and hands them to hb_peer_import. */
+#define HB_PEER_EXPORT_HANDLES 10                      /* 64-byte CUDA IPC handles per rank */
+#define HB_PEER_EXPORT_BYTES (64 * HB_PEER_EXPORT_HANDLES)
+/* out: HB_PEER_EXPORT_BYTES bytes (HB_EXCHANGE_DELTA: replica, arena, one delta box per source rank; HB_EXCHANGE_PEER: the two
+ * shard buffers); all_handles: world * HB_PEER_EXPORT_BYTES bytes in rank order */
+int hb_peer_export(hb_handle* h, void* out);
 int hb_peer_import(hb_handle* h, const void* all_handles);
 
 /* Testing hook -- rank emulation on ONE device: hs[r] is rank r of n (hb_comm_init(hs[r], r, n, NULL), HB_EXCHANGE_DELTA,
