@@ -38,11 +38,12 @@ def test_game_argument_checks_follow_the_reference():
 
 
 @pytest.mark.gpu
-def test_game_importance_and_bridge_sampling_with_the_device_target(hb):
+def test_game_importance_and_bridge_sampling_with_the_device_target():
     """posterior sample of the d = 2 t-distribution from dream_parallel (flat prior: the posterior density is the normalised
     target density, so Z = 1); the m0 target evaluations of IS / bridge sampling run through the device plugin"""
     d, nc, t = 2, 64, 1500
-    res = hb.dream_parallel("t_distribution", lik=2, par_info=dict(initial="user", val_ini=H.x0_tdist(nc, d) * 0.2, prior="flat"),
+    from hydrobayes_b200 import dream_parallel
+    res = dream_parallel("t_distribution", lik=2, par_info=dict(initial="user", val_ini=H.x0_tdist(nc, d) * 0.2, prior="flat"),
                             nc=nc, t=t, d=d, seed=11, verbose=False)
     ch = res["chain"][t // 2:]
     theta = ch[:, :d, :].transpose(0, 2, 1).reshape(-1, d)
@@ -55,7 +56,7 @@ def test_game_importance_and_bridge_sampling_with_the_device_target(hb):
 
 
 @pytest.mark.gpu
-def test_de_mc_is_the_sequential_sweep_with_one_pair_and_no_crossover(hb, oracle):
+def test_de_mc_is_the_sequential_sweep_with_one_pair_and_no_crossover(oracle):
     """R/de_mc.R:23-70 as a configuration of the dream() device path: replay parity of that configuration with the oracle, and
     the mixture target's moments (mean 7, P(x < 1) = 1/6)"""
     from hydrobayes_b200.game import de_mc
