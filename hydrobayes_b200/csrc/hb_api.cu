@@ -645,7 +645,7 @@ bool fused_available(hb_handle* h) {
 // Persistent generation loop (hb_persist_small_kernel): generations [i0, i1) of a small population, all behind the adaptation
 // period, in ONE cooperative launch.  Returns HB_OK with *taken = false when the handle cannot use it (the caller then runs
 // the generations one by one).
-int run_persistent(hb_handle* h, long long i0, long long i1, bool* taken) {
+int run_persistent(hb_handle* h, long long i0, long long i1, bool* taken, bool adapt = false) {
   const hb_config& c = h->cfg;
   *taken = false;
   if (h->persist_state < 0 || i1 <= i0 || c.check_convergence) return HB_OK;
@@ -661,9 +661,16 @@ int run_persistent(hb_handle* h, long long i0, long long i1, bool* taken) {
   if (h->ind_out + n_store > h->out_t) return fail(h, HB_ERR_INVALID, "subscript out of bounds (non-integer out_t, R/dream_parallel.R:195)");
   const bool tape_mode = (c.rng_mode == HB_RNG_TAPE);
   const hb_k1_params p = hb_make_k1(h, i0, h->chain0, 1, nl);
-  hb_k3_params q = hb_make_k3(h, i0, h->chain0, 1, nl, false, false, false);
+  hb_k3_params q = hb_make_k3(h, i0, h->chain0, 1, nl, false, adapt, false);
   q.Xout = h->Xalt;
   hb_persist_params pp{};
+  if (adapt) {
+    const size_t E = (size_t)(c.nCR + 2) * h->d;
+    if (h->islot + (i1 - i0) > c.update_interval) return fail(h, HB_ERR_STATE, "persistent adaptation launch crosses an updateInterval boundary");
+    if (!h->persist_partials) CK(dalloc(&h->persist_partials, (size_t)c.update_interval * ((nl + 7) / 8) * E));
+    if (!h->persist_ibuf) CK(dalloc(&h->persist_ibuf, (size_t)c.update_interval * E));
+    pp.adapt = 1; pp.slot0 = h->islot; pp.partials = h->persist_partials; pp.shift = h->shift;
+  }
   pp.i0 = i0; pp.i1 = i1; pp.XA = h->X; pp.XB = h->Xalt; pp.t = h->t; pp.burnin = c.burnin; pp.thin = c.thin;
   pp.update_interval = c.update_interval; pp.ind_out0 = h->ind_out;
   pp.hist_x = h->hist_x; pp.hist_l = h->hist_l; pp.hist_fx = h->hist_fx; pp.lpost_hist = h->lpost_hist; pp.H = h->H;
@@ -680,9 +687,28 @@ int run_persistent(hb_handle* h, long long i0, long long i1, bool* taken) {
   h->launches++;
   h->ind_out += n_store;
   long long last_upd = ((i1 - 1) / c.update_interval) * c.update_interval;       // largest multiple of updateInterval below i1
-  h->pending_evals = (last_upd >= i0) ? h->nc * (i1 - 1 - last_upd) : h->pending_evals + h->nc * (i1 - i0);
+  if (adapt) { h->islot += (int)(i1 - i0); h->pending_evals += h->nc * (i1 - i0); }   // folded by persist_fold
+  else h->pending_evals = (last_upd >= i0) ? h->nc * (i1 - 1 - last_upd) : h->pending_evals + h->nc * (i1 - i0);
   if ((i1 - i0) & 1) std::swap(h->X, h->Xalt);
   h->gen = i1 - 1;
+  return HB_OK;
+}
+
+// the finalize step for the adaptation generations a persistent launch has parked (their per-CTA statistic sums sit in
+// slots 0 .. islot-1): reduce every slot, then J / n_id / n_acc in generation order, pCR and the AR / CR rows if the last
+// one is an updateInterval boundary (hb_finalize_kernel's interval mode, shared with the multi-GPU path)
+int persist_fold(hb_handle* h, bool upd) {
+  if (h->islot <= 0) return HB_OK;
+  const hb_config& c = h->cfg;
+  const size_t E = (size_t)(c.nCR + 2) * h->d;
+  hb_fin_params f{};
+  f.ctrl = h->ctrl; f.partials = h->persist_partials; f.nblocks = (int)((h->n_local + 7) / 8); f.reduce_slots = h->islot;
+  f.shift = h->shift; f.colsum = h->persist_ibuf; f.qsum = h->persist_ibuf + 2 * h->d; f.nc = h->nc; f.d = h->d; f.nCR = c.nCR;
+  f.adapt = 1; f.do_pcr = upd; f.do_arcr = upd; f.out_ar = h->out_ar; f.out_cr = h->out_cr; f.ar_rows = h->ar_rows;
+  f.n_eval_inc = h->pending_evals; f.n_slots = h->islot; f.slot_stride = (long long)E; f.phase = 2;
+  CK(hb_launch_finalize(f, h->stream));
+  h->launches += 2;
+  h->islot = 0; h->pending_evals = 0;
   return HB_OK;
 }
 
@@ -1194,7 +1220,7 @@ void hb_destroy(hb_handle* h) {
     for (int b = 0; b < 2; ++b) for (int r = 0; r < 8; ++r) if (h->peer_opened[b][r]) cudaIpcCloseMemHandle(h->peer_opened[b][r]);
     cudaFree(h->Xbuf[0]); cudaFree(h->Xbuf[1]);
   }
-  void* ptrs[] = {h->X, h->Xalt, h->Z, h->XP, h->id, h->lp_xp, h->ll_raw, h->fx_xp, h->lp, h->ll, h->lpost, h->fx, h->lpost_hist,
+  void* ptrs[] = {h->X, h->Xalt, h->persist_partials, h->persist_ibuf, h->Z, h->XP, h->id, h->lp_xp, h->ll_raw, h->fx_xp, h->lp, h->ll, h->lpost, h->fx, h->lpost_hist,
                   h->hist_x, h->hist_l, h->hist_fx, h->accept_rec, h->ctrl, h->shift, h->colsum, h->qsum, h->partials,
                   h->out_ar, h->out_cr, h->proxy, h->proxy_full, h->lpost_full, h->outl_dev, h->news_dev, h->rstat_dev,
                   h->rstat_xm, h->rstat_ss, h->stage, h->log_ctr, h->ibuf, h->errbits_dev, h->grid_bar, h->pmin, h->pmax, h->prior_W, h->prior_mu, h->ZT, h->lp_zt, h->ll_zt, h->fx_zt, h->id_zt, h->mt_p1, h->mt_accept, h->rstat_sums, h->gamma_tab, h->outl_tmp, h->outl_sorted, h->outl_thr,
@@ -1571,10 +1597,35 @@ static int run_slice(std::vector<hb_handle*>& hs, int64_t n_generations) {
       hb_handle* h = hs[0];
       const bool in_adapt = ((double)i <= h->cfg.adapt * (double)h->t);
       if (!in_adapt && !h->modeb && h->cfg.mt <= 1 && fused_available(h)) {
+        if (!h->delta_mode) { if (int rc = persist_fold(h, false)) return rc; }
         bool taken = false;
         if (int rc = run_persistent(h, i, last + 1, &taken)) return rc;
         if (taken) break;
       }
+      if (in_adapt && !h->modeb && h->cfg.mt <= 1 && h->persist_adapt_ok >= 0 && fused_available(h)) {
+        // adaptation period: persistent launches that end at the next updateInterval boundary (pCR changes there and the
+        // outlier check of R/dream_parallel.R:414-419 runs between the launches)
+        if (h->persist_adapt_ok == 0) { const char* e = getenv("HB_PERSIST_ADAPT"); h->persist_adapt_ok = (e && e[0] == '0') ? -1 : 1; }
+        const long long ui = h->cfg.update_interval;
+        long long i1 = (i / ui + 1) * ui + 1;                      // one past the next multiple of updateInterval (>= i)
+        if (i % ui == 0) i1 = i + 1;
+        while ((double)(i1 - 1) > h->cfg.adapt * (double)h->t) --i1;  // generations of the slice all lie inside the period
+        if (i1 > last + 1) i1 = last + 1;
+        bool taken = false;
+        if (h->persist_adapt_ok > 0 && i1 > i) { if (int rc = run_persistent(h, i, i1, &taken, true)) return rc; }
+        if (taken) {
+          const long long ie = i1 - 1;
+          if (ie % ui == 0) { if (int rc = persist_fold(h, true)) return rc; }
+          if (ie % ui == 0 && !h->cfg.past_sample && h->cfg.outlier_check) {
+            std::vector<gen_prog> gs(1);
+            prog_outlier_check(h, gs[0], ie);
+            if (int rc = run_programs(hs, gs)) return rc;
+          }
+          i = ie;
+          continue;
+        }
+      }
+      if (!h->delta_mode) { if (int rc = persist_fold(h, false)) return rc; }   // parked generations precede this one
     }
     std::vector<gen_prog> gs(hs.size());
     for (size_t r = 0; r < hs.size(); ++r) if (int rc = build_generation(hs[r], i, gs[r])) return rc;

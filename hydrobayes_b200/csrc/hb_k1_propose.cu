@@ -433,7 +433,7 @@ __device__ __forceinline__ void fused_chain_step(const hb_k1_params& p, const hb
                                                  const k1_headv& hv, int lane, unsigned long long* s_cnt, unsigned& errbits,
                                                  double* stage, uint64_t* sbar, unsigned& sphase,
                                                  const double* __restrict__ xs_all, double* __restrict__ zpart, bool has_chain,
-                                                 long long* tm = nullptr) {
+                                                 long long* tm = nullptr, const double* shift_g = nullptr, int* s_ids = nullptr) {
   // BLOCK-COLLECTIVE: every warp of the CTA calls this once per round (has_chain = false for a warp without a chain); the
   // log-density of the CTA's eight proposals is computed cooperatively between two __syncthreads().
   constexpr unsigned FULL = 0xffffffffu;
@@ -529,7 +529,18 @@ __device__ __forceinline__ void fused_chain_step(const hb_k1_params& p, const hb
       }
       rss = hb_warp_sum(rss);
     }
-    if (!has_chain) return;
+    if (!has_chain) {
+      if (shift_g) {                                                    // no chain: no contribution to the statistics
+        const int wib = threadIdx.x >> 5;
+#pragma unroll
+        for (int m = 0; m < ITER; ++m) {
+          const int k = m * 32 + lane;
+          zpart[(size_t)wib * (ITER * 32) + k] = 0.0; zpart[(size_t)(8 + wib) * (ITER * 32) + k] = 0.0; xs[k] = 0.0;
+        }
+        if (lane == 0) s_ids[wib] = -1;
+      }
+      return;
+    }
     if (tm) tm[7] = clock64();
     const double dens = td.konst - 0.5 * (td.df + (double)d) * log1p(rss / td.df);
     __syncwarp();                                                       // xs is rewritten by the next chain
@@ -581,6 +592,25 @@ __device__ __forceinline__ void fused_chain_step(const hb_k1_params& p, const hb
       if (fg.accept_rec) fg.accept_rec[si] = (uint8_t)accf;
       atomicAdd(&s_cnt[1 + id], 1ull);                                  // n_id  :368-369
       if (accf) { atomicAdd(&s_cnt[0], 1ull); atomicAdd(&s_cnt[1 + HB_MAX_NCR + id], 1ull); }   // n_acc :374
+    }
+    if (shift_g) {
+      // adaptation period: this chain's terms of the std_x / jump statistics (R/dream_parallel.R:376-378; the sums of
+      // hb_k3_kernel: shifted post-update state, its square, dx^2 filed under the crossover index).  Rows of zpart / xs that
+      // only this warp touched in the product phase; the CTA folds them in warp order after the next block barrier.
+      const int wib = threadIdx.x >> 5;
+#pragma unroll
+      for (int m = 0; m < ITER; ++m) {
+        const int k = m * 32 + lane;
+        double cc = 0.0, dd = 0.0;
+        if (k < d) {
+          const double xn = accf ? xp[m] : xk[m];
+          cc = xn - __ldcg(shift_g + k);
+          const double dxv = accf ? xp[m] - xk[m] : 0.0;                // :357 (after bound handling), 0 if rejected
+          dd = dxv * dxv;
+        }
+        zpart[(size_t)wib * (ITER * 32) + k] = cc; zpart[(size_t)(8 + wib) * (ITER * 32) + k] = cc * cc; xs[k] = dd;
+      }
+      if (lane == 0) s_ids[wib] = id;
     }
 }
 
@@ -697,6 +727,7 @@ __global__ void __launch_bounds__(256) hb_persist_small_kernel(const hb_k1_param
   __shared__ unsigned long long s_cnt[2 * HB_MAX_NCR + 1];
   __shared__ __align__(8) uint64_t wbar;
   __shared__ __align__(8) uint64_t sbars[8];
+  __shared__ int s_ids[8];
   const int lane = threadIdx.x & 31;
   const int n_wib = blockDim.x >> 5, wib = threadIdx.x >> 5;
   const int stage_rows = (1 + 2 * p0.delta) > 4 ? (1 + 2 * p0.delta) : 4;
@@ -729,7 +760,6 @@ __global__ void __launch_bounds__(256) hb_persist_small_kernel(const hb_k1_param
   long long ind_out = pp.ind_out0, pending = pp.pending0;
   k1_headv hv;
   if (active) k1_chain_head<32, TAPE>(p0, (uint32_t)pp.i0, pp.i0 - 2, warp_id, lane, hv, errbits);
-
   for (long long i = pp.i0; i < pp.i1; ++i) {
     const bool store = ((double)i > pp.burnin * (double)pp.t) && (i % pp.thin == 0);   // R/dream_parallel.R:263, :386
     if (store) ind_out++;
@@ -748,12 +778,29 @@ __global__ void __launch_bounds__(256) hb_persist_small_kernel(const hb_k1_param
     const bool tr = pp.trace && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && i >= pp.i0 + 2 && i < pp.i0 + 6;
     if (tr) tm[4] = clock64();
     fused_chain_step<ITER, TAPE, true>(p0, q0, td, fg, Ws, xs, &wbar, w_ready, hv, lane, s_cnt, errbits, stage, &sbars[wib], sphase,
-                                       xs_all, zpart, active, tr ? tm : nullptr);
+                                       xs_all, zpart, active, tr ? tm : nullptr, pp.adapt ? q0.shift : nullptr, s_ids);
     if (tr) tm[5] = clock64();
     __syncthreads();
     if (tr) tm[6] = clock64();
     const bool upd = (i % pp.update_interval == 0);
     pending += p0.nc;
+    const int E = (p0.nCR + 2) * p0.d;
+    if (pp.adapt) {
+      // this CTA's partial sums, folded over its warps in warp order: [s1 | s2 | Q[0] .. Q[nCR-1]] (hb_k3_kernel's layout)
+      for (int e = threadIdx.x; e < E; e += blockDim.x) {
+        double sum = 0.0;
+        if (e < 2 * p0.d) {
+          const double* col = zpart + (size_t)(e < p0.d ? 0 : 8) * (ITER * 32) + (e < p0.d ? e : e - p0.d);
+#pragma unroll
+          for (int w = 0; w < 8; ++w) sum += col[(size_t)w * (ITER * 32)];
+        } else {
+          const int qq = (e - 2 * p0.d) / p0.d, k = (e - 2 * p0.d) - qq * p0.d;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) sum += (s_ids[w] == qq) ? xs_all[(size_t)w * (ITER * 32) + k] : 0.0;
+        }
+        pp.partials[((size_t)(pp.slot0 + (int)(i - pp.i0)) * gridDim.x + blockIdx.x) * E + e] = sum;
+      }
+    }
     // the per-generation counters stay in shared memory and reach the control block only when somebody reads them: at
     // updateInterval boundaries (AR / CR rows) and at the end of the launch
     if ((upd || i == pp.i1 - 1) && threadIdx.x <= 2 * HB_MAX_NCR) {
@@ -774,7 +821,9 @@ __global__ void __launch_bounds__(256) hb_persist_small_kernel(const hb_k1_param
     if (active && i + 1 < pp.i1) k1_chain_head<32, TAPE>(p0, (uint32_t)(i + 1), i - 1, warp_id, lane, hv, errbits);
     if (threadIdx.x == 0) {
       const unsigned target = gridDim.x * round;
-      if (!upd) {
+      // adaptation period: nothing to fold here -- the statistics of the interval's generations are parked in slots and the
+      // finalize kernels consume them after the launch (which ends at the updateInterval boundary)
+      if (!upd || pp.adapt) {
         while (*reinterpret_cast<volatile unsigned*>(&pp.bar[0]) < target) {}
       } else if (blockIdx.x == 0) {
         while (*reinterpret_cast<volatile unsigned*>(&pp.bar[0]) < target) {}
@@ -788,8 +837,8 @@ __global__ void __launch_bounds__(256) hb_persist_small_kernel(const hb_k1_param
       } else {
         while (*reinterpret_cast<volatile unsigned*>(&pp.bar[1]) < round) {}
       }
-      __threadfence();
     }
+    if (threadIdx.x == 0) __threadfence();
     if (upd) pending = 0;
     __syncthreads();
     if (tr) printf("[persist trace] gen %lld cta %d: setup %lld | sweep %lld | xp %lld | product %lld + log1p %lld | accept+store %lld | block sync %lld | barrier+next head %lld cycles\n",
@@ -1532,8 +1581,8 @@ bool hb_fused_small_eligible(long long n_local, int d, int sm_count) {
 
 cudaError_t hb_launch_persist_small(const hb_k1_params& p, const hb_k3_params& q, const hb_fused_tdist& td,
                                     const hb_persist_params& pp, bool tape_mode, int sm_count, cudaStream_t st) {
-  if (!hb_fused_small_eligible(p.n_local, p.d, sm_count) || p.past_sample || p.n_peers > 1 || q.adapt || q.n_runs > 1 ||
-      q.accept_in || q.lik22 || q.log_rows || pp.XA == pp.XB || pp.i1 <= pp.i0)
+  if (!hb_fused_small_eligible(p.n_local, p.d, sm_count) || p.past_sample || p.n_peers > 1 || q.n_runs > 1 ||
+      q.accept_in || q.lik22 || q.log_rows || pp.XA == pp.XB || pp.i1 <= pp.i0 || (pp.adapt && (!pp.partials || !pp.shift)))
     return cudaErrorInvalidValue;
   if (p.d <= 32) return launch_persist<1>(p, q, td, pp, tape_mode, sm_count, st);
   if (p.d <= 64) return launch_persist<2>(p, q, td, pp, tape_mode, sm_count, st);

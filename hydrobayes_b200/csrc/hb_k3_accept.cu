@@ -482,14 +482,15 @@ __global__ void __launch_bounds__(256) hb_finalize_reduce_kernel(const hb_fin_pa
   const int d = p.d, E = (p.nCR + 2) * d;
   const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int e = blockIdx.x * 32 + c;
+  const double* partials = p.partials + (size_t)blockIdx.y * p.nblocks * E;     // blockIdx.y: slot (generation of an interval)
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
   if (e < E) {
     int b = g;
     for (; b + 24 < p.nblocks; b += 32) {                   // four independent loads in flight
-      s0 += p.partials[(size_t)b * E + e]; s1 += p.partials[(size_t)(b + 8) * E + e];
-      s2 += p.partials[(size_t)(b + 16) * E + e]; s3 += p.partials[(size_t)(b + 24) * E + e];
+      s0 += partials[(size_t)b * E + e]; s1 += partials[(size_t)(b + 8) * E + e];
+      s2 += partials[(size_t)(b + 16) * E + e]; s3 += partials[(size_t)(b + 24) * E + e];
     }
-    for (; b < p.nblocks; b += 8) s0 += p.partials[(size_t)b * E + e];
+    for (; b < p.nblocks; b += 8) s0 += partials[(size_t)b * E + e];
   }
   part[g][c] = (s0 + s1) + (s2 + s3);
   __syncthreads();
@@ -497,7 +498,8 @@ __global__ void __launch_bounds__(256) hb_finalize_reduce_kernel(const hb_fin_pa
     double s = 0.0;
 #pragma unroll
     for (int q = 0; q < 8; ++q) s += part[q][c];
-    if (e < 2 * d) p.colsum[e] = s; else p.qsum[e - 2 * d] = s;
+    const size_t so = (size_t)blockIdx.y * p.slot_stride;
+    if (e < 2 * d) p.colsum[so + e] = s; else p.qsum[so + e - 2 * d] = s;
   }
 }
 
@@ -544,7 +546,20 @@ __global__ void hb_proxy_kernel(const double* __restrict__ hist, long long n, lo
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   double s = 0.0, c = 0.0;
-  for (long long r = row0; r <= row1; ++r) {
+  long long r = row0;
+  for (; r + 8 <= row1 + 1; r += 8) {            // eight loads in flight; the compensated sum runs in row order as before
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = hist[(r + u) * ld + j];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const double y = v[u] - c;
+      const double t = s + y;
+      c = (t - s) - y;
+      s = t;
+    }
+  }
+  for (; r <= row1; ++r) {
     const double y = hist[r * ld + j] - c;
     const double t = s + y;
     c = (t - s) - y;
@@ -716,7 +731,7 @@ cudaError_t hb_launch_k3(const hb_k3_params& p, int sm_count, int* nblocks_out, 
 cudaError_t hb_launch_finalize(const hb_fin_params& p, cudaStream_t st) {
   if (p.adapt && (p.phase == 0 || p.phase == 2)) {
     const int E = (p.nCR + 2) * p.d;
-    hb_finalize_reduce_kernel<<<(E + 31) / 32, 256, 0, st>>>(p);
+    hb_finalize_reduce_kernel<<<dim3((E + 31) / 32, p.reduce_slots > 0 ? p.reduce_slots : 1), 256, 0, st>>>(p);
   }
   if (p.phase != 0) hb_finalize_kernel<<<1, 256, 0, st>>>(p);
   return cudaGetLastError();
@@ -724,7 +739,8 @@ cudaError_t hb_launch_finalize(const hb_fin_params& p, cudaStream_t st) {
 
 cudaError_t hb_launch_proxy(const double* lpost_hist, long long nc_local, long long row0, long long row1, long long ld,
                             double* proxy, cudaStream_t st) {
-  hb_proxy_kernel<<<(unsigned)((nc_local + 255) / 256), 256, 0, st>>>(lpost_hist, nc_local, row0, row1, ld, proxy);
+  const int th = nc_local >= 256 * 64 ? 256 : 64;          // small populations: more, smaller CTAs (the loop is latency bound)
+  hb_proxy_kernel<<<(unsigned)((nc_local + th - 1) / th), th, 0, st>>>(lpost_hist, nc_local, row0, row1, ld, proxy);
   return cudaGetLastError();
 }
 

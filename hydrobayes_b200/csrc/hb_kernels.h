@@ -82,6 +82,13 @@ struct hb_persist_params {
   long long pending0;       // evaluations since the last AR / CR fold
   double* out_ar; double* out_cr; long long ar_rows;
   unsigned* bar;            // [2], zero at launch: arrivals, released round
+  int adapt;                // generations inside the adaptation period: every CTA parks its std_x / jump statistic sums of
+                            // generation i in slot slot0 + (i - i0); the finalize kernels fold the slots after the launch, which
+                            // must END at the next updateInterval boundary (pCR changes there; the next generation's draws,
+                            // computed under the barrier, read it)
+  int slot0;
+  double* partials;         // adapt: [slots][grid][(nCR + 2) * d] per-CTA sums
+  const double* shift;      // adapt: [d] column shift of the one-pass variance, constant over the interval
   int trace;                // HB_PERSIST_TRACE=1: per-phase clock counts of a few generations on stdout (diagnostics)
 };
 cudaError_t hb_launch_persist_small(const hb_k1_params& p, const hb_k3_params& q, const hb_fused_tdist& td,
@@ -154,6 +161,7 @@ int hb_k3_grid(long long n_local, int d, int nCR, int sm_count, int force_wide, 
 struct hb_fin_params {
   hb_ctrl* ctrl;
   const double* partials; int nblocks;
+  int reduce_slots;       // phase 0: partials holds this many [nblocks][E] blocks; block s is reduced into colsum/qsum + s*slot_stride (0 = 1)
   double* shift;          // [d]
   double* colsum;         // [2*d] reduced (sum, sumsq) of the shifted columns -- exposed for multi-GPU all-reduce
   double* qsum;           // [nCR*d]

@@ -190,6 +190,41 @@ def test_fused_small_population_generation(hb, oracle, monkeypatch, bound, nativ
     assert dev["timing"][1] < ref["timing"][1] - (t - 1 - int(0.2 * t)) , "the fused path was not taken"
 
 
+@pytest.mark.parametrize("native", [False, True])
+@pytest.mark.parametrize("d,nc,slice_g", [(100, 64, None), (40, 37, 7), (20, 200, 13)])
+def test_persistent_kernel_in_adaptation_period(hb, oracle, monkeypatch, native, d, nc, slice_g):
+    # The adaptation period of a small population inside the persistent kernel (hb_persist_small_kernel with adapt = 1):
+    # per-CTA std_x / jump statistics, CTA 0 folds them and updates J / pCR / the AR-CR rows inside the grid barrier, one
+    # cooperative launch per updateInterval with the outlier check (R/dream_parallel.R:414-419) between the launches.
+    # Parity with the oracle (forced outlier resets included) and with the per-generation kernels (HB_PERSIST_ADAPT=0).
+    t = 120
+    cfg = A.default_config(nc=nc, t=t, d=d, lik=2, seed=70 + d, adapt=0.6, thin=2, record_accept=1, update_interval=10)
+    x0 = 0.3 * H.x0_tdist(nc, d); x0[1] = 250.0; x0[nc - 2] = -180.0          # two chains far out: outlier resets
+    kw = dict(slice_generations=slice_g) if slice_g else {}
+    monkeypatch.setenv("HB_PERSIST_ADAPT", "1")
+    if native:
+        cfg_t, tape_kw = cfg, {}
+        ora = oracle.run(cfg, "t_distribution", x0)
+        dev = H.run_device(cfg, "t_distribution", x0, **kw)
+        H.assert_run_parity(dev, ora, rtol=1e-9, atol=1e-12)
+    else:
+        rec = oracle.Tape.for_config(cfg)
+        assert oracle.run(cfg, "t_distribution", x0, record=rec)["rc"] == 0
+        cfg_t = H.copy_cfg(cfg, rng_mode=A.HB_RNG_TAPE)
+        ora = oracle.run(cfg_t, "t_distribution", x0, tape=rec)
+        tape_kw = dict(tape=rec)
+        dev = H.run_device(cfg_t, "t_distribution", x0, **tape_kw, **kw)
+        H.assert_run_parity(dev, ora, rtol=1e-10)
+    assert len(ora["outlier"]) > 0
+    monkeypatch.setenv("HB_PERSIST_ADAPT", "0")
+    ref = H.run_device(cfg_t, "t_distribution", x0, **tape_kw, **kw)
+    assert np.array_equal(ref["accept"], dev["accept"]) and ref["outlier"] == dev["outlier"]
+    np.testing.assert_allclose(dev["chain"], ref["chain"], rtol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(dev["CR"], ref["CR"], rtol=1e-12, equal_nan=True)
+    np.testing.assert_array_equal(dev["AR"], ref["AR"])
+    assert dev["timing"][1] < ref["timing"][1] - 3 * int(0.6 * t) // 2, "the adaptation period did not run in the persistent kernel"
+
+
 def test_series_fx_opt_in(hb, oracle):
     """fx of a series target (HydroModel: m = T values per stored state, R/dream_parallel.R:230, 394) is not kept on the
     device; series_fx=True rebuilds it from the stored chain, and it equals the reference's fx wherever that is not stale
