@@ -303,8 +303,11 @@ int allocate(hb_handle* h) {
   CK(dalloc(&h->id, mtn));
   CK(dalloc(&h->lp_xp, mtn)); CK(dalloc(&h->ll_raw, mtn)); CK(dalloc(&h->fx_xp, mtn));
   if (c.mt > 1) {
-    CK(dalloc(&h->ZT, (size_t)nl * ldx));
-    CK(cudaMemsetAsync(h->ZT, 0, (size_t)nl * ldx * sizeof(double), h->stream));
+    // candidates zt: the reference proposals draw their partners from the WHOLE candidate population (R/dream_parallel.R:316),
+    // so a sharded run keeps a full-size copy (this rank's rows at chain0, the others all-gathered every generation)
+    const size_t zrows = h->world > 1 ? (size_t)h->nc : (size_t)nl;
+    CK(dalloc(&h->ZT, zrows * ldx));
+    CK(cudaMemsetAsync(h->ZT, 0, zrows * ldx * sizeof(double), h->stream));
     CK(dalloc(&h->lp_zt, (size_t)nl)); CK(dalloc(&h->ll_zt, (size_t)nl)); CK(dalloc(&h->fx_zt, (size_t)nl));
     CK(dalloc(&h->id_zt, (size_t)nl)); CK(dalloc(&h->mt_p1, (size_t)nl)); CK(dalloc(&h->mt_accept, (size_t)nl));
   }
@@ -729,24 +732,31 @@ int mt_generation(hb_handle* h, long long i, bool store, bool in_adapt, bool tap
     ps.done();
     return HB_OK;
   };
+  double* const ZTl = h->world > 1 ? h->ZT + (size_t)h->chain0 * ldx : h->ZT;               // this rank's rows of the candidate population
+  const double* const ZTpop = h->world > 1 ? h->ZT : h->ZT - (size_t)h->chain0 * ldx;     // indexed by the chain number, like X
   for (int m = 0; m < mt; ++m) if (int rc = k1_set(m, m, h->X)) return rc;                 // :269  around xt
   if (int rc = hb_prior_after_k1(h, (long long)mt * nl)) return rc;
   { prof_scope ps(h, "K2"); if (int rc = hb_target_launch(h, h->XP, (long long)mt * nl, h->chain0, 1)) return fail(h, rc, "target launch failed"); ps.done(); }
   hb_mt_params mp{};
   mp.mt = mt; mp.n_local = nl; mp.ldx = ldx; mp.XP = h->XP; mp.lp_xp = h->lp_xp; mp.ll_raw = h->ll_raw;
-  mp.fx_xp = c.store_fx ? h->fx_xp : nullptr; mp.id = h->id; mp.ZT = h->ZT; mp.lp_zt = h->lp_zt; mp.ll_zt = h->ll_zt;
+  mp.fx_xp = c.store_fx ? h->fx_xp : nullptr; mp.id = h->id; mp.ZT = ZTl; mp.lp_zt = h->lp_zt; mp.ll_zt = h->ll_zt;
   mp.fx_zt = c.store_fx ? h->fx_zt : nullptr; mp.id_zt = h->id_zt; mp.p1 = h->mt_p1; mp.lpost = h->lpost;
   mp.accept_out = h->mt_accept; mp.seed = c.seed; mp.gen = (uint32_t)i; mp.gchain0 = (long long)c.run_offset * h->nc + h->chain0;
   mp.err = &h->ctrl->err;
-  mp.tape_pick = tape_mode ? h->tape_mt_pick + (size_t)(i - 2) * h->tape.nct : nullptr;
-  mp.u_accept = tape_mode ? h->tape.u_accept + (size_t)(i - 2) * h->tape.nct : nullptr;
+  mp.tape_pick = tape_mode ? h->tape_mt_pick + (size_t)(i - 2) * h->tape.nct + h->chain0 : nullptr;   // indexed by the local chain
+  mp.u_accept = tape_mode ? h->tape.u_accept + (size_t)(i - 2) * h->tape.nct + h->chain0 : nullptr;
   { prof_scope ps(h, "MT"); CK(hb_launch_mt_select(mp, h->stream)); ps.done(); }           // :297-314
-  for (int m = 0; m < mt - 1; ++m) if (int rc = k1_set(mt + m, m, h->ZT)) return rc;       // :316  around zt
+  if (h->world > 1) {   // every rank needs every candidate row: partners of the reference proposals come from all of zt
+    prof_scope ps(h, "XCHG");
+    if (int rc = hb_nccl_allgather_f64(h->comm, ZTl, h->ZT, (size_t)nl * ldx, h->stream, h->err)) return rc;
+    ps.done();
+  }
+  for (int m = 0; m < mt - 1; ++m) if (int rc = k1_set(mt + m, m, ZTpop)) return rc;       // :316  around zt
   if (int rc = hb_prior_after_k1(h, (long long)(mt - 1) * nl)) return rc;
   { prof_scope ps(h, "K2"); if (int rc = hb_target_launch(h, h->XP, (long long)(mt - 1) * nl, h->chain0, 1)) return fail(h, rc, "target launch failed"); ps.done(); }
   { prof_scope ps(h, "MT"); CK(hb_launch_mt_accept(mp, h->stream)); ps.done(); }           // :340, R/internals.R:229-236
   hb_k3_params p = hb_make_k3(h, i, h->chain0, 1, nl, store, in_adapt, false);
-  p.XP = h->ZT; p.XP_rw = h->ZT; p.id = h->id_zt; p.lp_xp = h->lp_zt; p.ll_raw = h->ll_zt;   // :349-355 accept the candidates
+  p.XP = ZTl; p.XP_rw = ZTl; p.id = h->id_zt; p.lp_xp = h->lp_zt; p.ll_raw = h->ll_zt;   // :349-355 accept the candidates
   p.fx_xp = c.store_fx ? h->fx_zt : nullptr; p.accept_in = h->mt_accept;
   prof_scope ps(h, "K3");
   int nb = 0;
@@ -1377,7 +1387,8 @@ int hb_comm_init(hb_handle* h, int rank, int world, const void* id128) {
   if (world < 1 || rank < 0 || rank >= world) return fail(h, HB_ERR_INVALID, "bad rank/world");
   if (h->nc % world) return fail(h, HB_ERR_INVALID, "nc must be divisible by the number of GPUs");
   if (h->cfg.sweep != HB_SWEEP_SYNCHRONOUS || h->cfg.n_runs > 1) return fail(h, HB_ERR_UNSUPPORTED, "only the synchronous single-population sweep shards across GPUs");
-  if (h->cfg.mt > 1 && world > 1) return fail(h, HB_ERR_UNSUPPORTED, "mt > 1 (MT-DREAM) is single-GPU for now: the candidate population zt would need its own exchange");
+  if (h->cfg.mt > 1 && world > 1 && h->cfg.exchange != HB_EXCHANGE_ALLGATHER)
+    return fail(h, HB_ERR_UNSUPPORTED, "mt > 1 (MT-DREAM) on several GPUs runs over HB_EXCHANGE_ALLGATHER (the candidate population zt is all-gathered too)");
   cudaSetDevice(h->device);
   const double t_begin = now_s();
   // HB_EXCHANGE_DELTA needs no NCCL communicator: its barriers and small collectives run over peer-mapped memory

@@ -436,7 +436,9 @@ def _drive(sweep, fun, extra, lik, par_info, nc, t, d, burnin, adapt, updateInte
         if world > 1:
             if sweep != A.HB_SWEEP_SYNCHRONOUS:
                 raise A.HbError(A.HB_ERR_UNSUPPORTED, "only dream_parallel (synchronous sweep) shards across GPUs")
-            cfg.exchange = A.HB_EXCHANGE_DELTA if exchange is None else exchange   # also with the DREAM-ZS archive (replicated per rank)
+            # delta exchange also with the DREAM-ZS archive (replicated per rank); MT-DREAM all-gathers the state and the
+            # candidate population zt (R/dream_parallel.R:316 draws the reference proposals' partners from all of zt)
+            cfg.exchange = (A.HB_EXCHANGE_ALLGATHER if mt > 1 else A.HB_EXCHANGE_DELTA) if exchange is None else exchange
     n_shard = shard_range(nc, rank, world)[1] if world > 1 else None
     with Sampler(cfg, device) as s:
         if par_info.get("min") is not None and par_info.get("max") is not None:

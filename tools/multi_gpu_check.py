@@ -67,6 +67,10 @@ def main():
     zs = A.default_config(nc=ncz, t=160, d=dz, lik=2, seed=11, past_sample=1, psnooker=0.2, m0=m0, archive_update=5, record_accept=1)
     xz = np.random.default_rng(7).uniform(-5, 15, size=(m0, dz))
     cases += [("tdist d=12 ZS+snooker", zs, "t_distribution", xz, {}, 0), ("tdist d=12 ZS+snooker", zs, "t_distribution", xz, {}, 2)]
+    # MT-DREAM (mt > 1) on a sharded population: all-gather exchange of the state and of the candidate population zt
+    ncm, dm = 16 * world, 20
+    mtc = A.default_config(nc=ncm, t=120, d=dm, lik=2, seed=13, mt=3, adapt=0.3, record_accept=1)
+    cases += [("tdist d=20 MT-DREAM mt=3", mtc, "t_distribution", H.x0_tdist(ncm, dm), {}, 0)]
     for name, cfg, tgt, x0, kw, xmode in cases:
         peer = xmode != 0
         if xmode:
