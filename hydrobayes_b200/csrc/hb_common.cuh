@@ -243,5 +243,21 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 template <int N>
 __device__ __forceinline__ void tma_store_wait() { asm volatile("cp.async.bulk.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+// ---- fp64 tensor-core tile (mma.sync m8n8k4 f64 -> SASS DMMA) and the block-triangular layout of the t-distribution's
+// W = chol(C)^-1 (hb_targets.cu: hb_tdist_dmma_kernel; hb_k1_propose.cu: the product phase of the fused small-population kernels) ----
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__host__ __device__ constexpr int tdist_blk_base(int nb, int KB) {   // blocks of the n-blocks before nb
+  int s = 0;
+  for (int j = 0; j < nb; ++j) s += (2 * j + 2 < KB) ? 2 * j + 2 : KB;
+  return s;
+}
+__host__ __device__ constexpr int tdist_n_blocks(int KB) { return tdist_blk_base((KB + 1) / 2, KB); }
+
+
 __device__ __forceinline__ double hb_warp_sum(double v) { return hb_group_sum<32>(v); }
 #endif  // __CUDACC__

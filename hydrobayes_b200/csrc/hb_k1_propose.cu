@@ -309,7 +309,9 @@ __device__ __forceinline__ void k1_chain_body(const hb_k1_params& p, uint32_t ge
       }
       kmin = bk; d_star = 1;
     }
-    const double gamma_d = 2.38 / sqrt(2.0 * (double)D * (double)d_star);   // :190
+    // :190  2.38/sqrt(2 D d*): the host-built table when there is one (same IEEE sqrt and division: bit-identical), which
+    // spares the warp ~40 fp64 instructions
+    const double gamma_d = p.gamma_tab ? __ldg(p.gamma_tab + (D - 1) * d + (d_star - 1)) : 2.38 / sqrt(2.0 * (double)D * (double)d_star);
     const double gam = g_is_one ? 1.0 : gamma_d;                            // :192
     rows_ready();
     int rank_base = 0;
@@ -425,6 +427,84 @@ __device__ __forceinline__ fused_gen fused_gen_of(const hb_k3_params& q) {
   return g;
 }
 
+// ---- the cooperative triangular product of the fused small-population kernels ----
+// z = xp W for the CTA's eight proposals is exactly one row block of the fp64 tensor-core tile (mma.sync m8n8k4 -> DMMA): A =
+// the 8 x 4 slice of the proposals, B = a 4 x 8 block of W in fragment order (the plugin's operand, hb_targets.cu), so a
+// k step costs two 64-bit shared loads per lane instead of the 24-72 shared-memory wavefronts per 32 FMAs of a broadcast /
+// FMA formulation (which is what bounded this phase: measured 4 400 cycles with 8 warps, 5 800 with 16).
+// Column block nb (columns 8 nb .. 8 nb + 7) needs the k blocks kb < K_nb = min(2 nb + 2, KB).  The column blocks are dealt
+// to the product warps longest first (each to the warp with the least work so far: 25 | 24 | 22 + 2 | 20 + 4 | ... at d = 100);
+// a warp runs the DMMA chain of each of its blocks (two accumulators: a dependent DMMA costs ~90 cycles), squares the tile
+// and adds it to its partial residual sum of squares per proposal; the warp that owns a chain adds the partials of the
+// product warps in a fixed order.  Nothing but eight doubles per product warp crosses warps.
+constexpr int FUSED_MAX_WORK = 8;
+struct fused_plan {
+  int nseg, NB, T;                // product warps, column blocks, 32-double blocks of the fragment-ordered W
+  int xld, zld;                   // row strides of the proposal tile (== 4 mod 16: conflict-free A loads) and of the statistics rows
+  short n_work[16];               // column blocks of product warp s ...
+  short work_nb[16][FUSED_MAX_WORK];   // ... in the order it runs them
+  short K[16], blk_base[16];      // k blocks of column block nb; its first 32-double block in the fragment-ordered W
+};
+inline bool fused_make_plan(int KB, int nseg, fused_plan* out) {
+  fused_plan pl{};
+  const int NB = (KB + 1) / 2;
+  if (nseg > 16 || NB > 16) return false;
+  pl.nseg = nseg; pl.NB = NB; pl.zld = 8 * NB; pl.xld = 4 * KB + ((4 - (4 * KB) % 16) + 16) % 16;
+  int T = 0;
+  for (int nb = 0; nb < NB; ++nb) { pl.K[nb] = (short)((2 * nb + 2 < KB) ? 2 * nb + 2 : KB); pl.blk_base[nb] = (short)T; T += pl.K[nb]; }
+  pl.T = T;
+  int load[16] = {0};
+  for (int nb = NB - 1; nb >= 0; --nb) {       // K is non-decreasing in nb: longest first
+    int best = 0;
+    for (int s2 = 1; s2 < nseg; ++s2) if (load[s2] < load[best]) best = s2;
+    if (pl.n_work[best] >= FUSED_MAX_WORK) return false;
+    pl.work_nb[best][pl.n_work[best]++] = (short)nb;
+    load[best] += pl.K[nb];
+  }
+  *out = pl;
+  return true;
+}
+// shared memory of the fused kernels in doubles: W blocks | proposal tile [8][xld] | statistics rows [16][zld] | row stages
+inline size_t fused_smem_doubles(const fused_plan& pl, int stage_rows, int ldx) {
+  return (size_t)pl.T * 32 + (size_t)8 * pl.xld + (size_t)16 * pl.zld + (size_t)8 * stage_rows * ldx;
+}
+
+// What a product warp does never changes during a launch, so every warp unpacks its part of the plan once, into shared
+// memory: entry = {first double of the block's B fragments, DMMA steps}; rsspart[s][c]: warp s's part of proposal c's sum.
+struct fused_work { int n[16]; int2 e[16][FUSED_MAX_WORK]; double rsspart[16][8]; };
+__device__ __forceinline__ void fused_work_init(fused_work* wk, const fused_plan& pl) {
+  const int seg = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane != 0 || seg >= pl.nseg || seg >= 16) return;
+  const int n = pl.n_work[seg];
+  for (int q = 0; q < n; ++q) { const int nb = pl.work_nb[seg][q]; wk->e[seg][q] = make_int2(pl.blk_base[nb] * 32, pl.K[nb]); }
+  wk->n[seg] = n;
+}
+
+__device__ __forceinline__ void fused_product(const double* __restrict__ Ws, const double* __restrict__ xs_all, fused_work* wk, int xld,
+                                              int seg, int lane) {
+  const int gid = lane >> 2, tig = lane & 3;
+  const double* __restrict__ ap = xs_all + gid * xld + tig;                // A fragment: proposal gid, coordinate 4 kb + tig
+  const double* __restrict__ wl = Ws + lane;                               // B fragment of a block: element `lane`
+  const int nw = wk->n[seg];
+  double r = 0.0;
+  for (int e = 0; e < nw; ++e) {
+    const int2 w = wk->e[seg][e];
+    const double* __restrict__ bp = wl + w.x;
+    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;                         // C: row gid, columns 2 tig, 2 tig + 1; even / odd k blocks
+    int i = 0;
+    for (; i + 2 <= w.y; i += 2) {
+      dmma884(c0, c1, ap[4 * i], bp[32 * i]);
+      dmma884(e0, e1, ap[4 * i + 4], bp[32 * i + 32]);
+    }
+    if (i < w.y) dmma884(c0, c1, ap[4 * i], bp[32 * i]);
+    c0 += e0; c1 += e1;
+    r = fma(c0, c0, r); r = fma(c1, c1, r);
+  }
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  r += __shfl_xor_sync(0xffffffffu, r, 2);
+  if (tig == 0) wk->rsspart[seg][gid] = r;
+}
+
 // One chain's whole generation for the warp that owns it: proposal, t-distribution log-density, Metropolis decision, state
 // update into q.Xout and history store.  Shared by the one-launch-per-generation kernel and the persistent kernel below.
 template <int ITER, bool TAPE, bool CG = false>
@@ -433,16 +513,18 @@ __device__ __forceinline__ void fused_chain_step(const hb_k1_params& p, const hb
                                                  const k1_headv& hv, int lane, unsigned long long* s_cnt, unsigned& errbits,
                                                  double* stage, uint64_t* sbar, unsigned& sphase,
                                                  const double* __restrict__ xs_all, double* __restrict__ zpart, bool has_chain,
-                                                 long long* tm = nullptr, const double* shift_g = nullptr, int* s_ids = nullptr) {
+                                                 const fused_plan& pl, fused_work* wk, long long* tm = nullptr,
+                                                 const double* shift_g = nullptr, int* s_ids = nullptr, const double* logu_pre = nullptr) {
   // BLOCK-COLLECTIVE: every warp of the CTA calls this once per round (has_chain = false for a warp without a chain); the
   // log-density of the CTA's eight proposals is computed cooperatively between two __syncthreads().
   constexpr unsigned FULL = 0xffffffffu;
-  constexpr int LDW_S = ITER * 32 + 4;   // row stride of W in shared memory: a compile-time constant, so the unrolled density
-                                         // loop addresses W with immediate offsets (no per-load address arithmetic)
   const int d = p.d, ldx = p.ldx;
     // ---------------- proposal (K1) ----------------
     double xk[ITER], dxk[ITER], xp[ITER];
     const long long jl = has_chain ? hv.jl : 0; const int id = has_chain ? hv.id : 0;
+    // the chain's current log posterior: fetched now, needed by the Metropolis decision at the end (an L2 round trip)
+    double lpost_early = 0.0;
+    if (lane == 0 && has_chain) lpost_early = q.lpost[q.chain0 + jl * q.stride - q.state0];
     if (tm) tm[0] = clock64();
 #pragma unroll
     for (int m = 0; m < ITER; ++m) { xk[m] = 0.0; dxk[m] = 0.0; }
@@ -463,7 +545,7 @@ __device__ __forceinline__ void fused_chain_step(const hb_k1_params& p, const hb
         }
         xp[m] = v;
       }
-      xs[k] = xp[m];
+      if (xs && k < pl.xld) xs[k] = xp[m];                              // (columns d .. 4 KB - 1 of the tile: zeros)
     }
     if (p.prior == 1) lp_part = hb_group_sum<32>(lp_part);
     double lpx = (p.prior == 1) ? lp_part : 0.0;                        // flat prior: 0  :55
@@ -472,70 +554,34 @@ __device__ __forceinline__ void fused_chain_step(const hb_k1_params& p, const hb
     __syncwarp();
 
     // ---------------- log-density (K2): dmvt, R/test_t_distribution.R:43 ----------------
-    // z_n = sum_{k <= n} xp_k W[k][n] for the EIGHT proposals of the CTA at once.  A warp that streams W from shared memory
-    // for its own chain alone moves 75 KB per chain: eight warps saturate the SM's shared-memory bandwidth (measured: 6 500
-    // cycles of a 21 000-cycle generation, whatever the FMA arrangement).  Instead warp w takes work unit (m, h) = (w % ITER... ,
-    // half h of the k range of column block m): each W element is read once per CTA and feeds eight accumulators, the
-    // proposals come in as shared-memory broadcasts.  The two halves of a column meet in zpart and the warp that owns the
-    // chain folds them, squares and reduces.  The strict lower triangle of W is stored as zeros (tdist_build), so no term
-    // needs a predicate.  ll differs from the DMMA plugin's in the last bits (<= 1e-13 relative); states and decisions agree.
+    // z_n = sum_{k <= n} xp_k W[k][n] for the EIGHT proposals of the CTA at once on the fp64 tensor cores (fused_product
+    // above); the warp that owns a chain folds the partial tiles of its row, squares and reduces.  ll differs from the
+    // plugin's in the last bits (<= 1e-13 relative: the k range of a column is cut at other places); states and decisions agree.
     if (!w_ready) { mbar_wait(wbar, 0); w_ready = true; }                // W has landed (first round of the launch only)
     __syncthreads();                                                     // the eight proposals are in xs_all
     if (tm) tm[2] = clock64();
     {
       const int wib = threadIdx.x >> 5;
-      if (wib < 2 * ITER) {
-        const int m = wib >> 1, h = wib & 1;
-        const int kend = (m * 32 + 32 < d) ? m * 32 + 32 : d;
-        const int kmid = ((kend + 1) / 2 + 3) & ~3;                      // a multiple of four: whole unrolled groups in the first half
-        const int k0 = h ? (kmid < kend ? kmid : kend) : 0, k1 = h ? kend : (kmid < kend ? kmid : kend);
-        const int n = m * 32 + lane;
-        const double* wcol = Ws + (n < d ? n : d - 1);                   // lanes past d: a valid column, result unused
-        double acc[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) acc[c] = 0.0;
-        int k = k0;
-        for (; k + 4 <= k1; k += 4) {
-          double w4[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) w4[u] = wcol[(size_t)(k + u) * LDW_S];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {       // four proposals' coordinates per chain as two 128-bit broadcasts (the loop is bound
-                                               // by shared-memory instructions, not by the FMAs)
-            const double2 xa = *reinterpret_cast<const double2*>(xs_all + c * (ITER * 32) + k);
-            const double2 xb = *reinterpret_cast<const double2*>(xs_all + c * (ITER * 32) + k + 2);
-            acc[c] = fma(xa.x, w4[0], acc[c]); acc[c] = fma(xa.y, w4[1], acc[c]);
-            acc[c] = fma(xb.x, w4[2], acc[c]); acc[c] = fma(xb.y, w4[3], acc[c]);
-          }
-        }
-        for (; k < k1; ++k) {
-          const double w1 = wcol[(size_t)k * LDW_S];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) acc[c] = fma(xs_all[c * (ITER * 32) + k], w1, acc[c]);
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) zpart[(size_t)(h * 8 + c) * (ITER * 32) + n] = acc[c];
-      }
+      if (wib < pl.nseg) fused_product(Ws, xs_all, wk, pl.xld, wib, lane);
     }
-    __syncthreads();                                                     // both halves of every column are in zpart
+    if (tm) tm[8] = clock64();
+    __syncthreads();                                                     // every product warp's partial sums are in place
+    if (tm) tm[9] = clock64();
     double rss = 0.0;
-    {
+    if (has_chain) {                                                     // fixed tree over the product warps
       const int wib = threadIdx.x >> 5;
+      rss = (lane < pl.nseg) ? wk->rsspart[lane & 15][wib] : 0.0;
 #pragma unroll
-      for (int m = 0; m < ITER; ++m) {
-        const int n = m * 32 + lane;
-        const double zz = zpart[(size_t)wib * (ITER * 32) + n] + zpart[(size_t)(8 + wib) * (ITER * 32) + n];
-        if (n < d) rss = fma(zz, zz, rss);
-      }
-      rss = hb_warp_sum(rss);
+      for (int o = 8; o > 0; o >>= 1) rss += __shfl_xor_sync(FULL, rss, o);
+      rss = __shfl_sync(FULL, rss, 0);
     }
     if (!has_chain) {
-      if (shift_g) {                                                    // no chain: no contribution to the statistics
+      if (shift_g && xs) {                                              // no chain: no contribution to the statistics
         const int wib = threadIdx.x >> 5;
 #pragma unroll
         for (int m = 0; m < ITER; ++m) {
           const int k = m * 32 + lane;
-          zpart[(size_t)wib * (ITER * 32) + k] = 0.0; zpart[(size_t)(8 + wib) * (ITER * 32) + k] = 0.0; xs[k] = 0.0;
+          if (k < d) { zpart[(size_t)wib * pl.zld + k] = 0.0; zpart[(size_t)(8 + wib) * pl.zld + k] = 0.0; xs[k] = 0.0; }
         }
         if (lane == 0) s_ids[wib] = -1;
       }
@@ -558,12 +604,13 @@ __device__ __forceinline__ void fused_chain_step(const hb_k1_params& p, const hb
       if (!isfinite(llr)) errbits |= HB_FLAG_LL_NONFINITE;              // :21
       lln = llr;
       lpostx = lpx + lln;                                               // R/dream_parallel.R:291
-      lpost_old = q.lpost[si];
-      double u;
-      if (TAPE) u = fg.u_accept[j];
-      else { const hb_phx ph(q.seed, (uint64_t)gch, fg.gen); u = hb_u53(hb_pair64(ph.slot(HB_SLOT_ACCEPT), 0)); }
+      lpost_old = lpost_early;
+      double logu;
+      if (TAPE) logu = log(fg.u_accept[j]);
+      else if (logu_pre) logu = *logu_pre;                              // the persistent kernel draws it while the grid barrier is in flight
+      else { const hb_phx ph(q.seed, (uint64_t)gch, fg.gen); logu = log(hb_u53(hb_pair64(ph.slot(HB_SLOT_ACCEPT), 0))); }
       const double p_acc = fmin(fmax(-100.0, lpostx - lpost_old), 0.0); // R/internals.R:239
-      accf = p_acc > log(u);                                            // :241
+      accf = p_acc > logu;                                              // :241
     }
     accf = __shfl_sync(FULL, accf, 0);
 #pragma unroll
@@ -608,7 +655,7 @@ __device__ __forceinline__ void fused_chain_step(const hb_k1_params& p, const hb
           const double dxv = accf ? xp[m] - xk[m] : 0.0;                // :357 (after bound handling), 0 if rejected
           dd = dxv * dxv;
         }
-        zpart[(size_t)wib * (ITER * 32) + k] = cc; zpart[(size_t)(8 + wib) * (ITER * 32) + k] = cc * cc; xs[k] = dd;
+        if (k < d) { zpart[(size_t)wib * pl.zld + k] = cc; zpart[(size_t)(8 + wib) * pl.zld + k] = cc * cc; xs[k] = dd; }
       }
       if (lane == 0) s_ids[wib] = id;
     }
@@ -628,43 +675,45 @@ __device__ __forceinline__ void fused_chain_step(const hb_k1_params& p, const hb
 //   accept        the non-adaptation path of hb_k3_kernel (R/internals.R:239-241, R/dream_parallel.R:348-366, 386-394)
 // ------------------------------------------------------------------------------------------------------------------
 template <int ITER, bool TAPE>
-__global__ void __launch_bounds__(256) hb_fused_small_kernel(const hb_k1_params p, const hb_k3_params q, const hb_fused_tdist td) {
+__global__ void __launch_bounds__(256) hb_fused_small_kernel(const hb_k1_params p, const hb_k3_params q, const hb_fused_tdist td,
+                                                             const fused_plan pl) {
   constexpr unsigned FULL = 0xffffffffu;
-  extern __shared__ __align__(16) double fused_smem[];               // W [d][ldw] | xs [warps][ITER * 32] | row stages [warps][rows][ldx]
+  extern __shared__ __align__(16) double fused_smem[];               // W blocks | proposal tile [8][xld] | statistics rows [16][zld] | row stages [8][rows][ldx]
   __shared__ unsigned long long s_cnt[2 * HB_MAX_NCR + 1];
   __shared__ __align__(8) uint64_t wbar;
   __shared__ __align__(8) uint64_t sbars[8];
+  __shared__ fused_work s_work;
   const int lane = threadIdx.x & 31;
   const int n_wib = blockDim.x >> 5, wib = threadIdx.x >> 5;
   const int stage_rows = (1 + 2 * p.delta) > 4 ? (1 + 2 * p.delta) : 4;
-  constexpr int LDW_S = ITER * 32 + 4;
-  const int W_D = p.d;
   double* Ws = fused_smem;
-  double* xs = fused_smem + (size_t)p.d * LDW_S + (size_t)wib * (ITER * 32);
-  const double* xs_all = fused_smem + (size_t)p.d * LDW_S;
-  double* zpart = fused_smem + (size_t)p.d * LDW_S + (size_t)n_wib * (ITER * 32);                      // [2][8][ITER * 32]
-  double* stage = zpart + (size_t)16 * (ITER * 32) + (size_t)wib * stage_rows * p.ldx;
+  double* xs = fused_smem + (size_t)pl.T * 32 + (size_t)wib * pl.xld;
+  const double* xs_all = fused_smem + (size_t)pl.T * 32;
+  double* zpart = fused_smem + (size_t)pl.T * 32 + (size_t)8 * pl.xld;
+  double* stage = zpart + (size_t)16 * pl.zld + (size_t)wib * stage_rows * p.ldx;
   unsigned sphase = 0;
   if (lane == 0) { mbar_init(&sbars[wib], 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
-  // W (d * ldw doubles, ldw even: a multiple of 16 bytes) is staged once per CTA by bulk TMA copies of at most 32 KB; it
-  // lands while the warps compute their first proposal (first measured version read W through L1/L2 inside the k loop:
-  // every warp of the SM missed on the same row at the same time, 33 us per generation against 23 us unfused)
-  const uint32_t w_bytes = (uint32_t)p.d * (uint32_t)td.ldw * 8u;
+  // the fragment-ordered W (pl.T blocks of 256 bytes) is staged once per CTA by bulk TMA copies of at most 32 KB; it lands
+  // while the warps compute their first proposal
+  const uint32_t w_bytes = (uint32_t)pl.T * 256u;
   if (threadIdx.x == 0) {
     mbar_init(&wbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const int d = p.d, ldx = p.ldx;
+  (void)d; (void)ldx;
   unsigned errbits = 0;
   if (threadIdx.x <= 2 * HB_MAX_NCR) s_cnt[threadIdx.x] = 0ull;
+  fused_work_init(&s_work, pl);
   __syncthreads();
-  // W: d rows of ldw doubles in global memory -> rows of LDW_S doubles in shared memory, one bulk copy per row
-  if (threadIdx.x == 0) mbar_expect_tx(&wbar, w_bytes);
-  __syncthreads();
-  for (int k = threadIdx.x; k < W_D; k += blockDim.x)
-    tma_load_1d(Ws + (size_t)k * LDW_S, td.W + (size_t)k * td.ldw, (uint32_t)td.ldw * 8u, &wbar);
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&wbar, w_bytes);
+    for (uint32_t off = 0; off < w_bytes; off += 32768u) {
+      const uint32_t nbytes = (w_bytes - off) < 32768u ? (w_bytes - off) : 32768u;
+      tma_load_1d(reinterpret_cast<char*>(Ws) + off, reinterpret_cast<const char*>(td.Wblk) + off, nbytes, &wbar);
+    }
+  }
 
   bool w_ready = false;
   for (long long base0 = (long long)blockIdx.x * n_wib; base0 < p.n_local; base0 += n_warps) {   // one round = this CTA's next 8 chains
@@ -673,7 +722,7 @@ __global__ void __launch_bounds__(256) hb_fused_small_kernel(const hb_k1_params 
     k1_headv hv;
     if (has_chain) k1_chain_head<32, TAPE>(p, p.gen, p.tape_g, base, lane, hv, errbits);
     fused_chain_step<ITER, TAPE>(p, q, td, fused_gen_of(q), Ws, xs, &wbar, w_ready, hv, lane, s_cnt, errbits, stage, &sbars[wib], sphase,
-                                 xs_all, zpart, has_chain);
+                                 xs_all, zpart, has_chain, pl, &s_work);
   }
   __syncthreads();
   if (threadIdx.x <= 2 * HB_MAX_NCR) {
@@ -696,8 +745,11 @@ cudaError_t launch_fused(const hb_k1_params& p, const hb_k3_params& q, const hb_
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   const int stage_rows = (1 + 2 * p.delta) > 4 ? (1 + 2 * p.delta) : 4;
-  const size_t smem = ((size_t)p.d * (ITER * 32 + 4) + (size_t)warps * ITER * 32 + (size_t)16 * ITER * 32 + (size_t)warps * stage_rows * p.ldx) * sizeof(double);
-  if (smem > 220 * 1024 || (td.ldw & 1) || td.ldw > ITER * 32 + 4 || (p.ldx & 1)) return cudaErrorInvalidValue;
+  if (td.KB <= 0 || !td.Wblk || 4 * td.KB < p.d) return cudaErrorInvalidValue;
+  fused_plan pl;
+  if (!fused_make_plan(td.KB, warps, &pl)) return cudaErrorInvalidValue;
+  const size_t smem = fused_smem_doubles(pl, stage_rows, p.ldx) * sizeof(double);
+  if (smem > 220 * 1024 || pl.xld > ITER * 32 + 4 || (p.ldx & 1)) return cudaErrorInvalidValue;
   static bool attr_set[2] = {false, false};
   if (!attr_set[tape]) {
     cudaError_t e = tape ? cudaFuncSetAttribute(hb_fused_small_kernel<ITER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)
@@ -705,8 +757,8 @@ cudaError_t launch_fused(const hb_k1_params& p, const hb_k3_params& q, const hb_
     if (e != cudaSuccess) return e;
     attr_set[tape] = true;
   }
-  if (tape) hb_fused_small_kernel<ITER, true><<<(unsigned)blocks, threads, smem, st>>>(p, q, td);
-  else hb_fused_small_kernel<ITER, false><<<(unsigned)blocks, threads, smem, st>>>(p, q, td);
+  if (tape) hb_fused_small_kernel<ITER, true><<<(unsigned)blocks, threads, smem, st>>>(p, q, td, pl);
+  else hb_fused_small_kernel<ITER, false><<<(unsigned)blocks, threads, smem, st>>>(p, q, td, pl);
   return cudaGetLastError();
 }
 
@@ -720,46 +772,60 @@ cudaError_t launch_fused(const hb_k1_params& p, const hb_k3_params& q, const hb_
 // the others.  The per-chain step is fused_chain_step, i.e. draw for draw and operation for operation the
 // one-launch-per-generation kernel; the population is read with L2-coherent loads (other CTAs rewrite it between barriers).
 // ------------------------------------------------------------------------------------------------------------------
-template <int ITER, bool TAPE>
-__global__ void __launch_bounds__(256) hb_persist_small_kernel(const hb_k1_params p0, const hb_k3_params q0, const hb_fused_tdist td,
-                                                               const hb_persist_params pp) {
-  extern __shared__ __align__(16) double fused_smem[];               // W [d][ldw] | xs [warps][ITER * 32]
+template <int ITER, bool TAPE, int NT>
+__global__ void __launch_bounds__(NT) hb_persist_small_kernel(const hb_k1_params p0, const hb_k3_params q0, const hb_fused_tdist td,
+                                                              const hb_persist_params pp, const fused_plan pl) {
+  // NT = 256: eight warps, one per chain (warps beyond the eighth would own no chain and only join the cooperative product)
+  extern __shared__ __align__(16) double fused_smem[];               // W blocks | proposal tile [8][xld] | statistics rows [16][zld] | row stages
   __shared__ unsigned long long s_cnt[2 * HB_MAX_NCR + 1];
   __shared__ __align__(8) uint64_t wbar;
   __shared__ __align__(8) uint64_t sbars[8];
   __shared__ int s_ids[8];
+  __shared__ fused_work s_work;
   const int lane = threadIdx.x & 31;
-  const int n_wib = blockDim.x >> 5, wib = threadIdx.x >> 5;
+  constexpr int n_wib = 8;                                           // chain warps
+  const int wib = threadIdx.x >> 5;
+  const bool chain_warp = wib < n_wib;
   const int stage_rows = (1 + 2 * p0.delta) > 4 ? (1 + 2 * p0.delta) : 4;
-  constexpr int LDW_S = ITER * 32 + 4;
-  const int W_D = p0.d;
   double* Ws = fused_smem;
-  double* xs = fused_smem + (size_t)p0.d * LDW_S + (size_t)wib * (ITER * 32);
-  const double* xs_all = fused_smem + (size_t)p0.d * LDW_S;
-  double* zpart = fused_smem + (size_t)p0.d * LDW_S + (size_t)n_wib * (ITER * 32);                     // [2][8][ITER * 32]
-  double* stage = zpart + (size_t)16 * (ITER * 32) + (size_t)wib * stage_rows * p0.ldx;
+  double* xs = chain_warp ? fused_smem + (size_t)pl.T * 32 + (size_t)wib * pl.xld : nullptr;
+  const double* xs_all = fused_smem + (size_t)pl.T * 32;
+  double* zpart = fused_smem + (size_t)pl.T * 32 + (size_t)8 * pl.xld;
+  double* stage = zpart + (size_t)16 * pl.zld + (size_t)(chain_warp ? wib : 0) * stage_rows * p0.ldx;
   unsigned sphase = 0;
-  if (lane == 0) { mbar_init(&sbars[wib], 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
-  const uint32_t w_bytes = (uint32_t)p0.d * (uint32_t)td.ldw * 8u;
+  if (lane == 0 && chain_warp) { mbar_init(&sbars[wib], 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+  const uint32_t w_bytes = (uint32_t)pl.T * 256u;
   if (threadIdx.x == 0) {
     mbar_init(&wbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (threadIdx.x <= 2 * HB_MAX_NCR) s_cnt[threadIdx.x] = 0ull;
+  fused_work_init(&s_work, pl);
   __syncthreads();
-  // W: d rows of ldw doubles in global memory -> rows of LDW_S doubles in shared memory, one bulk copy per row
-  if (threadIdx.x == 0) mbar_expect_tx(&wbar, w_bytes);
-  __syncthreads();
-  for (int k = threadIdx.x; k < W_D; k += blockDim.x)
-    tma_load_1d(Ws + (size_t)k * LDW_S, td.W + (size_t)k * td.ldw, (uint32_t)td.ldw * 8u, &wbar);
-  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // the fragment-ordered W: bulk TMA copies of at most 32 KB, once for the whole run
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&wbar, w_bytes);
+    for (uint32_t off = 0; off < w_bytes; off += 32768u) {
+      const uint32_t nbytes = (w_bytes - off) < 32768u ? (w_bytes - off) : 32768u;
+      tma_load_1d(reinterpret_cast<char*>(Ws) + off, reinterpret_cast<const char*>(td.Wblk) + off, nbytes, &wbar);
+    }
+  }
+  const long long warp_id = (long long)blockIdx.x * n_wib + wib;     // the chain of a chain warp
   const long long nl = p0.n_local;
-  const bool active = warp_id < nl;      // one chain per warp (the launcher sizes the grid that way)
+  const bool active = chain_warp && warp_id < nl;      // one chain per chain warp (the launcher sizes the grid that way)
   unsigned errbits = 0;
   bool w_ready = false;
   long long ind_out = pp.ind_out0, pending = pp.pending0;
   k1_headv hv;
   if (active) k1_chain_head<32, TAPE>(p0, (uint32_t)pp.i0, pp.i0 - 2, warp_id, lane, hv, errbits);
+  // log of the Metropolis uniform of generation i (R/internals.R:241): like the head, it does not depend on the population
+  const long long acc_gch = q0.gchain0 + q0.chain0 + warp_id * q0.stride;
+  auto draw_logu = [&](uint32_t gen) -> double {
+    const hb_phx ph(q0.seed, (uint64_t)acc_gch, gen);
+    return log(hb_u53(hb_pair64(ph.slot(HB_SLOT_ACCEPT), 0)));
+  };
+  double logu = 0.0;
+  if (!TAPE && active && lane == 0) logu = draw_logu((uint32_t)pp.i0);
   for (long long i = pp.i0; i < pp.i1; ++i) {
     const bool store = ((double)i > pp.burnin * (double)pp.t) && (i % pp.thin == 0);   // R/dream_parallel.R:263, :386
     if (store) ind_out++;
@@ -774,11 +840,12 @@ __global__ void __launch_bounds__(256) hb_persist_small_kernel(const hb_k1_param
       fg.accept_rec = pp.accept_rec ? pp.accept_rec + (size_t)(i - 2) * nl : nullptr;
       fg.u_accept = pp.u_accept ? pp.u_accept + (size_t)(i - 2) * pp.tape_nct : nullptr;
     }
-    long long tm[8];
+    long long tm[10];
     const bool tr = pp.trace && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && i >= pp.i0 + 2 && i < pp.i0 + 6;
     if (tr) tm[4] = clock64();
-    fused_chain_step<ITER, TAPE, true>(p0, q0, td, fg, Ws, xs, &wbar, w_ready, hv, lane, s_cnt, errbits, stage, &sbars[wib], sphase,
-                                       xs_all, zpart, active, tr ? tm : nullptr, pp.adapt ? q0.shift : nullptr, s_ids);
+    fused_chain_step<ITER, TAPE, true>(p0, q0, td, fg, Ws, xs, &wbar, w_ready, hv, lane, s_cnt, errbits, stage, &sbars[wib & 7], sphase,
+                                       xs_all, zpart, active, pl, &s_work, tr ? tm : nullptr, pp.adapt ? q0.shift : nullptr, s_ids,
+                                       TAPE ? nullptr : &logu);
     if (tr) tm[5] = clock64();
     __syncthreads();
     if (tr) tm[6] = clock64();
@@ -790,13 +857,13 @@ __global__ void __launch_bounds__(256) hb_persist_small_kernel(const hb_k1_param
       for (int e = threadIdx.x; e < E; e += blockDim.x) {
         double sum = 0.0;
         if (e < 2 * p0.d) {
-          const double* col = zpart + (size_t)(e < p0.d ? 0 : 8) * (ITER * 32) + (e < p0.d ? e : e - p0.d);
+          const double* col = zpart + (size_t)(e < p0.d ? 0 : 8) * pl.zld + (e < p0.d ? e : e - p0.d);
 #pragma unroll
-          for (int w = 0; w < 8; ++w) sum += col[(size_t)w * (ITER * 32)];
+          for (int w = 0; w < 8; ++w) sum += col[(size_t)w * pl.zld];
         } else {
           const int qq = (e - 2 * p0.d) / p0.d, k = (e - 2 * p0.d) - qq * p0.d;
 #pragma unroll
-          for (int w = 0; w < 8; ++w) sum += (s_ids[w] == qq) ? xs_all[(size_t)w * (ITER * 32) + k] : 0.0;
+          for (int w = 0; w < 8; ++w) sum += (s_ids[w] == qq) ? xs_all[(size_t)w * pl.xld + k] : 0.0;
         }
         pp.partials[((size_t)(pp.slot0 + (int)(i - pp.i0)) * gridDim.x + blockIdx.x) * E + e] = sum;
       }
@@ -818,7 +885,10 @@ __global__ void __launch_bounds__(256) hb_persist_small_kernel(const hb_k1_param
     // the others (they must not add the next generation's counts before the fold has zeroed the counters).
     const unsigned round = (unsigned)(i - pp.i0 + 1);
     if (threadIdx.x == 0) { __threadfence(); atomicAdd(&pp.bar[0], 1u); }
-    if (active && i + 1 < pp.i1) k1_chain_head<32, TAPE>(p0, (uint32_t)(i + 1), i - 1, warp_id, lane, hv, errbits);
+    if (active && i + 1 < pp.i1) {
+      k1_chain_head<32, TAPE>(p0, (uint32_t)(i + 1), i - 1, warp_id, lane, hv, errbits);
+      if (!TAPE && lane == 0) logu = draw_logu((uint32_t)(i + 1));
+    }
     if (threadIdx.x == 0) {
       const unsigned target = gridDim.x * round;
       // adaptation period: nothing to fold here -- the statistics of the interval's generations are parked in slots and the
@@ -841,6 +911,7 @@ __global__ void __launch_bounds__(256) hb_persist_small_kernel(const hb_k1_param
     if (threadIdx.x == 0) __threadfence();
     if (upd) pending = 0;
     __syncthreads();
+    if (tr) printf("[persist trace] product: own segment %lld | wait for the others %lld | fold %lld\n", tm[8] - tm[2], tm[9] - tm[8], tm[7] - tm[9]);
     if (tr) printf("[persist trace] gen %lld cta %d: setup %lld | sweep %lld | xp %lld | product %lld + log1p %lld | accept+store %lld | block sync %lld | barrier+next head %lld cycles\n",
                    i, (int)blockIdx.x, tm[0] - tm[4], tm[1] - tm[0], tm[2] - tm[1], tm[7] - tm[2], tm[3] - tm[7], tm[5] - tm[3], tm[6] - tm[5], clock64() - tm[6]);
   }
@@ -850,19 +921,25 @@ __global__ void __launch_bounds__(256) hb_persist_small_kernel(const hb_k1_param
 template <int ITER>
 cudaError_t launch_persist(const hb_k1_params& p, const hb_k3_params& q, const hb_fused_tdist& td, const hb_persist_params& pp,
                            bool tape, int sm_count, cudaStream_t st) {
-  const int threads = 256, warps = threads / 32;
+  const int warps = 8;                                                // chain warps per CTA
+  // (eight more helper warps that own no chain and only join the product phase were measured SLOWER: 512 threads cap the
+  // kernel at 128 registers -- spills in the proposal sweep -- and a product warp's 11 dependent DMMAs take as long as 23)
+  const int threads = 256;
   const long long blocks = (p.n_local + warps - 1) / warps;
   const int stage_rows = (1 + 2 * p.delta) > 4 ? (1 + 2 * p.delta) : 4;
-  const size_t smem = ((size_t)p.d * (ITER * 32 + 4) + (size_t)warps * ITER * 32 + (size_t)16 * ITER * 32 + (size_t)warps * stage_rows * p.ldx) * sizeof(double);
-  if (smem > 220 * 1024 || (td.ldw & 1) || td.ldw > ITER * 32 + 4 || (p.ldx & 1)) return cudaErrorInvalidValue;
-  const void* fn = tape ? (const void*)hb_persist_small_kernel<ITER, true> : (const void*)hb_persist_small_kernel<ITER, false>;
+  if (td.KB <= 0 || !td.Wblk || 4 * td.KB < p.d) return cudaErrorInvalidValue;
+  fused_plan pl;
+  if (!fused_make_plan(td.KB, threads / 32, &pl)) return cudaErrorInvalidValue;
+  const size_t smem = fused_smem_doubles(pl, stage_rows, p.ldx) * sizeof(double);
+  if (smem > 220 * 1024 || pl.xld > ITER * 32 + 4 || (p.ldx & 1)) return cudaErrorInvalidValue;
+  const void* fn = tape ? (const void*)hb_persist_small_kernel<ITER, true, 256> : (const void*)hb_persist_small_kernel<ITER, false, 256>;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem);
   if (e != cudaSuccess) return e;
   if (blocks > (long long)per_sm * sm_count) return cudaErrorCooperativeLaunchTooLarge;   // the grid barrier needs every CTA resident
-  void* args[] = {(void*)&p, (void*)&q, (void*)&td, (void*)&pp};
+  void* args[] = {(void*)&p, (void*)&q, (void*)&td, (void*)&pp, (void*)&pl};
   return cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(threads), args, smem, st);
 }
 

@@ -62,7 +62,11 @@ cudaError_t hb_launch_k1(const hb_k1_params& p, bool tape_mode, int sm_count, cu
 
 struct hb_k3_params;
 // ---- fused generation for small populations (hb_k1_propose.cu): K1 + t-distribution density + K3 in one launch ----
-struct hb_fused_tdist { const double* W; int ldw; int lik; double konst, df; };   // W = chol(C)^-1, dense upper triangle [d][ldw], zeros below
+struct hb_fused_tdist {
+  const double* W; int ldw;      // W = chol(C)^-1, dense upper triangle [d][ldw], zeros below
+  int lik; double konst, df;
+  const double* Wblk; int KB;    // the same W in block-triangular DMMA fragment order (hb_targets.cu), KB k-blocks of 4 (0: d > 128)
+};
 bool hb_fused_small_eligible(long long n_local, int d, int sm_count);
 cudaError_t hb_launch_fused_small(const hb_k1_params& p, const hb_k3_params& q, const hb_fused_tdist& td, bool tape_mode,
                                   int sm_count, cudaStream_t st);

@@ -71,12 +71,6 @@ void mixture_destroy(void* ctx) { delete (mixture_ctx*)ctx; }
 void mixture_work(void*, int, double* flops, double* bytes) { *flops = 40; *bytes = 16; }
 
 // =========================================== t_distribution ===============================================
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
-}
-
 // KB k-blocks of 4, NB = ceil(KB/2) n-blocks of 8.  One warp owns 8 chains per iteration:
 //   A (8x4, row): lane holds X[row = lane>>2][k = 4*kb + (lane&3)]   -- all KB fragments loaded up front (MLP = KB)
 //   B (4x8, col): lane holds W[k = 4*kb + (lane&3)][n = 8*nb + (lane>>2)] from shared memory
@@ -87,13 +81,6 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // `lane` of a block is the B fragment of that lane -- a warp's B load is one contiguous, conflict-free 256-byte line, and
 // the whole operand is 46 KB instead of 91 KB at d = 100, which is what lets three CTAs (24 warps) share an SM: the
 // kernel is bound by the latency of the 25 global loads that open every tile, hidden only by other warps.
-__host__ __device__ constexpr int tdist_blk_base(int nb, int KB) {   // blocks of the n-blocks before nb
-  int s = 0;
-  for (int j = 0; j < nb; ++j) s += (2 * j + 2 < KB) ? 2 * j + 2 : KB;
-  return s;
-}
-__host__ __device__ constexpr int tdist_n_blocks(int KB) { return tdist_blk_base((KB + 1) / 2, KB); }
-
 template <int KB>
 __global__ void __launch_bounds__(256, (KB > 25 ? 2 : 3)) hb_tdist_dmma_kernel(const double* __restrict__ X, long long n, int d, int ldx,
                                                             const double* __restrict__ Wblk, double konst,
@@ -337,6 +324,7 @@ bool hb_tdist_fused_info(const hb_target_vtable* vt, void* ctx, hb_fused_tdist* 
   const auto* c = (const tdist_ctx*)ctx;
   if (c->force_fma) return false;                       // HB_TDIST_FORCE_FMA=1 is a cross-check of the stand-alone kernels
   out->W = c->W_dev; out->ldw = c->ldw; out->lik = c->lik; out->konst = c->konst; out->df = c->df;
+  out->Wblk = c->Wblk_dev; out->KB = c->KB;
   return true;
 }
 
