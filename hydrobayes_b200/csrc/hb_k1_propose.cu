@@ -169,6 +169,65 @@ __device__ __forceinline__ void k1_chain_head(const hb_k1_params& p, uint32_t ge
   hv.jl = jl; hv.gl = gl; hv.rbase = rbase; hv.rix = rix; hv.gch = gch;
 }
 
+// The population-independent part of the parallel direction update (R/internals.R:173-192): the crossover subspace
+// A = {k : zt_k < CR[id]} (or which.min), d*, gamma, and the Philox words behind lambda / zeta.  Split from the sweep so that
+// the persistent kernel can run it for generation i + 1 while the grid barrier of generation i is in flight.
+template <int ITER>
+struct k1_prev {
+  unsigned selmask[ITER];
+  uint32_t wl[ITER], wz[ITER];     // slot map v2: lo word >> 16 -> lambda; hi word -> zeta
+  int d_star, kmin;
+  double gam;
+};
+template <int G, int ITER, bool TAPE>
+__device__ __forceinline__ void k1_chain_pre(const hb_k1_params& p, uint32_t gen, const k1_headv& hv, int lane, k1_prev<ITER>& pv) {
+  const int lg = lane & (G - 1);
+  const unsigned gmask = hb_group_mask<G>(lane);
+  const int d = p.d, nCR = p.nCR;
+  const int D = hv.D, id = hv.id;
+  const long long rix = hv.rix;
+  const hb_phx ph(p.seed, (uint64_t)hv.gch, gen);
+  const double CRv = (double)(id + 1) / (double)nCR;               // CR <- (1:nCR)/nCR
+  double ztv[ITER];
+  int d_star = 0;
+#pragma unroll
+  for (int m = 0; m < ITER; ++m) {
+    const int k = m * G + lg;
+    ztv[m] = 2.0; pv.wl[m] = 0; pv.wz[m] = 0;
+    if (k < d) {
+      if (TAPE) ztv[m] = p.tape.zt[rix * d + k];                   // :175
+      else {
+        const uint4 w = ph.slot(HB_SLOT_DIM0 + (uint32_t)(k >> 1));
+        const uint32_t lo = (k & 1) ? w.z : w.x;
+        ztv[m] = hb_rng_u16(lo); pv.wl[m] = lo >> 16; pv.wz[m] = (k & 1) ? w.w : w.y;
+      }
+    }
+    pv.selmask[m] = hb_group_ballot<G>(k < d && ztv[m] < CRv, lane, gmask); // A <- which(zt < CR[id])  :177
+    d_star += __popc(pv.selmask[m]);
+  }
+  int kmin = -1;
+  if (d_star == 0) {                             // :181-184  A <- which.min(zt)
+    double bv = 3.0; int bk = 0x7fffffff;
+#pragma unroll
+    for (int m = 0; m < ITER; ++m) {
+      const int k = m * G + lg;
+      if (k < d && ztv[m] < bv) { bv = ztv[m]; bk = k; }
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(gmask, bv, o);
+      const int ok = __shfl_xor_sync(gmask, bk, o);
+      if (ov < bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
+    }
+    kmin = bk; d_star = 1;
+  }
+  // :190  2.38/sqrt(2 D d*): the host-built table when there is one (same IEEE sqrt and division: bit-identical), which
+  // spares the warp ~40 fp64 instructions
+  const double gamma_d = p.gamma_tab ? __ldg(p.gamma_tab + (D - 1) * d + (d_star - 1)) : 2.38 / sqrt(2.0 * (double)D * (double)d_star);
+  pv.gam = hv.g_is_one ? 1.0 : gamma_d;                            // :192
+  pv.d_star = d_star; pv.kmin = kmin;
+}
+
 // The sweep of a proposal (R/internals.R:150-200): partner rows, crossover subspace, dx.
 // STAGE (one chain per warp, G == 32): the rows the chain needs -- its own state and the 2D partner rows -- are fetched into
 // a per-warp shared-memory stage by 1-D bulk TMA copies first, the Philox work of the crossover pass runs while they are in
@@ -180,7 +239,7 @@ template <int G, int ITER, bool TAPE, bool CG = false, bool STAGE = false>
 __device__ __forceinline__ void k1_chain_body(const hb_k1_params& p, uint32_t gen, const k1_headv& hv, int lane, double (&xk)[ITER],
                                               double (&dxk)[ITER], unsigned& errbits,
                                               double* stage = nullptr, uint64_t* sbar = nullptr, unsigned* sphase = nullptr,
-                                              const double* Xcur = nullptr) {
+                                              const double* Xcur = nullptr, const k1_prev<ITER>* pre = nullptr) {
   static_assert(!STAGE || G == 32, "row staging is written for one chain per warp");
   const int lg = lane & (G - 1);
   const unsigned gmask = hb_group_mask<G>(lane);
@@ -273,64 +332,29 @@ __device__ __forceinline__ void k1_chain_body(const hb_k1_params& p, uint32_t ge
     }
   } else {
     // ---------------- parallel direction update, R/internals.R:166-200 ----------------
-    const double CRv = (double)(id + 1) / (double)nCR;               // CR <- (1:nCR)/nCR
-    double ztv[ITER];
-    uint32_t wl[ITER], wz[ITER];     // slot map v2: one Philox call per two dimensions (lo word: zt | lambda; hi: zeta)
-    unsigned selmask[ITER];
-    int d_star = 0;
-#pragma unroll
-    for (int m = 0; m < ITER; ++m) {
-      const int k = m * G + lg;
-      ztv[m] = 2.0; wl[m] = 0; wz[m] = 0;
-      if (k < d) {
-        if (TAPE) ztv[m] = p.tape.zt[rix * d + k];                   // :175
-        else {
-          const uint4 w = ph.slot(HB_SLOT_DIM0 + (uint32_t)(k >> 1));
-          const uint32_t lo = (k & 1) ? w.z : w.x;
-          ztv[m] = hb_rng_u16(lo); wl[m] = lo >> 16; wz[m] = (k & 1) ? w.w : w.y;
-        }
-      }
-      selmask[m] = hb_group_ballot<G>(k < d && ztv[m] < CRv, lane, gmask); // A <- which(zt < CR[id])  :177
-      d_star += __popc(selmask[m]);
-    }
-    int kmin = -1;
-    if (d_star == 0) {                             // :181-184  A <- which.min(zt)
-      double bv = 3.0; int bk = 0x7fffffff;
-#pragma unroll
-      for (int m = 0; m < ITER; ++m) {
-        const int k = m * G + lg;
-        if (k < d && ztv[m] < bv) { bv = ztv[m]; bk = k; }
-      }
-#pragma unroll
-      for (int o = G / 2; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(gmask, bv, o);
-        const int ok = __shfl_xor_sync(gmask, bk, o);
-        if (ov < bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
-      }
-      kmin = bk; d_star = 1;
-    }
-    // :190  2.38/sqrt(2 D d*): the host-built table when there is one (same IEEE sqrt and division: bit-identical), which
-    // spares the warp ~40 fp64 instructions
-    const double gamma_d = p.gamma_tab ? __ldg(p.gamma_tab + (D - 1) * d + (d_star - 1)) : 2.38 / sqrt(2.0 * (double)D * (double)d_star);
-    const double gam = g_is_one ? 1.0 : gamma_d;                            // :192
+    k1_prev<ITER> pv_local;
+    if (!pre) k1_chain_pre<G, ITER, TAPE>(p, gen, hv, lane, pv_local);
+    const k1_prev<ITER>& pv = pre ? *pre : pv_local;
+    const int kmin = pv.kmin;
+    const double gam = pv.gam;
     rows_ready();
     int rank_base = 0;
 #pragma unroll
     for (int m = 0; m < ITER; ++m) {
       const int k = m * G + lg;
-      const bool sel = (kmin >= 0) ? (k == kmin) : ((selmask[m] >> lg) & 1u);
+      const bool sel = (kmin >= 0) ? (k == kmin) : ((pv.selmask[m] >> lg) & 1u);
       xk[m] = 0; dxk[m] = 0;
       if (k < d) {
         xk[m] = k1_ld<CG && !STAGE>(xrow + k);
         if (sel) {
           double lambda, zeta;
           if (TAPE) {
-            const int rank = (kmin >= 0) ? 0 : rank_base + __popc(selmask[m] & ((1u << lg) - 1u));
+            const int rank = (kmin >= 0) ? 0 : rank_base + __popc(pv.selmask[m] & ((1u << lg) - 1u));
             lambda = p.tape.lambda[rix * d + rank];                  // :188 (by rank within A)
             zeta = p.tape.zeta[rix * d + rank];                      // :194
           } else {
-            lambda = hb_rng_lambda16(wl[m], p.c_val);
-            zeta = hb_zeta32(wz[m], p.c_star);
+            lambda = hb_rng_lambda16(pv.wl[m], p.c_val);
+            zeta = hb_zeta32(pv.wz[m], p.c_star);
           }
           // jump_diff <- colSums(r1[,A] - r2[,A])   :196
           double s = 0.0, comp = 0.0;
@@ -350,7 +374,7 @@ __device__ __forceinline__ void k1_chain_body(const hb_k1_params& p, uint32_t ge
           dxk[m] = __dmul_rn(v, p.beta0);
         }
       }
-      rank_base += __popc(selmask[m]);
+      rank_base += __popc(pv.selmask[m]);
     }
   }
 
@@ -514,7 +538,8 @@ __device__ __forceinline__ void fused_chain_step(const hb_k1_params& p, const hb
                                                  double* stage, uint64_t* sbar, unsigned& sphase,
                                                  const double* __restrict__ xs_all, double* __restrict__ zpart, bool has_chain,
                                                  const fused_plan& pl, fused_work* wk, long long* tm = nullptr,
-                                                 const double* shift_g = nullptr, int* s_ids = nullptr, const double* logu_pre = nullptr) {
+                                                 const double* shift_g = nullptr, int* s_ids = nullptr, const double* logu_pre = nullptr,
+                                                 const k1_prev<ITER>* sweep_pre = nullptr) {
   // BLOCK-COLLECTIVE: every warp of the CTA calls this once per round (has_chain = false for a warp without a chain); the
   // log-density of the CTA's eight proposals is computed cooperatively between two __syncthreads().
   constexpr unsigned FULL = 0xffffffffu;
@@ -528,7 +553,7 @@ __device__ __forceinline__ void fused_chain_step(const hb_k1_params& p, const hb
     if (tm) tm[0] = clock64();
 #pragma unroll
     for (int m = 0; m < ITER; ++m) { xk[m] = 0.0; dxk[m] = 0.0; }
-    if (has_chain) k1_chain_body<32, ITER, TAPE, CG, true>(p, fg.gen, hv, lane, xk, dxk, errbits, stage, sbar, &sphase, fg.Xin);
+    if (has_chain) k1_chain_body<32, ITER, TAPE, CG, true>(p, fg.gen, hv, lane, xk, dxk, errbits, stage, sbar, &sphase, fg.Xin, sweep_pre);
     if (tm) tm[1] = clock64();
     double lp_part = 0.0;
 #pragma unroll
@@ -826,6 +851,9 @@ __global__ void __launch_bounds__(NT) hb_persist_small_kernel(const hb_k1_params
   };
   double logu = 0.0;
   if (!TAPE && active && lane == 0) logu = draw_logu((uint32_t)pp.i0);
+  // ... and so is the crossover subspace of the proposal (k1_chain_pre): d*, gamma and the words behind lambda / zeta
+  k1_prev<ITER> pv;
+  if (active) k1_chain_pre<32, ITER, TAPE>(p0, (uint32_t)pp.i0, hv, lane, pv);
   for (long long i = pp.i0; i < pp.i1; ++i) {
     const bool store = ((double)i > pp.burnin * (double)pp.t) && (i % pp.thin == 0);   // R/dream_parallel.R:263, :386
     if (store) ind_out++;
@@ -845,7 +873,7 @@ __global__ void __launch_bounds__(NT) hb_persist_small_kernel(const hb_k1_params
     if (tr) tm[4] = clock64();
     fused_chain_step<ITER, TAPE, true>(p0, q0, td, fg, Ws, xs, &wbar, w_ready, hv, lane, s_cnt, errbits, stage, &sbars[wib & 7], sphase,
                                        xs_all, zpart, active, pl, &s_work, tr ? tm : nullptr, pp.adapt ? q0.shift : nullptr, s_ids,
-                                       TAPE ? nullptr : &logu);
+                                       TAPE ? nullptr : &logu, &pv);
     if (tr) tm[5] = clock64();
     __syncthreads();
     if (tr) tm[6] = clock64();
@@ -887,6 +915,7 @@ __global__ void __launch_bounds__(NT) hb_persist_small_kernel(const hb_k1_params
     if (threadIdx.x == 0) { __threadfence(); atomicAdd(&pp.bar[0], 1u); }
     if (active && i + 1 < pp.i1) {
       k1_chain_head<32, TAPE>(p0, (uint32_t)(i + 1), i - 1, warp_id, lane, hv, errbits);
+      k1_chain_pre<32, ITER, TAPE>(p0, (uint32_t)(i + 1), hv, lane, pv);
       if (!TAPE && lane == 0) logu = draw_logu((uint32_t)(i + 1));
     }
     if (threadIdx.x == 0) {
