@@ -645,6 +645,21 @@ bool fused_available(hb_handle* h) {
   return h->fused_state == 1 && !h->profile && hb_fused_small_eligible(h->n_local, h->d, h->sm_count);
 }
 
+// The built-in t_distribution target in its structured evaluation: hb_k1_pair_kernel (large populations, native draws) can
+// fold the log-density into the proposal sweep.  HB_K1_DENSITY=0 keeps the plugin launch (the cross-check of the tests).
+bool k1_density_available(hb_handle* h) {
+  const hb_config& c = h->cfg;
+  if (h->k1_td_state == 0) {
+    h->k1_td_state = -1;
+    const char* e = getenv("HB_K1_DENSITY");
+    const bool want = e ? (e[0] == '1') : true;
+    if (want && c.sweep == HB_SWEEP_SYNCHRONOUS && !h->modeb && c.mt <= 1 && c.n_runs <= 1 && c.rng_mode != HB_RNG_TAPE &&
+        hb_tdist_fused_info(h->vt, h->tctx, &h->k1_td))
+      h->k1_td_state = 1;
+  }
+  return h->k1_td_state == 1;
+}
+
 // Persistent generation loop (hb_persist_small_kernel): generations [i0, i1) of a small population, all behind the adaptation
 // period, in ONE cooperative launch.  Returns HB_OK with *taken = false when the handle cannot use it (the caller then runs
 // the generations one by one).
@@ -770,17 +785,22 @@ int piece_kernels(hb_handle* h, long long i, int piece, long long off, long long
                   cudaEvent_t ev_after_k1 = nullptr) {
   const hb_config& c = h->cfg;
   const int d = h->d, ldx = h->ldx;
+  bool density_done = false;
   {  // K1
     hb_k1_params p = hb_make_k1(h, i, h->chain0 + off, 1, n);
     p.XP += off * ldx; p.id_out += off; p.lp_xp += off;
     p.reserve_ctas = h->reserve_ctas;
+    if (k1_density_available(h)) {   // built-in t_distribution, structured evaluation: the large-population proposal kernel writes ll too
+      p.td_rs = h->k1_td.rs; p.td_konst = h->k1_td.konst; p.td_df = h->k1_td.df; p.td_lik = h->k1_td.lik;
+      p.td_ll = h->ll_raw + off; p.td_fx = h->fx_xp + off;
+    }
     prof_scope ps(h, "K1");
-    CK(hb_launch_k1(p, tape_mode, h->sm_count, h->stream));
+    CK(hb_launch_k1(p, tape_mode, h->sm_count, h->stream, &density_done));
     ps.done();
     if (ev_after_k1) CK(cudaEventRecord(ev_after_k1, h->stream));
     if (int rc = hb_prior_after_k1(h, n, off)) return rc;
   }
-  {  // K2: the target plugin
+  if (!density_done) {  // K2: the target plugin
     prof_scope ps(h, "K2");
     if (int rc = hb_target_launch(h, h->XP + off * ldx, n, h->chain0 + off, 1, off)) return fail(h, rc, "target launch failed");
     ps.done();

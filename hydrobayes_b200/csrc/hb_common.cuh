@@ -260,4 +260,19 @@ __host__ __device__ constexpr int tdist_n_blocks(int KB) { return tdist_blk_base
 
 
 __device__ __forceinline__ double hb_warp_sum(double v) { return hb_group_sum<32>(v); }
+// two warp sums for the price of one: after the first exchange the lower half of the warp carries a, the upper half b;
+// on return every lane holds both totals.  Fixed order (deterministic).
+__device__ __forceinline__ void hb_warp_sum2(double& a, double& b, int lane) {
+  const bool up = lane >= 16;
+  const double give = up ? a : b;
+  double v = (up ? b : a) + __shfl_xor_sync(0xffffffffu, give, 16);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  a = __shfl_sync(0xffffffffu, v, 0);
+  b = __shfl_sync(0xffffffffu, v, 16);
+}
+// x' C^-1 x of the reference's t_distribution from s1 = sum u_i, s2 = sum u_i^2, u_i = x_i / sqrt(i)  (hb_targets.cu)
+__device__ __forceinline__ double hb_tdist_rss(double s1, double s2, int d) {
+  return 2.0 * fma(-s1 / (double)(d + 1), s1, s2);
+}
 #endif  // __CUDACC__

@@ -114,6 +114,8 @@ struct hb_handle {
   int persist_state = 0;                  // persistent generation loop (one cooperative launch per slice): same convention
   unsigned* grid_bar = nullptr;           // [2] grid barrier words of the persistent kernel
   hb_fused_tdist fused_td{};
+  int k1_td_state = 0;                    // large populations: log-density folded into the proposal kernel; 0 undecided, 1 on, -1 off
+  hb_fused_tdist k1_td{};
   double* persist_partials = nullptr;     // [update_interval][ceil(n_local / 8)][(nCR + 2) d]: per-CTA statistic sums parked by the persistent kernel
   double* persist_ibuf = nullptr;         // [update_interval][(nCR + 2) d]: their per-generation reductions
   int persist_adapt_ok = 0;               // 0 undecided, 1 on, -1 off (HB_PERSIST_ADAPT=0)

@@ -451,99 +451,27 @@ __device__ __forceinline__ fused_gen fused_gen_of(const hb_k3_params& q) {
   return g;
 }
 
-// ---- the cooperative triangular product of the fused small-population kernels ----
-// z = xp W for the CTA's eight proposals is exactly one row block of the fp64 tensor-core tile (mma.sync m8n8k4 -> DMMA): A =
-// the 8 x 4 slice of the proposals, B = a 4 x 8 block of W in fragment order (the plugin's operand, hb_targets.cu), so a
-// k step costs two 64-bit shared loads per lane instead of the 24-72 shared-memory wavefronts per 32 FMAs of a broadcast /
-// FMA formulation (which is what bounded this phase: measured 4 400 cycles with 8 warps, 5 800 with 16).
-// Column block nb (columns 8 nb .. 8 nb + 7) needs the k blocks kb < K_nb = min(2 nb + 2, KB).  The column blocks are dealt
-// to the product warps longest first (each to the warp with the least work so far: 25 | 24 | 22 + 2 | 20 + 4 | ... at d = 100);
-// a warp runs the DMMA chain of each of its blocks (two accumulators: a dependent DMMA costs ~90 cycles), squares the tile
-// and adds it to its partial residual sum of squares per proposal; the warp that owns a chain adds the partials of the
-// product warps in a fixed order.  Nothing but eight doubles per product warp crosses warps.
-constexpr int FUSED_MAX_WORK = 8;
-struct fused_plan {
-  int nseg, NB, T;                // product warps, column blocks, 32-double blocks of the fragment-ordered W
-  int xld, zld;                   // row strides of the proposal tile (== 4 mod 16: conflict-free A loads) and of the statistics rows
-  short n_work[16];               // column blocks of product warp s ...
-  short work_nb[16][FUSED_MAX_WORK];   // ... in the order it runs them
-  short K[16], blk_base[16];      // k blocks of column block nb; its first 32-double block in the fragment-ordered W
-};
-inline bool fused_make_plan(int KB, int nseg, fused_plan* out) {
-  fused_plan pl{};
-  const int NB = (KB + 1) / 2;
-  if (nseg > 16 || NB > 16) return false;
-  pl.nseg = nseg; pl.NB = NB; pl.zld = 8 * NB; pl.xld = 4 * KB + ((4 - (4 * KB) % 16) + 16) % 16;
-  int T = 0;
-  for (int nb = 0; nb < NB; ++nb) { pl.K[nb] = (short)((2 * nb + 2 < KB) ? 2 * nb + 2 : KB); pl.blk_base[nb] = (short)T; T += pl.K[nb]; }
-  pl.T = T;
-  int load[16] = {0};
-  for (int nb = NB - 1; nb >= 0; --nb) {       // K is non-decreasing in nb: longest first
-    int best = 0;
-    for (int s2 = 1; s2 < nseg; ++s2) if (load[s2] < load[best]) best = s2;
-    if (pl.n_work[best] >= FUSED_MAX_WORK) return false;
-    pl.work_nb[best][pl.n_work[best]++] = (short)nb;
-    load[best] += pl.K[nb];
-  }
-  *out = pl;
-  return true;
-}
-// shared memory of the fused kernels in doubles: W blocks | proposal tile [8][xld] | statistics rows [16][zld] | row stages
-inline size_t fused_smem_doubles(const fused_plan& pl, int stage_rows, int ldx) {
-  return (size_t)pl.T * 32 + (size_t)8 * pl.xld + (size_t)16 * pl.zld + (size_t)8 * stage_rows * ldx;
-}
-
-// What a product warp does never changes during a launch, so every warp unpacks its part of the plan once, into shared
-// memory: entry = {first double of the block's B fragments, DMMA steps}; rsspart[s][c]: warp s's part of proposal c's sum.
-struct fused_work { int n[16]; int2 e[16][FUSED_MAX_WORK]; double rsspart[16][8]; };
-__device__ __forceinline__ void fused_work_init(fused_work* wk, const fused_plan& pl) {
-  const int seg = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane != 0 || seg >= pl.nseg || seg >= 16) return;
-  const int n = pl.n_work[seg];
-  for (int q = 0; q < n; ++q) { const int nb = pl.work_nb[seg][q]; wk->e[seg][q] = make_int2(pl.blk_base[nb] * 32, pl.K[nb]); }
-  wk->n[seg] = n;
-}
-
-__device__ __forceinline__ void fused_product(const double* __restrict__ Ws, const double* __restrict__ xs_all, fused_work* wk, int xld,
-                                              int seg, int lane) {
-  const int gid = lane >> 2, tig = lane & 3;
-  const double* __restrict__ ap = xs_all + gid * xld + tig;                // A fragment: proposal gid, coordinate 4 kb + tig
-  const double* __restrict__ wl = Ws + lane;                               // B fragment of a block: element `lane`
-  const int nw = wk->n[seg];
-  double r = 0.0;
-  for (int e = 0; e < nw; ++e) {
-    const int2 w = wk->e[seg][e];
-    const double* __restrict__ bp = wl + w.x;
-    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;                         // C: row gid, columns 2 tig, 2 tig + 1; even / odd k blocks
-    int i = 0;
-    for (; i + 2 <= w.y; i += 2) {
-      dmma884(c0, c1, ap[4 * i], bp[32 * i]);
-      dmma884(e0, e1, ap[4 * i + 4], bp[32 * i + 32]);
-    }
-    if (i < w.y) dmma884(c0, c1, ap[4 * i], bp[32 * i]);
-    c0 += e0; c1 += e1;
-    r = fma(c0, c0, r); r = fma(c1, c1, r);
-  }
-  r += __shfl_xor_sync(0xffffffffu, r, 1);
-  r += __shfl_xor_sync(0xffffffffu, r, 2);
-  if (tig == 0) wk->rsspart[seg][gid] = r;
-}
-
 // One chain's whole generation for the warp that owns it: proposal, t-distribution log-density, Metropolis decision, state
 // update into q.Xout and history store.  Shared by the one-launch-per-generation kernel and the persistent kernel below.
+// st (adaptation period only, else nullptr): this warp's three statistics rows [3][ITER * 32] in shared memory.
 template <int ITER, bool TAPE, bool CG = false>
 __device__ __forceinline__ void fused_chain_step(const hb_k1_params& p, const hb_k3_params& q, const hb_fused_tdist& td, const fused_gen& fg,
-                                                 const double* __restrict__ Ws, double* __restrict__ xs, uint64_t* wbar, bool& w_ready,
-                                                 const k1_headv& hv, int lane, unsigned long long* s_cnt, unsigned& errbits,
-                                                 double* stage, uint64_t* sbar, unsigned& sphase,
-                                                 const double* __restrict__ xs_all, double* __restrict__ zpart, bool has_chain,
-                                                 const fused_plan& pl, fused_work* wk, long long* tm = nullptr,
-                                                 const double* shift_g = nullptr, int* s_ids = nullptr, const double* logu_pre = nullptr,
+                                                 const double* __restrict__ rs_s, const k1_headv& hv, int lane, unsigned long long* s_cnt,
+                                                 unsigned& errbits, double* stage, uint64_t* sbar, unsigned& sphase, bool has_chain,
+                                                 long long* tm = nullptr, const double* shift_g = nullptr, double* st = nullptr,
+                                                 int* s_id = nullptr, const double* logu_pre = nullptr,
                                                  const k1_prev<ITER>* sweep_pre = nullptr) {
-  // BLOCK-COLLECTIVE: every warp of the CTA calls this once per round (has_chain = false for a warp without a chain); the
-  // log-density of the CTA's eight proposals is computed cooperatively between two __syncthreads().
   constexpr unsigned FULL = 0xffffffffu;
+  constexpr int SLD = ITER * 32;
   const int d = p.d, ldx = p.ldx;
+    if (!has_chain) {                                                   // no chain: no contribution to the statistics
+      if (st) {
+#pragma unroll
+        for (int m = 0; m < ITER; ++m) { st[m * 32 + lane] = 0.0; st[SLD + m * 32 + lane] = 0.0; st[2 * SLD + m * 32 + lane] = 0.0; }
+        if (lane == 0) *s_id = -1;
+      }
+      return;
+    }
     // ---------------- proposal (K1) ----------------
     double xk[ITER], dxk[ITER], xp[ITER];
     const long long jl = has_chain ? hv.jl : 0; const int id = has_chain ? hv.id : 0;
@@ -570,51 +498,29 @@ __device__ __forceinline__ void fused_chain_step(const hb_k1_params& p, const hb
         }
         xp[m] = v;
       }
-      if (xs && k < pl.xld) xs[k] = xp[m];                              // (columns d .. 4 KB - 1 of the tile: zeros)
     }
     if (p.prior == 1) lp_part = hb_group_sum<32>(lp_part);
     double lpx = (p.prior == 1) ? lp_part : 0.0;                        // flat prior: 0  :55
     if (!(lpx >= HB_FLOOR)) lpx = (lpx != lpx) ? lpx : HB_FLOOR;        // :65
     if (!isfinite(lpx)) errbits |= HB_FLAG_LP_NONFINITE;                // :67
-    __syncwarp();
 
     // ---------------- log-density (K2): dmvt, R/test_t_distribution.R:43 ----------------
-    // z_n = sum_{k <= n} xp_k W[k][n] for the EIGHT proposals of the CTA at once on the fp64 tensor cores (fused_product
-    // above); the warp that owns a chain folds the partial tiles of its row, squares and reduces.  ll differs from the
-    // plugin's in the last bits (<= 1e-13 relative: the k range of a column is cut at other places); states and decisions agree.
-    if (!w_ready) { mbar_wait(wbar, 0); w_ready = true; }                // W has landed (first round of the launch only)
-    __syncthreads();                                                     // the eight proposals are in xs_all
+    // the structured evaluation of the target (hb_targets.cu: hb_tdist_struct_kernel) on the proposal in registers:
+    // x' C^-1 x = 2 (sum u^2 - (sum u)^2 / (d + 1)), u_k = xp_k / sqrt(k); rs_s: 1 / sqrt(k) in shared memory, zero past d
     if (tm) tm[2] = clock64();
+    double rss;
     {
-      const int wib = threadIdx.x >> 5;
-      if (wib < pl.nseg) fused_product(Ws, xs_all, wk, pl.xld, wib, lane);
-    }
-    if (tm) tm[8] = clock64();
-    __syncthreads();                                                     // every product warp's partial sums are in place
-    if (tm) tm[9] = clock64();
-    double rss = 0.0;
-    if (has_chain) {                                                     // fixed tree over the product warps
-      const int wib = threadIdx.x >> 5;
-      rss = (lane < pl.nseg) ? wk->rsspart[lane & 15][wib] : 0.0;
+      double s1 = 0.0, s2 = 0.0;
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) rss += __shfl_xor_sync(FULL, rss, o);
-      rss = __shfl_sync(FULL, rss, 0);
-    }
-    if (!has_chain) {
-      if (shift_g && xs) {                                              // no chain: no contribution to the statistics
-        const int wib = threadIdx.x >> 5;
-#pragma unroll
-        for (int m = 0; m < ITER; ++m) {
-          const int k = m * 32 + lane;
-          if (k < d) { zpart[(size_t)wib * pl.zld + k] = 0.0; zpart[(size_t)(8 + wib) * pl.zld + k] = 0.0; xs[k] = 0.0; }
-        }
-        if (lane == 0) s_ids[wib] = -1;
+      for (int m = 0; m < ITER; ++m) {
+        const double u = xp[m] * rs_s[m * 32 + lane];
+        s1 += u; s2 = fma(u, u, s2);
       }
-      return;
+      hb_warp_sum2(s1, s2, lane);
+      rss = hb_tdist_rss(s1, s2, d);
     }
     if (tm) tm[7] = clock64();
     const double dens = td.konst - 0.5 * (td.df + (double)d) * log1p(rss / td.df);
-    __syncwarp();                                                       // xs is rewritten by the next chain
     if (tm) tm[3] = clock64();
 
     // ---------------- accept / update / store (K3, outside the adaptation period) ----------------
@@ -665,11 +571,10 @@ __device__ __forceinline__ void fused_chain_step(const hb_k1_params& p, const hb
       atomicAdd(&s_cnt[1 + id], 1ull);                                  // n_id  :368-369
       if (accf) { atomicAdd(&s_cnt[0], 1ull); atomicAdd(&s_cnt[1 + HB_MAX_NCR + id], 1ull); }   // n_acc :374
     }
-    if (shift_g) {
+    if (st) {
       // adaptation period: this chain's terms of the std_x / jump statistics (R/dream_parallel.R:376-378; the sums of
-      // hb_k3_kernel: shifted post-update state, its square, dx^2 filed under the crossover index).  Rows of zpart / xs that
-      // only this warp touched in the product phase; the CTA folds them in warp order after the next block barrier.
-      const int wib = threadIdx.x >> 5;
+      // hb_k3_kernel: shifted post-update state, its square, dx^2 filed under the crossover index); the CTA folds the rows of
+      // its warps in warp order after the next block barrier
 #pragma unroll
       for (int m = 0; m < ITER; ++m) {
         const int k = m * 32 + lane;
@@ -680,9 +585,9 @@ __device__ __forceinline__ void fused_chain_step(const hb_k1_params& p, const hb
           const double dxv = accf ? xp[m] - xk[m] : 0.0;                // :357 (after bound handling), 0 if rejected
           dd = dxv * dxv;
         }
-        if (k < d) { zpart[(size_t)wib * pl.zld + k] = cc; zpart[(size_t)(8 + wib) * pl.zld + k] = cc * cc; xs[k] = dd; }
+        st[k] = cc; st[SLD + k] = cc * cc; st[2 * SLD + k] = dd;
       }
-      if (lane == 0) s_ids[wib] = id;
+      if (lane == 0) *s_id = id;
     }
 }
 
@@ -700,54 +605,27 @@ __device__ __forceinline__ void fused_chain_step(const hb_k1_params& p, const hb
 //   accept        the non-adaptation path of hb_k3_kernel (R/internals.R:239-241, R/dream_parallel.R:348-366, 386-394)
 // ------------------------------------------------------------------------------------------------------------------
 template <int ITER, bool TAPE>
-__global__ void __launch_bounds__(256) hb_fused_small_kernel(const hb_k1_params p, const hb_k3_params q, const hb_fused_tdist td,
-                                                             const fused_plan pl) {
-  constexpr unsigned FULL = 0xffffffffu;
-  extern __shared__ __align__(16) double fused_smem[];               // W blocks | proposal tile [8][xld] | statistics rows [16][zld] | row stages [8][rows][ldx]
+__global__ void __launch_bounds__(256) hb_fused_small_kernel(const hb_k1_params p, const hb_k3_params q, const hb_fused_tdist td) {
+  extern __shared__ __align__(16) double fused_smem[];               // 1 / sqrt(k) [ITER * 32] | row stages [warps][rows][ldx]
   __shared__ unsigned long long s_cnt[2 * HB_MAX_NCR + 1];
-  __shared__ __align__(8) uint64_t wbar;
   __shared__ __align__(8) uint64_t sbars[8];
-  __shared__ fused_work s_work;
   const int lane = threadIdx.x & 31;
   const int n_wib = blockDim.x >> 5, wib = threadIdx.x >> 5;
   const int stage_rows = (1 + 2 * p.delta) > 4 ? (1 + 2 * p.delta) : 4;
-  double* Ws = fused_smem;
-  double* xs = fused_smem + (size_t)pl.T * 32 + (size_t)wib * pl.xld;
-  const double* xs_all = fused_smem + (size_t)pl.T * 32;
-  double* zpart = fused_smem + (size_t)pl.T * 32 + (size_t)8 * pl.xld;
-  double* stage = zpart + (size_t)16 * pl.zld + (size_t)wib * stage_rows * p.ldx;
+  double* rs_s = fused_smem;
+  double* stage = fused_smem + ITER * 32 + (size_t)wib * stage_rows * p.ldx;
   unsigned sphase = 0;
   if (lane == 0) { mbar_init(&sbars[wib], 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
-  // the fragment-ordered W (pl.T blocks of 256 bytes) is staged once per CTA by bulk TMA copies of at most 32 KB; it lands
-  // while the warps compute their first proposal
-  const uint32_t w_bytes = (uint32_t)pl.T * 256u;
-  if (threadIdx.x == 0) {
-    mbar_init(&wbar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  }
+  for (int k = threadIdx.x; k < ITER * 32; k += blockDim.x) rs_s[k] = (k < p.d) ? td.rs[k] : 0.0;
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const int d = p.d, ldx = p.ldx;
-  (void)d; (void)ldx;
   unsigned errbits = 0;
   if (threadIdx.x <= 2 * HB_MAX_NCR) s_cnt[threadIdx.x] = 0ull;
-  fused_work_init(&s_work, pl);
   __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(&wbar, w_bytes);
-    for (uint32_t off = 0; off < w_bytes; off += 32768u) {
-      const uint32_t nbytes = (w_bytes - off) < 32768u ? (w_bytes - off) : 32768u;
-      tma_load_1d(reinterpret_cast<char*>(Ws) + off, reinterpret_cast<const char*>(td.Wblk) + off, nbytes, &wbar);
-    }
-  }
 
-  bool w_ready = false;
-  for (long long base0 = (long long)blockIdx.x * n_wib; base0 < p.n_local; base0 += n_warps) {   // one round = this CTA's next 8 chains
-    const long long base = base0 + wib;
-    const bool has_chain = base < p.n_local;
+  for (long long base = (long long)blockIdx.x * n_wib + wib; base < p.n_local; base += n_warps) {   // one chain per warp and round
     k1_headv hv;
-    if (has_chain) k1_chain_head<32, TAPE>(p, p.gen, p.tape_g, base, lane, hv, errbits);
-    fused_chain_step<ITER, TAPE>(p, q, td, fused_gen_of(q), Ws, xs, &wbar, w_ready, hv, lane, s_cnt, errbits, stage, &sbars[wib], sphase,
-                                 xs_all, zpart, has_chain, pl, &s_work);
+    k1_chain_head<32, TAPE>(p, p.gen, p.tape_g, base, lane, hv, errbits);
+    fused_chain_step<ITER, TAPE>(p, q, td, fused_gen_of(q), rs_s, hv, lane, s_cnt, errbits, stage, &sbars[wib], sphase, true);
   }
   __syncthreads();
   if (threadIdx.x <= 2 * HB_MAX_NCR) {
@@ -770,11 +648,9 @@ cudaError_t launch_fused(const hb_k1_params& p, const hb_k3_params& q, const hb_
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   const int stage_rows = (1 + 2 * p.delta) > 4 ? (1 + 2 * p.delta) : 4;
-  if (td.KB <= 0 || !td.Wblk || 4 * td.KB < p.d) return cudaErrorInvalidValue;
-  fused_plan pl;
-  if (!fused_make_plan(td.KB, warps, &pl)) return cudaErrorInvalidValue;
-  const size_t smem = fused_smem_doubles(pl, stage_rows, p.ldx) * sizeof(double);
-  if (smem > 220 * 1024 || pl.xld > ITER * 32 + 4 || (p.ldx & 1)) return cudaErrorInvalidValue;
+  if (!td.rs || p.d > ITER * 32 || (p.ldx & 1)) return cudaErrorInvalidValue;
+  const size_t smem = ((size_t)ITER * 32 + (size_t)warps * stage_rows * p.ldx) * sizeof(double);
+  if (smem > 220 * 1024) return cudaErrorInvalidValue;
   static bool attr_set[2] = {false, false};
   if (!attr_set[tape]) {
     cudaError_t e = tape ? cudaFuncSetAttribute(hb_fused_small_kernel<ITER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)
@@ -782,8 +658,8 @@ cudaError_t launch_fused(const hb_k1_params& p, const hb_k3_params& q, const hb_
     if (e != cudaSuccess) return e;
     attr_set[tape] = true;
   }
-  if (tape) hb_fused_small_kernel<ITER, true><<<(unsigned)blocks, threads, smem, st>>>(p, q, td, pl);
-  else hb_fused_small_kernel<ITER, false><<<(unsigned)blocks, threads, smem, st>>>(p, q, td, pl);
+  if (tape) hb_fused_small_kernel<ITER, true><<<(unsigned)blocks, threads, smem, st>>>(p, q, td);
+  else hb_fused_small_kernel<ITER, false><<<(unsigned)blocks, threads, smem, st>>>(p, q, td);
   return cudaGetLastError();
 }
 
@@ -797,49 +673,30 @@ cudaError_t launch_fused(const hb_k1_params& p, const hb_k3_params& q, const hb_
 // the others.  The per-chain step is fused_chain_step, i.e. draw for draw and operation for operation the
 // one-launch-per-generation kernel; the population is read with L2-coherent loads (other CTAs rewrite it between barriers).
 // ------------------------------------------------------------------------------------------------------------------
-template <int ITER, bool TAPE, int NT>
-__global__ void __launch_bounds__(NT) hb_persist_small_kernel(const hb_k1_params p0, const hb_k3_params q0, const hb_fused_tdist td,
-                                                              const hb_persist_params pp, const fused_plan pl) {
-  // NT = 256: eight warps, one per chain (warps beyond the eighth would own no chain and only join the cooperative product)
-  extern __shared__ __align__(16) double fused_smem[];               // W blocks | proposal tile [8][xld] | statistics rows [16][zld] | row stages
+template <int ITER, bool TAPE>
+__global__ void __launch_bounds__(256) hb_persist_small_kernel(const hb_k1_params p0, const hb_k3_params q0, const hb_fused_tdist td,
+                                                               const hb_persist_params pp) {
+  extern __shared__ __align__(16) double fused_smem[];               // 1 / sqrt(k) [SLD] | statistics rows [8][3][SLD] | row stages
   __shared__ unsigned long long s_cnt[2 * HB_MAX_NCR + 1];
-  __shared__ __align__(8) uint64_t wbar;
   __shared__ __align__(8) uint64_t sbars[8];
   __shared__ int s_ids[8];
-  __shared__ fused_work s_work;
+  constexpr int SLD = ITER * 32;
   const int lane = threadIdx.x & 31;
-  constexpr int n_wib = 8;                                           // chain warps
+  constexpr int n_wib = 8;                                           // warps per CTA, one chain each
   const int wib = threadIdx.x >> 5;
-  const bool chain_warp = wib < n_wib;
   const int stage_rows = (1 + 2 * p0.delta) > 4 ? (1 + 2 * p0.delta) : 4;
-  double* Ws = fused_smem;
-  double* xs = chain_warp ? fused_smem + (size_t)pl.T * 32 + (size_t)wib * pl.xld : nullptr;
-  const double* xs_all = fused_smem + (size_t)pl.T * 32;
-  double* zpart = fused_smem + (size_t)pl.T * 32 + (size_t)8 * pl.xld;
-  double* stage = zpart + (size_t)16 * pl.zld + (size_t)(chain_warp ? wib : 0) * stage_rows * p0.ldx;
+  double* rs_s = fused_smem;
+  double* stats = fused_smem + SLD;                                  // warp w: rows [w][0..2]: shifted state, its square, dx^2
+  double* stage = stats + (size_t)n_wib * 3 * SLD + (size_t)wib * stage_rows * p0.ldx;
   unsigned sphase = 0;
-  if (lane == 0 && chain_warp) { mbar_init(&sbars[wib], 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
-  const uint32_t w_bytes = (uint32_t)pl.T * 256u;
-  if (threadIdx.x == 0) {
-    mbar_init(&wbar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  }
+  if (lane == 0) { mbar_init(&sbars[wib], 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+  for (int k = threadIdx.x; k < SLD; k += blockDim.x) rs_s[k] = (k < p0.d) ? td.rs[k] : 0.0;
   if (threadIdx.x <= 2 * HB_MAX_NCR) s_cnt[threadIdx.x] = 0ull;
-  fused_work_init(&s_work, pl);
   __syncthreads();
-  // the fragment-ordered W: bulk TMA copies of at most 32 KB, once for the whole run
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(&wbar, w_bytes);
-    for (uint32_t off = 0; off < w_bytes; off += 32768u) {
-      const uint32_t nbytes = (w_bytes - off) < 32768u ? (w_bytes - off) : 32768u;
-      tma_load_1d(reinterpret_cast<char*>(Ws) + off, reinterpret_cast<const char*>(td.Wblk) + off, nbytes, &wbar);
-    }
-  }
-  const long long warp_id = (long long)blockIdx.x * n_wib + wib;     // the chain of a chain warp
+  const long long warp_id = (long long)blockIdx.x * n_wib + wib;     // this warp's chain
   const long long nl = p0.n_local;
-  const bool active = chain_warp && warp_id < nl;      // one chain per chain warp (the launcher sizes the grid that way)
+  const bool active = warp_id < nl;                    // one chain per warp (the launcher sizes the grid that way)
   unsigned errbits = 0;
-  bool w_ready = false;
   long long ind_out = pp.ind_out0, pending = pp.pending0;
   k1_headv hv;
   if (active) k1_chain_head<32, TAPE>(p0, (uint32_t)pp.i0, pp.i0 - 2, warp_id, lane, hv, errbits);
@@ -868,12 +725,12 @@ __global__ void __launch_bounds__(NT) hb_persist_small_kernel(const hb_k1_params
       fg.accept_rec = pp.accept_rec ? pp.accept_rec + (size_t)(i - 2) * nl : nullptr;
       fg.u_accept = pp.u_accept ? pp.u_accept + (size_t)(i - 2) * pp.tape_nct : nullptr;
     }
-    long long tm[10];
+    long long tm[8];
     const bool tr = pp.trace && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && i >= pp.i0 + 2 && i < pp.i0 + 6;
     if (tr) tm[4] = clock64();
-    fused_chain_step<ITER, TAPE, true>(p0, q0, td, fg, Ws, xs, &wbar, w_ready, hv, lane, s_cnt, errbits, stage, &sbars[wib & 7], sphase,
-                                       xs_all, zpart, active, pl, &s_work, tr ? tm : nullptr, pp.adapt ? q0.shift : nullptr, s_ids,
-                                       TAPE ? nullptr : &logu, &pv);
+    fused_chain_step<ITER, TAPE, true>(p0, q0, td, fg, rs_s, hv, lane, s_cnt, errbits, stage, &sbars[wib], sphase, active,
+                                       tr ? tm : nullptr, pp.adapt ? q0.shift : nullptr, pp.adapt ? stats + (size_t)wib * 3 * SLD : nullptr,
+                                       &s_ids[wib], TAPE ? nullptr : &logu, &pv);
     if (tr) tm[5] = clock64();
     __syncthreads();
     if (tr) tm[6] = clock64();
@@ -885,13 +742,13 @@ __global__ void __launch_bounds__(NT) hb_persist_small_kernel(const hb_k1_params
       for (int e = threadIdx.x; e < E; e += blockDim.x) {
         double sum = 0.0;
         if (e < 2 * p0.d) {
-          const double* col = zpart + (size_t)(e < p0.d ? 0 : 8) * pl.zld + (e < p0.d ? e : e - p0.d);
+          const double* col = stats + (e < p0.d ? e : SLD + e - p0.d);
 #pragma unroll
-          for (int w = 0; w < 8; ++w) sum += col[(size_t)w * pl.zld];
+          for (int w = 0; w < 8; ++w) sum += col[(size_t)w * 3 * SLD];
         } else {
           const int qq = (e - 2 * p0.d) / p0.d, k = (e - 2 * p0.d) - qq * p0.d;
 #pragma unroll
-          for (int w = 0; w < 8; ++w) sum += (s_ids[w] == qq) ? xs_all[(size_t)w * pl.xld + k] : 0.0;
+          for (int w = 0; w < 8; ++w) sum += (s_ids[w] == qq) ? stats[(size_t)w * 3 * SLD + 2 * SLD + k] : 0.0;
         }
         pp.partials[((size_t)(pp.slot0 + (int)(i - pp.i0)) * gridDim.x + blockIdx.x) * E + e] = sum;
       }
@@ -940,8 +797,7 @@ __global__ void __launch_bounds__(NT) hb_persist_small_kernel(const hb_k1_params
     if (threadIdx.x == 0) __threadfence();
     if (upd) pending = 0;
     __syncthreads();
-    if (tr) printf("[persist trace] product: own segment %lld | wait for the others %lld | fold %lld\n", tm[8] - tm[2], tm[9] - tm[8], tm[7] - tm[9]);
-    if (tr) printf("[persist trace] gen %lld cta %d: setup %lld | sweep %lld | xp %lld | product %lld + log1p %lld | accept+store %lld | block sync %lld | barrier+next head %lld cycles\n",
+    if (tr) printf("[persist trace] gen %lld cta %d: setup %lld | sweep %lld | xp %lld | density sums %lld + log1p %lld | accept+store %lld | block sync %lld | barrier+next head %lld cycles\n",
                    i, (int)blockIdx.x, tm[0] - tm[4], tm[1] - tm[0], tm[2] - tm[1], tm[7] - tm[2], tm[3] - tm[7], tm[5] - tm[3], tm[6] - tm[5], clock64() - tm[6]);
   }
   if (errbits) atomicOr(&q0.ctrl->err, errbits);
@@ -950,25 +806,20 @@ __global__ void __launch_bounds__(NT) hb_persist_small_kernel(const hb_k1_params
 template <int ITER>
 cudaError_t launch_persist(const hb_k1_params& p, const hb_k3_params& q, const hb_fused_tdist& td, const hb_persist_params& pp,
                            bool tape, int sm_count, cudaStream_t st) {
-  const int warps = 8;                                                // chain warps per CTA
-  // (eight more helper warps that own no chain and only join the product phase were measured SLOWER: 512 threads cap the
-  // kernel at 128 registers -- spills in the proposal sweep -- and a product warp's 11 dependent DMMAs take as long as 23)
-  const int threads = 256;
+  const int threads = 256, warps = threads / 32;
   const long long blocks = (p.n_local + warps - 1) / warps;
   const int stage_rows = (1 + 2 * p.delta) > 4 ? (1 + 2 * p.delta) : 4;
-  if (td.KB <= 0 || !td.Wblk || 4 * td.KB < p.d) return cudaErrorInvalidValue;
-  fused_plan pl;
-  if (!fused_make_plan(td.KB, threads / 32, &pl)) return cudaErrorInvalidValue;
-  const size_t smem = fused_smem_doubles(pl, stage_rows, p.ldx) * sizeof(double);
-  if (smem > 220 * 1024 || pl.xld > ITER * 32 + 4 || (p.ldx & 1)) return cudaErrorInvalidValue;
-  const void* fn = tape ? (const void*)hb_persist_small_kernel<ITER, true, 256> : (const void*)hb_persist_small_kernel<ITER, false, 256>;
+  if (!td.rs || p.d > ITER * 32 || (p.ldx & 1)) return cudaErrorInvalidValue;
+  const size_t smem = ((size_t)ITER * 32 * (1 + 3 * warps) + (size_t)warps * stage_rows * p.ldx) * sizeof(double);
+  if (smem > 220 * 1024) return cudaErrorInvalidValue;
+  const void* fn = tape ? (const void*)hb_persist_small_kernel<ITER, true> : (const void*)hb_persist_small_kernel<ITER, false>;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem);
   if (e != cudaSuccess) return e;
   if (blocks > (long long)per_sm * sm_count) return cudaErrorCooperativeLaunchTooLarge;   // the grid barrier needs every CTA resident
-  void* args[] = {(void*)&p, (void*)&q, (void*)&td, (void*)&pp, (void*)&pl};
+  void* args[] = {(void*)&p, (void*)&q, (void*)&td, (void*)&pp};
   return cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(threads), args, smem, st);
 }
 
@@ -1126,11 +977,15 @@ __device__ __forceinline__ double2 lds2(const double* q) { return *reinterpret_c
 
 constexpr int K1_PAIR_WARPS = 8;     // 2 CTAs x 8 warps per SM at 126 registers.  Measured: 9 warps (launch bounds 288 -> 96
                                      // registers, spills) is 9 % SLOWER (1.174 vs 1.075 ms); 14 warps/SM is 13 % slower
-template <int ITER2>
+// TD: the handle's target is the built-in t_distribution in its structured evaluation -- the kernel also accumulates
+// sum u, sum u^2 (u_k = xp_k / sqrt(k)) of every proposal while it holds it in registers and writes the log-density, so the
+// plugin launch (a second pass over the proposals: 808 bytes per chain) is not needed.
+template <int ITER2, bool TD>
 __global__ void __launch_bounds__(K1_PAIR_WARPS * 32, 2) hb_k1_pair_kernel(const hb_k1_params p) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr bool KEEP = ITER2 <= 4;     // keep the Philox words of the subspace pass in registers (else recompute)
   extern __shared__ __align__(16) unsigned char k1_smem[];
+  __shared__ __align__(16) double td_rs_s[TD ? 2 * 32 * ITER2 : 2];   // 1 / sqrt(k + 1), zero past d
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1153,6 +1008,10 @@ __global__ void __launch_bounds__(K1_PAIR_WARPS * 32, 2) hb_k1_pair_kernel(const
     for (int s = 0; s < K1_STAGES; ++s) mbar_init(&bars[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
+  if (TD) {
+    for (int k = threadIdx.x; k < 2 * 32 * ITER2; k += blockDim.x) td_rs_s[k] = (k < d) ? p.td_rs[k] : 0.0;
+    __syncthreads();
+  }
   __syncwarp();
   unsigned it = 0;   // chains consumed by this warp so far: stage = it % STAGES, parity = (it / STAGES) & 1
 
@@ -1161,6 +1020,7 @@ __global__ void __launch_bounds__(K1_PAIR_WARPS * 32, 2) hb_k1_pair_kernel(const
     k1_phase_a<false>(p, base, lane, n_src, heads, errbits);
     __syncwarp();
     double lp_mine = 0.0;
+    double td_s1_mine = 0.0, td_s2_mine = 0.0;     // TD: lane c keeps chain c's sums
 
     const int n_in_batch = (int)((p.n_local - base) < B ? (p.n_local - base) : B);
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
@@ -1340,6 +1200,7 @@ __global__ void __launch_bounds__(K1_PAIR_WARPS * 32, 2) hb_k1_pair_kernel(const
 
       // finite check ; bounds ; prior ; store
       double lp_part = 0.0;
+      double td_s1 = 0.0, td_s2 = 0.0;
       double* __restrict__ xp_row = p.XP + jl * (long long)ldx;
 #pragma unroll
       for (int m = 0; m < ITER2; ++m) {
@@ -1359,9 +1220,15 @@ __global__ void __launch_bounds__(K1_PAIR_WARPS * 32, 2) hb_k1_pair_kernel(const
             }
           }
           *reinterpret_cast<double2*>(xp_row + k0) = x;
+          if (TD) {                                      // u = xp / sqrt(k) (the scale of a coordinate past d is zero)
+            const double2 r = lds2(td_rs_s + k0);
+            const double u0 = x.x * r.x, u1 = has1 ? x.y * r.y : 0.0;
+            td_s1 += u0 + u1; td_s2 = fma(u0, u0, td_s2); td_s2 = fma(u1, u1, td_s2);
+          }
         }
       }
       if (p.prior == 1) { lp_part = hb_group_sum<32>(lp_part); if (lane == c) lp_mine = lp_part; }   // lane c keeps chain c's log prior
+      if (TD) { hb_warp_sum2(td_s1, td_s2, lane); if (lane == c) { td_s1_mine = td_s1; td_s2_mine = td_s2; } }
     }
     // the scalars of the batch leave as coalesced stores: lane c owns chain base + c
     if (lane < n_in_batch) {
@@ -1370,6 +1237,11 @@ __global__ void __launch_bounds__(K1_PAIR_WARPS * 32, 2) hb_k1_pair_kernel(const
       if (!isfinite(lp)) errbits |= HB_FLAG_LP_NONFINITE;                // :67
       p.lp_xp[base + lane] = lp;
       p.id_out[base + lane] = (heads[lane * hw] >> 8) & 0xff;
+      if (TD) {                                                          // dmvt, R/test_t_distribution.R:43 (hb_tdist_struct_kernel)
+        const double v = p.td_konst - 0.5 * (p.td_df + (double)d) * log1p(hb_tdist_rss(td_s1_mine, td_s2_mine, d) / p.td_df);
+        if (p.td_fx) p.td_fx[base + lane] = v;
+        p.td_ll[base + lane] = (p.td_lik == 1) ? log(v) : v;
+      }
     }
     __syncwarp();
   }
@@ -1617,14 +1489,19 @@ cudaError_t launch_wide_tape(hb_k1_params p, int sm_count, cudaStream_t st) {
 }
 
 template <int ITER2>
-cudaError_t launch_wide_pair(hb_k1_params p, int sm_count, cudaStream_t st) {
+cudaError_t launch_wide_pair(hb_k1_params p, int sm_count, cudaStream_t st, bool* density_done) {
   int threads; long long blocks; size_t smem;
   k1_wide_geometry(p, sm_count, K1_PAIR_WARPS, &threads, &blocks, &smem);
   if (smem > 220 * 1024) return cudaErrorInvalidValue;
-  cudaError_t e = cudaFuncSetAttribute(hb_k1_pair_kernel<ITER2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const bool td = ITER2 <= 4 && p.td_rs != nullptr && p.td_ll != nullptr && density_done != nullptr && p.n_runs <= 1;
+  cudaError_t e = td ? cudaFuncSetAttribute(hb_k1_pair_kernel<ITER2, (ITER2 <= 4)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                     : cudaFuncSetAttribute(hb_k1_pair_kernel<ITER2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  hb_k1_pair_kernel<ITER2><<<(unsigned)blocks, threads, smem, st>>>(p);
-  return cudaGetLastError();
+  if (td) hb_k1_pair_kernel<ITER2, (ITER2 <= 4)><<<(unsigned)blocks, threads, smem, st>>>(p);
+  else hb_k1_pair_kernel<ITER2, false><<<(unsigned)blocks, threads, smem, st>>>(p);
+  e = cudaGetLastError();
+  if (e == cudaSuccess && td) *density_done = true;
+  return e;
 }
 
 template <int G, int ITER>
@@ -1645,8 +1522,9 @@ cudaError_t launch_gi(const hb_k1_params& p, bool tape, int sm_count, cudaStream
 
 int g_hb_force_wide = 0;
 
-cudaError_t hb_launch_k1(const hb_k1_params& p, bool tape_mode, int sm_count, cudaStream_t st) {
+cudaError_t hb_launch_k1(const hb_k1_params& p, bool tape_mode, int sm_count, cudaStream_t st, bool* density_done) {
   const int d = p.d;
+  if (density_done) *density_done = false;
   if (d <= 1) return launch_gi<1, 1>(p, tape_mode, sm_count, st);
   if (d <= 2) return launch_gi<2, 1>(p, tape_mode, sm_count, st);
   if (d <= 4) return launch_gi<4, 1>(p, tape_mode, sm_count, st);
@@ -1672,12 +1550,12 @@ cudaError_t hb_launch_k1(const hb_k1_params& p, bool tape_mode, int sm_count, cu
     if (d <= 1024) return launch_wide_tape<32>(p, sm_count, st);
     return cudaErrorInvalidValue;
   }
-  if (d <= 64) return launch_wide_pair<1>(p, sm_count, st);      // ITER2 = ceil(ceil(d/2)/32) pairs per lane
-  if (d <= 128) return launch_wide_pair<2>(p, sm_count, st);
-  if (d <= 192) return launch_wide_pair<3>(p, sm_count, st);
-  if (d <= 256) return launch_wide_pair<4>(p, sm_count, st);
-  if (d <= 512) return launch_wide_pair<8>(p, sm_count, st);
-  if (d <= 1024) return launch_wide_pair<16>(p, sm_count, st);
+  if (d <= 64) return launch_wide_pair<1>(p, sm_count, st, density_done);      // ITER2 = ceil(ceil(d/2)/32) pairs per lane
+  if (d <= 128) return launch_wide_pair<2>(p, sm_count, st, density_done);
+  if (d <= 192) return launch_wide_pair<3>(p, sm_count, st, density_done);
+  if (d <= 256) return launch_wide_pair<4>(p, sm_count, st, density_done);
+  if (d <= 512) return launch_wide_pair<8>(p, sm_count, st, density_done);
+  if (d <= 1024) return launch_wide_pair<16>(p, sm_count, st, density_done);
   return cudaErrorInvalidValue;
 }
 

@@ -55,17 +55,23 @@ struct hb_k1_params {
   int force_wide;         // host decision: use the large-population kernels (the launch may be one PIECE of a big shard)
   int batch;              // wide kernels: chains a warp takes per batch (32, or 16 / 8 for pieces with fewer batches than warps)
   int reserve_ctas;       // wide kernels: CTAs left out of the persistent grid (room for the concurrent send kernel)
+  // the built-in t_distribution target in its structured evaluation (hb_targets.cu): the large-population proposal kernel
+  // folds the log-density of every proposal into its own sweep (4 d flops on values it holds in registers) and the plugin
+  // launch -- a second pass over the proposals -- is skipped.  td_rs == nullptr: not requested.
+  const double* td_rs;    // [d] 1 / sqrt(i)
+  double td_konst, td_df; int td_lik;
+  double* td_ll; double* td_fx;   // [n_local] the plugin's outputs (raw log-likelihood; target value or nullptr)
   uint32_t ks[20];        // Philox round keys of `seed` (constant bank operands in the kernel)
   uint32_t thr16[HB_MAX_NCR];   // hb_rng_zt_threshold16(CR_q) = ceil(CR_q 2^16 - 0.5): exact integer form of zt < CR[id]
 };
-cudaError_t hb_launch_k1(const hb_k1_params& p, bool tape_mode, int sm_count, cudaStream_t st);
+// density_done (may be nullptr): set to true when the launch also wrote td_ll / td_fx (the caller then skips the plugin)
+cudaError_t hb_launch_k1(const hb_k1_params& p, bool tape_mode, int sm_count, cudaStream_t st, bool* density_done = nullptr);
 
 struct hb_k3_params;
 // ---- fused generation for small populations (hb_k1_propose.cu): K1 + t-distribution density + K3 in one launch ----
 struct hb_fused_tdist {
-  const double* W; int ldw;      // W = chol(C)^-1, dense upper triangle [d][ldw], zeros below
+  const double* rs;              // [d] 1 / sqrt(i): the structured evaluation of the target (hb_targets.cu)
   int lik; double konst, df;
-  const double* Wblk; int KB;    // the same W in block-triangular DMMA fragment order (hb_targets.cu), KB k-blocks of 4 (0: d > 128)
 };
 bool hb_fused_small_eligible(long long n_local, int d, int sm_count);
 cudaError_t hb_launch_fused_small(const hb_k1_params& p, const hb_k3_params& q, const hb_fused_tdist& td, bool tape_mode,

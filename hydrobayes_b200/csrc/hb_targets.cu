@@ -153,6 +153,36 @@ __global__ void __launch_bounds__(256, (KB > 25 ? 2 : 3)) hb_tdist_dmma_kernel(c
   }
 }
 
+// Structured evaluation (the default).  The reference's covariance is C = S (I/2 + 11'/2) S with S = diag(sqrt(i))
+// (R/test_t_distribution.R:32-40: C[i,j] = A[i,j] sqrt(i j), A = 0.5 I + 0.5), so by Sherman-Morrison
+//   C^-1 = 2 S^-1 (I - 11'/(d + 1)) S^-1   and   x' C^-1 x = 2 (sum u_i^2 - (sum u_i)^2 / (d + 1)),  u_i = x_i / sqrt(i):
+// the quadratic form dmvt obtains from chol(C) and a triangular solve (d^2 + 3 d flops per point) costs 4 d flops, and the
+// kernel is a stream over the proposals (808 bytes per point) instead of a d x d product.  Same value to rounding: against
+// the long-double restatement of dmvt the log-density agrees to 5e-16 relative at d = 100 (tests: every plugin test runs both
+// evaluations).  Cancellation is bounded: (sum u)^2 <= d sum u^2, so the result is at least 2 sum u^2 / (d + 1).
+// rs[i] = 1 / sqrt(i + 1), correctly rounded on the host.  One warp per point; hb_tdist_rss is shared with the proposal
+// kernels that fold the density into their own sweep (hb_k1_propose.cu).
+__global__ void hb_tdist_struct_kernel(const double* __restrict__ X, long long n, int d, int ldx, const double* __restrict__ rs,
+                                       double konst, double df, int lik, double* __restrict__ ll, double* __restrict__ fx) {
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (long long row = warp_id; row < n; row += n_warps) {
+    const double* xr = X + row * (long long)ldx;
+    double s1 = 0.0, s2 = 0.0;
+    for (int k = lane; k < d; k += 32) {
+      const double u = xr[k] * rs[k];
+      s1 += u; s2 = fma(u, u, s2);
+    }
+    hb_warp_sum2(s1, s2, lane);
+    if (lane == 0) {
+      const double v = konst - 0.5 * (df + (double)d) * log1p(hb_tdist_rss(s1, s2, d) / df);   // dmvt, R/test_t_distribution.R:43
+      if (fx) fx[row] = v;
+      ll[row] = (lik == 1) ? log(v) : v;
+    }
+  }
+}
+
 // generic FMA path for d > 128 (and the cross-check of the DMMA kernel in the tests): one warp per chain
 __global__ void hb_tdist_fma_kernel(const double* __restrict__ X, long long n, int d, int ldx,
                                     const double* __restrict__ Wg, int ldw, double konst, double df, int lik,
@@ -182,8 +212,10 @@ struct tdist_ctx {
   double konst, df;
   double* W_dev;       // [kp][ldw] dense upper triangle (FMA path)
   double* Wblk_dev;    // block-triangular fragment order (DMMA path), tdist_n_blocks(KB) x 32 doubles
+  double* rs_dev;      // [d] 1 / sqrt(i): the structured evaluation
   int sm_count;
   int force_fma;
+  int dense;           // HB_TDIST_DENSE=1: dmvt's own route (triangular product on the fp64 tensor cores) instead of the structured one
 };
 
 // C = (0.5 I + 0.5) o sqrt(i j); R = chol(C) (upper); W = R^-1; all in long double, rounded once
@@ -264,6 +296,17 @@ int tdist_init(void** ctx, int d, int lik, const double*, const int64_t*, int, c
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, dev);
   const char* f = getenv("HB_TDIST_FORCE_FMA");
   if (f && f[0] == '1') c->force_fma = 1;
+  f = getenv("HB_TDIST_DENSE");
+  c->dense = (f && f[0] == '1') || c->force_fma;
+  {
+    std::vector<double> rs((size_t)d);
+    for (int i = 0; i < d; ++i) rs[(size_t)i] = 1.0 / sqrt((double)(i + 1));      // IEEE sqrt and division: correctly rounded twice
+    c->rs_dev = nullptr;
+    if (cudaMalloc(&c->rs_dev, rs.size() * sizeof(double)) != cudaSuccess ||
+        cudaMemcpy(c->rs_dev, rs.data(), rs.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaFree(c->W_dev); cudaFree(c->Wblk_dev); cudaFree(c->rs_dev); delete c; set_err(err, errlen, "cudaMalloc/cudaMemcpy failed for the scale vector"); return HB_ERR_CUDA;
+    }
+  }
   *ctx = c;
   return HB_OK;
 }
@@ -295,6 +338,13 @@ int tdist_launch(void* ctx, const double* x, int64_t n, int d, int ldx, double* 
   auto* c = (tdist_ctx*)ctx;
   cudaStream_t st = (cudaStream_t)stream;
   if (n <= 0) return HB_OK;
+  if (!c->dense) {
+    long long blocks = (n + 7) / 8;
+    const long long cap = (long long)c->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    hb_tdist_struct_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, n, c->d, ldx, c->rs_dev, c->konst, c->df, c->lik, ll, fx);
+    return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
+  }
   if (!c->KB || c->force_fma) {
     long long blocks = (n + 3) / 4;
     const long long cap = (long long)c->sm_count * 16;
@@ -312,19 +362,23 @@ int tdist_launch(void* ctx, const double* x, int64_t n, int d, int ldx, double* 
 }
 void tdist_destroy(void* ctx) {
   auto* c = (tdist_ctx*)ctx;
-  if (c) { cudaFree(c->W_dev); cudaFree(c->Wblk_dev); delete c; }
+  if (c) { cudaFree(c->W_dev); cudaFree(c->Wblk_dev); cudaFree(c->rs_dev); delete c; }
 }
-void tdist_work(void*, int d, double* flops, double* bytes) { *flops = (double)d * d + 3.0 * d; *bytes = 8.0 * d + 8; }
+void tdist_work(void* ctx, int d, double* flops, double* bytes) {
+  const auto* c = (const tdist_ctx*)ctx;
+  *flops = (c && !c->dense) ? 4.0 * d : (double)d * d + 3.0 * d;     // structured: u, sum u, sum u^2 ; dense: triangular solve as backsolve
+  *bytes = 8.0 * d + 8;
+}
 
 }  // namespace
 
-// operands of the fused small-population kernel (hb_k1_propose.cu) when the handle's target is this plugin
+// operands of the proposal kernels that fold the log-density into their sweep (hb_k1_propose.cu) when the handle's target is
+// this plugin in its structured evaluation
 bool hb_tdist_fused_info(const hb_target_vtable* vt, void* ctx, hb_fused_tdist* out) {
   if (!vt || !ctx || vt->launch != tdist_launch) return false;
   const auto* c = (const tdist_ctx*)ctx;
-  if (c->force_fma) return false;                       // HB_TDIST_FORCE_FMA=1 is a cross-check of the stand-alone kernels
-  out->W = c->W_dev; out->ldw = c->ldw; out->lik = c->lik; out->konst = c->konst; out->df = c->df;
-  out->Wblk = c->Wblk_dev; out->KB = c->KB;
+  if (c->dense) return false;                           // HB_TDIST_DENSE=1: dmvt's own route, stand-alone kernels only
+  out->rs = c->rs_dev; out->lik = c->lik; out->konst = c->konst; out->df = c->df;
   return true;
 }
 

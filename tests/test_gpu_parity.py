@@ -32,18 +32,26 @@ def test_mixture_logdensity(hb, oracle):
     assert (ll == oracle.log_xmin()).sum() >= 2
 
 
+@pytest.mark.parametrize("dense", ["0", "1"])
 @pytest.mark.parametrize("d", [1, 2, 3, 5, 8, 17, 37, 64, 100, 128, 130])
-def test_tdist_logdensity(hb, oracle, d):
+def test_tdist_logdensity(hb, oracle, monkeypatch, d, dense):
+    # both evaluations of the plugin against the oracle's restatement of dmvt (chol + triangular solve): the structured one
+    # (default: x' C^-1 x = 2 (sum u^2 - (sum u)^2 / (d + 1)), u_i = x_i / sqrt(i)) and dmvt's own route on the fp64 tensor
+    # cores (HB_TDIST_DENSE=1).  The last rows are the structured form's worst case for cancellation: x_i proportional to sqrt(i).
+    monkeypatch.setenv("HB_TDIST_DENSE", dense)
     rng = np.random.default_rng(d)
     x = np.concatenate([rng.uniform(-5, 15, size=(1001, d)), np.zeros((1, d)), np.ones((1, d)),
-                        rng.normal(size=(30, d)) * np.sqrt(np.arange(1, d + 1))])
+                        rng.normal(size=(30, d)) * np.sqrt(np.arange(1, d + 1)),
+                        np.outer([1.0, -3.7, 30.0], np.sqrt(np.arange(1, d + 1)))])
     ll, fx = hb.log_density("t_distribution", x, lik=2)
     ll_o = oracle.tdist_logpdf(x)
     np.testing.assert_allclose(ll, ll_o, rtol=1e-12)
     np.testing.assert_allclose(fx, ll_o, rtol=1e-12)
 
 
-def test_tdist_known_answers(hb):
+@pytest.mark.parametrize("dense", ["0", "1"])
+def test_tdist_known_answers(hb, monkeypatch, dense):
+    monkeypatch.setenv("HB_TDIST_DENSE", dense)
     ll, _ = hb.log_density("t_distribution", np.zeros((1, 100)), lik=2)
     assert ll[0] == pytest.approx(-213.43955272792834, rel=1e-13)
     ll, _ = hb.log_density("t_distribution", np.ones((1, 100)), lik=2)
@@ -192,6 +200,34 @@ def test_wide_kernels_native(hb, oracle, force_wide, d, nc):
     # (identical today; the opt-in fused small-population kernel sums the quadratic form in a different order)
     assert np.array_equal(dev["chain"][:, :d, :], narrow["chain"][:, :d, :], equal_nan=True) and np.array_equal(dev["accept"], narrow["accept"])
     np.testing.assert_allclose(dev["chain"][:, d:, :], narrow["chain"][:, d:, :], rtol=1e-13, equal_nan=True)
+
+
+@pytest.mark.parametrize("d,nc,opts", [
+    (100, 96, {}), (99, 77, {}), (100, 5000, {"t": 40}), (52, 203, {}), (64, 130, {"store_fx": 1}), (17, 67, {}), (128, 90, {}),
+    (200, 70, {"t": 50}), (100, 333, {"prior": A.HB_PRIOR_UNIFORM, "bound": A.HB_BOUND_REFLECT}),
+    (60, 1100, {"past_sample": 1, "psnooker": 0.3, "m0": 1400, "archive_update": 5, "t": 50}),
+])
+def test_density_folded_into_the_proposal_kernel(hb, force_wide, monkeypatch, d, nc, opts):
+    # large-population path with the built-in t_distribution: hb_k1_pair_kernel<., TD> accumulates the structured quadratic form
+    # of every proposal in its own sweep and writes ll (no plugin launch), against the two-kernel path (HB_K1_DENSITY=0:
+    # hb_k1_pair_kernel -> hb_tdist_struct_kernel).  Same draws and proposals bit for bit; the two sum u and u^2 over the
+    # coordinates in different orders, so ll agrees to rounding (1e-13), and with it every decision of these runs.
+    o = dict(opts)
+    t = o.pop("t", 70)
+    cfg = A.default_config(nc=nc, t=t, d=d, lik=2, seed=91, adapt=0.4, record_accept=1, thin=2, **o)
+    n0 = o.get("m0", nc)
+    x0 = H.x0_tdist(n0, d) * (0.2 if "bound" in o else 1.0)
+    kw = dict(par_min=[-3.0] * d, par_max=[3.5] * d) if "bound" in o else {}
+    monkeypatch.setenv("HB_K1_DENSITY", "1")
+    fused = H.run_device(cfg, "t_distribution", x0, **kw)
+    monkeypatch.setenv("HB_K1_DENSITY", "0")
+    plain = H.run_device(cfg, "t_distribution", x0, **kw)
+    assert fused["timing"][1] < plain["timing"][1]        # one launch fewer per generation: the folded path did run
+    assert np.array_equal(fused["accept"], plain["accept"]) and fused["outlier"] == plain["outlier"]
+    assert np.array_equal(fused["chain"][:, :d, :], plain["chain"][:, :d, :], equal_nan=True) and np.array_equal(fused["xt"], plain["xt"])
+    for key in ("chain", "AR", "CR", "lp", "ll", "lpost") + (("fx",) if cfg.store_fx else ()):
+        np.testing.assert_allclose(fused[key], plain[key], rtol=1e-13, equal_nan=True, err_msg=key)
+    assert 0.02 < fused["accept"].mean() < (0.9 if d <= 128 else 1.0)     # (d = 200 from U[-5, 15]: ll sits on the floor of R/internals.R:19)
 
 
 def test_wide_kernels_bounds_prior_and_zs(hb, oracle, force_wide):
