@@ -219,14 +219,17 @@ def sharded_check(local, rank, world, torch, nc=1 << 16, d=100, gens=30):
             "what": "every rank compares its shard of the sharded run with the same chains of a single-GPU run on its own GPU"}
 
 
-def roofline_for(kname, per_launch_ms, n_local, vt_work, peaks, dmma_peak, acc_rate=0.16):
+def roofline_for(kname, per_launch_ms, n_local, vt_work, peaks, dmma_peak, acc_rate=0.16, density_in_k1=False):
     """algorithmic bytes/flops per chain-generation x chains per launch / launch duration"""
     d = 100
     if kname == "K1":
-        bytes_ = (48 * d + 16) * n_local
+        # gather of 1 + 2 D-bar rows + the proposal row written: 48 d + 16 bytes; with the log-density folded in (built-in
+        # t_distribution, structured evaluation) 8 more for ll -- the 808 bytes per chain the plugin would re-read are not moved
+        bytes_ = (48 * d + 16 + (8 if density_in_k1 else 0)) * n_local
         a = bytes_ / (per_launch_ms * 1e-3) / 1e9
-        return {"kernel": "hb_k1_kernel (proposal)", "bound": "hbm", "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": a / peaks["hbm_gbs"], "peak_source": peaks["source"]}
+        return {"kernel": "hb_k1_pair_kernel<2, true> (proposal + folded t-distribution log-density)" if density_in_k1 else "hb_k1_kernel (proposal)",
+                "bound": "hbm", "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": a / peaks["hbm_gbs"], "peak_source": peaks["source"], "algorithmic_bytes_per_chain": bytes_ / n_local}
     if kname == "K3":
         # steady state (thin >> 1, outside the adaptation period): only accepted rows move -- read xp, write x -- plus
         # the per-chain scalars lp_xp, ll_raw, lpost, id and the accepted lp/ll/lpost stores (DESIGN.md section 4)
@@ -234,6 +237,13 @@ def roofline_for(kname, per_launch_ms, n_local, vt_work, peaks, dmma_peak, acc_r
         a = bytes_ / (per_launch_ms * 1e-3) / 1e9
         return {"kernel": "hb_k3_kernel (accept)", "bound": "hbm", "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": a / peaks["hbm_gbs"], "peak_source": peaks["source"]}
+    if os.environ.get("HB_TDIST_DENSE") != "1" and vt_work[0] == d * d + 3.0 * d:
+        # the t_distribution plugin in its structured evaluation (HB_K1_DENSITY=0 runs it as its own launch): a stream over
+        # the proposals, 8 d + 8 bytes per chain
+        bytes_ = (8 * d + 8) * n_local
+        a = bytes_ / (per_launch_ms * 1e-3) / 1e9
+        return {"kernel": "hb_tdist_struct_kernel (log-density, structured evaluation)", "bound": "hbm", "achieved": a,
+                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": a / peaks["hbm_gbs"], "peak_source": peaks["source"]}
     flops = vt_work[0] * n_local
     a = flops / (per_launch_ms * 1e-3) / 1e12
     return {"kernel": "K2 log-density plugin", "bound": "tensor", "achieved": a, "peak": dmma_peak, "unit": "TFLOP/s",
@@ -583,7 +593,9 @@ def main():
             dom = max(("K1", "K2", "K3"), key=lambda k: kernels.get(k, {"ms_per_launch": 0})["ms_per_launch"])
             pieces = max(1, round(kernels["K1"]["launches"] / (2 * GENS_PER_STEP))) if "K1" in kernels else 1
             chains_per_launch = n_local / pieces
-            roof = roofline_for(dom, kernels[dom]["ms_per_launch"], chains_per_launch, flops, peaks, dm.value, acc_rate)
+            # no K2 launches on a t_distribution workload: the proposal kernel wrote the log-density itself
+            folded = w["target"] == "t_distribution" and "K2" not in kernels
+            roof = roofline_for(dom, kernels[dom]["ms_per_launch"], chains_per_launch, flops, peaks, dm.value, acc_rate, folded)
             # DRAM traffic of the dominant kernel is NOT measured inside this run (that needs ncu): at N = 1 the figure of
             # the committed ncu capture of the same kernel on the same workload is quoted and labelled; never at N > 1,
             # where a launch covers a different number of chains
@@ -593,8 +605,12 @@ def main():
                 pj = json.load(open(prof))
                 roof["traffic"] = pj.get(dom)
                 roof["traffic_source"] = f"not measured in this run: {pj.get('_source', 'profiles/ncu_traffic.json')} (N = 1, {cfg.nc} chains per launch)"
-            roof["all_kernels"] = {k: roofline_for(k, kernels[k]["ms_per_launch"], chains_per_launch, flops, peaks, dm.value, acc_rate)
+            roof["all_kernels"] = {k: roofline_for(k, kernels[k]["ms_per_launch"], chains_per_launch, flops, peaks, dm.value, acc_rate, folded)
                                    for k in ("K1", "K2", "K3") if k in kernels}
+            if folded:
+                roof["log_density"] = ("t_distribution in its structured evaluation (x' C^-1 x = 2 (sum u^2 - (sum u)^2 / (d + 1)), u_i = x_i / sqrt(i): "
+                                       "4 d flops per chain), accumulated by the proposal kernel on the proposal it holds in registers; no K2 launch. "
+                                       "HB_K1_DENSITY=0 runs it as a separate kernel, HB_TDIST_DENSE=1 restores dmvt's triangular product on the fp64 tensor cores")
             roof["kernel_ms_per_launch"] = {k: v["ms_per_launch"] for k, v in kernels.items()}
             roof["launches_per_generation"] = {k: v["launches"] / (2 * GENS_PER_STEP) for k, v in kernels.items()}
             roof["chains_per_launch"] = chains_per_launch
@@ -604,6 +620,12 @@ def main():
             if dg and "K2" in roof["all_kernels"]:
                 roof["all_kernels"]["K2"]["frac_of_cublas_dgemm"] = roof["all_kernels"]["K2"]["achieved"] / dg
             roof["acceptance_rate"] = acc_rate
+            if w["target"] == "t_distribution" and world == 1:
+                # the least a generation has to move (gather + accepted rows + stored rows), against the wall time of a generation
+                single_pass = (8 * cfg.d * 5 + 8 * cfg.d * acc_rate + 8 * (cfg.d + 3) / max(1, cfg.thin)) * cfg.nc
+                gen_s = (steady["ms_per_generation"] if steady else wall / gens * 1e3) * 1e-3
+                roof["generation_vs_single_pass_bound"] = {"bytes": single_pass, "generation_ms": gen_s * 1e3,
+                                                           "frac": single_pass / gen_s / 1e9 / peaks["hbm_gbs"]}
             if world > 1 and cfg.exchange == 2 and "XCHG" in kernels:
                 roof["exchange"] = exchange_roofline(kernels["XCHG"]["ms_per_launch"], kernels["XCHG"]["launches"] / (2 * GENS_PER_STEP),
                                                      n_local, world, cfg.d, acc_rate)
@@ -621,24 +643,32 @@ def main():
         par = dict(initial="user", val_ini=x0, prior={0: "flat", 1: "uniform"}[c2.prior])
         if "par_min" in w2["kw"]:
             par.update(min=w2["kw"]["par_min"], max=w2["kw"]["par_max"], bound="bound")
-        lib().hb_wait_idle()       # the teardown of the sampler above (deferred frees) is not part of the call timed below
-        barrier_sync(torch, world)
-        t0 = time.perf_counter()
-        res = hb.dream_parallel(w2["target"], lik=c2.lik, par_info=par, nc=c2.nc, t=c2.t, d=c2.d, thin=c2.thin,
-                                glue_shape=c2.glue_shape, obs=w2["kw"].get("obs"), forcing=w2["kw"].get("forcing"),
-                                verbose=False, seed=1312, store_fx=False, device=local, distributed=world > 1,
-                                exchange=cfg.exchange if world > 1 else None)
-        barrier_sync(torch, world)
-        e2e_s = max_over_ranks(torch, world, time.perf_counter() - t0)
+        # The call is host-bound outside its device loop (9.5 GB of result pages to fault and fill, x0 through a pinned ring)
+        # and varies from call to call on a shared box (1.6 .. 3 s measured for the same code): three complete calls, every
+        # one reported, the MEDIAN is the value.
+        reps = []
+        d2h = 0
+        for _ in range(3):
+            lib().hb_wait_idle()   # the teardown of the previous sampler (deferred frees) is not part of the call timed below
+            barrier_sync(torch, world)
+            t0 = time.perf_counter()
+            res = hb.dream_parallel(w2["target"], lik=c2.lik, par_info=par, nc=c2.nc, t=c2.t, d=c2.d, thin=c2.thin,
+                                    glue_shape=c2.glue_shape, obs=w2["kw"].get("obs"), forcing=w2["kw"].get("forcing"),
+                                    verbose=False, seed=1312, store_fx=False, device=local, distributed=world > 1,
+                                    exchange=cfg.exchange if world > 1 else None)
+            barrier_sync(torch, world)
+            reps.append(max_over_ranks(torch, world, time.perf_counter() - t0))
+            d2h = res["chain"].nbytes + res["AR"].nbytes + res["CR"].nbytes
+            del res
+        e2e_s = sorted(reps)[1]
         n_steps = (c2.t - 1) / GENS_PER_STEP
         if rank == 0:
             line["e2e"] = {"value": c2.nc * (c2.t - 1) / e2e_s, "unit": UNIT,
                            "h2d_bytes_per_step": world * x0.nbytes / n_steps,
-                           "d2h_bytes_per_step": world * (res["chain"].nbytes + res["AR"].nbytes + res["CR"].nbytes) / n_steps,
-                           "seconds": e2e_s,
+                           "d2h_bytes_per_step": world * d2h / n_steps,
+                           "seconds": e2e_s, "seconds_of_every_call": reps, "statistic": "median of 3 complete calls",
                            "call": "hydrobayes_b200.dream_parallel(...) full run incl. x0 upload and chain fetch"
                                    + (" (distributed=True: every rank uploads x0 and fetches the chain of its shard)" if world > 1 else "")}
-        del res
     if world > 1 and not args.no_extras and not args.quick:
         try:
             c5 = convergence_c5(local, torch, rank=rank, world=world)

@@ -271,8 +271,19 @@ __device__ __forceinline__ void hb_warp_sum2(double& a, double& b, int lane) {
   a = __shfl_sync(0xffffffffu, v, 0);
   b = __shfl_sync(0xffffffffu, v, 16);
 }
-// x' C^-1 x of the reference's t_distribution from s1 = sum u_i, s2 = sum u_i^2, u_i = x_i / sqrt(i)  (hb_targets.cu)
-__device__ __forceinline__ double hb_tdist_rss(double s1, double s2, int d) {
-  return 2.0 * fma(-s1 / (double)(d + 1), s1, s2);
+// ---- the structured evaluation of the reference's t_distribution (hb_targets.cu), shared by every kernel that computes it.
+// The log-density must not depend on which kernel produced it (a shard of a multi-GPU run and the single-GPU run of the same
+// chains may take different kernels and are compared bit for bit), so the order of the sums is fixed here: lane L of a warp
+// accumulates the coordinate pairs k0 = 2 (32 m + L), k0 + 1 for m = 0, 1, ... (hb_tdist_acc, explicit IEEE operations: no
+// contraction the compiler could apply in one kernel and not in another), then hb_warp_sum2, then hb_tdist_logdens.
+__device__ __forceinline__ void hb_tdist_acc(double& s1, double& s2, double x0, double x1, double r0, double r1) {
+  const double u0 = __dmul_rn(x0, r0), u1 = __dmul_rn(x1, r1);          // u = x / sqrt(k)  (callers pass x1 = r1 = 0 past d)
+  s1 = __dadd_rn(s1, __dadd_rn(u0, u1));
+  s2 = __fma_rn(u0, u0, s2); s2 = __fma_rn(u1, u1, s2);
+}
+// x' C^-1 x = 2 (s2 - s1^2 / (d + 1)) from s1 = sum u, s2 = sum u^2, then dmvt's log-density (R/test_t_distribution.R:43)
+__device__ __forceinline__ double hb_tdist_logdens(double s1, double s2, int d, double konst, double df) {
+  const double rss = __dmul_rn(2.0, __fma_rn(-__ddiv_rn(s1, (double)(d + 1)), s1, s2));
+  return __fma_rn(-__dmul_rn(0.5, __dadd_rn(df, (double)d)), log1p(__ddiv_rn(rss, df)), konst);
 }
 #endif  // __CUDACC__

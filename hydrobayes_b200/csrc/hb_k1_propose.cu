@@ -456,7 +456,8 @@ __device__ __forceinline__ fused_gen fused_gen_of(const hb_k3_params& q) {
 // st (adaptation period only, else nullptr): this warp's three statistics rows [3][ITER * 32] in shared memory.
 template <int ITER, bool TAPE, bool CG = false>
 __device__ __forceinline__ void fused_chain_step(const hb_k1_params& p, const hb_k3_params& q, const hb_fused_tdist& td, const fused_gen& fg,
-                                                 const double* __restrict__ rs_s, const k1_headv& hv, int lane, unsigned long long* s_cnt,
+                                                 const double* __restrict__ rs_s, double* __restrict__ xrow_s, const k1_headv& hv, int lane,
+                                                 unsigned long long* s_cnt,
                                                  unsigned& errbits, double* stage, uint64_t* sbar, unsigned& sphase, bool has_chain,
                                                  long long* tm = nullptr, const double* shift_g = nullptr, double* st = nullptr,
                                                  int* s_id = nullptr, const double* logu_pre = nullptr,
@@ -507,20 +508,29 @@ __device__ __forceinline__ void fused_chain_step(const hb_k1_params& p, const hb
     // ---------------- log-density (K2): dmvt, R/test_t_distribution.R:43 ----------------
     // the structured evaluation of the target (hb_targets.cu: hb_tdist_struct_kernel) on the proposal in registers:
     // x' C^-1 x = 2 (sum u^2 - (sum u)^2 / (d + 1)), u_k = xp_k / sqrt(k); rs_s: 1 / sqrt(k) in shared memory, zero past d
+    // (the sums run in the fixed order of hb_tdist_acc -- lane L takes the coordinate pairs 2 (32 m + L) -- so the proposal goes
+    // through this warp's scratch row once)
     if (tm) tm[2] = clock64();
-    double rss;
+    double dens;
     {
+#pragma unroll
+      for (int m = 0; m < ITER; ++m) xrow_s[m * 32 + lane] = xp[m];       // zeros past d
+      __syncwarp();
       double s1 = 0.0, s2 = 0.0;
 #pragma unroll
-      for (int m = 0; m < ITER; ++m) {
-        const double u = xp[m] * rs_s[m * 32 + lane];
-        s1 += u; s2 = fma(u, u, s2);
+      for (int m = 0; m < (ITER + 1) / 2; ++m) {
+        const int k0 = 2 * (m * 32 + lane);
+        if (k0 < ITER * 32) {
+          const double2 x2 = *reinterpret_cast<const double2*>(xrow_s + k0);
+          const double2 r2 = *reinterpret_cast<const double2*>(rs_s + k0);
+          if (k0 < d) hb_tdist_acc(s1, s2, x2.x, x2.y, r2.x, r2.y);
+        }
       }
+      __syncwarp();
       hb_warp_sum2(s1, s2, lane);
-      rss = hb_tdist_rss(s1, s2, d);
+      dens = hb_tdist_logdens(s1, s2, d, td.konst, td.df);
     }
     if (tm) tm[7] = clock64();
-    const double dens = td.konst - 0.5 * (td.df + (double)d) * log1p(rss / td.df);
     if (tm) tm[3] = clock64();
 
     // ---------------- accept / update / store (K3, outside the adaptation period) ----------------
@@ -613,7 +623,8 @@ __global__ void __launch_bounds__(256) hb_fused_small_kernel(const hb_k1_params 
   const int n_wib = blockDim.x >> 5, wib = threadIdx.x >> 5;
   const int stage_rows = (1 + 2 * p.delta) > 4 ? (1 + 2 * p.delta) : 4;
   double* rs_s = fused_smem;
-  double* stage = fused_smem + ITER * 32 + (size_t)wib * stage_rows * p.ldx;
+  double* xrow_s = fused_smem + ITER * 32 * (1 + wib);              // this warp's scratch row
+  double* stage = fused_smem + ITER * 32 * (1 + n_wib) + (size_t)wib * stage_rows * p.ldx;
   unsigned sphase = 0;
   if (lane == 0) { mbar_init(&sbars[wib], 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
   for (int k = threadIdx.x; k < ITER * 32; k += blockDim.x) rs_s[k] = (k < p.d) ? td.rs[k] : 0.0;
@@ -625,7 +636,7 @@ __global__ void __launch_bounds__(256) hb_fused_small_kernel(const hb_k1_params 
   for (long long base = (long long)blockIdx.x * n_wib + wib; base < p.n_local; base += n_warps) {   // one chain per warp and round
     k1_headv hv;
     k1_chain_head<32, TAPE>(p, p.gen, p.tape_g, base, lane, hv, errbits);
-    fused_chain_step<ITER, TAPE>(p, q, td, fused_gen_of(q), rs_s, hv, lane, s_cnt, errbits, stage, &sbars[wib], sphase, true);
+    fused_chain_step<ITER, TAPE>(p, q, td, fused_gen_of(q), rs_s, xrow_s, hv, lane, s_cnt, errbits, stage, &sbars[wib], sphase, true);
   }
   __syncthreads();
   if (threadIdx.x <= 2 * HB_MAX_NCR) {
@@ -649,7 +660,7 @@ cudaError_t launch_fused(const hb_k1_params& p, const hb_k3_params& q, const hb_
   if (blocks < 1) blocks = 1;
   const int stage_rows = (1 + 2 * p.delta) > 4 ? (1 + 2 * p.delta) : 4;
   if (!td.rs || p.d > ITER * 32 || (p.ldx & 1)) return cudaErrorInvalidValue;
-  const size_t smem = ((size_t)ITER * 32 + (size_t)warps * stage_rows * p.ldx) * sizeof(double);
+  const size_t smem = ((size_t)ITER * 32 * (1 + warps) + (size_t)warps * stage_rows * p.ldx) * sizeof(double);
   if (smem > 220 * 1024) return cudaErrorInvalidValue;
   static bool attr_set[2] = {false, false};
   if (!attr_set[tape]) {
@@ -686,7 +697,8 @@ __global__ void __launch_bounds__(256) hb_persist_small_kernel(const hb_k1_param
   const int wib = threadIdx.x >> 5;
   const int stage_rows = (1 + 2 * p0.delta) > 4 ? (1 + 2 * p0.delta) : 4;
   double* rs_s = fused_smem;
-  double* stats = fused_smem + SLD;                                  // warp w: rows [w][0..2]: shifted state, its square, dx^2
+  double* xrow_s = fused_smem + SLD * (1 + wib);                     // this warp's scratch row
+  double* stats = fused_smem + SLD * (1 + n_wib);                    // warp w: rows [w][0..2]: shifted state, its square, dx^2
   double* stage = stats + (size_t)n_wib * 3 * SLD + (size_t)wib * stage_rows * p0.ldx;
   unsigned sphase = 0;
   if (lane == 0) { mbar_init(&sbars[wib], 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
@@ -728,7 +740,7 @@ __global__ void __launch_bounds__(256) hb_persist_small_kernel(const hb_k1_param
     long long tm[8];
     const bool tr = pp.trace && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && i >= pp.i0 + 2 && i < pp.i0 + 6;
     if (tr) tm[4] = clock64();
-    fused_chain_step<ITER, TAPE, true>(p0, q0, td, fg, rs_s, hv, lane, s_cnt, errbits, stage, &sbars[wib], sphase, active,
+    fused_chain_step<ITER, TAPE, true>(p0, q0, td, fg, rs_s, xrow_s, hv, lane, s_cnt, errbits, stage, &sbars[wib], sphase, active,
                                        tr ? tm : nullptr, pp.adapt ? q0.shift : nullptr, pp.adapt ? stats + (size_t)wib * 3 * SLD : nullptr,
                                        &s_ids[wib], TAPE ? nullptr : &logu, &pv);
     if (tr) tm[5] = clock64();
@@ -810,7 +822,7 @@ cudaError_t launch_persist(const hb_k1_params& p, const hb_k3_params& q, const h
   const long long blocks = (p.n_local + warps - 1) / warps;
   const int stage_rows = (1 + 2 * p.delta) > 4 ? (1 + 2 * p.delta) : 4;
   if (!td.rs || p.d > ITER * 32 || (p.ldx & 1)) return cudaErrorInvalidValue;
-  const size_t smem = ((size_t)ITER * 32 * (1 + 3 * warps) + (size_t)warps * stage_rows * p.ldx) * sizeof(double);
+  const size_t smem = ((size_t)ITER * 32 * (1 + 4 * warps) + (size_t)warps * stage_rows * p.ldx) * sizeof(double);
   if (smem > 220 * 1024) return cudaErrorInvalidValue;
   const void* fn = tape ? (const void*)hb_persist_small_kernel<ITER, true> : (const void*)hb_persist_small_kernel<ITER, false>;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1021,6 +1033,8 @@ __global__ void __launch_bounds__(K1_PAIR_WARPS * 32, 2) hb_k1_pair_kernel(const
     __syncwarp();
     double lp_mine = 0.0;
     double td_s1_mine = 0.0, td_s2_mine = 0.0;     // TD: lane c keeps chain c's sums
+    double td_p1 = 0.0, td_p2 = 0.0;               // TD: the previous chain's per-lane partial sums -- their warp reduction (a chain
+                                                   // of dependent shuffles and adds) is issued inside the NEXT chain's Philox pass
 
     const int n_in_batch = (int)((p.n_local - base) < B ? (p.n_local - base) : B);
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
@@ -1044,6 +1058,10 @@ __global__ void __launch_bounds__(K1_PAIR_WARPS * 32, 2) hb_k1_pair_kernel(const
       const double* __restrict__ rowa = rows + ldx;
       const double* __restrict__ rowb = rows + (1 + delta) * ldx;
       double2 xp2[ITER2];
+      if (TD && c > 0) {                       // chain c - 1's density sums: independent of everything this chain does
+        hb_warp_sum2(td_p1, td_p2, lane);
+        if (lane == c - 1) { td_s1_mine = td_p1; td_s2_mine = td_p2; }
+      }
 
       if (snooker) {
         // snooker update, R/internals.R:150-163 with orth_proj :250-263 (rare path: psnooker is 0.1 at most)
@@ -1222,13 +1240,16 @@ __global__ void __launch_bounds__(K1_PAIR_WARPS * 32, 2) hb_k1_pair_kernel(const
           *reinterpret_cast<double2*>(xp_row + k0) = x;
           if (TD) {                                      // u = xp / sqrt(k) (the scale of a coordinate past d is zero)
             const double2 r = lds2(td_rs_s + k0);
-            const double u0 = x.x * r.x, u1 = has1 ? x.y * r.y : 0.0;
-            td_s1 += u0 + u1; td_s2 = fma(u0, u0, td_s2); td_s2 = fma(u1, u1, td_s2);
+            hb_tdist_acc(td_s1, td_s2, x.x, has1 ? x.y : 0.0, r.x, r.y);
           }
         }
       }
       if (p.prior == 1) { lp_part = hb_group_sum<32>(lp_part); if (lane == c) lp_mine = lp_part; }   // lane c keeps chain c's log prior
-      if (TD) { hb_warp_sum2(td_s1, td_s2, lane); if (lane == c) { td_s1_mine = td_s1; td_s2_mine = td_s2; } }
+      if (TD) { td_p1 = td_s1; td_p2 = td_s2; }
+    }
+    if (TD && n_in_batch > 0) {                // the last chain of the batch
+      hb_warp_sum2(td_p1, td_p2, lane);
+      if (lane == n_in_batch - 1) { td_s1_mine = td_p1; td_s2_mine = td_p2; }
     }
     // the scalars of the batch leave as coalesced stores: lane c owns chain base + c
     if (lane < n_in_batch) {
@@ -1238,7 +1259,7 @@ __global__ void __launch_bounds__(K1_PAIR_WARPS * 32, 2) hb_k1_pair_kernel(const
       p.lp_xp[base + lane] = lp;
       p.id_out[base + lane] = (heads[lane * hw] >> 8) & 0xff;
       if (TD) {                                                          // dmvt, R/test_t_distribution.R:43 (hb_tdist_struct_kernel)
-        const double v = p.td_konst - 0.5 * (p.td_df + (double)d) * log1p(hb_tdist_rss(td_s1_mine, td_s2_mine, d) / p.td_df);
+        const double v = hb_tdist_logdens(td_s1_mine, td_s2_mine, d, p.td_konst, p.td_df);
         if (p.td_fx) p.td_fx[base + lane] = v;
         p.td_ll[base + lane] = (p.td_lik == 1) ? log(v) : v;
       }

@@ -160,8 +160,9 @@ __global__ void __launch_bounds__(256, (KB > 25 ? 2 : 3)) hb_tdist_dmma_kernel(c
 // kernel is a stream over the proposals (808 bytes per point) instead of a d x d product.  Same value to rounding: against
 // the long-double restatement of dmvt the log-density agrees to 5e-16 relative at d = 100 (tests: every plugin test runs both
 // evaluations).  Cancellation is bounded: (sum u)^2 <= d sum u^2, so the result is at least 2 sum u^2 / (d + 1).
-// rs[i] = 1 / sqrt(i + 1), correctly rounded on the host.  One warp per point; hb_tdist_rss is shared with the proposal
-// kernels that fold the density into their own sweep (hb_k1_propose.cu).
+// rs[i] = 1 / sqrt(i + 1), correctly rounded on the host.  One warp per point; hb_tdist_acc / hb_tdist_logdens (hb_common.cuh)
+// are shared with the proposal kernels that fold the density into their own sweep (hb_k1_propose.cu) and fix the order of
+// the sums, so the value does not depend on the kernel that produced it.
 __global__ void hb_tdist_struct_kernel(const double* __restrict__ X, long long n, int d, int ldx, const double* __restrict__ rs,
                                        double konst, double df, int lik, double* __restrict__ ll, double* __restrict__ fx) {
   const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -170,13 +171,13 @@ __global__ void hb_tdist_struct_kernel(const double* __restrict__ X, long long n
   for (long long row = warp_id; row < n; row += n_warps) {
     const double* xr = X + row * (long long)ldx;
     double s1 = 0.0, s2 = 0.0;
-    for (int k = lane; k < d; k += 32) {
-      const double u = xr[k] * rs[k];
-      s1 += u; s2 = fma(u, u, s2);
+    for (int k0 = 2 * lane; k0 < d; k0 += 64) {                            // the fixed order of hb_tdist_acc: pairs 2 (32 m + lane)
+      const bool has1 = k0 + 1 < d;
+      hb_tdist_acc(s1, s2, xr[k0], has1 ? xr[k0 + 1] : 0.0, rs[k0], has1 ? rs[k0 + 1] : 0.0);
     }
     hb_warp_sum2(s1, s2, lane);
     if (lane == 0) {
-      const double v = konst - 0.5 * (df + (double)d) * log1p(hb_tdist_rss(s1, s2, d) / df);   // dmvt, R/test_t_distribution.R:43
+      const double v = hb_tdist_logdens(s1, s2, d, konst, df);             // dmvt, R/test_t_distribution.R:43
       if (fx) fx[row] = v;
       ll[row] = (lik == 1) ? log(v) : v;
     }

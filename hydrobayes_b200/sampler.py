@@ -440,7 +440,9 @@ def _drive(sweep, fun, extra, lik, par_info, nc, t, d, burnin, adapt, updateInte
             # candidate population zt (R/dream_parallel.R:316 draws the reference proposals' partners from all of zt)
             cfg.exchange = (A.HB_EXCHANGE_ALLGATHER if mt > 1 else A.HB_EXCHANGE_DELTA) if exchange is None else exchange
     n_shard = shard_range(nc, rank, world)[1] if world > 1 else None
+    _t_in = time.perf_counter()
     with Sampler(cfg, device) as s:
+        _timing_note("py: hb_create", _t_in)
         if par_info.get("min") is not None and par_info.get("max") is not None:
             s.set_bounds(par_info["min"], par_info["max"])
         if cfg.prior == A.HB_PRIOR_NORMAL:
@@ -460,6 +462,7 @@ def _drive(sweep, fun, extra, lik, par_info, nc, t, d, burnin, adapt, updateInte
         if world > 1:
             uid = None if cfg.exchange == A.HB_EXCHANGE_DELTA else broadcast_unique_id(lambda: _unique_id(s.L), rank)
             s.comm_init(rank, world, uid)
+        _timing_note("py: ... target / communicator set up", _t_in)
         x0 = prior_sample(par_info, d, n0, rng)   # same seed on every rank: every rank holds the whole initial population
         if x0.shape[0] != n0:
             raise ValueError(f"initial sample has {x0.shape[0]} rows, expected {n0}")
@@ -470,12 +473,18 @@ def _drive(sweep, fun, extra, lik, par_info, nc, t, d, burnin, adapt, updateInte
             s.set_tape(tape.struct(), keepalive=tape)
         step = int(slice_generations) if slice_generations else (max(1, t // 50) if verbose else t)
         chain_buf, toucher = s.alloc_chain(n_shard)                 # chain <- array(NA, ...) before the loop, :201-203
+        _timing_note("py: ... initial population uploaded, result allocated", _t_in)
         done = 1
+        _tn = _timing_note
+        _t0 = time.perf_counter()
         while done < t:
             done = s.run(step)          # the R driver ticks txtProgressBar / checks interrupts between slices
+        _tn("py: generation loop", _t0); _t0 = time.perf_counter()
         if toucher is not None:
             toucher.join()
+        _tn("py: wait for the pre-fault thread", _t0); _t0 = time.perf_counter()
         chain = s.fetch_chain(n_shard, out=chain_buf)   # sharded: this rank's chains, chain[out_t, d+3, nc/world]
+        _tn("py: fetch_chain", _t0)
         _unpin_later(chain_buf)
         ar, cr = s.fetch_ar_cr()
         out = {"chain": chain, "rank": rank, "world": world}
@@ -501,8 +510,17 @@ def _drive(sweep, fun, extra, lik, par_info, nc, t, d, burnin, adapt, updateInte
         loop_ms, launches = s.timing()
         out["device_loop_seconds"] = loop_ms * 1e-3
         out["gpu_launches"] = launches
+        _timing_note("py: ... results fetched", _t_in)
+    _timing_note("py: ... handle closed (total)", _t_in)
     out["runtime"] = time.time() - timea
     return out
+
+
+def _timing_note(what, t0):
+    """HB_TIMING=1: host-side phases of the drivers on stderr (next to the library's own `[hb timing]` lines)"""
+    if os.environ.get("HB_TIMING") == "1":
+        import sys
+        print(f"[hb timing] {what:38s} {(time.perf_counter() - t0) * 1e3:8.1f} ms", file=sys.stderr, flush=True)
 
 
 def _outlier_list(pairs, cfg, sweep):

@@ -210,8 +210,8 @@ def test_wide_kernels_native(hb, oracle, force_wide, d, nc):
 def test_density_folded_into_the_proposal_kernel(hb, force_wide, monkeypatch, d, nc, opts):
     # large-population path with the built-in t_distribution: hb_k1_pair_kernel<., TD> accumulates the structured quadratic form
     # of every proposal in its own sweep and writes ll (no plugin launch), against the two-kernel path (HB_K1_DENSITY=0:
-    # hb_k1_pair_kernel -> hb_tdist_struct_kernel).  Same draws and proposals bit for bit; the two sum u and u^2 over the
-    # coordinates in different orders, so ll agrees to rounding (1e-13), and with it every decision of these runs.
+    # hb_k1_pair_kernel -> hb_tdist_struct_kernel).  Every kernel that evaluates the target sums in the same fixed order
+    # (hb_tdist_acc in hb_common.cuh), so every output is bit-identical.
     o = dict(opts)
     t = o.pop("t", 70)
     cfg = A.default_config(nc=nc, t=t, d=d, lik=2, seed=91, adapt=0.4, record_accept=1, thin=2, **o)
@@ -223,10 +223,9 @@ def test_density_folded_into_the_proposal_kernel(hb, force_wide, monkeypatch, d,
     monkeypatch.setenv("HB_K1_DENSITY", "0")
     plain = H.run_device(cfg, "t_distribution", x0, **kw)
     assert fused["timing"][1] < plain["timing"][1]        # one launch fewer per generation: the folded path did run
-    assert np.array_equal(fused["accept"], plain["accept"]) and fused["outlier"] == plain["outlier"]
-    assert np.array_equal(fused["chain"][:, :d, :], plain["chain"][:, :d, :], equal_nan=True) and np.array_equal(fused["xt"], plain["xt"])
-    for key in ("chain", "AR", "CR", "lp", "ll", "lpost") + (("fx",) if cfg.store_fx else ()):
-        np.testing.assert_allclose(fused[key], plain[key], rtol=1e-13, equal_nan=True, err_msg=key)
+    assert fused["outlier"] == plain["outlier"]
+    for key in ("chain", "accept", "AR", "CR", "xt", "lp", "ll", "lpost") + (("fx",) if cfg.store_fx else ()):
+        assert np.array_equal(fused[key], plain[key], equal_nan=True), key
     assert 0.02 < fused["accept"].mean() < (0.9 if d <= 128 else 1.0)     # (d = 200 from U[-5, 15]: ll sits on the floor of R/internals.R:19)
 
 

@@ -1,0 +1,5 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" || exit 1
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
+python tools/kernel_times.py C4 2>&1 | tail -2
+python tools/c2_probe.py 2>&1 | tail -2
