@@ -44,7 +44,7 @@ enum {
   HB_ERR_UNKNOWN_TARGET = 5, /* name not in the device plugin registry (get(fun) would fail in R) */
   HB_ERR_STATE = 6,        /* call order (e.g. hb_run before hb_set_initial) */
   HB_ERR_NCCL = 7,
-  HB_ERR_UNSUPPORTED = 8   /* a combination that is not on the device path (e.g. mt > 1 on several GPUs) */
+  HB_ERR_UNSUPPORTED = 8   /* a combination that is not on the device path (e.g. mt > 1 with the delta exchange) */
 };
 
 /* sweep: which reference driver's data dependence to reproduce */
@@ -96,7 +96,7 @@ typedef struct hb_config {
   int32_t past_sample;     /* DREAM(ZS) archive sampling (dream_parallel only) */
   int64_t m0;              /* 0 = reference default (10*d if past_sample else nc) */
   int32_t archive_update;  /* 0 = reference default (10 if past_sample else never) */
-  int32_t mt;              /* multi-try (MT-DREAM, R/dream_parallel.R:295-341); synchronous sweep, one GPU */
+  int32_t mt;              /* multi-try (MT-DREAM, R/dream_parallel.R:295-341); synchronous sweep; several GPUs: HB_EXCHANGE_ALLGATHER */
   double psnooker;         /* 0 */
   double glue_shape;       /* lik == 31 */
   int32_t rng_mode;        /* HB_RNG_* */
