@@ -608,10 +608,10 @@ __device__ __forceinline__ void fused_chain_step(const hb_k1_params& p, const hb
 // XP / ll round trips through L2.  The synchronous sweep (R/dream_parallel.R:269, all proposals from the generation-start
 // state) is kept without a grid-wide barrier by double buffering the population: every chain reads partners from X and
 // writes its post-generation row into Xout (its proposal if accepted, its old row otherwise); the host swaps the buffers.
-// Only outside the adaptation period (the std_x / jump statistics need the whole post-update population).
-//   proposal      k1_chain_jump -- the same code, draw for draw, as hb_k1_kernel<32, ITER>
-//   log-density   z_n = sum_{k <= n} xp_k W[k][n], rss = sum z_n^2: the summation order of hb_tdist_fma_kernel (lane owns
-//                 columns n = 32 m + lane, k ascending); xp and W staged in shared memory (W by bulk TMA, once per CTA)
+// This kernel runs outside the adaptation period only (the persistent kernel below also covers the adaptation period).
+//   proposal      k1_chain_head + k1_chain_body -- the same code, draw for draw, as hb_k1_kernel<32, ITER>
+//   log-density   the structured evaluation of the built-in t_distribution (hb_targets.cu) on the proposal in registers,
+//                 summed in the fixed order of hb_tdist_acc: bit-identical to the plugin's value
 //   accept        the non-adaptation path of hb_k3_kernel (R/internals.R:239-241, R/dream_parallel.R:348-366, 386-394)
 // ------------------------------------------------------------------------------------------------------------------
 template <int ITER, bool TAPE>
@@ -677,11 +677,14 @@ cudaError_t launch_fused(const hb_k1_params& p, const hb_k3_params& q, const hb_
 // ------------------------------------------------------------------------------------------------------------------
 // Persistent generation loop for small populations (BASELINE C2 is latency bound: 20 000 strictly dependent generations of
 // 1 024 chains).  ONE cooperative launch runs all generations of a slice that lie behind the adaptation
-// period: one warp per chain, W staged in shared memory once for the whole run, the population double buffered (generation
-// i reads buffer A and writes B, i + 1 the other way round), and a grid-wide barrier per generation in place of a kernel
-// boundary -- every CTA arrives on a counter, CTA 0 waits for all of them, folds the AR / CR bookkeeping at
-// updateInterval boundaries (R/dream_parallel.R:425-433; the non-adaptation part of hb_finalize_kernel), then releases
-// the others.  The per-chain step is fused_chain_step, i.e. draw for draw and operation for operation the
+// period -- or, with pp.adapt, the generations of the adaptation period up to the next updateInterval boundary: one warp per
+// chain, the population double buffered (generation i reads buffer A and writes B, i + 1 the other way round), and a
+// grid-wide barrier per generation in place of a kernel boundary -- every CTA arrives on a counter, then works out what
+// generation i + 1 needs that does not depend on the population (the per-chain draws, the crossover subspace, the logarithm
+// of the Metropolis uniform) while the others arrive; outside the adaptation period CTA 0 folds the AR / CR bookkeeping at
+// updateInterval boundaries (R/dream_parallel.R:425-433; the non-adaptation part of hb_finalize_kernel) before it releases
+// the others; inside it every CTA parks its std_x / jump statistic sums of the generation in a slot and the finalize kernels
+// fold the slots after the launch.  The per-chain step is fused_chain_step, i.e. draw for draw and operation for operation the
 // one-launch-per-generation kernel; the population is read with L2-coherent loads (other CTAs rewrite it between barriers).
 // ------------------------------------------------------------------------------------------------------------------
 template <int ITER, bool TAPE>
