@@ -704,6 +704,22 @@ def main():
                 finally:
                     for k in env:
                         os.environ.pop(k, None)
+        if args.workload == "C4":
+            # The same workload with the target evaluated by dmvt's own route (chol(C)^-1, triangular product on the fp64 tensor
+            # cores, its own launch) and with the structured evaluation as a separate launch: what the default path -- the
+            # structured form folded into the proposal kernel -- is to be read against.
+            for label, env, what in (("C4_dense_log_density", {"HB_TDIST_DENSE": "1"}, "K1 -> hb_tdist_dmma_kernel -> K3"),
+                                     ("C4_structured_log_density_own_launch", {"HB_K1_DENSITY": "0"}, "K1 -> hb_tdist_struct_kernel -> K3")):
+                os.environ.update(env)
+                try:
+                    f = quick_rate("C4", local, torch, gens=60, warm=110)
+                    others[label] = {"path": what, "enable": " ".join(f"{k}={v}" for k, v in env.items()),
+                                     **{k: f[k] for k in ("value", "us_per_generation", "device_us_per_generation", "gpu_launches", "generations", "note")}}
+                except Exception as e:
+                    others[label] = {"error": repr(e)}
+                finally:
+                    for k in env:
+                        os.environ.pop(k, None)
         try:
             others["C5"] = convergence_c5(local, torch)
         except Exception as e:

@@ -164,22 +164,29 @@ __global__ void __launch_bounds__(256, (KB > 25 ? 2 : 3)) hb_tdist_dmma_kernel(c
 // are shared with the proposal kernels that fold the density into their own sweep (hb_k1_propose.cu) and fix the order of
 // the sums, so the value does not depend on the kernel that produced it.
 __global__ void hb_tdist_struct_kernel(const double* __restrict__ X, long long n, int d, int ldx, const double* __restrict__ rs,
-                                       double konst, double df, int lik, double* __restrict__ ll, double* __restrict__ fx) {
+                                       double konst, double df, int lik, int batch, double* __restrict__ ll, double* __restrict__ fx) {
+  // a warp takes `batch` (<= 32) consecutive points: the sums of point c stay with lane c, so the log1p of the batch runs
+  // lane-parallel and ll leaves as one coalesced store (one point per warp would spend most of its time in lane 0's log1p)
   const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const int lane = threadIdx.x & 31;
-  for (long long row = warp_id; row < n; row += n_warps) {
-    const double* xr = X + row * (long long)ldx;
-    double s1 = 0.0, s2 = 0.0;
-    for (int k0 = 2 * lane; k0 < d; k0 += 64) {                            // the fixed order of hb_tdist_acc: pairs 2 (32 m + lane)
-      const bool has1 = k0 + 1 < d;
-      hb_tdist_acc(s1, s2, xr[k0], has1 ? xr[k0 + 1] : 0.0, rs[k0], has1 ? rs[k0 + 1] : 0.0);
+  for (long long base = warp_id * batch; base < n; base += n_warps * batch) {
+    const int nb = (int)((n - base) < batch ? (n - base) : batch);
+    double m1 = 0.0, m2 = 0.0;
+    for (int c = 0; c < nb; ++c) {
+      const double* xr = X + (base + c) * (long long)ldx;
+      double s1 = 0.0, s2 = 0.0;
+      for (int k0 = 2 * lane; k0 < d; k0 += 64) {                          // the fixed order of hb_tdist_acc: pairs 2 (32 m + lane)
+        const bool has1 = k0 + 1 < d;
+        hb_tdist_acc(s1, s2, xr[k0], has1 ? xr[k0 + 1] : 0.0, rs[k0], has1 ? rs[k0 + 1] : 0.0);
+      }
+      hb_warp_sum2(s1, s2, lane);
+      if (lane == c) { m1 = s1; m2 = s2; }
     }
-    hb_warp_sum2(s1, s2, lane);
-    if (lane == 0) {
-      const double v = hb_tdist_logdens(s1, s2, d, konst, df);             // dmvt, R/test_t_distribution.R:43
-      if (fx) fx[row] = v;
-      ll[row] = (lik == 1) ? log(v) : v;
+    if (lane < nb) {
+      const double v = hb_tdist_logdens(m1, m2, d, konst, df);             // dmvt, R/test_t_distribution.R:43
+      if (fx) fx[base + lane] = v;
+      ll[base + lane] = (lik == 1) ? log(v) : v;
     }
   }
 }
@@ -340,10 +347,14 @@ int tdist_launch(void* ctx, const double* x, int64_t n, int d, int ldx, double* 
   cudaStream_t st = (cudaStream_t)stream;
   if (n <= 0) return HB_OK;
   if (!c->dense) {
-    long long blocks = (n + 7) / 8;
-    const long long cap = (long long)c->sm_count * 16;
+    const long long resident_warps = (long long)c->sm_count * 64;            // points per warp: as many as keep every warp of the device busy
+    long long batch = n / resident_warps;
+    batch = batch < 1 ? 1 : batch > 32 ? 32 : batch;
+    const long long warps = (n + batch - 1) / batch;
+    long long blocks = (warps + 7) / 8;
+    const long long cap = (long long)c->sm_count * 8;
     if (blocks > cap) blocks = cap;
-    hb_tdist_struct_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, n, c->d, ldx, c->rs_dev, c->konst, c->df, c->lik, ll, fx);
+    hb_tdist_struct_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, n, c->d, ldx, c->rs_dev, c->konst, c->df, c->lik, (int)batch, ll, fx);
     return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
   }
   if (!c->KB || c->force_fma) {
