@@ -14,6 +14,9 @@
 #include <mutex>
 #include <atomic>
 #include <chrono>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <cstdlib>
 #include <string>
 #include <thread>
@@ -158,6 +161,28 @@ void timing_note(const char* what, double seconds, double bytes = 0) {
   if (!on) return;
   if (bytes > 0) fprintf(stderr, "[hb timing] %-14s %8.1f ms  %6.2f GB  %6.1f GB/s\n", what, seconds * 1e3, bytes / 1e9, bytes / 1e9 / seconds);
   else fprintf(stderr, "[hb timing] %-14s %8.1f ms\n", what, seconds * 1e3);
+}
+
+// Copy into the caller's (pageable, pre-faulted) result array with non-temporal stores: the destination is written once and
+// not read again here, so the read-for-ownership of every destination line a plain memcpy of this size would do (a thread's
+// share of a chunk is below glibc's non-temporal threshold) is a third of the copy's memory traffic -- and the fetch of a
+// 9.5 GB result is bound by the host's memory bandwidth (DMA into the ring + this copy), not by PCIe.
+void stream_copy(char* dst, const char* src, size_t n) {
+#if defined(__SSE2__)
+  while (n >= 8 && (reinterpret_cast<uintptr_t>(dst) & 15)) { memcpy(dst, src, 8); dst += 8; src += 8; n -= 8; }
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    size_t i = 0;
+    for (; i + 64 <= n; i += 64) {
+      const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i)), b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 16));
+      const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 32)), d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 48));
+      _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), a); _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 16), b);
+      _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 32), c); _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 48), d);
+    }
+    _mm_sfence();
+    dst += i; src += i; n -= i;
+  }
+#endif
+  if (n) memcpy(dst, src, n);
 }
 
 // Pinned host ring of the upload / fetch pipelines.  cudaHostAlloc of 128 MB costs ~0.1 s, more than the transfer of a
@@ -1824,7 +1849,7 @@ int hb_fetch_chain_rows(hb_handle* h, int64_t row0, int64_t nrows, double* out) 
         const long long c0 = k * chunk, ncs = std::min(chunk, nl - c0);
         const size_t bytes = per_chain * (size_t)ncs;
         const size_t lo = bytes / n_thr * t & ~(size_t)63, hi = (t == n_thr - 1) ? bytes : (bytes / n_thr * (t + 1) & ~(size_t)63);
-        if (hi > lo) memcpy(outb + (size_t)c0 * per_chain + lo, pin + (size_t)(k & 1) * half + lo, hi - lo);
+        if (hi > lo) stream_copy(outb + (size_t)c0 * per_chain + lo, pin + (size_t)(k & 1) * half + lo, hi - lo);
         done[(size_t)k].fetch_add(1, std::memory_order_release);
       }
     });
