@@ -193,11 +193,15 @@ __global__ void __launch_bounds__(256, 3) hb_k3_wide_kernel(const hb_k3_params p
 
   double* ring = reinterpret_cast<double*>(k3_smem + (size_t)slot * warp_smem);          // [K3_SLOTS][ldx]
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)K3_SLOTS * ldx);           // [K3_SLOTS]
-  double* acc_all = reinterpret_cast<double*>(k3_smem + acc_off);                        // [n_slots][E] (stats only)
-  double* acc = acc_all + (size_t)slot * E;
+  // jump-statistic accumulators Q[id][k] of this warp (stats only).  The column sums s1 / s2 live in registers and are parked
+  // in the warp's first two ring rows at the end: 2.4 KB of accumulators per warp instead of 4 KB is what lets a third CTA
+  // share the SM (the adaptation-period launch is bound by the rows it keeps in flight per SM, profiles/r02b_k3_adaptation_full.txt)
+  const int EQ = nCR * d;
+  double* acc_all = reinterpret_cast<double*>(k3_smem + acc_off);                        // [n_slots][EQ]
+  double* acc = acc_all + (size_t)slot * EQ;
 
   if (threadIdx.x <= 2 * HB_MAX_NCR) s_cnt[threadIdx.x] = 0ull;
-  if (stats) for (int e = threadIdx.x; e < n_slots * E; e += blockDim.x) acc_all[e] = 0.0;
+  if (stats) for (int e = threadIdx.x; e < n_slots * EQ; e += blockDim.x) acc_all[e] = 0.0;
   if (lane == 0) {
 #pragma unroll
     for (int q = 0; q < K3_SLOTS; ++q) mbar_init(&bars[q], 1);
@@ -319,7 +323,7 @@ __global__ void __launch_bounds__(256, 3) hb_k3_wide_kernel(const hb_k3_params p
                 if (adapt) {
                   const double dx = xn - rowv[ldx + k];                 // R/dream_parallel.R:357 (after bound handling)
                   if (p.write_dx) p.XP_rw[jr * (long long)ldx + k] = dx;
-                  else acc[(2 + id_c) * d + k] += dx * dx;
+                  else acc[id_c * d + k] += dx * dx;
                 }
               } else {
                 if (copy_all) p.Xout[j * (long long)ldx + k] = xn;
@@ -344,18 +348,24 @@ __global__ void __launch_bounds__(256, 3) hb_k3_wide_kernel(const hb_k3_params p
   if (lane == 0) tma_store_wait<0>();                                   // all rows have left before the block retires
 
   if (stats) {
+    __syncwarp();                                                       // lane 0's wait: no bulk copy touches the ring any more
 #pragma unroll
     for (int m = 0; m < ITER; ++m) {
       const int k = m * 32 + lane;
-      if (k < d) { acc[k] = s1[m]; acc[d + k] = s2[m]; }
+      if (k < d) { ring[k] = s1[m]; ring[ldx + k] = s2[m]; }
     }
   }
   __syncthreads();
   if (stats) {
-    // fixed-order reduction over the block's warps -> one partial row per block
+    // fixed-order reduction over the block's warps -> one partial row per block: [s1 | s2 | Q[0] .. Q[nCR-1]]
     for (int e = threadIdx.x; e < E; e += blockDim.x) {
       double s = 0.0;
-      for (int q = 0; q < n_slots; ++q) s += acc_all[(size_t)q * E + e];
+      if (e < 2 * d) {
+        const int off = e < d ? e : ldx + (e - d);
+        for (int q = 0; q < n_slots; ++q) s += reinterpret_cast<const double*>(k3_smem + (size_t)q * warp_smem)[off];
+      } else {
+        for (int q = 0; q < n_slots; ++q) s += acc_all[(size_t)q * EQ + (e - 2 * d)];
+      }
       p.partials[(size_t)blockIdx.x * E + e] = s;
     }
   }
@@ -373,7 +383,7 @@ __global__ void __launch_bounds__(256, 3) hb_k3_wide_kernel(const hb_k3_params p
 template <int ITER>
 cudaError_t launch_wide(const hb_k3_params& p, int sm_count, int* nblocks_out, size_t* smem_out, cudaStream_t st) {
   const size_t per_warp_ring = (k3_warp_smem_bytes(p.ldx) + 15) & ~(size_t)15;
-  const size_t per_warp_acc = (size_t)(p.nCR + 2) * p.d * sizeof(double);
+  const size_t per_warp_acc = (size_t)p.nCR * p.d * sizeof(double);       // Q[id][k]; s1 / s2 are parked in the ring
   int warps = 8;
   while (warps > 1 && (per_warp_ring + per_warp_acc) * warps > 100 * 1024) warps >>= 1;
   if ((per_warp_ring + per_warp_acc) * warps > 220 * 1024) return cudaErrorInvalidValue;
