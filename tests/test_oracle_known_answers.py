@@ -62,6 +62,47 @@ def test_t_distribution_vs_scipy(oracle):
         np.testing.assert_allclose(got, np.atleast_1d(ref), rtol=1e-12)
 
 
+@pytest.mark.parametrize("d", [1, 2, 3, 17, 64, 100, 130])
+def test_t_distribution_structured_identity(oracle, d):
+    """The device evaluates the reference's t_distribution in structured form (hydrobayes_b200/csrc/hb_targets.cu,
+    hb_common.cuh: hb_tdist_acc / hb_warp_sum2 / hb_tdist_logdens): C = S (I/2 + 11'/2) S, S = diag(sqrt(i))
+    (R/test_t_distribution.R:32-40), so by Sherman-Morrison x' C^-1 x = 2 (sum u^2 - (sum u)^2 / (d + 1)), u_i = x_i / sqrt(i),
+    and log|C| = sum(log i) - d log 2 + log(d + 1).  Restated here in numpy with the device's order of operations (lane L of a
+    warp takes the coordinate pairs 2 (32 m + L); the two halves of the warp are added first, then strides 8, 4, 2, 1) and
+    checked against the oracle's dmvt (Cholesky + triangular solve) and against scipy's multivariate_t: the identity is
+    pinned on the CPU, the GPU tests pin the kernels to it."""
+    from scipy.stats import multivariate_t
+    rng = np.random.default_rng(100 + d)
+    x = np.concatenate([rng.uniform(-5, 15, size=(64, d)), rng.normal(size=(32, d)) * np.sqrt(np.arange(1, d + 1)),
+                        np.zeros((1, d)), np.outer([1.0, -3.7, 30.0], np.sqrt(np.arange(1, d + 1)))])   # last rows: worst case for cancellation
+    rs = 1.0 / np.sqrt(np.arange(1, d + 1, dtype=np.float64))
+    df = 60.0
+    ll = np.empty(x.shape[0])
+    logdet = np.sum(np.log(np.arange(1, d + 1))) - d * math.log(2.0) + math.log(d + 1.0)
+    konst = math.lgamma((d + df) / 2) - (math.lgamma(df / 2) + 0.5 * logdet + d / 2 * math.log(math.pi * df))
+    for r, row in enumerate(x):
+        s1 = np.zeros(32); s2 = np.zeros(32)
+        for lane in range(32):
+            for k0 in range(2 * lane, d, 64):
+                u0 = row[k0] * rs[k0]; u1 = row[k0 + 1] * rs[k0 + 1] if k0 + 1 < d else 0.0
+                s1[lane] = s1[lane] + (u0 + u1)
+                s2[lane] = s2[lane] + u0 * u0                      # (the device uses fused multiply-adds here: one rounding less)
+                s2[lane] = s2[lane] + u1 * u1
+        def tree(v):
+            v = v[:16] + v[16:]
+            for o in (8, 4, 2, 1):
+                v = v[:o] + v[o:2 * o]
+            return v[0]
+        a, b = tree(s1), tree(s2)
+        rss = 2.0 * (b - a / (d + 1) * a)
+        ll[r] = konst - 0.5 * (df + d) * math.log1p(rss / df)
+    np.testing.assert_allclose(ll, oracle.tdist_logpdf(x), rtol=2e-13)
+    i = np.arange(1, d + 1)
+    Cm = (0.5 * np.eye(d) + 0.5) * np.sqrt(np.outer(i, i))
+    np.testing.assert_allclose(ll, np.atleast_1d(multivariate_t(loc=np.zeros(d), shape=Cm, df=60).logpdf(x)), rtol=1e-12)
+    assert abs(np.linalg.slogdet(Cm)[1] - logdet) < 1e-9 * max(1.0, abs(logdet))
+
+
 def test_hydromodel(oracle):
     # R/test_HydroModel.R:17-36
     y = oracle.hydromodel([0, 1, 2, 0, 5], 0.5)
