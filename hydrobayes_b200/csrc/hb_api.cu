@@ -2104,4 +2104,65 @@ int hb_logdensity(const char* name, int32_t lik, const double* data, const int64
   return HB_OK;
 }
 
+// ---- log-density session: the same evaluation as hb_logdensity with the plugin context and the device buffers kept ----
+// between calls (rwm() / am() / am_sd() evaluate the target once per iteration, R/rwm.R:42: per-call setup would dominate).
+struct hb_density {
+  const hb_target_vtable* vt = nullptr;
+  void* ctx = nullptr;
+  bool hydro = false;
+  int32_t d = 0;
+  int ldx = 0;
+  int64_t cap = 0;
+  double *xc = nullptr, *xr = nullptr, *ll = nullptr, *fx = nullptr;
+};
+
+int hb_density_open(const char* name, int32_t lik, const double* data, const int64_t* dims, int ndims, const double* obs,
+                    int64_t n_obs, double glue_shape, int32_t d, int64_t max_n, hb_density** out, char* err, int errlen) {
+  if (!name || !out || d < 1 || max_n < 1) { set_msg(err, errlen, "hb_density_open: bad arguments"); return HB_ERR_INVALID; }
+  *out = nullptr;
+  if (hb_device_count() < 1) { set_msg(err, errlen, "no CUDA device is available and there is no CPU fallback"); return HB_ERR_NO_DEVICE; }
+  const hb_target_vtable* vt = hb_find_target(name);
+  if (!vt) { set_msg(err, errlen, "unknown target"); return HB_ERR_UNKNOWN_TARGET; }
+  hb_density* s = new hb_density();
+  s->vt = vt; s->d = d; s->cap = max_n; s->ldx = d == 1 ? 1 : (d + 3) & ~3;
+  s->hydro = strcmp(name, "HydroModel") == 0 || strcmp(name, "fun_wrap_glue") == 0;
+  int rc = vt->init(&s->ctx, d, lik, data, dims, ndims, obs, n_obs, glue_shape, err, errlen);
+  if (rc) { delete s; return rc; }
+  const bool ok = cudaMalloc((void**)&s->xc, (size_t)max_n * d * 8) == cudaSuccess &&
+                  cudaMalloc((void**)&s->xr, (size_t)max_n * s->ldx * 8) == cudaSuccess &&
+                  cudaMalloc((void**)&s->ll, (size_t)max_n * 8) == cudaSuccess && cudaMalloc((void**)&s->fx, (size_t)max_n * 8) == cudaSuccess;
+  if (!ok) { set_msg(err, errlen, cudaGetErrorString(cudaGetLastError())); hb_density_close(s); return HB_ERR_CUDA; }
+  *out = s;
+  return HB_OK;
+}
+
+int hb_density_eval(hb_density* s, const double* x, int64_t n, double* ll_out, double* fx_out, char* err, int errlen) {
+  if (!s || !x || !ll_out || n < 1 || n > s->cap) { set_msg(err, errlen, "hb_density_eval: bad arguments (1 <= n <= max_n of the session)"); return HB_ERR_INVALID; }
+  const int32_t d = s->d;
+  int rc = HB_OK;
+  bool ok = cudaMemcpy(s->xc, x, (size_t)n * d * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+  ok = ok && cudaMemset(s->fx, 0, (size_t)n * 8) == cudaSuccess;
+  ok = ok && hb_launch_colmajor_to_rows(s->xc, n, 0, n, d, s->ldx, s->xr, nullptr) == cudaSuccess;
+  if (ok) rc = s->vt->launch(s->ctx, s->xr, n, d, s->ldx, s->ll, s->fx, nullptr);
+  ok = ok && rc == HB_OK && cudaDeviceSynchronize() == cudaSuccess;
+  ok = ok && cudaMemcpy(ll_out, s->ll, (size_t)n * 8, cudaMemcpyDeviceToHost) == cudaSuccess;
+  if (ok && fx_out) ok = cudaMemcpy(fx_out, s->fx, (size_t)n * 8, cudaMemcpyDeviceToHost) == cudaSuccess;
+  if (!ok) { set_msg(err, errlen, rc ? "target launch failed" : cudaGetErrorString(cudaGetLastError())); return rc ? rc : HB_ERR_CUDA; }
+  if (s->hydro && hb_hydro_poll_err(s->ctx)) { set_msg(err, errlen, "Argument 'param' has to be >= zero!"); return HB_ERR_INVALID; }
+  for (int64_t i = 0; i < n; ++i) {                         // calc_ll floor and check, R/internals.R:19-21
+    double v = ll_out[i];
+    if (!(v >= HB_FLOOR)) v = (v != v) ? v : HB_FLOOR;
+    if (!std::isfinite(v)) { set_msg(err, errlen, "Calculated log-likelihood is not finite!"); return HB_ERR_NONFINITE; }
+    ll_out[i] = v;
+  }
+  return HB_OK;
+}
+
+void hb_density_close(hb_density* s) {
+  if (!s) return;
+  if (s->ctx) s->vt->destroy(s->ctx);
+  cudaFree(s->xc); cudaFree(s->xr); cudaFree(s->ll); cudaFree(s->fx);
+  delete s;
+}
+
 }  // extern "C"

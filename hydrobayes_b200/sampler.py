@@ -606,6 +606,55 @@ def log_density(fun: str, x, lik: int, forcing=None, obs=None, glue_shape: float
     return ll, fx
 
 
+class DensitySession:
+    """log_density() with the plugin context and the device buffers kept between calls (``hb_density_open`` / ``_eval`` /
+    ``_close``): for callers that evaluate the target once per iteration -- ``pdf(xp)`` of rwm() / am() / am_sd()
+    (R/rwm.R:42) -- where the per-call setup of log_density() (covariance factor, forcing upload, allocations) would dominate."""
+
+    def __init__(self, fun: str, lik: int, d: int, max_n: int, forcing=None, obs=None, glue_shape: float = 0.0):
+        if not isinstance(fun, str):
+            raise A.HbError(A.HB_ERR_UNKNOWN_TARGET, "fun must be the NAME of a registered device target")
+        data = None if forcing is None else np.ascontiguousarray(np.asarray(forcing, np.float64))
+        o = None if obs is None else np.ascontiguousarray(np.asarray(obs, np.float64))
+        dims = (C.c_int64 * 1)(data.size if data is not None else 0)
+        self._s = C.c_void_p()
+        self.d, self.max_n = int(d), int(max_n)
+        err = C.create_string_buffer(256)
+        rc = A.lib().hb_density_open(fun.encode(), int(lik), _ptr(data), dims, 1 if data is not None else 0, _ptr(o),
+                                     o.size if o is not None else 0, float(glue_shape), self.d, self.max_n, C.byref(self._s),
+                                     err, 256)
+        if rc != A.HB_OK:
+            self._s = C.c_void_p()
+            raise A.HbError(rc, err.value.decode())
+
+    def __call__(self, x):
+        """(ll, fx) for the rows of x[n, d], n <= max_n"""
+        x = np.atleast_2d(np.asarray(x, np.float64))
+        n, d = x.shape
+        if d != self.d:
+            raise ValueError(f"x has {d} columns, the session was opened for d = {self.d}")
+        xf = np.asfortranarray(x)
+        ll = np.empty(n); fx = np.empty(n)
+        err = C.create_string_buffer(256)
+        rc = A.lib().hb_density_eval(self._s, xf.ctypes.data_as(_dp), n, _ptr(ll), _ptr(fx), err, 256)
+        if rc != A.HB_OK:
+            raise A.HbError(rc, err.value.decode())
+        return ll, fx
+
+    def close(self):
+        if getattr(self, "_s", None):
+            A.lib().hb_density_close(self._s)
+            self._s = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
 def HydroModel(forcing, param) -> np.ndarray:
     """HydroModel(forcing, param) (R/test_HydroModel.R:17-36) evaluated on the device; param may be a vector."""
     f = np.ascontiguousarray(np.asarray(forcing, np.float64))

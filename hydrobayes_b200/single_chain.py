@@ -4,7 +4,7 @@ for REGISTERED device targets.
 Each of them is one strictly sequential chain: x_i depends on x_{i-1}, so there is nothing to parallelise inside a chain.
 What a GPU can add is replicas: ``n_chains`` independent chains advance in lockstep, the proposals of an iteration are drawn
 on the host (``MASS::mvrnorm`` in the reference, numpy here: different generator, same law) and their target values come from
-ONE device evaluation per iteration through the log-density plugin (``hb_logdensity``: ``get(fun)`` + ``calc_ll``, floored at
+ONE device evaluation per iteration through a log-density session (``hb_density_open`` / ``hb_density_eval``: ``get(fun)`` + ``calc_ll``, floored at
 ``log(.Machine$double.xmin)`` like every likelihood in the package, R/internals.R:19).  The reference takes R closures
 ``prior`` / ``pdf``; those stay off the device path (like every R closure): ``fun`` names a device target and ``par_info``
 gives the initial sample and the prior, as for ``dream()``.
@@ -25,11 +25,13 @@ from . import _abi as A
 from .game import _prior_pdf
 
 
-def _post(fun, x, lik, par_info, target_kw):
-    from .sampler import log_density
-    if not isinstance(fun, str):
-        raise A.HbError(A.HB_ERR_UNKNOWN_TARGET, "fun must be the NAME of a registered device target")
-    ll, _ = log_density(fun, x, int(lik), **target_kw)
+def _open(fun, lik, d, n, target_kw):
+    from .sampler import DensitySession
+    return DensitySession(fun, int(lik), d, n, **target_kw)      # plugin context and device buffers live for the whole run
+
+
+def _post(sess, x, lik, par_info):
+    ll, _ = sess(x)
     return ll + _prior_pdf(x, par_info, lik)                     # log posterior density up to a constant (pdf() of the reference)
 
 
@@ -43,10 +45,15 @@ def _run(kind, fun, lik, par_info, t, d, n_chains, seed, target_kw):
         raise ValueError("t must be at least 2")
     rng = np.random.default_rng(seed)
     n = int(n_chains)
+    with _open(fun, lik, d, n, target_kw) as sess:
+        return _chains(kind, sess, lik, par_info, t, d, n, rng)
+
+
+def _chains(kind, sess, lik, par_info, t, d, n, rng):
     s_d = np.full(n, 2.38 ** 2 / d)                              # scaling factor of the covariance matrix
     x = np.full((t, d, n), np.nan); lpx = np.full((t, n), np.nan)
     x[0] = _initial(par_info, d, n, rng).T
-    lpx[0] = _post(fun, x[0].T, lik, par_info, target_kw)
+    lpx[0] = _post(sess, x[0].T, lik, par_info)
     L = np.sqrt(s_d)[:, None, None] * np.eye(d)[None]            # chol(C), C = s_d * diag(d)
     accept = np.ones(n)                                          # am_sd: "first sample accepted" (R/am_sd.R:38)
     S1 = x[0].T.copy(); S2 = np.einsum("ni,nj->nij", x[0].T, x[0].T)   # running sums for cov(x[1:(i-1), ])
@@ -64,7 +71,7 @@ def _run(kind, fun, lik, par_info, t, d, n_chains, seed, target_kw):
             L = np.sqrt(s_d + 1e-4)[:, None, None] * np.eye(d)[None]   # :53  C <- (s_d + 1e-4) * diag(d)
         z = rng.standard_normal((n, d))
         xp = x[i - 2].T + np.einsum("nij,nj->ni", L, z)          # x[i-1, ] + mvrnorm(mu = 0, Sigma = C)
-        lpp = _post(fun, xp, lik, par_info, target_kw)
+        lpp = _post(sess, xp, lik, par_info)
         acc = np.minimum(0.0, lpp - lpx[i - 2]) > np.log(rng.uniform(size=n))   # min(1, p_xp / p_x) > runif(1)
         x[i - 1] = np.where(acc[None, :], xp.T, x[i - 2])
         lpx[i - 1] = np.where(acc, lpp, lpx[i - 2])

@@ -275,6 +275,17 @@ int hb_rstat_array(const double* x, int64_t t, int32_t d, int64_t n, double* out
 int hb_logdensity(const char* name, int32_t lik, const double* data, const int64_t* dims, int ndims,
                   const double* obs, int64_t n_obs, double glue_shape, const double* x_colmajor, int64_t n,
                   int32_t d, double* ll_out, double* fx_out, char* err, int errlen);
+/* The same evaluation as a session: the plugin context (covariance factor, forcing, observations) and the device buffers
+ * are set up once and kept, hb_density_eval() evaluates up to max_n points per call.  For callers that evaluate the
+ * target once per iteration: pdf(xp) of rwm() / am() / am_sd() (R/rwm.R:42, R/am.R:51, R/am_sd.R:59) and of de_mc()
+ * (R/de_mc.R:56), get(fun) + calc_ll of game() (R/game.R:163-176).  Errors as hb_logdensity. */
+typedef struct hb_density hb_density;
+int hb_density_open(const char* name, int32_t lik, const double* data, const int64_t* dims, int ndims,
+                    const double* obs, int64_t n_obs, double glue_shape, int32_t d, int64_t max_n, hb_density** out,
+                    char* err, int errlen);
+int hb_density_eval(hb_density* s, const double* x_colmajor, int64_t n, double* ll_out, double* fx_out, char* err,
+                    int errlen);
+void hb_density_close(hb_density* s);
 /* HydroModel(forcing, param) full series for n parameters: out [n][T] row-major  (R/test_HydroModel.R:17-36) */
 int hb_hydromodel_series(const double* forcing, int64_t T, const double* param, int64_t n, double* out, char* err,
                          int errlen);

@@ -143,6 +143,41 @@ SEXP hbR_hydromodel_series(SEXP forcing, SEXP param) {   /* HydroModel(forcing, 
   return out;
 }
 
+/* ---- log-density sessions: pdf(x) of rwm() / am() / am_sd() / de_mc() and get(fun) + calc_ll of game() on the device ---- */
+static void hb_density_finalizer(SEXP ptr) {
+  hb_density* s = (hb_density*)R_ExternalPtrAddr(ptr);
+  if (s) { hb_density_close(s); R_ClearExternalPtr(ptr); }
+}
+/* .hb_density_open(fun, lik, data = the `...` of get(fun), obs, glue_shape, d, max_n) -> external pointer */
+SEXP hbR_density_open(SEXP fun, SEXP lik, SEXP data, SEXP obs, SEXP glue_shape, SEXP d, SEXP max_n) {
+  int64_t dims[1] = { isNull(data) ? 0 : (int64_t)XLENGTH(data) };
+  hb_density* s = NULL;
+  char err[256];
+  if (hb_density_open(CHAR(STRING_ELT(fun, 0)), asInteger(lik), isNull(data) ? NULL : REAL(data), dims, isNull(data) ? 0 : 1,
+                      isNull(obs) ? NULL : REAL(obs), isNull(obs) ? 0 : (int64_t)XLENGTH(obs),
+                      isNull(glue_shape) ? 0.0 : asReal(glue_shape), asInteger(d), (int64_t)asReal(max_n), &s, err,
+                      sizeof err) != HB_OK) error("%s", err);
+  SEXP ptr = PROTECT(R_MakeExternalPtr(s, R_NilValue, R_NilValue));
+  R_RegisterCFinalizerEx(ptr, hb_density_finalizer, TRUE);
+  UNPROTECT(1);
+  return ptr;
+}
+/* x: double matrix [n, d] (column-major, as R stores it) -> calc_ll(get(fun)(x[i, ], ...), lik, ...) for every row */
+SEXP hbR_density_eval(SEXP p, SEXP x) {
+  hb_density* s = (hb_density*)R_ExternalPtrAddr(p);
+  if (!s) error("log-density session was already closed");
+  if (TYPEOF(x) != REALSXP) error("hbR_density_eval: x must be a double matrix");
+  SEXP dim = getAttrib(x, R_DimSymbol);
+  if (isNull(dim) || length(dim) != 2) error("x must be a matrix [points, parameters]");
+  const int n = INTEGER(dim)[0];
+  SEXP out = PROTECT(allocVector(REALSXP, n));
+  char err[256];
+  if (hb_density_eval(s, REAL(x), (int64_t)n, REAL(out), NULL, err, sizeof err) != HB_OK) error("%s", err);
+  UNPROTECT(1);
+  return out;
+}
+SEXP hbR_density_close(SEXP p) { hb_density_finalizer(p); return R_NilValue; }
+
 #define HB_CALLDEF(name, n) { #name, (DL_FUNC)&name, n }
 static const R_CallMethodDef hb_call_entries[] = {
   HB_CALLDEF(hbR_create, 2), HB_CALLDEF(hbR_destroy, 1), HB_CALLDEF(hbR_set_bounds, 3), HB_CALLDEF(hbR_set_obs, 2),
@@ -150,7 +185,8 @@ static const R_CallMethodDef hb_call_entries[] = {
   HB_CALLDEF(hbR_target_registered, 1), HB_CALLDEF(hbR_set_initial, 2), HB_CALLDEF(hbR_run, 2), HB_CALLDEF(hbR_out_dims, 1),
   HB_CALLDEF(hbR_fetch_chain, 2), HB_CALLDEF(hbR_fetch_ar, 2), HB_CALLDEF(hbR_fetch_cr, 2), HB_CALLDEF(hbR_fetch_fx, 2),
   HB_CALLDEF(hbR_fetch_rstat, 2), HB_CALLDEF(hbR_fetch_outliers, 1), HB_CALLDEF(hbR_rstat_array, 1),
-  HB_CALLDEF(hbR_hydromodel_series, 2),
+  HB_CALLDEF(hbR_hydromodel_series, 2), HB_CALLDEF(hbR_density_open, 7), HB_CALLDEF(hbR_density_eval, 2),
+  HB_CALLDEF(hbR_density_close, 1),
   { NULL, NULL, 0 }
 };
 void R_init_HydroBayes(DllInfo* dll) {

@@ -126,6 +126,8 @@ SEXP mockR_dotCall(const char* name, int nargs, SEXP* a, char* err, int errlen) 
       case 2: res = ((f2)e->fun)(a[0], a[1]); break;
       case 3: res = ((f3)e->fun)(a[0], a[1], a[2]); break;
       case 4: res = ((f4)e->fun)(a[0], a[1], a[2], a[3]); break;
+      case 7: { typedef SEXP (*f7)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
+                res = ((f7)e->fun)(a[0], a[1], a[2], a[3], a[4], a[5], a[6]); break; }
       default: snprintf(err_msg, sizeof err_msg, "mock .Call: %d arguments not supported", nargs); longjmp(jb, 1);
     }
     if (protect_depth != depth0) { snprintf(err, (size_t)errlen, "stack imbalance in .Call(%s): %d", name, protect_depth - depth0); res = NULL; }

@@ -91,6 +91,8 @@ def test_no_device_becomes_an_r_error(R):
         R.call("hbR_rstat_array", x)
     with pytest.raises(rmock.RError, match="3-d array"):
         R.call("hbR_rstat_array", R.real(np.zeros(10)))
+    with pytest.raises(rmock.RError, match="(?i)cuda|device"):
+        R.call("hbR_density_open", R.string("t_distribution"), R.integer(2), R.nil, R.nil, R.nil, R.integer(3), R.real([8.0]))
     assert R.to_numpy(R.call("hbR_target_registered", R.string("t_distribution")))[0] == 1
     assert R.to_numpy(R.call("hbR_target_registered", R.string("my_r_closure")))[0] == 0
     # the wrapper name of the reference's example script resolves like the package's own targets (script_examples.R:495-501)
@@ -181,6 +183,35 @@ def test_dotcall_hydromodel_with_bounds_and_library_errors(R):
     R.call("hbR_destroy", h)
 
 
+@pytest.mark.gpu
+def test_dotcall_density_session(R):
+    """hbR_density_open / _eval / _close as r-package/R/hb_density.R calls them: R matrices in, the library's log-density out"""
+    from hydrobayes_b200 import log_density
+    rng = np.random.default_rng(4)
+    x = rng.normal(0, 2, (40, 5))
+    s = R.call("hbR_density_open", R.string("t_distribution"), R.integer(2), R.nil, R.nil, R.nil, R.integer(5), R.real([40.0]))
+    got = R.to_numpy(R.call("hbR_density_eval", s, R.real(x)))
+    assert np.array_equal(got, log_density("t_distribution", x, 2)[0])
+    one = R.to_numpy(R.call("hbR_density_eval", s, R.real(x[:1])))           # pdf(xp) of rwm(): one point, a 1 x d matrix
+    np.testing.assert_allclose(one, got[:1], rtol=1e-12)
+    with pytest.raises(rmock.RError, match="matrix"):
+        R.call("hbR_density_eval", s, R.real(x[0]))
+    with pytest.raises(rmock.RError, match="max_n"):
+        R.call("hbR_density_eval", s, R.real(np.zeros((41, 5))))
+    R.call("hbR_density_close", s)
+    with pytest.raises(rmock.RError, match="already closed"):
+        R.call("hbR_density_eval", s, R.real(x))
+    P, obs = H.hydro_data(T=150)
+    k = np.linspace(0.05, 1.5, 24)[:, None]
+    s = R.call("hbR_density_open", R.string("HydroModel"), R.integer(31), R.real(P), R.real(obs), R.real([50.0]), R.integer(1),
+               R.real([24.0]))
+    got = R.to_numpy(R.call("hbR_density_eval", s, R.real(k)))
+    assert np.array_equal(got, log_density("HydroModel", k, 31, forcing=P, obs=obs, glue_shape=50.0)[0])
+    R.call("hbR_density_close", s)
+    with pytest.raises(rmock.RError, match="unknown target"):
+        R.call("hbR_density_open", R.string("my_r_closure"), R.integer(2), R.nil, R.nil, R.nil, R.integer(3), R.real([8.0]))
+
+
 def test_r_sources_are_lexically_balanced():
     # no R parser here: at least every bracket of the R drivers closes (strings and comments skipped), the files end at
     # top level, and every function the drivers call is either base R, the reference's own (kept) internals, or defined here
@@ -205,12 +236,15 @@ def test_r_sources_are_lexically_balanced():
             i += 1
         assert not stack, f"{f}: unclosed {stack[-1][0]!r} opened at line {stack[-1][1]}"
     text = "\n".join(_r_sources().values())
-    defined = set(re.findall(r"^([.\w]+) <- function\(", text, flags=re.M))
-    assert {"dream", "dream_parallel", "R_stat", ".hb_drive"} <= defined
+    defined = set(re.findall(r"^\s*([.\w]+) <- function\(", text, flags=re.M))
+    assert {"dream", "dream_parallel", "R_stat", ".hb_drive", "hb_logdensity", "hb_pdf", ".hb_game_lpost", "metropolis_replicas",
+            "de_mc_device"} <= defined
     called = set(re.findall(r"(?<![\w.$])([.A-Za-z][\w.]*)\(", re.sub(r"#.*", "", text)))
     known = defined | {"function", "list", "c", "if", "for", "while", "stop", "match", "is.na", "is.null", "is.character", "as.integer",
                        "as.numeric", "as.matrix", "aperm", "nrow", "ncol", "storage.mode", "array", "matrix", "paste0", "dimnames", "colnames", "length", "floor", "max",
                        "seq_len", "invisible", "on.exit", "Sys.time", "sample.int", "txtProgressBar", "setTxtProgressBar", "close",
-                       "prior_sample"}      # prior_sample: the reference's own R/internals.R:26-47, kept
+                       "rep", "lapply", "vapply", "apply", "sqrt", "diag", "t", "chol", "cov", "ifelse", "rnorm", "runif", "pmin",
+                       "log", "exp", "numeric", "is.matrix", "match.arg", "return",
+                       "prior_sample", "prior_pdf"}   # the reference's own R/internals.R:26-69, kept
     unknown = {c for c in called if c not in known and not c.startswith(".Call")}
     assert not unknown, f"R drivers call functions that are neither base R nor defined in the package: {sorted(unknown)}"

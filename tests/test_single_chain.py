@@ -7,9 +7,27 @@ import hydrobayes_b200.single_chain as SC
 from hydrobayes_b200 import am, am_sd, rwm
 
 
-def _std_normal_logpdf(fun, x, lik, forcing=None, obs=None, glue_shape=0.0):
-    x = np.atleast_2d(x)
-    return -0.5 * (x ** 2).sum(axis=1) - 0.5 * x.shape[1] * np.log(2 * np.pi), None
+def _stand_in_session(logpdf):
+    """a DensitySession that evaluates `logpdf` on the host: same constructor, call and context-manager protocol"""
+    class Session:
+        def __init__(self, fun, lik, d, max_n, forcing=None, obs=None, glue_shape=0.0):
+            self.d, self.max_n = d, max_n
+
+        def __call__(self, x):
+            x = np.atleast_2d(x)
+            assert x.shape[1] == self.d and x.shape[0] <= self.max_n
+            return logpdf(x), None
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            pass
+    return Session
+
+
+def _std_normal_logpdf(x):
+    return -0.5 * (x ** 2).sum(axis=1) - 0.5 * x.shape[1] * np.log(2 * np.pi)
 
 
 @pytest.mark.parametrize("sampler", [rwm, am, am_sd])
@@ -17,7 +35,7 @@ def test_single_chain_samplers_host_logic(monkeypatch, sampler):
     # the loop of the reference with the device evaluation replaced by a standard normal: shapes of the return list, the
     # first row is the initial sample, rejected iterations repeat the previous row, moments of the stationary law
     import hydrobayes_b200.sampler as S
-    monkeypatch.setattr(S, "log_density", _std_normal_logpdf)
+    monkeypatch.setattr(S, "DensitySession", _stand_in_session(_std_normal_logpdf))
     d, t, n = 3, 3000, 16
     x0 = np.linspace(-1, 1, n * d).reshape(n, d)
     res = sampler("stand_in", lik=2, par_info=dict(initial="user", val_ini=x0, prior="flat"), t=t, d=d, n_chains=n, seed=5)
@@ -35,7 +53,7 @@ def test_single_chain_samplers_host_logic(monkeypatch, sampler):
 
 def test_am_sd_scales_towards_the_target_acceptance_rate(monkeypatch):
     import hydrobayes_b200.sampler as S
-    monkeypatch.setattr(S, "log_density", lambda fun, x, lik, **kw: (-0.5 * (np.atleast_2d(x) ** 2).sum(axis=1) / 1e-4, None))
+    monkeypatch.setattr(S, "DensitySession", _stand_in_session(lambda x: -0.5 * (x ** 2).sum(axis=1) / 1e-4))
     res = am_sd("narrow", lik=2, par_info=dict(initial="user", val_ini=np.zeros((8, 2)), prior="flat"), t=4000, d=2, n_chains=8, seed=2)
     early = np.any(res["chain"][1:200] != res["chain"][:199], axis=1).mean()
     late = np.any(res["chain"][3000:] != res["chain"][2999:-1], axis=1).mean()
@@ -59,3 +77,36 @@ def test_single_chain_samplers_on_the_device_target(sampler):
     for k in range(d):
         assert abs(v[k].mean() / (60 / 58 * (k + 1)) - 1) < 0.25
     assert np.all(np.isfinite(res["density"])) and np.all(res["density"] > 0)
+
+
+@pytest.mark.gpu
+def test_density_session_equals_the_one_shot_evaluation():
+    """hb_density_open / _eval / _close against hb_logdensity: same plugin, same kernels -> array_equal, call after call"""
+    import helpers as H
+    from hydrobayes_b200 import HbError, log_density
+    from hydrobayes_b200.sampler import DensitySession
+    rng = np.random.default_rng(11)
+    for d in (1, 2, 100):
+        x = rng.normal(0, 3, (257, d))
+        want, want_fx = log_density("t_distribution", x, 2)
+        with DensitySession("t_distribution", 2, d, 257) as s:
+            for n in (257, 1, 33, 257):                              # buffers are reused: smaller batches after a full one
+                ll, fx = s(x[:n])
+                if n == 257:
+                    assert np.array_equal(ll, want) and np.array_equal(fx, want_fx)
+                else:
+                    np.testing.assert_allclose(ll, want[:n], rtol=1e-12)
+            with pytest.raises(HbError):
+                s(np.zeros((258, d)))                                # more points than the session was opened for
+    P, obs = H.hydro_data(T=200)
+    k = np.linspace(0.05, 1.5, 64)[:, None]
+    want, _ = log_density("HydroModel", k, 31, forcing=P, obs=obs, glue_shape=50.0)
+    with DensitySession("HydroModel", 31, 1, 64, forcing=P, obs=obs, glue_shape=50.0) as s:
+        assert np.array_equal(s(k)[0], want)
+        np.testing.assert_allclose(s(k[:5])[0], want[:5], rtol=1e-12)
+        assert np.array_equal(s(k)[0], want)
+    xm = np.linspace(-12, 14, 50)[:, None]
+    with DensitySession("mixture", 1, 1, 50) as s:
+        assert np.array_equal(s(xm)[0], log_density("mixture", xm, 1)[0])
+    with pytest.raises(HbError):
+        DensitySession("my_r_closure", 2, 3, 8)
