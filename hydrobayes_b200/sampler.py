@@ -618,9 +618,10 @@ class DensitySession:
         o = None if obs is None else np.ascontiguousarray(np.asarray(obs, np.float64))
         dims = (C.c_int64 * 1)(data.size if data is not None else 0)
         self._s = C.c_void_p()
+        self._L = A.lib()
         self.d, self.max_n = int(d), int(max_n)
         err = C.create_string_buffer(256)
-        rc = A.lib().hb_density_open(fun.encode(), int(lik), _ptr(data), dims, 1 if data is not None else 0, _ptr(o),
+        rc = self._L.hb_density_open(fun.encode(), int(lik), _ptr(data), dims, 1 if data is not None else 0, _ptr(o),
                                      o.size if o is not None else 0, float(glue_shape), self.d, self.max_n, C.byref(self._s),
                                      err, 256)
         if rc != A.HB_OK:
@@ -636,17 +637,21 @@ class DensitySession:
         xf = np.asfortranarray(x)
         ll = np.empty(n); fx = np.empty(n)
         err = C.create_string_buffer(256)
-        rc = A.lib().hb_density_eval(self._s, xf.ctypes.data_as(_dp), n, _ptr(ll), _ptr(fx), err, 256)
+        rc = self._L.hb_density_eval(self._s, xf.ctypes.data_as(_dp), n, _ptr(ll), _ptr(fx), err, 256)
         if rc != A.HB_OK:
             raise A.HbError(rc, err.value.decode())
         return ll, fx
 
     def close(self):
         if getattr(self, "_s", None):
-            A.lib().hb_density_close(self._s)
+            self._L.hb_density_close(self._s)
             self._s = C.c_void_p()
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def __enter__(self):
         return self
