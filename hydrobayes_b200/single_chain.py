@@ -54,7 +54,7 @@ def _chains(kind, sess, lik, par_info, t, d, n, rng):
     x = np.full((t, d, n), np.nan); lpx = np.full((t, n), np.nan)
     x[0] = _initial(par_info, d, n, rng).T
     lpx[0] = _post(sess, x[0].T, lik, par_info)
-    L = np.sqrt(s_d)[:, None, None] * np.eye(d)[None]            # chol(C), C = s_d * diag(d)
+    sig, L = np.sqrt(s_d), None                                  # chol(C) of C = s_d * diag(d) is sig * I: kept as a scale
     accept = np.ones(n)                                          # am_sd: "first sample accepted" (R/am_sd.R:38)
     S1 = x[0].T.copy(); S2 = np.einsum("ni,nj->nij", x[0].T, x[0].T)   # running sums for cov(x[1:(i-1), ])
     for i in range(2, t + 1):                                    # R's i = 2..t
@@ -68,9 +68,10 @@ def _chains(kind, sess, lik, par_info, t, d, n, rng):
                 AR = 100.0 * accept / (i - 1)
                 s_d = np.where(AR < 20, 0.8 * s_d, s_d)
                 s_d = np.where(AR > 30, 1.2 * s_d, s_d)
-            L = np.sqrt(s_d + 1e-4)[:, None, None] * np.eye(d)[None]   # :53  C <- (s_d + 1e-4) * diag(d)
+            sig = np.sqrt(s_d + 1e-4)                            # :53  C <- (s_d + 1e-4) * diag(d)
         z = rng.standard_normal((n, d))
-        xp = x[i - 2].T + np.einsum("nij,nj->ni", L, z)          # x[i-1, ] + mvrnorm(mu = 0, Sigma = C)
+        jump = sig[:, None] * z if L is None else np.einsum("nij,nj->ni", L, z)
+        xp = x[i - 2].T + jump                                   # x[i-1, ] + mvrnorm(mu = 0, Sigma = C)
         lpp = _post(sess, xp, lik, par_info)
         acc = np.minimum(0.0, lpp - lpx[i - 2]) > np.log(rng.uniform(size=n))   # min(1, p_xp / p_x) > runif(1)
         x[i - 1] = np.where(acc[None, :], xp.T, x[i - 2])
