@@ -80,7 +80,13 @@ def test_plugin_builds_against_the_public_header_only():
 @pytest.fixture(scope="module")
 def gauss_plugin():
     A.lib()                                                     # the library first: the plugin resolves hb_register_target in it
-    P = C.CDLL(_build_plugin())
+    try:
+        so = _build_plugin()
+    except (OSError, subprocess.CalledProcessError) as e:       # no nvcc on this machine: use the library build()'s copy
+        if not os.path.exists(PLUGIN_SO):
+            pytest.skip(f"third-party target not built and cannot be built here: {e}")
+        so = PLUGIN_SO
+    P = C.CDLL(so)
     P.hb_gauss_plugin_register.restype = C.c_int
     rc = P.hb_gauss_plugin_register()
     assert rc == A.HB_OK or A.lib().hb_target_registered(b"gauss_shifted") == 1
