@@ -606,6 +606,22 @@ def log_density(fun: str, x, lik: int, forcing=None, obs=None, glue_shape: float
     return ll, fx
 
 
+def mixture(x) -> np.ndarray:
+    """mixture(x) = 1/6 dnorm(x, -8, 1) + 5/6 dnorm(x, 10, 1), the exported test target of R/test_mixture.R:16, evaluated on the
+    device for every element of x (a DENSITY, as in the reference; `lik = 1` takes its log inside the samplers)."""
+    a = np.asarray(x, np.float64)
+    _, fx = log_density("mixture", a.reshape(-1, 1), 1)
+    return fx.reshape(a.shape) if a.ndim else float(fx[0])
+
+
+def t_distribution(x):
+    """t_distribution(x), the exported d-variate Student target of R/test_t_distribution.R:19-46 (60 degrees of freedom,
+    C[i, j] = 0.5 sqrt(i j), C[i, i] = i): the LOG-density of one point x[d] or of every row of x[n, d], on the device."""
+    a = np.asarray(x, np.float64)
+    _, fx = log_density("t_distribution", np.atleast_2d(a), 2)
+    return fx if a.ndim > 1 else float(fx[0])
+
+
 class DensitySession:
     """log_density() with the plugin context and the device buffers kept between calls (``hb_density_open`` / ``_eval`` /
     ``_close``): for callers that evaluate the target once per iteration -- ``pdf(xp)`` of rwm() / am() / am_sd()

@@ -140,3 +140,23 @@ int main(void) {
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     assert r.stdout.strip() == "targets: 1 1 1 0"
+
+
+def test_exported_target_callables_shapes(monkeypatch):
+    # mixture(x) / t_distribution(x) of the reference's NAMESPACE (R/test_mixture.R:16, R/test_t_distribution.R:19-46): the
+    # argument handling of the Python callables, with the device evaluation replaced by numpy
+    import hydrobayes_b200 as hb
+    import hydrobayes_b200.sampler as S
+    calls = []
+
+    def fake(fun, x, lik, **kw):
+        x = np.atleast_2d(np.asarray(x, float)); calls.append((fun, x.shape, lik))
+        v = x.sum(axis=1)
+        return v - 1.0, v
+    monkeypatch.setattr(S, "log_density", fake)
+    assert hb.mixture(2.0) == 2.0 and calls[-1] == ("mixture", (1, 1), 1)                     # a scalar: one point
+    m = hb.mixture(np.arange(6.0).reshape(2, 3))                                              # elementwise, shape kept
+    assert m.shape == (2, 3) and np.array_equal(m, np.arange(6.0).reshape(2, 3)) and calls[-1] == ("mixture", (6, 1), 1)
+    assert hb.t_distribution([1.0, 2.0, 3.0]) == 6.0 and calls[-1] == ("t_distribution", (1, 3), 2)   # a vector: ONE point of dimension d
+    t = hb.t_distribution(np.ones((4, 5)))                                                    # a matrix: one point per row
+    assert t.shape == (4,) and np.all(t == 5.0) and calls[-1] == ("t_distribution", (4, 5), 2)

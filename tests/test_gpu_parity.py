@@ -675,3 +675,13 @@ def test_c2_size_properties(hb):
     # stored log-density equals a fresh evaluation of the stored state
     ll, _ = hb.log_density("t_distribution", ch[-1, :d, :].T, lik=2)
     np.testing.assert_allclose(ch[-1, d + 1, :], ll, rtol=1e-12)
+
+
+def test_exported_target_callables(hb):
+    # mixture() / t_distribution() as the reference exports them: thin callables over the device plugins
+    x = np.linspace(-12, 15, 28)
+    assert np.array_equal(hb.mixture(x), hb.log_density("mixture", x[:, None], lik=1)[1])
+    assert hb.mixture(10.0) == hb.mixture(np.array([10.0]))[0] and 0.3 < hb.mixture(10.0) < 0.34     # 5/6 dnorm(0) = 0.3325
+    p = np.random.default_rng(3).normal(0, 2, (9, 100))
+    assert np.array_equal(hb.t_distribution(p), hb.log_density("t_distribution", p, lik=2)[1])
+    assert hb.t_distribution(p[0]) == hb.t_distribution(p[:1])[0]
