@@ -248,3 +248,34 @@ def test_multi_try_oracle_moments(oracle):
         v = r["chain"][500:, :3, :].var(axis=(0, 2))
         np.testing.assert_allclose(v, 60.0 / 58.0 * np.arange(1, 4), rtol=0.15)
     assert acc[4] > 1.3 * acc[1]
+
+
+def test_third_party_arithmetic_against_multiprecision(oracle):
+    """dnorm (R nmath, split-exponent branch for |z| >= 5) and mvtnorm::dmvt are restated from recollection of their published
+    sources; this pins the restatement to the EXACT values of the formulas, evaluated with 50 digits."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 50
+    xs = np.concatenate([np.linspace(-30, 32, 311), np.random.default_rng(0).uniform(-30, 32, 200)])
+    for x in xs:
+        X = mp.mpf(float(x))
+        ref = mp.mpf(1) / 6 * mp.npdf(X, -8, 1) + mp.mpf(5) / 6 * mp.npdf(X, 10, 1)          # R/test_mixture.R:16
+        if ref > mp.mpf(2.3e-308):
+            assert abs((mp.mpf(oracle.mixture(float(x))) - ref) / ref) < 4e-15, x
+
+    def dmvt_log(x):                                                                          # R/test_t_distribution.R:19-46
+        d = len(x); df = mp.mpf(60)
+        C = mp.matrix(d, d)
+        for a in range(d):
+            for b in range(d):
+                C[a, b] = (mp.mpf(1) if a == b else mp.mpf("0.5")) * mp.sqrt(mp.mpf(a + 1) * mp.mpf(b + 1))
+        xv = mp.matrix([mp.mpf(float(v)) for v in x])
+        q = (xv.T * mp.lu_solve(C, xv))[0]
+        return (mp.loggamma((df + d) / 2) - mp.loggamma(df / 2) - mp.mpf(d) / 2 * mp.log(df * mp.pi) - mp.log(mp.det(C)) / 2
+                - (df + d) / 2 * mp.log(1 + q / df))
+    rng = np.random.default_rng(1)
+    for d in (1, 2, 5, 17, 40):
+        x = rng.uniform(-5, 15, (2, d))
+        got = oracle.tdist_logpdf(x)
+        for r in range(2):
+            ref = dmvt_log(x[r])
+            assert abs((mp.mpf(float(got[r])) - ref) / ref) < 2e-14, (d, r)
