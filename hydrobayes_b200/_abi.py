@@ -177,6 +177,7 @@ def lib() -> C.CDLL:
         "hb_density_open": ([cp, C.c_int32, _dp, _i64p, C.c_int, _dp, C.c_int64, C.c_double, C.c_int32, C.c_int64,
                              C.POINTER(C.c_void_p), C.c_char_p, C.c_int], C.c_int),
         "hb_density_eval": ([C.c_void_p, _dp, C.c_int64, _dp, _dp, C.c_char_p, C.c_int], C.c_int),
+        "hb_density_dim": ([C.c_void_p], C.c_int32),
         "hb_density_close": ([C.c_void_p], None),
         "hb_hydromodel_series": ([_dp, C.c_int64, _dp, C.c_int64, _dp, C.c_char_p, C.c_int], C.c_int),
         "hb_fp64_peaks": ([_dp, _dp], C.c_int),
@@ -196,5 +197,5 @@ EXPORTED_SYMBOLS = [
     "hb_set_initial", "hb_set_initial_rows", "hb_set_tape", "hb_comm_unique_id", "hb_comm_init", "hb_peer_export", "hb_peer_import", "hb_run", "hb_group_attach", "hb_group_run", "hb_sync", "hb_out_dims",
     "hb_fetch_chain", "hb_fetch_chain_rows", "hb_fetch_fx", "hb_fetch_ar", "hb_fetch_cr", "hb_fetch_rstat",
     "hb_fetch_state", "hb_fetch_accept", "hb_fetch_outliers", "hb_rstat", "hb_rstat_runs", "hb_wait_idle", "hb_host_prefault", "hb_host_register", "hb_host_unregister", "hb_test_force_wide", "hb_ind_out", "hb_get_timing", "hb_profile",
-    "hb_get_kernel_ms", "hb_rstat_array", "hb_logdensity", "hb_density_open", "hb_density_eval", "hb_density_close", "hb_hydromodel_series", "hb_fp64_peaks", "hb_divcheck",
+    "hb_get_kernel_ms", "hb_rstat_array", "hb_logdensity", "hb_density_open", "hb_density_eval", "hb_density_dim", "hb_density_close", "hb_hydromodel_series", "hb_fp64_peaks", "hb_divcheck",
 ]

@@ -2158,6 +2158,8 @@ int hb_density_eval(hb_density* s, const double* x, int64_t n, double* ll_out, d
   return HB_OK;
 }
 
+int32_t hb_density_dim(const hb_density* s) { return s ? s->d : 0; }
+
 void hb_density_close(hb_density* s) {
   if (!s) return;
   if (s->ctx) s->vt->destroy(s->ctx);

@@ -285,6 +285,7 @@ int hb_density_open(const char* name, int32_t lik, const double* data, const int
                     char* err, int errlen);
 int hb_density_eval(hb_density* s, const double* x_colmajor, int64_t n, double* ll_out, double* fx_out, char* err,
                     int errlen);
+int32_t hb_density_dim(const hb_density* s);   /* d the session was opened for (0 for NULL): callers check ncol(x) against it */
 void hb_density_close(hb_density* s);
 /* HydroModel(forcing, param) full series for n parameters: out [n][T] row-major  (R/test_HydroModel.R:17-36) */
 int hb_hydromodel_series(const double* forcing, int64_t T, const double* param, int64_t n, double* out, char* err,

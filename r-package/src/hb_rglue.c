@@ -170,6 +170,7 @@ SEXP hbR_density_eval(SEXP p, SEXP x) {
   SEXP dim = getAttrib(x, R_DimSymbol);
   if (isNull(dim) || length(dim) != 2) error("x must be a matrix [points, parameters]");
   const int n = INTEGER(dim)[0];
+  if (INTEGER(dim)[1] != hb_density_dim(s)) error("x has %d columns, the session was opened for d = %d", INTEGER(dim)[1], (int)hb_density_dim(s));
   SEXP out = PROTECT(allocVector(REALSXP, n));
   char err[256];
   if (hb_density_eval(s, REAL(x), (int64_t)n, REAL(out), NULL, err, sizeof err) != HB_OK) error("%s", err);

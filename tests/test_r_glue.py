@@ -198,6 +198,8 @@ def test_dotcall_density_session(R):
         R.call("hbR_density_eval", s, R.real(x[0]))
     with pytest.raises(rmock.RError, match="max_n"):
         R.call("hbR_density_eval", s, R.real(np.zeros((41, 5))))
+    with pytest.raises(rmock.RError, match="opened for d = 5"):
+        R.call("hbR_density_eval", s, R.real(np.zeros((4, 3))))              # fewer columns than d: refused, not read past the end
     R.call("hbR_density_close", s)
     with pytest.raises(rmock.RError, match="already closed"):
         R.call("hbR_density_eval", s, R.real(x))
